@@ -1,0 +1,136 @@
+/* pnp_b200.h -- C ABI of libpnp_b200.so: the sm_100a kernels behind the PnP iteration hot path.
+ *
+ * The reference (vmonardo/pnp-svrg) is pure Python and has no FFI layer; its boundary is the
+ * duck-typed protocol  problem.{grad_full,grad_stoch,select_mb,PSNR} / denoiser.denoise  that
+ * algorithms/pnp_*.py call.  Each entry point below names the reference line(s) it replaces.
+ * The Python host side (pnp_svrg_b200/) binds these with ctypes; INTEGRATION.md shows the stub
+ * a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless its name ends in _host;
+ *   - images are float32 and TRANSPOSED: [batch][W lines][H samples], line c = original column c;
+ *   - `stream` is a cudaStream_t passed as void*; nothing here touches the default stream
+ *     unless the caller passes it, nothing synchronises unless stated;
+ *   - every function returns 0 on success or a negative pnp_status; pnp_last_error() gives text;
+ *   - H and W must be powers of two in [32, 4096].
+ */
+#ifndef PNP_B200_H
+#define PNP_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+    PNP_OK = 0,
+    PNP_ERR_ARG = -1,       /* bad argument (size not supported, null pointer, ...) */
+    PNP_ERR_CUDA = -2,      /* a CUDA runtime call failed */
+    PNP_ERR_NOT_INIT = -3   /* pnp_init() has not been called on this device */
+} pnp_status;
+
+/* Library / device set-up: uploads the twiddle table and raises the dynamic shared-memory
+ * limits of the FFT kernels on the CURRENT device.  Idempotent. */
+int pnp_init(void);
+const char* pnp_last_error(void);
+int pnp_version(void);
+
+/* ---- CSMRI data-fidelity gradient, fused with the variance-reduced update -----------------
+ * Replaces CSMRI.grad_full (problems/CSMRI.py:76-81) and CSMRI.grad_stoch (:83-89), and the
+ * update lines  z -= eta*lr_decay**i * v  of algorithms/pnp_gd.py:32-35, pnp_sgd.py:32-36,
+ * pnp_svrg.py:53-57, pnp_sarah.py:72-75.
+ *
+ *   g   = Re(ifft2(sel o fft2(a - b) - Ysel))             (b, Y* optional)
+ *   gs  = g * gscale
+ *   v   = gs + vadd                                        (vadd optional)
+ *   z_out = z_in - step * v                                (optional)
+ * g_out / v_out receive gs / v when non-null. */
+typedef struct {
+    int H, W, batch;
+    const float* a;               /* [batch][W][H] */
+    const float* b;               /* optional: transform a - b (SVRG/SARAH difference, Y cancels) */
+    float* S;                     /* scratch, batch*W*H floats (packed half spectrum, complex64) */
+    const unsigned char* bits;    /* selection bits [batch][W][H/2], see pnp_csmri_sel_* */
+    const float* Y1;              /* optional complex64 [batch][W][H/2]: (mask o Y)[kyp][kx]        */
+    const float* Y2;              /*                                     conj (mask o Y)[-kyp][-kx]  */
+    const float* Y1n;             /* optional complex64 [batch][W]: Nyquist row (mask o Y)[H/2][kx] */
+    const float* Y2n;             /*                                conj (mask o Y)[H/2][-kx]       */
+    float gscale;
+    const float* gscale_ptr;      /* optional [batch], replaces gscale */
+    float step;
+    const float* step_ptr;        /* optional [batch], replaces step */
+    float* g_out;
+    const float* vadd;
+    float* v_out;
+    const float* z_in;
+    float* z_out;
+} pnp_csmri_grad_args;
+int pnp_csmri_grad(const pnp_csmri_grad_args* args, void* stream);
+
+/* Selection bits from explicit k-space indices (k = ky*W + kx, the flat index into the
+ * reference's (H, W) mask / minibatch arrays).  Replaces the dense 0/1 (H, W) minibatch array of
+ * CSMRI.select_mb (problems/CSMRI.py:66-74) and the mask itself (:45).
+ * idx: [batch][n_sets][count]; the set used is *cursor (0 when cursor is null).
+ * `bits` is cleared first when clear != 0. */
+int pnp_csmri_sel_from_indices(unsigned char* bits, int H, int W, int batch, const int* idx, int count,
+                               long long idx_img_stride, const int* cursor, int clear, void* stream);
+
+/* Device-drawn minibatch: `count` distinct entries of support[img][0..m0[img]) chosen by a keyed
+ * Feistel permutation (seed, *counter).  Same role as np.random.choice(mask_locs, size,
+ * replace=False) at problems/CSMRI.py:72 but not the same stream of numbers.
+ * idx_out (optional, [batch][count]) receives the chosen k indices. */
+int pnp_csmri_sel_sample(unsigned char* bits, int H, int W, int batch, const int* support, const int* m0,
+                         long long support_img_stride, int count, unsigned seed, const int* counter,
+                         int* idx_out, int clear, void* stream);
+
+/* ---- prox step ------------------------------------------------------------------------------
+ * estimate_sigma(z0, multichannel=True, average_sigmas=True)  (algorithms/pnp_svrg.py:71 and
+ * pnp_gd.py:49, pnp_sgd.py:50, pnp_saga.py:64, pnp_sarah.py:47,89).  ADDS the sum over columns of
+ * the per-column estimates to sig_log[slot*batch + img] (double); the mean is that / W. */
+int pnp_estimate_sigma(const float* z, int H, int W, int batch, double* sig_log, const int* slot,
+                       void* stream);
+
+/* TVDenoiser.denoise (denoisers/TV.py:21-26) = skimage denoise_wavelet(BayesShrink, db1, soft,
+ * multichannel=True): per column multi-level Haar shrinkage.  sigma_est comes from
+ * sig_log[slot*batch+img]/W when sig_log is non-null, else from sigma_est.  If it is > 0 the
+ * threshold uses sigma_est*sigma_modifier, otherwise fallback_sigma (denoise_strength*decay**t).
+ * When xrec and mse_log are non-null, sum((out - xrec)^2) is ADDED to mse_log[slot*batch+img]
+ * (Problem.PSNR, problems/problem.py:33-35). */
+int pnp_wavelet_denoise(const float* z_in, float* z_out, int H, int W, int batch, const double* sig_log,
+                        float sigma_est, float sigma_modifier, float fallback_sigma, const float* xrec,
+                        double* mse_log, const int* slot, void* stream);
+
+/* Problem.PSNR (problems/problem.py:33-35): ADDS sum((z - xrec)^2) to out[slot*batch+img]. */
+int pnp_sq_err(const float* z, const float* xrec, long long n, int batch, double* out, const int* slot,
+               void* stream);
+
+/* ---- variance-reduction bookkeeping ---------------------------------------------------------
+ * z_out = z_in - step * v   (algorithms/pnp_svrg.py:54-57 as committed: v = mu) */
+int pnp_axpy(const float* z_in, const float* v, float* z_out, long long n, int batch, float step,
+             const float* step_ptr, void* stream);
+/* algorithms/pnp_saga.py:28 -- every table row starts as the same gradient */
+int pnp_saga_init(const float* g0, float* table, float* tsum, long long n, int batch, int hist, void* stream);
+/* algorithms/pnp_saga.py:45-50,72; g_prev is overwritten with g_new (prev_stoch = table[slot]) */
+int pnp_saga_update(const float* g_new, float* g_prev, float* table, float* tsum, float* z,
+                    long long n, int batch, int hist, const int* slot_idx, long long slot_img_stride,
+                    const int* cursor, float step, const float* step_ptr, void* stream);
+/* counters[0..n) += 1 on the device (log slot / minibatch cursor for CUDA-graph replay) */
+int pnp_advance(int* counters, int n, void* stream);
+
+/* counters[0..n) += 1 and *x *= factor (step decay  eta*lr_decay**i  kept on the device) */
+int pnp_advance_scale(int* counters, int n, float* x, float factor, void* stream);
+/* dst[0..n) = src[0..n)  (w = copy(z), algorithms/pnp_svrg.py:35; capturable device copy) */
+int pnp_copy_f32(float* dst, const float* src, long long n, void* stream);
+
+/* ---- CUDA-graph helpers ---------------------------------------------------------------------
+ * One inner iteration is launch-bound at 256x256 (about 2 MB of traffic); the host side captures
+ * the iteration's launches once and replays the executable graph.  begin/end bracket the
+ * launches on `stream`; `exec` is an opaque cudaGraphExec_t. */
+int pnp_graph_begin(void* stream);
+int pnp_graph_end(void* stream, void** exec_out);
+int pnp_graph_launch(void* exec, void* stream);
+int pnp_graph_destroy(void* exec);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PNP_B200_H */

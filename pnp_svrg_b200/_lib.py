@@ -1,0 +1,101 @@
+"""ctypes binding of libpnp_b200.so (C ABI in include/pnp_b200.h).
+
+There is NO fallback: if the shared library is missing or cannot be loaded the import of any
+compute path raises.  Build it with ``python -c 'import __graft_entry__ as g; g.build()'`` or
+``python -m pnp_svrg_b200.build``.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'lib', 'libpnp_b200.so')
+
+c_float_p = C.c_void_p      # all device pointers travel as integers
+c_int_p = C.c_void_p
+
+
+class CsmriGradArgs(C.Structure):
+    """mirror of pnp_csmri_grad_args"""
+    _fields_ = [
+        ('H', C.c_int), ('W', C.c_int), ('batch', C.c_int),
+        ('a', C.c_void_p), ('b', C.c_void_p), ('S', C.c_void_p), ('bits', C.c_void_p),
+        ('Y1', C.c_void_p), ('Y2', C.c_void_p), ('Y1n', C.c_void_p), ('Y2n', C.c_void_p),
+        ('gscale', C.c_float), ('gscale_ptr', C.c_void_p),
+        ('step', C.c_float), ('step_ptr', C.c_void_p),
+        ('g_out', C.c_void_p), ('vadd', C.c_void_p), ('v_out', C.c_void_p),
+        ('z_in', C.c_void_p), ('z_out', C.c_void_p),
+    ]
+
+
+# name -> (restype, argtypes); every symbol declared in include/pnp_b200.h
+PROTOTYPES = {
+    'pnp_init': (C.c_int, []),
+    'pnp_last_error': (C.c_char_p, []),
+    'pnp_version': (C.c_int, []),
+    'pnp_csmri_grad': (C.c_int, [C.POINTER(CsmriGradArgs), C.c_void_p]),
+    'pnp_csmri_sel_from_indices': (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int,
+                                             C.c_longlong, C.c_void_p, C.c_int, C.c_void_p]),
+    'pnp_csmri_sel_sample': (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                       C.c_longlong, C.c_int, C.c_uint, C.c_void_p, C.c_void_p, C.c_int,
+                                       C.c_void_p]),
+    'pnp_estimate_sigma': (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    'pnp_wavelet_denoise': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_float,
+                                      C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    'pnp_sq_err': (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    'pnp_axpy': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_float, C.c_void_p,
+                           C.c_void_p]),
+    'pnp_saga_init': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_int, C.c_void_p]),
+    'pnp_saga_update': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong,
+                                  C.c_int, C.c_int, C.c_void_p, C.c_longlong, C.c_void_p, C.c_float, C.c_void_p,
+                                  C.c_void_p]),
+    'pnp_advance': (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
+    'pnp_advance_scale': (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_float, C.c_void_p]),
+    'pnp_copy_f32': (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p]),
+    'pnp_graph_begin': (C.c_int, [C.c_void_p]),
+    'pnp_graph_end': (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
+    'pnp_graph_launch': (C.c_int, [C.c_void_p, C.c_void_p]),
+    'pnp_graph_destroy': (C.c_int, [C.c_void_p]),
+}
+
+_lib = None
+_inited_devices = set()
+
+
+class PnpError(RuntimeError):
+    pass
+
+
+def load():
+    """Load the shared library (once) and attach the prototypes."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise PnpError('%s not found: the CUDA extension is not built and there is no CPU fallback '
+                       '(run `python -m pnp_svrg_b200.build`)' % LIB_PATH)
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in PROTOTYPES.items():
+        fn = getattr(lib, name)        # AttributeError here = header / library mismatch
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc):
+    if rc != 0:
+        raise PnpError('libpnp_b200: status %d: %s' % (rc, load().pnp_last_error().decode()))
+
+
+def init_device():
+    """pnp_init() on torch's current CUDA device (twiddle table, shared-memory limits)."""
+    import torch
+    if not torch.cuda.is_available():
+        raise PnpError('no CUDA device: pnp_svrg_b200 has no CPU path')
+    dev = torch.cuda.current_device()
+    if dev not in _inited_devices:
+        torch.cuda.init()
+        torch.zeros(1, device='cuda')          # make sure the primary context exists and is current
+        check(load().pnp_init())
+        _inited_devices.add(dev)
+    return dev

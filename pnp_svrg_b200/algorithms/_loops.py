@@ -1,0 +1,489 @@
+"""The five PnP loops on the device engine.  Control flow, logging and stop rules follow the
+reference line by line (cited per function); the arithmetic is the fused CUDA path.
+
+Additive keyword arguments (all optional, defaults reproduce the reference behaviour):
+  max_iters   stop after this many prox (denoiser) calls, in addition to the wall-clock ``tt``
+  vr_mode     pnp_svrg only: 'as_committed' (v = mu, algorithms/pnp_svrg.py:54) or
+              'paper' (v = (g_B(z) - g_B(w))/B + mu, the commented line :53)
+  mb_source   'legacy' np.random global RNG in the reference's call order (default),
+              'host' np.random.Generator(mb_seed), 'device' GPU sampler, 'stream' use mb_stream
+  fast        replay a captured CUDA graph per inner iteration and defer the PSNR read-back to the
+              end / every ``sync_every`` iterations (stop rules are then applied at those points)
+"""
+import time
+
+import numpy as np
+import torch
+
+from .. import device as D
+from ..engine import LOG_CHUNK, Budget, Engine, stop_rule
+
+
+def _grad_update(eng, a, b, sel, with_y, gscale, **kw):
+    eng.p._dev_grad(a, b=b, sel=sel, with_y=with_y, gscale=gscale, **kw)
+
+
+class _Faithful:
+    """One eager iteration with the reference's wall-clock phase timing and PSNR read-back."""
+
+    def __init__(self, eng, verbose):
+        self.eng, self.verbose = eng, verbose
+
+    def run(self, grad_phase, prox_in, prox_out, label_before=None, label_after=None, gd_style_time=False):
+        eng = self.eng
+        t0 = time.time()
+        with torch.cuda.stream(eng.stream):
+            grad_phase()
+        eng.stream.synchronize()
+        g_t = time.time() - t0
+        eng.gradient_time += g_t
+        if self.verbose and label_before is not None:
+            print(label_before + str(eng.psnr_of(prox_in)))
+        t1 = time.time()
+        with torch.cuda.stream(eng.stream):
+            eng.prox(prox_in, prox_out)
+            eng.advance()
+            psnr = eng.read_slot()
+        d_t = time.time() - t1
+        eng.denoise_time += d_t
+        eng.time_log.append(time.time() - t0 if gd_style_time else g_t + d_t)
+        eng.psnr_log.append(psnr)
+        if self.verbose and label_after is not None:
+            print(label_after + str(psnr))
+        return psnr
+
+
+def _fast_inner(eng, budget, n_iters, inner_ops, host_draw, sync_every, converge_check, diverge_check, start_psnr):
+    """Run up to n_iters graph-replayed inner iterations; returns (psnr_z, stop, done_iters)."""
+    # minibatches: device sampler draws in-graph; host sources are pre-drawn into a device ring
+    if eng.graph is None:
+        eng.graph = eng.capture(inner_ops)
+    done = 0
+    stop = False
+    psnr_z = start_psnr
+    while done < n_iters and not stop:
+        left = budget.left()
+        room = min(n_iters - done, sync_every, LOG_CHUNK - eng.slot_host, left if left is not None else 1 << 30)
+        if room <= 0:
+            break
+        t0 = time.time()
+        with torch.cuda.stream(eng.stream):
+            for _ in range(room):
+                if host_draw is not None:
+                    host_draw()
+                eng.replay(eng.graph)
+        eng.slot_host += room
+        vals = eng.flush_fast()
+        dt = time.time() - t0
+        for v in vals:
+            eng.time_log.append(dt / len(vals))
+            eng.psnr_log.append(v)
+            budget.calls += 1
+            eng.n_prox += 1
+            done += 1
+            if stop_rule(psnr_z, v, converge_check, diverge_check):
+                stop = True
+            psnr_z = v
+        if not budget.alive():
+            break
+    return psnr_z, stop, done
+
+
+def _host_draw_fn(eng, extra_fn=None):
+    if eng.B <= 0 or eng.mb_source == 'device':
+        return None
+
+    def draw():
+        eng.draw_host(extra_fn() if extra_fn else ())
+        eng.idx_dev.copy_(eng.idx_host, non_blocking=True)
+        # the pinned staging buffer is reused by the next draw: wait for the copy only
+        eng.stream.synchronize()
+    return draw
+
+
+def _sel_ops(eng):
+    """selection rebuild inside the (possibly captured) iteration"""
+    if eng.mb_source == 'device':
+        eng.sample_sel_device()
+    else:
+        eng.p._dev_set_sel(eng.sel, eng.idx_dev, eng.B)
+
+
+# ------------------------------------------------------------------------------------------ GD
+def pnp_gd(problem, denoiser, eta, tt, verbose=True, lr_decay=1, converge_check=True, diverge_check=False,
+           max_iters=None, fast=False, sync_every=64):
+    """algorithms/pnp_gd.py:8-84."""
+    eng = Engine(problem, denoiser, fast=fast)
+    budget = Budget(tt, max_iters)
+    eng.time_log.append(time.time() - budget.t0)
+    psnr_z = eng.psnr_of(eng.z)
+    eng.psnr_log.append(psnr_z)
+    z = eng.z
+    i = 0
+    M0 = getattr(problem, 'M0', problem.M)
+
+    def grad_phase():
+        _grad_update(eng, z, None, None, True, 1.0 / _full_norm(problem), step_ptr=eng.step, z_in=z, z_out=z)
+
+    if fast:
+        with torch.cuda.stream(eng.stream):
+            eng.set_step(eta)
+
+        def ops():
+            grad_phase()
+            eng.prox(z, z)
+            eng.check(eng.lib.pnp_advance_scale(D.ptr(eng.counters), 3, D.ptr(eng.step), float(lr_decay), eng.sptr))
+        while budget.alive():
+            psnr_z, stop, done = _fast_inner(eng, budget, 1 << 30, ops, None, sync_every, converge_check,
+                                             diverge_check, psnr_z)
+            if stop or done == 0:
+                break
+        eng.destroy(eng.graph)
+        return eng.result('PnP GD')
+
+    it = _Faithful(eng, verbose)
+    while budget.alive():
+        start = psnr_z
+        with torch.cuda.stream(eng.stream):
+            eng.set_step(eta * lr_decay ** i)
+        psnr_z = it.run(grad_phase, z, z, str(i) + " Before denoising:  ", str(i) + " After denoising:  ",
+                        gd_style_time=True)
+        budget.calls += 1
+        i += 1
+        if stop_rule(start, psnr_z, converge_check, diverge_check):
+            break
+    return eng.result('PnP GD')
+
+
+def _full_norm(problem):
+    """divisor of grad_full: M0 for CSMRI (problems/CSMRI.py:81), M otherwise (DeblurSR.py:132, PR.py:79)"""
+    return problem.M0 if getattr(problem, 'pname', '') == 'csmri' else problem.M
+
+
+# ----------------------------------------------------------------------------------------- SGD
+def pnp_sgd(problem, denoiser, eta, tt, mini_batch_size, verbose=True, lr_decay=1, converge_check=True,
+            diverge_check=False, max_iters=None, mb_source='legacy', mb_seed=0, mb_stream=None, fast=False,
+            sync_every=64):
+    """algorithms/pnp_sgd.py:8-84."""
+    B = int(mini_batch_size)
+    eng = Engine(problem, denoiser, B, mb_source, mb_seed, mb_stream, fast)
+    budget = Budget(tt, max_iters)
+    eng.time_log.append(time.time() - budget.t0)
+    psnr_z = eng.psnr_of(eng.z)
+    eng.psnr_log.append(psnr_z)
+    z = eng.z
+    i = 0
+
+    def grad_ops():
+        _grad_update(eng, z, None, eng.sel, True, 1.0 / B, step_ptr=eng.step, z_in=z, z_out=z)
+
+    if fast:
+        with torch.cuda.stream(eng.stream):
+            eng.set_step(eta)
+
+        def ops():
+            _sel_ops(eng)
+            grad_ops()
+            eng.prox(z, z)
+            eng.check(eng.lib.pnp_advance_scale(D.ptr(eng.counters), 3, D.ptr(eng.step), float(lr_decay), eng.sptr))
+        draw = _host_draw_fn(eng)
+        while budget.alive():
+            psnr_z, stop, done = _fast_inner(eng, budget, 1 << 30, ops, draw, sync_every, converge_check,
+                                             diverge_check, psnr_z)
+            if stop or done == 0:
+                break
+        eng.destroy(eng.graph)
+        return eng.result('PnP SGD')
+
+    it = _Faithful(eng, verbose)
+    while budget.alive():
+        start = psnr_z
+
+        def grad_phase():
+            eng.set_step(eta * lr_decay ** i)
+            if mb_source == 'device':
+                eng.sample_sel_device()
+            else:
+                eng.draw_host()
+                eng.upload_sel()
+            grad_ops()
+        psnr_z = it.run(grad_phase, z, z, str(i) + " Before denoising:  ", str(i) + " After denoising:  ")
+        budget.calls += 1
+        i += 1
+        if stop_rule(start, psnr_z, converge_check, diverge_check):
+            break
+    return eng.result('PnP SGD')
+
+
+# ---------------------------------------------------------------------------------------- SVRG
+def pnp_svrg(problem, denoiser, eta, tt, T2, mini_batch_size, verbose=True, lr_decay=1, converge_check=True,
+             diverge_check=False, max_iters=None, vr_mode='as_committed', mb_source='legacy', mb_seed=0,
+             mb_stream=None, fast=False, sync_every=64):
+    """algorithms/pnp_svrg.py:8-105."""
+    if vr_mode not in ('as_committed', 'paper'):
+        raise ValueError("vr_mode must be 'as_committed' or 'paper'")
+    B = int(mini_batch_size)
+    T2 = int(T2)
+    eng = Engine(problem, denoiser, B, mb_source, mb_seed, mb_stream, fast)
+    budget = Budget(tt, max_iters)
+    eng.time_log.append(time.time() - budget.t0)
+    psnr_z = eng.psnr_of(eng.z)
+    eng.psnr_log.append(psnr_z)
+    z = eng.z
+    with torch.cuda.stream(eng.stream):
+        w = torch.empty_like(z)
+        mu = torch.empty_like(z)
+    paper = vr_mode == 'paper'
+
+    def snapshot():
+        # mu = grad_full(z) ; w = copy(z)          (pnp_svrg.py:32-35)
+        _grad_update(eng, z, None, None, True, 1.0 / _full_norm(problem), g_out=mu)
+        eng.copy(w, z)
+
+    def grad_ops():
+        if paper:
+            _grad_update(eng, z, w, eng.sel, False, 1.0 / B, vadd=mu, step_ptr=eng.step, z_in=z, z_out=z)
+        else:
+            eng.check(eng.lib.pnp_axpy(D.ptr(z), D.ptr(mu), D.ptr(z), eng.N, 1, 0.0, D.ptr(eng.step), eng.sptr))
+
+    i = 0
+    stop = False
+    it = _Faithful(eng, verbose)
+
+    def fast_ops():
+        if paper:
+            _sel_ops(eng)
+        grad_ops()
+        eng.prox(z, z)
+        eng.advance()
+    draw = _host_draw_fn(eng) if (paper or mb_source == 'legacy') else None
+
+    while budget.alive() and not stop:
+        t_outer = time.time()
+        with torch.cuda.stream(eng.stream):
+            snapshot()
+            eng.set_step(eta * lr_decay ** i)
+        if not fast:
+            eng.stream.synchronize()
+        eng.time_log.append(time.time() - t_outer)
+        eng.psnr_log.append(psnr_z)
+        if fast:
+            psnr_z, stop, _ = _fast_inner(eng, budget, T2, fast_ops, draw, min(sync_every, T2) if converge_check or diverge_check else sync_every,
+                                          converge_check, diverge_check, psnr_z)
+        else:
+            for j in range(T2):
+                if not budget.alive():
+                    break
+                start = psnr_z
+
+                def grad_phase():
+                    if mb_source == 'device':
+                        if paper:
+                            eng.sample_sel_device()
+                    else:
+                        eng.draw_host()            # drawn even when unused (pnp_svrg.py:52)
+                        if paper:
+                            eng.upload_sel()
+                    grad_ops()
+                psnr_z = it.run(grad_phase, z, z, str(i) + " " + str(j) + " Before denoising:  ",
+                                "After denoising update: " + str(i) + " " + str(j) + " ")
+                budget.calls += 1
+                if stop_rule(start, psnr_z, converge_check, diverge_check):
+                    stop = True
+                    break
+        i += 1
+    eng.destroy(eng.graph)
+    return eng.result('PnP SVRG')
+
+
+# ---------------------------------------------------------------------------------------- SAGA
+def pnp_saga(problem, denoiser, eta, tt, mini_batch_size, hist_size=50, verbose=True, lr_decay=1,
+             converge_check=True, diverge_check=False, max_iters=None, mb_source='legacy', mb_seed=0,
+             mb_stream=None, fast=False, sync_every=64):
+    """algorithms/pnp_saga.py:8-102 (including its non-textbook use of the previous iteration's
+    gradient, :47,72)."""
+    B = int(mini_batch_size)
+    hist = int(hist_size)
+    eng = Engine(problem, denoiser, B, mb_source, mb_seed, mb_stream, fast, n_extra_ints=1)
+    budget = Budget(tt, max_iters)
+    z = eng.z
+    slot_rng = np.random.default_rng(mb_seed + 1) if mb_source != 'legacy' else None
+    with torch.cuda.stream(eng.stream):
+        g_new = torch.empty_like(z)
+        g_prev = torch.empty_like(z)
+        table = torch.empty(hist * eng.N, dtype=torch.float32, device=eng.dev)
+        tsum = torch.empty_like(z)
+    slot_dev = eng.idx_dev[B:B + 1]
+
+    def draw_slot():
+        if slot_rng is None:
+            return (int(np.random.choice(hist, 1).item()),)     # pnp_saga.py:44
+        return (int(slot_rng.integers(hist)),)
+
+    t0 = time.time()
+    with torch.cuda.stream(eng.stream):
+        # stoch_init / table fill                       (pnp_saga.py:25-29)
+        if mb_source == 'device':
+            eng.sample_sel_device()
+            eng.advance()
+        else:
+            eng.draw_host()
+            eng.upload_sel()
+        _grad_update(eng, z, None, eng.sel, True, 1.0 / B, g_out=g_prev)
+        eng.check(eng.lib.pnp_saga_init(D.ptr(g_prev), D.ptr(table), D.ptr(tsum), eng.N, 1, hist, eng.sptr))
+    eng.stream.synchronize()
+    if mb_source == 'device':
+        with torch.cuda.stream(eng.stream):
+            eng.counters[0:2].zero_()
+    eng.time_log.append(time.time() - t0)
+    psnr_z = eng.psnr_of(z)
+    eng.psnr_log.append(psnr_z)
+
+    def grad_ops():
+        _grad_update(eng, z, None, eng.sel, True, 1.0 / B, g_out=g_new)
+        eng.check(eng.lib.pnp_saga_update(D.ptr(g_new), D.ptr(g_prev), D.ptr(table), D.ptr(tsum), D.ptr(z), eng.N, 1,
+                                          hist, D.ptr(slot_dev), 0, None, 0.0, D.ptr(eng.step), eng.sptr))
+
+    i = 0
+    if fast:
+        with torch.cuda.stream(eng.stream):
+            eng.set_step(eta)
+
+        def ops():
+            _sel_ops(eng)
+            grad_ops()
+            eng.prox(z, z)
+            eng.check(eng.lib.pnp_advance_scale(D.ptr(eng.counters), 3, D.ptr(eng.step), float(lr_decay), eng.sptr))
+        if mb_source == 'device':
+            def draw():
+                eng.idx_host.numpy()[B] = draw_slot()[0]
+                eng.idx_dev[B:B + 1].copy_(eng.idx_host[B:B + 1], non_blocking=True)
+                eng.stream.synchronize()
+        else:
+            draw = _host_draw_fn(eng, draw_slot)
+        while budget.alive():
+            psnr_z, stop, done = _fast_inner(eng, budget, 1 << 30, ops, draw, sync_every, converge_check,
+                                             diverge_check, psnr_z)
+            if stop or done == 0:
+                break
+        eng.destroy(eng.graph)
+        return eng.result('pnp_saga')
+
+    it = _Faithful(eng, verbose)
+    while budget.alive():
+        start = psnr_z
+
+        def grad_phase():
+            eng.set_step(eta * lr_decay ** i)
+            if mb_source == 'device':
+                eng.sample_sel_device()
+                eng.idx_host.numpy()[B] = draw_slot()[0]
+                eng.idx_dev[B:B + 1].copy_(eng.idx_host[B:B + 1], non_blocking=True)
+            else:
+                # reference order: select_mb, then the table slot (pnp_saga.py:43-44)
+                idx = eng.p._draw_indices(B) if mb_source == 'legacy' else None
+                if idx is None:
+                    eng.draw_host(draw_slot())
+                else:
+                    buf = eng.idx_host.numpy()
+                    buf[:B] = idx
+                    buf[B] = draw_slot()[0]
+                eng.upload_sel()
+            grad_ops()
+        psnr_z = it.run(grad_phase, z, z, str(i) + " Before denoising:  ", str(i) + " After denoising:  ")
+        budget.calls += 1
+        i += 1
+        if stop_rule(start, psnr_z, converge_check, diverge_check):
+            break
+    return eng.result('pnp_saga')
+
+
+# --------------------------------------------------------------------------------------- SARAH
+def pnp_sarah(problem, denoiser, eta, tt, T2, mini_batch_size, verbose=True, lr_decay=1, converge_check=True,
+              diverge_check=False, max_iters=None, mb_source='legacy', mb_seed=0, mb_stream=None, fast=False,
+              sync_every=64):
+    """algorithms/pnp_sarah.py:8-129 (w_next is never advanced inside the inner loop and z is not
+    reset to it -- kept as in the reference, :60-104)."""
+    B = int(mini_batch_size)
+    T2 = int(T2)
+    eng = Engine(problem, denoiser, B, mb_source, mb_seed, mb_stream, fast)
+    budget = Budget(tt, max_iters)
+    z = eng.z
+    with torch.cuda.stream(eng.stream):
+        w_prev = torch.empty_like(z)
+        w_next = torch.empty_like(z)
+        v_prev = torch.empty_like(z)
+    psnr_z = eng.psnr_of(z)            # start_PSNR of the first inner iteration (not logged, :65)
+    it = _Faithful(eng, verbose)
+
+    def outer_grad():
+        # w_prev = z ; v_prev = grad_full(z) ; w_next = w_prev - eta * v_prev   (no lr_decay, :28-36)
+        eng.copy(w_prev, z)
+        _grad_update(eng, z, None, None, True, 1.0 / _full_norm(problem), g_out=v_prev, step=float(eta),
+                     z_in=z, z_out=w_next)
+
+    def grad_ops():
+        # v_next = (g_B(w_next) - g_B(w_prev)) / B + v_prev ; z -= step * v_next ; v_prev = v_next  (:72-75,97)
+        _grad_update(eng, w_next, w_prev, eng.sel, False, 1.0 / B, vadd=v_prev, v_out=v_prev, step_ptr=eng.step,
+                     z_in=z, z_out=z)
+
+    def after_prox():
+        eng.copy(w_prev, z)                     # w_previous = z0   (:98)
+
+    def fast_ops():
+        _sel_ops(eng)
+        grad_ops()
+        eng.prox(z, z)
+        after_prox()
+        eng.advance()
+    draw = _host_draw_fn(eng)
+
+    i = 0
+    stop = False
+    while budget.alive() and not stop:
+        # the outer prox step is logged like an iteration (:38-50)
+        t0 = time.time()
+        with torch.cuda.stream(eng.stream):
+            outer_grad()
+        eng.stream.synchronize()
+        g_t = time.time() - t0
+        eng.gradient_time += g_t
+        t1 = time.time()
+        with torch.cuda.stream(eng.stream):
+            eng.prox(w_next, w_next)
+            eng.advance()
+            psnr_w = eng.read_slot()
+        d_t = time.time() - t1
+        eng.denoise_time += d_t
+        eng.time_log.append(g_t + d_t)
+        eng.psnr_log.append(psnr_w)
+        budget.calls += 1
+        with torch.cuda.stream(eng.stream):
+            eng.set_step(eta * lr_decay ** i)
+        if fast:
+            psnr_z, stop, _ = _fast_inner(eng, budget, T2, fast_ops, draw, min(sync_every, T2) if converge_check or diverge_check else sync_every,
+                                          converge_check, diverge_check, psnr_z)
+        else:
+            for j in range(T2):
+                if not budget.alive():
+                    break
+                start = psnr_z
+
+                def grad_phase():
+                    if mb_source == 'device':
+                        eng.sample_sel_device()
+                    else:
+                        eng.draw_host()
+                        eng.upload_sel()
+                    grad_ops()
+                psnr_z = it.run(grad_phase, z, z, "After gradient update: " + str(i) + " " + str(j) + " ",
+                                "After denoising update: " + str(i) + " " + str(j) + " ")
+                with torch.cuda.stream(eng.stream):
+                    after_prox()
+                budget.calls += 1
+                if stop_rule(start, psnr_z, converge_check, diverge_check):
+                    stop = True
+                    break
+        i += 1
+    eng.destroy(eng.graph)
+    return eng.result('pnp_sarah')

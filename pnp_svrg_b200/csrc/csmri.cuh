@@ -1,0 +1,275 @@
+// CSMRI data-fidelity gradient  Re(ifft2(sel o fft2(x) - Y_sel))  fused with the
+// variance-reduced update, for sm_100a.
+//
+// Reference: problems/CSMRI.py:76-81 (grad_full), :83-89 (grad_stoch); update lines
+// algorithms/pnp_gd.py:32-35, pnp_sgd.py:32-36, pnp_svrg.py:53-57, pnp_sarah.py:72-75.
+//
+// DEVICE LAYOUT.  Images are kept TRANSPOSED: line c (c = original column, W lines) holds
+// the H samples z[0..H-1][c] contiguously.  The per-column operators of the prox step
+// (estimate_sigma / denoise_wavelet with multichannel=True) therefore work on contiguous
+// lines, and fft2 of the transpose is the transpose of fft2.
+//
+//   pass 1  k_lines_r2c   two real lines -> one complex FFT of length H (two-for-one), unpacked
+//                         to the packed half spectrum S[kx'][kyp], kyp in [0, H/2): the real
+//                         Nyquist term (ky = H/2) rides in the imaginary slot of the real DC term.
+//                         Input may be a difference a - b (g_B(z) - g_B(w) is linear, Y cancels).
+//   pass 2  k_cols_mask   per packed ky column: FFT over the W lines, multiply by the
+//                         Hermitian-symmetrised selection  (sel[k] + sel[-k]) / 2, subtract the
+//                         symmetrised measurements, inverse FFT -- the spectrum never leaves
+//                         shared memory between the three steps.
+//   pass 3  k_lines_c2r   two-for-one inverse, 1/(HW) scaling and the fused update epilogue
+//                         v = g * gscale + vadd ;  z_out = z_in - step * v.
+//
+// Because sel is not Hermitian-symmetric, Re(ifft2(sel o Z)) is computed exactly as the
+// real inverse of its Hermitian part:  ((sel[k] + sel[-k]) / 2) Z[k]  (Z[-k] = conj Z[k]).
+#pragma once
+#include "fft_core.cuh"
+
+namespace pnp {
+
+struct GradEpilogue {
+    float gscale;                 // multiplies the raw gradient (after 1/(HW))
+    const float* gscale_ptr;      // optional per-image multiplier, replaces gscale
+    float step;                   // z_out = z_in - step * v
+    const float* step_ptr;        // optional per-image step, replaces step
+    float* g_out;                 // optional: g * gscale
+    const float* vadd;            // optional: v = g * gscale + vadd
+    float* v_out;                 // optional: v
+    const float* z_in;            // optional (with z_out)
+    float* z_out;
+};
+
+// ------------------------------------------------------------------ pass 1
+template <int L, int GP>
+__global__ void __launch_bounds__(GP * (L / FftPlan<L>::EPT))
+k_lines_r2c(const float* __restrict__ a, const float* __restrict__ b, float2* __restrict__ S,
+            int nlines, long long img_stride) {
+    constexpr int T = fft_threads<L>();
+    constexpr int PL = fft_plane<L>();
+    extern __shared__ float smem[];
+    const int g = threadIdx.x / T, t = threadIdx.x % T;
+    const int pair = blockIdx.x * GP + g;
+    const bool active = 2 * pair < nlines;
+    const long long base = (long long)blockIdx.y * img_stride + (long long)(2 * pair) * L;
+    const SmemBuf sb{smem + g * 2 * PL, smem + g * 2 * PL + PL};
+    const float* a0 = a + base;
+    const float* b0 = b ? b + base : nullptr;
+    auto ld = [&](int idx) -> float2 {
+        if (!active) return make_float2(0.f, 0.f);
+        float x = a0[idx], y = a0[idx + L];
+        if (b0) { x -= b0[idx]; y -= b0[idx + L]; }
+        return make_float2(x, y);
+    };
+    auto st = [&](int idx, float2 v) { sb.put(idx, v); };
+    fft_forward<L, false>(t, sb, ld, st);
+    __syncthreads();
+    if (!active) return;
+    float2* SA = S + (base >> 1);          // line 2*pair, L/2 complex per line
+    float2* SB = SA + L / 2;
+    for (int k = t; k < L / 2; k += T) {
+        const float2 xk = sb.get(k);
+        const float2 xm = sb.get(k == 0 ? L / 2 : L - k);
+        float2 A, B;
+        if (k == 0) {
+            A = make_float2(xk.x, xm.x);   // (DC, Nyquist) of line 2*pair
+            B = make_float2(xk.y, xm.y);
+        } else {
+            A = make_float2(0.5f * (xk.x + xm.x), 0.5f * (xk.y - xm.y));
+            B = make_float2(0.5f * (xk.y + xm.y), 0.5f * (xm.x - xk.x));
+        }
+        SA[k] = A;
+        SB[k] = B;
+    }
+}
+
+// ------------------------------------------------------------------ pass 2
+// sel bits per packed entry [kx][kyp]:  bit0 = sel[kyp][kx], bit1 = sel[-kyp][-kx];
+// for kyp == 0 additionally bit2 = sel[H/2][kx], bit3 = sel[H/2][-kx] (the packed Nyquist row).
+__device__ __forceinline__ float2 apply_sel(float2 F, unsigned bb, bool use_y, const float2* y1,
+                                            const float2* y2) {
+    const float w = 0.5f * (float)((bb & 1u) + ((bb >> 1) & 1u));
+    float2 o = make_float2(w * F.x, w * F.y);
+    if (use_y) {
+        if (bb & 1u) { const float2 y = *y1; o.x -= 0.5f * y.x; o.y -= 0.5f * y.y; }
+        if (bb & 2u) { const float2 y = *y2; o.x -= 0.5f * y.x; o.y -= 0.5f * y.y; }
+    }
+    return o;
+}
+
+template <int L, int CT>
+__global__ void __launch_bounds__(CT * (L / FftPlan<L>::EPT))
+k_cols_mask(float2* __restrict__ S, const unsigned char* __restrict__ bits,
+            const float2* __restrict__ Y1, const float2* __restrict__ Y2,
+            const float2* __restrict__ Y1n, const float2* __restrict__ Y2n,
+            int hp, long long bits_img_stride, long long y_img_stride) {
+    constexpr int T = fft_threads<L>();
+    constexpr int EPT = FftPlan<L>::EPT;
+    constexpr int PL = fft_plane<L>();
+    extern __shared__ float smem[];
+    const int col = threadIdx.x % CT, t = threadIdx.x / CT;
+    const int kyp = blockIdx.x * CT + col;
+    const int img = blockIdx.y;
+    const SmemBuf sb{smem + col * 2 * PL, smem + col * 2 * PL + PL};
+    float2* Sc = S + (long long)img * L * hp + kyp;
+    const unsigned char* bc = bits + (long long)img * bits_img_stride + kyp;
+    const bool use_y = Y1 != nullptr;
+    const float2* y1c = use_y ? Y1 + (long long)img * y_img_stride + kyp : nullptr;
+    const float2* y2c = use_y ? Y2 + (long long)img * y_img_stride + kyp : nullptr;
+
+    auto ld = [&](int idx) -> float2 { return Sc[(long long)idx * hp]; };
+    auto st = [&](int idx, float2 v) { sb.put(idx, v); };
+    fft_forward<L, false>(t, sb, ld, st);
+    __syncthreads();
+
+    if (kyp != 0) {
+#pragma unroll 4
+        for (int m = 0; m < EPT; ++m) {
+            const int kx = t + m * T;
+            const long long e = (long long)kx * hp;
+            const float2 o = apply_sel(sb.get(kx), bc[e], use_y, y1c + e, y2c + e);
+            sb.put(kx, cswap(o));
+        }
+    } else {
+        // packed column: C = FFT(DC + i * Nyq); split, select each row, re-pack
+        const float2* y1n = use_y ? Y1n + (long long)img * L : nullptr;
+        const float2* y2n = use_y ? Y2n + (long long)img * L : nullptr;
+        for (int kx = t; kx <= L / 2; kx += T) {
+            const int km = (L - kx) % L;
+            const float2 ck = sb.get(kx), cm = sb.get(km);
+            const float2 fdc = make_float2(0.5f * (ck.x + cm.x), 0.5f * (ck.y - cm.y));
+            const float2 fny = make_float2(0.5f * (ck.y + cm.y), 0.5f * (cm.x - ck.x));
+            const long long ek = (long long)kx * hp, em = (long long)km * hp;
+            const unsigned bk = bc[ek], bm = bc[em];
+            const float2 dk = apply_sel(fdc, bk, use_y, y1c + ek, y2c + ek);
+            const float2 nk = apply_sel(fny, bk >> 2, use_y, y1n + kx, y2n + kx);
+            const float2 dm = apply_sel(make_float2(fdc.x, -fdc.y), bm, use_y, y1c + em, y2c + em);
+            const float2 nm = apply_sel(make_float2(fny.x, -fny.y), bm >> 2, use_y, y1n + km, y2n + km);
+            // C'[k] = dc[k] + i * ny[k], stored re/im swapped for the inverse transform
+            sb.put(kx, make_float2(dk.y + nk.x, dk.x - nk.y));
+            if (km != kx) sb.put(km, make_float2(dm.y + nm.x, dm.x - nm.y));
+        }
+    }
+    __syncthreads();
+    auto ld2 = [&](int idx) -> float2 { return sb.get(idx); };
+    auto st2 = [&](int idx, float2 v) { Sc[(long long)idx * hp] = cswap(v); };
+    fft_forward<L, true>(t, sb, ld2, st2);
+}
+
+// ------------------------------------------------------------------ pass 3
+template <int L, int GP>
+__global__ void __launch_bounds__(GP * (L / FftPlan<L>::EPT))
+k_lines_c2r(const float2* __restrict__ S, int nlines, long long img_stride, float inv_n, GradEpilogue ep) {
+    constexpr int T = fft_threads<L>();
+    constexpr int PL = fft_plane<L>();
+    extern __shared__ float smem[];
+    const int g = threadIdx.x / T, t = threadIdx.x % T;
+    const int pair = blockIdx.x * GP + g;
+    const bool active = 2 * pair < nlines;
+    const int img = blockIdx.y;
+    const long long base = (long long)img * img_stride + (long long)(2 * pair) * L;
+    const SmemBuf sb{smem + g * 2 * PL, smem + g * 2 * PL + PL};
+    if (active) {
+        const float2* SA = S + (base >> 1);
+        const float2* SB = SA + L / 2;
+        for (int k = t; k < L / 2; k += T) {
+            const float2 A = SA[k], B = SB[k];
+            if (k == 0) {
+                sb.put(0, make_float2(B.x, A.x));           // X[0]   = A_dc + i B_dc   (swapped)
+                sb.put(L / 2, make_float2(B.y, A.y));       // X[L/2] = A_ny + i B_ny   (swapped)
+            } else {
+                sb.put(k, make_float2(A.y + B.x, A.x - B.y));       // X[k]   = A + iB
+                sb.put(L - k, make_float2(B.x - A.y, A.x + B.y));   // X[L-k] = conj A + i conj B
+            }
+        }
+    }
+    __syncthreads();
+    const float gs = inv_n * (ep.gscale_ptr ? ep.gscale_ptr[img] : ep.gscale);
+    const float step = ep.step_ptr ? ep.step_ptr[img] : ep.step;
+    auto emit = [&](long long e, float graw) {
+        const float gval = graw * gs;
+        if (ep.g_out) ep.g_out[e] = gval;
+        float v = gval;
+        if (ep.vadd) v += ep.vadd[e];
+        if (ep.v_out) ep.v_out[e] = v;
+        if (ep.z_out) ep.z_out[e] = ep.z_in[e] - step * v;
+    };
+    auto ld = [&](int idx) -> float2 { return active ? sb.get(idx) : make_float2(0.f, 0.f); };
+    auto st = [&](int idx, float2 v) {
+        if (!active) return;
+        emit(base + idx, v.y);          // swapped output: .y = real part -> line 2*pair
+        emit(base + L + idx, v.x);      //                 .x = imag part -> line 2*pair + 1
+    };
+    fft_forward<L, true>(t, sb, ld, st);
+}
+
+// ------------------------------------------------------------------ selection bits
+__device__ __forceinline__ void or_byte(unsigned char* base, long long byte_idx, unsigned v) {
+    unsigned* w = reinterpret_cast<unsigned*>(base) + (byte_idx >> 2);
+    atomicOr(w, v << (8 * (int)(byte_idx & 3)));
+}
+
+// k = ky * W + kx is an index into the reference's (H, W) k-space array (problems/CSMRI.py:66-74)
+__device__ __forceinline__ void set_sel_bits(unsigned char* bits, int H, int W, int k) {
+    const int ky = k / W, kx = k % W;
+    const int hp = H / 2;
+    const int kym = (H - ky) % H, kxm = (W - kx) % W;
+    if (ky < hp) or_byte(bits, (long long)kx * hp + ky, 1u);
+    else if (ky == hp) or_byte(bits, (long long)kx * hp, 4u);
+    if (kym < hp) or_byte(bits, (long long)kxm * hp + kym, 2u);
+    else if (kym == hp) or_byte(bits, (long long)kxm * hp, 8u);
+}
+
+// explicit minibatch:  idx[img][cursor][0..B)
+__global__ void k_sel_from_indices(unsigned char* __restrict__ bits, int H, int W, const int* __restrict__ idx,
+                                   int B, long long idx_img_stride, const int* __restrict__ cursor) {
+    const int img = blockIdx.y;
+    const int cur = cursor ? *cursor : 0;
+    const int* src = idx + (long long)img * idx_img_stride + (long long)cur * B;
+    unsigned char* bi = bits + (long long)img * W * (H / 2);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < B; i += gridDim.x * blockDim.x)
+        set_sel_bits(bi, H, W, src[i]);
+}
+
+// device-drawn minibatch: B distinct positions of the sampled support through a keyed
+// cycle-walking Feistel permutation of [0, M0)  (bench / production mode; the reference draws
+// with np.random.choice(..., replace=False), problems/CSMRI.py:72)
+__device__ __forceinline__ unsigned mix32(unsigned x) {
+    x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15; x *= 0x846ca68bU; x ^= x >> 16;
+    return x;
+}
+__device__ __forceinline__ unsigned feistel_perm(unsigned i, unsigned n, unsigned key) {
+    int hb = 1;
+    while ((1u << (2 * hb)) < n) ++hb;                 // 2*hb bits cover n
+    const unsigned hm = (1u << hb) - 1u;
+    unsigned x = i;
+    do {
+        unsigned l = x >> hb, r = x & hm;
+#pragma unroll
+        for (int rd = 0; rd < 4; ++rd) {
+            const unsigned f = mix32(r ^ (key + 0x9e3779b9U * (rd + 1))) & hm;
+            const unsigned nl = r;
+            r = l ^ f;
+            l = nl;
+        }
+        x = (l << hb) | r;
+    } while (x >= n);
+    return x;
+}
+
+__global__ void k_sel_from_feistel(unsigned char* __restrict__ bits, int H, int W,
+                                   const int* __restrict__ support, const int* __restrict__ m0,
+                                   long long support_img_stride, int B, unsigned seed,
+                                   const int* __restrict__ counter, int* __restrict__ idx_out) {
+    const int img = blockIdx.y;
+    const unsigned key = mix32(seed ^ mix32((counter ? (unsigned)*counter : 0u) * 0x632be5abU + (unsigned)img));
+    const int* sup = support + (long long)img * support_img_stride;
+    const unsigned n = (unsigned)m0[img];
+    unsigned char* bi = bits + (long long)img * W * (H / 2);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < B; i += gridDim.x * blockDim.x) {
+        const int k = sup[feistel_perm((unsigned)i, n, key)];
+        if (idx_out) idx_out[(long long)img * B + i] = k;
+        set_sel_bits(bi, H, W, k);
+    }
+}
+
+}  // namespace pnp

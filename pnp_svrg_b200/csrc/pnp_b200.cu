@@ -1,0 +1,326 @@
+// libpnp_b200.so -- C ABI (include/pnp_b200.h) over the sm_100a kernels of the PnP hot path.
+// One translation unit: the kernels live in the .cuh files next to this one.
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+#include "../../include/pnp_b200.h"
+#include "csmri.cuh"
+#include "prox.cuh"
+#include "vr.cuh"
+
+namespace {
+
+thread_local char g_err[512] = "";
+bool g_init[64] = {false};
+
+int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CU_TRY(expr)                                                                            \
+    do {                                                                                        \
+        cudaError_t e__ = (expr);                                                               \
+        if (e__ != cudaSuccess)                                                                 \
+            return fail(PNP_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__),  \
+                        __FILE__, __LINE__);                                                    \
+    } while (0)
+
+#define LAUNCH_CHECK() CU_TRY(cudaGetLastError())
+
+bool pow2_ok(int n) { return n >= 32 && n <= 4096 && (n & (n - 1)) == 0; }
+
+int check_init() {
+    int dev = 0;
+    CU_TRY(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64 || !g_init[dev]) return fail(PNP_ERR_NOT_INIT, "pnp_init() not called on device %d", dev);
+    return PNP_OK;
+}
+
+// ---- per-size launch geometry ------------------------------------------------------------
+template <int L> constexpr int lines_gp() {            // line pairs per CTA in passes 1 and 3
+    return pnp::fft_threads<L>() >= 128 ? 1 : (pnp::fft_threads<L>() >= 64 ? 2 : (128 / pnp::fft_threads<L>() > 8 ? 8 : 128 / pnp::fft_threads<L>()));
+}
+template <int L> constexpr int cols_ct() { return 4; }  // packed columns per CTA in pass 2
+template <int L> constexpr size_t lines_smem() { return sizeof(float) * 2 * pnp::fft_plane<L>() * lines_gp<L>(); }
+template <int L> constexpr size_t cols_smem() { return sizeof(float) * 2 * pnp::fft_plane<L>() * cols_ct<L>(); }
+
+template <int L>
+int set_attrs() {
+    CU_TRY(cudaFuncSetAttribute(pnp::k_lines_r2c<L, lines_gp<L>()>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lines_smem<L>()));
+    CU_TRY(cudaFuncSetAttribute(pnp::k_lines_c2r<L, lines_gp<L>()>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lines_smem<L>()));
+    CU_TRY(cudaFuncSetAttribute(pnp::k_cols_mask<L, cols_ct<L>()>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cols_smem<L>()));
+    cudaFuncAttributes fa;
+    CU_TRY(cudaFuncGetAttributes(&fa, pnp::k_sigma_mad<L>));
+    CU_TRY(cudaFuncGetAttributes(&fa, pnp::k_haar_bayes<L>));
+    return PNP_OK;
+}
+
+template <int L>
+int launch_r2c(const pnp_csmri_grad_args& a, cudaStream_t st) {
+    constexpr int GP = lines_gp<L>();
+    const int pairs = a.W / 2;
+    dim3 grid((pairs + GP - 1) / GP, a.batch);
+    pnp::k_lines_r2c<L, GP><<<grid, GP * pnp::fft_threads<L>(), lines_smem<L>(), st>>>(
+        a.a, a.b, reinterpret_cast<float2*>(a.S), a.W, (long long)a.H * a.W);
+    LAUNCH_CHECK();
+    return PNP_OK;
+}
+
+template <int L>
+int launch_cols(const pnp_csmri_grad_args& a, cudaStream_t st) {
+    constexpr int CT = cols_ct<L>();
+    const int hp = a.H / 2;
+    dim3 grid(hp / CT, a.batch);
+    pnp::k_cols_mask<L, CT><<<grid, CT * pnp::fft_threads<L>(), cols_smem<L>(), st>>>(
+        reinterpret_cast<float2*>(a.S), a.bits, reinterpret_cast<const float2*>(a.Y1),
+        reinterpret_cast<const float2*>(a.Y2), reinterpret_cast<const float2*>(a.Y1n),
+        reinterpret_cast<const float2*>(a.Y2n), hp, (long long)a.W * hp, (long long)a.W * hp);
+    LAUNCH_CHECK();
+    return PNP_OK;
+}
+
+template <int L>
+int launch_c2r(const pnp_csmri_grad_args& a, cudaStream_t st) {
+    constexpr int GP = lines_gp<L>();
+    const int pairs = a.W / 2;
+    dim3 grid((pairs + GP - 1) / GP, a.batch);
+    pnp::GradEpilogue ep{a.gscale, a.gscale_ptr, a.step, a.step_ptr, a.g_out, a.vadd, a.v_out, a.z_in, a.z_out};
+    const float inv_n = (float)(1.0 / ((double)a.H * (double)a.W));
+    pnp::k_lines_c2r<L, GP><<<grid, GP * pnp::fft_threads<L>(), lines_smem<L>(), st>>>(
+        reinterpret_cast<const float2*>(a.S), a.W, (long long)a.H * a.W, inv_n, ep);
+    LAUNCH_CHECK();
+    return PNP_OK;
+}
+
+#define DISPATCH_POW2(n, FN, ...)                                 \
+    switch (n) {                                                  \
+        case 32: return FN<32>(__VA_ARGS__);                      \
+        case 64: return FN<64>(__VA_ARGS__);                      \
+        case 128: return FN<128>(__VA_ARGS__);                    \
+        case 256: return FN<256>(__VA_ARGS__);                    \
+        case 512: return FN<512>(__VA_ARGS__);                    \
+        case 1024: return FN<1024>(__VA_ARGS__);                  \
+        case 2048: return FN<2048>(__VA_ARGS__);                  \
+        case 4096: return FN<4096>(__VA_ARGS__);                  \
+        default: return fail(PNP_ERR_ARG, "size %d is not a power of two in [32, 4096]", (int)(n)); \
+    }
+
+int dispatch_r2c(int n, const pnp_csmri_grad_args& a, cudaStream_t st) { DISPATCH_POW2(n, launch_r2c, a, st) }
+int dispatch_cols(int n, const pnp_csmri_grad_args& a, cudaStream_t st) { DISPATCH_POW2(n, launch_cols, a, st) }
+int dispatch_c2r(int n, const pnp_csmri_grad_args& a, cudaStream_t st) { DISPATCH_POW2(n, launch_c2r, a, st) }
+int dispatch_attrs(int n) { DISPATCH_POW2(n, set_attrs) }
+
+template <int L>
+int launch_sigma(const float* z, int W, int batch, double* sig_log, const int* slot, cudaStream_t st) {
+    dim3 grid((W + 3) / 4, batch);
+    pnp::k_sigma_mad<L><<<grid, 128, 0, st>>>(z, W, (long long)L * W, sig_log, slot, batch);
+    LAUNCH_CHECK();
+    return PNP_OK;
+}
+int dispatch_sigma(int n, const float* z, int W, int batch, double* sig_log, const int* slot, cudaStream_t st) {
+    DISPATCH_POW2(n, launch_sigma, z, W, batch, sig_log, slot, st)
+}
+
+template <int L>
+int launch_haar(const float* zin, float* zout, const float* xrec, int W, int batch, pnp::ShrinkParams sp,
+                double* mse_log, const int* slot, cudaStream_t st) {
+    dim3 grid((W + 3) / 4, batch);
+    pnp::k_haar_bayes<L><<<grid, 128, 0, st>>>(zin, zout, xrec, W, (long long)L * W, sp, mse_log, slot, batch);
+    LAUNCH_CHECK();
+    return PNP_OK;
+}
+int dispatch_haar(int n, const float* zin, float* zout, const float* xrec, int W, int batch, pnp::ShrinkParams sp,
+                  double* mse_log, const int* slot, cudaStream_t st) {
+    DISPATCH_POW2(n, launch_haar, zin, zout, xrec, W, batch, sp, mse_log, slot, st)
+}
+
+int ew_blocks(long long n, int per_thread) {
+    long long b = (n / per_thread + 255) / 256;
+    if (b < 1) b = 1;
+    if (b > 148 * 8) b = 148 * 8;
+    return (int)b;
+}
+
+}  // namespace
+
+extern "C" {
+
+int pnp_version(void) { return 100; }
+const char* pnp_last_error(void) { return g_err; }
+
+int pnp_init(void) {
+    int dev = 0;
+    CU_TRY(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64) return fail(PNP_ERR_ARG, "device index %d out of range", dev);
+    if (g_init[dev]) return PNP_OK;
+    std::vector<float2> tw(PNP_TW_N);
+    for (int m = 0; m < PNP_TW_N; ++m) {
+        const double ang = -2.0 * M_PI * (double)m / (double)PNP_TW_N;
+        tw[m] = make_float2((float)std::cos(ang), (float)std::sin(ang));
+    }
+    CU_TRY(cudaMemcpyToSymbol(g_tw, tw.data(), sizeof(float2) * PNP_TW_N));
+    for (int n = 32; n <= 4096; n *= 2) {
+        const int rc = dispatch_attrs(n);
+        if (rc != PNP_OK) return rc;
+    }
+    {
+        cudaFuncAttributes fa;
+        CU_TRY(cudaFuncGetAttributes(&fa, pnp::k_sel_from_indices));
+        CU_TRY(cudaFuncGetAttributes(&fa, pnp::k_sel_from_feistel));
+        CU_TRY(cudaFuncGetAttributes(&fa, pnp::k_sq_err));
+        CU_TRY(cudaFuncGetAttributes(&fa, pnp::k_axpy));
+        CU_TRY(cudaFuncGetAttributes(&fa, pnp::k_saga_update));
+        CU_TRY(cudaFuncGetAttributes(&fa, pnp::k_saga_init));
+        CU_TRY(cudaFuncGetAttributes(&fa, pnp::k_advance));
+    }
+    g_init[dev] = true;
+    return PNP_OK;
+}
+
+int pnp_csmri_grad(const pnp_csmri_grad_args* args, void* stream) {
+    if (!args) return fail(PNP_ERR_ARG, "null args");
+    const pnp_csmri_grad_args& a = *args;
+    if (!pow2_ok(a.H) || !pow2_ok(a.W)) return fail(PNP_ERR_ARG, "H=%d W=%d must be powers of two in [32, 4096]", a.H, a.W);
+    if (a.batch < 1 || a.batch > 65535) return fail(PNP_ERR_ARG, "batch=%d out of range", a.batch);
+    if (!a.a || !a.S || !a.bits) return fail(PNP_ERR_ARG, "a, S and bits must be non-null");
+    if ((a.Y1 == nullptr) != (a.Y2 == nullptr) || (a.Y1 == nullptr) != (a.Y1n == nullptr) ||
+        (a.Y1 == nullptr) != (a.Y2n == nullptr))
+        return fail(PNP_ERR_ARG, "Y1, Y2, Y1n, Y2n must be all null or all non-null");
+    if ((a.z_out != nullptr) && !a.z_in) return fail(PNP_ERR_ARG, "z_out needs z_in");
+    int rc = check_init();
+    if (rc != PNP_OK) return rc;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if ((rc = dispatch_r2c(a.H, a, st)) != PNP_OK) return rc;
+    if ((rc = dispatch_cols(a.W, a, st)) != PNP_OK) return rc;
+    return dispatch_c2r(a.H, a, st);
+}
+
+int pnp_csmri_sel_from_indices(unsigned char* bits, int H, int W, int batch, const int* idx, int count,
+                               long long idx_img_stride, const int* cursor, int clear, void* stream) {
+    if (!bits || !idx || !pow2_ok(H) || !pow2_ok(W) || batch < 1 || count < 0) return fail(PNP_ERR_ARG, "bad argument");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (clear) CU_TRY(cudaMemsetAsync(bits, 0, (size_t)batch * W * (H / 2), st));
+    if (count == 0) return PNP_OK;
+    int blocks = (count + 255) / 256;
+    if (blocks > 592) blocks = 592;
+    pnp::k_sel_from_indices<<<dim3(blocks, batch), 256, 0, st>>>(bits, H, W, idx, count, idx_img_stride, cursor);
+    LAUNCH_CHECK();
+    return PNP_OK;
+}
+
+int pnp_csmri_sel_sample(unsigned char* bits, int H, int W, int batch, const int* support, const int* m0,
+                         long long support_img_stride, int count, unsigned seed, const int* counter,
+                         int* idx_out, int clear, void* stream) {
+    if (!bits || !support || !m0 || !pow2_ok(H) || !pow2_ok(W) || batch < 1 || count < 1) return fail(PNP_ERR_ARG, "bad argument");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (clear) CU_TRY(cudaMemsetAsync(bits, 0, (size_t)batch * W * (H / 2), st));
+    int blocks = (count + 255) / 256;
+    if (blocks > 592) blocks = 592;
+    pnp::k_sel_from_feistel<<<dim3(blocks, batch), 256, 0, st>>>(bits, H, W, support, m0, support_img_stride, count,
+                                                                  seed, counter, idx_out);
+    LAUNCH_CHECK();
+    return PNP_OK;
+}
+
+int pnp_estimate_sigma(const float* z, int H, int W, int batch, double* sig_log, const int* slot, void* stream) {
+    if (!z || !sig_log || batch < 1) return fail(PNP_ERR_ARG, "bad argument");
+    return dispatch_sigma(H, z, W, batch, sig_log, slot, static_cast<cudaStream_t>(stream));
+}
+
+int pnp_wavelet_denoise(const float* z_in, float* z_out, int H, int W, int batch, const double* sig_log,
+                        float sigma_est, float sigma_modifier, float fallback_sigma, const float* xrec,
+                        double* mse_log, const int* slot, void* stream) {
+    if (!z_in || !z_out || batch < 1) return fail(PNP_ERR_ARG, "bad argument");
+    pnp::ShrinkParams sp{sig_log, sigma_est, sigma_modifier, fallback_sigma};
+    return dispatch_haar(H, z_in, z_out, xrec, W, batch, sp, mse_log, slot, static_cast<cudaStream_t>(stream));
+}
+
+int pnp_sq_err(const float* z, const float* xrec, long long n, int batch, double* out, const int* slot, void* stream) {
+    if (!z || !xrec || !out || n < 1 || batch < 1) return fail(PNP_ERR_ARG, "bad argument");
+    pnp::k_sq_err<<<dim3(ew_blocks(n, 4), batch), 256, 0, static_cast<cudaStream_t>(stream)>>>(z, xrec, n, n, out, slot, batch);
+    LAUNCH_CHECK();
+    return PNP_OK;
+}
+
+int pnp_axpy(const float* z_in, const float* v, float* z_out, long long n, int batch, float step,
+             const float* step_ptr, void* stream) {
+    if (!z_in || !v || !z_out || n < 4 || (n & 3) || batch < 1) return fail(PNP_ERR_ARG, "bad argument (n must be a multiple of 4)");
+    pnp::k_axpy<<<dim3(ew_blocks(n, 4), batch), 256, 0, static_cast<cudaStream_t>(stream)>>>(z_in, v, z_out, n, n, step, step_ptr);
+    LAUNCH_CHECK();
+    return PNP_OK;
+}
+
+int pnp_saga_init(const float* g0, float* table, float* tsum, long long n, int batch, int hist, void* stream) {
+    if (!g0 || !table || !tsum || n < 1 || batch < 1 || hist < 1) return fail(PNP_ERR_ARG, "bad argument");
+    pnp::k_saga_init<<<dim3(ew_blocks(n, 1), batch), 256, 0, static_cast<cudaStream_t>(stream)>>>(g0, table, tsum, n, n, hist);
+    LAUNCH_CHECK();
+    return PNP_OK;
+}
+
+int pnp_saga_update(const float* g_new, float* g_prev, float* table, float* tsum, float* z, long long n,
+                    int batch, int hist, const int* slot_idx, long long slot_img_stride, const int* cursor,
+                    float step, const float* step_ptr, void* stream) {
+    if (!g_new || !g_prev || !table || !tsum || !z || !slot_idx || n < 1 || batch < 1 || hist < 1)
+        return fail(PNP_ERR_ARG, "bad argument");
+    pnp::k_saga_update<<<dim3(ew_blocks(n, 1), batch), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        g_new, g_prev, table, tsum, z, n, n, hist, slot_idx, slot_img_stride, cursor, step, step_ptr);
+    LAUNCH_CHECK();
+    return PNP_OK;
+}
+
+int pnp_advance(int* counters, int n, void* stream) {
+    if (!counters || n < 1 || n > 32) return fail(PNP_ERR_ARG, "bad argument");
+    pnp::k_advance<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(counters, n, nullptr, 1.0f);
+    LAUNCH_CHECK();
+    return PNP_OK;
+}
+
+int pnp_advance_scale(int* counters, int n, float* x, float factor, void* stream) {
+    if (!counters || n < 1 || n > 32) return fail(PNP_ERR_ARG, "bad argument");
+    pnp::k_advance<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(counters, n, x, factor);
+    LAUNCH_CHECK();
+    return PNP_OK;
+}
+
+int pnp_copy_f32(float* dst, const float* src, long long n, void* stream) {
+    if (!dst || !src || n < 0) return fail(PNP_ERR_ARG, "bad argument");
+    CU_TRY(cudaMemcpyAsync(dst, src, sizeof(float) * (size_t)n, cudaMemcpyDeviceToDevice, static_cast<cudaStream_t>(stream)));
+    return PNP_OK;
+}
+
+int pnp_graph_begin(void* stream) {
+    CU_TRY(cudaStreamBeginCapture(static_cast<cudaStream_t>(stream), cudaStreamCaptureModeRelaxed));
+    return PNP_OK;
+}
+
+int pnp_graph_end(void* stream, void** exec_out) {
+    if (!exec_out) return fail(PNP_ERR_ARG, "null exec_out");
+    cudaGraph_t graph = nullptr;
+    CU_TRY(cudaStreamEndCapture(static_cast<cudaStream_t>(stream), &graph));
+    cudaGraphExec_t exec = nullptr;
+    cudaError_t e = cudaGraphInstantiate(&exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (e != cudaSuccess) return fail(PNP_ERR_CUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(e));
+    *exec_out = exec;
+    return PNP_OK;
+}
+
+int pnp_graph_launch(void* exec, void* stream) {
+    if (!exec) return fail(PNP_ERR_ARG, "null exec");
+    CU_TRY(cudaGraphLaunch(static_cast<cudaGraphExec_t>(exec), static_cast<cudaStream_t>(stream)));
+    return PNP_OK;
+}
+
+int pnp_graph_destroy(void* exec) {
+    if (exec) CU_TRY(cudaGraphExecDestroy(static_cast<cudaGraphExec_t>(exec)));
+    return PNP_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,236 @@
+// Prox-step kernels on TRANSPOSED images (line c = original column c, contiguous, length H):
+//
+//   k_sigma_mad     skimage estimate_sigma(z0, multichannel=True, average_sigmas=True)
+//                   (algorithms/pnp_svrg.py:71 and the five sibling call sites): per column the
+//                   db2 detail coefficients (symmetric extension), median of |d| over d != 0,
+//                   / Phi^-1(0.75); the mean over columns is accumulated in a double slot.
+//   k_haar_bayes    skimage denoise_wavelet(BayesShrink, db1, soft, multichannel=True)
+//                   (denoisers/TV.py:24,26): per column multi-level Haar, per-level threshold
+//                   sigma^2 / sqrt(max(mean(d^2) - sigma^2, eps)), soft shrink, inverse -- one
+//                   warp per column, pyramid in registers + warp shuffles; the squared error
+//                   against the ground truth (problems/problem.py:33-35) is reduced in the epilogue.
+//   k_sq_err        stand-alone sum((z - xrec)^2) for Problem.PSNR.
+#pragma once
+#include <cuda_runtime.h>
+
+namespace pnp {
+
+__device__ __forceinline__ int warp_sum_i(int v) { return __reduce_add_sync(0xffffffffu, v); }
+__device__ __forceinline__ float warp_sum_f(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// log slot addressing shared by the prox kernels: slot s of image i lives at base[s * batch + i]
+__device__ __forceinline__ double* slot_ptr(double* base, const int* slot, int batch, int img) {
+    return base + (long long)(slot ? *slot : 0) * batch + img;
+}
+
+template <int L>
+__global__ void __launch_bounds__(128)
+k_sigma_mad(const float* __restrict__ z, int nlines, long long img_stride, double* __restrict__ sig_log,
+            const int* __restrict__ slot, int batch) {
+    constexpr int NO = (L + 3) / 2;            // db2 detail coefficients per line
+    constexpr int PER = (NO + 31) / 32;
+    const int lane = threadIdx.x & 31;
+    const int line = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int img = blockIdx.y;
+    if (line >= nlines) return;
+    const float* x = z + (long long)img * img_stride + (long long)line * L;
+    // pywt dec_hi of db2; out[o] = sum_j h[j] * x_ext[2o + 1 - j]
+    const float h0 = -0.48296291314469025f, h1 = 0.836516303737469f,
+                h2 = -0.22414386804185735f, h3 = -0.12940952255092145f;
+    unsigned a[PER];
+    int nnz = 0;
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+        const int o = lane + 32 * i;
+        a[i] = 0xffffffffu;
+        if (o < NO) {
+            int i0 = 2 * o + 1, i1 = 2 * o, i2 = 2 * o - 1, i3 = 2 * o - 2;
+            // half-sample symmetric extension
+            i0 = i0 >= L ? 2 * L - 1 - i0 : i0;
+            i1 = i1 >= L ? 2 * L - 1 - i1 : i1;
+            i2 = i2 < 0 ? -1 - i2 : (i2 >= L ? 2 * L - 1 - i2 : i2);
+            i3 = i3 < 0 ? -1 - i3 : (i3 >= L ? 2 * L - 1 - i3 : i3);
+            const float d = fmaf(h0, x[i0], fmaf(h1, x[i1], fmaf(h2, x[i2], h3 * x[i3])));
+            if (d != 0.f) { a[i] = __float_as_uint(fabsf(d)); ++nnz; }
+        }
+    }
+    nnz = warp_sum_i(nnz);
+    double sig;
+    if (nnz == 0) {
+        sig = __longlong_as_double(0x7ff8000000000000LL);      // median of nothing = NaN
+    } else {
+        const int k1 = (nnz - 1) >> 1, k2 = nnz >> 1;
+        unsigned res = 0;
+        for (int bit = 30; bit >= 0; --bit) {                  // k1-th smallest by bit search
+            const unsigned cand = res | (1u << bit);
+            int c = 0;
+#pragma unroll
+            for (int i = 0; i < PER; ++i) c += a[i] < cand;
+            if (warp_sum_i(c) <= k1) res = cand;
+        }
+        unsigned res2 = res;
+        if (k2 != k1) {
+            int c = 0;
+            unsigned mn = 0xffffffffu;
+#pragma unroll
+            for (int i = 0; i < PER; ++i) { c += a[i] <= res; if (a[i] > res) mn = min(mn, a[i]); }
+            c = warp_sum_i(c);
+            mn = __reduce_min_sync(0xffffffffu, mn);
+            if (c < k2 + 1) res2 = mn;
+        }
+        sig = 0.5 * ((double)__uint_as_float(res) + (double)__uint_as_float(res2)) / 0.6744897501960817;
+    }
+    if (lane == 0) atomicAdd(slot_ptr(sig_log, slot, batch, img), sig);
+}
+
+__device__ __forceinline__ float soft_shrink(float d, float thr) {
+    const float m = fabsf(d) - thr;
+    return m > 0.f ? copysignf(m, d) : 0.f;
+}
+
+struct ShrinkParams {
+    const double* sig_log;      // optional: sigma_est = slot value / nlines (mean over columns)
+    float sigma_est;            // used when sig_log == nullptr
+    float sigma_modifier;       // TVDenoiser.sigma_modifier
+    float fallback_sigma;       // denoise_strength * decay**t, used when sigma_est <= 0 or NaN
+};
+
+template <int L>
+__global__ void __launch_bounds__(128)
+k_haar_bayes(const float* __restrict__ zin, float* __restrict__ zout, const float* __restrict__ xrec,
+             int nlines, long long img_stride, ShrinkParams sp, double* __restrict__ mse_log,
+             const int* __restrict__ slot, int batch) {
+    constexpr int VPL = L / 32;                 // consecutive samples per lane
+    constexpr int LIN = (VPL == 1) ? 0 : (VPL == 2) ? 1 : (VPL == 4) ? 2 : (VPL == 8) ? 3 : (VPL == 16) ? 4
+                        : (VPL == 32) ? 5 : (VPL == 64) ? 6 : 7;     // in-lane levels
+    constexpr int LEVELS = LIN + 2;             // = log2(L) - 3  (skimage skips the 3 coarsest)
+    constexpr float RS2 = 0.70710678118654752f;
+    const int lane = threadIdx.x & 31;
+    const int line = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int img = blockIdx.y;
+    if (line >= nlines) return;
+    const long long off = (long long)img * img_stride + (long long)line * L + lane * VPL;
+
+    float x[VPL];
+    if (VPL >= 4) {
+#pragma unroll
+        for (int i = 0; i < VPL / 4; ++i) {
+            const float4 q = reinterpret_cast<const float4*>(zin + off)[i];
+            x[4 * i] = q.x; x[4 * i + 1] = q.y; x[4 * i + 2] = q.z; x[4 * i + 3] = q.w;
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < VPL; ++i) x[i] = zin[off + i];
+    }
+
+    double se = sp.sig_log ? *slot_ptr(const_cast<double*>(sp.sig_log), slot, batch, img) / (double)nlines
+                           : (double)sp.sigma_est;
+    const float sigma = (se > 0.0) ? (float)(se * (double)sp.sigma_modifier) : sp.fallback_sigma;
+    const float var = sigma * sigma;
+
+    float ss[LEVELS];
+#pragma unroll
+    for (int l = 0; l < LEVELS; ++l) ss[l] = 0.f;
+
+    // forward pyramid, in place: after level lv the approximation sits at multiples of 2^lv
+#pragma unroll
+    for (int lv = 1; lv <= LIN; ++lv) {
+        const int stride = 1 << lv, half = stride >> 1;
+#pragma unroll
+        for (int i = 0; i < VPL / stride; ++i) {
+            const float p = x[i * stride], q = x[i * stride + half];
+            const float d = (p - q) * RS2;
+            x[i * stride] = (p + q) * RS2;
+            x[i * stride + half] = d;
+            ss[lv - 1] = fmaf(d, d, ss[lv - 1]);
+        }
+    }
+    const float a0 = x[0];
+    const float p1 = __shfl_xor_sync(0xffffffffu, a0, 1);
+    const bool ev1 = (lane & 1) == 0;
+    const float A1 = (a0 + p1) * RS2;
+    const float D1 = (ev1 ? (a0 - p1) : (p1 - a0)) * RS2;
+    ss[LIN] = ev1 ? D1 * D1 : 0.f;
+    const float p2 = __shfl_xor_sync(0xffffffffu, A1, 2);
+    const bool ev2 = (lane & 2) == 0;
+    const float A2 = (A1 + p2) * RS2;
+    const float D2 = (ev2 ? (A1 - p2) : (p2 - A1)) * RS2;
+    ss[LIN + 1] = (lane & 3) == 0 ? D2 * D2 : 0.f;
+
+    float thr[LEVELS];
+#pragma unroll
+    for (int l = 0; l < LEVELS; ++l) {
+        const float dvar = warp_sum_f(ss[l]) / (float)(L >> (l + 1));
+        thr[l] = var / sqrtf(fmaxf(dvar - var, 2.220446049250313e-16f));
+    }
+
+    // inverse pyramid with soft-thresholded details
+    const float D2t = soft_shrink(D2, thr[LIN + 1]);
+    const float A1r = (ev2 ? (A2 + D2t) : (A2 - D2t)) * RS2;
+    const float D1t = soft_shrink(D1, thr[LIN]);
+    x[0] = (ev1 ? (A1r + D1t) : (A1r - D1t)) * RS2;
+#pragma unroll
+    for (int lv = LIN; lv >= 1; --lv) {
+        const int stride = 1 << lv, half = stride >> 1;
+#pragma unroll
+        for (int i = 0; i < VPL / stride; ++i) {
+            const float a = x[i * stride];
+            const float d = soft_shrink(x[i * stride + half], thr[lv - 1]);
+            x[i * stride] = (a + d) * RS2;
+            x[i * stride + half] = (a - d) * RS2;
+        }
+    }
+
+    float err = 0.f;
+    if (VPL >= 4) {
+#pragma unroll
+        for (int i = 0; i < VPL / 4; ++i) {
+            reinterpret_cast<float4*>(zout + off)[i] = make_float4(x[4 * i], x[4 * i + 1], x[4 * i + 2], x[4 * i + 3]);
+            if (xrec) {
+                const float4 r = reinterpret_cast<const float4*>(xrec + off)[i];
+                const float e0 = x[4 * i] - r.x, e1 = x[4 * i + 1] - r.y, e2 = x[4 * i + 2] - r.z, e3 = x[4 * i + 3] - r.w;
+                err += e0 * e0 + e1 * e1 + e2 * e2 + e3 * e3;
+            }
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < VPL; ++i) {
+            zout[off + i] = x[i];
+            if (xrec) { const float e = x[i] - xrec[off + i]; err = fmaf(e, e, err); }
+        }
+    }
+    if (xrec && mse_log) {
+        err = warp_sum_f(err);
+        if (lane == 0) atomicAdd(slot_ptr(mse_log, slot, batch, img), (double)err);
+    }
+}
+
+// sum((z - xrec)^2) per image -> out[slot][img]
+__global__ void __launch_bounds__(256)
+k_sq_err(const float* __restrict__ z, const float* __restrict__ xrec, long long n, long long img_stride,
+         double* __restrict__ out, const int* __restrict__ slot, int batch) {
+    const int img = blockIdx.y;
+    const float* a = z + (long long)img * img_stride;
+    const float* b = xrec + (long long)img * img_stride;
+    float acc = 0.f;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const float e = a[i] - b[i];
+        acc = fmaf(e, e, acc);
+    }
+    acc = warp_sum_f(acc);
+    __shared__ float part[8];
+    if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x < 8) {
+        float v = part[threadIdx.x];
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1) v += __shfl_xor_sync(0xffu, v, o);
+        if (threadIdx.x == 0) atomicAdd(slot_ptr(out, slot, batch, img), (double)v);
+    }
+}
+
+}  // namespace pnp

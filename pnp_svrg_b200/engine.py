@@ -1,0 +1,251 @@
+"""Device-resident PnP iteration engine shared by algorithms/pnp_{gd,sgd,svrg,saga,sarah}.
+
+The reference loops (algorithms/pnp_*.py) keep the iterate in host NumPy and call
+problem.grad_* / estimate_sigma / denoiser.denoise / problem.PSNR every iteration.  Here the
+iterate, the snapshot, the gradient tables and the PSNR / sigma logs stay in HBM; one inner
+iteration is a fixed sequence of kernel launches on one CUDA stream:
+
+    [selection bits] -> [gradient + variance-reduced update] -> [sigma estimate] -> [prox + PSNR]
+    -> [advance device counters]
+
+Two ways of driving that sequence:
+  faithful (default)  launches are issued eagerly, the minibatch is drawn on the host with
+                      NumPy's legacy global RNG in the reference's call order, and the PSNR of
+                      every iterate is read back (8 bytes) so converge_check / diverge_check /
+                      verbose behave exactly like the reference;
+  fast                the sequence is captured once in a CUDA graph and replayed; minibatches
+                      come from a pre-drawn device buffer or the device sampler, logs are read
+                      back once per chunk, stop rules are applied at chunk boundaries.
+"""
+import time
+
+import numpy as np
+import torch
+
+from . import _lib, device as D
+
+TOL = 1e-5
+LOG_CHUNK = 4096
+
+
+class ProxCtx:
+    """What a denoiser's _dev_denoise needs."""
+    __slots__ = ('z_in', 'z_out', 'H', 'W', 'sig_log', 'sigma_est', 'xrec', 'mse_log', 'slot')
+
+    def __init__(self, z_in, z_out, H, W, sig_log=None, sigma_est=0.0, xrec=None, mse_log=None, slot=None):
+        self.z_in, self.z_out, self.H, self.W = z_in, z_out, H, W
+        self.sig_log, self.sigma_est, self.xrec, self.mse_log, self.slot = sig_log, sigma_est, xrec, mse_log, slot
+
+
+def _require_device_objects(problem, denoiser):
+    if not hasattr(problem, '_dev_grad'):
+        raise TypeError('%s is not a pnp_svrg_b200 problem: the loops run on the GPU only (no CPU fallback)'
+                        % type(problem).__name__)
+    if not hasattr(denoiser, '_dev_denoise'):
+        raise TypeError('%s is not a pnp_svrg_b200 denoiser: the loops run on the GPU only (no CPU fallback)'
+                        % type(denoiser).__name__)
+
+
+class Engine:
+    def __init__(self, problem, denoiser, mini_batch_size=0, mb_source='legacy', mb_seed=0, mb_stream=None,
+                 fast=False, n_extra_ints=0):
+        _require_device_objects(problem, denoiser)
+        self.p, self.d = problem, denoiser
+        self.lib = _lib.load()
+        self.dev = problem._device
+        self.H, self.W, self.N = problem.H, problem.W, problem.N
+        self.B = int(mini_batch_size)
+        self.mb_source = mb_source
+        self.mb_stream = mb_stream
+        self.fast = fast
+        if mb_source not in ('legacy', 'host', 'device', 'stream'):
+            raise ValueError("mb_source must be 'legacy', 'host', 'device' or 'stream'")
+        if mb_source == 'stream' and mb_stream is None:
+            raise ValueError("mb_source='stream' needs mb_stream (a sequence of index arrays)")
+        self.rng = np.random.default_rng(mb_seed) if mb_source == 'host' else None
+        self.mb_seed = int(mb_seed)
+        self.stream = torch.cuda.Stream(device=self.dev)
+        torch.cuda.synchronize(self.dev)
+        self.sptr = self.stream.cuda_stream
+        with torch.cuda.stream(self.stream):
+            self.z = D.to_lines(problem.Xinit, self.H, self.W, self.dev)
+            self.mse_log = torch.zeros(LOG_CHUNK, dtype=torch.float64, device=self.dev)
+            self.sig_log = torch.zeros(LOG_CHUNK, dtype=torch.float64, device=self.dev)
+            self.counters = torch.zeros(4, dtype=torch.int32, device=self.dev)   # [0] log slot [1] mb cursor [2] draws
+            self.step = torch.zeros(1, dtype=torch.float32, device=self.dev)
+            self.sel = problem._dev_new_sel() if self.B > 0 else None
+            self.n_extra = n_extra_ints
+            if self.B > 0:
+                self.idx_host = torch.empty(self.B + n_extra_ints, dtype=torch.int32).pin_memory()
+                self.idx_dev = torch.zeros(self.B + n_extra_ints, dtype=torch.int32, device=self.dev)
+        self.slot_ptr = self.counters[0:1]
+        self.cursor_ptr = self.counters[1:2]
+        self.draw_ptr = self.counters[2:3]
+        self.slot_host = 0
+        self.n_prox = 0
+        self.psnr_log = []
+        self.sig_hist = []
+        self.time_log = []
+        self.gradient_time = 0.0
+        self.denoise_time = 0.0
+        self._stream_pos = 0
+        self._ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        self._pending = []          # fast mode: (kind,) markers for slots not yet read back
+        self.graph = None
+        self.uses_sigma = getattr(denoiser, '_uses_sigma_est', True)
+
+    # ------------------------------------------------------------------ helpers
+    def check(self, rc):
+        if rc:
+            _lib.check(rc)
+
+    def set_step(self, value):
+        self.step.fill_(float(value))
+
+    def copy(self, dst, src):
+        self.check(self.lib.pnp_copy_f32(D.ptr(dst), D.ptr(src), dst.numel(), self.sptr))
+
+    def psnr_of(self, z_lines):
+        """Problem.PSNR of a device iterate (one reduction kernel + 8-byte readback)."""
+        self.stream.synchronize()
+        with torch.cuda.stream(self.stream):
+            s = self.p._sq_err_dev(z_lines)
+        return self.p._psnr_from_sum(s)
+
+    def _psnr_from_sum(self, s):
+        return self.p._psnr_from_sum(s)
+
+    # ------------------------------------------------------------------ minibatches
+    def draw_host(self, extra=()):
+        """Draw one minibatch on the host in the reference's RNG call order and stage it in pinned
+        memory; returns the positions (k-space / measurement indices)."""
+        if self.mb_source == 'legacy':
+            idx = self.p._draw_indices(self.B)
+        elif self.mb_source == 'host':
+            idx = self.rng.choice(self.p._support_host if hasattr(self.p, '_support_host') else self.p.M,
+                                  self.B, replace=False)
+        elif self.mb_source == 'stream':
+            idx = np.asarray(self.mb_stream[self._stream_pos])
+            self._stream_pos += 1
+            if idx.size != self.B:
+                raise ValueError('mb_stream entry %d has %d positions, expected %d' % (self._stream_pos - 1, idx.size, self.B))
+        else:
+            raise RuntimeError('draw_host called with mb_source=%r' % self.mb_source)
+        buf = self.idx_host.numpy()
+        buf[:self.B] = idx
+        for i, e in enumerate(extra):
+            buf[self.B + i] = e
+        return idx
+
+    def upload_sel(self):
+        """pinned -> device copy of the staged minibatch and rebuild of the selection."""
+        self.idx_dev.copy_(self.idx_host, non_blocking=True)
+        self.p._dev_set_sel(self.sel, self.idx_dev, self.B)
+
+    def sample_sel_device(self):
+        self.p._dev_sample_sel(self.sel, self.B, self.mb_seed, counter=self.draw_ptr)
+
+    # ------------------------------------------------------------------ prox + log
+    def prox(self, z_in, z_out):
+        """sigma estimate + denoiser + squared error against the ground truth into the current slot."""
+        if self.uses_sigma:
+            self.check(self.lib.pnp_estimate_sigma(D.ptr(z_in), self.H, self.W, 1, D.ptr(self.sig_log),
+                                                   D.ptr(self.slot_ptr), self.sptr))
+        self.d._dev_denoise(ProxCtx(z_in, z_out, self.H, self.W, sig_log=self.sig_log if self.uses_sigma else None,
+                                    xrec=self.p._xrec_dev, mse_log=self.mse_log, slot=self.slot_ptr))
+        if not getattr(self.d, '_fused_psnr', True):
+            self.check(self.lib.pnp_sq_err(D.ptr(z_out), D.ptr(self.p._xrec_dev), self.N, 1, D.ptr(self.mse_log),
+                                           D.ptr(self.slot_ptr), self.sptr))
+
+    def advance(self, n=3):
+        self.check(self.lib.pnp_advance(D.ptr(self.counters), n, self.sptr))
+
+    def read_slot(self):
+        """faithful mode: PSNR of the prox output just computed (synchronises the stream)."""
+        s = self.slot_host
+        vals = torch.stack([self.mse_log[s], self.sig_log[s]]).cpu().numpy()
+        self.slot_host += 1
+        self.n_prox += 1
+        if self.slot_host >= LOG_CHUNK:
+            self._reset_logs()
+        self.sig_hist.append(float(vals[1]) / self.W)
+        return self._psnr_from_sum(float(vals[0]))
+
+    def _reset_logs(self):
+        self.mse_log.zero_()
+        self.sig_log.zero_()
+        self.counters[0:1].zero_()
+        self.slot_host = 0
+
+    def flush_fast(self):
+        """fast mode: read back every slot written since the last flush."""
+        self.stream.synchronize()
+        n = self.slot_host
+        if n == 0:
+            return []
+        mse = self.mse_log[:n].cpu().numpy()
+        sig = self.sig_log[:n].cpu().numpy()
+        self.sig_hist.extend(list(sig / self.W))
+        with torch.cuda.stream(self.stream):
+            self._reset_logs()
+        return [self._psnr_from_sum(float(v)) for v in mse]
+
+    # ------------------------------------------------------------------ graphs
+    def capture(self, fn):
+        """Capture the launches issued by fn() on the engine stream into an executable graph."""
+        import ctypes as C
+        self.stream.synchronize()
+        self.check(self.lib.pnp_graph_begin(self.sptr))
+        try:
+            with torch.cuda.stream(self.stream):
+                fn()
+        finally:
+            exec_ = C.c_void_p()
+            rc = self.lib.pnp_graph_end(self.sptr, C.byref(exec_))
+        self.check(rc)
+        return exec_
+
+    def replay(self, exec_):
+        self.check(self.lib.pnp_graph_launch(exec_, self.sptr))
+
+    def destroy(self, exec_):
+        if exec_:
+            self.lib.pnp_graph_destroy(exec_)
+
+    def result(self, name):
+        self.stream.synchronize()
+        z = D.from_lines(self.z, self.H, self.W)
+        return {
+            'z': z,
+            'time_per_iter': self.time_log,
+            'psnr_per_iter': self.psnr_log,
+            'gradient_time': self.gradient_time,
+            'denoise_time': self.denoise_time,
+            'algo_name': name,
+        }
+
+
+class Budget:
+    """Loop bound: the reference's wall clock ``tt`` plus the additive ``max_iters`` (prox calls)."""
+
+    def __init__(self, tt, max_iters):
+        self.tt = float(tt)
+        self.max_iters = None if max_iters is None else int(max_iters)
+        self.t0 = time.time()
+        self.calls = 0
+
+    def alive(self):
+        if self.max_iters is not None and self.calls >= self.max_iters:
+            return False
+        return (time.time() - self.t0) < self.tt
+
+    def left(self):
+        return None if self.max_iters is None else self.max_iters - self.calls
+
+
+def stop_rule(start_psnr, last_psnr, converge_check, diverge_check):
+    if converge_check is True and np.abs(start_psnr - last_psnr) < TOL:
+        return True
+    if diverge_check is True and last_psnr < 0:
+        return True
+    return False

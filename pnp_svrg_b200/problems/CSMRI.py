@@ -1,0 +1,135 @@
+"""Compressive-sensing MRI -- same public surface as the reference's problems/CSMRI.py:11-89,
+gradients on the GPU through pnp_csmri_grad (csrc/csmri.cuh)."""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from .. import _lib, device as D
+from .problem import MiniBatch, Problem
+
+
+class CSMRI(Problem):
+    def __init__(self, img_path=None, H=256, W=256, sample_prob=0.5, snr=None, sigma=None, *,
+                 image=None, mask_type='bernoulli'):
+        super().__init__(img_path, H, W, image=image)
+        if H != W:
+            raise Exception('CSMRI needs a square image (the reference applies an HxH DFT matrix on both sides)')
+        self.pname = 'csmri'
+        self.sample_prob = sample_prob
+        self.snr = snr
+        self.sigma = sigma
+        self.mask_type = mask_type
+
+        self._generate_mask()
+        self.Y0 = self.forward_model(self.X)
+        self.set_snr_sigma()
+        noises = np.random.normal(0, self.sigma, self.Y0.shape)
+        self.Y = self.Y0 + np.multiply(self.mask, noises)
+        self.SNR = self.get_snr_from_sigma
+        x0 = np.absolute(np.fft.ifft2(self.Y)).ravel()
+        self.Xinit = (x0 - np.min(x0)) / (np.max(x0) - np.min(x0))
+
+        self.lrH, self.lrW = self.H, self.W
+        self.M = self.N
+        self.M0 = np.count_nonzero(self.mask)
+        self._upload_measurements()
+
+    # ---- construction (host, one-off; SURVEY section 8(f) rank 2 moves it to the device) ------
+    def _generate_mask(self):
+        if self.mask_type == 'bernoulli':      # problems/CSMRI.py:43-45
+            self.mask = np.random.choice([0, 1], size=(self.H, self.W),
+                                         p=[1 - self.sample_prob, self.sample_prob])
+        elif self.mask_type == 'rows':         # additive mode named by the north star (not in the reference)
+            rows = np.random.choice([0, 1], size=(self.H, 1), p=[1 - self.sample_prob, self.sample_prob])
+            self.mask = np.repeat(rows, self.W, axis=1)
+        else:
+            raise Exception('unknown mask_type %r' % (self.mask_type,))
+
+    def forward_model(self, w):
+        """mask o fft2(w): the reference multiplies by a dense DFT matrix on both sides
+        (problems/CSMRI.py:47-59), which equals fft2 to ~6e-9; the dense matrix is not built."""
+        return np.multiply(self.mask, np.fft.fft2(np.asarray(w, dtype=np.float64).reshape(self.H, self.W)))
+
+    def f(self, w):
+        return np.linalg.norm(self.Y - self.forward_model(w)) ** 2 / 2 / self.M
+
+    def _upload_measurements(self):
+        H, W, hp = self.H, self.W, self.H // 2
+        dev = self._device
+        Ym = np.multiply(self.mask, self.Y)
+        Ymir = np.conj(Ym[(-np.arange(H)) % H][:, (-np.arange(W)) % W])
+
+        def up(a):
+            t = torch.from_numpy(np.ascontiguousarray(a).astype(np.complex64)).to(dev)
+            return torch.view_as_real(t).contiguous()
+        self._Y1 = up(Ym[:hp, :].T)             # [kx][kyp]
+        self._Y2 = up(Ymir[:hp, :].T)
+        self._Y1n = up(Ym[hp, :])
+        self._Y2n = up(Ymir[hp, :])
+        self._support_host = np.flatnonzero(self.mask).astype(np.int32)
+        self._support = torch.from_numpy(self._support_host).to(dev)
+        self._m0_dev = torch.tensor([self.M0], dtype=torch.int32, device=dev)
+        self._bits_full = torch.zeros(W * hp, dtype=torch.uint8, device=dev)
+        self._dev_set_sel(self._bits_full, self._support, self.M0)
+        self._S = torch.empty(self.N, dtype=torch.float32, device=dev)
+        self._bits_tmp = torch.zeros(W * hp, dtype=torch.uint8, device=dev)
+
+    # ---- device protocol used by pnp_svrg_b200.engine ------------------------------------------
+    def _dev_new_sel(self):
+        return torch.zeros(self.W * (self.H // 2), dtype=torch.uint8, device=self._device)
+
+    def _dev_full_sel(self):
+        return self._bits_full
+
+    def _dev_set_sel(self, sel, idx_dev, count, cursor=None, stride=0):
+        _lib.check(_lib.load().pnp_csmri_sel_from_indices(D.ptr(sel), self.H, self.W, 1, D.ptr(idx_dev), int(count),
+                                                          int(stride), D.ptr(cursor), 1, D.stream()))
+
+    def _dev_sample_sel(self, sel, count, seed, counter=None, idx_out=None):
+        _lib.check(_lib.load().pnp_csmri_sel_sample(D.ptr(sel), self.H, self.W, 1, D.ptr(self._support),
+                                                    D.ptr(self._m0_dev), 0, int(count), int(seed) & 0xffffffff,
+                                                    D.ptr(counter), D.ptr(idx_out), 1, D.stream()))
+
+    def _dev_grad(self, a, b=None, sel=None, with_y=True, gscale=1.0, gscale_ptr=None, step=0.0, step_ptr=None,
+                  g_out=None, vadd=None, v_out=None, z_in=None, z_out=None):
+        """g = Re(ifft2(sel o fft2(a - b) - Ysel)) * gscale ; v = g + vadd ; z_out = z_in - step*v."""
+        args = _lib.CsmriGradArgs(
+            H=self.H, W=self.W, batch=1, a=D.ptr(a), b=D.ptr(b), S=D.ptr(self._S),
+            bits=D.ptr(self._bits_full if sel is None else sel),
+            Y1=D.ptr(self._Y1) if with_y else None, Y2=D.ptr(self._Y2) if with_y else None,
+            Y1n=D.ptr(self._Y1n) if with_y else None, Y2n=D.ptr(self._Y2n) if with_y else None,
+            gscale=float(gscale), gscale_ptr=D.ptr(gscale_ptr), step=float(step), step_ptr=D.ptr(step_ptr),
+            g_out=D.ptr(g_out), vadd=D.ptr(vadd), v_out=D.ptr(v_out), z_in=D.ptr(z_in), z_out=D.ptr(z_out))
+        _lib.check(_lib.load().pnp_csmri_grad(C.byref(args), D.stream()))
+
+    # ---- reference API ---------------------------------------------------------------------
+    def _draw_indices(self, size):
+        # problems/CSMRI.py:66-74: uniform draw without replacement from the sampled support
+        if size > self.M:
+            print('MB size is too big: ', size, ' > ', self.M)
+        return np.random.choice(self._support_host, size, replace=False)
+
+    def select_mb(self, size):
+        locs = self._draw_indices(size)
+        batch = np.zeros(self.M)
+        batch[locs] = 1
+        return MiniBatch(batch.reshape(self.H, self.W).astype(int), locs)
+
+    def grad_full(self, z):
+        """problems/CSMRI.py:76-81."""
+        zl = D.to_lines(z, self.H, self.W, self._device)
+        g = torch.empty_like(zl)
+        self._dev_grad(zl, gscale=1.0 / self.M0, g_out=g)
+        return D.from_lines(g, self.H, self.W)
+
+    def grad_stoch(self, z, mb):
+        """problems/CSMRI.py:83-89 (not divided by the batch size; positions outside the mask drop out)."""
+        idx = self._indices_of(mb)
+        idx = idx[self.mask.ravel()[idx] != 0]
+        zl = D.to_lines(z, self.H, self.W, self._device)
+        g = torch.empty_like(zl)
+        idx_dev = torch.from_numpy(np.ascontiguousarray(idx, dtype=np.int32)).to(self._device)
+        self._dev_set_sel(self._bits_tmp, idx_dev, idx.size)
+        self._dev_grad(zl, sel=self._bits_tmp, g_out=g)
+        return D.from_lines(g, self.H, self.W)
