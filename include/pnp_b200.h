@@ -63,6 +63,8 @@ typedef struct {
     float* v_out;
     const float* z_in;
     float* z_out;
+    int phases;                   /* 0 = all three passes; else bit0 lines r2c, bit1 columns+selection,
+                                     bit2 lines c2r + epilogue (used to time the passes one by one) */
 } pnp_csmri_grad_args;
 int pnp_csmri_grad(const pnp_csmri_grad_args* args, void* stream);
 

@@ -94,7 +94,10 @@ def _host_draw_fn(eng, extra_fn=None):
         return None
 
     def draw():
-        eng.draw_host(extra_fn() if extra_fn else ())
+        eng.draw_host()                                   # minibatch first, then the extras
+        if extra_fn:                                      # (reference RNG call order, pnp_saga.py:43-44)
+            for k, e in enumerate(extra_fn()):
+                eng.idx_host.numpy()[eng.B + k] = e
         eng.idx_dev.copy_(eng.idx_host, non_blocking=True)
         # the pinned staging buffer is reused by the next draw: wait for the copy only
         eng.stream.synchronize()

@@ -197,9 +197,11 @@ int pnp_csmri_grad(const pnp_csmri_grad_args* args, void* stream) {
     int rc = check_init();
     if (rc != PNP_OK) return rc;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if ((rc = dispatch_r2c(a.H, a, st)) != PNP_OK) return rc;
-    if ((rc = dispatch_cols(a.W, a, st)) != PNP_OK) return rc;
-    return dispatch_c2r(a.H, a, st);
+    const int ph = a.phases ? a.phases : 7;
+    if ((ph & 1) && (rc = dispatch_r2c(a.H, a, st)) != PNP_OK) return rc;
+    if ((ph & 2) && (rc = dispatch_cols(a.W, a, st)) != PNP_OK) return rc;
+    if (ph & 4) return dispatch_c2r(a.H, a, st);
+    return PNP_OK;
 }
 
 int pnp_csmri_sel_from_indices(unsigned char* bits, int H, int W, int batch, const int* idx, int count,

@@ -81,7 +81,8 @@ class Engine:
         self.slot_ptr = self.counters[0:1]
         self.cursor_ptr = self.counters[1:2]
         self.draw_ptr = self.counters[2:3]
-        self.slot_host = 0
+        self.slot_host = 0          # next log slot the device will write
+        self.slot_base = 0          # first slot not yet read back
         self.n_prox = 0
         self.psnr_log = []
         self.sig_hist = []
@@ -89,6 +90,7 @@ class Engine:
         self.gradient_time = 0.0
         self.denoise_time = 0.0
         self._stream_pos = 0
+        self._host_draws = 0
         self._ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
         self._pending = []          # fast mode: (kind,) markers for slots not yet read back
         self.graph = None
@@ -122,8 +124,10 @@ class Engine:
         if self.mb_source == 'legacy':
             idx = self.p._draw_indices(self.B)
         elif self.mb_source == 'host':
-            idx = self.rng.choice(self.p._support_host if hasattr(self.p, '_support_host') else self.p.M,
-                                  self.B, replace=False)
+            sup = getattr(self.p, '_support_host', None)
+            pos = feistel_sample(self.p.M if sup is None else sup.size, self.B, self.mb_seed, self._host_draws)
+            self._host_draws += 1
+            idx = pos if sup is None else sup[pos]
         elif self.mb_source == 'stream':
             idx = np.asarray(self.mb_stream[self._stream_pos])
             self._stream_pos += 1
@@ -165,6 +169,7 @@ class Engine:
         s = self.slot_host
         vals = torch.stack([self.mse_log[s], self.sig_log[s]]).cpu().numpy()
         self.slot_host += 1
+        self.slot_base = self.slot_host
         self.n_prox += 1
         if self.slot_host >= LOG_CHUNK:
             self._reset_logs()
@@ -176,15 +181,16 @@ class Engine:
         self.sig_log.zero_()
         self.counters[0:1].zero_()
         self.slot_host = 0
+        self.slot_base = 0
 
     def flush_fast(self):
         """fast mode: read back every slot written since the last flush."""
         self.stream.synchronize()
-        n = self.slot_host
-        if n == 0:
+        lo, n = self.slot_base, self.slot_host
+        if n == lo:
             return []
-        mse = self.mse_log[:n].cpu().numpy()
-        sig = self.sig_log[:n].cpu().numpy()
+        mse = self.mse_log[lo:n].cpu().numpy()
+        sig = self.sig_log[lo:n].cpu().numpy()
         self.sig_hist.extend(list(sig / self.W))
         with torch.cuda.stream(self.stream):
             self._reset_logs()
@@ -249,3 +255,47 @@ def stop_rule(start_psnr, last_psnr, converge_check, diverge_check):
     if diverge_check is True and last_psnr < 0:
         return True
     return False
+
+
+# ---------------------------------------------------------------------------------------------
+# Host twin of the device minibatch sampler (csrc/csmri.cuh::feistel_perm): the same keyed
+# cycle-walking Feistel permutation, vectorised in NumPy.  O(B) instead of the O(M0) permutation
+# behind np.random.choice(..., replace=False); used by mb_source='host'.
+def _mix32(x):
+    x = x.astype(np.uint32)
+    x ^= x >> np.uint32(16)
+    x = (x * np.uint32(0x7feb352d)).astype(np.uint32)
+    x ^= x >> np.uint32(15)
+    x = (x * np.uint32(0x846ca68b)).astype(np.uint32)
+    x ^= x >> np.uint32(16)
+    return x
+
+
+def feistel_key(seed, counter, img=0):
+    with np.errstate(over='ignore'):
+        c = _mix32(np.array([(np.uint64(counter) * np.uint64(0x632be5ab) + np.uint64(img)) & np.uint64(0xffffffff)],
+                            dtype=np.uint64).astype(np.uint32))
+        return int(_mix32(np.uint32(seed & 0xffffffff) ^ c)[0])
+
+
+def feistel_sample(n, count, seed, counter, img=0):
+    """positions feistel_perm(i, n, key) for i in [0, count) -- `count` distinct values in [0, n)."""
+    hb = 1
+    while (1 << (2 * hb)) < n:
+        hb += 1
+    hm = np.uint32((1 << hb) - 1)
+    key = np.uint32(feistel_key(seed, counter, img))
+    x = np.arange(count, dtype=np.uint32)
+    out = np.empty(count, dtype=np.uint32)
+    pending = np.arange(count)
+    with np.errstate(over='ignore'):
+        while pending.size:
+            l, r = x >> np.uint32(hb), x & hm
+            for rd in range(4):
+                f = _mix32(r ^ np.uint32((int(key) + 0x9e3779b9 * (rd + 1)) & 0xffffffff)) & hm
+                l, r = r, l ^ f
+            x = (l << np.uint32(hb)) | r
+            ok = x < np.uint32(n)
+            out[pending[ok]] = x[ok]
+            pending, x = pending[~ok], x[~ok]
+    return out.astype(np.int64)

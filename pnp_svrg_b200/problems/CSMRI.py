@@ -92,7 +92,7 @@ class CSMRI(Problem):
                                                     D.ptr(counter), D.ptr(idx_out), 1, D.stream()))
 
     def _dev_grad(self, a, b=None, sel=None, with_y=True, gscale=1.0, gscale_ptr=None, step=0.0, step_ptr=None,
-                  g_out=None, vadd=None, v_out=None, z_in=None, z_out=None):
+                  g_out=None, vadd=None, v_out=None, z_in=None, z_out=None, phases=0):
         """g = Re(ifft2(sel o fft2(a - b) - Ysel)) * gscale ; v = g + vadd ; z_out = z_in - step*v."""
         args = _lib.CsmriGradArgs(
             H=self.H, W=self.W, batch=1, a=D.ptr(a), b=D.ptr(b), S=D.ptr(self._S),
@@ -100,7 +100,7 @@ class CSMRI(Problem):
             Y1=D.ptr(self._Y1) if with_y else None, Y2=D.ptr(self._Y2) if with_y else None,
             Y1n=D.ptr(self._Y1n) if with_y else None, Y2n=D.ptr(self._Y2n) if with_y else None,
             gscale=float(gscale), gscale_ptr=D.ptr(gscale_ptr), step=float(step), step_ptr=D.ptr(step_ptr),
-            g_out=D.ptr(g_out), vadd=D.ptr(vadd), v_out=D.ptr(v_out), z_in=D.ptr(z_in), z_out=D.ptr(z_out))
+            g_out=D.ptr(g_out), vadd=D.ptr(vadd), v_out=D.ptr(v_out), z_in=D.ptr(z_in), z_out=D.ptr(z_out), phases=int(phases))
         _lib.check(_lib.load().pnp_csmri_grad(C.byref(args), D.stream()))
 
     # ---- reference API ---------------------------------------------------------------------

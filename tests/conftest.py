@@ -31,8 +31,10 @@ def synth_image(H, W, seed=0):
 
 
 def rel_l2(a, b):
-    a = np.asarray(a, dtype=np.float64).ravel()
-    b = np.asarray(b, dtype=np.float64).ravel()
+    a = np.asarray(a).ravel()
+    b = np.asarray(b).ravel()
+    a = a.astype(np.complex128 if np.iscomplexobj(a) or np.iscomplexobj(b) else np.float64)
+    b = b.astype(a.dtype)
     return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300))
 
 

@@ -66,7 +66,8 @@ def test_grad_stoch_special_frequencies(cuda):
             mb[r, c] = 1
         g_ref = ref.grad_stoch(z, mb)
         err = np.linalg.norm(dut.grad_stoch(z, mb) - g_ref) / np.linalg.norm(g_ref)
-        assert err < 5e-6, (pts, err)
+        # a single coefficient is a difference of O(N) sums: fp32 cancellation, logic errors are O(1)
+        assert err < 3e-4, (pts, err)
 
 
 def test_full_support_identity(cuda):
