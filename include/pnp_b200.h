@@ -49,8 +49,8 @@ typedef struct {
     const float* a;               /* [batch][W][H] */
     const float* b;               /* optional: transform a - b (SVRG/SARAH difference, Y cancels) */
     float* S;                     /* scratch, batch*W*H floats (packed half spectrum, complex64) */
-    const unsigned char* bits;    /* selection bits [batch][W][H/2], see pnp_csmri_sel_* */
-    const float* Y1;              /* optional complex64 [batch][W][H/2]: (mask o Y)[kyp][kx]        */
+    const unsigned char* bits;    /* selection bits [batch][H/2][W], see pnp_csmri_sel_* */
+    const float* Y1;              /* optional complex64 [batch][H/2][W]: (mask o Y)[kyp][kx]        */
     const float* Y2;              /*                                     conj (mask o Y)[-kyp][-kx]  */
     const float* Y1n;             /* optional complex64 [batch][W]: Nyquist row (mask o Y)[H/2][kx] */
     const float* Y2n;             /*                                conj (mask o Y)[H/2][-kx]       */

@@ -10,7 +10,8 @@
 // lines, and fft2 of the transpose is the transpose of fft2.
 //
 //   pass 1  k_lines_r2c   two real lines -> one complex FFT of length H (two-for-one), unpacked
-//                         to the packed half spectrum S[kx'][kyp], kyp in [0, H/2): the real
+//                         to the packed half spectrum, stored TRANSPOSED as S[kyp][c], kyp in
+//                         [0, H/2), c = line: the column pass then reads contiguous rows.  The real
 //                         Nyquist term (ky = H/2) rides in the imaginary slot of the real DC term.
 //                         Input may be a difference a - b (g_B(z) - g_B(w) is linear, Y cancels).
 //   pass 2  k_cols_mask   per packed ky column: FFT over the W lines, multiply by the
@@ -40,18 +41,27 @@ struct GradEpilogue {
 };
 
 // ------------------------------------------------------------------ pass 1
+// group stride (floats) of the per-pair exchange buffers: 2 planes, skewed so that GP groups read
+// at the same in-plane index hit different banks
+template <int L, int GP> __host__ __device__ constexpr int group_stride() {
+    return 2 * fft_plane<L>() + ((GP > 1 ? 32 / GP : 0) - (2 * fft_plane<L>()) % 32 + 32) % 32;
+}
+
 template <int L, int GP>
 __global__ void __launch_bounds__(GP * (L / FftPlan<L>::EPT))
 k_lines_r2c(const float* __restrict__ a, const float* __restrict__ b, float2* __restrict__ S,
             int nlines, long long img_stride) {
     constexpr int T = fft_threads<L>();
     constexpr int PL = fft_plane<L>();
+    constexpr int GS = group_stride<L, GP>();
     extern __shared__ float smem[];
     const int g = threadIdx.x / T, t = threadIdx.x % T;
-    const int pair = blockIdx.x * GP + g;
+    const int pair0 = blockIdx.x * GP;
+    const int pair = pair0 + g;
     const bool active = 2 * pair < nlines;
-    const long long base = (long long)blockIdx.y * img_stride + (long long)(2 * pair) * L;
-    const SmemBuf sb{smem + g * 2 * PL, smem + g * 2 * PL + PL};
+    const long long ibase = (long long)blockIdx.y * img_stride;
+    const long long base = ibase + (long long)(2 * pair) * L;
+    const SmemBuf sb{smem + g * GS, smem + g * GS + PL};
     const float* a0 = a + base;
     const float* b0 = b ? b + base : nullptr;
     auto ld = [&](int idx) -> float2 {
@@ -63,27 +73,28 @@ k_lines_r2c(const float* __restrict__ a, const float* __restrict__ b, float2* __
     auto st = [&](int idx, float2 v) { sb.put(idx, v); };
     fft_forward<L, false>(t, sb, ld, st);
     __syncthreads();
-    if (!active) return;
-    float2* SA = S + (base >> 1);          // line 2*pair, L/2 complex per line
-    float2* SB = SA + L / 2;
-    for (int k = t; k < L / 2; k += T) {
-        const float2 xk = sb.get(k);
-        const float2 xm = sb.get(k == 0 ? L / 2 : L - k);
-        float2 A, B;
+    // unpack the two real transforms; S[kyp][c]: the GP pairs of this CTA write 2*GP adjacent
+    // complex values (16 bytes per pair) of row kyp
+    float4* S4 = reinterpret_cast<float4*>(S + (ibase >> 1)) + pair0;
+    const int W2 = nlines >> 1;                     // float4 per spectrum row
+    for (int i = threadIdx.x; i < GP * (L / 2); i += GP * T) {
+        const int gg = i % GP, k = i / GP;
+        if (2 * (pair0 + gg) >= nlines) continue;
+        const SmemBuf sg{smem + gg * GS, smem + gg * GS + PL};
+        const float2 xk = sg.get(k);
+        const float2 xm = sg.get(k == 0 ? L / 2 : L - k);
+        float4 o;
         if (k == 0) {
-            A = make_float2(xk.x, xm.x);   // (DC, Nyquist) of line 2*pair
-            B = make_float2(xk.y, xm.y);
+            o = make_float4(xk.x, xm.x, xk.y, xm.y);           // A = (DC, Nyquist) line 2p ; B likewise line 2p+1
         } else {
-            A = make_float2(0.5f * (xk.x + xm.x), 0.5f * (xk.y - xm.y));
-            B = make_float2(0.5f * (xk.y + xm.y), 0.5f * (xm.x - xk.x));
+            o = make_float4(0.5f * (xk.x + xm.x), 0.5f * (xk.y - xm.y), 0.5f * (xk.y + xm.y), 0.5f * (xm.x - xk.x));
         }
-        SA[k] = A;
-        SB[k] = B;
+        S4[(long long)k * W2 + gg] = o;
     }
 }
 
 // ------------------------------------------------------------------ pass 2
-// sel bits per packed entry [kx][kyp]:  bit0 = sel[kyp][kx], bit1 = sel[-kyp][-kx];
+// sel bits per packed entry [kyp][kx]:  bit0 = sel[kyp][kx], bit1 = sel[-kyp][-kx];
 // for kyp == 0 additionally bit2 = sel[H/2][kx], bit3 = sel[H/2][-kx] (the packed Nyquist row).
 __device__ __forceinline__ float2 apply_sel(float2 F, unsigned bb, bool use_y, const float2* y1,
                                             const float2* y2) {
@@ -96,8 +107,9 @@ __device__ __forceinline__ float2 apply_sel(float2 F, unsigned bb, bool use_y, c
     return o;
 }
 
-template <int L, int CT>
-__global__ void __launch_bounds__(CT * (L / FftPlan<L>::EPT))
+// One group of T threads per packed column kyp; the column is the contiguous row S[kyp][0..L).
+template <int L, int NC>
+__global__ void __launch_bounds__(NC * (L / FftPlan<L>::EPT))
 k_cols_mask(float2* __restrict__ S, const unsigned char* __restrict__ bits,
             const float2* __restrict__ Y1, const float2* __restrict__ Y2,
             const float2* __restrict__ Y1n, const float2* __restrict__ Y2n,
@@ -106,17 +118,17 @@ k_cols_mask(float2* __restrict__ S, const unsigned char* __restrict__ bits,
     constexpr int EPT = FftPlan<L>::EPT;
     constexpr int PL = fft_plane<L>();
     extern __shared__ float smem[];
-    const int col = threadIdx.x % CT, t = threadIdx.x / CT;
-    const int kyp = blockIdx.x * CT + col;
+    const int g = threadIdx.x / T, t = threadIdx.x % T;
+    const int kyp = blockIdx.x * NC + g;
     const int img = blockIdx.y;
-    const SmemBuf sb{smem + col * 2 * PL, smem + col * 2 * PL + PL};
-    float2* Sc = S + (long long)img * L * hp + kyp;
-    const unsigned char* bc = bits + (long long)img * bits_img_stride + kyp;
+    const SmemBuf sb{smem + g * 2 * PL, smem + g * 2 * PL + PL};
+    float2* Sc = S + ((long long)img * hp + kyp) * L;
+    const unsigned char* bc = bits + (long long)img * bits_img_stride + (long long)kyp * L;
     const bool use_y = Y1 != nullptr;
-    const float2* y1c = use_y ? Y1 + (long long)img * y_img_stride + kyp : nullptr;
-    const float2* y2c = use_y ? Y2 + (long long)img * y_img_stride + kyp : nullptr;
+    const float2* y1c = use_y ? Y1 + (long long)img * y_img_stride + (long long)kyp * L : nullptr;
+    const float2* y2c = use_y ? Y2 + (long long)img * y_img_stride + (long long)kyp * L : nullptr;
 
-    auto ld = [&](int idx) -> float2 { return Sc[(long long)idx * hp]; };
+    auto ld = [&](int idx) -> float2 { return Sc[idx]; };
     auto st = [&](int idx, float2 v) { sb.put(idx, v); };
     fft_forward<L, false>(t, sb, ld, st);
     __syncthreads();
@@ -125,8 +137,7 @@ k_cols_mask(float2* __restrict__ S, const unsigned char* __restrict__ bits,
 #pragma unroll 4
         for (int m = 0; m < EPT; ++m) {
             const int kx = t + m * T;
-            const long long e = (long long)kx * hp;
-            const float2 o = apply_sel(sb.get(kx), bc[e], use_y, y1c + e, y2c + e);
+            const float2 o = apply_sel(sb.get(kx), bc[kx], use_y, y1c + kx, y2c + kx);
             sb.put(kx, cswap(o));
         }
     } else {
@@ -138,11 +149,10 @@ k_cols_mask(float2* __restrict__ S, const unsigned char* __restrict__ bits,
             const float2 ck = sb.get(kx), cm = sb.get(km);
             const float2 fdc = make_float2(0.5f * (ck.x + cm.x), 0.5f * (ck.y - cm.y));
             const float2 fny = make_float2(0.5f * (ck.y + cm.y), 0.5f * (cm.x - ck.x));
-            const long long ek = (long long)kx * hp, em = (long long)km * hp;
-            const unsigned bk = bc[ek], bm = bc[em];
-            const float2 dk = apply_sel(fdc, bk, use_y, y1c + ek, y2c + ek);
+            const unsigned bk = bc[kx], bm = bc[km];
+            const float2 dk = apply_sel(fdc, bk, use_y, y1c + kx, y2c + kx);
             const float2 nk = apply_sel(fny, bk >> 2, use_y, y1n + kx, y2n + kx);
-            const float2 dm = apply_sel(make_float2(fdc.x, -fdc.y), bm, use_y, y1c + em, y2c + em);
+            const float2 dm = apply_sel(make_float2(fdc.x, -fdc.y), bm, use_y, y1c + km, y2c + km);
             const float2 nm = apply_sel(make_float2(fny.x, -fny.y), bm >> 2, use_y, y1n + km, y2n + km);
             // C'[k] = dc[k] + i * ny[k], stored re/im swapped for the inverse transform
             sb.put(kx, make_float2(dk.y + nk.x, dk.x - nk.y));
@@ -151,7 +161,7 @@ k_cols_mask(float2* __restrict__ S, const unsigned char* __restrict__ bits,
     }
     __syncthreads();
     auto ld2 = [&](int idx) -> float2 { return sb.get(idx); };
-    auto st2 = [&](int idx, float2 v) { Sc[(long long)idx * hp] = cswap(v); };
+    auto st2 = [&](int idx, float2 v) { Sc[idx] = cswap(v); };
     fft_forward<L, true>(t, sb, ld2, st2);
 }
 
@@ -163,22 +173,27 @@ k_lines_c2r(const float2* __restrict__ S, int nlines, long long img_stride, floa
     constexpr int PL = fft_plane<L>();
     extern __shared__ float smem[];
     const int g = threadIdx.x / T, t = threadIdx.x % T;
-    const int pair = blockIdx.x * GP + g;
+    constexpr int GS = group_stride<L, GP>();
+    const int pair0 = blockIdx.x * GP;
+    const int pair = pair0 + g;
     const bool active = 2 * pair < nlines;
     const int img = blockIdx.y;
     const long long base = (long long)img * img_stride + (long long)(2 * pair) * L;
-    const SmemBuf sb{smem + g * 2 * PL, smem + g * 2 * PL + PL};
-    if (active) {
-        const float2* SA = S + (base >> 1);
-        const float2* SB = SA + L / 2;
-        for (int k = t; k < L / 2; k += T) {
-            const float2 A = SA[k], B = SB[k];
+    const SmemBuf sb{smem + g * GS, smem + g * GS + PL};
+    {
+        const float4* S4 = reinterpret_cast<const float4*>(S + (((long long)img * img_stride) >> 1)) + pair0;
+        const int W2 = nlines >> 1;
+        for (int i = threadIdx.x; i < GP * (L / 2); i += GP * T) {
+            const int gg = i % GP, k = i / GP;
+            if (2 * (pair0 + gg) >= nlines) continue;
+            const SmemBuf sg{smem + gg * GS, smem + gg * GS + PL};
+            const float4 q = S4[(long long)k * W2 + gg];          // A = (q.x, q.y) line 2p ; B = (q.z, q.w) line 2p+1
             if (k == 0) {
-                sb.put(0, make_float2(B.x, A.x));           // X[0]   = A_dc + i B_dc   (swapped)
-                sb.put(L / 2, make_float2(B.y, A.y));       // X[L/2] = A_ny + i B_ny   (swapped)
+                sg.put(0, make_float2(q.z, q.x));                  // X[0]   = A_dc + i B_dc   (swapped)
+                sg.put(L / 2, make_float2(q.w, q.y));              // X[L/2] = A_ny + i B_ny   (swapped)
             } else {
-                sb.put(k, make_float2(A.y + B.x, A.x - B.y));       // X[k]   = A + iB
-                sb.put(L - k, make_float2(B.x - A.y, A.x + B.y));   // X[L-k] = conj A + i conj B
+                sg.put(k, make_float2(q.y + q.z, q.x - q.w));      // X[k]   = A + iB
+                sg.put(L - k, make_float2(q.z - q.y, q.x + q.w));  // X[L-k] = conj A + i conj B
             }
         }
     }
@@ -213,10 +228,10 @@ __device__ __forceinline__ void set_sel_bits(unsigned char* bits, int H, int W, 
     const int ky = k / W, kx = k % W;
     const int hp = H / 2;
     const int kym = (H - ky) % H, kxm = (W - kx) % W;
-    if (ky < hp) or_byte(bits, (long long)kx * hp + ky, 1u);
-    else if (ky == hp) or_byte(bits, (long long)kx * hp, 4u);
-    if (kym < hp) or_byte(bits, (long long)kxm * hp + kym, 2u);
-    else if (kym == hp) or_byte(bits, (long long)kxm * hp, 8u);
+    if (ky < hp) or_byte(bits, (long long)ky * W + kx, 1u);
+    else if (ky == hp) or_byte(bits, kx, 4u);
+    if (kym < hp) or_byte(bits, (long long)kym * W + kxm, 2u);
+    else if (kym == hp) or_byte(bits, kxm, 8u);
 }
 
 // explicit minibatch:  idx[img][cursor][0..B)

@@ -45,17 +45,19 @@ int check_init() {
 
 // ---- per-size launch geometry ------------------------------------------------------------
 template <int L> constexpr int lines_gp() {            // line pairs per CTA in passes 1 and 3
-    return pnp::fft_threads<L>() >= 128 ? 1 : (pnp::fft_threads<L>() >= 64 ? 2 : (128 / pnp::fft_threads<L>() > 8 ? 8 : 128 / pnp::fft_threads<L>()));
+    return pnp::fft_threads<L>() >= 256 ? 1 : (pnp::fft_threads<L>() >= 128 ? 2 : 4);
 }
-template <int L> constexpr int cols_ct() { return 4; }  // packed columns per CTA in pass 2
-template <int L> constexpr size_t lines_smem() { return sizeof(float) * 2 * pnp::fft_plane<L>() * lines_gp<L>(); }
-template <int L> constexpr size_t cols_smem() { return sizeof(float) * 2 * pnp::fft_plane<L>() * cols_ct<L>(); }
+template <int L> constexpr int cols_nc() {             // packed columns per CTA in pass 2
+    return pnp::fft_threads<L>() >= 128 ? 1 : (pnp::fft_threads<L>() >= 64 ? 2 : (64 / pnp::fft_threads<L>() > 8 ? 8 : 64 / pnp::fft_threads<L>()));
+}
+template <int L> constexpr size_t lines_smem() { return sizeof(float) * pnp::group_stride<L, lines_gp<L>()>() * lines_gp<L>(); }
+template <int L> constexpr size_t cols_smem() { return sizeof(float) * 2 * pnp::fft_plane<L>() * cols_nc<L>(); }
 
 template <int L>
 int set_attrs() {
     CU_TRY(cudaFuncSetAttribute(pnp::k_lines_r2c<L, lines_gp<L>()>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lines_smem<L>()));
     CU_TRY(cudaFuncSetAttribute(pnp::k_lines_c2r<L, lines_gp<L>()>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lines_smem<L>()));
-    CU_TRY(cudaFuncSetAttribute(pnp::k_cols_mask<L, cols_ct<L>()>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cols_smem<L>()));
+    CU_TRY(cudaFuncSetAttribute(pnp::k_cols_mask<L, cols_nc<L>()>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cols_smem<L>()));
     cudaFuncAttributes fa;
     CU_TRY(cudaFuncGetAttributes(&fa, pnp::k_sigma_mad<L>));
     CU_TRY(cudaFuncGetAttributes(&fa, pnp::k_haar_bayes<L>));
@@ -75,10 +77,10 @@ int launch_r2c(const pnp_csmri_grad_args& a, cudaStream_t st) {
 
 template <int L>
 int launch_cols(const pnp_csmri_grad_args& a, cudaStream_t st) {
-    constexpr int CT = cols_ct<L>();
+    constexpr int NC = cols_nc<L>();
     const int hp = a.H / 2;
-    dim3 grid(hp / CT, a.batch);
-    pnp::k_cols_mask<L, CT><<<grid, CT * pnp::fft_threads<L>(), cols_smem<L>(), st>>>(
+    dim3 grid(hp / NC, a.batch);
+    pnp::k_cols_mask<L, NC><<<grid, NC * pnp::fft_threads<L>(), cols_smem<L>(), st>>>(
         reinterpret_cast<float2*>(a.S), a.bits, reinterpret_cast<const float2*>(a.Y1),
         reinterpret_cast<const float2*>(a.Y2), reinterpret_cast<const float2*>(a.Y1n),
         reinterpret_cast<const float2*>(a.Y2n), hp, (long long)a.W * hp, (long long)a.W * hp);
@@ -131,8 +133,10 @@ int dispatch_sigma(int n, const float* z, int W, int batch, double* sig_log, con
 template <int L>
 int launch_haar(const float* zin, float* zout, const float* xrec, int W, int batch, pnp::ShrinkParams sp,
                 double* mse_log, const int* slot, cudaStream_t st) {
-    dim3 grid((W + 3) / 4, batch);
-    pnp::k_haar_bayes<L><<<grid, 128, 0, st>>>(zin, zout, xrec, W, (long long)L * W, sp, mse_log, slot, batch);
+    constexpr int WPL = pnp::HaarCfg<L>::WPL;           // warps per line
+    constexpr int LPB = WPL >= 4 ? 1 : 4 / WPL;         // lines per CTA
+    dim3 grid((W + LPB - 1) / LPB, batch);
+    pnp::k_haar_bayes<L><<<grid, 32 * WPL * LPB, 0, st>>>(zin, zout, xrec, W, (long long)L * W, sp, mse_log, slot, batch);
     LAUNCH_CHECK();
     return PNP_OK;
 }

@@ -99,21 +99,37 @@ struct ShrinkParams {
     float fallback_sigma;       // denoise_strength * decay**t, used when sigma_est <= 0 or NaN
 };
 
+// VPL consecutive samples per lane; a line of L samples is spread over WPL warps.  The first
+// log2(VPL) levels stay inside a lane, the remaining XL levels are butterflies between lanes of
+// one warp (shuffles); only the per-level sum of squares crosses warps (shared memory).
+template <int L> struct HaarCfg {
+    static constexpr int VPL = L >= 512 ? 16 : L / 32;
+    static constexpr int WPL = L / (32 * VPL);
+    static constexpr int LIN = VPL == 1 ? 0 : VPL == 2 ? 1 : VPL == 4 ? 2 : VPL == 8 ? 3 : 4;
+    static constexpr int LOG2L = L == 32 ? 5 : L == 64 ? 6 : L == 128 ? 7 : L == 256 ? 8 : L == 512 ? 9
+                                 : L == 1024 ? 10 : L == 2048 ? 11 : 12;
+    static constexpr int LEVELS = LOG2L - 3;            // skimage skips the 3 coarsest scales
+    static constexpr int XL = LEVELS - LIN;             // cross-lane levels (2..5)
+};
+
 template <int L>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(HaarCfg<L>::WPL >= 4 ? 32 * HaarCfg<L>::WPL : 128)
 k_haar_bayes(const float* __restrict__ zin, float* __restrict__ zout, const float* __restrict__ xrec,
              int nlines, long long img_stride, ShrinkParams sp, double* __restrict__ mse_log,
              const int* __restrict__ slot, int batch) {
-    constexpr int VPL = L / 32;                 // consecutive samples per lane
-    constexpr int LIN = (VPL == 1) ? 0 : (VPL == 2) ? 1 : (VPL == 4) ? 2 : (VPL == 8) ? 3 : (VPL == 16) ? 4
-                        : (VPL == 32) ? 5 : (VPL == 64) ? 6 : 7;     // in-lane levels
-    constexpr int LEVELS = LIN + 2;             // = log2(L) - 3  (skimage skips the 3 coarsest)
+    using C = HaarCfg<L>;
+    constexpr int VPL = C::VPL, WPL = C::WPL, LIN = C::LIN, LEVELS = C::LEVELS, XL = C::XL;
+    constexpr int LPB = WPL >= 4 ? 1 : 4 / WPL;          // lines per CTA
     constexpr float RS2 = 0.70710678118654752f;
+    __shared__ float s_ss[LPB][LEVELS][WPL];
+    __shared__ float s_err[LPB][WPL];
     const int lane = threadIdx.x & 31;
-    const int line = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int warp = threadIdx.x >> 5;
+    const int lib = warp / WPL, wil = warp % WPL;          // line in block, warp in line
+    const int line = blockIdx.x * LPB + lib;
     const int img = blockIdx.y;
-    if (line >= nlines) return;
-    const long long off = (long long)img * img_stride + (long long)line * L + lane * VPL;
+    const bool active = line < nlines;
+    const long long off = (long long)img * img_stride + (long long)(active ? line : 0) * L + (wil * 32 + lane) * VPL;
 
     float x[VPL];
     if (VPL >= 4) {
@@ -149,30 +165,48 @@ k_haar_bayes(const float* __restrict__ zin, float* __restrict__ zout, const floa
             ss[lv - 1] = fmaf(d, d, ss[lv - 1]);
         }
     }
-    const float a0 = x[0];
-    const float p1 = __shfl_xor_sync(0xffffffffu, a0, 1);
-    const bool ev1 = (lane & 1) == 0;
-    const float A1 = (a0 + p1) * RS2;
-    const float D1 = (ev1 ? (a0 - p1) : (p1 - a0)) * RS2;
-    ss[LIN] = ev1 ? D1 * D1 : 0.f;
-    const float p2 = __shfl_xor_sync(0xffffffffu, A1, 2);
-    const bool ev2 = (lane & 2) == 0;
-    const float A2 = (A1 + p2) * RS2;
-    const float D2 = (ev2 ? (A1 - p2) : (p2 - A1)) * RS2;
-    ss[LIN + 1] = (lane & 3) == 0 ? D2 * D2 : 0.f;
+    float A[XL + 1], Dx[XL];
+    A[0] = x[0];
+#pragma unroll
+    for (int q = 0; q < XL; ++q) {
+        const float p = __shfl_xor_sync(0xffffffffu, A[q], 1 << q);
+        const bool ev = (lane & (1 << q)) == 0;
+        A[q + 1] = (A[q] + p) * RS2;
+        Dx[q] = (ev ? (A[q] - p) : (p - A[q])) * RS2;
+        ss[LIN + q] = (lane & ((2 << q) - 1)) == 0 ? Dx[q] * Dx[q] : 0.f;
+    }
 
     float thr[LEVELS];
 #pragma unroll
+    for (int l = 0; l < LEVELS; ++l) ss[l] = warp_sum_f(ss[l]);
+    if (WPL > 1) {
+        if (lane == 0) {
+#pragma unroll
+            for (int l = 0; l < LEVELS; ++l) s_ss[lib][l][wil] = ss[l];
+        }
+        __syncthreads();
+#pragma unroll
+        for (int l = 0; l < LEVELS; ++l) {
+            float t = 0.f;
+#pragma unroll
+            for (int w = 0; w < WPL; ++w) t += s_ss[lib][l][w];
+            ss[l] = t;
+        }
+    }
+#pragma unroll
     for (int l = 0; l < LEVELS; ++l) {
-        const float dvar = warp_sum_f(ss[l]) / (float)(L >> (l + 1));
+        const float dvar = ss[l] / (float)(L >> (l + 1));
         thr[l] = var / sqrtf(fmaxf(dvar - var, 2.220446049250313e-16f));
     }
 
     // inverse pyramid with soft-thresholded details
-    const float D2t = soft_shrink(D2, thr[LIN + 1]);
-    const float A1r = (ev2 ? (A2 + D2t) : (A2 - D2t)) * RS2;
-    const float D1t = soft_shrink(D1, thr[LIN]);
-    x[0] = (ev1 ? (A1r + D1t) : (A1r - D1t)) * RS2;
+#pragma unroll
+    for (int q = XL - 1; q >= 0; --q) {
+        const float d = soft_shrink(Dx[q], thr[LIN + q]);
+        const bool ev = (lane & (1 << q)) == 0;
+        A[q] = (ev ? (A[q + 1] + d) : (A[q + 1] - d)) * RS2;
+    }
+    x[0] = A[0];
 #pragma unroll
     for (int lv = LIN; lv >= 1; --lv) {
         const int stride = 1 << lv, half = stride >> 1;
@@ -186,26 +220,28 @@ k_haar_bayes(const float* __restrict__ zin, float* __restrict__ zout, const floa
     }
 
     float err = 0.f;
-    if (VPL >= 4) {
+    if (active) {
+        if (VPL >= 4) {
 #pragma unroll
-        for (int i = 0; i < VPL / 4; ++i) {
-            reinterpret_cast<float4*>(zout + off)[i] = make_float4(x[4 * i], x[4 * i + 1], x[4 * i + 2], x[4 * i + 3]);
-            if (xrec) {
-                const float4 r = reinterpret_cast<const float4*>(xrec + off)[i];
-                const float e0 = x[4 * i] - r.x, e1 = x[4 * i + 1] - r.y, e2 = x[4 * i + 2] - r.z, e3 = x[4 * i + 3] - r.w;
-                err += e0 * e0 + e1 * e1 + e2 * e2 + e3 * e3;
+            for (int i = 0; i < VPL / 4; ++i) {
+                reinterpret_cast<float4*>(zout + off)[i] = make_float4(x[4 * i], x[4 * i + 1], x[4 * i + 2], x[4 * i + 3]);
+                if (xrec) {
+                    const float4 r = reinterpret_cast<const float4*>(xrec + off)[i];
+                    const float e0 = x[4 * i] - r.x, e1 = x[4 * i + 1] - r.y, e2 = x[4 * i + 2] - r.z, e3 = x[4 * i + 3] - r.w;
+                    err += e0 * e0 + e1 * e1 + e2 * e2 + e3 * e3;
+                }
             }
-        }
-    } else {
+        } else {
 #pragma unroll
-        for (int i = 0; i < VPL; ++i) {
-            zout[off + i] = x[i];
-            if (xrec) { const float e = x[i] - xrec[off + i]; err = fmaf(e, e, err); }
+            for (int i = 0; i < VPL; ++i) {
+                zout[off + i] = x[i];
+                if (xrec) { const float e = x[i] - xrec[off + i]; err = fmaf(e, e, err); }
+            }
         }
     }
     if (xrec && mse_log) {
         err = warp_sum_f(err);
-        if (lane == 0) atomicAdd(slot_ptr(mse_log, slot, batch, img), (double)err);
+        if (lane == 0 && active) atomicAdd(slot_ptr(mse_log, slot, batch, img), (double)err);
     }
 }
 

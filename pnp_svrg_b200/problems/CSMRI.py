@@ -63,8 +63,8 @@ class CSMRI(Problem):
         def up(a):
             t = torch.from_numpy(np.ascontiguousarray(a).astype(np.complex64)).to(dev)
             return torch.view_as_real(t).contiguous()
-        self._Y1 = up(Ym[:hp, :].T)             # [kx][kyp]
-        self._Y2 = up(Ymir[:hp, :].T)
+        self._Y1 = up(Ym[:hp, :])               # [kyp][kx]
+        self._Y2 = up(Ymir[:hp, :])
         self._Y1n = up(Ym[hp, :])
         self._Y2n = up(Ymir[hp, :])
         self._support_host = np.flatnonzero(self.mask).astype(np.int32)

@@ -1,0 +1,110 @@
+"""CPU: the C-ABI library loads and exports every symbol include/pnp_b200.h declares (no compute
+calls without a GPU); host-side logic (minibatch container, sampler twin, budgets)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    src = open(os.path.join(ROOT, 'include', 'pnp_b200.h')).read()
+    src = re.sub(r'/\*.*?\*/', '', src, flags=re.S)
+    return sorted(set(re.findall(r'\b(pnp_[a-z0-9_]+)\s*\(', src)))
+
+
+def test_header_symbols_exported_and_bound():
+    import __graft_entry__ as g
+    g.build()
+    from pnp_svrg_b200 import _lib
+    names = _declared()
+    assert len(names) >= 18
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for n in names:
+        assert hasattr(lib, n), 'library does not export %s' % n
+        assert n in _lib.PROTOTYPES, 'ctypes prototype missing for %s' % n
+    assert set(_lib.PROTOTYPES) == set(names)
+    assert _lib.load().pnp_version() >= 100
+    # the args struct mirrors the header field for field
+    hdr = open(os.path.join(ROOT, 'include', 'pnp_b200.h')).read()
+    body = re.sub(r'/\*.*?\*/', '', hdr[hdr.index('typedef struct {'):hdr.index('} pnp_csmri_grad_args;')], flags=re.S)
+    fields = [f for stmt in body.split(';') for f in re.findall(r'[\*\s,]([A-Za-z_][A-Za-z0-9_]*)\s*(?=,|$)', stmt.strip())]
+    assert fields == [f[0] for f in _lib.CsmriGradArgs._fields_], fields
+
+
+def test_no_gpu_means_loud_failure():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip('has a GPU')
+    from pnp_svrg_b200 import _lib
+    from pnp_svrg_b200.problems import CSMRI
+    with pytest.raises(_lib.PnpError):
+        CSMRI(image=np.zeros((32, 32), np.uint8) + np.arange(32, dtype=np.uint8), H=32, W=32)
+
+
+def test_product_never_imports_oracle():
+    bad = []
+    for dirpath, _, files in os.walk(os.path.join(ROOT, 'pnp_svrg_b200')):
+        for f in files:
+            if f.endswith('.py') and re.search(r'^\s*(from|import)\s+oracle\b', open(os.path.join(dirpath, f)).read(), re.M):
+                bad.append(f)
+    assert not bad, bad
+
+
+def test_minibatch_container():
+    from pnp_svrg_b200.problems.problem import MiniBatch
+    dense = np.zeros(16, dtype=int)
+    dense[[3, 7]] = 1
+    mb = MiniBatch(dense.reshape(4, 4), [3, 7])
+    assert mb.shape == (4, 4) and list(mb.indices) == [3, 7]
+    assert list(mb.ravel().indices) == [3, 7]
+    assert list((np.ones((4, 4), dtype=int) * mb).indices) == [3, 7]
+    assert mb[:2].indices is None
+    assert int(np.asarray(mb).sum()) == 2
+
+
+def test_feistel_sampler_host():
+    from pnp_svrg_b200.engine import feistel_sample
+    for n, c in [(1, 1), (5, 5), (1234, 200), (19575, 1000), (70000, 70000)]:
+        a = feistel_sample(n, c, seed=9, counter=3)
+        assert a.shape == (c,) and a.min() >= 0 and a.max() < n and len(np.unique(a)) == c
+    a = feistel_sample(19575, 1000, 9, 3)
+    assert not np.array_equal(a, feistel_sample(19575, 1000, 9, 4))
+    assert np.array_equal(a, feistel_sample(19575, 1000, 9, 3))
+    # roughly uniform: mean position near n/2
+    m = np.mean([feistel_sample(10000, 500, 1, k).mean() for k in range(40)])
+    assert abs(m - 5000) < 150
+
+
+def test_budget_and_stop_rule():
+    from pnp_svrg_b200.engine import Budget, stop_rule
+    b = Budget(1e9, 3)
+    assert b.alive() and b.left() == 3
+    b.calls = 3
+    assert not b.alive()
+    assert not Budget(0.0, None).alive()
+    assert stop_rule(12.34, 12.34, True, False) and not stop_rule(12.34, 12.35, True, False)
+    assert stop_rule(1.0, -0.01, False, True) and not stop_rule(1.0, -0.01, False, False)
+
+
+def test_reference_names_alias():
+    import sys
+    import pnp_svrg_b200
+    saved = {k: sys.modules.get(k) for k in ('problems', 'denoisers', 'algorithms')}
+    try:
+        for k in saved:
+            sys.modules.pop(k, None)
+        pnp_svrg_b200.install_as_reference()
+        from algorithms import pnp_svrg, tune_pnp_svrg      # noqa: F401
+        from denoisers import TVDenoiser                    # noqa: F401
+        from problems import CSMRI, Deblur, PhaseRetrieval  # noqa: F401
+        from problems.CSMRI import CSMRI as C2
+        assert C2 is CSMRI
+    finally:
+        for k, v in saved.items():
+            sys.modules.pop(k, None)
+            if v is not None:
+                sys.modules[k] = v

@@ -1,0 +1,70 @@
+"""GPU parity against what the REFERENCE itself produced (tests/golden/ref_*.npz): the CUDA path is
+run on the stored inputs with the same seeds and compared with the stored reference outputs --
+no oracle code in between.  Tolerances: north star (rel L2 <= 1e-4 per iterate, PSNR within 0.05 dB)."""
+import glob
+import json
+import os
+
+import numpy as np
+import pytest
+
+from conftest import rel_l2
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
+
+
+def _load(name):
+    d = np.load(os.path.join(GOLD, 'ref_%s.npz' % name), allow_pickle=False)
+    return json.loads(str(d['meta'])), d
+
+
+def _build(meta, d):
+    from pnp_svrg_b200 import problems as P
+    kw = dict(meta['problem_kwargs'])
+    H, W = kw.pop('H'), kw.pop('W')
+    np.random.seed(meta['seed_problem'])
+    if meta['problem'] == 'csmri':
+        return P.CSMRI(image=d['image_u8'], H=H, W=W, **kw)
+    if meta['problem'] == 'deblur':
+        if kw.get('kernel_path'):
+            kw['kernel_path'] = None
+            kw['kernel'] = d['kernel_u8']
+        return P.Deblur(image=d['image_u8'], H=H, W=W, **kw)
+    return P.PhaseRetrieval(image=d['image_u8'], H=H, W=W, **kw)
+
+
+def _denoiser(meta):
+    from pnp_svrg_b200 import denoisers as DN
+    return DN.TVDenoiser() if meta['denoiser'] == 'tv' else DN.NLMDenoiser()
+
+
+CSMRI_CASES = ['csmri64_gd', 'csmri64_sgd', 'csmri64_svrg', 'csmri64_saga', 'csmri64_sarah', 'csmri256_svrg']
+
+
+def _check_case(name, tol=1e-4):
+    from pnp_svrg_b200 import algorithms as ALG
+    meta, d = _load(name)
+    p = _build(meta, d)
+    assert rel_l2(p.Xinit, d['Xinit']) < 1e-6 and p.M == int(d['M'])
+    assert abs(p.sigma - float(d['sigma'])) <= 1e-7 * float(d['sigma'])
+    assert rel_l2(p.grad_full(d['z_rand']), d['grad_full']) < 5e-6
+    mb = np.zeros(p.M, dtype=int)
+    mb[d['mb_idx']] = 1
+    if meta['problem'] == 'csmri':
+        mb = mb.reshape(p.H, p.W)
+    assert rel_l2(p.grad_stoch(d['z_rand'], mb), d['grad_stoch']) < 5e-6
+    np.random.seed(meta['seed_run'])
+    out = getattr(ALG, meta['algo'])(p, _denoiser(meta), tt=1e9, max_iters=meta['budget'], verbose=False,
+                                     converge_check=False, **meta['algo_kwargs'])
+    err = rel_l2(out['z'], d['z_final'])
+    assert err < tol, (name, err)
+    ps = np.array(out['psnr_per_iter'])
+    assert ps.shape == d['psnr'].shape
+    assert np.max(np.abs(ps - d['psnr'])) <= 0.05, (ps, d['psnr'])
+    return out
+
+
+@pytest.mark.parametrize('name', CSMRI_CASES)
+def test_csmri_against_reference_outputs(cuda, name):
+    _check_case(name)

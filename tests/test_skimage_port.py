@@ -1,0 +1,84 @@
+"""CPU: self-checks of the scikit-image / PyWavelets / pylops restatements (parity unpinned:
+those libraries are absent, so only analytic identities and documented values are available)."""
+import numpy as np
+
+from oracle import pylops_port, skimage_port as S
+
+
+def test_haar_known_value_and_perfect_reconstruction():
+    # documented: pywt.dwt([1, 2, 3, 4], 'db1') -> ([2.12132034, 4.94974747], [-0.70710678, -0.70710678])
+    a, d = S._haar_fwd_axis0(np.array([[1.], [2.], [3.], [4.]]))
+    assert np.allclose(a.ravel(), [2.12132034, 4.94974747]) and np.allclose(d.ravel(), [-0.70710678, -0.70710678])
+    rng = np.random.default_rng(0)
+    for n in (32, 64, 100, 101, 256, 37):
+        x = rng.standard_normal((n, 5))
+        assert np.allclose(S.bayes_shrink_columns(x, 0.0), x, atol=1e-12)       # sigma = 0 -> identity
+        big = S.bayes_shrink_columns(x, 50.0)                                   # huge sigma kills all details
+        lv = S.haar_levels(n)
+        assert np.abs(np.diff(big[: (n >> lv) << lv].reshape(-1, 1 << lv, 5), axis=1)).max() < 1e-9 or n % (1 << lv)
+
+
+def test_haar_parseval_and_levels():
+    x = np.random.default_rng(1).standard_normal((256, 3))
+    a, d = S._haar_fwd_axis0(x)
+    assert np.allclose((a ** 2).sum() + (d ** 2).sum(), (x ** 2).sum())
+    assert S.haar_levels(256) == 5 and S.haar_levels(2048) == 8 and S.haar_levels(32) == 2 and S.haar_levels(16) == 1
+
+
+def test_db2_detail_properties():
+    h = S.DB2_DEC_HI
+    assert abs(h.sum()) < 1e-15 and abs((h ** 2).sum() - 1) < 1e-12            # high-pass, unit norm
+    assert abs((h * np.arange(4)[::-1]).sum()) < 1e-12                          # two vanishing moments
+    x = np.random.default_rng(2).standard_normal((256, 4))
+    d = S.dwt_detail_db2_axis0(x)
+    assert d.shape == (129, 4)
+    # interior coefficients are a plain stride-2 correlation
+    o = 10
+    assert np.allclose(d[o], sum(h[j] * x[2 * o + 1 - j] for j in range(4)))
+    # symmetric extension at both ends
+    assert np.allclose(d[0], h[0] * x[1] + h[1] * x[0] + h[2] * x[0] + h[3] * x[1])
+    assert np.allclose(d[128], h[0] * x[254] + h[1] * x[255] + h[2] * x[255] + h[3] * x[254])
+    lin = np.arange(256.)[:, None] * np.ones((1, 2))
+    assert np.abs(S.dwt_detail_db2_axis0(lin)[2:-2]).max() < 1e-10              # kills linear ramps
+
+
+def test_estimate_sigma_on_white_noise_and_masking():
+    rng = np.random.default_rng(3)
+    z = 0.1 * rng.standard_normal((512, 256))
+    s = S.estimate_sigma(z, multichannel=True, average_sigmas=True)
+    assert abs(s - 0.1) < 0.004
+    per = S.estimate_sigma(z, multichannel=True)
+    assert len(per) == 256
+    z[:, 0] = 0
+    assert np.isnan(S.estimate_sigma(z, multichannel=True, average_sigmas=True))
+
+
+def test_psnr():
+    a = np.linspace(0, 1, 64).reshape(8, 8)
+    assert abs(S.peak_signal_noise_ratio(a, a + 0.1) - 20.0) < 1e-9
+    assert abs(S.peak_signal_noise_ratio(a - 0.5, a - 0.4) - (20.0 + 20 * np.log10(2))) < 1e-9  # range 2 if min < 0
+
+
+def test_nlm_basics():
+    rng = np.random.default_rng(4)
+    img = np.tile(np.linspace(0, 1, 24), (24, 1))
+    noisy = img + 0.05 * rng.standard_normal(img.shape)
+    out = S.denoise_nl_means(noisy, patch_size=4, patch_distance=5, h=0.05, sigma=0.05, fast_mode=False)
+    assert out.shape == img.shape
+    assert np.abs(out - img).mean() < np.abs(noisy - img).mean()
+    const = np.full((16, 16), 0.3)
+    assert np.allclose(S.denoise_nl_means(const, patch_size=4, patch_distance=5, h=0.1, sigma=0.0, fast_mode=False), 0.3)
+
+
+def test_bilinear_adjoint_and_values():
+    H = W = 16
+    pts = np.linspace(1e-10, H - 1 - 1e-10, 8)
+    mw, mh = np.meshgrid(pts, pts)
+    op = pylops_port.Bilinear(np.vstack([mh.ravel(), mw.ravel()]), (H, W))
+    rng = np.random.default_rng(5)
+    x, y = rng.standard_normal(H * W), rng.standard_normal(64)
+    assert abs(np.dot(op * x, y) - np.dot(x, op.H * y)) < 1e-10
+    ramp = (np.arange(H)[:, None] * 2.0 + np.arange(W)[None, :] * 3.0).ravel()
+    assert np.allclose(op * ramp, (mh * 2.0 + mw * 3.0).ravel())               # exact on bilinear functions
+    ident = pylops_port.Identity(7)
+    assert np.array_equal(ident * np.arange(7.), np.arange(7.)) and np.array_equal(ident.H * np.arange(7.), np.arange(7.))
