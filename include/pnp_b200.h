@@ -84,6 +84,72 @@ int pnp_csmri_sel_sample(unsigned char* bits, int H, int W, int batch, const int
                          long long support_img_stride, int count, unsigned seed, const int* counter,
                          int* idx_out, int clear, void* stream);
 
+/* Device-drawn minibatch for problems whose measurements are a plain list (Problem.select_mb,
+ * problems/problem.py:110-117): idx_out[0..count) = distinct positions in [0, n). */
+int pnp_sample_indices(int* idx_out, int n, int count, unsigned seed, const int* counter, void* stream);
+
+/* ---- Deblur + super-resolution gradient ------------------------------------------------------
+ * Replaces Deblur.grad_full (problems/DeblurSR.py:126-132), Deblur.grad_stoch (:135-147) and the
+ * same update lines as pnp_csmri_grad:
+ *   x  = fft_blur(a - b, B)                      length-N circular convolution (:119-120)
+ *   r  = S x - y on the selected measurements    (pylops Bilinear / Identity, :95-108)
+ *   g  = fft_blur(S^T r, roll(flip(B), 1)) * gscale ;  v = g + vadd ;  z_out = z_in - step * v
+ * sel = measurement ids [n_sets][count] (set *cursor), null = all M measurements. */
+typedef struct {
+    int H, W, batch;
+    const float* a;
+    const float* b;               /* optional: a - b, then y is ignored (use_y = 0) */
+    float* S;                     /* scratch spectrum, H*W floats per image */
+    float* blurred;               /* scratch image */
+    float* up;                    /* scratch image (S^T r) */
+    const float* Bf;              /* complex64 [H/2+1][W]: fft(B)[k1 + H*k2] * sqrt(N), row H/2 = Nyquist */
+    const float* twn;             /* complex64 [W]: exp(-2 pi i j / (H*W)) */
+    const float* y;               /* [M] measurements */
+    const int* tl;                /* [M][2] top row / left column of the 4-tap footprint (null if identity) */
+    const float* wts;             /* [M][2] weight of the lower row / right column */
+    int identity;                 /* scale_percent == 100 */
+    int M;
+    const int* sel;
+    int count;
+    const int* cursor;
+    int use_y;
+    float gscale;
+    float step;
+    const float* step_ptr;
+    float* g_out;
+    const float* vadd;
+    float* v_out;
+    const float* z_in;
+    float* z_out;
+} pnp_deblur_grad_args;
+int pnp_deblur_grad(const pnp_deblur_grad_args* args, void* stream);
+
+/* ---- Phase retrieval gradient (dense real Gaussian A, amplitude loss) ----------------------
+ * Replaces PhaseRetrieval.grad_full (problems/PR.py:75-79) and grad_stoch (:81-87):
+ *   t = A_sel z ;  r = ((|t| - y) / |t|) t  [ - the same at w when w != null ] ;  g = A_sel^T r * gscale
+ * A: [M][n] float32 with columns in the line layout; rows = measurement ids (null = all). */
+typedef struct {
+    const float* A;
+    long long n;
+    int M;
+    const float* z;
+    const float* w;               /* optional second point (SVRG / SARAH difference; not linear) */
+    const float* y;
+    const int* rows;
+    int count;
+    const int* cursor;
+    float* r;                     /* scratch, count floats */
+    float gscale;
+    float step;
+    const float* step_ptr;
+    float* g_out;
+    const float* vadd;
+    float* v_out;
+    const float* z_in;
+    float* z_out;
+} pnp_pr_grad_args;
+int pnp_pr_grad(const pnp_pr_grad_args* args, void* stream);
+
 /* ---- prox step ------------------------------------------------------------------------------
  * estimate_sigma(z0, multichannel=True, average_sigmas=True)  (algorithms/pnp_svrg.py:71 and
  * pnp_gd.py:49, pnp_sgd.py:50, pnp_saga.py:64, pnp_sarah.py:47,89).  ADDS the sum over columns of
@@ -100,6 +166,14 @@ int pnp_estimate_sigma(const float* z, int H, int W, int batch, double* sig_log,
 int pnp_wavelet_denoise(const float* z_in, float* z_out, int H, int W, int batch, const double* sig_log,
                         float sigma_est, float sigma_modifier, float fallback_sigma, const float* xrec,
                         double* mse_log, const int* slot, void* stream);
+
+/* NLMDenoiser.denoise (denoisers/NLM.py:22-27) = skimage denoise_nl_means(h = sigma = sigma_est *
+ * sigma_modifier, fast_mode=False, patch_size, patch_distance) on a 2-D grey image.  Even patch sizes
+ * are bumped to the next odd one as skimage does.  sigma_est <= 0 -> h = fallback_h, sigma = 0.
+ * z_out must not alias z_in.  sig_log / xrec / mse_log / slot as in pnp_wavelet_denoise. */
+int pnp_nlm_denoise(const float* z_in, float* z_out, int H, int W, int batch, int patch_size, int patch_distance,
+                    const double* sig_log, float sigma_est, float sigma_modifier, float fallback_h,
+                    const float* xrec, double* mse_log, const int* slot, void* stream);
 
 /* Problem.PSNR (problems/problem.py:33-35): ADDS sum((z - xrec)^2) to out[slot*batch+img]. */
 int pnp_sq_err(const float* z, const float* xrec, long long n, int batch, double* out, const int* slot,

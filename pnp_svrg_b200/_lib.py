@@ -28,6 +28,28 @@ class CsmriGradArgs(C.Structure):
     ]
 
 
+class DeblurGradArgs(C.Structure):
+    """mirror of pnp_deblur_grad_args"""
+    _fields_ = [
+        ('H', C.c_int), ('W', C.c_int), ('batch', C.c_int),
+        ('a', C.c_void_p), ('b', C.c_void_p), ('S', C.c_void_p), ('blurred', C.c_void_p), ('up', C.c_void_p),
+        ('Bf', C.c_void_p), ('twn', C.c_void_p), ('y', C.c_void_p), ('tl', C.c_void_p), ('wts', C.c_void_p),
+        ('identity', C.c_int), ('M', C.c_int), ('sel', C.c_void_p), ('count', C.c_int), ('cursor', C.c_void_p),
+        ('use_y', C.c_int), ('gscale', C.c_float), ('step', C.c_float), ('step_ptr', C.c_void_p),
+        ('g_out', C.c_void_p), ('vadd', C.c_void_p), ('v_out', C.c_void_p), ('z_in', C.c_void_p), ('z_out', C.c_void_p),
+    ]
+
+
+class PrGradArgs(C.Structure):
+    """mirror of pnp_pr_grad_args"""
+    _fields_ = [
+        ('A', C.c_void_p), ('n', C.c_longlong), ('M', C.c_int), ('z', C.c_void_p), ('w', C.c_void_p), ('y', C.c_void_p),
+        ('rows', C.c_void_p), ('count', C.c_int), ('cursor', C.c_void_p), ('r', C.c_void_p),
+        ('gscale', C.c_float), ('step', C.c_float), ('step_ptr', C.c_void_p),
+        ('g_out', C.c_void_p), ('vadd', C.c_void_p), ('v_out', C.c_void_p), ('z_in', C.c_void_p), ('z_out', C.c_void_p),
+    ]
+
+
 # name -> (restype, argtypes); every symbol declared in include/pnp_b200.h
 PROTOTYPES = {
     'pnp_init': (C.c_int, []),
@@ -39,6 +61,11 @@ PROTOTYPES = {
     'pnp_csmri_sel_sample': (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                        C.c_longlong, C.c_int, C.c_uint, C.c_void_p, C.c_void_p, C.c_int,
                                        C.c_void_p]),
+    'pnp_sample_indices': (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_uint, C.c_void_p, C.c_void_p]),
+    'pnp_deblur_grad': (C.c_int, [C.POINTER(DeblurGradArgs), C.c_void_p]),
+    'pnp_pr_grad': (C.c_int, [C.POINTER(PrGradArgs), C.c_void_p]),
+    'pnp_nlm_denoise': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
+                                  C.c_float, C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     'pnp_estimate_sigma': (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     'pnp_wavelet_denoise': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_float,
                                       C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),

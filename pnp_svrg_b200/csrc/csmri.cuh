@@ -287,4 +287,11 @@ __global__ void k_sel_from_feistel(unsigned char* __restrict__ bits, int H, int 
     }
 }
 
+__global__ void k_sample_indices(int* __restrict__ idx_out, int n, int count, unsigned seed,
+                                 const int* __restrict__ counter) {
+    const unsigned key = mix32(seed ^ mix32((counter ? (unsigned)*counter : 0u) * 0x632be5abU));
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x)
+        idx_out[i] = (int)feistel_perm((unsigned)i, (unsigned)n, key);
+}
+
 }  // namespace pnp

@@ -10,6 +10,9 @@
 #include "csmri.cuh"
 #include "prox.cuh"
 #include "vr.cuh"
+#include "deblur.cuh"
+#include "pr.cuh"
+#include "nlm.cuh"
 
 namespace {
 
@@ -61,6 +64,18 @@ int set_attrs() {
     cudaFuncAttributes fa;
     CU_TRY(cudaFuncGetAttributes(&fa, pnp::k_sigma_mad<L>));
     CU_TRY(cudaFuncGetAttributes(&fa, pnp::k_haar_bayes<L>));
+    CU_TRY(cudaFuncSetAttribute(pnp::k_cols_conv<L, cols_nc<L>()>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cols_smem<L>()));
+    return PNP_OK;
+}
+
+template <int L>
+int launch_conv(float2* S, const float2* Bf, const float2* twn, int H, int batch, int conj_kernel, cudaStream_t st) {
+    constexpr int NC = cols_nc<L>();
+    const int tasks = H / 2 + 1;
+    dim3 grid((tasks + NC - 1) / NC, batch);
+    pnp::k_cols_conv<L, NC><<<grid, NC * pnp::fft_threads<L>(), cols_smem<L>(), st>>>(S, Bf, twn, H, conj_kernel,
+                                                                                     (long long)tasks * L);
+    LAUNCH_CHECK();
     return PNP_OK;
 }
 
@@ -118,6 +133,9 @@ int dispatch_r2c(int n, const pnp_csmri_grad_args& a, cudaStream_t st) { DISPATC
 int dispatch_cols(int n, const pnp_csmri_grad_args& a, cudaStream_t st) { DISPATCH_POW2(n, launch_cols, a, st) }
 int dispatch_c2r(int n, const pnp_csmri_grad_args& a, cudaStream_t st) { DISPATCH_POW2(n, launch_c2r, a, st) }
 int dispatch_attrs(int n) { DISPATCH_POW2(n, set_attrs) }
+int dispatch_conv(int n, float2* S, const float2* Bf, const float2* twn, int H, int batch, int cj, cudaStream_t st) {
+    DISPATCH_POW2(n, launch_conv, S, Bf, twn, H, batch, cj, st)
+}
 
 template <int L>
 int launch_sigma(const float* z, int W, int batch, double* sig_log, const int* slot, cudaStream_t st) {
@@ -183,6 +201,11 @@ int pnp_init(void) {
         CU_TRY(cudaFuncGetAttributes(&fa, pnp::k_saga_update));
         CU_TRY(cudaFuncGetAttributes(&fa, pnp::k_saga_init));
         CU_TRY(cudaFuncGetAttributes(&fa, pnp::k_advance));
+        CU_TRY(cudaFuncGetAttributes(&fa, pnp::k_bilinear_residual));
+        CU_TRY(cudaFuncGetAttributes(&fa, pnp::k_pr_rows));
+        CU_TRY(cudaFuncGetAttributes(&fa, pnp::k_pr_cols));
+        CU_TRY(cudaFuncGetAttributes(&fa, pnp::k_nlm));
+        CU_TRY(cudaFuncGetAttributes(&fa, pnp::k_sample_indices));
     }
     g_init[dev] = true;
     return PNP_OK;
@@ -298,6 +321,88 @@ int pnp_advance_scale(int* counters, int n, float* x, float factor, void* stream
 int pnp_copy_f32(float* dst, const float* src, long long n, void* stream) {
     if (!dst || !src || n < 0) return fail(PNP_ERR_ARG, "bad argument");
     CU_TRY(cudaMemcpyAsync(dst, src, sizeof(float) * (size_t)n, cudaMemcpyDeviceToDevice, static_cast<cudaStream_t>(stream)));
+    return PNP_OK;
+}
+
+int pnp_sample_indices(int* idx_out, int n, int count, unsigned seed, const int* counter, void* stream) {
+    if (!idx_out || n < 1 || count < 1 || count > n) return fail(PNP_ERR_ARG, "bad argument");
+    int blocks = (count + 255) / 256;
+    if (blocks > 592) blocks = 592;
+    pnp::k_sample_indices<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(idx_out, n, count, seed, counter);
+    LAUNCH_CHECK();
+    return PNP_OK;
+}
+
+int pnp_deblur_grad(const pnp_deblur_grad_args* args, void* stream) {
+    if (!args) return fail(PNP_ERR_ARG, "null args");
+    const pnp_deblur_grad_args& a = *args;
+    if (!pow2_ok(a.H) || !pow2_ok(a.W)) return fail(PNP_ERR_ARG, "H=%d W=%d must be powers of two in [32, 4096]", a.H, a.W);
+    if (a.batch != 1) return fail(PNP_ERR_ARG, "pnp_deblur_grad: batch must be 1 in this revision");
+    if (!a.a || !a.S || !a.blurred || !a.up || !a.Bf || !a.twn || !a.y) return fail(PNP_ERR_ARG, "null pointer");
+    if (!a.identity && (!a.tl || !a.wts)) return fail(PNP_ERR_ARG, "bilinear tables missing");
+    if (a.z_out && !a.z_in) return fail(PNP_ERR_ARG, "z_out needs z_in");
+    int rc = check_init();
+    if (rc != PNP_OK) return rc;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const long long N = (long long)a.H * a.W;
+    pnp_csmri_grad_args f{};
+    f.H = a.H; f.W = a.W; f.batch = 1; f.S = a.S;
+    // x = fft_blur(a - b, B)
+    f.a = a.a; f.b = a.b; f.gscale = 1.0f; f.g_out = a.blurred;
+    if ((rc = dispatch_r2c(a.H, f, st)) != PNP_OK) return rc;
+    if ((rc = dispatch_conv(a.W, reinterpret_cast<float2*>(a.S), reinterpret_cast<const float2*>(a.Bf),
+                            reinterpret_cast<const float2*>(a.twn), a.H, 1, 0, st)) != PNP_OK) return rc;
+    if ((rc = dispatch_c2r(a.H, f, st)) != PNP_OK) return rc;
+    // up = S^T (S x - y) on the selection
+    CU_TRY(cudaMemsetAsync(a.up, 0, sizeof(float) * (size_t)N, st));
+    const int count = a.sel ? a.count : a.M;
+    if (count > 0) {
+        int blocks = (count + 255) / 256;
+        if (blocks > 1184) blocks = 1184;
+        pnp::k_bilinear_residual<<<dim3(blocks, 1), 256, 0, st>>>(a.blurred, a.up, a.y, a.tl, a.wts, a.sel, count, a.H,
+                                                                  a.identity, a.use_y, N, a.M, 0, a.cursor);
+        LAUNCH_CHECK();
+    }
+    // g = fft_blur(up, roll(flip(B), 1)) -> epilogue
+    f.a = a.up; f.b = nullptr; f.gscale = a.gscale; f.step = a.step; f.step_ptr = a.step_ptr;
+    f.g_out = a.g_out; f.vadd = a.vadd; f.v_out = a.v_out; f.z_in = a.z_in; f.z_out = a.z_out;
+    if ((rc = dispatch_r2c(a.H, f, st)) != PNP_OK) return rc;
+    if ((rc = dispatch_conv(a.W, reinterpret_cast<float2*>(a.S), reinterpret_cast<const float2*>(a.Bf),
+                            reinterpret_cast<const float2*>(a.twn), a.H, 1, 1, st)) != PNP_OK) return rc;
+    return dispatch_c2r(a.H, f, st);
+}
+
+int pnp_pr_grad(const pnp_pr_grad_args* args, void* stream) {
+    if (!args) return fail(PNP_ERR_ARG, "null args");
+    const pnp_pr_grad_args& a = *args;
+    if (!a.A || !a.z || !a.y || !a.r || a.n < 4 || (a.n & 3) || a.M < 1) return fail(PNP_ERR_ARG, "bad argument");
+    if (a.z_out && !a.z_in) return fail(PNP_ERR_ARG, "z_out needs z_in");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int count = a.rows ? a.count : a.M;
+    if (count < 1) return fail(PNP_ERR_ARG, "empty selection");
+    int blocks = count < 148 * 8 ? count : 148 * 8;
+    pnp::k_pr_rows<<<blocks, 256, 0, st>>>(a.A, a.z, a.w, a.y, a.rows, count, a.n, a.r, a.cursor);
+    LAUNCH_CHECK();
+    const long long n4 = a.n / 4;
+    pnp::k_pr_cols<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(a.A, a.r, a.rows, count, a.n, a.cursor, a.gscale, a.step,
+                                                                 a.step_ptr, a.g_out, a.vadd, a.v_out, a.z_in, a.z_out);
+    LAUNCH_CHECK();
+    return PNP_OK;
+}
+
+int pnp_nlm_denoise(const float* z_in, float* z_out, int H, int W, int batch, int patch_size, int patch_distance,
+                    const double* sig_log, float sigma_est, float sigma_modifier, float fallback_h,
+                    const float* xrec, double* mse_log, const int* slot, void* stream) {
+    if (!z_in || !z_out || z_in == z_out || batch < 1 || H < 1 || W < 1) return fail(PNP_ERR_ARG, "bad argument (z_out must not alias z_in)");
+    const int s = (patch_size % 2 == 0) ? patch_size + 1 : patch_size;
+    if (s < 1 || s > NLM_MAX_S || patch_distance < 0 || patch_distance + s / 2 > NLM_MAX_HALO)
+        return fail(PNP_ERR_ARG, "patch_size %d / patch_distance %d not supported", patch_size, patch_distance);
+    pnp::NlmParams np_{s, patch_distance, sig_log, sigma_est, sigma_modifier, fallback_h};
+    const int TW = NLM_TILE + 2 * (patch_distance + s / 2);
+    dim3 grid((W + NLM_TILE - 1) / NLM_TILE, (H + NLM_TILE - 1) / NLM_TILE, batch);
+    pnp::k_nlm<<<grid, dim3(NLM_TILE, NLM_TILE), sizeof(float) * TW * TW, static_cast<cudaStream_t>(stream)>>>(
+        z_in, z_out, xrec, H, W, (long long)H * W, np_, mse_log, slot, batch);
+    LAUNCH_CHECK();
     return PNP_OK;
 }
 

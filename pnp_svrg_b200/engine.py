@@ -73,7 +73,7 @@ class Engine:
             self.sig_log = torch.zeros(LOG_CHUNK, dtype=torch.float64, device=self.dev)
             self.counters = torch.zeros(4, dtype=torch.int32, device=self.dev)   # [0] log slot [1] mb cursor [2] draws
             self.step = torch.zeros(1, dtype=torch.float32, device=self.dev)
-            self.sel = problem._dev_new_sel() if self.B > 0 else None
+            self.sel = problem._dev_new_sel(self.B) if self.B > 0 else None
             self.n_extra = n_extra_ints
             if self.B > 0:
                 self.idx_host = torch.empty(self.B + n_extra_ints, dtype=torch.int32).pin_memory()

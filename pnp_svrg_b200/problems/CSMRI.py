@@ -76,7 +76,7 @@ class CSMRI(Problem):
         self._bits_tmp = torch.zeros(W * hp, dtype=torch.uint8, device=dev)
 
     # ---- device protocol used by pnp_svrg_b200.engine ------------------------------------------
-    def _dev_new_sel(self):
+    def _dev_new_sel(self, count=0):
         return torch.zeros(self.W * (self.H // 2), dtype=torch.uint8, device=self._device)
 
     def _dev_full_sel(self):

@@ -68,3 +68,27 @@ def _check_case(name, tol=1e-4):
 @pytest.mark.parametrize('name', CSMRI_CASES)
 def test_csmri_against_reference_outputs(cuda, name):
     _check_case(name)
+
+
+@pytest.mark.parametrize('name', ['deblur64_s50_saga', 'deblur64_s100_gd', 'deblur64_min_sgd'])
+def test_deblur_against_reference_outputs(cuda, name):
+    _check_case(name)
+
+
+@pytest.mark.parametrize('name', ['pr32_svrg', 'pr32_sarah', 'pr32_sgd'])
+def test_pr_against_reference_outputs(cuda, name):
+    _check_case(name)
+
+
+def test_deblur_nlm_saga_against_reference_outputs(cuda):
+    # NLM has hard decisions (distance cut-off 5.0, max(0, .)): fp32 vs float64 may flip isolated
+    # candidates, so the iterate tolerance is looser here; PSNR must still agree to 0.05 dB.
+    _check_case('deblur32_nlm_saga', tol=2e-3)
+
+
+def test_G1_known_answer_on_device_class(cuda):
+    from pnp_svrg_b200.problems import Deblur
+    meta, d = _load('G1_deblur_sigma')
+    p = Deblur(image=d['image_u8'], kernel='Minimal', H=256, W=256, snr=5., scale_percent=100)
+    assert p.M == 65536
+    assert abs(p.sigma - meta['notebook_value']) < 1e-17

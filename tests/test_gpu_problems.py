@@ -1,0 +1,163 @@
+"""GPU parity: Deblur, PhaseRetrieval and NLM against the float64 oracle."""
+import numpy as np
+import pytest
+
+from conftest import rel_l2, synth_image
+
+pytestmark = pytest.mark.gpu
+
+
+def _kernel(H, seed=0):
+    rng = np.random.default_rng(seed)
+    k = np.zeros((H, H))
+    c = H // 2
+    yy, xx = np.mgrid[0:H, 0:H]
+    k += 60 * np.exp(-((yy - c) ** 2 + (xx - c - 3) ** 2) / (2 * (H / 20.0) ** 2))
+    k[rng.integers(0, H, 8), rng.integers(0, H, 8)] += 20
+    return np.round(k).astype(np.uint8)
+
+
+def _deblur_pair(H, scale, kernel='img', seed=0):
+    from oracle.problems_port import DeblurPort
+    from pnp_svrg_b200.problems import Deblur
+    img = synth_image(H, H, 2)
+    kw = dict(H=H, W=H, scale_percent=scale, snr=20.)
+    if kernel == 'img':
+        kp, kd = dict(kernel_path=_kernel(H)), dict(kernel=_kernel(H))
+    else:
+        kp = kd = dict(kernel=kernel)
+    np.random.seed(seed)
+    ref = DeblurPort(img, **kw, **kp)
+    np.random.seed(seed)
+    dut = Deblur(image=img, **kw, **kd)
+    return ref, dut
+
+
+@pytest.mark.parametrize('H,scale,kernel', [(32, 50, 'img'), (64, 100, 'img'), (64, 50, 'Minimal'), (64, 25, 'Identity'),
+                                            (128, 50, 'img'), (256, 50, 'img'), (256, 100, 'Minimal'), (512, 50, 'img')])
+def test_deblur_constructor_and_grads(cuda, H, scale, kernel):
+    ref, dut = _deblur_pair(H, scale, kernel)
+    assert dut.M == ref.M and dut.lrH == ref.lrH
+    assert np.array_equal(dut.B, ref.B)
+    assert rel_l2(dut.Y, ref.Y) < 1e-12 and np.array_equal(dut.Xinit, ref.Xinit)
+    z = np.random.default_rng(1).uniform(0, 1, ref.N)
+    g_ref = ref.grad_full(z)
+    assert rel_l2(dut.grad_full(z), g_ref) < 5e-6, rel_l2(dut.grad_full(z), g_ref)
+    for B in (1, 37, min(1000, ref.M)):
+        np.random.seed(3)
+        mb_ref = ref.select_mb(B)
+        np.random.seed(3)
+        mb = dut.select_mb(B)
+        assert np.array_equal(np.asarray(mb), mb_ref)
+        g_ref = ref.grad_stoch(z, mb_ref)
+        assert rel_l2(dut.grad_stoch(z, mb), g_ref) < 5e-6, (B, rel_l2(dut.grad_stoch(z, mb), g_ref))
+
+
+def test_deblur_helical_boundary(cuda):
+    """The raveled 1-D convolution wraps rows into each other: a tap at flat offset 1 moves the last
+    pixel of a row to the first pixel of the NEXT row."""
+    from pnp_svrg_b200.problems import Deblur
+    H = 32
+    k = np.zeros(H * H)
+    k[1] = H * H / np.sqrt(H * H)          # fft_blur scales by sqrt(N) and B = kernel / N -> unit gain
+    dut = Deblur(image=synth_image(H, H, 1), H=H, W=H, kernel=k, scale_percent=100, sigma=0.0)
+    x = dut.X.reshape(H, H)
+    y = dut.Y.reshape(H, H)
+    assert np.allclose(y[3, 1:], x[3, :-1], atol=1e-9) and np.allclose(y[4, 0], x[3, -1], atol=1e-9)
+    # device gradient at z = 0: B^T (0 - y) / M -> shifts back by one flat position
+    g = dut.grad_full(np.zeros(H * H)).reshape(H, H)
+    assert rel_l2(g, -x / dut.M) < 1e-5
+
+
+def _pr_pair(H, M, seed=0):
+    from oracle.problems_port import PhaseRetrievalPort
+    from pnp_svrg_b200.problems import PhaseRetrieval
+    img = synth_image(H, H, 4)
+    np.random.seed(seed)
+    ref = PhaseRetrievalPort(img, H=H, W=H, num_meas=M, snr=20.)
+    np.random.seed(seed)
+    dut = PhaseRetrieval(image=img, H=H, W=H, num_meas=M, snr=20.)
+    return ref, dut
+
+
+@pytest.mark.parametrize('H,M', [(32, 512), (32, 100), (64, 2048)])
+def test_pr_constructor_and_grads(cuda, H, M):
+    ref, dut = _pr_pair(H, M)
+    assert np.array_equal(dut.A, ref.A) and np.array_equal(dut.Y, ref.Y)
+    assert rel_l2(dut.Xinit, ref.Xinit) < 1e-6          # matrix-free power iteration vs the N x N matrix
+    z = np.random.default_rng(1).uniform(0, 1, ref.N)
+    assert rel_l2(dut.grad_full(z), ref.grad_full(z)) < 5e-6
+    for B in (1, 33, min(800, M)):
+        np.random.seed(3)
+        mb_ref = ref.select_mb(B)
+        np.random.seed(3)
+        mb = dut.select_mb(B)
+        assert np.array_equal(np.asarray(mb), mb_ref)
+        assert rel_l2(dut.grad_stoch(z, mb), ref.grad_stoch(z, mb_ref)) < 5e-6
+
+
+@pytest.mark.parametrize('H,W', [(32, 32), (64, 32), (128, 128)])
+def test_nlm_denoise(cuda, H, W):
+    from oracle.skimage_port import denoise_nl_means
+    from pnp_svrg_b200.denoisers import NLMDenoiser
+    rng = np.random.default_rng(H)
+    clean = synth_image(H, W, 6).astype(np.float64) / 255
+    for s in (0.03, 0.1):
+        z0 = (clean + s * rng.standard_normal((H, W))).astype(np.float32).astype(np.float64)
+        want = denoise_nl_means(z0, h=s, sigma=s, fast_mode=False, patch_size=4, patch_distance=5)
+        got = NLMDenoiser().denoise(z0, sigma_est=s)
+        assert got.shape == (H, W)
+        bad = np.abs(got - want) > 1e-4
+        # isolated pixels may flip a hard decision (cut-off 5.0) in fp32; everything else is tight
+        assert bad.mean() < 2e-3, bad.mean()
+        assert rel_l2(got, want) < 1e-4, rel_l2(got, want)
+    d = NLMDenoiser(denoise_strength=0.05)
+    want = denoise_nl_means(z0, h=0.05, sigma=0.0, fast_mode=False, patch_size=4, patch_distance=5)
+    assert rel_l2(d.denoise(z0, sigma_est=0), want) < 1e-4      # sigma_est <= 0 branch (NLM.py:27)
+    assert d.t == 1
+
+
+@pytest.mark.parametrize('algo,kw', [('pnp_saga', dict(eta=0.3, mini_batch_size=100, hist_size=5)),
+                                     ('pnp_svrg', dict(eta=0.5, T2=4, mini_batch_size=100, vr_mode='paper')),
+                                     ('pnp_sarah', dict(eta=0.3, T2=3, mini_batch_size=100))])
+def test_deblur_loops(cuda, algo, kw):
+    from oracle import algorithms_port as AP
+    from pnp_svrg_b200 import algorithms as ALG
+    from pnp_svrg_b200.denoisers import TVDenoiser
+    ref, dut = _deblur_pair(64, 50)
+    np.random.seed(1)
+    o_ref = getattr(AP, algo)(ref, AP.TVPort(), budget=8, converge_check=False, **kw)
+    np.random.seed(1)
+    o = getattr(ALG, algo)(dut, TVDenoiser(), tt=1e9, max_iters=8, verbose=False, converge_check=False, **kw)
+    assert rel_l2(o['z'], o_ref['z']) < 1e-4, rel_l2(o['z'], o_ref['z'])
+    assert abs(o['psnr_per_iter'][-1] - o_ref['psnr_per_iter'][-1]) <= 0.05
+
+
+@pytest.mark.parametrize('algo,kw', [('pnp_svrg', dict(eta=0.05, T2=4, mini_batch_size=64, vr_mode='paper')),
+                                     ('pnp_sarah', dict(eta=0.03, T2=3, mini_batch_size=64)),
+                                     ('pnp_gd', dict(eta=0.05))])
+def test_pr_loops(cuda, algo, kw):
+    from oracle import algorithms_port as AP
+    from pnp_svrg_b200 import algorithms as ALG
+    from pnp_svrg_b200.denoisers import TVDenoiser
+    ref, dut = _pr_pair(32, 512)
+    dut.Xinit = ref.Xinit.copy()
+    np.random.seed(1)
+    o_ref = getattr(AP, algo)(ref, AP.TVPort(), budget=8, converge_check=False, **kw)
+    np.random.seed(1)
+    o = getattr(ALG, algo)(dut, TVDenoiser(), tt=1e9, max_iters=8, verbose=False, converge_check=False, **kw)
+    assert rel_l2(o['z'], o_ref['z']) < 1e-4, rel_l2(o['z'], o_ref['z'])
+    assert abs(o['psnr_per_iter'][-1] - o_ref['psnr_per_iter'][-1]) <= 0.05
+
+
+def test_device_sampler_matches_host_twin(cuda):
+    """csrc feistel_perm == engine.feistel_sample (mb_source='device' and 'host' draw identically)."""
+    import torch
+    from pnp_svrg_b200 import _lib, device as D
+    from pnp_svrg_b200.engine import feistel_sample
+    dev = D.require_cuda()
+    for n, c in [(1, 1), (100, 100), (16384, 800), (1258000, 100000)]:
+        out = torch.zeros(c, dtype=torch.int32, device=dev)
+        cnt = torch.tensor([5], dtype=torch.int32, device=dev)
+        _lib.check(_lib.load().pnp_sample_indices(D.ptr(out), n, c, 77, D.ptr(cnt), D.stream()))
+        assert np.array_equal(out.cpu().numpy().astype(np.int64), feistel_sample(n, c, 77, 5))
