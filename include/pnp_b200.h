@@ -175,6 +175,30 @@ int pnp_nlm_denoise(const float* z_in, float* z_out, int H, int W, int batch, in
                     const double* sig_log, float sigma_est, float sigma_modifier, float fallback_h,
                     const float* xrec, double* mse_log, const int* slot, void* stream);
 
+/* ---- CNN denoisers (3x3 conv stacks, 64 features) ---------------------------------------------
+ * Replaces self.model(x) + the wrapper arithmetic of RealSN_DnCNNDenoiser.denoise
+ * (denoisers/RealSN_DnCNN.py:16-40; nets: DeepDenoisers/model/models.py:5-22, realSN_models.py:5-18,
+ * SimpleCNN_models.py:6-56) and of MMODenoiser.denoise / apply_model (denoisers/MMODenoise.py:18-40,
+ * 73-103,124-128).  Weights are packed by the host: layer 0 [9][64], middle layers [9][64 ci][64 co],
+ * last layer [9][64]; tap = dl*3 + dp over (line, pixel-in-line) offsets of the transposed layout.
+ * scale/shift = folded eval-mode BatchNorm or bias (null = 1 / 0); slope = activation (0 ReLU,
+ * 0.01 LeakyReLU).  mode 0 = DnCNN wrapper (min/max normalise by *stats*, residual net),
+ * mode 1 = MMO (clamp, net + input, clamp).  act0/act1: scratch, PH*PW*64 floats each; stats: 2 ints.
+ * precision 0 = fp32 CUDA cores (exact-parity path), 1 = bf16 tcgen05 tensor cores. */
+#define PNP_CNN_MAX_LAYERS 32
+typedef struct {
+    int n_layers;
+    const float* w[PNP_CNN_MAX_LAYERS];
+    const float* scale[PNP_CNN_MAX_LAYERS];
+    const float* shift[PNP_CNN_MAX_LAYERS];
+    float slope[PNP_CNN_MAX_LAYERS];
+    float last_bias;
+    int mode;
+    float range, shift_in;
+} pnp_cnn_net;
+int pnp_cnn_forward(const pnp_cnn_net* net, const float* img, float* out, int PH, int PW, float* act0, float* act1,
+                    int* stats, const float* xrec, double* mse_log, const int* slot, int precision, void* stream);
+
 /* Problem.PSNR (problems/problem.py:33-35): ADDS sum((z - xrec)^2) to out[slot*batch+img]. */
 int pnp_sq_err(const float* z, const float* xrec, long long n, int batch, double* out, const int* slot,
                void* stream);

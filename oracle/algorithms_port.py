@@ -225,3 +225,38 @@ def pnp_sarah(problem, denoiser, eta, budget, T2, mini_batch_size, lr_decay=1, c
                 break
         i += 1
     return r.result(z, 'pnp_sarah')
+
+
+class DnCNNPort(DenoiserPort):
+    """denoisers/RealSN_DnCNN.py:8-40 with the network evaluated by torch on the CPU in fp32 (the
+    reference moves it to CUDA; the arithmetic is the same).  ``layers``: list of (weight (co,ci,3,3),
+    bn or None) with bn = (gamma, beta, mean, var); eps 1e-5, ReLU between layers, no bias."""
+
+    def __init__(self, layers, sigma):
+        super().__init__()
+        self.layers, self.sigma = layers, sigma
+
+    def _net(self, x):
+        import torch
+        import torch.nn.functional as F
+        t = torch.from_numpy(x.astype(np.float32))[None, None]
+        with torch.no_grad():
+            for i, (w, bn) in enumerate(self.layers):
+                t = F.conv2d(t, torch.from_numpy(np.asarray(w, dtype=np.float32)), padding=1)
+                if bn is not None:
+                    g, b, m, v = (torch.from_numpy(np.asarray(a, dtype=np.float32)) for a in bn)
+                    t = F.batch_norm(t, m, v, g, b, training=False, eps=1e-5)
+                if i < len(self.layers) - 1:
+                    t = F.relu(t)
+        return t[0, 0].numpy().astype(np.float64)
+
+    def denoise(self, noisy, sigma_est=0):
+        xt = np.copy(noisy)
+        mn, mx = np.min(xt), np.max(xt)
+        xt = (xt - mn) / (mx - mn)
+        rng_ = 1.0 + self.sigma / 255.0 / 2.0
+        sh = (1 - rng_) / 2.0
+        xt = xt * rng_ + sh
+        x = xt - self._net(xt)
+        x = (x - sh) / rng_
+        return x * (mx - mn) + mn

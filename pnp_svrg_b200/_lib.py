@@ -50,6 +50,19 @@ class PrGradArgs(C.Structure):
     ]
 
 
+CNN_MAX_LAYERS = 32
+
+
+class CnnNet(C.Structure):
+    """mirror of pnp_cnn_net"""
+    _fields_ = [
+        ('n_layers', C.c_int),
+        ('w', C.c_void_p * CNN_MAX_LAYERS), ('scale', C.c_void_p * CNN_MAX_LAYERS), ('shift', C.c_void_p * CNN_MAX_LAYERS),
+        ('slope', C.c_float * CNN_MAX_LAYERS),
+        ('last_bias', C.c_float), ('mode', C.c_int), ('range', C.c_float), ('shift_in', C.c_float),
+    ]
+
+
 # name -> (restype, argtypes); every symbol declared in include/pnp_b200.h
 PROTOTYPES = {
     'pnp_init': (C.c_int, []),
@@ -66,6 +79,8 @@ PROTOTYPES = {
     'pnp_pr_grad': (C.c_int, [C.POINTER(PrGradArgs), C.c_void_p]),
     'pnp_nlm_denoise': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
                                   C.c_float, C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    'pnp_cnn_forward': (C.c_int, [C.POINTER(CnnNet), C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                  C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     'pnp_estimate_sigma': (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     'pnp_wavelet_denoise': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_float,
                                       C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),

@@ -13,6 +13,7 @@
 #include "deblur.cuh"
 #include "pr.cuh"
 #include "nlm.cuh"
+#include "cnn_fp32.cuh"
 
 namespace {
 
@@ -206,6 +207,11 @@ int pnp_init(void) {
         CU_TRY(cudaFuncGetAttributes(&fa, pnp::k_pr_cols));
         CU_TRY(cudaFuncGetAttributes(&fa, pnp::k_nlm));
         CU_TRY(cudaFuncGetAttributes(&fa, pnp::k_sample_indices));
+        CU_TRY(cudaFuncGetAttributes(&fa, pnp::k_minmax_init));
+        CU_TRY(cudaFuncGetAttributes(&fa, pnp::k_minmax));
+        CU_TRY(cudaFuncGetAttributes(&fa, pnp::k_conv_first));
+        CU_TRY(cudaFuncGetAttributes(&fa, pnp::k_conv_mid));
+        CU_TRY(cudaFuncGetAttributes(&fa, pnp::k_conv_last));
     }
     g_init[dev] = true;
     return PNP_OK;
@@ -402,6 +408,39 @@ int pnp_nlm_denoise(const float* z_in, float* z_out, int H, int W, int batch, in
     dim3 grid((W + NLM_TILE - 1) / NLM_TILE, (H + NLM_TILE - 1) / NLM_TILE, batch);
     pnp::k_nlm<<<grid, dim3(NLM_TILE, NLM_TILE), sizeof(float) * TW * TW, static_cast<cudaStream_t>(stream)>>>(
         z_in, z_out, xrec, H, W, (long long)H * W, np_, mse_log, slot, batch);
+    LAUNCH_CHECK();
+    return PNP_OK;
+}
+
+int pnp_cnn_forward(const pnp_cnn_net* net, const float* img, float* out, int PH, int PW, float* act0, float* act1,
+                    int* stats, const float* xrec, double* mse_log, const int* slot, int precision, void* stream) {
+    if (!net || !img || !out || !act0 || !act1 || !stats || PH < 1 || PW < 1) return fail(PNP_ERR_ARG, "bad argument");
+    if (net->n_layers < 2 || net->n_layers > PNP_CNN_MAX_LAYERS) return fail(PNP_ERR_ARG, "n_layers out of range");
+    if (precision != 0) return fail(PNP_ERR_ARG, "precision %d not built in this revision", precision);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const long long npix = (long long)PH * PW;
+    pnp::CnnIo io{net->mode, stats, net->range, net->shift_in};
+    if (net->mode == 0) {
+        pnp::k_minmax_init<<<1, 32, 0, st>>>(stats);
+        LAUNCH_CHECK();
+        pnp::k_minmax<<<ew_blocks(npix, 4), 256, 0, st>>>(img, npix, stats);
+        LAUNCH_CHECK();
+    }
+    const int L = net->n_layers;
+    pnp::k_conv_first<<<ew_blocks(npix * 16, 1), 256, 0, st>>>(img, act0, net->w[0],
+        pnp::CnnAct{net->scale[0], net->shift[0], net->slope[0]}, io, PH, PW);
+    LAUNCH_CHECK();
+    float* cur = act0;
+    float* nxt = act1;
+    dim3 grid((PW + CM_TP - 1) / CM_TP, (PH + CM_TL - 1) / CM_TL);
+    for (int l = 1; l < L - 1; ++l) {
+        pnp::k_conv_mid<<<grid, 256, 0, st>>>(cur, nxt, net->w[l], pnp::CnnAct{net->scale[l], net->shift[l], net->slope[l]}, PH, PW);
+        LAUNCH_CHECK();
+        float* t = cur; cur = nxt; nxt = t;
+    }
+    long long lb = (npix + 7) / 8;
+    if (lb > 148 * 16) lb = 148 * 16;
+    pnp::k_conv_last<<<(unsigned)lb, 256, 0, st>>>(cur, img, out, net->w[L - 1], net->last_bias, io, PH, PW, xrec, mse_log, slot);
     LAUNCH_CHECK();
     return PNP_OK;
 }
