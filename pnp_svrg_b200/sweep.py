@@ -1,0 +1,115 @@
+"""Sweep partitioning over the GPUs of one node -- the data-parallel pattern of the reference's
+script_diff_sampratio_set12.py:109-146 / script_diff_snr_set12.py:144-148, which fan a grid of
+independent reconstructions out with multiprocessing.Pool.map(process_img, SET12_LIST).
+
+Here: one process per GPU (torchrun), the flat job list (image x sampling ratio x SNR [x algorithm x
+denoiser]) is dealt round-robin over the ranks, every rank reconstructs its share on its own GPU, the
+per-job records are gathered with all_gather_object.  No collective touches the data path.
+
+    torchrun --nproc-per-node 8 -m pnp_svrg_b200.sweep --images data/Set12 --out sweep.csv
+"""
+import argparse
+import csv
+import itertools
+import os
+import time
+
+import numpy as np
+
+# reference grids: script_diff_sampratio_set12.py:28-29, script_diff_snr_set12.py:29
+ALPHAS = [0.1, 0.2, 0.3, 0.4, 0.5, 0.6, 0.7, 0.8, 0.9, 1.0]
+SNRS = [0., 5., 10., 15., 20., 25., 30.]
+
+
+def make_jobs(images, alphas=ALPHAS, snrs=SNRS, problems=('CSMRI',), denoisers=('TV',), algos=('pnp_svrg',)):
+    """Flat, deterministic job list; job['id'] is its position."""
+    jobs = []
+    for i, (img, prob, den, algo, a, s) in enumerate(itertools.product(images, problems, denoisers, algos, alphas, snrs)):
+        jobs.append(dict(id=i, image=img, problem=prob, denoiser=den, algo=algo, alpha=a, snr=s))
+    return jobs
+
+
+def partition(jobs, rank, world):
+    """Round-robin deal: rank r takes jobs r, r + world, r + 2*world, ..."""
+    if not (0 <= rank < world):
+        raise ValueError('rank %d outside world of %d' % (rank, world))
+    return jobs[rank::world]
+
+
+def run_partitioned(jobs, runner, rank=0, world=1, gather=True):
+    """Run this rank's share with ``runner(job) -> dict``; returns all records sorted by job id on
+    every rank (when gather and torch.distributed is initialised), else the local ones."""
+    local = []
+    for job in partition(jobs, rank, world):
+        try:
+            rec = runner(job)
+        except Exception as e:             # a failed job must not take the sweep down (Pool.map would)
+            rec = dict(error=repr(e))
+        rec = dict(rec)
+        rec.setdefault('id', job['id'])
+        rec['rank'] = rank
+        local.append(rec)
+    if gather and world > 1:
+        import torch.distributed as dist
+        if not dist.is_initialized():
+            raise RuntimeError('world > 1 needs an initialised torch.distributed process group')
+        parts = [None] * world
+        dist.all_gather_object(parts, local)
+        local = [r for part in parts for r in part]
+    return sorted(local, key=lambda r: r['id'])
+
+
+def reconstruct(job, H=256, W=256, eta_scale=0.15, T2=10, mini_batch_size=1000, iters=200, images=None, seed=0):
+    """One reconstruction of the sweep on the current GPU (fixed hyper-parameters, no hyperopt)."""
+    from . import algorithms as ALG
+    from . import denoisers as DN
+    from . import problems as PR
+    img = job['image']
+    kw = dict(image=images[img]) if images is not None and not isinstance(img, str) else dict(img_path=img)
+    np.random.seed(seed + job['id'])
+    if job['problem'] != 'CSMRI':
+        raise NotImplementedError('sweep runner: only CSMRI jobs are wired up in this revision')
+    p = PR.CSMRI(H=H, W=W, sample_prob=job['alpha'], snr=job['snr'], **kw)
+    den = {'TV': DN.TVDenoiser, 'NLM': DN.NLMDenoiser}[job['denoiser']]()
+    B = min(mini_batch_size, p.M0)
+    t0 = time.time()
+    out = getattr(ALG, job['algo'])(p, den, eta=eta_scale * p.M0, tt=1e9, T2=T2, mini_batch_size=B, verbose=False,
+                                    converge_check=False, max_iters=iters, vr_mode='paper', mb_source='device',
+                                    mb_seed=job['id'], fast=True, sync_every=iters)
+    dt = time.time() - t0
+    ps = out['psnr_per_iter']
+    return dict(id=job['id'], image=str(img), alpha=job['alpha'], snr=job['snr'], algo=job['algo'],
+                denoiser=job['denoiser'], psnr_init=float(ps[0]), psnr_final=float(ps[-1]), iters=iters, seconds=dt)
+
+
+def main():
+    import torch
+    import torch.distributed as dist
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--images', required=True, help='directory of grey images (e.g. data/Set12)')
+    ap.add_argument('--out', default='sweep.csv')
+    ap.add_argument('--iters', type=int, default=200)
+    ap.add_argument('--size', type=int, default=256)
+    a = ap.parse_args()
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    torch.cuda.set_device(int(os.environ.get('LOCAL_RANK', '0')))
+    if world > 1:
+        dist.init_process_group('nccl')
+    files = sorted(os.path.join(a.images, f) for f in os.listdir(a.images) if f.lower().endswith(('.png', '.jpg')))
+    jobs = make_jobs(files)
+    t0 = time.time()
+    recs = run_partitioned(jobs, lambda j: reconstruct(j, H=a.size, W=a.size, iters=a.iters), rank, world)
+    if rank == 0:
+        with open(a.out, 'w', newline='') as f:
+            wr = csv.DictWriter(f, fieldnames=sorted({k for r in recs for k in r}))
+            wr.writeheader()
+            wr.writerows(recs)
+        print('%d reconstructions in %.1f s on %d GPU(s): %.2f recon/s' % (len(recs), time.time() - t0, world,
+                                                                          len(recs) / (time.time() - t0)))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

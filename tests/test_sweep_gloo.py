@@ -1,0 +1,60 @@
+"""CPU, world_size 2 over gloo: the sweep's partition / gather logic (the N>1 path of config 4)."""
+import os
+import sys
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    from pnp_svrg_b200 import sweep
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    jobs = sweep.make_jobs(['a.png', 'b.png', 'c.png'], alphas=[0.1, 0.5], snrs=[0., 20., 30.])
+
+    def runner(job):
+        if job['id'] == 4:
+            raise RuntimeError('boom')                 # a failing job is recorded, not fatal
+        return dict(id=job['id'], value=job['id'] ** 2, alpha=job['alpha'])
+    recs = sweep.run_partitioned(jobs, runner, rank, world)
+    q.put((rank, recs))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_partition_covers_every_job_once():
+    from pnp_svrg_b200 import sweep
+    jobs = sweep.make_jobs(['x'] * 12)
+    assert len(jobs) == 12 * 10 * 7 == 840              # config 4: 12 images x 10 ratios x 7 SNRs
+    for world in (1, 2, 4, 8):
+        seen = sorted(j['id'] for r in range(world) for j in sweep.partition(jobs, r, world))
+        assert seen == list(range(840))
+        sizes = [len(sweep.partition(jobs, r, world)) for r in range(world)]
+        assert max(sizes) - min(sizes) <= 1
+    with pytest.raises(ValueError):
+        sweep.partition(jobs, 2, 2)
+
+
+def test_world_size_2_gloo_gather():
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = dict(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert got[0] == got[1]                               # every rank ends with the full, ordered table
+    recs = got[0]
+    assert [r['id'] for r in recs] == list(range(18))
+    assert all(r['rank'] == r['id'] % 2 for r in recs)
+    assert 'error' in recs[4] and 'boom' in recs[4]['error']
+    assert all(r['value'] == r['id'] ** 2 for r in recs if r['id'] != 4)
