@@ -46,50 +46,90 @@ struct GradEpilogue {
 template <int L, int GP> __host__ __device__ constexpr int group_stride() {
     return 2 * fft_plane<L>() + ((GP > 1 ? 32 / GP : 0) - (2 * fft_plane<L>()) % 32 + 32) % 32;
 }
+// floats of exchange planes in front of the TMA staging buffers (kept 128-byte aligned)
+template <int L, int GP> __host__ __device__ constexpr int lines_stage_off() { return (GP * group_stride<L, GP>() + 31) & ~31; }
 
+// Persistent: CTA b processes items b, b + gridDim.x, ... (an item = GP line pairs).  The 2*GP input
+// lines of an item are contiguous in memory: ONE thread stages them into shared memory with TMA bulk
+// copies (cp.async.bulk + mbarrier); the copy of item i+1 is in flight while item i is transformed.
+// smem: [GP groups x exchange planes][stage a: 2*GP*L floats][stage b: 2*GP*L floats]
 template <int L, int GP>
-__global__ void __launch_bounds__(GP * (L / FftPlan<L>::EPT))
+__global__ void __launch_bounds__(GP * (L / FftPlan<L>::EPT), (GP * (L / FftPlan<L>::EPT) >= 256 ? 2 : 4))
 k_lines_r2c(const float* __restrict__ a, const float* __restrict__ b, float2* __restrict__ S,
             int nlines, long long img_stride) {
     constexpr int T = fft_threads<L>();
+    constexpr int EPT = FftPlan<L>::EPT;
     constexpr int PL = fft_plane<L>();
     constexpr int GS = group_stride<L, GP>();
-    extern __shared__ float smem[];
+    extern __shared__ __align__(128) float smem[];
+    __shared__ __align__(8) unsigned long long bar;
+    float* stage_a = smem + lines_stage_off<L, GP>();
+    float* stage_b = stage_a + 2 * GP * L;
     const int g = threadIdx.x / T, t = threadIdx.x % T;
-    const int pair0 = blockIdx.x * GP;
-    const int pair = pair0 + g;
-    const bool active = 2 * pair < nlines;
+    const int npairs = nlines >> 1;
+    const int items = (npairs + GP - 1) / GP;
     const long long ibase = (long long)blockIdx.y * img_stride;
-    const long long base = ibase + (long long)(2 * pair) * L;
     const SmemBuf sb{smem + g * GS, smem + g * GS + PL};
-    const float* a0 = a + base;
-    const float* b0 = b ? b + base : nullptr;
-    auto ld = [&](int idx) -> float2 {
-        if (!active) return make_float2(0.f, 0.f);
-        float x = a0[idx], y = a0[idx + L];
-        if (b0) { x -= b0[idx]; y -= b0[idx + L]; }
-        return make_float2(x, y);
-    };
-    auto st = [&](int idx, float2 v) { sb.put(idx, v); };
-    fft_forward<L, false>(t, sb, ld, st);
-    __syncthreads();
-    // unpack the two real transforms; S[kyp][c]: the GP pairs of this CTA write 2*GP adjacent
-    // complex values (16 bytes per pair) of row kyp
-    float4* S4 = reinterpret_cast<float4*>(S + (ibase >> 1)) + pair0;
     const int W2 = nlines >> 1;                     // float4 per spectrum row
-    for (int i = threadIdx.x; i < GP * (L / 2); i += GP * T) {
-        const int gg = i % GP, k = i / GP;
-        if (2 * (pair0 + gg) >= nlines) continue;
-        const SmemBuf sg{smem + gg * GS, smem + gg * GS + PL};
-        const float2 xk = sg.get(k);
-        const float2 xm = sg.get(k == 0 ? L / 2 : L - k);
-        float4 o;
-        if (k == 0) {
-            o = make_float4(xk.x, xm.x, xk.y, xm.y);           // A = (DC, Nyquist) line 2p ; B likewise line 2p+1
+
+    auto issue = [&](int item) {                    // one thread: stage the item's lines
+        int np = npairs - item * GP;
+        np = np < GP ? np : GP;
+        const unsigned bytes = (unsigned)(np * 2 * L * sizeof(float));
+        mbar_expect_tx(&bar, b ? 2 * bytes : bytes);
+        bulk_g2s(stage_a, a + ibase + (long long)(2 * item * GP) * L, bytes, &bar);
+        if (b) bulk_g2s(stage_b, b + ibase + (long long)(2 * item * GP) * L, bytes, &bar);
+    };
+
+    if (threadIdx.x == 0) { mbar_init(&bar, 1); mbar_fence_init(); }
+    __syncthreads();
+    int item = blockIdx.x;
+    if (threadIdx.x == 0 && item < items) issue(item);
+    unsigned parity = 0;
+    for (; item < items; item += gridDim.x) {
+        float2 x[EPT];
+        mbar_wait(&bar, parity);
+        parity ^= 1;
+        if (item * GP + g < npairs) {
+            const float* la = stage_a + 2 * g * L;
+            const float* lb = stage_b + 2 * g * L;
+#pragma unroll
+            for (int i = 0; i < EPT; ++i) {
+                const int idx = FftIdx<L>::in(t, i);
+                float re = la[idx], im = la[idx + L];
+                if (b) { re -= lb[idx]; im -= lb[idx + L]; }
+                x[i] = make_float2(re, im);
+            }
         } else {
-            o = make_float4(0.5f * (xk.x + xm.x), 0.5f * (xk.y - xm.y), 0.5f * (xk.y + xm.y), 0.5f * (xm.x - xk.x));
+#pragma unroll
+            for (int i = 0; i < EPT; ++i) x[i] = make_float2(0.f, 0.f);
         }
-        S4[(long long)k * W2 + gg] = o;
+        __syncthreads();                            // staging consumed -> refill it for the next item
+        if (threadIdx.x == 0 && item + (int)gridDim.x < items) issue(item + gridDim.x);
+        fft_regs<L>(t, sb, x);
+        if (FftPlan<L>::NS > 1) __syncthreads();
+#pragma unroll
+        for (int i = 0; i < EPT; ++i) sb.put(FftIdx<L>::out(t, i), x[i]);
+        __syncthreads();
+        // unpack the two real transforms; S[kyp][c]: the GP pairs of this CTA write 2*GP adjacent
+        // complex values (16 bytes per pair) of row kyp
+        const int pair0 = item * GP;
+        float4* S4 = reinterpret_cast<float4*>(S + (ibase >> 1)) + pair0;
+        for (int i = threadIdx.x; i < GP * (L / 2); i += GP * T) {
+            const int gg = i % GP, k = i / GP;
+            if (pair0 + gg >= npairs) continue;
+            const SmemBuf sg{smem + gg * GS, smem + gg * GS + PL};
+            const float2 xk = sg.get(k);
+            const float2 xm = sg.get(k == 0 ? L / 2 : L - k);
+            float4 o;
+            if (k == 0) {
+                o = make_float4(xk.x, xm.x, xk.y, xm.y);       // A = (DC, Nyquist) line 2p ; B likewise line 2p+1
+            } else {
+                o = make_float4(0.5f * (xk.x + xm.x), 0.5f * (xk.y - xm.y), 0.5f * (xk.y + xm.y), 0.5f * (xm.x - xk.x));
+            }
+            S4[(long long)k * W2 + gg] = o;
+        }
+        __syncthreads();
     }
 }
 
@@ -107,9 +147,15 @@ __device__ __forceinline__ float2 apply_sel(float2 F, unsigned bb, bool use_y, c
     return o;
 }
 
-// One group of T threads per packed column kyp; the column is the contiguous row S[kyp][0..L).
+template <int L, int NC> __host__ __device__ constexpr int cols_stage_off() { return (NC * 2 * fft_plane<L>() + 31) & ~31; }
+
+// Persistent: one group of T threads per packed column (= contiguous row S[kyp][0..L)), NC groups
+// per CTA; the NC rows of an item are one contiguous block, staged by a TMA bulk copy that runs
+// one item ahead.  Columns 1..hp-1 are element-wise in the spectrum: forward FFT, selection and
+// inverse FFT happen in registers + the exchange buffer.  Column 0 (DC + i*Nyquist packed) needs
+// C[kx] and C[-kx] together and is done by CTA 0 after its loop.
 template <int L, int NC>
-__global__ void __launch_bounds__(NC * (L / FftPlan<L>::EPT))
+__global__ void __launch_bounds__(NC * (L / FftPlan<L>::EPT), (NC * (L / FftPlan<L>::EPT) >= 256 ? 2 : 4))
 k_cols_mask(float2* __restrict__ S, const unsigned char* __restrict__ bits,
             const float2* __restrict__ Y1, const float2* __restrict__ Y2,
             const float2* __restrict__ Y1n, const float2* __restrict__ Y2n,
@@ -117,77 +163,185 @@ k_cols_mask(float2* __restrict__ S, const unsigned char* __restrict__ bits,
     constexpr int T = fft_threads<L>();
     constexpr int EPT = FftPlan<L>::EPT;
     constexpr int PL = fft_plane<L>();
-    extern __shared__ float smem[];
+    using IX = FftIdx<L>;
+    extern __shared__ __align__(128) float smem[];
+    __shared__ __align__(8) unsigned long long bar;
     const int g = threadIdx.x / T, t = threadIdx.x % T;
-    const int kyp = blockIdx.x * NC + g;
     const int img = blockIdx.y;
     const SmemBuf sb{smem + g * 2 * PL, smem + g * 2 * PL + PL};
-    float2* Sc = S + ((long long)img * hp + kyp) * L;
-    const unsigned char* bc = bits + (long long)img * bits_img_stride + (long long)kyp * L;
+    float2* stage = reinterpret_cast<float2*>(smem + cols_stage_off<L, NC>());      // NC columns of L complex
+    float2* Si = S + (long long)img * hp * L;
+    const unsigned char* bi = bits + (long long)img * bits_img_stride;
     const bool use_y = Y1 != nullptr;
-    const float2* y1c = use_y ? Y1 + (long long)img * y_img_stride + (long long)kyp * L : nullptr;
-    const float2* y2c = use_y ? Y2 + (long long)img * y_img_stride + (long long)kyp * L : nullptr;
+    const float2* y1i = use_y ? Y1 + (long long)img * y_img_stride : nullptr;
+    const float2* y2i = use_y ? Y2 + (long long)img * y_img_stride : nullptr;
+    const int items = (hp - 1 + NC - 1) / NC;
 
-    auto ld = [&](int idx) -> float2 { return Sc[idx]; };
-    auto st = [&](int idx, float2 v) { sb.put(idx, v); };
-    fft_forward<L, false>(t, sb, ld, st);
+    auto issue = [&](int item) {
+        int nc = hp - 1 - item * NC;
+        nc = nc < NC ? nc : NC;
+        const unsigned bytes = (unsigned)(nc * L * sizeof(float2));
+        mbar_expect_tx(&bar, bytes);
+        bulk_g2s(stage, Si + (long long)(1 + item * NC) * L, bytes, &bar);
+    };
+    if (threadIdx.x == 0) { mbar_init(&bar, 1); mbar_fence_init(); }
     __syncthreads();
-
-    if (kyp != 0) {
-#pragma unroll 4
-        for (int m = 0; m < EPT; ++m) {
-            const int kx = t + m * T;
-            const float2 o = apply_sel(sb.get(kx), bc[kx], use_y, y1c + kx, y2c + kx);
-            sb.put(kx, cswap(o));
+    int item = blockIdx.x;
+    if (threadIdx.x == 0 && item < items) issue(item);
+    unsigned parity = 0;
+    for (; item < items; item += gridDim.x) {
+        const int col = 1 + item * NC + g;
+        const bool active = col < hp;
+        const long long crow = (long long)(active ? col : 0) * L;
+        unsigned long long bbp = 0ull;                                      // 4 selection bits per element
+#pragma unroll
+        for (int m = 0; m < EPT; ++m) bbp |= (unsigned long long)(bi[crow + t + T * m] & 0xFu) << (4 * m);
+        float2 x[EPT];
+        mbar_wait(&bar, parity);
+        parity ^= 1;
+        if (active) {
+#pragma unroll
+            for (int i = 0; i < EPT; ++i) x[i] = stage[g * L + IX::in(t, i)];
+        } else {
+#pragma unroll
+            for (int i = 0; i < EPT; ++i) x[i] = make_float2(0.f, 0.f);
         }
-    } else {
-        // packed column: C = FFT(DC + i * Nyq); split, select each row, re-pack
+        __syncthreads();                            // staging consumed -> refill it for the next item
+        if (threadIdx.x == 0 && item + (int)gridDim.x < items) issue(item + gridDim.x);
+        fft_regs<L>(t, sb, x);
+        // selection in registers, then reorder (same elements t + T*m) into the inverse's input order
+        float2 y[EPT];
+#pragma unroll
+        for (int m = 0; m < EPT; ++m) {
+            const int kx = t + T * m;
+            const float2 o = apply_sel(x[IX::out_slot(m)], (unsigned)(bbp >> (4 * m)) & 0xFu, use_y, y1i + crow + kx,
+                                       y2i + crow + kx);
+            y[IX::in_slot(m)] = cswap(o);
+        }
+        if (FftPlan<L>::NS > 1) __syncthreads();
+        fft_regs<L>(t, sb, y);
+        if (active) {
+            float2* Sc = Si + crow;
+#pragma unroll
+            for (int i = 0; i < EPT; ++i) Sc[IX::out(t, i)] = cswap(y[i]);
+        }
+        if (FftPlan<L>::NS > 1) __syncthreads();
+    }
+
+    if (blockIdx.x != 0) return;
+    // ---- packed column 0: C = FFT(DC + i * Nyq); split, select each row, re-pack ----
+    {
+        float2 x[EPT];
+        if (g == 0) {
+#pragma unroll
+            for (int i = 0; i < EPT; ++i) x[i] = Si[IX::in(t, i)];
+        } else {
+#pragma unroll
+            for (int i = 0; i < EPT; ++i) x[i] = make_float2(0.f, 0.f);
+        }
+        fft_regs<L>(t, sb, x);
+        if (FftPlan<L>::NS > 1) __syncthreads();
+#pragma unroll
+        for (int i = 0; i < EPT; ++i) sb.put(IX::out(t, i), x[i]);
+        __syncthreads();
         const float2* y1n = use_y ? Y1n + (long long)img * L : nullptr;
         const float2* y2n = use_y ? Y2n + (long long)img * L : nullptr;
-        for (int kx = t; kx <= L / 2; kx += T) {
-            const int km = (L - kx) % L;
-            const float2 ck = sb.get(kx), cm = sb.get(km);
-            const float2 fdc = make_float2(0.5f * (ck.x + cm.x), 0.5f * (ck.y - cm.y));
-            const float2 fny = make_float2(0.5f * (ck.y + cm.y), 0.5f * (cm.x - ck.x));
-            const unsigned bk = bc[kx], bm = bc[km];
-            const float2 dk = apply_sel(fdc, bk, use_y, y1c + kx, y2c + kx);
-            const float2 nk = apply_sel(fny, bk >> 2, use_y, y1n + kx, y2n + kx);
-            const float2 dm = apply_sel(make_float2(fdc.x, -fdc.y), bm, use_y, y1c + km, y2c + km);
-            const float2 nm = apply_sel(make_float2(fny.x, -fny.y), bm >> 2, use_y, y1n + km, y2n + km);
-            // C'[k] = dc[k] + i * ny[k], stored re/im swapped for the inverse transform
-            sb.put(kx, make_float2(dk.y + nk.x, dk.x - nk.y));
-            if (km != kx) sb.put(km, make_float2(dm.y + nm.x, dm.x - nm.y));
+        if (g == 0) {
+            for (int kx = t; kx <= L / 2; kx += T) {
+                const int km = (L - kx) % L;
+                const float2 ck = sb.get(kx), cm = sb.get(km);
+                const float2 fdc = make_float2(0.5f * (ck.x + cm.x), 0.5f * (ck.y - cm.y));
+                const float2 fny = make_float2(0.5f * (ck.y + cm.y), 0.5f * (cm.x - ck.x));
+                const unsigned bk = bi[kx], bm = bi[km];
+                const float2 dk = apply_sel(fdc, bk, use_y, y1i + kx, y2i + kx);
+                const float2 nk = apply_sel(fny, bk >> 2, use_y, y1n + kx, y2n + kx);
+                const float2 dm = apply_sel(make_float2(fdc.x, -fdc.y), bm, use_y, y1i + km, y2i + km);
+                const float2 nm = apply_sel(make_float2(fny.x, -fny.y), bm >> 2, use_y, y1n + km, y2n + km);
+                // C'[k] = dc[k] + i * ny[k], stored re/im swapped for the inverse transform
+                sb.put(kx, make_float2(dk.y + nk.x, dk.x - nk.y));
+                if (km != kx) sb.put(km, make_float2(dm.y + nm.x, dm.x - nm.y));
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < EPT; ++i) x[i] = sb.get(IX::in(t, i));
+        __syncthreads();
+        fft_regs<L>(t, sb, x);
+        if (g == 0) {
+#pragma unroll
+            for (int i = 0; i < EPT; ++i) Si[IX::out(t, i)] = cswap(x[i]);
         }
     }
-    __syncthreads();
-    auto ld2 = [&](int idx) -> float2 { return sb.get(idx); };
-    auto st2 = [&](int idx, float2 v) { Sc[idx] = cswap(v); };
-    fft_forward<L, true>(t, sb, ld2, st2);
 }
 
 // ------------------------------------------------------------------ pass 3
+// Persistent like pass 1.  The spectrum entries of the next item are prefetched into registers (they
+// are strided: 16*GP bytes per spectrum row); the epilogue operands (vadd and z_in lines, contiguous)
+// are staged by TMA bulk copies issued at the start of the item, so they arrive while the inverse FFT
+// runs and the epilogue never waits on a global load.
 template <int L, int GP>
-__global__ void __launch_bounds__(GP * (L / FftPlan<L>::EPT))
+__global__ void __launch_bounds__(GP * (L / FftPlan<L>::EPT), (GP * (L / FftPlan<L>::EPT) >= 256 ? 2 : 4))
 k_lines_c2r(const float2* __restrict__ S, int nlines, long long img_stride, float inv_n, GradEpilogue ep) {
     constexpr int T = fft_threads<L>();
+    constexpr int EPT = FftPlan<L>::EPT;
     constexpr int PL = fft_plane<L>();
-    extern __shared__ float smem[];
-    const int g = threadIdx.x / T, t = threadIdx.x % T;
     constexpr int GS = group_stride<L, GP>();
-    const int pair0 = blockIdx.x * GP;
-    const int pair = pair0 + g;
-    const bool active = 2 * pair < nlines;
+    constexpr int NQ = (L / 2) / T;                 // float4 spectrum entries per thread per item
+    using IX = FftIdx<L>;
+    extern __shared__ __align__(128) float smem[];
+    __shared__ __align__(8) unsigned long long bar;
+    float* stage_v = smem + lines_stage_off<L, GP>();      // vadd lines of the item
+    float* stage_z = stage_v + 2 * GP * L;                  // z_in lines of the item
+    const int g = threadIdx.x / T, t = threadIdx.x % T;
     const int img = blockIdx.y;
-    const long long base = (long long)img * img_stride + (long long)(2 * pair) * L;
+    const int npairs = nlines >> 1;
+    const int items = (npairs + GP - 1) / GP;
+    const long long ibase = (long long)img * img_stride;
     const SmemBuf sb{smem + g * GS, smem + g * GS + PL};
-    {
-        const float4* S4 = reinterpret_cast<const float4*>(S + (((long long)img * img_stride) >> 1)) + pair0;
-        const int W2 = nlines >> 1;
-        for (int i = threadIdx.x; i < GP * (L / 2); i += GP * T) {
+    const int W2 = nlines >> 1;
+    const float4* S4 = reinterpret_cast<const float4*>(S + (ibase >> 1));
+    const float gs = inv_n * (ep.gscale_ptr ? ep.gscale_ptr[img] : ep.gscale);
+    const float step = ep.step_ptr ? ep.step_ptr[img] : ep.step;
+    const float* p_vadd = ep.vadd;
+    const float* p_zin = ep.z_in;
+    float* p_gout = ep.g_out;
+    float* p_vout = ep.v_out;
+    float* p_zout = ep.z_out;
+    const bool staged = (p_vadd != nullptr) || (p_zout != nullptr);
+
+    auto load_spec = [&](int item, float4 (&q)[NQ]) {
+#pragma unroll
+        for (int n = 0; n < NQ; ++n) {
+            const int i = threadIdx.x + n * GP * T;
             const int gg = i % GP, k = i / GP;
-            if (2 * (pair0 + gg) >= nlines) continue;
+            q[n] = (item * GP + gg < npairs) ? S4[(long long)k * W2 + item * GP + gg] : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    };
+    auto issue = [&](int item) {                    // one thread: TMA bulk copies of the epilogue operands
+        int np = npairs - item * GP;
+        np = np < GP ? np : GP;
+        const unsigned bytes = (unsigned)(np * 2 * L * sizeof(float));
+        const long long off = ibase + (long long)(2 * item * GP) * L;
+        mbar_expect_tx(&bar, (p_vadd ? bytes : 0u) + (p_zout ? bytes : 0u));
+        if (p_vadd) bulk_g2s(stage_v, p_vadd + off, bytes, &bar);
+        if (p_zout) bulk_g2s(stage_z, p_zin + off, bytes, &bar);
+    };
+    if (threadIdx.x == 0) { mbar_init(&bar, 1); mbar_fence_init(); }
+    __syncthreads();
+    unsigned parity = 0;
+
+    float4 qn[NQ];
+    int item = blockIdx.x;
+    if (item < items) load_spec(item, qn);
+    for (; item < items; item += gridDim.x) {
+        if (staged && threadIdx.x == 0) issue(item);
+        // X[k] = A[k] + i B[k] of the two lines, written re/im swapped for the inverse transform
+#pragma unroll
+        for (int n = 0; n < NQ; ++n) {
+            const int i = threadIdx.x + n * GP * T;
+            const int gg = i % GP, k = i / GP;
             const SmemBuf sg{smem + gg * GS, smem + gg * GS + PL};
-            const float4 q = S4[(long long)k * W2 + gg];          // A = (q.x, q.y) line 2p ; B = (q.z, q.w) line 2p+1
+            const float4 q = qn[n];                                // A = (q.x, q.y) line 2p ; B = (q.z, q.w) line 2p+1
             if (k == 0) {
                 sg.put(0, make_float2(q.z, q.x));                  // X[0]   = A_dc + i B_dc   (swapped)
                 sg.put(L / 2, make_float2(q.w, q.y));              // X[L/2] = A_ny + i B_ny   (swapped)
@@ -196,25 +350,39 @@ k_lines_c2r(const float2* __restrict__ S, int nlines, long long img_stride, floa
                 sg.put(L - k, make_float2(q.z - q.y, q.x + q.w));  // X[L-k] = conj A + i conj B
             }
         }
+        if (item + (int)gridDim.x < items) load_spec(item + gridDim.x, qn);
+        __syncthreads();
+        float2 x[EPT];
+#pragma unroll
+        for (int i = 0; i < EPT; ++i) x[i] = sb.get(IX::in(t, i));
+        __syncthreads();
+        fft_regs<L>(t, sb, x);
+        if (staged) mbar_wait(&bar, parity);
+        parity ^= 1;
+        const int pair = item * GP + g;
+        if (pair < npairs) {
+            const long long base = ibase + (long long)(2 * pair) * L;
+            const float* sv = stage_v + 2 * g * L;
+            const float* sz = stage_z + 2 * g * L;
+#pragma unroll
+            for (int i = 0; i < EPT; ++i) {
+                const int idx = IX::out(t, i);
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    // swapped output: .y = real part -> line 2*pair, .x = imag part -> line 2*pair + 1
+                    const float gval = (h == 0 ? x[i].y : x[i].x) * gs;
+                    const int sh = idx + (h ? L : 0);
+                    const long long eh = base + sh;
+                    if (p_gout) p_gout[eh] = gval;
+                    float v = gval;
+                    if (p_vadd) v += sv[sh];
+                    if (p_vout) p_vout[eh] = v;
+                    if (p_zout) p_zout[eh] = sz[sh] - step * v;
+                }
+            }
+        }
+        __syncthreads();                            // staging + exchange buffers free for the next item
     }
-    __syncthreads();
-    const float gs = inv_n * (ep.gscale_ptr ? ep.gscale_ptr[img] : ep.gscale);
-    const float step = ep.step_ptr ? ep.step_ptr[img] : ep.step;
-    auto emit = [&](long long e, float graw) {
-        const float gval = graw * gs;
-        if (ep.g_out) ep.g_out[e] = gval;
-        float v = gval;
-        if (ep.vadd) v += ep.vadd[e];
-        if (ep.v_out) ep.v_out[e] = v;
-        if (ep.z_out) ep.z_out[e] = ep.z_in[e] - step * v;
-    };
-    auto ld = [&](int idx) -> float2 { return active ? sb.get(idx) : make_float2(0.f, 0.f); };
-    auto st = [&](int idx, float2 v) {
-        if (!active) return;
-        emit(base + idx, v.y);          // swapped output: .y = real part -> line 2*pair
-        emit(base + L + idx, v.x);      //                 .x = imag part -> line 2*pair + 1
-    };
-    fft_forward<L, true>(t, sb, ld, st);
 }
 
 // ------------------------------------------------------------------ selection bits

@@ -23,6 +23,33 @@ __device__ float2 g_tw[PNP_TW_N];
 
 namespace pnp {
 
+// ------------------------------------------------------------------ TMA bulk copy + mbarrier (sm_90+)
+// 1-D bulk copies global -> shared issued by ONE thread; completion is signalled on an mbarrier by
+// byte count (complete_tx), every consumer thread waits on the barrier's phase parity.
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "MBAR_WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra MBAR_DONE_%=;\n\t"
+        "bra MBAR_WAIT_%=;\n\t"
+        "MBAR_DONE_%=:\n\t"
+        "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+
 __device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
 __device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
@@ -93,64 +120,97 @@ struct SmemBuf {
     __device__ __forceinline__ void put(int i, float2 v) const { int p = fpad(i); re[p] = v.x; im[p] = v.y; }
 };
 
-// One Stockham stage.  FIRST: inputs come from ld(idx); LAST: outputs go to st(idx, v).
-// LD_SMEM says the FIRST-stage loader itself reads the exchange buffer (needs a barrier before
-// the stage writes it).
-template <int L, int R, int NSP, bool FIRST, bool LAST, bool LD_SMEM, class Load, class Store>
-__device__ __forceinline__ void fft_stage(int t, const SmemBuf& sb, Load& ld, Store& st) {
+// ---------------------------------------------------------------------------------- register API
+// Thread t of a group owns, before AND after the transform, the elements  idx = t + T*m, m < EPT
+// (only their order inside the register array differs), so element-wise work on the spectrum and
+// a following inverse transform need no shared-memory exchange at all.
+//   input  order: x[b*R0 + r]            holds element  (t + b*T) + r*(L/R0)
+//   output order: x[b*RL + r] (RL last radix) holds element  (t + b*T) + r*(L/RL)
+template <int L> struct FftIdx {
+    using P = FftPlan<L>;
+    static constexpr int EPT = P::EPT, T = L / P::EPT;
+    static constexpr int RL = P::NS == 1 ? P::R0 : (P::NS == 2 ? P::R1 : P::R2);
+    __host__ __device__ static constexpr int in(int t, int i) { return t + (i / P::R0) * T + (i % P::R0) * (L / P::R0); }
+    __host__ __device__ static constexpr int out(int t, int i) { return t + (i / RL) * T + (i % RL) * (L / RL); }
+    // register slot (input order) that holds the element with multiplier m (idx = t + T*m)
+    __host__ __device__ static constexpr int in_slot(int m) {
+        // m = b + r * (L/R0)/T  with b < EPT/R0
+        return (m % (EPT / P::R0)) * P::R0 + m / (EPT / P::R0);
+    }
+    __host__ __device__ static constexpr int out_slot(int m) { return (m % (EPT / RL)) * RL + m / (EPT / RL); }
+};
+
+template <int L, int R, int NSP>
+__device__ __forceinline__ void fft_reg_stage(int t, float2 (&x)[FftPlan<L>::EPT]) {
     constexpr int EPT = FftPlan<L>::EPT;
     constexpr int T = L / EPT;
     constexpr int NB = EPT / R;
-    constexpr int LR = L / R;
-    float2 v[NB][R];
 #pragma unroll
     for (int b = 0; b < NB; ++b) {
         const int j = t + b * T;
+        float2 v[R];
 #pragma unroll
-        for (int r = 0; r < R; ++r) {
-            const int idx = j + r * LR;
-            if (FIRST) v[b][r] = ld(idx); else v[b][r] = sb.get(idx);
-        }
-    }
-    if (!FIRST || LD_SMEM) __syncthreads();      // every read done before the in-place writes
-#pragma unroll
-    for (int b = 0; b < NB; ++b) {
-        const int j = t + b * T;
+        for (int r = 0; r < R; ++r) v[r] = x[b * R + r];
         if (NSP > 1) {
             const int k = j % NSP;
 #pragma unroll
-            for (int r = 1; r < R; ++r) {
-                const float2 w = g_tw[(r * k) * (PNP_TW_N / (NSP * R))];
-                v[b][r] = cmul(v[b][r], w);
-            }
+            for (int r = 1; r < R; ++r) v[r] = cmul(v[r], g_tw[(r * k) * (PNP_TW_N / (NSP * R))]);
         }
-        Dft<R>::run(v[b]);
-        const int base = (j / NSP) * (NSP * R) + (j % NSP);
+        Dft<R>::run(v);
 #pragma unroll
-        for (int r = 0; r < R; ++r) {
-            const int idx = base + r * NSP;
-            if (LAST) st(idx, v[b][r]); else sb.put(idx, v[b][r]);
-        }
+        for (int r = 0; r < R; ++r) x[b * R + r] = v[r];
     }
-    if (!LAST) __syncthreads();                  // exchange visible to the next stage
 }
 
-// Forward FFT of length L by threads t = 0 .. fft_threads<L>()-1 of a group.  Every thread of
-// the CTA must call it (it contains __syncthreads()).  The exchange buffer must be free on entry
-// unless LD_SMEM, in which case ld() may read it.
+// exchange between a stage of radix RA (prefix NSP) and the next stage of radix RB
+template <int L, int RA, int NSP, int RB>
+__device__ __forceinline__ void fft_reg_exchange(int t, const SmemBuf& sb, float2 (&x)[FftPlan<L>::EPT]) {
+    constexpr int EPT = FftPlan<L>::EPT;
+    constexpr int T = L / EPT;
+#pragma unroll
+    for (int b = 0; b < EPT / RA; ++b) {
+        const int j = t + b * T;
+        const int base = (j / NSP) * (NSP * RA) + (j % NSP);
+#pragma unroll
+        for (int r = 0; r < RA; ++r) sb.put(base + r * NSP, x[b * RA + r]);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int b = 0; b < EPT / RB; ++b) {
+        const int j = t + b * T;
+#pragma unroll
+        for (int r = 0; r < RB; ++r) x[b * RB + r] = sb.get(j + r * (L / RB));
+    }
+}
+
+// In-register forward FFT.  The exchange buffer must be free on entry; on exit the LAST exchange's
+// reads may still be in flight in other threads: callers sync before writing the buffer again.
+template <int L>
+__device__ __forceinline__ void fft_regs(int t, const SmemBuf& sb, float2 (&x)[FftPlan<L>::EPT]) {
+    using P = FftPlan<L>;
+    fft_reg_stage<L, P::R0, 1>(t, x);
+    if constexpr (P::NS >= 2) {
+        fft_reg_exchange<L, P::R0, 1, P::R1>(t, sb, x);
+        fft_reg_stage<L, P::R1, P::R0>(t, x);
+    }
+    if constexpr (P::NS >= 3) {
+        __syncthreads();                         // reads of the first exchange done before the second writes
+        fft_reg_exchange<L, P::R1, P::R0, P::R2>(t, sb, x);
+        fft_reg_stage<L, P::R2, P::R0 * P::R1>(t, x);
+    }
+}
+
+// functor API kept for callers that stream through global / shared memory directly
 template <int L, bool LD_SMEM, class Load, class Store>
 __device__ __forceinline__ void fft_forward(int t, const SmemBuf& sb, Load& ld, Store& st) {
-    using P = FftPlan<L>;
-    if constexpr (P::NS == 1) {
-        fft_stage<L, P::R0, 1, true, true, LD_SMEM>(t, sb, ld, st);
-    } else if constexpr (P::NS == 2) {
-        fft_stage<L, P::R0, 1, true, false, LD_SMEM>(t, sb, ld, st);
-        fft_stage<L, P::R1, P::R0, false, true, false>(t, sb, ld, st);
-    } else {
-        fft_stage<L, P::R0, 1, true, false, LD_SMEM>(t, sb, ld, st);
-        fft_stage<L, P::R1, P::R0, false, false, false>(t, sb, ld, st);
-        fft_stage<L, P::R2, P::R0 * P::R1, false, true, false>(t, sb, ld, st);
-    }
+    constexpr int EPT = FftPlan<L>::EPT;
+    float2 x[EPT];
+#pragma unroll
+    for (int i = 0; i < EPT; ++i) x[i] = ld(FftIdx<L>::in(t, i));
+    if (LD_SMEM) __syncthreads();                // loader read the exchange buffer
+    fft_regs<L>(t, sb, x);
+#pragma unroll
+    for (int i = 0; i < EPT; ++i) st(FftIdx<L>::out(t, i), x[i]);
 }
 
 }  // namespace pnp

@@ -54,8 +54,15 @@ template <int L> constexpr int lines_gp() {            // line pairs per CTA in 
 template <int L> constexpr int cols_nc() {             // packed columns per CTA in pass 2
     return pnp::fft_threads<L>() >= 128 ? 1 : (pnp::fft_threads<L>() >= 64 ? 2 : (64 / pnp::fft_threads<L>() > 8 ? 8 : 64 / pnp::fft_threads<L>()));
 }
-template <int L> constexpr size_t lines_smem() { return sizeof(float) * pnp::group_stride<L, lines_gp<L>()>() * lines_gp<L>(); }
-template <int L> constexpr size_t cols_smem() { return sizeof(float) * 2 * pnp::fft_plane<L>() * cols_nc<L>(); }
+// exchange planes + two staging buffers of 2*GP lines each (TMA bulk copy targets)
+template <int L> constexpr size_t lines_smem() {
+    return sizeof(float) * (pnp::lines_stage_off<L, lines_gp<L>()>() + 4 * lines_gp<L>() * L);
+}
+// exchange planes + one staging buffer of NC columns (complex)
+template <int L> constexpr size_t cols_smem() {
+    return sizeof(float) * (pnp::cols_stage_off<L, cols_nc<L>()>() + 2 * cols_nc<L>() * L);
+}
+template <int L> constexpr size_t conv_smem() { return sizeof(float) * 2 * pnp::fft_plane<L>() * cols_nc<L>(); }
 
 template <int L>
 int set_attrs() {
@@ -65,7 +72,7 @@ int set_attrs() {
     cudaFuncAttributes fa;
     CU_TRY(cudaFuncGetAttributes(&fa, pnp::k_sigma_mad<L>));
     CU_TRY(cudaFuncGetAttributes(&fa, pnp::k_haar_bayes<L>));
-    CU_TRY(cudaFuncSetAttribute(pnp::k_cols_conv<L, cols_nc<L>()>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cols_smem<L>()));
+    CU_TRY(cudaFuncSetAttribute(pnp::k_cols_conv<L, cols_nc<L>()>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)conv_smem<L>()));
     return PNP_OK;
 }
 
@@ -74,17 +81,33 @@ int launch_conv(float2* S, const float2* Bf, const float2* twn, int H, int batch
     constexpr int NC = cols_nc<L>();
     const int tasks = H / 2 + 1;
     dim3 grid((tasks + NC - 1) / NC, batch);
-    pnp::k_cols_conv<L, NC><<<grid, NC * pnp::fft_threads<L>(), cols_smem<L>(), st>>>(S, Bf, twn, H, conj_kernel,
+    pnp::k_cols_conv<L, NC><<<grid, NC * pnp::fft_threads<L>(), conv_smem<L>(), st>>>(S, Bf, twn, H, conj_kernel,
                                                                                      (long long)tasks * L);
     LAUNCH_CHECK();
     return PNP_OK;
+}
+
+int g_num_sms = 148;
+
+template <class K>
+int persistent_ctas(K kernel, int threads, size_t smem, int items, int batch) {
+    static int per_sm = 0;                 // one static per kernel instantiation
+    if (per_sm == 0) {
+        int n = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, threads, smem) != cudaSuccess || n < 1) n = 1;
+        per_sm = n;
+    }
+    long long cap = (long long)g_num_sms * per_sm / (batch > 0 ? batch : 1);
+    if (cap < 1) cap = 1;
+    return (int)(items < cap ? items : cap);
 }
 
 template <int L>
 int launch_r2c(const pnp_csmri_grad_args& a, cudaStream_t st) {
     constexpr int GP = lines_gp<L>();
     const int pairs = a.W / 2;
-    dim3 grid((pairs + GP - 1) / GP, a.batch);
+    const int items = (pairs + GP - 1) / GP;
+    dim3 grid(persistent_ctas(pnp::k_lines_r2c<L, GP>, GP * pnp::fft_threads<L>(), lines_smem<L>(), items, a.batch), a.batch);
     pnp::k_lines_r2c<L, GP><<<grid, GP * pnp::fft_threads<L>(), lines_smem<L>(), st>>>(
         a.a, a.b, reinterpret_cast<float2*>(a.S), a.W, (long long)a.H * a.W);
     LAUNCH_CHECK();
@@ -95,7 +118,8 @@ template <int L>
 int launch_cols(const pnp_csmri_grad_args& a, cudaStream_t st) {
     constexpr int NC = cols_nc<L>();
     const int hp = a.H / 2;
-    dim3 grid(hp / NC, a.batch);
+    const int items = (hp - 1 + NC - 1) / NC;
+    dim3 grid(persistent_ctas(pnp::k_cols_mask<L, NC>, NC * pnp::fft_threads<L>(), cols_smem<L>(), items, a.batch), a.batch);
     pnp::k_cols_mask<L, NC><<<grid, NC * pnp::fft_threads<L>(), cols_smem<L>(), st>>>(
         reinterpret_cast<float2*>(a.S), a.bits, reinterpret_cast<const float2*>(a.Y1),
         reinterpret_cast<const float2*>(a.Y2), reinterpret_cast<const float2*>(a.Y1n),
@@ -108,7 +132,8 @@ template <int L>
 int launch_c2r(const pnp_csmri_grad_args& a, cudaStream_t st) {
     constexpr int GP = lines_gp<L>();
     const int pairs = a.W / 2;
-    dim3 grid((pairs + GP - 1) / GP, a.batch);
+    const int items = (pairs + GP - 1) / GP;
+    dim3 grid(persistent_ctas(pnp::k_lines_c2r<L, GP>, GP * pnp::fft_threads<L>(), lines_smem<L>(), items, a.batch), a.batch);
     pnp::GradEpilogue ep{a.gscale, a.gscale_ptr, a.step, a.step_ptr, a.g_out, a.vadd, a.v_out, a.z_in, a.z_out};
     const float inv_n = (float)(1.0 / ((double)a.H * (double)a.W));
     pnp::k_lines_c2r<L, GP><<<grid, GP * pnp::fft_threads<L>(), lines_smem<L>(), st>>>(
@@ -183,6 +208,7 @@ int pnp_init(void) {
     CU_TRY(cudaGetDevice(&dev));
     if (dev < 0 || dev >= 64) return fail(PNP_ERR_ARG, "device index %d out of range", dev);
     if (g_init[dev]) return PNP_OK;
+    CU_TRY(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
     std::vector<float2> tw(PNP_TW_N);
     for (int m = 0; m < PNP_TW_N; ++m) {
         const double ang = -2.0 * M_PI * (double)m / (double)PNP_TW_N;
