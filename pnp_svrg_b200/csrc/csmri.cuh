@@ -85,6 +85,8 @@ k_lines_r2c(const float* __restrict__ a, const float* __restrict__ b, float2* __
     __syncthreads();
     int item = blockIdx.x;
     if (threadIdx.x == 0 && item < items) issue(item);
+    FftTw<L> tw;
+    tw.init(t);
     unsigned parity = 0;
     for (; item < items; item += gridDim.x) {
         float2 x[EPT];
@@ -106,7 +108,7 @@ k_lines_r2c(const float* __restrict__ a, const float* __restrict__ b, float2* __
         }
         __syncthreads();                            // staging consumed -> refill it for the next item
         if (threadIdx.x == 0 && item + (int)gridDim.x < items) issue(item + gridDim.x);
-        fft_regs<L>(t, sb, x);
+        fft_regs<L>(t, sb, x, tw);
         if (FftPlan<L>::NS > 1) __syncthreads();
 #pragma unroll
         for (int i = 0; i < EPT; ++i) sb.put(FftIdx<L>::out(t, i), x[i]);
@@ -170,6 +172,7 @@ k_cols_mask(float2* __restrict__ S, const unsigned char* __restrict__ bits,
     const int img = blockIdx.y;
     const SmemBuf sb{smem + g * 2 * PL, smem + g * 2 * PL + PL};
     float2* stage = reinterpret_cast<float2*>(smem + cols_stage_off<L, NC>());      // NC columns of L complex
+    const unsigned char* stage_bits = reinterpret_cast<const unsigned char*>(stage + NC * L);   // + NC rows of L bytes
     float2* Si = S + (long long)img * hp * L;
     const unsigned char* bi = bits + (long long)img * bits_img_stride;
     const bool use_y = Y1 != nullptr;
@@ -181,34 +184,37 @@ k_cols_mask(float2* __restrict__ S, const unsigned char* __restrict__ bits,
         int nc = hp - 1 - item * NC;
         nc = nc < NC ? nc : NC;
         const unsigned bytes = (unsigned)(nc * L * sizeof(float2));
-        mbar_expect_tx(&bar, bytes);
+        mbar_expect_tx(&bar, bytes + (unsigned)(nc * L));
         bulk_g2s(stage, Si + (long long)(1 + item * NC) * L, bytes, &bar);
+        bulk_g2s(const_cast<unsigned char*>(stage_bits), bi + (long long)(1 + item * NC) * L, (unsigned)(nc * L), &bar);
     };
     if (threadIdx.x == 0) { mbar_init(&bar, 1); mbar_fence_init(); }
     __syncthreads();
     int item = blockIdx.x;
     if (threadIdx.x == 0 && item < items) issue(item);
+    FftTw<L> tw;
+    tw.init(t);
     unsigned parity = 0;
     for (; item < items; item += gridDim.x) {
         const int col = 1 + item * NC + g;
         const bool active = col < hp;
         const long long crow = (long long)(active ? col : 0) * L;
         unsigned long long bbp = 0ull;                                      // 4 selection bits per element
-#pragma unroll
-        for (int m = 0; m < EPT; ++m) bbp |= (unsigned long long)(bi[crow + t + T * m] & 0xFu) << (4 * m);
         float2 x[EPT];
         mbar_wait(&bar, parity);
         parity ^= 1;
         if (active) {
 #pragma unroll
             for (int i = 0; i < EPT; ++i) x[i] = stage[g * L + IX::in(t, i)];
+#pragma unroll
+            for (int m = 0; m < EPT; ++m) bbp |= (unsigned long long)(stage_bits[g * L + t + T * m] & 0xFu) << (4 * m);
         } else {
 #pragma unroll
             for (int i = 0; i < EPT; ++i) x[i] = make_float2(0.f, 0.f);
         }
         __syncthreads();                            // staging consumed -> refill it for the next item
         if (threadIdx.x == 0 && item + (int)gridDim.x < items) issue(item + gridDim.x);
-        fft_regs<L>(t, sb, x);
+        fft_regs<L>(t, sb, x, tw);
         // selection in registers, then reorder (same elements t + T*m) into the inverse's input order
         float2 y[EPT];
 #pragma unroll
@@ -219,7 +225,7 @@ k_cols_mask(float2* __restrict__ S, const unsigned char* __restrict__ bits,
             y[IX::in_slot(m)] = cswap(o);
         }
         if (FftPlan<L>::NS > 1) __syncthreads();
-        fft_regs<L>(t, sb, y);
+        fft_regs<L>(t, sb, y, tw);
         if (active) {
             float2* Sc = Si + crow;
 #pragma unroll
@@ -333,6 +339,8 @@ k_lines_c2r(const float2* __restrict__ S, int nlines, long long img_stride, floa
     float4 qn[NQ];
     int item = blockIdx.x;
     if (item < items) load_spec(item, qn);
+    FftTw<L> tw;
+    tw.init(t);
     for (; item < items; item += gridDim.x) {
         if (staged && threadIdx.x == 0) issue(item);
         // X[k] = A[k] + i B[k] of the two lines, written re/im swapped for the inverse transform
@@ -356,7 +364,7 @@ k_lines_c2r(const float2* __restrict__ S, int nlines, long long img_stride, floa
 #pragma unroll
         for (int i = 0; i < EPT; ++i) x[i] = sb.get(IX::in(t, i));
         __syncthreads();
-        fft_regs<L>(t, sb, x);
+        fft_regs<L>(t, sb, x, tw);
         if (staged) mbar_wait(&bar, parity);
         parity ^= 1;
         const int pair = item * GP + g;

@@ -108,16 +108,17 @@ template <> struct FftPlan<4096> { static constexpr int NS = 3, R0 = 16, R1 = 16
 
 template <int L> __host__ __device__ constexpr int fft_threads() { return L / FftPlan<L>::EPT; }
 
-// padded index into a split re/im plane (one extra word every 32 to spread power-of-two strides)
-__host__ __device__ __forceinline__ constexpr int fpad(int i) { return i + (i >> 5); }
-// floats in ONE plane of one transform's exchange buffer
-template <int L> __host__ __device__ constexpr int fft_plane() { return L + (L >> 5) + 1; }
+// padded index into the complex exchange buffer: one extra float2 every 16 spreads the
+// power-of-two strides of the Stockham exchanges over the banks (64-bit accesses: 16 lanes per phase)
+__host__ __device__ __forceinline__ constexpr int fpad(int i) { return i + (i >> 4); }
+// floats in HALF of one transform's exchange buffer (the buffer holds 2 * fft_plane<L>() floats)
+template <int L> __host__ __device__ constexpr int fft_plane() { return L + (L >> 4) + 2; }
 
 struct SmemBuf {
-    float* re;
+    float* re;        // base of the buffer (float2 elements); `im` kept for layout compatibility
     float* im;
-    __device__ __forceinline__ float2 get(int i) const { int p = fpad(i); return make_float2(re[p], im[p]); }
-    __device__ __forceinline__ void put(int i, float2 v) const { int p = fpad(i); re[p] = v.x; im[p] = v.y; }
+    __device__ __forceinline__ float2 get(int i) const { return reinterpret_cast<const float2*>(re)[fpad(i)]; }
+    __device__ __forceinline__ void put(int i, float2 v) const { reinterpret_cast<float2*>(re)[fpad(i)] = v; }
 };
 
 // ---------------------------------------------------------------------------------- register API
@@ -140,21 +141,53 @@ template <int L> struct FftIdx {
     __host__ __device__ static constexpr int out_slot(int m) { return (m % (EPT / RL)) * RL + m / (EPT / RL); }
 };
 
-template <int L, int R, int NSP>
-__device__ __forceinline__ void fft_reg_stage(int t, float2 (&x)[FftPlan<L>::EPT]) {
+// w[r] = w1^r for r = 1..R-1 with multiplication depth <= 4 (error ~2e-7)
+template <int R>
+__device__ __forceinline__ void twiddle_powers(float2 w1, float2 (&w)[16]) {
+    w[1] = w1;
+    if (R > 2) { w[2] = cmul(w1, w1); w[3] = cmul(w[2], w1); }
+    if (R > 4) { w[4] = cmul(w[2], w[2]); w[5] = cmul(w[4], w1); w[6] = cmul(w[4], w[2]); w[7] = cmul(w[4], w[3]); }
+    if (R > 8) {
+        w[8] = cmul(w[4], w[4]);
+#pragma unroll
+        for (int r = 1; r < 8; ++r) w[8 + r] = cmul(w[8], w[r]);
+    }
+}
+
+// per-thread base twiddles exp(-2*pi*i*k/(NSP*R)), k = (t + b*T) % NSP, of the stages after the
+// first.  They depend on the thread only, so persistent kernels load them once.
+template <int L> struct FftTw {
+    using P = FftPlan<L>;
+    static constexpr int EPT = P::EPT, T = L / P::EPT;
+    static constexpr int NB1 = P::NS >= 2 ? EPT / P::R1 : 1;
+    static constexpr int NB2 = P::NS >= 3 ? EPT / P::R2 : 1;
+    float2 s1[NB1], s2[NB2];
+    __device__ __forceinline__ void init(int t) {
+        if (P::NS >= 2) {
+#pragma unroll
+            for (int b = 0; b < NB1; ++b) s1[b] = g_tw[((t + b * T) % P::R0) * (PNP_TW_N / (P::R0 * P::R1))];
+        }
+        if (P::NS >= 3) {
+#pragma unroll
+            for (int b = 0; b < NB2; ++b) s2[b] = g_tw[((t + b * T) % (P::R0 * P::R1)) * (PNP_TW_N / (P::R0 * P::R1 * P::R2))];
+        }
+    }
+};
+
+template <int L, int R, int NSP, int NBW>
+__device__ __forceinline__ void fft_reg_stage(int t, float2 (&x)[FftPlan<L>::EPT], const float2 (&w1)[NBW]) {
     constexpr int EPT = FftPlan<L>::EPT;
-    constexpr int T = L / EPT;
     constexpr int NB = EPT / R;
 #pragma unroll
     for (int b = 0; b < NB; ++b) {
-        const int j = t + b * T;
         float2 v[R];
 #pragma unroll
         for (int r = 0; r < R; ++r) v[r] = x[b * R + r];
         if (NSP > 1) {
-            const int k = j % NSP;
+            float2 w[16];
+            twiddle_powers<R>(w1[b], w);
 #pragma unroll
-            for (int r = 1; r < R; ++r) v[r] = cmul(v[r], g_tw[(r * k) * (PNP_TW_N / (NSP * R))]);
+            for (int r = 1; r < R; ++r) v[r] = cmul(v[r], w[r]);
         }
         Dft<R>::run(v);
 #pragma unroll
@@ -186,18 +219,24 @@ __device__ __forceinline__ void fft_reg_exchange(int t, const SmemBuf& sb, float
 // In-register forward FFT.  The exchange buffer must be free on entry; on exit the LAST exchange's
 // reads may still be in flight in other threads: callers sync before writing the buffer again.
 template <int L>
-__device__ __forceinline__ void fft_regs(int t, const SmemBuf& sb, float2 (&x)[FftPlan<L>::EPT]) {
+__device__ __forceinline__ void fft_regs(int t, const SmemBuf& sb, float2 (&x)[FftPlan<L>::EPT], const FftTw<L>& tw) {
     using P = FftPlan<L>;
-    fft_reg_stage<L, P::R0, 1>(t, x);
+    fft_reg_stage<L, P::R0, 1>(t, x, tw.s1);
     if constexpr (P::NS >= 2) {
         fft_reg_exchange<L, P::R0, 1, P::R1>(t, sb, x);
-        fft_reg_stage<L, P::R1, P::R0>(t, x);
+        fft_reg_stage<L, P::R1, P::R0>(t, x, tw.s1);
     }
     if constexpr (P::NS >= 3) {
         __syncthreads();                         // reads of the first exchange done before the second writes
         fft_reg_exchange<L, P::R1, P::R0, P::R2>(t, sb, x);
-        fft_reg_stage<L, P::R2, P::R0 * P::R1>(t, x);
+        fft_reg_stage<L, P::R2, P::R0 * P::R1>(t, x, tw.s2);
     }
+}
+template <int L>
+__device__ __forceinline__ void fft_regs(int t, const SmemBuf& sb, float2 (&x)[FftPlan<L>::EPT]) {
+    FftTw<L> tw;
+    tw.init(t);
+    fft_regs<L>(t, sb, x, tw);
 }
 
 // functor API kept for callers that stream through global / shared memory directly

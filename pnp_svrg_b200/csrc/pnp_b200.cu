@@ -60,7 +60,7 @@ template <int L> constexpr size_t lines_smem() {
 }
 // exchange planes + one staging buffer of NC columns (complex)
 template <int L> constexpr size_t cols_smem() {
-    return sizeof(float) * (pnp::cols_stage_off<L, cols_nc<L>()>() + 2 * cols_nc<L>() * L);
+    return sizeof(float) * (pnp::cols_stage_off<L, cols_nc<L>()>() + 2 * cols_nc<L>() * L) + (size_t)cols_nc<L>() * L;
 }
 template <int L> constexpr size_t conv_smem() { return sizeof(float) * 2 * pnp::fft_plane<L>() * cols_nc<L>(); }
 
