@@ -192,7 +192,7 @@ class Epoch:
         h = hook or (lambda name: None)
         eng.sample_sel_device(); h('sel_sample')
         gk = dict(b=self.w, sel=eng.sel, with_y=False, gscale=1.0 / B, vadd=self.mu, step_ptr=eng.step,
-                  z_in=eng.z, z_out=eng.z)
+                  z_in=eng.z, z_out=eng.z, clear_sel=True)
         if hook is None:
             p._dev_grad(eng.z, **gk)
         else:                                  # same three kernels, launched one by one so each can be timed
@@ -236,7 +236,7 @@ class Epoch:
         eng.stream.synchronize()
 
 
-LAUNCHES_PER_INNER = 8        # memset + sel_sample + r2c + cols + c2r + sigma_mad + haar_bayes + advance
+LAUNCHES_PER_INNER = 7        # sel_sample + r2c + cols + c2r + sigma_mad + haar_bayes + advance
 LAUNCHES_PER_SNAPSHOT = 4     # r2c + cols + c2r + D2D copy
 
 

@@ -65,6 +65,8 @@ typedef struct {
     float* z_out;
     int phases;                   /* 0 = all three passes; else bit0 lines r2c, bit1 columns+selection,
                                      bit2 lines c2r + epilogue (used to time the passes one by one) */
+    int clear_bits;               /* != 0: the column pass zeroes `bits` after using it (single-use minibatch
+                                     selection; the next pnp_csmri_sel_* call then needs clear = 0) */
 } pnp_csmri_grad_args;
 int pnp_csmri_grad(const pnp_csmri_grad_args* args, void* stream);
 

@@ -24,7 +24,7 @@ class CsmriGradArgs(C.Structure):
         ('step', C.c_float), ('step_ptr', C.c_void_p),
         ('g_out', C.c_void_p), ('vadd', C.c_void_p), ('v_out', C.c_void_p),
         ('z_in', C.c_void_p), ('z_out', C.c_void_p),
-        ('phases', C.c_int),
+        ('phases', C.c_int), ('clear_bits', C.c_int),
     ]
 
 

@@ -20,7 +20,8 @@ from ..engine import LOG_CHUNK, Budget, Engine, stop_rule
 
 
 def _grad_update(eng, a, b, sel, with_y, gscale, **kw):
-    eng.p._dev_grad(a, b=b, sel=sel, with_y=with_y, gscale=gscale, **kw)
+    # the engine's minibatch selection is single use: the pass that consumes it leaves it zeroed
+    eng.p._dev_grad(a, b=b, sel=sel, with_y=with_y, gscale=gscale, clear_sel=sel is not None and sel is eng.sel, **kw)
 
 
 class _Faithful:
@@ -109,7 +110,7 @@ def _sel_ops(eng):
     if eng.mb_source == 'device':
         eng.sample_sel_device()
     else:
-        eng.p._dev_set_sel(eng.sel, eng.idx_dev, eng.B)
+        eng.p._dev_set_sel(eng.sel, eng.idx_dev, eng.B, clear=False)
 
 
 # ------------------------------------------------------------------------------------------ GD

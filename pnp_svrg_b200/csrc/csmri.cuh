@@ -161,7 +161,7 @@ __global__ void __launch_bounds__(NC * (L / FftPlan<L>::EPT), (NC * (L / FftPlan
 k_cols_mask(float2* __restrict__ S, const unsigned char* __restrict__ bits,
             const float2* __restrict__ Y1, const float2* __restrict__ Y2,
             const float2* __restrict__ Y1n, const float2* __restrict__ Y2n,
-            int hp, long long bits_img_stride, long long y_img_stride) {
+            int hp, long long bits_img_stride, long long y_img_stride, unsigned char* __restrict__ clear_bits) {
     constexpr int T = fft_threads<L>();
     constexpr int EPT = FftPlan<L>::EPT;
     constexpr int PL = fft_plane<L>();
@@ -214,6 +214,10 @@ k_cols_mask(float2* __restrict__ S, const unsigned char* __restrict__ bits,
         }
         __syncthreads();                            // staging consumed -> refill it for the next item
         if (threadIdx.x == 0 && item + (int)gridDim.x < items) issue(item + gridDim.x);
+        if (clear_bits && active) {                 // minibatch selection is single use: leave the row zeroed
+            unsigned char* cb = clear_bits + (long long)img * bits_img_stride + crow;
+            for (int i = t; i < L / 16; i += T) reinterpret_cast<uint4*>(cb)[i] = make_uint4(0u, 0u, 0u, 0u);
+        }
         fft_regs<L>(t, sb, x, tw);
         // selection in registers, then reorder (same elements t + T*m) into the inverse's input order
         float2 y[EPT];
@@ -276,6 +280,10 @@ k_cols_mask(float2* __restrict__ S, const unsigned char* __restrict__ bits,
         if (g == 0) {
 #pragma unroll
             for (int i = 0; i < EPT; ++i) Si[IX::out(t, i)] = cswap(x[i]);
+            if (clear_bits) {
+                unsigned char* cb = clear_bits + (long long)img * bits_img_stride;
+                for (int i = t; i < L / 16; i += T) reinterpret_cast<uint4*>(cb)[i] = make_uint4(0u, 0u, 0u, 0u);
+            }
         }
     }
 }

@@ -123,7 +123,8 @@ int launch_cols(const pnp_csmri_grad_args& a, cudaStream_t st) {
     pnp::k_cols_mask<L, NC><<<grid, NC * pnp::fft_threads<L>(), cols_smem<L>(), st>>>(
         reinterpret_cast<float2*>(a.S), a.bits, reinterpret_cast<const float2*>(a.Y1),
         reinterpret_cast<const float2*>(a.Y2), reinterpret_cast<const float2*>(a.Y1n),
-        reinterpret_cast<const float2*>(a.Y2n), hp, (long long)a.W * hp, (long long)a.W * hp);
+        reinterpret_cast<const float2*>(a.Y2n), hp, (long long)a.W * hp, (long long)a.W * hp,
+        a.clear_bits ? const_cast<unsigned char*>(a.bits) : nullptr);
     LAUNCH_CHECK();
     return PNP_OK;
 }

@@ -132,15 +132,23 @@ k_haar_bayes(const float* __restrict__ zin, float* __restrict__ zout, const floa
     const long long off = (long long)img * img_stride + (long long)(active ? line : 0) * L + (wil * 32 + lane) * VPL;
 
     float x[VPL];
+    float xr[VPL];                               // ground truth, fetched up front so both streams overlap
     if (VPL >= 4) {
 #pragma unroll
         for (int i = 0; i < VPL / 4; ++i) {
             const float4 q = reinterpret_cast<const float4*>(zin + off)[i];
             x[4 * i] = q.x; x[4 * i + 1] = q.y; x[4 * i + 2] = q.z; x[4 * i + 3] = q.w;
         }
+        if (xrec) {
+#pragma unroll
+            for (int i = 0; i < VPL / 4; ++i) {
+                const float4 r = reinterpret_cast<const float4*>(xrec + off)[i];
+                xr[4 * i] = r.x; xr[4 * i + 1] = r.y; xr[4 * i + 2] = r.z; xr[4 * i + 3] = r.w;
+            }
+        }
     } else {
 #pragma unroll
-        for (int i = 0; i < VPL; ++i) x[i] = zin[off + i];
+        for (int i = 0; i < VPL; ++i) { x[i] = zin[off + i]; if (xrec) xr[i] = xrec[off + i]; }
     }
 
     double se = sp.sig_log ? *slot_ptr(const_cast<double*>(sp.sig_log), slot, batch, img) / (double)nlines
@@ -226,8 +234,8 @@ k_haar_bayes(const float* __restrict__ zin, float* __restrict__ zout, const floa
             for (int i = 0; i < VPL / 4; ++i) {
                 reinterpret_cast<float4*>(zout + off)[i] = make_float4(x[4 * i], x[4 * i + 1], x[4 * i + 2], x[4 * i + 3]);
                 if (xrec) {
-                    const float4 r = reinterpret_cast<const float4*>(xrec + off)[i];
-                    const float e0 = x[4 * i] - r.x, e1 = x[4 * i + 1] - r.y, e2 = x[4 * i + 2] - r.z, e3 = x[4 * i + 3] - r.w;
+                    const float e0 = x[4 * i] - xr[4 * i], e1 = x[4 * i + 1] - xr[4 * i + 1], e2 = x[4 * i + 2] - xr[4 * i + 2],
+                                e3 = x[4 * i + 3] - xr[4 * i + 3];
                     err += e0 * e0 + e1 * e1 + e2 * e2 + e3 * e3;
                 }
             }
@@ -235,7 +243,7 @@ k_haar_bayes(const float* __restrict__ zin, float* __restrict__ zout, const floa
 #pragma unroll
             for (int i = 0; i < VPL; ++i) {
                 zout[off + i] = x[i];
-                if (xrec) { const float e = x[i] - xrec[off + i]; err = fmaf(e, e, err); }
+                if (xrec) { const float e = x[i] - xr[i]; err = fmaf(e, e, err); }
             }
         }
     }

@@ -144,10 +144,11 @@ class Engine:
     def upload_sel(self):
         """pinned -> device copy of the staged minibatch and rebuild of the selection."""
         self.idx_dev.copy_(self.idx_host, non_blocking=True)
-        self.p._dev_set_sel(self.sel, self.idx_dev, self.B)
+        # the selection buffer is zero on entry: the gradient pass that consumes it clears it again
+        self.p._dev_set_sel(self.sel, self.idx_dev, self.B, clear=False)
 
     def sample_sel_device(self):
-        self.p._dev_sample_sel(self.sel, self.B, self.mb_seed, counter=self.draw_ptr)
+        self.p._dev_sample_sel(self.sel, self.B, self.mb_seed, counter=self.draw_ptr, clear=False)
 
     # ------------------------------------------------------------------ prox + log
     def prox(self, z_in, z_out):

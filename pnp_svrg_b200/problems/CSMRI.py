@@ -82,17 +82,17 @@ class CSMRI(Problem):
     def _dev_full_sel(self):
         return self._bits_full
 
-    def _dev_set_sel(self, sel, idx_dev, count, cursor=None, stride=0):
+    def _dev_set_sel(self, sel, idx_dev, count, cursor=None, stride=0, clear=True):
         _lib.check(_lib.load().pnp_csmri_sel_from_indices(D.ptr(sel), self.H, self.W, 1, D.ptr(idx_dev), int(count),
-                                                          int(stride), D.ptr(cursor), 1, D.stream()))
+                                                          int(stride), D.ptr(cursor), int(bool(clear)), D.stream()))
 
-    def _dev_sample_sel(self, sel, count, seed, counter=None, idx_out=None):
+    def _dev_sample_sel(self, sel, count, seed, counter=None, idx_out=None, clear=True):
         _lib.check(_lib.load().pnp_csmri_sel_sample(D.ptr(sel), self.H, self.W, 1, D.ptr(self._support),
                                                     D.ptr(self._m0_dev), 0, int(count), int(seed) & 0xffffffff,
-                                                    D.ptr(counter), D.ptr(idx_out), 1, D.stream()))
+                                                    D.ptr(counter), D.ptr(idx_out), int(bool(clear)), D.stream()))
 
     def _dev_grad(self, a, b=None, sel=None, with_y=True, gscale=1.0, gscale_ptr=None, step=0.0, step_ptr=None,
-                  g_out=None, vadd=None, v_out=None, z_in=None, z_out=None, phases=0):
+                  g_out=None, vadd=None, v_out=None, z_in=None, z_out=None, phases=0, clear_sel=False):
         """g = Re(ifft2(sel o fft2(a - b) - Ysel)) * gscale ; v = g + vadd ; z_out = z_in - step*v."""
         args = _lib.CsmriGradArgs(
             H=self.H, W=self.W, batch=1, a=D.ptr(a), b=D.ptr(b), S=D.ptr(self._S),
@@ -100,7 +100,8 @@ class CSMRI(Problem):
             Y1=D.ptr(self._Y1) if with_y else None, Y2=D.ptr(self._Y2) if with_y else None,
             Y1n=D.ptr(self._Y1n) if with_y else None, Y2n=D.ptr(self._Y2n) if with_y else None,
             gscale=float(gscale), gscale_ptr=D.ptr(gscale_ptr), step=float(step), step_ptr=D.ptr(step_ptr),
-            g_out=D.ptr(g_out), vadd=D.ptr(vadd), v_out=D.ptr(v_out), z_in=D.ptr(z_in), z_out=D.ptr(z_out), phases=int(phases))
+            g_out=D.ptr(g_out), vadd=D.ptr(vadd), v_out=D.ptr(v_out), z_in=D.ptr(z_in), z_out=D.ptr(z_out), phases=int(phases),
+            clear_bits=int(bool(clear_sel) and sel is not None))
         _lib.check(_lib.load().pnp_csmri_grad(C.byref(args), D.stream()))
 
     # ---- reference API ---------------------------------------------------------------------

@@ -63,15 +63,15 @@ class PhaseRetrieval(Problem):
     def _dev_new_sel(self, count=0):
         return torch.zeros(max(int(count), 1), dtype=torch.int32, device=self._device)
 
-    def _dev_set_sel(self, sel, idx_dev, count, cursor=None, stride=0):
+    def _dev_set_sel(self, sel, idx_dev, count, cursor=None, stride=0, clear=True):
         _lib.check(_lib.load().pnp_copy_f32(D.ptr(sel), D.ptr(idx_dev), int(count), D.stream()))
 
-    def _dev_sample_sel(self, sel, count, seed, counter=None, idx_out=None):
+    def _dev_sample_sel(self, sel, count, seed, counter=None, idx_out=None, clear=True):
         _lib.check(_lib.load().pnp_sample_indices(D.ptr(sel), int(self.M), int(count), int(seed) & 0xffffffff,
                                                   D.ptr(counter), D.stream()))
 
     def _dev_grad(self, a, b=None, sel=None, with_y=True, gscale=1.0, gscale_ptr=None, step=0.0, step_ptr=None,
-                  g_out=None, vadd=None, v_out=None, z_in=None, z_out=None, phases=0):
+                  g_out=None, vadd=None, v_out=None, z_in=None, z_out=None, phases=0, clear_sel=False):
         """g = [A_sel^T r(a)] - [A_sel^T r(b)] (two-point form when b is given), scaled by gscale."""
         args = _lib.PrGradArgs(
             A=D.ptr(self._A), n=self.N, M=int(self.M), z=D.ptr(a), w=D.ptr(b), y=D.ptr(self._y), rows=D.ptr(sel),
