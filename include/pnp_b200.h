@@ -186,7 +186,9 @@ int pnp_nlm_denoise(const float* z_in, float* z_out, int H, int W, int batch, in
  * scale/shift = folded eval-mode BatchNorm or bias (null = 1 / 0); slope = activation (0 ReLU,
  * 0.01 LeakyReLU).  mode 0 = DnCNN wrapper (min/max normalise by *stats*, residual net),
  * mode 1 = MMO (clamp, net + input, clamp).  act0/act1: scratch, PH*PW*64 floats each; stats: 2 ints.
- * precision 0 = fp32 CUDA cores (exact-parity path), 1 = bf16 tcgen05 tensor cores. */
+ * precision 0 = fp32 CUDA cores (exact-parity path); 1 = bf16 operands / fp32 accumulation on the tcgen05
+ * tensor cores for the 64->64 layers: act0/act1 are then bf16 buffers of PH*(PW+1)*64 elements that the
+ * caller ZEROES ONCE (one zero pad pixel per line is never written), and net->w_tc must be set. */
 #define PNP_CNN_MAX_LAYERS 32
 typedef struct {
     int n_layers;
@@ -197,6 +199,8 @@ typedef struct {
     float last_bias;
     int mode;
     float range, shift_in;
+    const void* w_tc[PNP_CNN_MAX_LAYERS];   /* middle layers for the tensor-core path: bf16 [192 (dp,co)][192 (dl,ci)],
+                                               null when only the fp32 path is used */
 } pnp_cnn_net;
 int pnp_cnn_forward(const pnp_cnn_net* net, const float* img, float* out, int PH, int PW, float* act0, float* act1,
                     int* stats, const float* xrec, double* mse_log, const int* slot, int precision, void* stream);

