@@ -227,6 +227,9 @@ int pnp_advance_scale(int* counters, int n, float* x, float factor, void* stream
 /* dst[0..n) = src[0..n)  (w = copy(z), algorithms/pnp_svrg.py:35; capturable device copy) */
 int pnp_copy_f32(float* dst, const float* src, long long n, void* stream);
 
+/* debugging knobs (key 1: tensor-core conv epilogue ablation bits); not part of the stable surface */
+int pnp_debug_set(int key, int value);
+
 /* ---- CUDA-graph helpers ---------------------------------------------------------------------
  * One inner iteration is launch-bound at 256x256 (about 2 MB of traffic); the host side captures
  * the iteration's launches once and replays the executable graph.  begin/end bracket the

@@ -95,6 +95,7 @@ PROTOTYPES = {
     'pnp_advance': (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
     'pnp_advance_scale': (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_float, C.c_void_p]),
     'pnp_copy_f32': (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p]),
+    'pnp_debug_set': (C.c_int, [C.c_int, C.c_int]),
     'pnp_graph_begin': (C.c_int, [C.c_void_p]),
     'pnp_graph_end': (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
     'pnp_graph_launch': (C.c_int, [C.c_void_p, C.c_void_p]),

@@ -44,12 +44,14 @@ namespace pnp {
 struct TcSmem {
     unsigned long long full[TC_STAGES], empty[TC_STAGES], bfull, tfull[2], tempty[2];
     unsigned tmem_base;
-    float halo[2][4][2][16];     // [chunk parity][epilogue warp][0: lane31 T_-1, 1: lane0 T_+1][16 channels]
+    __align__(16) float halo[2][4][2][16];     // [chunk parity][epilogue warp][0: lane31 T_-1, 1: lane0 T_+1][16 channels]
+    float2 affine[64];           // per output channel (scale, shift): folded BatchNorm / bias
 };
 
-__device__ __forceinline__ void mbar_wait_bounded(unsigned long long* bar, unsigned parity) {
+__device__ __forceinline__ void mbar_wait_bounded(unsigned long long* bar, unsigned parity, int backoff = 0) {
     unsigned done = 0;
     for (unsigned spin = 0; !done; ++spin) {
+        if (backoff && spin) __nanosleep(backoff);
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
             "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
@@ -104,7 +106,7 @@ __device__ __forceinline__ void tmem_ld16(unsigned taddr, float (&v)[16]) {
 __global__ void __launch_bounds__(TC_THREADS, 1)
 k_conv_mid_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
               __nv_bfloat16* __restrict__ out, const float* __restrict__ scale, const float* __restrict__ shift,
-              float slope, int PW, int S, int n_tiles) {
+              float slope, int PW, int S, int n_tiles, int dbg) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<unsigned long long>(smem_raw) + 1023ull) & ~1023ull);
     unsigned char* sB = base;                                   // 3 x 24 KiB
@@ -118,6 +120,10 @@ k_conv_mid_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
         mbar_init(&ctl->bfull, 1);
         for (int i = 0; i < 2; ++i) { mbar_init(&ctl->tfull[i], 1); mbar_init(&ctl->tempty[i], 4); }
         mbar_fence_init();
+    }
+    if (threadIdx.x >= 64 && threadIdx.x < 128) {
+        const int c = threadIdx.x - 64;
+        ctl->affine[c] = make_float2(scale ? scale[c] : 1.f, shift ? shift[c] : 0.f);
     }
     if (warp == 1) {                                            // TMEM: 512 columns (2 accumulators of 192)
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&ctl->tmem_base)), "r"(512u));
@@ -138,7 +144,7 @@ k_conv_mid_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
             for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
                 const int s0 = tile * TC_OUT_PER_TILE - 1;
                 for (int dl = -1; dl <= 1; ++dl) {
-                    mbar_wait_bounded(&ctl->empty[stage], phase ^ 1);
+                    mbar_wait_bounded(&ctl->empty[stage], phase ^ 1, (dbg & 16) ? 100 : 0);
                     mbar_expect_tx(&ctl->full[stage], TC_A_BYTES);
                     tma_load_2d(sA + stage * TC_A_BYTES, &tmA, 0, s0 + dl * pitch, &ctl->full[stage]);
                     if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
@@ -153,11 +159,11 @@ k_conv_mid_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
             int stage = 0, acc = 0;
             unsigned phase = 0, aphase = 0;
             for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-                mbar_wait_bounded(&ctl->tempty[acc], aphase ^ 1);          // epilogue has drained this accumulator
+                mbar_wait_bounded(&ctl->tempty[acc], aphase ^ 1, (dbg & 16) ? 100 : 0);   // epilogue has drained this accumulator
                 asm volatile("tcgen05.fence::after_thread_sync;");
                 const unsigned d = tmem + acc * 256;                       // accumulators at columns 0 and 256
                 for (int kb = 0; kb < 3; ++kb) {
-                    mbar_wait_bounded(&ctl->full[stage], phase);
+                    mbar_wait_bounded(&ctl->full[stage], phase, (dbg & 16) ? 100 : 0);
                     asm volatile("tcgen05.fence::after_thread_sync;");
                     const unsigned long long da = umma_desc_sw128(sA + stage * TC_A_BYTES);
                     const unsigned long long db = umma_desc_sw128(sB + kb * TC_B_BYTES);
@@ -182,34 +188,53 @@ k_conv_mid_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
             mbar_wait_bounded(&ctl->tfull[acc], aphase);
             asm volatile("tcgen05.fence::after_thread_sync;");
             const unsigned t0 = tmem + acc * 256 + ((unsigned)(q * 32) << 16);
-            const bool valid = row >= 1 && row <= TC_OUT_PER_TILE && s >= 0 && s < S && (s % pitch) != PW;
+            const bool valid = row >= 1 && row <= TC_OUT_PER_TILE && s >= 0 && s < S && (s % pitch) != PW && !(dbg & 1);
 #pragma unroll 1
-            for (int c = 0; c < 64; c += 16) {
+            for (int c = 0; c < ((dbg & 4) ? 0 : 64); c += 16) {
                 float tm[16], tz[16], tp[16];
-                tmem_ld16(t0 + c, tm);              // T_-1 own row
-                tmem_ld16(t0 + 64 + c, tz);         // T_0
-                tmem_ld16(t0 + 128 + c, tp);        // T_+1
-                asm volatile("tcgen05.wait::ld.sync.aligned;");
+                if (!(dbg & 8)) {
+                    tmem_ld16(t0 + c, tm);              // T_-1 own row
+                    tmem_ld16(t0 + 64 + c, tz);         // T_0
+                    tmem_ld16(t0 + 128 + c, tp);        // T_+1
+                    asm volatile("tcgen05.wait::ld.sync.aligned;");
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) { tm[i] = (float)(row + i); tz[i] = (float)(c + i); tp[i] = 1.f; }
+                }
+                if (dbg & 2) {
+                    if (tm[0] + tz[1] + tp[2] == 12345.678f) out[0] = __float2bfloat16(tm[3]);
+                    continue;
+                }
                 const int par = (c >> 4) & 1;
                 if (lane == 31) {
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) ctl->halo[par][q][0][i] = tm[i];
+                    for (int i = 0; i < 4; ++i)
+                        reinterpret_cast<float4*>(ctl->halo[par][q][0])[i] = make_float4(tm[4 * i], tm[4 * i + 1], tm[4 * i + 2], tm[4 * i + 3]);
                 }
                 if (lane == 0) {
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) ctl->halo[par][q][1][i] = tp[i];
+                    for (int i = 0; i < 4; ++i)
+                        reinterpret_cast<float4*>(ctl->halo[par][q][1])[i] = make_float4(tp[4 * i], tp[4 * i + 1], tp[4 * i + 2], tp[4 * i + 3]);
                 }
-                asm volatile("bar.sync 1, 128;");                          // the four epilogue warps
+                if (!(dbg & 32)) asm volatile("bar.sync 1, 128;" ::: "memory");   // the four epilogue warps
+                // neighbour warps' boundary rows, read by every lane (broadcast) so that no branch diverges
+                float hu[16], hd[16];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float4 a4 = reinterpret_cast<const float4*>(ctl->halo[par][(q + 3) & 3][0])[i];   // previous quadrant's last row
+                    const float4 b4 = reinterpret_cast<const float4*>(ctl->halo[par][(q + 1) & 3][1])[i];   // next quadrant's first row
+                    hu[4 * i] = a4.x; hu[4 * i + 1] = a4.y; hu[4 * i + 2] = a4.z; hu[4 * i + 3] = a4.w;
+                    hd[4 * i] = b4.x; hd[4 * i + 1] = b4.y; hd[4 * i + 2] = b4.z; hd[4 * i + 3] = b4.w;
+                }
                 float o[16];
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
                     float up = __shfl_up_sync(0xffffffffu, tm[i], 1);       // T_-1 of row - 1
                     float dn = __shfl_down_sync(0xffffffffu, tp[i], 1);     // T_+1 of row + 1
-                    if (lane == 0) up = ctl->halo[par][(q + 3) & 3][0][i];   // previous warp's last row (q = 0: unused halo row)
-                    if (lane == 31) dn = ctl->halo[par][(q + 1) & 3][1][i];  // next warp's first row   (q = 3: unused halo row)
-                    float v = up + tz[i] + dn;
-                    if (scale) v *= scale[c + i];
-                    if (shift) v += shift[c + i];
+                    up = lane == 0 ? hu[i] : up;                            // (quadrant 0 / 3 edges are halo rows: unused)
+                    dn = lane == 31 ? hd[i] : dn;
+                    const float2 af = ctl->affine[c + i];
+                    const float v = fmaf(up + tz[i] + dn, af.x, af.y);
                     o[i] = v > 0.f ? v : v * slope;
                 }
                 if (valid) {

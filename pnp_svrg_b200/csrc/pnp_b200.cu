@@ -467,6 +467,7 @@ int make_tmap_bf16_2d(CUtensorMap* map, const void* base, unsigned long long inn
     return PNP_OK;
 }
 
+int g_tc_dbg = 0;
 constexpr size_t kTcSmem = 3 * TC_B_BYTES + TC_STAGES * TC_A_BYTES + sizeof(pnp::TcSmem) + 1024;
 
 int cnn_forward_tc(const pnp_cnn_net* net, const float* img, float* out, int PH, int PW, void* act0, void* act1, int* stats,
@@ -502,7 +503,7 @@ int cnn_forward_tc(const pnp_cnn_net* net, const float* img, float* out, int PH,
         if ((rc = make_tmap_bf16_2d(&tmA, cur, 64, (unsigned long long)S, 64, TC_M)) != PNP_OK) return rc;
         if ((rc = make_tmap_bf16_2d(&tmB, net->w_tc[l], 192, 192, 64, TC_N)) != PNP_OK) return rc;
         pnp::k_conv_mid_tc<<<grid, TC_THREADS, kTcSmem, st>>>(tmA, tmB, nxt, net->scale[l], net->shift[l], net->slope[l], PW,
-                                                            (int)S, n_tiles);
+                                                            (int)S, n_tiles, g_tc_dbg);
         LAUNCH_CHECK();
         __nv_bfloat16* t = cur; cur = nxt; nxt = t;
     }
@@ -546,6 +547,11 @@ int pnp_cnn_forward(const pnp_cnn_net* net, const float* img, float* out, int PH
     if (lb > 148 * 16) lb = 148 * 16;
     pnp::k_conv_last<<<(unsigned)lb, 256, 0, st>>>(cur, img, out, net->w[L - 1], net->last_bias, io, PH, PW, xrec, mse_log, slot);
     LAUNCH_CHECK();
+    return PNP_OK;
+}
+
+int pnp_debug_set(int key, int value) {
+    if (key == 1) g_tc_dbg = value;
     return PNP_OK;
 }
 
