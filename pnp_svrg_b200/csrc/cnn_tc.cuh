@@ -21,8 +21,8 @@
 // read 3x (once per dl) instead of 9x.  A shifted A operand cannot be expressed by a UMMA shared
 // memory descriptor (rows are grouped by 8 in the canonical layouts), hence the output-side shift.
 //
-// Warp roles (192 threads, one persistent CTA per SM): warp 0 TMA producer, warp 1 MMA issuer + TMEM
-// allocator, warps 2-5 epilogue (TMEM lane quadrant = warp_id % 4).
+// Warp roles (320 threads, one persistent CTA per SM): warp 0 TMA producer, warp 1 MMA issuer + TMEM
+// allocator, warps 2-9 epilogue (TMEM lane quadrant = warp_id % 4, two warps per quadrant split the channels).
 #pragma once
 #include <cuda.h>
 #include <cuda_bf16.h>
@@ -39,12 +39,12 @@ namespace pnp {
 #define TC_B_BYTES (TC_N * 128)  // 24 KiB per K block
 #define TC_STAGES 4
 #define TC_OUT_PER_TILE 126
-#define TC_THREADS 192
+#define TC_THREADS 320           // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue (2 per TMEM lane quadrant)
 
 struct TcSmem {
     unsigned long long full[TC_STAGES], empty[TC_STAGES], bfull, tfull[2], tempty[2];
     unsigned tmem_base;
-    __align__(16) float halo[2][4][2][16];     // [chunk parity][epilogue warp][0: lane31 T_-1, 1: lane0 T_+1][16 channels]
+    __align__(16) float halo[2][2][4][2][16];  // [channel half][chunk parity][quadrant][0: lane31 T_-1, 1: lane0 T_+1][16 channels]
     float2 affine[64];           // per output channel (scale, shift): folded BatchNorm / bias
 };
 
@@ -118,7 +118,7 @@ k_conv_mid_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
     if (threadIdx.x == 0) {
         for (int i = 0; i < TC_STAGES; ++i) { mbar_init(&ctl->full[i], 1); mbar_init(&ctl->empty[i], 1); }
         mbar_init(&ctl->bfull, 1);
-        for (int i = 0; i < 2; ++i) { mbar_init(&ctl->tfull[i], 1); mbar_init(&ctl->tempty[i], 4); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&ctl->tfull[i], 1); mbar_init(&ctl->tempty[i], 8); }
         mbar_fence_init();
     }
     if (threadIdx.x >= 64 && threadIdx.x < 128) {
@@ -178,8 +178,9 @@ k_conv_mid_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
             }
         }
     } else {
-        // ===== epilogue warps 2..5: TMEM lane quadrant q = warp % 4 =====
+        // ===== epilogue warps 2..9: TMEM lane quadrant q = warp % 4, channel half = (warp - 2) / 4 =====
         const int q = warp & 3;
+        const int half = (warp - 2) >> 2;
         const int row = q * 32 + lane;                                     // position inside the tile
         int acc = 0;
         unsigned aphase = 0;
@@ -190,7 +191,7 @@ k_conv_mid_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
             const unsigned t0 = tmem + acc * 256 + ((unsigned)(q * 32) << 16);
             const bool valid = row >= 1 && row <= TC_OUT_PER_TILE && s >= 0 && s < S && (s % pitch) != PW && !(dbg & 1);
 #pragma unroll 1
-            for (int c = 0; c < ((dbg & 4) ? 0 : 64); c += 16) {
+            for (int c = 32 * half; c < ((dbg & 4) ? 0 : 32 * half + 32); c += 16) {
                 float tm[16], tz[16], tp[16];
                 if (!(dbg & 8)) {
                     tmem_ld16(t0 + c, tm);              // T_-1 own row
@@ -209,20 +210,21 @@ k_conv_mid_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
                 if (lane == 31) {
 #pragma unroll
                     for (int i = 0; i < 4; ++i)
-                        reinterpret_cast<float4*>(ctl->halo[par][q][0])[i] = make_float4(tm[4 * i], tm[4 * i + 1], tm[4 * i + 2], tm[4 * i + 3]);
+                        reinterpret_cast<float4*>(ctl->halo[half][par][q][0])[i] = make_float4(tm[4 * i], tm[4 * i + 1], tm[4 * i + 2], tm[4 * i + 3]);
                 }
                 if (lane == 0) {
 #pragma unroll
                     for (int i = 0; i < 4; ++i)
-                        reinterpret_cast<float4*>(ctl->halo[par][q][1])[i] = make_float4(tp[4 * i], tp[4 * i + 1], tp[4 * i + 2], tp[4 * i + 3]);
+                        reinterpret_cast<float4*>(ctl->halo[half][par][q][1])[i] = make_float4(tp[4 * i], tp[4 * i + 1], tp[4 * i + 2], tp[4 * i + 3]);
                 }
-                if (!(dbg & 32)) asm volatile("bar.sync 1, 128;" ::: "memory");   // the four epilogue warps
+                if (half == 0) asm volatile("bar.sync 1, 128;" ::: "memory");     // the four warps of this channel half
+                else asm volatile("bar.sync 2, 128;" ::: "memory");
                 // neighbour warps' boundary rows, read by every lane (broadcast) so that no branch diverges
                 float hu[16], hd[16];
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
-                    const float4 a4 = reinterpret_cast<const float4*>(ctl->halo[par][(q + 3) & 3][0])[i];   // previous quadrant's last row
-                    const float4 b4 = reinterpret_cast<const float4*>(ctl->halo[par][(q + 1) & 3][1])[i];   // next quadrant's first row
+                    const float4 a4 = reinterpret_cast<const float4*>(ctl->halo[half][par][(q + 3) & 3][0])[i];   // previous quadrant's last row
+                    const float4 b4 = reinterpret_cast<const float4*>(ctl->halo[half][par][(q + 1) & 3][1])[i];   // next quadrant's first row
                     hu[4 * i] = a4.x; hu[4 * i + 1] = a4.y; hu[4 * i + 2] = a4.z; hu[4 * i + 3] = a4.w;
                     hd[4 * i] = b4.x; hd[4 * i + 1] = b4.y; hd[4 * i + 2] = b4.z; hd[4 * i + 3] = b4.w;
                 }
@@ -248,7 +250,7 @@ k_conv_mid_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
                 }
             }
             asm volatile("tcgen05.fence::before_thread_sync;");
-            if (lane == 0) mbar_arrive(&ctl->tempty[acc]);                 // 4 arrivals (one per epilogue warp)
+            if (lane == 0) mbar_arrive(&ctl->tempty[acc]);                 // 8 arrivals (one per epilogue warp)
             if (++acc == 2) { acc = 0; aphase ^= 1; }
         }
     }
