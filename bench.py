@@ -190,17 +190,22 @@ class Epoch:
     def inner_ops(self, hook=None):
         eng, p, B = self.eng, self.prob, self.cfg['mini_batch_size']
         h = hook or (lambda name: None)
-        eng.sample_sel_device(); h('sel_sample')
         gk = dict(b=self.w, sel=eng.sel, with_y=False, gscale=1.0 / B, vadd=self.mu, step_ptr=eng.step,
                   z_in=eng.z, z_out=eng.z, clear_sel=True)
+        if FUSE_SIGMA:
+            gk.update(sig_log=eng.sig_log, sig_slot=eng.slot_ptr)
         if hook is None:
-            p._dev_grad(eng.z, **gk)
-        else:                                  # same three kernels, launched one by one so each can be timed
+            # the minibatch selection only feeds the column pass: draw it on a parallel graph branch
+            eng.fork(eng.sample_sel_device, lambda: p._dev_grad(eng.z, phases=1, **gk))
+            p._dev_grad(eng.z, phases=6, **gk)
+        else:                                  # same kernels, launched one by one so each can be timed
+            eng.sample_sel_device(); h('sel_sample')
             p._dev_grad(eng.z, phases=1, **gk); h('lines_r2c')
             p._dev_grad(eng.z, phases=2, **gk); h('cols_mask')
             p._dev_grad(eng.z, phases=4, **gk); h('lines_c2r+update')
-        eng.check(eng.lib.pnp_estimate_sigma(self.D.ptr(eng.z), eng.H, eng.W, 1, self.D.ptr(eng.sig_log),
-                                             self.D.ptr(eng.slot_ptr), eng.sptr)); h('sigma_mad')
+        if not FUSE_SIGMA:
+            eng.check(eng.lib.pnp_estimate_sigma(self.D.ptr(eng.z), eng.H, eng.W, 1, self.D.ptr(eng.sig_log),
+                                                 self.D.ptr(eng.slot_ptr), eng.sptr)); h('sigma_mad')
         self.den._dev_denoise(self._ctx()); h('haar_bayes+psnr')
         eng.advance(); h('advance')
 
@@ -236,7 +241,8 @@ class Epoch:
         eng.stream.synchronize()
 
 
-LAUNCHES_PER_INNER = 7        # sel_sample + r2c + cols + c2r + sigma_mad + haar_bayes + advance
+FUSE_SIGMA = os.environ.get('PNP_BENCH_FUSE_SIGMA', '0') == '1'   # sigma estimate inside the c2r pass (slower today)
+LAUNCHES_PER_INNER = 7 - int(FUSE_SIGMA)   # sel_sample + r2c + cols + c2r + sigma_mad + haar_bayes + advance
 LAUNCHES_PER_SNAPSHOT = 4     # r2c + cols + c2r + D2D copy
 
 

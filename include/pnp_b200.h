@@ -67,6 +67,8 @@ typedef struct {
                                      bit2 lines c2r + epilogue (used to time the passes one by one) */
     int clear_bits;               /* != 0: the column pass zeroes `bits` after using it (single-use minibatch
                                      selection; the next pnp_csmri_sel_* call then needs clear = 0) */
+    double* sig_log;              /* optional, with z_out: fused pnp_estimate_sigma of z_out (same semantics:  */
+    const int* sig_slot;          /* the sum over columns is ADDED to sig_log[*sig_slot * batch + img])        */
 } pnp_csmri_grad_args;
 int pnp_csmri_grad(const pnp_csmri_grad_args* args, void* stream);
 

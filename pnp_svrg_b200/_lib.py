@@ -25,6 +25,7 @@ class CsmriGradArgs(C.Structure):
         ('g_out', C.c_void_p), ('vadd', C.c_void_p), ('v_out', C.c_void_p),
         ('z_in', C.c_void_p), ('z_out', C.c_void_p),
         ('phases', C.c_int), ('clear_bits', C.c_int),
+        ('sig_log', C.c_void_p), ('sig_slot', C.c_void_p),
     ]
 
 

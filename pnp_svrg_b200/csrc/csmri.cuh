@@ -25,6 +25,7 @@
 // real inverse of its Hermitian part:  ((sel[k] + sel[-k]) / 2) Z[k]  (Z[-k] = conj Z[k]).
 #pragma once
 #include "fft_core.cuh"
+#include "prox.cuh"
 
 namespace pnp {
 
@@ -38,6 +39,9 @@ struct GradEpilogue {
     float* v_out;                 // optional: v
     const float* z_in;            // optional (with z_out)
     float* z_out;
+    double* sig_log;              // optional (with z_out): fused estimate_sigma of the updated lines,
+    const int* sig_slot;          //   sum over lines added to sig_log[*sig_slot * batch + img]
+    int batch;
 };
 
 // ------------------------------------------------------------------ pass 1
@@ -393,11 +397,27 @@ k_lines_c2r(const float2* __restrict__ S, int nlines, long long img_stride, floa
                     float v = gval;
                     if (p_vadd) v += sv[sh];
                     if (p_vout) p_vout[eh] = v;
-                    if (p_zout) p_zout[eh] = sz[sh] - step * v;
+                    if (p_zout) {
+                        const float zn = sz[sh] - step * v;
+                        p_zout[eh] = zn;
+                        if (ep.sig_log) const_cast<float*>(sz)[sh] = zn;      // keep the updated line for the sigma estimate
+                    }
                 }
             }
         }
-        __syncthreads();                            // staging + exchange buffers free for the next item
+        __syncthreads();                            // exchange buffers free; updated lines complete in stage_z
+        if (GP * T >= 32 && ep.sig_log && p_zout) {
+            // fused estimate_sigma (algorithms/pnp_svrg.py:71): one warp per updated line of this item;
+            // the exchange buffer (free here) provides 32 scratch words per warp
+            constexpr int NW = (GP * T) / 32;
+            unsigned* scratch = reinterpret_cast<unsigned*>(smem) + (threadIdx.x >> 5) * 32;
+            for (int ln = threadIdx.x >> 5; ln < 2 * GP; ln += NW) {
+                if (item * GP * 2 + ln >= nlines) break;
+                const double sig = line_sigma_mad<L>(stage_z + ln * L, threadIdx.x & 31, scratch);
+                if ((threadIdx.x & 31) == 0) atomicAdd(slot_ptr(ep.sig_log, ep.sig_slot, ep.batch, img), sig);
+            }
+            __syncthreads();                        // stage_z consumed before the next item's bulk copy lands
+        }
     }
 }
 

@@ -136,7 +136,8 @@ int launch_c2r(const pnp_csmri_grad_args& a, cudaStream_t st) {
     const int pairs = a.W / 2;
     const int items = (pairs + GP - 1) / GP;
     dim3 grid(persistent_ctas(pnp::k_lines_c2r<L, GP>, GP * pnp::fft_threads<L>(), lines_smem<L>(), items, a.batch), a.batch);
-    pnp::GradEpilogue ep{a.gscale, a.gscale_ptr, a.step, a.step_ptr, a.g_out, a.vadd, a.v_out, a.z_in, a.z_out};
+    pnp::GradEpilogue ep{a.gscale, a.gscale_ptr, a.step, a.step_ptr, a.g_out, a.vadd, a.v_out, a.z_in, a.z_out,
+                         a.sig_log, a.sig_slot, a.batch};
     const float inv_n = (float)(1.0 / ((double)a.H * (double)a.W));
     pnp::k_lines_c2r<L, GP><<<grid, GP * pnp::fft_threads<L>(), lines_smem<L>(), st>>>(
         reinterpret_cast<const float2*>(a.S), a.W, (long long)a.H * a.W, inv_n, ep);

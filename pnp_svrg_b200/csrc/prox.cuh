@@ -27,17 +27,13 @@ __device__ __forceinline__ double* slot_ptr(double* base, const int* slot, int b
     return base + (long long)(slot ? *slot : 0) * batch + img;
 }
 
+// Warp-collective sigma estimate of ONE line x[0..L) (global or shared memory): db2 detail
+// coefficients with half-sample symmetric extension, exact median of |d| over d != 0 by a 31-step
+// bit search on the float bit patterns (values stay in registers), / Phi^-1(0.75).
 template <int L>
-__global__ void __launch_bounds__(128)
-k_sigma_mad(const float* __restrict__ z, int nlines, long long img_stride, double* __restrict__ sig_log,
-            const int* __restrict__ slot, int batch) {
+__device__ __forceinline__ double line_sigma_mad(const float* __restrict__ x, int lane, unsigned* scratch /* 32 words per warp, shared */) {
     constexpr int NO = (L + 3) / 2;            // db2 detail coefficients per line
     constexpr int PER = (NO + 31) / 32;
-    const int lane = threadIdx.x & 31;
-    const int line = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    const int img = blockIdx.y;
-    if (line >= nlines) return;
-    const float* x = z + (long long)img * img_stride + (long long)line * L;
     // pywt dec_hi of db2; out[o] = sum_j h[j] * x_ext[2o + 1 - j]
     const float h0 = -0.48296291314469025f, h1 = 0.836516303737469f,
                 h2 = -0.22414386804185735f, h3 = -0.12940952255092145f;
@@ -59,31 +55,72 @@ k_sigma_mad(const float* __restrict__ z, int nlines, long long img_stride, doubl
         }
     }
     nnz = warp_sum_i(nnz);
-    double sig;
-    if (nnz == 0) {
-        sig = __longlong_as_double(0x7ff8000000000000LL);      // median of nothing = NaN
-    } else {
-        const int k1 = (nnz - 1) >> 1, k2 = nnz >> 1;
-        unsigned res = 0;
-        for (int bit = 30; bit >= 0; --bit) {                  // k1-th smallest by bit search
-            const unsigned cand = res | (1u << bit);
-            int c = 0;
+    if (nnz == 0) return __longlong_as_double(0x7ff8000000000000LL);      // median of nothing = NaN
+    const int k1 = (nnz - 1) >> 1, k2 = nnz >> 1;
+    // Bit search for the k1-th smallest key, tracking how many keys still share the decided prefix
+    // (c_hi - c_lo).  Once at most 32 remain they are gathered, one per lane, and ranked directly.
+    unsigned res = 0;
+    int c_lo = 0, c_hi = nnz;                   // #keys < res  and  #keys < res + 2^(bit+1)  (sentinels excluded)
+    int bit = 30;
+    for (; bit >= 0 && c_hi - c_lo > 32; --bit) {
+        const unsigned cand = res | (1u << bit);
+        int c = 0;
 #pragma unroll
-            for (int i = 0; i < PER; ++i) c += a[i] < cand;
-            if (warp_sum_i(c) <= k1) res = cand;
-        }
-        unsigned res2 = res;
-        if (k2 != k1) {
-            int c = 0;
-            unsigned mn = 0xffffffffu;
-#pragma unroll
-            for (int i = 0; i < PER; ++i) { c += a[i] <= res; if (a[i] > res) mn = min(mn, a[i]); }
-            c = warp_sum_i(c);
-            mn = __reduce_min_sync(0xffffffffu, mn);
-            if (c < k2 + 1) res2 = mn;
-        }
-        sig = 0.5 * ((double)__uint_as_float(res) + (double)__uint_as_float(res2)) / 0.6744897501960817;
+        for (int i = 0; i < PER; ++i) c += a[i] < cand;
+        c = warp_sum_i(c);
+        if (c <= k1) { res = cand; c_lo = c; } else { c_hi = c; }
     }
+    unsigned v1;
+    if (bit < 0) {
+        v1 = res;                               // every bit decided
+    } else {
+        // candidates: keys in [res, res + 2^(bit+1)); exactly c_hi - c_lo <= 32 of them
+        const unsigned hi = res + (2u << bit);  // bit <= 29 here, no overflow
+        int base = 0;
+#pragma unroll
+        for (int i = 0; i < PER; ++i) {
+            const bool in = a[i] >= res && a[i] < hi;
+            const unsigned m = __ballot_sync(0xffffffffu, in);
+            if (in) scratch[base + __popc(m & ((1u << lane) - 1u))] = a[i];
+            base += __popc(m);
+        }
+        __syncwarp();
+        const unsigned mine = lane < base ? scratch[lane] : 0xffffffffu;
+        __syncwarp();
+        // rank of every candidate among the candidates (ties broken by lane)
+        int rnk = 0;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            const unsigned u = __shfl_sync(0xffffffffu, mine, j);
+            rnk += (u < mine) || (u == mine && j < lane);
+        }
+        const int target = k1 - c_lo;
+        const unsigned hit = __ballot_sync(0xffffffffu, rnk == target && mine != 0xffffffffu);
+        v1 = __shfl_sync(0xffffffffu, mine, __ffs(hit) - 1);
+    }
+    unsigned v2 = v1;
+    if (k2 != k1) {
+        int c = 0;
+        unsigned mn = 0xffffffffu;
+#pragma unroll
+        for (int i = 0; i < PER; ++i) { c += a[i] <= v1; if (a[i] > v1) mn = min(mn, a[i]); }
+        c = warp_sum_i(c);
+        mn = __reduce_min_sync(0xffffffffu, mn);
+        if (c < k2 + 1) v2 = mn;
+    }
+    return 0.5 * ((double)__uint_as_float(v1) + (double)__uint_as_float(v2)) / 0.6744897501960817;
+}
+
+template <int L>
+__global__ void __launch_bounds__(128)
+k_sigma_mad(const float* __restrict__ z, int nlines, long long img_stride, double* __restrict__ sig_log,
+            const int* __restrict__ slot, int batch) {
+    __shared__ unsigned scratch[4][32];
+    const int lane = threadIdx.x & 31;
+    const int line = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int img = blockIdx.y;
+    if (line >= nlines) return;
+    const double sig = line_sigma_mad<L>(z + (long long)img * img_stride + (long long)line * L, lane, scratch[threadIdx.x >> 5]);
     if (lane == 0) atomicAdd(slot_ptr(sig_log, slot, batch, img), sig);
 }
 

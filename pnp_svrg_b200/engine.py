@@ -94,6 +94,8 @@ class Engine:
         self._ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
         self._pending = []          # fast mode: (kind,) markers for slots not yet read back
         self.graph = None
+        self.side = None
+        self.sigma_ready = False    # set when the gradient pass already accumulated sigma for this slot
         self.uses_sigma = getattr(denoiser, '_uses_sigma_est', True)
 
     # ------------------------------------------------------------------ helpers
@@ -103,6 +105,21 @@ class Engine:
 
     def set_step(self, value):
         self.step.fill_(float(value))
+
+    def fork(self, side_fn, main_fn):
+        """Run side_fn on a second stream concurrently with main_fn (both are captured as parallel
+        graph branches when a capture is active), then join."""
+        if self.side is None:
+            self.side = torch.cuda.Stream(device=self.dev)
+            self._ev_fork = torch.cuda.Event()
+            self._ev_join = torch.cuda.Event()
+        self._ev_fork.record(self.stream)
+        self.side.wait_event(self._ev_fork)
+        with torch.cuda.stream(self.side):
+            side_fn()
+            self._ev_join.record(self.side)
+        main_fn()
+        self.stream.wait_event(self._ev_join)
 
     def copy(self, dst, src):
         self.check(self.lib.pnp_copy_f32(D.ptr(dst), D.ptr(src), dst.numel(), self.sptr))
@@ -153,9 +170,10 @@ class Engine:
     # ------------------------------------------------------------------ prox + log
     def prox(self, z_in, z_out):
         """sigma estimate + denoiser + squared error against the ground truth into the current slot."""
-        if self.uses_sigma:
+        if self.uses_sigma and not self.sigma_ready:
             self.check(self.lib.pnp_estimate_sigma(D.ptr(z_in), self.H, self.W, 1, D.ptr(self.sig_log),
                                                    D.ptr(self.slot_ptr), self.sptr))
+        self.sigma_ready = False
         self.d._dev_denoise(ProxCtx(z_in, z_out, self.H, self.W, sig_log=self.sig_log if self.uses_sigma else None,
                                     xrec=self.p._xrec_dev, mse_log=self.mse_log, slot=self.slot_ptr))
         if not getattr(self.d, '_fused_psnr', True):

@@ -229,6 +229,16 @@ def test_device_minibatch_sampler(cuda):
     g = torch.empty_like(zl)
     dut._dev_grad(zl, sel=sel, g_out=g)
     assert rel_l2(D.from_lines(g, dut.H, dut.W), g1) < 1e-6
+    # single-use selection: the pass that consumes it can leave it zeroed (no memset before the next draw)
+    assert int(sel.sum().item()) > 0
+    dut._dev_grad(zl, sel=sel, g_out=g, clear_sel=True)
+    assert rel_l2(D.from_lines(g, dut.H, dut.W), g1) < 1e-6
+    assert int(sel.sum().item()) == 0
+    dut._dev_sample_sel(sel, 500, seed=5, counter=cnt, clear=False)
+    dut._dev_sample_sel(sel, 500, seed=5, counter=cnt, idx_out=None, clear=False)      # same draw twice: idempotent bits
+    n1 = int((sel != 0).sum().item())
+    dut._dev_sample_sel(sel, 500, seed=5, counter=cnt, clear=True)
+    assert int((sel != 0).sum().item()) == n1
 
 
 def test_stop_rules(cuda):
