@@ -92,6 +92,11 @@ int pnp_csmri_sel_sample(unsigned char* bits, int H, int W, int batch, const int
  * problems/problem.py:110-117): idx_out[0..count) = distinct positions in [0, n). */
 int pnp_sample_indices(int* idx_out, int n, int count, unsigned seed, const int* counter, void* stream);
 
+/* Host twin of the device sampler (same keyed Feistel permutation, bit-identical positions): fills
+ * idx_out_host[0..count) on the CPU with `threads` worker threads.  Host plumbing for mb_source='host'
+ * (the reference draws on the host too, problems/CSMRI.py:72); not a compute fallback. */
+int pnp_sample_indices_host(int* idx_out_host, int n, int count, unsigned seed, unsigned counter, int img, int threads);
+
 /* ---- Deblur + super-resolution gradient ------------------------------------------------------
  * Replaces Deblur.grad_full (problems/DeblurSR.py:126-132), Deblur.grad_stoch (:135-147) and the
  * same update lines as pnp_csmri_grad:

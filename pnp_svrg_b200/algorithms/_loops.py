@@ -246,6 +246,8 @@ def pnp_svrg(problem, denoiser, eta, tt, T2, mini_batch_size, verbose=True, lr_d
     def snapshot():
         # mu = grad_full(z) ; w = copy(z)          (pnp_svrg.py:32-35)
         _grad_update(eng, z, None, None, True, 1.0 / _full_norm(problem), g_out=mu)
+        if getattr(problem, 'shard', None) is not None:
+            problem._snapshot_allreduce(mu)          # measurement-sharded snapshot: partial sums -> full gradient
         eng.copy(w, z)
 
     def grad_ops():

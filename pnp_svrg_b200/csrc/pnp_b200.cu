@@ -4,6 +4,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <thread>
 #include <vector>
 
 #include "../../include/pnp_b200.h"
@@ -365,6 +366,48 @@ int pnp_sample_indices(int* idx_out, int n, int count, unsigned seed, const int*
     if (blocks > 592) blocks = 592;
     pnp::k_sample_indices<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(idx_out, n, count, seed, counter);
     LAUNCH_CHECK();
+    return PNP_OK;
+}
+
+namespace {
+inline unsigned h_mix32(unsigned x) {
+    x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15; x *= 0x846ca68bU; x ^= x >> 16;
+    return x;
+}
+inline unsigned h_feistel(unsigned i, unsigned n, unsigned key, int hb) {
+    const unsigned hm = (1u << hb) - 1u;
+    unsigned x = i;
+    do {
+        unsigned l = x >> hb, r = x & hm;
+        for (int rd = 0; rd < 4; ++rd) {
+            const unsigned f = h_mix32(r ^ (key + 0x9e3779b9U * (rd + 1))) & hm;
+            const unsigned nl = r;
+            r = l ^ f;
+            l = nl;
+        }
+        x = (l << hb) | r;
+    } while (x >= n);
+    return x;
+}
+}  // namespace
+
+int pnp_sample_indices_host(int* out, int n, int count, unsigned seed, unsigned counter, int img, int threads) {
+    if (!out || n < 1 || count < 1 || count > n) return fail(PNP_ERR_ARG, "bad argument");
+    const unsigned key = h_mix32(seed ^ h_mix32(counter * 0x632be5abU + (unsigned)img));
+    int hb = 1;
+    while ((1u << (2 * hb)) < (unsigned)n) ++hb;
+    if (threads < 1) threads = 1;
+    if (threads > 16) threads = 16;
+    if (count < 4096) threads = 1;
+    auto work = [=](int lo, int hi) { for (int i = lo; i < hi; ++i) out[i] = (int)h_feistel((unsigned)i, (unsigned)n, key, hb); };
+    if (threads == 1) { work(0, count); return PNP_OK; }
+    std::vector<std::thread> pool;
+    const int per = (count + threads - 1) / threads;
+    for (int t = 0; t < threads; ++t) {
+        const int lo = t * per, hi = lo + per < count ? lo + per : count;
+        if (lo < hi) pool.emplace_back(work, lo, hi);
+    }
+    for (auto& th : pool) th.join();
     return PNP_OK;
 }
 

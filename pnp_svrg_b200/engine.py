@@ -17,6 +17,7 @@ Two ways of driving that sequence:
                       come from a pre-drawn device buffer or the device sampler, logs are read
                       back once per chunk, stop rules are applied at chunk boundaries.
 """
+import os
 import time
 
 import numpy as np
@@ -91,6 +92,8 @@ class Engine:
         self.denoise_time = 0.0
         self._stream_pos = 0
         self._host_draws = 0
+        self._pos_host = None
+        self._host_threads = max(1, min(8, (os.cpu_count() or 1) // 2))
         self._ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
         self._pending = []          # fast mode: (kind,) markers for slots not yet read back
         self.graph = None
@@ -142,9 +145,13 @@ class Engine:
             idx = self.p._draw_indices(self.B)
         elif self.mb_source == 'host':
             sup = getattr(self.p, '_support_host', None)
-            pos = feistel_sample(self.p.M if sup is None else sup.size, self.B, self.mb_seed, self._host_draws)
+            n = self.p.M if sup is None else sup.size
+            if self._pos_host is None:
+                self._pos_host = np.empty(self.B, dtype=np.int32)
+            _lib.check(self.lib.pnp_sample_indices_host(self._pos_host.ctypes.data, int(n), self.B, self.mb_seed & 0xffffffff,
+                                                        self._host_draws & 0xffffffff, 0, self._host_threads))
             self._host_draws += 1
-            idx = pos if sup is None else sup[pos]
+            idx = self._pos_host if sup is None else sup[self._pos_host]
         elif self.mb_source == 'stream':
             idx = np.asarray(self.mb_stream[self._stream_pos])
             self._stream_pos += 1

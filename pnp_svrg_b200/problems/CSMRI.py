@@ -9,12 +9,19 @@ from .. import _lib, device as D
 from .problem import MiniBatch, Problem
 
 
+def shard_rows(H, rank, world):
+    """contiguous block of ky rows owned by `rank` (last rank takes the remainder)"""
+    per = H // world
+    lo = rank * per
+    return lo, (H if rank == world - 1 else lo + per)
+
+
 class CSMRI(Problem):
     _fuses_sigma = False     # pnp_csmri_grad CAN estimate sigma of the iterate it writes (sig_log=); measured
                              # slower than the separate kernel at 2048^2, so the engine does not use it
 
     def __init__(self, img_path=None, H=256, W=256, sample_prob=0.5, snr=None, sigma=None, *,
-                 image=None, mask_type='bernoulli'):
+                 image=None, mask_type='bernoulli', shard=None):
         super().__init__(img_path, H, W, image=image)
         if H != W:
             raise Exception('CSMRI needs a square image (the reference applies an HxH DFT matrix on both sides)')
@@ -23,6 +30,11 @@ class CSMRI(Problem):
         self.snr = snr
         self.sigma = sigma
         self.mask_type = mask_type
+        # shard = (rank, world): this process holds only the measurements whose ky row falls in its
+        # contiguous row block; grad_full then returns a PARTIAL sum that the caller all-reduces
+        # (the one real exchange step of the path).  Minibatch gradients and
+        # everything else stay replicated.
+        self.shard = shard
 
         self._generate_mask()
         self.Y0 = self.forward_model(self.X)
@@ -74,7 +86,16 @@ class CSMRI(Problem):
         self._support = torch.from_numpy(self._support_host).to(dev)
         self._m0_dev = torch.tensor([self.M0], dtype=torch.int32, device=dev)
         self._bits_full = torch.zeros(W * hp, dtype=torch.uint8, device=dev)
-        self._dev_set_sel(self._bits_full, self._support, self.M0)
+        if self.shard is None:
+            self._dev_set_sel(self._bits_full, self._support, self.M0)
+        else:
+            lo, hi = shard_rows(self.H, *self.shard)
+            rows = self._support_host // W
+            own = np.ascontiguousarray(self._support_host[(rows >= lo) & (rows < hi)])
+            self._shard_count = int(own.size)
+            own_dev = torch.from_numpy(own).to(dev)
+            if own.size:
+                self._dev_set_sel(self._bits_full, own_dev, own.size)
         self._S = torch.empty(self.N, dtype=torch.float32, device=dev)
         self._bits_tmp = torch.zeros(W * hp, dtype=torch.uint8, device=dev)
 
@@ -84,6 +105,12 @@ class CSMRI(Problem):
 
     def _dev_full_sel(self):
         return self._bits_full
+
+    def _snapshot_allreduce(self, mu):
+        """sum the per-rank partial snapshot gradients (NCCL all-reduce of 4N bytes over NVLink)"""
+        if self.shard is not None and self.shard[1] > 1:
+            import torch.distributed as dist
+            dist.all_reduce(mu, op=dist.ReduceOp.SUM)
 
     def _dev_set_sel(self, sel, idx_dev, count, cursor=None, stride=0, clear=True):
         _lib.check(_lib.load().pnp_csmri_sel_from_indices(D.ptr(sel), self.H, self.W, 1, D.ptr(idx_dev), int(count),

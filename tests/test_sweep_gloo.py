@@ -58,3 +58,17 @@ def test_world_size_2_gloo_gather():
     assert all(r['rank'] == r['id'] % 2 for r in recs)
     assert 'error' in recs[4] and 'boom' in recs[4]['error']
     assert all(r['value'] == r['id'] ** 2 for r in recs if r['id'] != 4)
+
+
+def test_measurement_shards_partition_the_rows():
+    """config 5: k-space rows are split into disjoint contiguous blocks that cover every row."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location('csmri_mod', os.path.join(ROOT, 'pnp_svrg_b200', 'problems', 'CSMRI.py'))
+    src = open(spec.origin).read()
+    ns = {}
+    exec(src[src.index('def shard_rows'):src.index('class CSMRI')], ns)
+    for H in (32, 256, 2048):
+        for world in (1, 2, 4, 8, 3):
+            blocks = [ns['shard_rows'](H, r, world) for r in range(world)]
+            assert blocks[0][0] == 0 and blocks[-1][1] == H
+            assert all(blocks[i][1] == blocks[i + 1][0] for i in range(world - 1))
