@@ -33,7 +33,7 @@ UNIT = 'inner_iterations/s'
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=100)
+    ap.add_argument('--steps', type=int, default=200)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--size', type=int, default=2048)
@@ -83,12 +83,22 @@ class ClockSampler:
         except OSError:
             self.proc = None
 
+    def mark(self):
+        """timed region starts now: samples taken before this instant are dropped"""
+        self.t_mark = time.time()
+
     def stop(self):
         if self.proc is None:
             return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        t_stop = time.time()
         time.sleep(0.05)
         self.proc.terminate()
         out = self.proc.communicate()[0]
+        lines = out.strip().splitlines()
+        # nvidia-smi -lms samples at a fixed period: keep the tail that falls inside [mark, stop]
+        period = 0.02
+        keep = max(1, int((t_stop - getattr(self, 't_mark', t_stop)) / period) + 1)
+        out = '\n'.join(lines[-keep:])
         sm, mx, reasons = [], [], set()
         names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
         for line in out.strip().splitlines():
@@ -269,12 +279,15 @@ def run_b200(a, cfg, rank, world, local_rank):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    for _ in range(a.warmup):
-        ep.step()
-    barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+        time.sleep(0.6)                    # nvidia-smi needs a moment before its first sample
+    for _ in range(a.warmup):
+        ep.step()
+    barrier()
+    if rank == 0:
+        sampler.mark()
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(a.steps)]
     t_wall = time.time()
     for s in range(a.steps):
@@ -363,11 +376,14 @@ def breakdown(a, cfg, ep, us_inner_graph):
     }
     top = max(alg, key=lambda k: per.get(k, 0.0))
     ach = alg[top] / (per[top] * 1e-6) / 1e9
+    traffic = ncu_traffic({'lines_r2c': 'k_lines_r2c', 'cols_mask': 'k_cols_mask', 'lines_c2r+update': 'k_lines_c2r',
+                           'sigma_mad': 'k_sigma_mad', 'haar_bayes+psnr': 'k_haar_bayes'}[top])
     iter_bytes = 28.125 * N
     out = {
         'kernel_us': per, 'kernel_us_sum_eager': tot,
         'roofline': {'bound': 'hbm', 'kernel': top, 'achieved': ach, 'peak': peak, 'unit': 'GB/s', 'frac': ach / peak,
-                     'traffic': None, 'peak_source': peak_src,
+                     'traffic': traffic, 'traffic_source': 'profiles/r01_ncu_full_iteration_kernels.csv (ncu --set full, one launch, cold L2)',
+                     'peak_source': peak_src,
                      'algorithmic_bytes_per_launch': alg[top], 'us_per_launch': per[top]},
         'roofline_iteration': {'bound': 'hbm', 'algorithmic_bytes': iter_bytes,
                                'achieved': iter_bytes / (us_inner_graph * 1e-6) / 1e9, 'peak': peak, 'unit': 'GB/s',
@@ -376,6 +392,25 @@ def breakdown(a, cfg, ep, us_inner_graph):
     }
     eng.flush_fast()
     return out
+
+
+def ncu_traffic(kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch of `kernel` from the committed ncu capture"""
+    path = os.path.join(ROOT, 'profiles', 'r01_ncu_full_iteration_kernels.csv')
+    if not os.path.exists(path):
+        return None
+    import csv
+    rows = list(csv.reader(open(path)))
+    hdr, units = rows[0], rows[1]
+    mult = {'byte': 1.0, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}
+    for r in rows[2:]:
+        if kernel in r[0]:
+            tot = 0.0
+            for name in ('dram__bytes_read.sum', 'dram__bytes_write.sum'):
+                i = hdr.index(name)
+                tot += float(r[i]) * mult.get(units[i], 1.0)
+            return tot
+    return None
 
 
 def run_e2e(a, cfg, prob, dev, world):
