@@ -66,6 +66,25 @@ def _fast_inner(eng, budget, n_iters, inner_ops, host_draw, sync_every, converge
     done = 0
     stop = False
     psnr_z = start_psnr
+    if not (converge_check is True or diverge_check is True):
+        # no stop rule needs the PSNR of every iterate: enqueue, count, and read the log back later
+        while done < n_iters and budget.alive():
+            left = budget.left()
+            room = min(n_iters - done, LOG_CHUNK - eng.slot_host, left if left is not None else 1 << 30)
+            if room <= 0:
+                eng.resolve()
+                continue
+            with torch.cuda.stream(eng.stream):
+                for _ in range(room):
+                    if host_draw is not None:
+                        host_draw()
+                    eng.replay(eng.graph)
+            eng.defer_slots(room)
+            budget.calls += room
+            done += room
+            if eng.since_sync >= sync_every:
+                eng.resolve()              # bounds how far the host runs ahead of the GPU (wall-clock budget tt)
+        return None, False, done
     while done < n_iters and not stop:
         left = budget.left()
         room = min(n_iters - done, sync_every, LOG_CHUNK - eng.slot_host, left if left is not None else 1 << 30)
@@ -275,8 +294,11 @@ def pnp_svrg(problem, denoiser, eta, tt, T2, mini_batch_size, verbose=True, lr_d
             eng.set_step(eta * lr_decay ** i)
         if not fast:
             eng.stream.synchronize()
-        eng.time_log.append(time.time() - t_outer)
-        eng.psnr_log.append(psnr_z)
+        if eng.deferred:
+            eng.defer_dup()
+        else:
+            eng.time_log.append(time.time() - t_outer)
+            eng.psnr_log.append(psnr_z if psnr_z is not None else eng.psnr_log[-1])
         if fast:
             psnr_z, stop, _ = _fast_inner(eng, budget, T2, fast_ops, draw, min(sync_every, T2) if converge_check or diverge_check else sync_every,
                                           converge_check, diverge_check, psnr_z)
@@ -452,6 +474,7 @@ def pnp_sarah(problem, denoiser, eta, tt, T2, mini_batch_size, verbose=True, lr_
     stop = False
     while budget.alive() and not stop:
         # the outer prox step is logged like an iteration (:38-50)
+        eng.resolve()
         t0 = time.time()
         with torch.cuda.stream(eng.stream):
             outer_grad()

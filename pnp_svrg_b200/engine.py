@@ -97,6 +97,8 @@ class Engine:
         self._ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
         self._pending = []          # fast mode: (kind,) markers for slots not yet read back
         self.graph = None
+        self.deferred = []
+        self.since_sync = 0
         self.side = None
         self.sigma_ready = False    # set when the gradient pass already accumulated sigma for this slot
         self.uses_sigma = getattr(denoiser, '_uses_sigma_est', True)
@@ -209,6 +211,38 @@ class Engine:
         self.slot_host = 0
         self.slot_base = 0
 
+    # deferred logging (fast mode without stop rules): iterations are only counted while they are
+    # enqueued; PSNR values are read back in one go by resolve()
+    def defer_slots(self, n):
+        if not self.deferred:
+            self._defer_t0 = time.time()
+        self.deferred.append(n)
+        self.slot_host += n
+        self.since_sync += n
+
+    def defer_dup(self):
+        """the log repeats the previous value (PnP-SVRG logs PSNR(z) again at every snapshot)"""
+        self.deferred.append('dup')
+
+    def resolve(self):
+        if not self.deferred:
+            return
+        vals = self.flush_fast()
+        n_slots = sum(d for d in self.deferred if d != 'dup')
+        dt = (time.time() - self._defer_t0) / max(n_slots, 1)
+        it = iter(vals)
+        for d in self.deferred:
+            if d == 'dup':
+                self.psnr_log.append(self.psnr_log[-1])
+                self.time_log.append(0.0)
+            else:
+                for _ in range(d):
+                    self.psnr_log.append(next(it))
+                    self.time_log.append(dt)
+                    self.n_prox += 1
+        self.deferred = []
+        self.since_sync = 0
+
     def flush_fast(self):
         """fast mode: read back every slot written since the last flush."""
         self.stream.synchronize()
@@ -245,6 +279,7 @@ class Engine:
             self.lib.pnp_graph_destroy(exec_)
 
     def result(self, name):
+        self.resolve()
         self.stream.synchronize()
         z = D.from_lines(self.z, self.H, self.W)
         return {

@@ -73,7 +73,8 @@ def reconstruct(job, H=256, W=256, eta_scale=0.15, T2=10, mini_batch_size=1000, 
     den = {'TV': DN.TVDenoiser, 'NLM': DN.NLMDenoiser}[job['denoiser']]()
     B = min(mini_batch_size, p.M0)
     t0 = time.time()
-    out = getattr(ALG, job['algo'])(p, den, eta=eta_scale * p.M0, tt=1e9, T2=T2, mini_batch_size=B, verbose=False,
+    eta = min(eta_scale * p.M0, 3.0 * B)          # full-gradient step ~0.15 * M0, capped by the minibatch term
+    out = getattr(ALG, job['algo'])(p, den, eta=eta, tt=1e9, T2=T2, mini_batch_size=B, verbose=False,
                                     converge_check=False, max_iters=iters, vr_mode='paper', mb_source='device',
                                     mb_seed=job['id'], fast=True, sync_every=iters)
     dt = time.time() - t0

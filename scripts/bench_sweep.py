@@ -1,0 +1,64 @@
+"""Config 4: Set12-style sampling-ratio x SNR sweep (12 images x 10 ratios x 7 SNRs = 840 CSMRI 256x256
+PnP-SVRG + wavelet-prox reconstructions, 200 inner iterations each, fixed hyper-parameters) partitioned
+over the GPUs of one node.  Prints reconstructions/s (whole job).
+
+    python scripts/bench_sweep.py [--jobs 840]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port 29512 scripts/bench_sweep.py
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, 'tests'))
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--jobs', type=int, default=840)
+    ap.add_argument('--iters', type=int, default=200)
+    ap.add_argument('--size', type=int, default=256)
+    a = ap.parse_args()
+    rank, world = int(os.environ.get('RANK', '0')), int(os.environ.get('WORLD_SIZE', '1'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+    from conftest import synth_image
+    from pnp_svrg_b200 import sweep
+    images = {i: synth_image(a.size, a.size, i) for i in range(12)}
+    jobs = sweep.make_jobs(list(range(12)))[:a.jobs]
+
+    def runner(job):
+        return sweep.reconstruct(job, H=a.size, W=a.size, iters=a.iters, images=images)
+    runner(dict(jobs[0]))                       # warm-up (module loads, first graph)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.time()
+    recs = sweep.run_partitioned(jobs, runner, rank, world, gather=True)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    dt = time.time() - t0
+    if rank == 0:
+        bad = [r for r in recs if 'error' in r]
+        gain = float(np.mean([r['psnr_final'] - r['psnr_init'] for r in recs if 'error' not in r]))
+        print(json.dumps({'metric': 'set12_sweep_reconstructions_per_s', 'value': len(recs) / dt, 'unit': 'recon/s',
+                          'n_gpus': world, 'jobs': len(recs), 'failed': len(bad), 'seconds': dt, 'iters_per_recon': a.iters,
+                          'mean_psnr_gain_db': gain, 'size': a.size,
+                          'note': 'includes host-side problem construction (mask, fft2 measurements, uploads) per job'}))
+        if bad:
+            print(bad[0], file=sys.stderr)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

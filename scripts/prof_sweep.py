@@ -1,0 +1,12 @@
+import sys, os, cProfile, pstats
+sys.path.insert(0, os.getcwd()); sys.path.insert(0, 'tests')
+import numpy as np, torch
+from conftest import synth_image
+from pnp_svrg_b200 import sweep
+images = {i: synth_image(256, 256, i) for i in range(12)}
+jobs = sweep.make_jobs(list(range(12)))[:60]
+sweep.reconstruct(dict(jobs[0]), images=images)
+pr = cProfile.Profile(); pr.enable()
+for j in jobs: sweep.reconstruct(j, images=images)
+torch.cuda.synchronize(); pr.disable()
+st = pstats.Stats(pr); st.sort_stats('cumulative').print_stats(28)

@@ -271,3 +271,21 @@ def test_rejects_host_objects(cuda):
     _, dut = _pair(32)
     with pytest.raises(TypeError):
         pnp_gd(dut, AP.TVPort(), eta=1.0, tt=1.0, verbose=False)
+
+
+@pytest.mark.parametrize('algo,kw', ALGOS)
+def test_fast_mode_deferred_log_matches(cuda, algo, kw):
+    """fast mode without stop rules defers the PSNR read-back; logs and iterate must equal the
+    eager run's (same minibatch stream)."""
+    from pnp_svrg_b200 import algorithms as ALG
+    from pnp_svrg_b200.denoisers import TVDenoiser
+    _, dut = _pair(64)
+    extra = {'vr_mode': 'paper'} if algo == 'pnp_svrg' else {}
+    np.random.seed(5)
+    a = getattr(ALG, algo)(dut, TVDenoiser(), tt=1e9, max_iters=23, verbose=False, converge_check=False, **kw, **extra)
+    np.random.seed(5)
+    b = getattr(ALG, algo)(dut, TVDenoiser(), tt=1e9, max_iters=23, verbose=False, converge_check=False, fast=True,
+                           sync_every=1000, **kw, **extra)
+    assert len(a['psnr_per_iter']) == len(b['psnr_per_iter']) == len(b['time_per_iter'])
+    assert rel_l2(b['z'], a['z']) < 1e-6
+    assert np.allclose(a['psnr_per_iter'], b['psnr_per_iter'], atol=0.011)
