@@ -1,0 +1,198 @@
+"""Batched PnP-SVRG for sweeps: many same-size CSMRI reconstructions advance together, one kernel
+launch per pass for the whole batch (the kernels take a batch dimension, blockIdx.y = problem).
+
+A 256x256 iteration moves ~2 MB and is launch-latency bound on a B200; the sweeps of
+script_diff_sampratio_set12.py / script_diff_snr_set12.py (image x sampling ratio x SNR, independent
+reconstructions, `Pool.map` in the reference) are therefore run as batches: per-problem masks,
+measurements, ground truths, M0 and step sizes live in stacked device arrays, the minibatch of every
+problem is drawn by the device sampler (keyed by problem index), and the PSNR / sigma logs are
+[slot][problem] arrays read back once at the end.
+
+Only the paper-mode SVRG + wavelet-prox combination (config 1 / 4) is batched here; every other
+combination goes through the per-problem engine.
+"""
+import ctypes as C
+import time
+
+import numpy as np
+import torch
+
+from . import _lib, device as D
+
+
+def csmri_host_spec(image, H, W, sample_prob, snr, rng=np.random):
+    """Host-side construction of one CSMRI problem, same draws and arithmetic as problems.CSMRI
+    (reference problems/CSMRI.py:12-41) but without touching the GPU.  `rng` is np.random or a
+    np.random.RandomState (thread-safe sweeps)."""
+    from .problems.problem import load_image
+    xrec = load_image(None, image, H, W)
+    mask = rng.choice([0, 1], size=(H, W), p=[1 - sample_prob, sample_prob])
+    Y0 = mask * np.fft.fft2(xrec)
+    sigma = np.sqrt(np.linalg.norm(Y0.ravel()) / 10 ** (snr / 10) / H / W)
+    Y = Y0 + mask * rng.normal(0, sigma, Y0.shape)
+    x0 = np.absolute(np.fft.ifft2(Y))
+    xinit = (x0 - x0.min()) / (x0.max() - x0.min())
+    hp = H // 2
+    Ym = mask * Y
+    Ymir = np.conj(Ym[(-np.arange(H)) % H][:, (-np.arange(W)) % W])
+    return dict(H=H, W=W, M0=int(np.count_nonzero(mask)), sigma=float(sigma),
+                xrec=np.ascontiguousarray(xrec.T, dtype=np.float32), xinit=np.ascontiguousarray(xinit.T, dtype=np.float32),
+                Y1=Ym[:hp].astype(np.complex64), Y2=Ymir[:hp].astype(np.complex64),
+                Y1n=Ym[hp].astype(np.complex64), Y2n=Ymir[hp].astype(np.complex64),
+                support=np.flatnonzero(mask).astype(np.int32), data_range=1.0 if xrec.min() >= 0 else 2.0)
+
+
+class BatchedSVRG:
+    """PnP-SVRG (paper-mode VR, algorithms/pnp_svrg.py:8-105 with line 53) + wavelet prox
+    (denoisers/TV.py) on a batch of CSMRI problems of one size."""
+
+    def __init__(self, specs, T2, mini_batch_size, etas, seed=0, lr_decay=1.0, sigma_modifier=1.0, max_slots=4096):
+        self.lib = _lib.load()
+        self.dev = D.require_cuda()
+        self.nb = nb = len(specs)
+        self.H, self.W = specs[0]['H'], specs[0]['W']
+        if any(s['H'] != self.H or s['W'] != self.W for s in specs):
+            raise ValueError('all problems of a batch must have the same size')
+        self.N = N = self.H * self.W
+        hp = self.H // 2
+        self.T2, self.B, self.seed, self.lr_decay = int(T2), int(mini_batch_size), int(seed), float(lr_decay)
+        self.sigma_modifier = float(sigma_modifier)
+        if any(s['M0'] < self.B for s in specs):
+            raise ValueError('mini_batch_size exceeds the number of measurements of a problem')
+        self.stream = torch.cuda.Stream(device=self.dev)
+        self.sptr = self.stream.cuda_stream
+        dev = self.dev
+
+        def stack(key, dtype):
+            return torch.from_numpy(np.ascontiguousarray(np.stack([s[key] for s in specs]))).to(dev).to(dtype).contiguous()
+
+        def stack_c(key):
+            return torch.view_as_real(torch.from_numpy(np.ascontiguousarray(np.stack([s[key] for s in specs]))).to(dev)).contiguous()
+        with torch.cuda.stream(self.stream):
+            self.xrec = stack('xrec', torch.float32)
+            self.z = stack('xinit', torch.float32)
+            self.Y1, self.Y2, self.Y1n, self.Y2n = stack_c('Y1'), stack_c('Y2'), stack_c('Y1n'), stack_c('Y2n')
+            self.m0_host = np.array([s['M0'] for s in specs], dtype=np.int32)
+            self.m0 = torch.from_numpy(self.m0_host).to(dev)
+            self.sup_stride = int(self.m0_host.max())
+            sup = np.zeros((nb, self.sup_stride), dtype=np.int32)
+            for i, s in enumerate(specs):
+                sup[i, :s['M0']] = s['support']
+            self.support = torch.from_numpy(sup).to(dev)
+            self.w = torch.empty_like(self.z)
+            self.mu = torch.empty_like(self.z)
+            self.S = torch.empty(nb * N, dtype=torch.float32, device=dev)
+            self.bits_full = torch.zeros(nb * self.W * hp, dtype=torch.uint8, device=dev)
+            self.bits_mb = torch.zeros(nb * self.W * hp, dtype=torch.uint8, device=dev)
+            self.inv_m0 = torch.from_numpy((1.0 / self.m0_host).astype(np.float32)).to(dev)
+            self.eta_host = np.broadcast_to(np.asarray(etas, dtype=np.float64), (nb,)).copy()
+            self.step = torch.from_numpy(self.eta_host.astype(np.float32)).to(dev)
+            self.mse_log = torch.zeros(max_slots * nb, dtype=torch.float64, device=dev)
+            self.sig_log = torch.zeros(max_slots * nb, dtype=torch.float64, device=dev)
+            self.counters = torch.zeros(4, dtype=torch.int32, device=dev)
+            self.check(self.lib.pnp_csmri_sel_from_indices(D.ptr(self.bits_full), self.H, self.W, nb, D.ptr(self.support), 0,
+                                                           self.sup_stride, None, 1, self.sptr))
+            # full-mask bits: every problem's own support (counts differ, so one launch per distinct problem)
+            for i, s in enumerate(specs):
+                self.check(self.lib.pnp_csmri_sel_from_indices(
+                    self.bits_full.data_ptr() + i * self.W * hp, self.H, self.W, 1,
+                    self.support.data_ptr() + 4 * i * self.sup_stride, int(s['M0']), 0, None, 0, self.sptr))
+            self.mse0 = torch.zeros(nb, dtype=torch.float64, device=dev)
+            self.check(self.lib.pnp_sq_err(D.ptr(self.z), D.ptr(self.xrec), N, nb, D.ptr(self.mse0), None, self.sptr))
+        self.data_range = np.array([s['data_range'] for s in specs])
+        self.max_slots = max_slots
+        self.slots_used = 0
+        self.graph = None
+        self.side = torch.cuda.Stream(device=self.dev)
+        self.ev_fork, self.ev_join = torch.cuda.Event(), torch.cuda.Event()
+        self.outer = 0
+
+    def check(self, rc):
+        if rc:
+            _lib.check(rc)
+
+    # ---- the launches -------------------------------------------------------------------------
+    def _grad(self, a, b, bits, with_y, stream, phases=0, **kw):
+        args = _lib.CsmriGradArgs(
+            H=self.H, W=self.W, batch=self.nb, a=D.ptr(a), b=D.ptr(b), S=D.ptr(self.S), bits=D.ptr(bits),
+            Y1=D.ptr(self.Y1) if with_y else None, Y2=D.ptr(self.Y2) if with_y else None,
+            Y1n=D.ptr(self.Y1n) if with_y else None, Y2n=D.ptr(self.Y2n) if with_y else None,
+            gscale=float(kw.get('gscale', 1.0)), gscale_ptr=D.ptr(kw.get('gscale_ptr')), step=0.0,
+            step_ptr=D.ptr(kw.get('step_ptr')), g_out=D.ptr(kw.get('g_out')), vadd=D.ptr(kw.get('vadd')), v_out=None,
+            z_in=D.ptr(kw.get('z_in')), z_out=D.ptr(kw.get('z_out')), phases=int(phases),
+            clear_bits=int(kw.get('clear', False)), sig_log=None, sig_slot=None)
+        self.check(self.lib.pnp_csmri_grad(C.byref(args), stream))
+
+    def _snapshot(self):
+        # mu = grad_full(z) (per-problem 1/M0), w = z                     (pnp_svrg.py:32-35)
+        self._grad(self.z, None, self.bits_full, True, self.sptr, gscale_ptr=self.inv_m0, g_out=self.mu)
+        self.check(self.lib.pnp_copy_f32(D.ptr(self.w), D.ptr(self.z), self.nb * self.N, self.sptr))
+
+    def _inner(self):
+        slot, draws = self.counters[0:1], self.counters[2:3]
+        gk = dict(gscale=1.0 / self.B, vadd=self.mu, step_ptr=self.step, z_in=self.z, z_out=self.z, clear=True)
+        # minibatch selection (device sampler, keyed by problem index) in parallel with the line pass
+        self.ev_fork.record(self.stream)
+        self.side.wait_event(self.ev_fork)
+        self.check(self.lib.pnp_csmri_sel_sample(D.ptr(self.bits_mb), self.H, self.W, self.nb, D.ptr(self.support), D.ptr(self.m0),
+                                                 self.sup_stride, self.B, self.seed & 0xffffffff, D.ptr(draws), None, 0,
+                                                 self.side.cuda_stream))
+        self.ev_join.record(self.side)
+        self._grad(self.z, self.w, self.bits_mb, False, self.sptr, phases=1, **gk)
+        self.stream.wait_event(self.ev_join)
+        self._grad(self.z, self.w, self.bits_mb, False, self.sptr, phases=6, **gk)
+        self.check(self.lib.pnp_estimate_sigma(D.ptr(self.z), self.H, self.W, self.nb, D.ptr(self.sig_log), D.ptr(slot), self.sptr))
+        self.check(self.lib.pnp_wavelet_denoise(D.ptr(self.z), D.ptr(self.z), self.H, self.W, self.nb, D.ptr(self.sig_log), 0.0,
+                                                self.sigma_modifier, 0.0, D.ptr(self.xrec), D.ptr(self.mse_log), D.ptr(slot),
+                                                self.sptr))
+        self.check(self.lib.pnp_advance(D.ptr(self.counters), 3, self.sptr))
+
+    def _capture(self):
+        exec_ = C.c_void_p()
+        self.stream.synchronize()
+        self.check(self.lib.pnp_graph_begin(self.sptr))
+        try:
+            with torch.cuda.stream(self.stream):
+                self._inner()
+        finally:
+            rc = self.lib.pnp_graph_end(self.sptr, C.byref(exec_))
+        self.check(rc)
+        self.graph = exec_
+
+    def run(self, n_inner):
+        """n_inner inner iterations in total (snapshot every T2), nothing is read back."""
+        if self.slots_used + n_inner > self.max_slots:
+            raise ValueError('log capacity exceeded')
+        with torch.cuda.stream(self.stream):
+            if self.graph is None:
+                self._capture()
+            done = 0
+            while done < n_inner:
+                if self.lr_decay != 1.0:
+                    self.step.copy_(torch.from_numpy((self.eta_host * self.lr_decay ** self.outer).astype(np.float32)),
+                                    non_blocking=True)
+                self._snapshot()
+                k = min(self.T2, n_inner - done)
+                for _ in range(k):
+                    self.check(self.lib.pnp_graph_launch(self.graph, self.sptr))
+                done += k
+                self.outer += 1
+        self.slots_used += n_inner
+
+    def results(self):
+        """-> dict(z [nb][N] float64 in the reference's raveled order, psnr [slots][nb], sigma_est)"""
+        self.stream.synchronize()
+        n = self.slots_used
+        mse = self.mse_log[:n * self.nb].cpu().numpy().reshape(n, self.nb)
+        sig = self.sig_log[:n * self.nb].cpu().numpy().reshape(n, self.nb) / self.W
+        with np.errstate(divide='ignore'):
+            psnr = np.around(10.0 * np.log10(self.data_range[None, :] ** 2 / (mse / self.N)), 2)
+        z = self.z.reshape(self.nb, self.W, self.H).transpose(1, 2).contiguous().cpu().numpy().astype(np.float64)
+        with np.errstate(divide='ignore'):
+            psnr0 = np.around(10.0 * np.log10(self.data_range ** 2 / (self.mse0.cpu().numpy() / self.N)), 2)
+        return dict(z=z.reshape(self.nb, self.N), psnr=psnr, psnr_init=psnr0, sigma_est=sig)
+
+    def close(self):
+        if self.graph:
+            self.lib.pnp_graph_destroy(self.graph)
+            self.graph = None

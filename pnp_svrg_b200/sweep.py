@@ -83,6 +83,56 @@ def reconstruct(job, H=256, W=256, eta_scale=0.15, T2=10, mini_batch_size=1000, 
                 denoiser=job['denoiser'], psnr_init=float(ps[0]), psnr_final=float(ps[-1]), iters=iters, seconds=dt)
 
 
+def reconstruct_batch(jobs, H=256, W=256, eta_scale=0.15, T2=10, mini_batch_size=1000, iters=200, images=None,
+                      seed=0, host_threads=8):
+    """A group of same-size CSMRI jobs as ONE batched device run (pnp_svrg_b200.batched); the host-side
+    problem construction (mask, fft2) is spread over a thread pool."""
+    from concurrent.futures import ThreadPoolExecutor
+    from .batched import BatchedSVRG, csmri_host_spec
+    from .problems.problem import load_image
+
+    def spec(job):
+        img = images[job['image']] if images is not None and not isinstance(job['image'], str) else None
+        if img is None:
+            from PIL import Image
+            img = np.array(Image.open(job['image']).resize((H, W)))
+        return csmri_host_spec(img, H, W, job['alpha'], job['snr'], rng=np.random.RandomState(seed + job['id']))
+    t0 = time.time()
+    with ThreadPoolExecutor(max_workers=host_threads) as ex:
+        specs = list(ex.map(spec, jobs))
+    B = min([mini_batch_size] + [s['M0'] for s in specs])
+    etas = [min(eta_scale * s['M0'], 3.0 * B) for s in specs]
+    run = BatchedSVRG(specs, T2=T2, mini_batch_size=B, etas=etas, seed=seed + jobs[0]['id'], max_slots=iters)
+    run.run(iters)
+    out = run.results()
+    run.close()
+    dt = time.time() - t0
+    return [dict(id=j['id'], image=str(j['image']), alpha=j['alpha'], snr=j['snr'], algo='pnp_svrg', denoiser='TV',
+                 psnr_init=float(out['psnr_init'][i]), psnr_final=float(out['psnr'][-1, i]), iters=iters,
+                 seconds=dt / len(jobs)) for i, j in enumerate(jobs)]
+
+
+def run_partitioned_batched(jobs, batch_runner, rank=0, world=1, batch=28, gather=True):
+    """Like run_partitioned, but this rank's share is processed in groups of `batch` jobs."""
+    mine = partition(jobs, rank, world)
+    local = []
+    for k in range(0, len(mine), batch):
+        group = mine[k:k + batch]
+        try:
+            recs = batch_runner(group)
+        except Exception as e:
+            recs = [dict(id=j['id'], error=repr(e)) for j in group]
+        for r in recs:
+            r['rank'] = rank
+        local.extend(recs)
+    if gather and world > 1:
+        import torch.distributed as dist
+        parts = [None] * world
+        dist.all_gather_object(parts, local)
+        local = [r for part in parts for r in part]
+    return sorted(local, key=lambda r: r['id'])
+
+
 def main():
     import torch
     import torch.distributed as dist

@@ -24,6 +24,7 @@ def main():
     ap.add_argument('--jobs', type=int, default=840)
     ap.add_argument('--iters', type=int, default=200)
     ap.add_argument('--size', type=int, default=256)
+    ap.add_argument('--batch', type=int, default=28, help='reconstructions per batched launch (0 = per-problem engine)')
     a = ap.parse_args()
     rank, world = int(os.environ.get('RANK', '0')), int(os.environ.get('WORLD_SIZE', '1'))
     local = int(os.environ.get('LOCAL_RANK', '0'))
@@ -41,8 +42,16 @@ def main():
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
+    def batch_runner(group):
+        return sweep.reconstruct_batch(group, H=a.size, W=a.size, iters=a.iters, images=images)
+    if a.batch > 0:
+        batch_runner(jobs[:min(a.batch, len(jobs))])
+        torch.cuda.synchronize()
     t0 = time.time()
-    recs = sweep.run_partitioned(jobs, runner, rank, world, gather=True)
+    if a.batch > 0:
+        recs = sweep.run_partitioned_batched(jobs, batch_runner, rank, world, batch=a.batch, gather=True)
+    else:
+        recs = sweep.run_partitioned(jobs, runner, rank, world, gather=True)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -52,7 +61,7 @@ def main():
         gain = float(np.mean([r['psnr_final'] - r['psnr_init'] for r in recs if 'error' not in r]))
         print(json.dumps({'metric': 'set12_sweep_reconstructions_per_s', 'value': len(recs) / dt, 'unit': 'recon/s',
                           'n_gpus': world, 'jobs': len(recs), 'failed': len(bad), 'seconds': dt, 'iters_per_recon': a.iters,
-                          'mean_psnr_gain_db': gain, 'size': a.size,
+                          'mean_psnr_gain_db': gain, 'size': a.size, 'batch': a.batch,
                           'note': 'includes host-side problem construction (mask, fft2 measurements, uploads) per job'}))
         if bad:
             print(bad[0], file=sys.stderr)
