@@ -213,10 +213,13 @@ class Epoch:
             p._dev_grad(eng.z, phases=1, **gk); h('lines_r2c')
             p._dev_grad(eng.z, phases=2, **gk); h('cols_mask')
             p._dev_grad(eng.z, phases=4, **gk); h('lines_c2r+update')
-        if not FUSE_SIGMA:
-            eng.check(eng.lib.pnp_estimate_sigma(self.D.ptr(eng.z), eng.H, eng.W, 1, self.D.ptr(eng.sig_log),
-                                                 self.D.ptr(eng.slot_ptr), eng.sptr)); h('sigma_mad')
-        self.den._dev_denoise(self._ctx()); h('haar_bayes+psnr')
+        if FUSED_PROX and self.den._dev_prox_fused(self._ctx()):
+            h('prox_fused(sigma+haar+psnr)')
+        else:
+            if not FUSE_SIGMA:
+                eng.check(eng.lib.pnp_estimate_sigma(self.D.ptr(eng.z), eng.H, eng.W, 1, self.D.ptr(eng.sig_log),
+                                                     self.D.ptr(eng.slot_ptr), eng.sptr)); h('sigma_mad')
+            self.den._dev_denoise(self._ctx()); h('haar_bayes+psnr')
         eng.advance(); h('advance')
 
     def _ctx(self):
@@ -251,8 +254,9 @@ class Epoch:
         eng.stream.synchronize()
 
 
+FUSED_PROX = os.environ.get('PNP_BENCH_FUSED_PROX', '1') == '1'    # sigma + wavelet + PSNR as one cooperative launch
 FUSE_SIGMA = os.environ.get('PNP_BENCH_FUSE_SIGMA', '0') == '1'   # sigma estimate inside the c2r pass (slower today)
-LAUNCHES_PER_INNER = 7 - int(FUSE_SIGMA)   # sel_sample + r2c + cols + c2r + sigma_mad + haar_bayes + advance
+LAUNCHES_PER_INNER = 7 - int(FUSE_SIGMA) - int(FUSED_PROX)   # sel_sample + r2c + cols + c2r + sigma_mad + haar_bayes + advance
 LAUNCHES_PER_SNAPSHOT = 4     # r2c + cols + c2r + D2D copy
 
 
@@ -372,12 +376,14 @@ def breakdown(a, cfg, ep, us_inner_graph):
         'cols_mask': 8.5 * N,                        # read + write spectrum (8N), selection bytes (N/2)
         'lines_c2r+update': 16.0 * N,                # read spectrum, mu, z (12N), write z (4N)
         'sigma_mad': 4.0 * N,                        # read z
+        'prox_fused(sigma+haar+psnr)': 12.0 * N,     # read z, xrec (8N), write z (4N)
         'haar_bayes+psnr': 12.0 * N,                 # read z, xrec (8N), write z (4N)
     }
     top = max(alg, key=lambda k: per.get(k, 0.0))
     ach = alg[top] / (per[top] * 1e-6) / 1e9
     traffic = ncu_traffic({'lines_r2c': 'k_lines_r2c', 'cols_mask': 'k_cols_mask', 'lines_c2r+update': 'k_lines_c2r',
-                           'sigma_mad': 'k_sigma_mad', 'haar_bayes+psnr': 'k_haar_bayes'}[top])
+                           'sigma_mad': 'k_sigma_mad', 'haar_bayes+psnr': 'k_haar_bayes',
+                           'prox_fused(sigma+haar+psnr)': 'k_prox_wavelet_fused'}[top])
     iter_bytes = 28.125 * N
     out = {
         'kernel_us': per, 'kernel_us_sum_eager': tot,

@@ -25,7 +25,8 @@ typedef enum {
     PNP_OK = 0,
     PNP_ERR_ARG = -1,       /* bad argument (size not supported, null pointer, ...) */
     PNP_ERR_CUDA = -2,      /* a CUDA runtime call failed */
-    PNP_ERR_NOT_INIT = -3   /* pnp_init() has not been called on this device */
+    PNP_ERR_NOT_INIT = -3,  /* pnp_init() has not been called on this device */
+    PNP_ERR_UNSUPPORTED = -4 /* this entry point cannot handle the given size; use the documented alternative */
 } pnp_status;
 
 /* Library / device set-up: uploads the twiddle table and raises the dynamic shared-memory
@@ -175,6 +176,14 @@ int pnp_estimate_sigma(const float* z, int H, int W, int batch, double* sig_log,
 int pnp_wavelet_denoise(const float* z_in, float* z_out, int H, int W, int batch, const double* sig_log,
                         float sigma_est, float sigma_modifier, float fallback_sigma, const float* xrec,
                         double* mse_log, const int* slot, void* stream);
+
+/* estimate_sigma + TVDenoiser.denoise + PSNR in ONE cooperative launch (the iterate is read once, every
+ * CTA keeps its lines in shared memory across a grid barrier).  Same results and log semantics as
+ * pnp_estimate_sigma followed by pnp_wavelet_denoise with sig_log.  Returns PNP_ERR_UNSUPPORTED when the
+ * image does not fit the SMs' shared memory (then use the two separate calls). */
+int pnp_prox_wavelet_fused(const float* z_in, float* z_out, int H, int W, int batch, double* sig_log,
+                           float sigma_modifier, float fallback_sigma, const float* xrec, double* mse_log,
+                           const int* slot, void* stream);
 
 /* NLMDenoiser.denoise (denoisers/NLM.py:22-27) = skimage denoise_nl_means(h = sigma = sigma_est *
  * sigma_modifier, fast_mode=False, patch_size, patch_distance) on a 2-D grey image.  Even patch sizes

@@ -106,6 +106,7 @@ class BatchedSVRG:
         self.side = torch.cuda.Stream(device=self.dev)
         self.ev_fork, self.ev_join = torch.cuda.Event(), torch.cuda.Event()
         self.outer = 0
+        self.fused_prox = True
 
     def check(self, rc):
         if rc:
@@ -141,6 +142,15 @@ class BatchedSVRG:
         self._grad(self.z, self.w, self.bits_mb, False, self.sptr, phases=1, **gk)
         self.stream.wait_event(self.ev_join)
         self._grad(self.z, self.w, self.bits_mb, False, self.sptr, phases=6, **gk)
+        if self.fused_prox:
+            rc = self.lib.pnp_prox_wavelet_fused(D.ptr(self.z), D.ptr(self.z), self.H, self.W, self.nb, D.ptr(self.sig_log),
+                                                 self.sigma_modifier, 0.0, D.ptr(self.xrec), D.ptr(self.mse_log), D.ptr(slot), self.sptr)
+            if rc == 0:
+                self.check(self.lib.pnp_advance(D.ptr(self.counters), 3, self.sptr))
+                return
+            if rc != -4:
+                self.check(rc)
+            self.fused_prox = False
         self.check(self.lib.pnp_estimate_sigma(D.ptr(self.z), self.H, self.W, self.nb, D.ptr(self.sig_log), D.ptr(slot), self.sptr))
         self.check(self.lib.pnp_wavelet_denoise(D.ptr(self.z), D.ptr(self.z), self.H, self.W, self.nb, D.ptr(self.sig_log), 0.0,
                                                 self.sigma_modifier, 0.0, D.ptr(self.xrec), D.ptr(self.mse_log), D.ptr(slot),

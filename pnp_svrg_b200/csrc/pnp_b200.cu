@@ -202,6 +202,34 @@ int ew_blocks(long long n, int per_thread) {
 
 }  // namespace
 
+namespace {
+template <int L>
+int launch_prox_fused(const float* zin, float* zout, const float* xrec, int W, int batch, float sm, float fb, double* sig_log,
+                      double* mse_log, const int* slot, cudaStream_t st) {
+    const long long total = (long long)W * batch;
+    int grid = g_num_sms;
+    if (total < grid) grid = (int)total;
+    int lpc = (int)((total + grid - 1) / grid);
+    grid = (int)((total + lpc - 1) / lpc);
+    const size_t smem = (size_t)lpc * L * sizeof(float);
+    if (smem > 200 * 1024) return fail(PNP_ERR_UNSUPPORTED, "fused prox: %zu bytes of lines per CTA do not fit shared memory", smem);
+    static size_t attr = 0;
+    if (smem > attr) {
+        CU_TRY(cudaFuncSetAttribute(pnp::k_prox_wavelet_fused<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        attr = 200 * 1024;
+    }
+    int nl = W;
+    void* args[] = {(void*)&zin, (void*)&zout, (void*)&xrec, (void*)&nl, (void*)&batch, (void*)&lpc, (void*)&sm, (void*)&fb,
+                    (void*)&sig_log, (void*)&mse_log, (void*)&slot};
+    CU_TRY(cudaLaunchCooperativeKernel((const void*)pnp::k_prox_wavelet_fused<L>, dim3(grid), dim3(512), args, smem, st));
+    return PNP_OK;
+}
+int dispatch_prox_fused(int n, const float* zin, float* zout, const float* xrec, int W, int batch, float sm, float fb,
+                        double* sig_log, double* mse_log, const int* slot, cudaStream_t st) {
+    DISPATCH_POW2(n, launch_prox_fused, zin, zout, xrec, W, batch, sm, fb, sig_log, mse_log, slot, st)
+}
+}  // namespace
+
 extern "C" {
 
 int pnp_version(void) { return 100; }
@@ -305,6 +333,13 @@ int pnp_wavelet_denoise(const float* z_in, float* z_out, int H, int W, int batch
     if (!z_in || !z_out || batch < 1) return fail(PNP_ERR_ARG, "bad argument");
     pnp::ShrinkParams sp{sig_log, sigma_est, sigma_modifier, fallback_sigma};
     return dispatch_haar(H, z_in, z_out, xrec, W, batch, sp, mse_log, slot, static_cast<cudaStream_t>(stream));
+}
+
+int pnp_prox_wavelet_fused(const float* z_in, float* z_out, int H, int W, int batch, double* sig_log, float sigma_modifier,
+                           float fallback_sigma, const float* xrec, double* mse_log, const int* slot, void* stream) {
+    if (!z_in || !z_out || !sig_log || batch < 1) return fail(PNP_ERR_ARG, "bad argument");
+    return dispatch_prox_fused(H, z_in, z_out, xrec, W, batch, sigma_modifier, fallback_sigma, sig_log, mse_log, slot,
+                               static_cast<cudaStream_t>(stream));
 }
 
 int pnp_sq_err(const float* z, const float* xrec, long long n, int batch, double* out, const int* slot, void* stream) {

@@ -315,3 +315,194 @@ k_sq_err(const float* __restrict__ z, const float* __restrict__ xrec, long long 
 }
 
 }  // namespace pnp
+
+// ------------------------------------------------------------------------------------------------
+// Fused prox: estimate_sigma + wavelet BayesShrink + PSNR in ONE cooperative launch.  Every CTA keeps
+// its share of the image lines resident in shared memory (2048 lines x 8 KiB over 148 SMs = 113 KiB
+// each), staged by TMA bulk copies: phase 1 computes the per-line sigma estimates from shared memory
+// and adds them to the global slot, a grid-wide barrier publishes the mean, phase 2 shrinks the same
+// resident lines (one warp per line, 512-sample sub-blocks: forward pass for the per-level energies,
+// second pass forward + threshold + inverse) and streams them out with the squared error.  The iterate
+// is read from HBM/L2 once instead of twice and two launches become one.
+#include <cooperative_groups.h>
+#include "fft_core.cuh"
+
+namespace pnp {
+
+template <int L> struct HaarSub {
+    static constexpr int SB = L >= 512 ? 512 : L;          // samples per sub-block
+    static constexpr int VPL = SB / 32;
+    static constexpr int NSB = L / SB;
+    static constexpr int LIN = VPL == 1 ? 0 : VPL == 2 ? 1 : VPL == 4 ? 2 : VPL == 8 ? 3 : 4;
+    static constexpr int LEVELS = HaarCfg<L>::LEVELS;
+    static constexpr int XL = LEVELS - LIN;
+};
+
+// forward pyramid of one sub-block held as VPL consecutive samples per lane; details stay in x[] / Dx[]
+template <int L>
+__device__ __forceinline__ void haar_sub_forward(float (&x)[HaarSub<L>::VPL], float (&A)[HaarSub<L>::XL + 1],
+                                                 float (&Dx)[HaarSub<L>::XL], float (&ss)[HaarSub<L>::LEVELS], int lane) {
+    using C = HaarSub<L>;
+    constexpr float RS2 = 0.70710678118654752f;
+#pragma unroll
+    for (int lv = 1; lv <= C::LIN; ++lv) {
+        const int stride = 1 << lv, half = stride >> 1;
+#pragma unroll
+        for (int i = 0; i < C::VPL / stride; ++i) {
+            const float p = x[i * stride], q = x[i * stride + half];
+            const float d = (p - q) * RS2;
+            x[i * stride] = (p + q) * RS2;
+            x[i * stride + half] = d;
+            ss[lv - 1] = fmaf(d, d, ss[lv - 1]);
+        }
+    }
+    A[0] = x[0];
+#pragma unroll
+    for (int q = 0; q < C::XL; ++q) {
+        const float p = __shfl_xor_sync(0xffffffffu, A[q], 1 << q);
+        const bool ev = (lane & (1 << q)) == 0;
+        A[q + 1] = (A[q] + p) * RS2;
+        Dx[q] = (ev ? (A[q] - p) : (p - A[q])) * RS2;
+        if ((lane & ((2 << q) - 1)) == 0) ss[C::LIN + q] = fmaf(Dx[q], Dx[q], ss[C::LIN + q]);
+    }
+}
+
+template <int L>
+__global__ void __launch_bounds__(512, 1)
+k_prox_wavelet_fused(const float* __restrict__ zin, float* __restrict__ zout, const float* __restrict__ xrec,
+                     int nlines, int batch, int lines_per_cta, float sigma_modifier, float fallback_sigma,
+                     double* __restrict__ sig_log, double* __restrict__ mse_log, const int* __restrict__ slot) {
+    using C = HaarSub<L>;
+    constexpr int VPL = C::VPL, LEVELS = C::LEVELS, XL = C::XL, LIN = C::LIN, SB = C::SB, NSB = C::NSB;
+    constexpr float RS2 = 0.70710678118654752f;
+    extern __shared__ __align__(128) float lines[];                   // lines_per_cta x L
+    __shared__ __align__(8) unsigned long long bar;
+    __shared__ unsigned scratch[16][32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long total = (long long)nlines * batch;
+    const long long first = (long long)blockIdx.x * lines_per_cta;
+    long long mine = total - first;
+    mine = mine < 0 ? 0 : (mine > lines_per_cta ? lines_per_cta : mine);
+    const int cur_slot = slot ? *slot : 0;
+
+    // ---- stage my lines (contiguous in memory) ----
+    if (threadIdx.x == 0) {
+        mbar_init(&bar, 1);
+        mbar_fence_init();
+        if (mine > 0) {
+            mbar_expect_tx(&bar, (unsigned)(mine * L * sizeof(float)));
+            for (int l = 0; l < (int)mine; ++l)
+                bulk_g2s(lines + (long long)l * L, zin + (first + l) * L, (unsigned)(L * sizeof(float)), &bar);
+        }
+    }
+    __syncthreads();
+    if (mine > 0) mbar_wait(&bar, 0);
+
+    // ---- phase 1: per-line sigma estimate (one warp per line) ----
+    for (int l = warp; l < (int)mine; l += 16) {
+        const double sig = line_sigma_mad<L>(lines + (long long)l * L, lane, scratch[warp]);
+        const int img = (int)((first + l) / nlines);
+        if (lane == 0) atomicAdd(sig_log + (long long)cur_slot * batch + img, sig);
+    }
+    __threadfence();
+    cooperative_groups::this_grid().sync();
+
+    // ---- phase 2: BayesShrink of the resident lines ----
+    float err_acc = 0.f;
+    int err_img = -1;
+    for (int l = warp; l < (int)mine; l += 16) {
+        const long long gl = first + l;
+        const int img = (int)(gl / nlines);
+        const double se = __ldcg(sig_log + (long long)cur_slot * batch + img) / (double)nlines;
+        const float sigma = (se > 0.0) ? (float)(se * (double)sigma_modifier) : fallback_sigma;
+        const float var = sigma * sigma;
+        const float* src = lines + (long long)l * L;
+        float ss[LEVELS];
+#pragma unroll
+        for (int k = 0; k < LEVELS; ++k) ss[k] = 0.f;
+        // pass A: per-level detail energies of the whole line
+#pragma unroll 1
+        for (int sbk = 0; sbk < NSB; ++sbk) {
+            float x[VPL], A[XL + 1], Dx[XL];
+            const float* s0 = src + sbk * SB + lane * VPL;
+#pragma unroll
+            for (int i = 0; i < VPL; ++i) x[i] = s0[i];
+            haar_sub_forward<L>(x, A, Dx, ss, lane);
+        }
+        float thr[LEVELS];
+#pragma unroll
+        for (int k = 0; k < LEVELS; ++k) {
+            const float dvar = warp_sum_f(ss[k]) / (float)(L >> (k + 1));
+            thr[k] = var / sqrtf(fmaxf(dvar - var, 2.220446049250313e-16f));
+        }
+        // pass B: forward again, shrink, inverse, stream out
+        if (err_img != img) {
+            if (err_img >= 0 && xrec && mse_log) {
+                const float e = warp_sum_f(err_acc);
+                if (lane == 0) atomicAdd(mse_log + (long long)cur_slot * batch + err_img, (double)e);
+            }
+            err_acc = 0.f;
+            err_img = img;
+        }
+#pragma unroll 1
+        for (int sbk = 0; sbk < NSB; ++sbk) {
+            float x[VPL], A[XL + 1], Dx[XL], dummy[LEVELS];
+            const long long goff = gl * L + sbk * SB + lane * VPL;
+            float xr[VPL];
+            if (xrec) {
+                if (VPL >= 4) {
+#pragma unroll
+                    for (int i = 0; i < VPL / 4; ++i) {
+                        const float4 r = reinterpret_cast<const float4*>(xrec + goff)[i];
+                        xr[4 * i] = r.x; xr[4 * i + 1] = r.y; xr[4 * i + 2] = r.z; xr[4 * i + 3] = r.w;
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < VPL; ++i) xr[i] = xrec[goff + i];
+                }
+            }
+            const float* s0 = src + sbk * SB + lane * VPL;
+#pragma unroll
+            for (int i = 0; i < VPL; ++i) x[i] = s0[i];
+#pragma unroll
+            for (int k = 0; k < LEVELS; ++k) dummy[k] = 0.f;
+            haar_sub_forward<L>(x, A, Dx, dummy, lane);
+#pragma unroll
+            for (int q = XL - 1; q >= 0; --q) {
+                const float d = soft_shrink(Dx[q], thr[LIN + q]);
+                const bool ev = (lane & (1 << q)) == 0;
+                A[q] = (ev ? (A[q + 1] + d) : (A[q + 1] - d)) * RS2;
+            }
+            x[0] = A[0];
+#pragma unroll
+            for (int lv = LIN; lv >= 1; --lv) {
+                const int stride = 1 << lv, half = stride >> 1;
+#pragma unroll
+                for (int i = 0; i < VPL / stride; ++i) {
+                    const float a = x[i * stride];
+                    const float d = soft_shrink(x[i * stride + half], thr[lv - 1]);
+                    x[i * stride] = (a + d) * RS2;
+                    x[i * stride + half] = (a - d) * RS2;
+                }
+            }
+            if (VPL >= 4) {
+#pragma unroll
+                for (int i = 0; i < VPL / 4; ++i)
+                    reinterpret_cast<float4*>(zout + goff)[i] = make_float4(x[4 * i], x[4 * i + 1], x[4 * i + 2], x[4 * i + 3]);
+            } else {
+#pragma unroll
+                for (int i = 0; i < VPL; ++i) zout[goff + i] = x[i];
+            }
+            if (xrec) {
+#pragma unroll
+                for (int i = 0; i < VPL; ++i) { const float e = x[i] - xr[i]; err_acc = fmaf(e, e, err_acc); }
+            }
+        }
+    }
+    if (err_img >= 0 && xrec && mse_log) {
+        const float e = warp_sum_f(err_acc);
+        if (lane == 0) atomicAdd(mse_log + (long long)cur_slot * batch + err_img, (double)e);
+    }
+}
+
+}  // namespace pnp

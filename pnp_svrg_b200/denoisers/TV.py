@@ -26,6 +26,19 @@ class TVDenoiser(Denoise):
             D.ptr(ctx.z_in), D.ptr(ctx.z_out), ctx.H, ctx.W, 1, D.ptr(ctx.sig_log), float(ctx.sigma_est),
             float(self.sigma_modifier), fallback, D.ptr(ctx.xrec), D.ptr(ctx.mse_log), D.ptr(ctx.slot), D.stream()))
 
+    def _dev_prox_fused(self, ctx):
+        """estimate_sigma + denoise + PSNR in one cooperative launch (ctx.sig_log must be the slot array the
+        estimate is accumulated into).  Returns False when the image does not fit the SMs' shared memory."""
+        rc = _lib.load().pnp_prox_wavelet_fused(
+            D.ptr(ctx.z_in), D.ptr(ctx.z_out), ctx.H, ctx.W, 1, D.ptr(ctx.sig_log), float(self.sigma_modifier),
+            float(self.denoise_strength * self.decay ** (self.t + 1)), D.ptr(ctx.xrec), D.ptr(ctx.mse_log), D.ptr(ctx.slot),
+            D.stream())
+        if rc == -4:            # PNP_ERR_UNSUPPORTED
+            return False
+        _lib.check(rc)
+        self.t += 1
+        return True
+
     def denoise(self, noisy, sigma_est=0):
         from ..engine import ProxCtx
         noisy = np.asarray(noisy)

@@ -97,6 +97,7 @@ class Engine:
         self._ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
         self._pending = []          # fast mode: (kind,) markers for slots not yet read back
         self.graph = None
+        self.fused_prox = None      # None: try the single-launch prox; False: image too large for it
         self.deferred = []
         self.since_sync = 0
         self.side = None
@@ -179,6 +180,12 @@ class Engine:
     # ------------------------------------------------------------------ prox + log
     def prox(self, z_in, z_out):
         """sigma estimate + denoiser + squared error against the ground truth into the current slot."""
+        if self.uses_sigma and not self.sigma_ready and self.fused_prox is not False and hasattr(self.d, '_dev_prox_fused'):
+            ok = self.d._dev_prox_fused(ProxCtx(z_in, z_out, self.H, self.W, sig_log=self.sig_log, xrec=self.p._xrec_dev,
+                                                mse_log=self.mse_log, slot=self.slot_ptr))
+            self.fused_prox = ok
+            if ok:
+                return
         if self.uses_sigma and not self.sigma_ready:
             self.check(self.lib.pnp_estimate_sigma(D.ptr(z_in), self.H, self.W, 1, D.ptr(self.sig_log),
                                                    D.ptr(self.slot_ptr), self.sptr))

@@ -289,3 +289,34 @@ def test_fast_mode_deferred_log_matches(cuda, algo, kw):
     assert len(a['psnr_per_iter']) == len(b['psnr_per_iter']) == len(b['time_per_iter'])
     assert rel_l2(b['z'], a['z']) < 1e-6
     assert np.allclose(a['psnr_per_iter'], b['psnr_per_iter'], atol=0.011)
+
+
+@pytest.mark.parametrize('H,W', [(32, 32), (64, 64), (256, 256), (1024, 64), (2048, 2048)])
+def test_fused_prox_equals_two_kernel_prox(cuda, H, W):
+    """pnp_prox_wavelet_fused (one cooperative launch) == pnp_estimate_sigma + pnp_wavelet_denoise."""
+    import torch
+    from pnp_svrg_b200 import _lib, device as D
+    rng = np.random.default_rng(H + W)
+    z0 = synth_image(H, W, 7).astype(np.float64) / 255 + 0.05 * rng.standard_normal((H, W))
+    xr = synth_image(H, W, 7).astype(np.float64) / 255
+    dev = D.require_cuda()
+    lib = _lib.load()
+    zl, xl = D.to_lines(z0, H, W, dev), D.to_lines(xr, H, W, dev)
+    outs = []
+    for fused in (False, True):
+        sig = torch.zeros(4, dtype=torch.float64, device=dev)
+        mse = torch.zeros(4, dtype=torch.float64, device=dev)
+        slot = torch.tensor([2], dtype=torch.int32, device=dev)
+        o = torch.empty_like(zl)
+        if fused:
+            _lib.check(lib.pnp_prox_wavelet_fused(D.ptr(zl), D.ptr(o), H, W, 1, D.ptr(sig), 1.0, 0.0, D.ptr(xl), D.ptr(mse),
+                                                  D.ptr(slot), D.stream()))
+        else:
+            _lib.check(lib.pnp_estimate_sigma(D.ptr(zl), H, W, 1, D.ptr(sig), D.ptr(slot), D.stream()))
+            _lib.check(lib.pnp_wavelet_denoise(D.ptr(zl), D.ptr(o), H, W, 1, D.ptr(sig), 0.0, 1.0, 0.0, D.ptr(xl), D.ptr(mse),
+                                               D.ptr(slot), D.stream()))
+        outs.append((o.cpu().numpy(), sig.cpu().numpy(), mse.cpu().numpy()))
+    (a, sa, ma), (b, sb, mb) = outs
+    assert sa[2] > 0 and abs(sa[2] - sb[2]) <= 1e-12 * sa[2] and sb[0] == sb[1] == sb[3] == 0
+    assert np.array_equal(a, b) or rel_l2(b, a) < 1e-6
+    assert abs(ma[2] - mb[2]) <= 1e-6 * ma[2]
