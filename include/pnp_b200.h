@@ -96,7 +96,8 @@ int pnp_sample_indices(int* idx_out, int n, int count, unsigned seed, const int*
 /* Host twin of the device sampler (same keyed Feistel permutation, bit-identical positions): fills
  * idx_out_host[0..count) on the CPU with `threads` worker threads.  Host plumbing for mb_source='host'
  * (the reference draws on the host too, problems/CSMRI.py:72); not a compute fallback. */
-int pnp_sample_indices_host(int* idx_out_host, int n, int count, unsigned seed, unsigned counter, int img, int threads);
+int pnp_sample_indices_host(int* idx_out_host, int n, int count, unsigned seed, unsigned counter, int img, int threads,
+                            const int* support_host /* optional: idx_out = support_host[position] */);
 
 /* ---- Deblur + super-resolution gradient ------------------------------------------------------
  * Replaces Deblur.grad_full (problems/DeblurSR.py:126-132), Deblur.grad_stoch (:135-147) and the

@@ -77,7 +77,7 @@ PROTOTYPES = {
                                        C.c_longlong, C.c_int, C.c_uint, C.c_void_p, C.c_void_p, C.c_int,
                                        C.c_void_p]),
     'pnp_sample_indices': (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_uint, C.c_void_p, C.c_void_p]),
-    'pnp_sample_indices_host': (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_uint, C.c_uint, C.c_int, C.c_int]),
+    'pnp_sample_indices_host': (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_uint, C.c_uint, C.c_int, C.c_int, C.c_void_p]),
     'pnp_deblur_grad': (C.c_int, [C.POINTER(DeblurGradArgs), C.c_void_p]),
     'pnp_pr_grad': (C.c_int, [C.POINTER(PrGradArgs), C.c_void_p]),
     'pnp_nlm_denoise': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,

@@ -426,7 +426,8 @@ inline unsigned h_feistel(unsigned i, unsigned n, unsigned key, int hb) {
 }
 }  // namespace
 
-int pnp_sample_indices_host(int* out, int n, int count, unsigned seed, unsigned counter, int img, int threads) {
+int pnp_sample_indices_host(int* out, int n, int count, unsigned seed, unsigned counter, int img, int threads,
+                            const int* support_host) {
     if (!out || n < 1 || count < 1 || count > n) return fail(PNP_ERR_ARG, "bad argument");
     const unsigned key = h_mix32(seed ^ h_mix32(counter * 0x632be5abU + (unsigned)img));
     int hb = 1;
@@ -434,7 +435,12 @@ int pnp_sample_indices_host(int* out, int n, int count, unsigned seed, unsigned 
     if (threads < 1) threads = 1;
     if (threads > 16) threads = 16;
     if (count < 4096) threads = 1;
-    auto work = [=](int lo, int hi) { for (int i = lo; i < hi; ++i) out[i] = (int)h_feistel((unsigned)i, (unsigned)n, key, hb); };
+    auto work = [=](int lo, int hi) {
+        for (int i = lo; i < hi; ++i) {
+            const int p = (int)h_feistel((unsigned)i, (unsigned)n, key, hb);
+            out[i] = support_host ? support_host[p] : p;
+        }
+    };
     if (threads == 1) { work(0, count); return PNP_OK; }
     std::vector<std::thread> pool;
     const int per = (count + threads - 1) / threads;

@@ -92,8 +92,15 @@ class Engine:
         self.denoise_time = 0.0
         self._stream_pos = 0
         self._host_draws = 0
-        self._pos_host = None
-        self._host_threads = max(1, min(8, (os.cpu_count() or 1) // 2))
+        self._draw_queue = []
+        self._draw_ahead = 3
+        self._draw_pool = None
+        if mb_source == 'host':
+            from concurrent.futures import ThreadPoolExecutor
+            self._draw_pool = ThreadPoolExecutor(max_workers=3)
+            self._host_threads = max(1, min(4, (os.cpu_count() or 1) // 4))
+        if mb_source != 'host':
+            self._host_threads = max(1, min(8, (os.cpu_count() or 1) // 2))
         self._ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
         self._pending = []          # fast mode: (kind,) markers for slots not yet read back
         self.graph = None
@@ -147,14 +154,12 @@ class Engine:
         if self.mb_source == 'legacy':
             idx = self.p._draw_indices(self.B)
         elif self.mb_source == 'host':
-            sup = getattr(self.p, '_support_host', None)
-            n = self.p.M if sup is None else sup.size
-            if self._pos_host is None:
-                self._pos_host = np.empty(self.B, dtype=np.int32)
-            _lib.check(self.lib.pnp_sample_indices_host(self._pos_host.ctypes.data, int(n), self.B, self.mb_seed & 0xffffffff,
-                                                        self._host_draws & 0xffffffff, 0, self._host_threads))
+            # the draw for the NEXT iteration is produced by a helper thread (C sampler, GIL released) while the
+            # GPU works on the current one: one draw of look-ahead, same sequence as without the thread
+            while len(self._draw_queue) < self._draw_ahead:
+                self._draw_queue.append(self._draw_pool.submit(self._host_draw_job, self._host_draws + len(self._draw_queue)))
+            idx = self._draw_queue.pop(0).result()
             self._host_draws += 1
-            idx = self._pos_host if sup is None else sup[self._pos_host]
         elif self.mb_source == 'stream':
             idx = np.asarray(self.mb_stream[self._stream_pos])
             self._stream_pos += 1
@@ -167,6 +172,15 @@ class Engine:
         for i, e in enumerate(extra):
             buf[self.B + i] = e
         return idx
+
+    def _host_draw_job(self, counter):
+        sup = getattr(self.p, '_support_host', None)
+        n = self.p.M if sup is None else sup.size
+        out = np.empty(self.B, dtype=np.int32)
+        _lib.check(self.lib.pnp_sample_indices_host(out.ctypes.data, int(n), self.B, self.mb_seed & 0xffffffff,
+                                                    counter & 0xffffffff, 0, self._host_threads,
+                                                    None if sup is None else sup.ctypes.data))
+        return out
 
     def upload_sel(self):
         """pinned -> device copy of the staged minibatch and rebuild of the selection."""
@@ -286,6 +300,9 @@ class Engine:
             self.lib.pnp_graph_destroy(exec_)
 
     def result(self, name):
+        if self._draw_pool is not None:
+            self._draw_pool.shutdown(wait=True)
+            self._draw_pool = None
         self.resolve()
         self.stream.synchronize()
         z = D.from_lines(self.z, self.H, self.W)
