@@ -216,8 +216,9 @@ typedef struct {
     float last_bias;
     int mode;
     float range, shift_in;
-    const void* w_tc[PNP_CNN_MAX_LAYERS];   /* middle layers for the tensor-core path: bf16 [192 (dp,co)][192 (dl,ci)],
-                                               null when only the fp32 path is used */
+    const void* w_tc[PNP_CNN_MAX_LAYERS];   /* tensor-core path only (null otherwise), bf16, K = (dl, ci) contiguous:
+                                               middle layers [192 rows (dp, co)][192] with scale[l] folded in,
+                                               last layer [16 rows (dp, then zeros)][192] */
 } pnp_cnn_net;
 int pnp_cnn_forward(const pnp_cnn_net* net, const float* img, float* out, int PH, int PW, float* act0, float* act1,
                     int* stats, const float* xrec, double* mse_log, const int* slot, int precision, void* stream);

@@ -1,4 +1,4 @@
-// 64 -> 64 channel 3x3 convolution on the 5th-generation tensor cores (tcgen05 / TMEM / TMA), bf16
+// 64 -> 64 (and 64 -> 1) channel 3x3 convolution on the 5th-generation tensor cores (tcgen05 / TMEM / TMA), bf16
 // operands, fp32 accumulation -- the throughput path of the DnCNN / MMO conv stacks
 // (reference: denoisers/DeepDenoisers/model/models.py:5-22, realSN_models.py:5-18,
 // denoisers/MMODenoise.py:73-103; cuDNN via torch in the reference, no sm_100 code there).
@@ -16,10 +16,18 @@
 //
 //     out[s] = T_-1[s-1] + T_0[s] + T_+1[s+1]
 //
-// (neighbour TMEM lanes via warp shuffles, warp boundaries through shared memory).  Row 0 and row 127
-// of a tile are halo, so a tile yields 126 outputs (98.4 % efficiency) and the activation tile is
-// read 3x (once per dl) instead of 9x.  A shifted A operand cannot be expressed by a UMMA shared
-// memory descriptor (rows are grouped by 8 in the canonical layouts), hence the output-side shift.
+// (neighbour TMEM lanes via warp shuffles).  Each 32-lane TMEM quadrant of a tile is loaded with its own
+// 32 consecutive positions (a separate TMA box), overlapping the next quadrant's by two, so rows 0 and 31
+// of every quadrant are halo, the shift never crosses a warp, and a tile yields 4 x 30 = 120 outputs
+// (93.75 % efficiency); the activation tile is read 3x (once per dl) instead of 9x.  A shifted A operand
+// would need N = 64 (one GEMM per tap), which makes the A re-read from shared memory the bound (4 KiB per
+// 32-cycle MMA); the N = 192 output-shift form reads A once per 96-cycle MMA.
+// The per-channel BatchNorm scale is folded into the bf16 weights by the host; the epilogue adds the
+// shift and applies max(v, slope*v).
+//
+// The last layer (64 -> 1) is the same kernel with N = 16 (three used columns, one per dp): its
+// epilogue sums the three shifted columns and applies the denoiser's output map
+// (denoisers/RealSN_DnCNN.py:29-39, denoisers/MMODenoise.py:57-66).
 //
 // Warp roles (320 threads, one persistent CTA per SM): warp 0 TMA producer, warp 1 MMA issuer + TMEM
 // allocator, warps 2-9 epilogue (TMEM lane quadrant = warp_id % 4, two warps per quadrant split the channels).
@@ -33,25 +41,35 @@
 namespace pnp {
 
 #define TC_M 128
-#define TC_N 192
 #define TC_KBLK 64               // one dl: 64 input channels = 128 bytes per row (one swizzle span)
 #define TC_A_BYTES (TC_M * 128)  // 16 KiB
-#define TC_B_BYTES (TC_N * 128)  // 24 KiB per K block
 #define TC_STAGES 4
-#define TC_OUT_PER_TILE 126
+#define TC_Q_ROWS 32             // rows per TMEM lane quadrant = rows per TMA box
+#define TC_OUT_PER_Q 30          // rows 0 and 31 of every quadrant are halo
+#define TC_OUT_PER_TILE (4 * TC_OUT_PER_Q)
 #define TC_THREADS 320           // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue (2 per TMEM lane quadrant)
+
+template <int CO> struct TcCfg {                       // CO = 64: middle layers, CO = 1: last layer
+    static constexpr int N = CO == 64 ? 192 : 16;      // (dp, co) columns, padded to a legal UMMA N
+    static constexpr int B_BYTES = N * 128;            // per K block
+    static constexpr int ACC_COLS = CO == 64 ? 256 : 32;
+    static constexpr int TMEM_COLS = CO == 64 ? 512 : 64;
+};
 
 struct TcSmem {
     unsigned long long full[TC_STAGES], empty[TC_STAGES], bfull, tfull[2], tempty[2];
     unsigned tmem_base;
-    __align__(16) float halo[2][2][4][2][16];  // [channel half][chunk parity][quadrant][0: lane31 T_-1, 1: lane0 T_+1][16 channels]
-    float2 affine[64];           // per output channel (scale, shift): folded BatchNorm / bias
+    __align__(16) float shift[64];   // per output channel shift (bias / folded BatchNorm; the scale is folded into the weights)
+    float err[8];
 };
 
-__device__ __forceinline__ void mbar_wait_bounded(unsigned long long* bar, unsigned parity, int backoff = 0) {
+template <int CO> constexpr size_t tc_smem() {
+    return ((3 * TcCfg<CO>::B_BYTES + 1023) & ~(size_t)1023) + TC_STAGES * TC_A_BYTES + sizeof(TcSmem) + 1024;
+}
+
+__device__ __forceinline__ void mbar_wait_bounded(unsigned long long* bar, unsigned parity) {
     unsigned done = 0;
     for (unsigned spin = 0; !done; ++spin) {
-        if (backoff && spin) __nanosleep(backoff);
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
             "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
@@ -77,7 +95,7 @@ __device__ __forceinline__ unsigned long long umma_desc_sw128(const void* smem_p
     d |= (unsigned long long)2 << 61;                                      // layout type SWIZZLE_128B
     return d;
 }
-// instruction descriptor kind::f16: D fp32, A/B bf16, both K-major, N = 192, M = 128
+// instruction descriptor kind::f16: D fp32, A/B bf16, both K-major
 __device__ __forceinline__ constexpr unsigned umma_idesc_bf16(int M, int N) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((unsigned)(N >> 3) << 17) | ((unsigned)(M >> 4) << 24);
 }
@@ -100,17 +118,39 @@ __device__ __forceinline__ void tmem_ld16(unsigned taddr, float (&v)[16]) {
 #pragma unroll
     for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
+__device__ __forceinline__ void tmem_ld4(unsigned taddr, float (&v)[4]) {
+    unsigned r[4];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(taddr));
+#pragma unroll
+    for (int i = 0; i < 4; ++i) v[i] = __uint_as_float(r[i]);
+}
 
-// in / out: bf16 [S][64] with S = PH*(PW+1) positions; tmA over `in` (box 64 x 128), tmB over the packed
-// weights [192 rows (dp,co)][192 (dl,ci)] (box 64 x 192).
+// Output side of the last layer (CO = 1): the wrapper arithmetic around the network
+struct TcLast {
+    const float* img;       // network input image (fp32 line layout, pitch PW)
+    float* out;             // denoised image
+    const float* xrec;      // optional ground truth for the PSNR
+    double* mse_log;
+    const int* slot;
+    float bias;
+    CnnIo io;
+};
+
+// in / out: bf16 [S][64] with S = PH*(PW+1) positions.  tmA over `in` with box 64 x 32: every TMEM lane
+// quadrant (32 rows) of a tile gets its own 32 consecutive positions, overlapping its neighbours by
+// two, so that rows 0 and 31 of each quadrant are halo and the output shift never leaves a warp.
+// tmB over the packed weights [N rows (dp, co)][192 (dl, ci)] (box 64 x N), BatchNorm scale folded in.
+template <int CO>
 __global__ void __launch_bounds__(TC_THREADS, 1)
-k_conv_mid_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-              __nv_bfloat16* __restrict__ out, const float* __restrict__ scale, const float* __restrict__ shift,
-              float slope, int PW, int S, int n_tiles, int dbg) {
+k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+          __nv_bfloat16* __restrict__ out, const float* __restrict__ shift, float slope, int PW, int S, int n_tiles,
+          TcLast last) {
+    using CF = TcCfg<CO>;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<unsigned long long>(smem_raw) + 1023ull) & ~1023ull);
-    unsigned char* sB = base;                                   // 3 x 24 KiB
-    unsigned char* sA = base + 3 * TC_B_BYTES;                  // TC_STAGES x 16 KiB
+    unsigned char* sB = base;                                                  // 3 K blocks
+    unsigned char* sA = base + ((3 * CF::B_BYTES + 1023) & ~1023);             // TC_STAGES x 16 KiB
     TcSmem* ctl = reinterpret_cast<TcSmem*>(sA + TC_STAGES * TC_A_BYTES);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int pitch = PW + 1;
@@ -121,12 +161,10 @@ k_conv_mid_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
         for (int i = 0; i < 2; ++i) { mbar_init(&ctl->tfull[i], 1); mbar_init(&ctl->tempty[i], 8); }
         mbar_fence_init();
     }
-    if (threadIdx.x >= 64 && threadIdx.x < 128) {
-        const int c = threadIdx.x - 64;
-        ctl->affine[c] = make_float2(scale ? scale[c] : 1.f, shift ? shift[c] : 0.f);
-    }
-    if (warp == 1) {                                            // TMEM: 512 columns (2 accumulators of 192)
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&ctl->tmem_base)), "r"(512u));
+    if (threadIdx.x >= 64 && threadIdx.x < 128) ctl->shift[threadIdx.x - 64] = (CO == 64 && shift) ? shift[threadIdx.x - 64] : 0.f;
+    if (threadIdx.x < 8) ctl->err[threadIdx.x] = 0.f;
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&ctl->tmem_base)), "r"((unsigned)CF::TMEM_COLS));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
     asm volatile("tcgen05.fence::before_thread_sync;");
@@ -137,16 +175,19 @@ k_conv_mid_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
     if (warp == 0) {
         // ===== TMA producer =====
         if (lane == 0) {
-            mbar_expect_tx(&ctl->bfull, 3 * TC_B_BYTES);
-            for (int kb = 0; kb < 3; ++kb) tma_load_2d(sB + kb * TC_B_BYTES, &tmB, kb * TC_KBLK, 0, &ctl->bfull);
+            mbar_expect_tx(&ctl->bfull, 3 * CF::B_BYTES);
+            for (int kb = 0; kb < 3; ++kb) tma_load_2d(sB + kb * CF::B_BYTES, &tmB, kb * TC_KBLK, 0, &ctl->bfull);
             int stage = 0;
             unsigned phase = 0;
             for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
                 const int s0 = tile * TC_OUT_PER_TILE - 1;
                 for (int dl = -1; dl <= 1; ++dl) {
-                    mbar_wait_bounded(&ctl->empty[stage], phase ^ 1, (dbg & 16) ? 100 : 0);
+                    mbar_wait_bounded(&ctl->empty[stage], phase ^ 1);
                     mbar_expect_tx(&ctl->full[stage], TC_A_BYTES);
-                    tma_load_2d(sA + stage * TC_A_BYTES, &tmA, 0, s0 + dl * pitch, &ctl->full[stage]);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q)
+                        tma_load_2d(sA + stage * TC_A_BYTES + q * (TC_Q_ROWS * 128), &tmA, 0, s0 + q * TC_OUT_PER_Q + dl * pitch,
+                                    &ctl->full[stage]);
                     if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
                 }
             }
@@ -154,19 +195,19 @@ k_conv_mid_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
     } else if (warp == 1) {
         // ===== MMA issuer (one thread) =====
         if (lane == 0) {
-            const unsigned idesc = umma_idesc_bf16(TC_M, TC_N);
+            const unsigned idesc = umma_idesc_bf16(TC_M, CF::N);
             mbar_wait_bounded(&ctl->bfull, 0);
             int stage = 0, acc = 0;
             unsigned phase = 0, aphase = 0;
             for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-                mbar_wait_bounded(&ctl->tempty[acc], aphase ^ 1, (dbg & 16) ? 100 : 0);   // epilogue has drained this accumulator
+                mbar_wait_bounded(&ctl->tempty[acc], aphase ^ 1);          // epilogue has drained this accumulator
                 asm volatile("tcgen05.fence::after_thread_sync;");
-                const unsigned d = tmem + acc * 256;                       // accumulators at columns 0 and 256
+                const unsigned d = tmem + acc * CF::ACC_COLS;
                 for (int kb = 0; kb < 3; ++kb) {
-                    mbar_wait_bounded(&ctl->full[stage], phase, (dbg & 16) ? 100 : 0);
+                    mbar_wait_bounded(&ctl->full[stage], phase);
                     asm volatile("tcgen05.fence::after_thread_sync;");
                     const unsigned long long da = umma_desc_sw128(sA + stage * TC_A_BYTES);
-                    const unsigned long long db = umma_desc_sw128(sB + kb * TC_B_BYTES);
+                    const unsigned long long db = umma_desc_sw128(sB + kb * CF::B_BYTES);
 #pragma unroll
                     for (int k = 0; k < TC_KBLK / 16; ++k)                 // 32 bytes (= 2 x 16 B units) per K step
                         umma_f16(d, da + 2 * k, db + 2 * k, idesc, (kb | k) ? 1u : 0u);
@@ -178,125 +219,149 @@ k_conv_mid_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
             }
         }
     } else {
-        // ===== epilogue warps 2..9: TMEM lane quadrant q = warp % 4, channel half = (warp - 2) / 4 =====
+        // ===== epilogue warps 2..9: TMEM lane quadrant q = warp % 4, second index = (warp - 2) / 4 =====
         const int q = warp & 3;
         const int half = (warp - 2) >> 2;
-        const int row = q * 32 + lane;                                     // position inside the tile
+        const bool interior = lane >= 1 && lane <= TC_OUT_PER_Q;
         int acc = 0;
         unsigned aphase = 0;
+        float err = 0.f;
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-            const int s = tile * TC_OUT_PER_TILE - 1 + row;
+            const int s = tile * TC_OUT_PER_TILE + q * TC_OUT_PER_Q + lane - 1;       // position of this lane's row
             mbar_wait_bounded(&ctl->tfull[acc], aphase);
             asm volatile("tcgen05.fence::after_thread_sync;");
-            const unsigned t0 = tmem + acc * 256 + ((unsigned)(q * 32) << 16);
-            const bool valid = row >= 1 && row <= TC_OUT_PER_TILE && s >= 0 && s < S && (s % pitch) != PW && !(dbg & 1);
+            const unsigned t0 = tmem + acc * CF::ACC_COLS + ((unsigned)(q * 32) << 16);
+            const bool valid = interior && s >= 0 && s < S && (s % pitch) != PW;
+            if (CO == 64) {
 #pragma unroll 1
-            for (int c = 32 * half; c < ((dbg & 4) ? 0 : 32 * half + 32); c += 16) {
-                float tm[16], tz[16], tp[16];
-                if (!(dbg & 8)) {
-                    tmem_ld16(t0 + c, tm);              // T_-1 own row
+                for (int c = 32 * half; c < 32 * half + 32; c += 16) {
+                    float tm[16], tz[16], tp[16], sh[16];
+                    tmem_ld16(t0 + c, tm);              // T_-1 of this lane's row
                     tmem_ld16(t0 + 64 + c, tz);         // T_0
                     tmem_ld16(t0 + 128 + c, tp);        // T_+1
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        *reinterpret_cast<float4*>(sh + 4 * i) = *reinterpret_cast<const float4*>(ctl->shift + c + 4 * i);
                     asm volatile("tcgen05.wait::ld.sync.aligned;");
-                } else {
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) { tm[i] = (float)(row + i); tz[i] = (float)(c + i); tp[i] = 1.f; }
-                }
-                if (dbg & 2) {
-                    if (tm[0] + tz[1] + tp[2] == 12345.678f) out[0] = __float2bfloat16(tm[3]);
-                    continue;
-                }
-                const int par = (c >> 4) & 1;
-                if (lane == 31) {
-#pragma unroll
-                    for (int i = 0; i < 4; ++i)
-                        reinterpret_cast<float4*>(ctl->halo[half][par][q][0])[i] = make_float4(tm[4 * i], tm[4 * i + 1], tm[4 * i + 2], tm[4 * i + 3]);
-                }
-                if (lane == 0) {
-#pragma unroll
-                    for (int i = 0; i < 4; ++i)
-                        reinterpret_cast<float4*>(ctl->halo[half][par][q][1])[i] = make_float4(tp[4 * i], tp[4 * i + 1], tp[4 * i + 2], tp[4 * i + 3]);
-                }
-                if (half == 0) asm volatile("bar.sync 1, 128;" ::: "memory");     // the four warps of this channel half
-                else asm volatile("bar.sync 2, 128;" ::: "memory");
-                // neighbour warps' boundary rows, read by every lane (broadcast) so that no branch diverges
-                float hu[16], hd[16];
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const float4 a4 = reinterpret_cast<const float4*>(ctl->halo[half][par][(q + 3) & 3][0])[i];   // previous quadrant's last row
-                    const float4 b4 = reinterpret_cast<const float4*>(ctl->halo[half][par][(q + 1) & 3][1])[i];   // next quadrant's first row
-                    hu[4 * i] = a4.x; hu[4 * i + 1] = a4.y; hu[4 * i + 2] = a4.z; hu[4 * i + 3] = a4.w;
-                    hd[4 * i] = b4.x; hd[4 * i + 1] = b4.y; hd[4 * i + 2] = b4.z; hd[4 * i + 3] = b4.w;
-                }
-                float o[16];
-#pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    float up = __shfl_up_sync(0xffffffffu, tm[i], 1);       // T_-1 of row - 1
-                    float dn = __shfl_down_sync(0xffffffffu, tp[i], 1);     // T_+1 of row + 1
-                    up = lane == 0 ? hu[i] : up;                            // (quadrant 0 / 3 edges are halo rows: unused)
-                    dn = lane == 31 ? hd[i] : dn;
-                    const float2 af = ctl->affine[c + i];
-                    const float v = fmaf(up + tz[i] + dn, af.x, af.y);
-                    o[i] = v > 0.f ? v : v * slope;
-                }
-                if (valid) {
                     uint4 pk[2];
                     __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(pk);
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) h[i] = __floats2bfloat162_rn(o[2 * i], o[2 * i + 1]);
-                    uint4* dst = reinterpret_cast<uint4*>(out + (long long)s * 64 + c);
-                    dst[0] = pk[0];
-                    dst[1] = pk[1];
+                    for (int i = 0; i < 16; i += 2) {
+                        float o2[2];
+#pragma unroll
+                        for (int u = 0; u < 2; ++u) {
+                            const float up = __shfl_up_sync(0xffffffffu, tm[i + u], 1);       // T_-1 of row - 1
+                            const float dn = __shfl_down_sync(0xffffffffu, tp[i + u], 1);     // T_+1 of row + 1
+                            const float v = (up + tz[i + u]) + (dn + sh[i + u]);
+                            o2[u] = fmaxf(v, v * slope);                                       // ReLU / leaky ReLU (slope <= 1)
+                        }
+                        h[i >> 1] = __floats2bfloat162_rn(o2[0], o2[1]);
+                    }
+                    if (valid) {
+                        uint4* dst = reinterpret_cast<uint4*>(out + (long long)s * 64 + c);
+                        dst[0] = pk[0];
+                        dst[1] = pk[1];
+                    }
+                }
+            } else if (half == 0) {
+                // last layer: one output per position + the wrapper's output map
+                float t[4];
+                tmem_ld4(t0, t);
+                asm volatile("tcgen05.wait::ld.sync.aligned;");
+                const float up = __shfl_up_sync(0xffffffffu, t[0], 1);
+                const float dn = __shfl_down_sync(0xffffffffu, t[2], 1);
+                const float conv = up + t[1] + dn;
+                if (valid) {
+                    const int l = s / pitch, p = s - l * pitch;
+                    const long long pix = (long long)l * PW + p;
+                    const float x = last.img[pix];
+                    float res;
+                    if (last.io.mode == 0) {
+                        const float mn = ord2f(last.io.stats[0]), mx = ord2f(last.io.stats[1]);
+                        const float xt = (x - mn) / (mx - mn) * last.io.range + last.io.shift;
+                        res = ((xt - conv) - last.io.shift) / last.io.range * (mx - mn) + mn;
+                    } else {
+                        res = fminf(fmaxf(conv + last.bias + fminf(fmaxf(x, 0.f), 1.f), 0.f), 1.f);
+                    }
+                    last.out[pix] = res;
+                    if (last.xrec) { const float df = res - last.xrec[pix]; err = fmaf(df, df, err); }
                 }
             }
             asm volatile("tcgen05.fence::before_thread_sync;");
             if (lane == 0) mbar_arrive(&ctl->tempty[acc]);                 // 8 arrivals (one per epilogue warp)
             if (++acc == 2) { acc = 0; aphase ^= 1; }
         }
+        if (CO == 1 && last.xrec && last.mse_log) {
+            err = warp_sum_f(err);
+            if (lane == 0) ctl->err[warp - 2] = err;
+        }
     }
     asm volatile("tcgen05.fence::before_thread_sync;");
     __syncthreads();
+    if (CO == 1 && last.xrec && last.mse_log && threadIdx.x == 0) {
+        float t = 0.f;
+        for (int k = 0; k < 8; ++k) t += ctl->err[k];
+        atomicAdd(last.mse_log + (last.slot ? *last.slot : 0), (double)t);
+    }
     if (warp == 1) {
         asm volatile("tcgen05.fence::after_thread_sync;");
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u));
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((unsigned)CF::TMEM_COLS));
     }
 }
 
 // ---- thin first / last layers for the bf16 path (CUDA cores; padded bf16 NHWC activations) ----
+// first layer (1 -> 64): one thread per pixel, 16 channels at a time (576 FMAs per pixel, the nine inputs
+// transformed once), 32-byte sector stores
 __global__ void __launch_bounds__(256)
 k_conv_first_bf16(const float* __restrict__ img, __nv_bfloat16* __restrict__ out, const float* __restrict__ w, CnnAct a,
                   CnnIo io, int PH, int PW) {
-    __shared__ float sw[9 * CNN_C];
+    __shared__ __align__(16) float sw[9 * CNN_C];
+    __shared__ __align__(16) float s_scale[CNN_C], s_shift[CNN_C];
     for (int i = threadIdx.x; i < 9 * CNN_C; i += blockDim.x) sw[i] = w[i];
+    for (int i = threadIdx.x; i < CNN_C; i += blockDim.x) {
+        s_scale[i] = a.scale ? a.scale[i] : 1.f;
+        s_shift[i] = a.shift ? a.shift[i] : 0.f;
+    }
     __syncthreads();
-    const long long total = (long long)PH * PW * (CNN_C / 8);
-    for (long long id = (long long)blockIdx.x * blockDim.x + threadIdx.x; id < total; id += (long long)gridDim.x * blockDim.x) {
-        const int cg = (int)(id % (CNN_C / 8));
-        const long long pix = id / (CNN_C / 8);
-        const int l = (int)(pix / PW), p = (int)(pix % PW);
-        float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    const long long total = (long long)PH * PW;
+    for (long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x; pix < total; pix += (long long)gridDim.x * blockDim.x) {
+        const int l = (int)(pix / PW), p = (int)(pix - (long long)l * PW);
+        float x[9];
 #pragma unroll
         for (int dl = -1; dl <= 1; ++dl)
 #pragma unroll
             for (int dp = -1; dp <= 1; ++dp) {
                 const int ll = l + dl, pp = p + dp;
-                if (ll < 0 || ll >= PH || pp < 0 || pp >= PW) continue;
-                const float v = cnn_input(io, img[(long long)ll * PW + pp]);
-                const float* ww = sw + ((dl + 1) * 3 + (dp + 1)) * CNN_C + cg * 8;
-#pragma unroll
-                for (int k = 0; k < 8; ++k) acc[k] = fmaf(v, ww[k], acc[k]);
+                const bool in = ll >= 0 && ll < PH && pp >= 0 && pp < PW;
+                x[(dl + 1) * 3 + dp + 1] = in ? cnn_input(io, img[(long long)ll * PW + pp]) : 0.f;
             }
-        uint4 pk;
-        __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&pk);
+        __nv_bfloat16* dst = out + ((long long)l * (PW + 1) + p) * CNN_C;
+#pragma unroll 1
+        for (int c = 0; c < CNN_C; c += 16) {
+            float acc[16];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            float v0 = acc[2 * k], v1 = acc[2 * k + 1];
-            const int c = cg * 8 + 2 * k;
-            if (a.scale) { v0 *= a.scale[c]; v1 *= a.scale[c + 1]; }
-            if (a.shift) { v0 += a.shift[c]; v1 += a.shift[c + 1]; }
-            h[k] = __floats2bfloat162_rn(act(v0, a.slope), act(v1, a.slope));
+            for (int k = 0; k < 16; ++k) acc[k] = 0.f;
+#pragma unroll
+            for (int t = 0; t < 9; ++t)
+#pragma unroll
+                for (int k = 0; k < 16; k += 4) {
+                    const float4 ww = *reinterpret_cast<const float4*>(sw + t * CNN_C + c + k);
+                    acc[k] = fmaf(x[t], ww.x, acc[k]);
+                    acc[k + 1] = fmaf(x[t], ww.y, acc[k + 1]);
+                    acc[k + 2] = fmaf(x[t], ww.z, acc[k + 2]);
+                    acc[k + 3] = fmaf(x[t], ww.w, acc[k + 3]);
+                }
+            uint4 pk[2];
+            __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(pk);
+#pragma unroll
+            for (int k = 0; k < 16; k += 2) {
+                const float v0 = fmaf(acc[k], s_scale[c + k], s_shift[c + k]);
+                const float v1 = fmaf(acc[k + 1], s_scale[c + k + 1], s_shift[c + k + 1]);
+                h[k >> 1] = __floats2bfloat162_rn(act(v0, a.slope), act(v1, a.slope));
+            }
+            reinterpret_cast<uint4*>(dst + c)[0] = pk[0];
+            reinterpret_cast<uint4*>(dst + c)[1] = pk[1];
         }
-        *reinterpret_cast<uint4*>(out + ((long long)l * (PW + 1) + p) * CNN_C + cg * 8) = pk;
     }
 }
 

@@ -553,19 +553,21 @@ int make_tmap_bf16_2d(CUtensorMap* map, const void* base, unsigned long long inn
 }
 
 int g_tc_dbg = 0;
-constexpr size_t kTcSmem = 3 * TC_B_BYTES + TC_STAGES * TC_A_BYTES + sizeof(pnp::TcSmem) + 1024;
 
 int cnn_forward_tc(const pnp_cnn_net* net, const float* img, float* out, int PH, int PW, void* act0, void* act1, int* stats,
                    const float* xrec, double* mse_log, const int* slot, cudaStream_t st) {
     const long long npix = (long long)PH * PW;
     const long long S = (long long)PH * (PW + 1);
-    if (S >= (1ll << 31)) return fail(PNP_ERR_ARG, "image too large");
+    if (S >= (1ll << 31) - 4096) return fail(PNP_ERR_ARG, "image too large");
     const int L = net->n_layers;
-    for (int l = 1; l < L - 1; ++l)
+    for (int l = 1; l < L; ++l) {
         if (!net->w_tc[l]) return fail(PNP_ERR_ARG, "w_tc[%d] missing: the net was not packed for the tensor-core path", l);
+        if (l < L - 1 && !(net->slope[l] <= 1.f)) return fail(PNP_ERR_UNSUPPORTED, "activation slope %g > 1 on the tensor-core path", net->slope[l]);
+    }
     static bool attr_set = false;
     if (!attr_set) {
-        CU_TRY(cudaFuncSetAttribute(pnp::k_conv_mid_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmem));
+        CU_TRY(cudaFuncSetAttribute(pnp::k_conv_tc<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pnp::tc_smem<64>()));
+        CU_TRY(cudaFuncSetAttribute(pnp::k_conv_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pnp::tc_smem<1>()));
         attr_set = true;
     }
     pnp::CnnIo io{net->mode, stats, net->range, net->shift_in};
@@ -577,24 +579,25 @@ int cnn_forward_tc(const pnp_cnn_net* net, const float* img, float* out, int PH,
     }
     __nv_bfloat16* cur = static_cast<__nv_bfloat16*>(act0);
     __nv_bfloat16* nxt = static_cast<__nv_bfloat16*>(act1);
-    pnp::k_conv_first_bf16<<<ew_blocks(npix * 8, 1), 256, 0, st>>>(img, cur, net->w[0],
+    pnp::k_conv_first_bf16<<<ew_blocks(npix, 1), 256, 0, st>>>(img, cur, net->w[0],
         pnp::CnnAct{net->scale[0], net->shift[0], net->slope[0]}, io, PH, PW);
     LAUNCH_CHECK();
     const int n_tiles = (int)((S + TC_OUT_PER_TILE - 1) / TC_OUT_PER_TILE);
     const int grid = n_tiles < g_num_sms ? n_tiles : g_num_sms;
     int rc;
+    CUtensorMap tmA, tmB;
     for (int l = 1; l < L - 1; ++l) {
-        CUtensorMap tmA, tmB;
-        if ((rc = make_tmap_bf16_2d(&tmA, cur, 64, (unsigned long long)S, 64, TC_M)) != PNP_OK) return rc;
-        if ((rc = make_tmap_bf16_2d(&tmB, net->w_tc[l], 192, 192, 64, TC_N)) != PNP_OK) return rc;
-        pnp::k_conv_mid_tc<<<grid, TC_THREADS, kTcSmem, st>>>(tmA, tmB, nxt, net->scale[l], net->shift[l], net->slope[l], PW,
-                                                            (int)S, n_tiles, g_tc_dbg);
+        if ((rc = make_tmap_bf16_2d(&tmA, cur, 64, (unsigned long long)S, 64, TC_Q_ROWS)) != PNP_OK) return rc;
+        if ((rc = make_tmap_bf16_2d(&tmB, net->w_tc[l], 192, 192, 64, 192)) != PNP_OK) return rc;
+        pnp::k_conv_tc<64><<<grid, TC_THREADS, pnp::tc_smem<64>(), st>>>(tmA, tmB, nxt, net->shift[l], net->slope[l], PW, (int)S, n_tiles,
+                                                                    pnp::TcLast{});
         LAUNCH_CHECK();
         __nv_bfloat16* t = cur; cur = nxt; nxt = t;
     }
-    long long lb = (npix + 7) / 8;
-    if (lb > 148 * 16) lb = 148 * 16;
-    pnp::k_conv_last_bf16<<<(unsigned)lb, 256, 0, st>>>(cur, img, out, net->w[L - 1], net->last_bias, io, PH, PW, xrec, mse_log, slot);
+    if ((rc = make_tmap_bf16_2d(&tmA, cur, 64, (unsigned long long)S, 64, TC_Q_ROWS)) != PNP_OK) return rc;
+    if ((rc = make_tmap_bf16_2d(&tmB, net->w_tc[L - 1], 192, 16, 64, 16)) != PNP_OK) return rc;
+    pnp::k_conv_tc<1><<<grid, TC_THREADS, pnp::tc_smem<1>(), st>>>(tmA, tmB, nullptr, nullptr, 0.f, PW, (int)S, n_tiles,
+                                                              pnp::TcLast{img, out, xrec, mse_log, slot, net->last_bias, io});
     LAUNCH_CHECK();
     return PNP_OK;
 }

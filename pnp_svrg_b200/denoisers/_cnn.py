@@ -69,8 +69,13 @@ class PackedNet:
             packed = np.ascontiguousarray(w.transpose(2, 3, 1, 0).reshape(9, ci, co), dtype=np.float32)
             net.w[i] = self._up(packed)
             if 0 < i < len(layers) - 1:
-                # tensor-core operand: rows n = (dp, co), columns k = (dl, ci), bf16
-                w2 = w.transpose(3, 0, 2, 1).reshape(3 * 64, 3 * 64)        # [dp][co][dl][ci]
+                # tensor-core operand: rows n = (dp, co), columns k = (dl, ci), bf16, BatchNorm scale folded in
+                ws = w if lay['scale'] is None else w * np.asarray(lay['scale'], dtype=np.float64)[:, None, None, None]
+                w2 = ws.transpose(3, 0, 2, 1).reshape(3 * 64, 3 * 64)       # [dp][co][dl][ci]
+            elif i == len(layers) - 1:
+                w2 = np.zeros((16, 3 * 64))                                 # rows dp, padded to a legal UMMA N
+                w2[:3] = w[0].transpose(2, 1, 0).reshape(3, 3 * 64)         # [dp][dl][ci]
+            if i > 0:
                 t = torch.from_numpy(np.ascontiguousarray(w2, dtype=np.float32)).to(self.device).to(torch.bfloat16).contiguous()
                 self.keep.append(t)
                 net.w_tc[i] = t.data_ptr()
