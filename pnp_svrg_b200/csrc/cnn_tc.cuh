@@ -47,6 +47,8 @@ namespace pnp {
 #define TC_Q_ROWS 32             // rows per TMEM lane quadrant = rows per TMA box
 #define TC_OUT_PER_Q 30          // rows 0 and 31 of every quadrant are halo
 #define TC_OUT_PER_TILE (4 * TC_OUT_PER_Q)
+#define TC_O_WARP_BYTES 2048     // output staging of one epilogue warp: 30 rows x 64 B (bf16 x 32 channels), swizzle-aligned
+#define TC_O_BYTES (8 * 2 * TC_O_WARP_BYTES)
 #define TC_THREADS 320           // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue (2 per TMEM lane quadrant)
 
 template <int CO> struct TcCfg {                       // CO = 64: middle layers, CO = 1: last layer
@@ -59,12 +61,11 @@ template <int CO> struct TcCfg {                       // CO = 64: middle layers
 struct TcSmem {
     unsigned long long full[TC_STAGES], empty[TC_STAGES], bfull, tfull[2], tempty[2];
     unsigned tmem_base;
-    __align__(16) float shift[64];   // per output channel shift (bias / folded BatchNorm; the scale is folded into the weights)
     float err[8];
 };
 
 template <int CO> constexpr size_t tc_smem() {
-    return ((3 * TcCfg<CO>::B_BYTES + 1023) & ~(size_t)1023) + TC_STAGES * TC_A_BYTES + sizeof(TcSmem) + 1024;
+    return ((3 * TcCfg<CO>::B_BYTES + 1023) & ~(size_t)1023) + TC_STAGES * TC_A_BYTES + (CO == 64 ? TC_O_BYTES : 0) + sizeof(TcSmem) + 1024;
 }
 
 __device__ __forceinline__ void mbar_wait_bounded(unsigned long long* bar, unsigned parity) {
@@ -141,17 +142,21 @@ struct TcLast {
 // quadrant (32 rows) of a tile gets its own 32 consecutive positions, overlapping its neighbours by
 // two, so that rows 0 and 31 of each quadrant are halo and the output shift never leaves a warp.
 // tmB over the packed weights [N rows (dp, co)][192 (dl, ci)] (box 64 x N), BatchNorm scale folded in.
+// tmO over `out` with box 32 x 30, 64-byte swizzle: every epilogue warp stages its 30 rows x 32 channels in
+// shared memory and stores them with one TMA tensor store (a per-lane 16-byte store to rows 128 B apart is
+// 32 LSU wavefronts per instruction, which made the LSU data pipe the bound).
 template <int CO>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-          __nv_bfloat16* __restrict__ out, const float* __restrict__ shift, float slope, int PW, int S, int n_tiles,
+          const __grid_constant__ CUtensorMap tmO, const float* __restrict__ shift, float slope, int PW, int S, int n_tiles,
           TcLast last) {
     using CF = TcCfg<CO>;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<unsigned long long>(smem_raw) + 1023ull) & ~1023ull);
     unsigned char* sB = base;                                                  // 3 K blocks
     unsigned char* sA = base + ((3 * CF::B_BYTES + 1023) & ~1023);             // TC_STAGES x 16 KiB
-    TcSmem* ctl = reinterpret_cast<TcSmem*>(sA + TC_STAGES * TC_A_BYTES);
+    unsigned char* sO = sA + TC_STAGES * TC_A_BYTES;                           // output staging, 8 warps x 2 x 2 KiB (CO = 64)
+    TcSmem* ctl = reinterpret_cast<TcSmem*>(sO + (CO == 64 ? TC_O_BYTES : 0));
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int pitch = PW + 1;
 
@@ -161,7 +166,6 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         for (int i = 0; i < 2; ++i) { mbar_init(&ctl->tfull[i], 1); mbar_init(&ctl->tempty[i], 8); }
         mbar_fence_init();
     }
-    if (threadIdx.x >= 64 && threadIdx.x < 128) ctl->shift[threadIdx.x - 64] = (CO == 64 && shift) ? shift[threadIdx.x - 64] : 0.f;
     if (threadIdx.x < 8) ctl->err[threadIdx.x] = 0.f;
     if (warp == 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&ctl->tmem_base)), "r"((unsigned)CF::TMEM_COLS));
@@ -223,26 +227,40 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         const int q = warp & 3;
         const int half = (warp - 2) >> 2;
         const bool interior = lane >= 1 && lane <= TC_OUT_PER_Q;
-        int acc = 0;
+        int acc = 0, it = 0;
         unsigned aphase = 0;
         float err = 0.f;
-        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        float sh[32];                                   // shift of this warp's 32 output channels
+#pragma unroll
+        for (int i = 0; i < 32; ++i) sh[i] = (CO == 64 && shift) ? shift[32 * half + i] : 0.f;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
             const int s = tile * TC_OUT_PER_TILE + q * TC_OUT_PER_Q + lane - 1;       // position of this lane's row
             mbar_wait_bounded(&ctl->tfull[acc], aphase);
             asm volatile("tcgen05.fence::after_thread_sync;");
             const unsigned t0 = tmem + acc * CF::ACC_COLS + ((unsigned)(q * 32) << 16);
             const bool valid = interior && s >= 0 && s < S && (s % pitch) != PW;
             if (CO == 64) {
-#pragma unroll 1
-                for (int c = 32 * half; c < 32 * half + 32; c += 16) {
-                    float tm[16], tz[16], tp[16], sh[16];
-                    tmem_ld16(t0 + c, tm);              // T_-1 of this lane's row
-                    tmem_ld16(t0 + 64 + c, tz);         // T_0
-                    tmem_ld16(t0 + 128 + c, tp);        // T_+1
+                // both 16-channel chunks of this warp's 32 channels: TMEM -> registers, then hand the accumulator back
+                float tm[2][16], tz[2][16], tp[2][16];
 #pragma unroll
-                    for (int i = 0; i < 4; ++i)
-                        *reinterpret_cast<float4*>(sh + 4 * i) = *reinterpret_cast<const float4*>(ctl->shift + c + 4 * i);
-                    asm volatile("tcgen05.wait::ld.sync.aligned;");
+                for (int j = 0; j < 2; ++j) {
+                    const int c = 32 * half + 16 * j;
+                    tmem_ld16(t0 + c, tm[j]);           // T_-1 of this lane's row
+                    tmem_ld16(t0 + 64 + c, tz[j]);      // T_0
+                    tmem_ld16(t0 + 128 + c, tp[j]);     // T_+1
+                }
+                asm volatile("tcgen05.wait::ld.sync.aligned;");
+                asm volatile("tcgen05.fence::before_thread_sync;");
+                if (lane == 0) {
+                    mbar_arrive(&ctl->tempty[acc]);                                          // 8 arrivals (one per epilogue warp)
+                    asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");           // staging buffer `it & 1` is free again
+                }
+                __syncwarp();
+                const bool keep = (s % pitch) != PW;                                         // the pad pixel of a line stays zero
+                unsigned char* stage_o = sO + ((warp - 2) * 2 + (it & 1)) * TC_O_WARP_BYTES;
+                const int r = lane - 1;
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
                     uint4 pk[2];
                     __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(pk);
 #pragma unroll
@@ -250,18 +268,26 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                         float o2[2];
 #pragma unroll
                         for (int u = 0; u < 2; ++u) {
-                            const float up = __shfl_up_sync(0xffffffffu, tm[i + u], 1);       // T_-1 of row - 1
-                            const float dn = __shfl_down_sync(0xffffffffu, tp[i + u], 1);     // T_+1 of row + 1
-                            const float v = (up + tz[i + u]) + (dn + sh[i + u]);
-                            o2[u] = fmaxf(v, v * slope);                                       // ReLU / leaky ReLU (slope <= 1)
+                            const float up = __shfl_up_sync(0xffffffffu, tm[j][i + u], 1);   // T_-1 of row - 1
+                            const float dn = __shfl_down_sync(0xffffffffu, tp[j][i + u], 1); // T_+1 of row + 1
+                            const float v = (up + tz[j][i + u]) + (dn + sh[16 * j + i + u]);
+                            o2[u] = keep ? fmaxf(v, v * slope) : 0.f;                        // ReLU / leaky ReLU (slope <= 1)
                         }
                         h[i >> 1] = __floats2bfloat162_rn(o2[0], o2[1]);
                     }
-                    if (valid) {
-                        uint4* dst = reinterpret_cast<uint4*>(out + (long long)s * 64 + c);
-                        dst[0] = pk[0];
-                        dst[1] = pk[1];
+                    if (interior) {
+                        // 64-byte rows, 16-byte chunk index XOR (row / 2) % 4  ==  CU_TENSOR_MAP_SWIZZLE_64B
+#pragma unroll
+                        for (int k = 0; k < 2; ++k)
+                            *reinterpret_cast<uint4*>(stage_o + r * 64 + (((2 * j + k) ^ ((r >> 1) & 3)) << 4)) = pk[k];
                     }
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) {
+                    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                                 ::"l"(&tmO), "r"(smem_u32(stage_o)), "r"(32 * half), "r"(s + 1) : "memory");
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                 }
             } else if (half == 0) {
                 // last layer: one output per position + the wrapper's output map
@@ -287,10 +313,13 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                     if (last.xrec) { const float df = res - last.xrec[pix]; err = fmaf(df, df, err); }
                 }
             }
-            asm volatile("tcgen05.fence::before_thread_sync;");
-            if (lane == 0) mbar_arrive(&ctl->tempty[acc]);                 // 8 arrivals (one per epilogue warp)
+            if (CO != 64) {
+                asm volatile("tcgen05.fence::before_thread_sync;");
+                if (lane == 0) mbar_arrive(&ctl->tempty[acc]);             // 8 arrivals (one per epilogue warp)
+            }
             if (++acc == 2) { acc = 0; aphase ^= 1; }
         }
+        if (CO == 64 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
         if (CO == 1 && last.xrec && last.mse_log) {
             err = warp_sum_f(err);
             if (lane == 0) ctl->err[warp - 2] = err;

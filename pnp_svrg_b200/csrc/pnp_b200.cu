@@ -532,7 +532,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 int make_tmap_bf16_2d(CUtensorMap* map, const void* base, unsigned long long inner, unsigned long long outer,
-                      unsigned box_inner, unsigned box_outer) {
+                      unsigned box_inner, unsigned box_outer, CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B) {
     static EncodeTiledFn fn = nullptr;
     if (!fn) {
         void* p = nullptr;
@@ -546,7 +546,7 @@ int make_tmap_bf16_2d(CUtensorMap* map, const void* base, unsigned long long inn
     const cuuint32_t box[2] = {box_inner, box_outer};
     const cuuint32_t estr[2] = {1, 1};
     const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
-                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(PNP_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
     return PNP_OK;
@@ -585,18 +585,19 @@ int cnn_forward_tc(const pnp_cnn_net* net, const float* img, float* out, int PH,
     const int n_tiles = (int)((S + TC_OUT_PER_TILE - 1) / TC_OUT_PER_TILE);
     const int grid = n_tiles < g_num_sms ? n_tiles : g_num_sms;
     int rc;
-    CUtensorMap tmA, tmB;
+    CUtensorMap tmA, tmB, tmO;
     for (int l = 1; l < L - 1; ++l) {
         if ((rc = make_tmap_bf16_2d(&tmA, cur, 64, (unsigned long long)S, 64, TC_Q_ROWS)) != PNP_OK) return rc;
         if ((rc = make_tmap_bf16_2d(&tmB, net->w_tc[l], 192, 192, 64, 192)) != PNP_OK) return rc;
-        pnp::k_conv_tc<64><<<grid, TC_THREADS, pnp::tc_smem<64>(), st>>>(tmA, tmB, nxt, net->shift[l], net->slope[l], PW, (int)S, n_tiles,
-                                                                    pnp::TcLast{});
+        if ((rc = make_tmap_bf16_2d(&tmO, nxt, 64, (unsigned long long)S, 32, TC_OUT_PER_Q, CU_TENSOR_MAP_SWIZZLE_64B)) != PNP_OK) return rc;
+        pnp::k_conv_tc<64><<<grid, TC_THREADS, pnp::tc_smem<64>(), st>>>(tmA, tmB, tmO, net->shift[l], net->slope[l], PW, (int)S, n_tiles,
+                                                                         pnp::TcLast{});
         LAUNCH_CHECK();
         __nv_bfloat16* t = cur; cur = nxt; nxt = t;
     }
     if ((rc = make_tmap_bf16_2d(&tmA, cur, 64, (unsigned long long)S, 64, TC_Q_ROWS)) != PNP_OK) return rc;
     if ((rc = make_tmap_bf16_2d(&tmB, net->w_tc[L - 1], 192, 16, 64, 16)) != PNP_OK) return rc;
-    pnp::k_conv_tc<1><<<grid, TC_THREADS, pnp::tc_smem<1>(), st>>>(tmA, tmB, nullptr, nullptr, 0.f, PW, (int)S, n_tiles,
+    pnp::k_conv_tc<1><<<grid, TC_THREADS, pnp::tc_smem<1>(), st>>>(tmA, tmB, tmA, nullptr, 0.f, PW, (int)S, n_tiles,
                                                               pnp::TcLast{img, out, xrec, mse_log, slot, net->last_bias, io});
     LAUNCH_CHECK();
     return PNP_OK;
