@@ -43,7 +43,7 @@ namespace pnp {
 #define TC_M 128
 #define TC_KBLK 64               // one dl: 64 input channels = 128 bytes per row (one swizzle span)
 #define TC_A_BYTES (TC_M * 128)  // 16 KiB
-#define TC_STAGES 4
+#define TC_STAGES 6               // two groups of three (one per dl)
 #define TC_Q_ROWS 32             // rows per TMEM lane quadrant = rows per TMA box
 #define TC_OUT_PER_Q 30          // rows 0 and 31 of every quadrant are halo
 #define TC_OUT_PER_TILE (4 * TC_OUT_PER_Q)
@@ -78,6 +78,15 @@ __device__ __forceinline__ void mbar_wait_bounded(unsigned long long* bar, unsig
             : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
         if (spin > (1u << 26)) __trap();          // a protocol bug must fail loudly, not hang the GPU
     }
+}
+__device__ __forceinline__ bool elect_one() {
+    unsigned pred;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
 }
 __device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -176,50 +185,73 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     asm volatile("tcgen05.fence::after_thread_sync;");
     const unsigned tmem = ctl->tmem_base;
 
+    // Pipeline indexing: tile iteration `it` of this CTA uses accumulator g = it & 1 and the three smem stages
+    // 3g .. 3g+2 (one per dl); every barrier of group g is used once per two tiles, so all share the phase
+    // (it >> 1) & 1.  The loops below are unrolled over g to keep stage indices and descriptors static, and run
+    // by the WHOLE warp with one elected lane issuing, so that addresses and descriptors stay in uniform registers.
     if (warp == 0) {
         // ===== TMA producer =====
-        if (lane == 0) {
+        if (elect_one()) {
             mbar_expect_tx(&ctl->bfull, 3 * CF::B_BYTES);
             for (int kb = 0; kb < 3; ++kb) tma_load_2d(sB + kb * CF::B_BYTES, &tmB, kb * TC_KBLK, 0, &ctl->bfull);
-            int stage = 0;
-            unsigned phase = 0;
-            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-                const int s0 = tile * TC_OUT_PER_TILE - 1;
-                for (int dl = -1; dl <= 1; ++dl) {
-                    mbar_wait_bounded(&ctl->empty[stage], phase ^ 1);
-                    mbar_expect_tx(&ctl->full[stage], TC_A_BYTES);
+        }
+        __syncwarp();
+        unsigned ph = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; ph ^= 1) {
 #pragma unroll
-                    for (int q = 0; q < 4; ++q)
-                        tma_load_2d(sA + stage * TC_A_BYTES + q * (TC_Q_ROWS * 128), &tmA, 0, s0 + q * TC_OUT_PER_Q + dl * pitch,
-                                    &ctl->full[stage]);
-                    if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+            for (int g = 0; g < 2; ++g) {
+                if (tile < n_tiles) {
+                    const int s0 = tile * TC_OUT_PER_TILE - 1;
+#pragma unroll
+                    for (int kb = 0; kb < 3; ++kb) {
+                        const int stage = 3 * g + kb;
+                        mbar_wait_bounded(&ctl->empty[stage], ph ^ 1);
+                        if (elect_one()) {
+                            mbar_expect_tx(&ctl->full[stage], TC_A_BYTES);
+#pragma unroll
+                            for (int q = 0; q < 4; ++q)
+                                tma_load_2d(sA + stage * TC_A_BYTES + q * (TC_Q_ROWS * 128), &tmA, 0,
+                                            s0 + q * TC_OUT_PER_Q + (kb - 1) * pitch, &ctl->full[stage]);
+                        }
+                        __syncwarp();
+                    }
                 }
+                tile += gridDim.x;
             }
         }
     } else if (warp == 1) {
-        // ===== MMA issuer (one thread) =====
-        if (lane == 0) {
-            const unsigned idesc = umma_idesc_bf16(TC_M, CF::N);
-            mbar_wait_bounded(&ctl->bfull, 0);
-            int stage = 0, acc = 0;
-            unsigned phase = 0, aphase = 0;
-            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-                mbar_wait_bounded(&ctl->tempty[acc], aphase ^ 1);          // epilogue has drained this accumulator
-                asm volatile("tcgen05.fence::after_thread_sync;");
-                const unsigned d = tmem + acc * CF::ACC_COLS;
-                for (int kb = 0; kb < 3; ++kb) {
-                    mbar_wait_bounded(&ctl->full[stage], phase);
-                    asm volatile("tcgen05.fence::after_thread_sync;");
-                    const unsigned long long da = umma_desc_sw128(sA + stage * TC_A_BYTES);
-                    const unsigned long long db = umma_desc_sw128(sB + kb * CF::B_BYTES);
+        // ===== MMA issuer =====
+        const unsigned idesc = umma_idesc_bf16(TC_M, CF::N);
+        unsigned long long da[TC_STAGES], db[3];
 #pragma unroll
-                    for (int k = 0; k < TC_KBLK / 16; ++k)                 // 32 bytes (= 2 x 16 B units) per K step
-                        umma_f16(d, da + 2 * k, db + 2 * k, idesc, (kb | k) ? 1u : 0u);
-                    umma_commit(&ctl->empty[stage]);                       // smem slot free when these MMAs retire
-                    if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+        for (int i = 0; i < TC_STAGES; ++i) da[i] = umma_desc_sw128(sA + i * TC_A_BYTES);
+#pragma unroll
+        for (int kb = 0; kb < 3; ++kb) db[kb] = umma_desc_sw128(sB + kb * CF::B_BYTES);
+        mbar_wait_bounded(&ctl->bfull, 0);
+        unsigned ph = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; ph ^= 1) {
+#pragma unroll
+            for (int g = 0; g < 2; ++g) {
+                if (tile < n_tiles) {
+                    mbar_wait_bounded(&ctl->tempty[g], ph ^ 1);            // epilogue has drained this accumulator
+                    asm volatile("tcgen05.fence::after_thread_sync;");
+                    const unsigned d = tmem + g * CF::ACC_COLS;
+#pragma unroll
+                    for (int kb = 0; kb < 3; ++kb) {
+                        const int stage = 3 * g + kb;
+                        mbar_wait_bounded(&ctl->full[stage], ph);
+                        asm volatile("tcgen05.fence::after_thread_sync;");
+                        if (elect_one()) {
+#pragma unroll
+                            for (int k = 0; k < TC_KBLK / 16; ++k)         // 32 bytes (= 2 x 16 B units) per K step
+                                umma_f16(d, da[stage] + 2 * k, db[kb] + 2 * k, idesc, (kb | k) ? 1u : 0u);
+                            umma_commit(&ctl->empty[stage]);               // smem slot free when these MMAs retire
+                            if (kb == 2) umma_commit(&ctl->tfull[g]);      // accumulator ready for the epilogue
+                        }
+                        __syncwarp();
+                    }
                 }
-                umma_commit(&ctl->tfull[acc]);                             // accumulator ready for the epilogue
-                if (++acc == 2) { acc = 0; aphase ^= 1; }
+                tile += gridDim.x;
             }
         }
     } else {
