@@ -29,8 +29,8 @@
 // epilogue sums the three shifted columns and applies the denoiser's output map
 // (denoisers/RealSN_DnCNN.py:29-39, denoisers/MMODenoise.py:57-66).
 //
-// Warp roles (320 threads, one persistent CTA per SM): warp 0 TMA producer, warp 1 MMA issuer + TMEM
-// allocator, warps 2-9 epilogue (TMEM lane quadrant = warp_id % 4, two warps per quadrant split the channels).
+// Warp roles (576 threads, one persistent CTA per SM): warp 0 TMA producer, warp 1 MMA issuer + TMEM
+// allocator, warps 2-17 epilogue in two ping-pong groups of eight (TMEM lane quadrant = warp_id % 4).
 #pragma once
 #include <cuda.h>
 #include <cuda_bf16.h>
@@ -47,9 +47,10 @@ namespace pnp {
 #define TC_Q_ROWS 32             // rows per TMEM lane quadrant = rows per TMA box
 #define TC_OUT_PER_Q 30          // rows 0 and 31 of every quadrant are halo
 #define TC_OUT_PER_TILE (4 * TC_OUT_PER_Q)
-#define TC_O_WARP_BYTES 2048     // output staging of one epilogue warp: 30 rows x 64 B (bf16 x 32 channels), swizzle-aligned
-#define TC_O_BYTES (8 * 2 * TC_O_WARP_BYTES)
-#define TC_THREADS 320           // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue (2 per TMEM lane quadrant)
+#define TC_EPI_WARPS 16          // 4 per TMEM lane quadrant, 16 output channels each
+#define TC_O_WARP_BYTES 1024     // output staging of one 16-channel chunk: 30 rows x 32 B, swizzle-aligned
+#define TC_O_BYTES (TC_EPI_WARPS * 2 * TC_O_WARP_BYTES)
+#define TC_THREADS (64 + 32 * TC_EPI_WARPS)   // warp 0 TMA, warp 1 MMA, warps 2-17 epilogue
 
 template <int CO> struct TcCfg {                       // CO = 64: middle layers, CO = 1: last layer
     static constexpr int N = CO == 64 ? 192 : 16;      // (dp, co) columns, padded to a legal UMMA N
@@ -61,7 +62,8 @@ template <int CO> struct TcCfg {                       // CO = 64: middle layers
 struct TcSmem {
     unsigned long long full[TC_STAGES], empty[TC_STAGES], bfull, tfull[2], tempty[2];
     unsigned tmem_base;
-    float err[8];
+    float err[TC_EPI_WARPS];
+    __align__(16) float shift[64];   // per output channel shift (bias / folded BatchNorm; the scale is folded into the weights)
 };
 
 template <int CO> constexpr size_t tc_smem() {
@@ -151,20 +153,20 @@ struct TcLast {
 // quadrant (32 rows) of a tile gets its own 32 consecutive positions, overlapping its neighbours by
 // two, so that rows 0 and 31 of each quadrant are halo and the output shift never leaves a warp.
 // tmB over the packed weights [N rows (dp, co)][192 (dl, ci)] (box 64 x N), BatchNorm scale folded in.
-// tmO over `out` with box 32 x 30, 64-byte swizzle: every epilogue warp stages its 30 rows x 32 channels in
-// shared memory and stores them with one TMA tensor store (a per-lane 16-byte store to rows 128 B apart is
-// 32 LSU wavefronts per instruction, which made the LSU data pipe the bound).
+// tmO over `out` with box 16 x 30, 32-byte swizzle: every epilogue warp stages 30 rows x 16 channels in shared
+// memory and stores them with one TMA tensor store (a per-lane 16-byte store to rows 128 B apart is 32 LSU
+// wavefronts per instruction, which made the LSU data pipe the bound; staging + coalesced st.global was slower).
 template <int CO>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
           const __grid_constant__ CUtensorMap tmO, const float* __restrict__ shift, float slope, int PW, int S, int n_tiles,
-          TcLast last) {
+          TcLast last, int dbg) {
     using CF = TcCfg<CO>;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<unsigned long long>(smem_raw) + 1023ull) & ~1023ull);
     unsigned char* sB = base;                                                  // 3 K blocks
     unsigned char* sA = base + ((3 * CF::B_BYTES + 1023) & ~1023);             // TC_STAGES x 16 KiB
-    unsigned char* sO = sA + TC_STAGES * TC_A_BYTES;                           // output staging, 8 warps x 2 x 2 KiB (CO = 64)
+    unsigned char* sO = sA + TC_STAGES * TC_A_BYTES;                           // output staging, 4 quadrants x 2 x 4 KiB (CO = 64)
     TcSmem* ctl = reinterpret_cast<TcSmem*>(sO + (CO == 64 ? TC_O_BYTES : 0));
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int pitch = PW + 1;
@@ -172,10 +174,11 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     if (threadIdx.x == 0) {
         for (int i = 0; i < TC_STAGES; ++i) { mbar_init(&ctl->full[i], 1); mbar_init(&ctl->empty[i], 1); }
         mbar_init(&ctl->bfull, 1);
-        for (int i = 0; i < 2; ++i) { mbar_init(&ctl->tfull[i], 1); mbar_init(&ctl->tempty[i], 8); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&ctl->tfull[i], 1); mbar_init(&ctl->tempty[i], TC_EPI_WARPS / 2); }
         mbar_fence_init();
     }
-    if (threadIdx.x < 8) ctl->err[threadIdx.x] = 0.f;
+    if (threadIdx.x < TC_EPI_WARPS) ctl->err[threadIdx.x] = 0.f;
+    if (threadIdx.x >= 64 && threadIdx.x < 128) ctl->shift[threadIdx.x - 64] = (CO == 64 && shift) ? shift[threadIdx.x - 64] : 0.f;
     if (warp == 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&ctl->tmem_base)), "r"((unsigned)CF::TMEM_COLS));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
@@ -207,10 +210,10 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                         const int stage = 3 * g + kb;
                         mbar_wait_bounded(&ctl->empty[stage], ph ^ 1);
                         if (elect_one()) {
-                            mbar_expect_tx(&ctl->full[stage], TC_A_BYTES);
+                            mbar_expect_tx(&ctl->full[stage], (kb == 0 || !(dbg & 4)) ? TC_A_BYTES : 0);
 #pragma unroll
                             for (int q = 0; q < 4; ++q)
-                                tma_load_2d(sA + stage * TC_A_BYTES + q * (TC_Q_ROWS * 128), &tmA, 0,
+                                if (kb == 0 || !(dbg & 4)) tma_load_2d(sA + stage * TC_A_BYTES + q * (TC_Q_ROWS * 128), &tmA, 0,
                                             s0 + q * TC_OUT_PER_Q + (kb - 1) * pitch, &ctl->full[stage]);
                         }
                         __syncwarp();
@@ -255,44 +258,42 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             }
         }
     } else {
-        // ===== epilogue warps 2..9: TMEM lane quadrant q = warp % 4, second index = (warp - 2) / 4 =====
+        // ===== epilogue warps 2..17 =====
+        // Two groups of eight warps ping-pong over the tiles: group wg owns accumulator wg and takes the tiles with
+        // it % 2 == wg, so its TMEM loads overlap the other group's arithmetic and a tile's epilogue may take up to
+        // two MMA periods.  Inside a group: TMEM lane quadrant q = warp % 4 (a hardware rule), channel half hf.
+        const int ew = warp - 2;
+        const int wg = ew >> 3;
         const int q = warp & 3;
-        const int half = (warp - 2) >> 2;
+        const int hf = (ew >> 2) & 1;
         const bool interior = lane >= 1 && lane <= TC_OUT_PER_Q;
-        int acc = 0, it = 0;
+        const bool relu = slope == 0.f;
         unsigned aphase = 0;
         float err = 0.f;
-        float sh[32];                                   // shift of this warp's 32 output channels
-#pragma unroll
-        for (int i = 0; i < 32; ++i) sh[i] = (CO == 64 && shift) ? shift[32 * half + i] : 0.f;
-        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+        const unsigned t0 = tmem + wg * CF::ACC_COLS + ((unsigned)(q * 32) << 16);
+        for (int tile = blockIdx.x + wg * gridDim.x; tile < n_tiles; tile += 2 * gridDim.x, aphase ^= 1) {
             const int s = tile * TC_OUT_PER_TILE + q * TC_OUT_PER_Q + lane - 1;       // position of this lane's row
-            mbar_wait_bounded(&ctl->tfull[acc], aphase);
+            mbar_wait_bounded(&ctl->tfull[wg], aphase);
             asm volatile("tcgen05.fence::after_thread_sync;");
-            const unsigned t0 = tmem + acc * CF::ACC_COLS + ((unsigned)(q * 32) << 16);
-            const bool valid = interior && s >= 0 && s < S && (s % pitch) != PW;
             if (CO == 64) {
-                // both 16-channel chunks of this warp's 32 channels: TMEM -> registers, then hand the accumulator back
-                float tm[2][16], tz[2][16], tp[2][16];
+                const bool pad = (s % pitch) == PW;                                   // the pad pixel of a line stays zero
 #pragma unroll
-                for (int j = 0; j < 2; ++j) {
-                    const int c = 32 * half + 16 * j;
-                    tmem_ld16(t0 + c, tm[j]);           // T_-1 of this lane's row
-                    tmem_ld16(t0 + 64 + c, tz[j]);      // T_0
-                    tmem_ld16(t0 + 128 + c, tp[j]);     // T_+1
-                }
-                asm volatile("tcgen05.wait::ld.sync.aligned;");
-                asm volatile("tcgen05.fence::before_thread_sync;");
-                if (lane == 0) {
-                    mbar_arrive(&ctl->tempty[acc]);                                          // 8 arrivals (one per epilogue warp)
-                    asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");           // staging buffer `it & 1` is free again
-                }
-                __syncwarp();
-                const bool keep = (s % pitch) != PW;                                         // the pad pixel of a line stays zero
-                unsigned char* stage_o = sO + ((warp - 2) * 2 + (it & 1)) * TC_O_WARP_BYTES;
-                const int r = lane - 1;
+                for (int j = 0; j < 2; ++j) {                                         // two chunks of 16 channels
+                    const int c = 32 * hf + 16 * j;
+                    float tm[16], tz[16], tp[16], sh[16];
+                    tmem_ld16(t0 + c, tm);              // T_-1 of this lane's row
+                    tmem_ld16(t0 + 64 + c, tz);         // T_0
+                    tmem_ld16(t0 + 128 + c, tp);        // T_+1
 #pragma unroll
-                for (int j = 0; j < 2; ++j) {
+                    for (int i = 0; i < 4; ++i) reinterpret_cast<float4*>(sh)[i] = reinterpret_cast<const float4*>(ctl->shift + c)[i];
+                    asm volatile("tcgen05.wait::ld.sync.aligned;");
+                    if (j == 1) {                                                     // accumulator read: hand it back before the math
+                        asm volatile("tcgen05.fence::before_thread_sync;");
+                        if (lane == 0) mbar_arrive(&ctl->tempty[wg]);
+                    }
+                    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // staging buffer j is free again
+                    __syncwarp();
+                    if (dbg & 2) continue;
                     uint4 pk[2];
                     __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(pk);
 #pragma unroll
@@ -300,68 +301,69 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                         float o2[2];
 #pragma unroll
                         for (int u = 0; u < 2; ++u) {
-                            const float up = __shfl_up_sync(0xffffffffu, tm[j][i + u], 1);   // T_-1 of row - 1
-                            const float dn = __shfl_down_sync(0xffffffffu, tp[j][i + u], 1); // T_+1 of row + 1
-                            const float v = (up + tz[j][i + u]) + (dn + sh[16 * j + i + u]);
-                            o2[u] = keep ? fmaxf(v, v * slope) : 0.f;                        // ReLU / leaky ReLU (slope <= 1)
+                            const float up = __shfl_up_sync(0xffffffffu, tm[i + u], 1);      // T_-1 of row - 1
+                            const float dn = __shfl_down_sync(0xffffffffu, tp[i + u], 1);    // T_+1 of row + 1
+                            const float v = (up + tz[i + u]) + (dn + sh[i + u]);
+                            o2[u] = relu ? fmaxf(v, 0.f) : fmaxf(v, v * slope);              // leaky ReLU needs slope <= 1
                         }
                         h[i >> 1] = __floats2bfloat162_rn(o2[0], o2[1]);
                     }
+                    if (pad) pk[0] = pk[1] = make_uint4(0u, 0u, 0u, 0u);
+                    // 30 rows x 32 B per chunk; 16-byte chunk index XOR (row / 4) % 2  ==  CU_TENSOR_MAP_SWIZZLE_32B
+                    unsigned char* stage_o = sO + (ew * 2 + j) * TC_O_WARP_BYTES;
                     if (interior) {
-                        // 64-byte rows, 16-byte chunk index XOR (row / 2) % 4  ==  CU_TENSOR_MAP_SWIZZLE_64B
+                        const int r = lane - 1;
 #pragma unroll
-                        for (int k = 0; k < 2; ++k)
-                            *reinterpret_cast<uint4*>(stage_o + r * 64 + (((2 * j + k) ^ ((r >> 1) & 3)) << 4)) = pk[k];
+                        for (int k = 0; k < 2; ++k) *reinterpret_cast<uint4*>(stage_o + r * 32 + ((k ^ ((r >> 2) & 1)) << 4)) = pk[k];
+                    }
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) {
+                        asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                                     ::"l"(&tmO), "r"(smem_u32(stage_o)), "r"(c), "r"(s + 1) : "memory");
+                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                     }
                 }
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                __syncwarp();
-                if (lane == 0) {
-                    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
-                                 ::"l"(&tmO), "r"(smem_u32(stage_o)), "r"(32 * half), "r"(s + 1) : "memory");
-                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-                }
-            } else if (half == 0) {
+            } else {
                 // last layer: one output per position + the wrapper's output map
                 float t[4];
-                tmem_ld4(t0, t);
+                if (hf == 0) tmem_ld4(t0, t);
                 asm volatile("tcgen05.wait::ld.sync.aligned;");
-                const float up = __shfl_up_sync(0xffffffffu, t[0], 1);
-                const float dn = __shfl_down_sync(0xffffffffu, t[2], 1);
-                const float conv = up + t[1] + dn;
-                if (valid) {
-                    const int l = s / pitch, p = s - l * pitch;
-                    const long long pix = (long long)l * PW + p;
-                    const float x = last.img[pix];
-                    float res;
-                    if (last.io.mode == 0) {
-                        const float mn = ord2f(last.io.stats[0]), mx = ord2f(last.io.stats[1]);
-                        const float xt = (x - mn) / (mx - mn) * last.io.range + last.io.shift;
-                        res = ((xt - conv) - last.io.shift) / last.io.range * (mx - mn) + mn;
-                    } else {
-                        res = fminf(fmaxf(conv + last.bias + fminf(fmaxf(x, 0.f), 1.f), 0.f), 1.f);
+                asm volatile("tcgen05.fence::before_thread_sync;");
+                if (lane == 0) mbar_arrive(&ctl->tempty[wg]);
+                if (hf == 0) {
+                    const float up = __shfl_up_sync(0xffffffffu, t[0], 1);
+                    const float dn = __shfl_down_sync(0xffffffffu, t[2], 1);
+                    const float conv = up + t[1] + dn;
+                    if (interior && s < S && (s % pitch) != PW) {
+                        const int l = s / pitch, p = s - l * pitch;
+                        const long long pix = (long long)l * PW + p;
+                        const float x = last.img[pix];
+                        float res;
+                        if (last.io.mode == 0) {
+                            const float mn = ord2f(last.io.stats[0]), mx = ord2f(last.io.stats[1]);
+                            const float xt = (x - mn) / (mx - mn) * last.io.range + last.io.shift;
+                            res = ((xt - conv) - last.io.shift) / last.io.range * (mx - mn) + mn;
+                        } else {
+                            res = fminf(fmaxf(conv + last.bias + fminf(fmaxf(x, 0.f), 1.f), 0.f), 1.f);
+                        }
+                        last.out[pix] = res;
+                        if (last.xrec) { const float df = res - last.xrec[pix]; err = fmaf(df, df, err); }
                     }
-                    last.out[pix] = res;
-                    if (last.xrec) { const float df = res - last.xrec[pix]; err = fmaf(df, df, err); }
                 }
             }
-            if (CO != 64) {
-                asm volatile("tcgen05.fence::before_thread_sync;");
-                if (lane == 0) mbar_arrive(&ctl->tempty[acc]);             // 8 arrivals (one per epilogue warp)
-            }
-            if (++acc == 2) { acc = 0; aphase ^= 1; }
         }
         if (CO == 64 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
         if (CO == 1 && last.xrec && last.mse_log) {
             err = warp_sum_f(err);
-            if (lane == 0) ctl->err[warp - 2] = err;
+            if (lane == 0) ctl->err[ew] = err;
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;");
     __syncthreads();
     if (CO == 1 && last.xrec && last.mse_log && threadIdx.x == 0) {
         float t = 0.f;
-        for (int k = 0; k < 8; ++k) t += ctl->err[k];
+        for (int k = 0; k < TC_EPI_WARPS; ++k) t += ctl->err[k];
         atomicAdd(last.mse_log + (last.slot ? *last.slot : 0), (double)t);
     }
     if (warp == 1) {

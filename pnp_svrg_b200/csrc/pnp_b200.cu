@@ -589,16 +589,16 @@ int cnn_forward_tc(const pnp_cnn_net* net, const float* img, float* out, int PH,
     for (int l = 1; l < L - 1; ++l) {
         if ((rc = make_tmap_bf16_2d(&tmA, cur, 64, (unsigned long long)S, 64, TC_Q_ROWS)) != PNP_OK) return rc;
         if ((rc = make_tmap_bf16_2d(&tmB, net->w_tc[l], 192, 192, 64, 192)) != PNP_OK) return rc;
-        if ((rc = make_tmap_bf16_2d(&tmO, nxt, 64, (unsigned long long)S, 32, TC_OUT_PER_Q, CU_TENSOR_MAP_SWIZZLE_64B)) != PNP_OK) return rc;
+        if ((rc = make_tmap_bf16_2d(&tmO, nxt, 64, (unsigned long long)S, 16, TC_OUT_PER_Q, CU_TENSOR_MAP_SWIZZLE_32B)) != PNP_OK) return rc;
         pnp::k_conv_tc<64><<<grid, TC_THREADS, pnp::tc_smem<64>(), st>>>(tmA, tmB, tmO, net->shift[l], net->slope[l], PW, (int)S, n_tiles,
-                                                                         pnp::TcLast{});
+                                                                         pnp::TcLast{}, g_tc_dbg);
         LAUNCH_CHECK();
         __nv_bfloat16* t = cur; cur = nxt; nxt = t;
     }
     if ((rc = make_tmap_bf16_2d(&tmA, cur, 64, (unsigned long long)S, 64, TC_Q_ROWS)) != PNP_OK) return rc;
     if ((rc = make_tmap_bf16_2d(&tmB, net->w_tc[L - 1], 192, 16, 64, 16)) != PNP_OK) return rc;
     pnp::k_conv_tc<1><<<grid, TC_THREADS, pnp::tc_smem<1>(), st>>>(tmA, tmB, tmA, nullptr, 0.f, PW, (int)S, n_tiles,
-                                                              pnp::TcLast{img, out, xrec, mse_log, slot, net->last_bias, io});
+                                                              pnp::TcLast{img, out, xrec, mse_log, slot, net->last_bias, io}, 0);
     LAUNCH_CHECK();
     return PNP_OK;
 }

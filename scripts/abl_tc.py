@@ -11,7 +11,7 @@ sd = _random_dncnn_sd(17, True, False, seed=1)
 H = 2048
 z = D.to_lines(synth_image(H, H, 0).astype(np.float64) / 255, H, H, dev); o = torch.empty_like(z)
 den = RealSN_DnCNNDenoiser('DnCNN', 15, state_dict=sd, precision='bf16'); ctx = ProxCtx(z, o, H, H)
-for dbg in (0, 1, 4):
+for dbg in (0, 2, 0, 2):
     _lib.load().pnp_debug_set(1, dbg)
     for _ in range(2): den._dev_denoise(ctx)
     torch.cuda.synchronize()
