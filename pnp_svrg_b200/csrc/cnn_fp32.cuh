@@ -112,9 +112,10 @@ k_conv_mid(const float* __restrict__ in, float* __restrict__ out, const float* _
     __shared__ __align__(16) float s_w[9][CM_CK][CNN_C];
     const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
     const int l0 = blockIdx.y * CM_TL, p0 = blockIdx.x * CM_TP;
-    float acc0[CNN_C], acc1[CNN_C];
+    // accumulators as channel pairs: fma.rn.f32x2 issues two FMAs per slot (each half rounds like fmaf)
+    float2 acc0[CNN_C / 2], acc1[CNN_C / 2];
 #pragma unroll
-    for (int c = 0; c < CNN_C; ++c) { acc0[c] = 0.f; acc1[c] = 0.f; }
+    for (int c = 0; c < CNN_C / 2; ++c) { acc0[c] = make_float2(0.f, 0.f); acc1[c] = make_float2(0.f, 0.f); }
     for (int c0 = 0; c0 < CNN_C; c0 += CM_CK) {
         __syncthreads();
         // input tile with halo: 8 channels = 32 contiguous bytes per pixel
@@ -144,14 +145,14 @@ k_conv_mid(const float* __restrict__ in, float* __restrict__ out, const float* _
             for (int ci = 0; ci < CM_CK; ++ci) {
                 const float x0 = s_in[ci][ty + dl][2 * tx + dp];
                 const float x1 = s_in[ci][ty + dl][2 * tx + 1 + dp];
+                const float2 xx0 = make_float2(x0, x0), xx1 = make_float2(x1, x1);
                 const float4* wv = reinterpret_cast<const float4*>(&s_w[tap][ci][0]);
 #pragma unroll
                 for (int q = 0; q < CNN_C / 4; ++q) {
                     const float4 ww = wv[q];
-                    acc0[4 * q + 0] = fmaf(x0, ww.x, acc0[4 * q + 0]); acc1[4 * q + 0] = fmaf(x1, ww.x, acc1[4 * q + 0]);
-                    acc0[4 * q + 1] = fmaf(x0, ww.y, acc0[4 * q + 1]); acc1[4 * q + 1] = fmaf(x1, ww.y, acc1[4 * q + 1]);
-                    acc0[4 * q + 2] = fmaf(x0, ww.z, acc0[4 * q + 2]); acc1[4 * q + 2] = fmaf(x1, ww.z, acc1[4 * q + 2]);
-                    acc0[4 * q + 3] = fmaf(x0, ww.w, acc0[4 * q + 3]); acc1[4 * q + 3] = fmaf(x1, ww.w, acc1[4 * q + 3]);
+                    const float2 wlo = make_float2(ww.x, ww.y), whi = make_float2(ww.z, ww.w);
+                    acc0[2 * q + 0] = __ffma2_rn(xx0, wlo, acc0[2 * q + 0]); acc1[2 * q + 0] = __ffma2_rn(xx1, wlo, acc1[2 * q + 0]);
+                    acc0[2 * q + 1] = __ffma2_rn(xx0, whi, acc0[2 * q + 1]); acc1[2 * q + 1] = __ffma2_rn(xx1, whi, acc1[2 * q + 1]);
                 }
             }
         }
@@ -169,7 +170,8 @@ k_conv_mid(const float* __restrict__ in, float* __restrict__ out, const float* _
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 const int c = 4 * q + k;
-                float t = px == 0 ? acc0[c] : acc1[c];
+                const float2 pr = px == 0 ? acc0[c >> 1] : acc1[c >> 1];
+                float t = (c & 1) ? pr.y : pr.x;
                 if (a.scale) t *= a.scale[c];
                 if (a.shift) t += a.shift[c];
                 v[k] = act(t, a.slope);

@@ -372,7 +372,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     }
 }
 
-// ---- thin first / last layers for the bf16 path (CUDA cores; padded bf16 NHWC activations) ----
+// ---- thin first layer for the bf16 path (CUDA cores; writes padded bf16 NHWC activations) ----
 // first layer (1 -> 64): one thread per pixel, 16 channels at a time (576 FMAs per pixel, the nine inputs
 // transformed once), 32-byte sector stores
 __global__ void __launch_bounds__(256)
@@ -401,80 +401,29 @@ k_conv_first_bf16(const float* __restrict__ img, __nv_bfloat16* __restrict__ out
         __nv_bfloat16* dst = out + ((long long)l * (PW + 1) + p) * CNN_C;
 #pragma unroll 1
         for (int c = 0; c < CNN_C; c += 16) {
-            float acc[16];
+            float2 acc[8];                                  // channel pairs: fma.rn.f32x2, two FMAs per issue slot
 #pragma unroll
-            for (int k = 0; k < 16; ++k) acc[k] = 0.f;
+            for (int k = 0; k < 8; ++k) acc[k] = make_float2(0.f, 0.f);
 #pragma unroll
-            for (int t = 0; t < 9; ++t)
+            for (int t = 0; t < 9; ++t) {
+                const float2 xx = make_float2(x[t], x[t]);
 #pragma unroll
                 for (int k = 0; k < 16; k += 4) {
                     const float4 ww = *reinterpret_cast<const float4*>(sw + t * CNN_C + c + k);
-                    acc[k] = fmaf(x[t], ww.x, acc[k]);
-                    acc[k + 1] = fmaf(x[t], ww.y, acc[k + 1]);
-                    acc[k + 2] = fmaf(x[t], ww.z, acc[k + 2]);
-                    acc[k + 3] = fmaf(x[t], ww.w, acc[k + 3]);
+                    acc[k >> 1] = __ffma2_rn(xx, make_float2(ww.x, ww.y), acc[k >> 1]);
+                    acc[(k >> 1) + 1] = __ffma2_rn(xx, make_float2(ww.z, ww.w), acc[(k >> 1) + 1]);
                 }
+            }
             uint4 pk[2];
             __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(pk);
 #pragma unroll
             for (int k = 0; k < 16; k += 2) {
-                const float v0 = fmaf(acc[k], s_scale[c + k], s_shift[c + k]);
-                const float v1 = fmaf(acc[k + 1], s_scale[c + k + 1], s_shift[c + k + 1]);
-                h[k >> 1] = __floats2bfloat162_rn(act(v0, a.slope), act(v1, a.slope));
+                const float2 sc = *reinterpret_cast<const float2*>(s_scale + c + k), sf = *reinterpret_cast<const float2*>(s_shift + c + k);
+                const float2 v = __ffma2_rn(acc[k >> 1], sc, sf);
+                h[k >> 1] = __floats2bfloat162_rn(act(v.x, a.slope), act(v.y, a.slope));
             }
             reinterpret_cast<uint4*>(dst + c)[0] = pk[0];
             reinterpret_cast<uint4*>(dst + c)[1] = pk[1];
-        }
-    }
-}
-
-__global__ void __launch_bounds__(256)
-k_conv_last_bf16(const __nv_bfloat16* __restrict__ in, const float* __restrict__ img, float* __restrict__ out,
-                 const float* __restrict__ w, float bias, CnnIo io, int PH, int PW, const float* __restrict__ xrec,
-                 double* __restrict__ mse_log, const int* __restrict__ slot) {
-    __shared__ float sw[9 * CNN_C];
-    __shared__ float s_err[8];
-    for (int i = threadIdx.x; i < 9 * CNN_C; i += blockDim.x) sw[i] = w[i];
-    __syncthreads();
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const long long npix = (long long)PH * PW;
-    float err = 0.f;
-    for (long long pix = (long long)blockIdx.x * 8 + wib; pix < npix; pix += (long long)gridDim.x * 8) {
-        const int l = (int)(pix / PW), p = (int)(pix % PW);
-        float acc = 0.f;
-#pragma unroll
-        for (int dl = -1; dl <= 1; ++dl)
-#pragma unroll
-            for (int dp = -1; dp <= 1; ++dp) {
-                const int ll = l + dl, pp = p + dp;
-                if (ll < 0 || ll >= PH || pp < 0 || pp >= PW) continue;
-                const __nv_bfloat162 v = reinterpret_cast<const __nv_bfloat162*>(in + ((long long)ll * (PW + 1) + pp) * CNN_C)[lane];
-                const float* ww = sw + ((dl + 1) * 3 + (dp + 1)) * CNN_C + 2 * lane;
-                acc = fmaf(__low2float(v), ww[0], fmaf(__high2float(v), ww[1], acc));
-            }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-        if (lane == 0) {
-            const float x = img[pix];
-            float res;
-            if (io.mode == 0) {
-                const float mn = ord2f(io.stats[0]), mx = ord2f(io.stats[1]);
-                const float xt = (x - mn) / (mx - mn) * io.range + io.shift;
-                res = ((xt - acc) - io.shift) / io.range * (mx - mn) + mn;
-            } else {
-                res = fminf(fmaxf(acc + bias + fminf(fmaxf(x, 0.f), 1.f), 0.f), 1.f);
-            }
-            out[pix] = res;
-            if (xrec) { const float d = res - xrec[pix]; err = fmaf(d, d, err); }
-        }
-    }
-    if (xrec && mse_log) {
-        if (lane == 0) s_err[wib] = err;
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            float t = 0.f;
-            for (int k = 0; k < 8; ++k) t += s_err[k];
-            atomicAdd(mse_log + (slot ? *slot : 0), (double)t);
         }
     }
 }
