@@ -202,8 +202,6 @@ class Epoch:
         h = hook or (lambda name: None)
         gk = dict(b=self.w, sel=eng.sel, with_y=False, gscale=1.0 / B, vadd=self.mu, step_ptr=eng.step,
                   z_in=eng.z, z_out=eng.z, clear_sel=True)
-        if FUSE_SIGMA:
-            gk.update(sig_log=eng.sig_log, sig_slot=eng.slot_ptr)
         if hook is None:
             # the minibatch selection only feeds the column pass: draw it on a parallel graph branch
             eng.fork(eng.sample_sel_device, lambda: p._dev_grad(eng.z, phases=1, **gk))
@@ -216,9 +214,8 @@ class Epoch:
         if FUSED_PROX and self.den._dev_prox_fused(self._ctx()):
             h('prox_fused(sigma+haar+psnr)')
         else:
-            if not FUSE_SIGMA:
-                eng.check(eng.lib.pnp_estimate_sigma(self.D.ptr(eng.z), eng.H, eng.W, 1, self.D.ptr(eng.sig_log),
-                                                     self.D.ptr(eng.slot_ptr), eng.sptr)); h('sigma_mad')
+            eng.check(eng.lib.pnp_estimate_sigma(self.D.ptr(eng.z), eng.H, eng.W, 1, self.D.ptr(eng.sig_log),
+                                                 self.D.ptr(eng.slot_ptr), eng.sptr)); h('sigma_mad')
             self.den._dev_denoise(self._ctx()); h('haar_bayes+psnr')
         eng.advance(); h('advance')
 
@@ -255,8 +252,7 @@ class Epoch:
 
 
 FUSED_PROX = os.environ.get('PNP_BENCH_FUSED_PROX', '1') == '1'    # sigma + wavelet + PSNR as one cooperative launch
-FUSE_SIGMA = os.environ.get('PNP_BENCH_FUSE_SIGMA', '0') == '1'   # sigma estimate inside the c2r pass (slower today)
-LAUNCHES_PER_INNER = 7 - int(FUSE_SIGMA) - int(FUSED_PROX)   # sel_sample + r2c + cols + c2r + sigma_mad + haar_bayes + advance
+LAUNCHES_PER_INNER = 7 - int(FUSED_PROX)   # sel_sample + r2c + cols + c2r + sigma_mad + haar_bayes + advance
 LAUNCHES_PER_SNAPSHOT = 4     # r2c + cols + c2r + D2D copy
 
 

@@ -68,8 +68,6 @@ typedef struct {
                                      bit2 lines c2r + epilogue (used to time the passes one by one) */
     int clear_bits;               /* != 0: the column pass zeroes `bits` after using it (single-use minibatch
                                      selection; the next pnp_csmri_sel_* call then needs clear = 0) */
-    double* sig_log;              /* optional, with z_out: fused pnp_estimate_sigma of z_out (same semantics:  */
-    const int* sig_slot;          /* the sum over columns is ADDED to sig_log[*sig_slot * batch + img])        */
 } pnp_csmri_grad_args;
 int pnp_csmri_grad(const pnp_csmri_grad_args* args, void* stream);
 
@@ -185,6 +183,17 @@ int pnp_wavelet_denoise(const float* z_in, float* z_out, int H, int W, int batch
 int pnp_prox_wavelet_fused(const float* z_in, float* z_out, int H, int W, int batch, double* sig_log,
                            float sigma_modifier, float fallback_sigma, const float* xrec, double* mse_log,
                            const int* slot, void* stream);
+
+/* TV prox by Chambolle's dual projection, ADDITIVE mode (TVDenoiser(method='chambolle')): the north star's
+ * "TV (Chambolle)" kernel; no counterpart in the reference, whose TVDenoiser is the wavelet shrink above
+ * (denoisers/TV.py:24,26).  Arithmetic of scikit-image 0.18.2 denoise_tv_chambolle with a fixed n_iter >= 1
+ * (no eps stop): z_out = z_in - div p after n_iter - 1 dual updates.  The weight is `weight` when > 0, else
+ * sigma_est * sigma_modifier with sigma_est = sig_log[slot*batch+img]/W when that is > 0, else
+ * fallback_weight; a weight <= 0 copies the input.  `work`: 4*H*W*batch floats of scratch (two ping-pong copies
+ * of the dual field).  z_out must not alias z_in.  xrec / mse_log / slot as above. */
+int pnp_tv_chambolle(const float* z_in, float* z_out, int H, int W, int batch, float weight, const double* sig_log,
+                     float sigma_modifier, float fallback_weight, int n_iter, float* work, const float* xrec,
+                     double* mse_log, const int* slot, void* stream);
 
 /* NLMDenoiser.denoise (denoisers/NLM.py:22-27) = skimage denoise_nl_means(h = sigma = sigma_est *
  * sigma_modifier, fast_mode=False, patch_size, patch_distance) on a 2-D grey image.  Even patch sizes

@@ -37,6 +37,26 @@ class TVPort(DenoiserPort):
         return bayes_shrink_columns(noisy, s)
 
 
+class ChambollePort(DenoiserPort):
+    """Additive mode TVDenoiser(method='chambolle') (SURVEY section 8(a')); weight as in the device class."""
+
+    def __init__(self, weight=None, n_iter=20, decay=1, denoise_strength=0, sigma_modifier=1):
+        super().__init__()
+        self.weight, self.n_iter = weight, n_iter
+        self.decay, self.denoise_strength, self.sigma_modifier = decay, denoise_strength, sigma_modifier
+
+    def denoise(self, noisy, sigma_est=0):
+        from .skimage_port import denoise_tv_chambolle
+        self.t += 1
+        if self.weight is not None:
+            w = self.weight
+        else:
+            w = sigma_est * self.sigma_modifier if sigma_est > 0 else self.denoise_strength * self.decay ** self.t
+        if not w > 0:
+            return np.array(noisy)
+        return denoise_tv_chambolle(noisy, weight=w, eps=0.0, n_iter_max=self.n_iter)
+
+
 class NLMPort(DenoiserPort):
     """denoisers/NLM.py:9-27 with ``self.sigma`` (never set in the reference -> AttributeError)
     replaced by the ``sigma_est > 0`` test the sibling denoisers use."""

@@ -160,6 +160,53 @@ def denoise_wavelet(image, sigma=None, wavelet='db1', mode='soft', wavelet_level
     return bayes_shrink_columns(image.astype(np.float64), sigma)
 
 
+# ----------------------------------------------------------------------------- TV (Chambolle)
+def denoise_tv_chambolle(image, weight=0.1, eps=2.e-4, n_iter_max=200):
+    """skimage.restoration.denoise_tv_chambolle (0.18.2, `_denoise_tv_chambolle_nd`) for a 2-D float image.
+
+    NOT on the reference's path (its TVDenoiser is the wavelet shrink above): checker of the additive
+    `TVDenoiser(method='chambolle')` mode, SURVEY section 8(a').  PARITY UNPINNED (no skimage here);
+    self-checks in tests/test_skimage_port.py: constant images are fixed points, the mean is preserved,
+    total variation decreases.  `eps=0` never stops early, which is what the CUDA kernel does.
+    """
+    image = np.asarray(image, dtype=np.float64)
+    ndim = image.ndim
+    p = np.zeros((ndim,) + image.shape)
+    g = np.zeros_like(p)
+    d = np.zeros_like(image)
+    out = image
+    i = 0
+    E_init = E_previous = 0.0
+    while i < n_iter_max:
+        if i > 0:
+            d = -p.sum(0)                       # d is the (negative) divergence of p
+            d[1:, :] += p[0, :-1, :]
+            d[:, 1:] += p[1, :, :-1]
+            out = image + d
+        else:
+            out = image
+        E = (d ** 2).sum()
+        g[0, :-1, :] = np.diff(out, axis=0)     # forward differences, last row / column stay 0
+        g[1, :, :-1] = np.diff(out, axis=1)
+        norm = np.sqrt((g ** 2).sum(axis=0))[np.newaxis, ...]
+        E += weight * norm.sum()
+        tau = 1.0 / (2.0 * ndim)
+        norm *= tau / weight
+        norm += 1.0
+        p -= tau * g
+        p /= norm
+        E /= float(image.size)
+        if i == 0:
+            E_init = E
+            E_previous = E
+        else:
+            if np.abs(E_previous - E) < eps * E_init:
+                break
+            E_previous = E
+        i += 1
+    return out
+
+
 # ----------------------------------------------------------------------------- NLM
 def denoise_nl_means(image, patch_size=7, patch_distance=11, h=0.1, multichannel=False,
                      fast_mode=True, sigma=0.0, exp_mode='exact'):

@@ -25,7 +25,6 @@ class CsmriGradArgs(C.Structure):
         ('g_out', C.c_void_p), ('vadd', C.c_void_p), ('v_out', C.c_void_p),
         ('z_in', C.c_void_p), ('z_out', C.c_void_p),
         ('phases', C.c_int), ('clear_bits', C.c_int),
-        ('sig_log', C.c_void_p), ('sig_slot', C.c_void_p),
     ]
 
 
@@ -84,6 +83,8 @@ PROTOTYPES = {
                                   C.c_float, C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     'pnp_cnn_forward': (C.c_int, [C.POINTER(CnnNet), C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                   C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
+    'pnp_tv_chambolle': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p, C.c_float,
+                                   C.c_float, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     'pnp_estimate_sigma': (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     'pnp_wavelet_denoise': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_float,
                                       C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),

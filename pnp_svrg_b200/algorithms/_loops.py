@@ -21,10 +21,6 @@ from ..engine import LOG_CHUNK, Budget, Engine, stop_rule
 
 def _grad_update(eng, a, b, sel, with_y, gscale, **kw):
     # the engine's minibatch selection is single use: the pass that consumes it leaves it zeroed
-    if kw.get('z_out') is not None and eng.uses_sigma and getattr(eng.p, '_fuses_sigma', False):
-        # the update pass also estimates sigma of the lines it writes (saves a pass over the iterate)
-        kw.update(sig_log=eng.sig_log, sig_slot=eng.slot_ptr)
-        eng.sigma_ready = True
     eng.p._dev_grad(a, b=b, sel=sel, with_y=with_y, gscale=gscale, clear_sel=sel is not None and sel is eng.sel, **kw)
 
 

@@ -121,7 +121,7 @@ class BatchedSVRG:
             gscale=float(kw.get('gscale', 1.0)), gscale_ptr=D.ptr(kw.get('gscale_ptr')), step=0.0,
             step_ptr=D.ptr(kw.get('step_ptr')), g_out=D.ptr(kw.get('g_out')), vadd=D.ptr(kw.get('vadd')), v_out=None,
             z_in=D.ptr(kw.get('z_in')), z_out=D.ptr(kw.get('z_out')), phases=int(phases),
-            clear_bits=int(kw.get('clear', False)), sig_log=None, sig_slot=None)
+            clear_bits=int(kw.get('clear', False)))
         self.check(self.lib.pnp_csmri_grad(C.byref(args), stream))
 
     def _snapshot(self):

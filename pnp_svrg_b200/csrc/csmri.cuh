@@ -39,9 +39,6 @@ struct GradEpilogue {
     float* v_out;                 // optional: v
     const float* z_in;            // optional (with z_out)
     float* z_out;
-    double* sig_log;              // optional (with z_out): fused estimate_sigma of the updated lines,
-    const int* sig_slot;          //   sum over lines added to sig_log[*sig_slot * batch + img]
-    int batch;
 };
 
 // ------------------------------------------------------------------ pass 1
@@ -297,7 +294,9 @@ k_cols_mask(float2* __restrict__ S, const unsigned char* __restrict__ bits,
 // are strided: 16*GP bytes per spectrum row); the epilogue operands (vadd and z_in lines, contiguous)
 // are staged by TMA bulk copies issued at the start of the item, so they arrive while the inverse FFT
 // runs and the epilogue never waits on a global load.
-template <int L, int GP>
+// UPD = true is the inner-iteration form (vadd, z_in and z_out given, nothing else written): the generic
+// epilogue with its five optional pointers unrolls to >100 KiB of code and stalls on instruction fetch.
+template <int L, int GP, bool UPD>
 __global__ void __launch_bounds__(GP * (L / FftPlan<L>::EPT), (GP * (L / FftPlan<L>::EPT) >= 256 ? 2 : 4))
 k_lines_c2r(const float2* __restrict__ S, int nlines, long long img_stride, float inv_n, GradEpilogue ep) {
     constexpr int T = fft_threads<L>();
@@ -322,10 +321,10 @@ k_lines_c2r(const float2* __restrict__ S, int nlines, long long img_stride, floa
     const float step = ep.step_ptr ? ep.step_ptr[img] : ep.step;
     const float* p_vadd = ep.vadd;
     const float* p_zin = ep.z_in;
-    float* p_gout = ep.g_out;
-    float* p_vout = ep.v_out;
+    float* p_gout = UPD ? nullptr : ep.g_out;
+    float* p_vout = UPD ? nullptr : ep.v_out;
     float* p_zout = ep.z_out;
-    const bool staged = (p_vadd != nullptr) || (p_zout != nullptr);
+    const bool staged = UPD || (p_vadd != nullptr) || (p_zout != nullptr);
 
     auto load_spec = [&](int item, float4 (&q)[NQ]) {
 #pragma unroll
@@ -340,9 +339,9 @@ k_lines_c2r(const float2* __restrict__ S, int nlines, long long img_stride, floa
         np = np < GP ? np : GP;
         const unsigned bytes = (unsigned)(np * 2 * L * sizeof(float));
         const long long off = ibase + (long long)(2 * item * GP) * L;
-        mbar_expect_tx(&bar, (p_vadd ? bytes : 0u) + (p_zout ? bytes : 0u));
-        if (p_vadd) bulk_g2s(stage_v, p_vadd + off, bytes, &bar);
-        if (p_zout) bulk_g2s(stage_z, p_zin + off, bytes, &bar);
+        mbar_expect_tx(&bar, ((UPD || p_vadd) ? bytes : 0u) + ((UPD || p_zout) ? bytes : 0u));
+        if (UPD || p_vadd) bulk_g2s(stage_v, p_vadd + off, bytes, &bar);
+        if (UPD || p_zout) bulk_g2s(stage_z, p_zin + off, bytes, &bar);
     };
     if (threadIdx.x == 0) { mbar_init(&bar, 1); mbar_fence_init(); }
     __syncthreads();
@@ -393,31 +392,19 @@ k_lines_c2r(const float2* __restrict__ S, int nlines, long long img_stride, floa
                     const float gval = (h == 0 ? x[i].y : x[i].x) * gs;
                     const int sh = idx + (h ? L : 0);
                     const long long eh = base + sh;
-                    if (p_gout) p_gout[eh] = gval;
-                    float v = gval;
-                    if (p_vadd) v += sv[sh];
-                    if (p_vout) p_vout[eh] = v;
-                    if (p_zout) {
-                        const float zn = sz[sh] - step * v;
-                        p_zout[eh] = zn;
-                        if (ep.sig_log) const_cast<float*>(sz)[sh] = zn;      // keep the updated line for the sigma estimate
+                    if (UPD) {
+                        p_zout[eh] = sz[sh] - step * (gval + sv[sh]);
+                    } else {
+                        if (p_gout) p_gout[eh] = gval;
+                        float v = gval;
+                        if (p_vadd) v += sv[sh];
+                        if (p_vout) p_vout[eh] = v;
+                        if (p_zout) p_zout[eh] = sz[sh] - step * v;
                     }
                 }
             }
         }
-        __syncthreads();                            // exchange buffers free; updated lines complete in stage_z
-        if (GP * T >= 32 && ep.sig_log && p_zout) {
-            // fused estimate_sigma (algorithms/pnp_svrg.py:71): one warp per updated line of this item;
-            // the exchange buffer (free here) provides 32 scratch words per warp
-            constexpr int NW = (GP * T) / 32;
-            unsigned* scratch = reinterpret_cast<unsigned*>(smem) + (threadIdx.x >> 5) * 32;
-            for (int ln = threadIdx.x >> 5; ln < 2 * GP; ln += NW) {
-                if (item * GP * 2 + ln >= nlines) break;
-                const double sig = line_sigma_mad<L>(stage_z + ln * L, threadIdx.x & 31, scratch);
-                if ((threadIdx.x & 31) == 0) atomicAdd(slot_ptr(ep.sig_log, ep.sig_slot, ep.batch, img), sig);
-            }
-            __syncthreads();                        // stage_z consumed before the next item's bulk copy lands
-        }
+        __syncthreads();                            // exchange and staging buffers free for the next item
     }
 }
 

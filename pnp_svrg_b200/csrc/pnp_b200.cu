@@ -16,6 +16,7 @@
 #include "nlm.cuh"
 #include "cnn_fp32.cuh"
 #include "cnn_tc.cuh"
+#include "tv_chambolle.cuh"
 
 namespace {
 
@@ -69,7 +70,8 @@ template <int L> constexpr size_t conv_smem() { return sizeof(float) * 2 * pnp::
 template <int L>
 int set_attrs() {
     CU_TRY(cudaFuncSetAttribute(pnp::k_lines_r2c<L, lines_gp<L>()>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lines_smem<L>()));
-    CU_TRY(cudaFuncSetAttribute(pnp::k_lines_c2r<L, lines_gp<L>()>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lines_smem<L>()));
+    CU_TRY(cudaFuncSetAttribute(pnp::k_lines_c2r<L, lines_gp<L>(), true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lines_smem<L>()));
+    CU_TRY(cudaFuncSetAttribute(pnp::k_lines_c2r<L, lines_gp<L>(), false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lines_smem<L>()));
     CU_TRY(cudaFuncSetAttribute(pnp::k_cols_mask<L, cols_nc<L>()>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cols_smem<L>()));
     cudaFuncAttributes fa;
     CU_TRY(cudaFuncGetAttributes(&fa, pnp::k_sigma_mad<L>));
@@ -136,12 +138,17 @@ int launch_c2r(const pnp_csmri_grad_args& a, cudaStream_t st) {
     constexpr int GP = lines_gp<L>();
     const int pairs = a.W / 2;
     const int items = (pairs + GP - 1) / GP;
-    dim3 grid(persistent_ctas(pnp::k_lines_c2r<L, GP>, GP * pnp::fft_threads<L>(), lines_smem<L>(), items, a.batch), a.batch);
-    pnp::GradEpilogue ep{a.gscale, a.gscale_ptr, a.step, a.step_ptr, a.g_out, a.vadd, a.v_out, a.z_in, a.z_out,
-                         a.sig_log, a.sig_slot, a.batch};
+    pnp::GradEpilogue ep{a.gscale, a.gscale_ptr, a.step, a.step_ptr, a.g_out, a.vadd, a.v_out, a.z_in, a.z_out};
     const float inv_n = (float)(1.0 / ((double)a.H * (double)a.W));
-    pnp::k_lines_c2r<L, GP><<<grid, GP * pnp::fft_threads<L>(), lines_smem<L>(), st>>>(
-        reinterpret_cast<const float2*>(a.S), a.W, (long long)a.H * a.W, inv_n, ep);
+    if (a.vadd && a.z_in && a.z_out && !a.g_out && !a.v_out) {          // the inner-iteration update
+        dim3 grid(persistent_ctas(pnp::k_lines_c2r<L, GP, true>, GP * pnp::fft_threads<L>(), lines_smem<L>(), items, a.batch), a.batch);
+        pnp::k_lines_c2r<L, GP, true><<<grid, GP * pnp::fft_threads<L>(), lines_smem<L>(), st>>>(
+            reinterpret_cast<const float2*>(a.S), a.W, (long long)a.H * a.W, inv_n, ep);
+    } else {
+        dim3 grid(persistent_ctas(pnp::k_lines_c2r<L, GP, false>, GP * pnp::fft_threads<L>(), lines_smem<L>(), items, a.batch), a.batch);
+        pnp::k_lines_c2r<L, GP, false><<<grid, GP * pnp::fft_threads<L>(), lines_smem<L>(), st>>>(
+            reinterpret_cast<const float2*>(a.S), a.W, (long long)a.H * a.W, inv_n, ep);
+    }
     LAUNCH_CHECK();
     return PNP_OK;
 }
@@ -506,6 +513,37 @@ int pnp_pr_grad(const pnp_pr_grad_args* args, void* stream) {
     pnp::k_pr_cols<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(a.A, a.r, a.rows, count, a.n, a.cursor, a.gscale, a.step,
                                                                  a.step_ptr, a.g_out, a.vadd, a.v_out, a.z_in, a.z_out);
     LAUNCH_CHECK();
+    return PNP_OK;
+}
+
+int pnp_tv_chambolle(const float* z_in, float* z_out, int H, int W, int batch, float weight, const double* sig_log,
+                     float sigma_modifier, float fallback_weight, int n_iter, float* work, const float* xrec,
+                     double* mse_log, const int* slot, void* stream) {
+    if (!z_in || !z_out || !work || H < 1 || W < 1 || batch < 1 || n_iter < 1) return fail(PNP_ERR_ARG, "bad argument");
+    if (z_in == z_out) return fail(PNP_ERR_ARG, "z_out must not alias z_in");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    static bool attr = false;
+    if (!attr) {
+        CU_TRY(cudaFuncSetAttribute(pnp::k_tv_chambolle, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TV_SMEM_BYTES));
+        attr = true;
+    }
+    // device layout: W lines of H samples; the operator is symmetric under transposition
+    const int nl = W, np = H;
+    const long long n = (long long)nl * np;
+    dim3 grid((np + TV_TP - 1) / TV_TP, (nl + TV_TL - 1) / TV_TL, batch);
+    float* pa = work;
+    float* pb = work + 2 * n * batch;
+    int left = n_iter - 1, first = 1;
+    do {
+        const int u = left < TV_KB ? left : TV_KB;
+        left -= u;
+        pnp::k_tv_chambolle<<<grid, 256, TV_SMEM_BYTES, st>>>(z_in, pa, pb, z_out, nl, np, u, first, left == 0 ? 1 : 0,
+                                                              weight, sig_log, sigma_modifier, fallback_weight, xrec, mse_log,
+                                                              slot, batch);
+        LAUNCH_CHECK();
+        float* t = pa; pa = pb; pb = t;
+        first = 0;
+    } while (left > 0);
     return PNP_OK;
 }
 

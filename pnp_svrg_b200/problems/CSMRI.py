@@ -17,9 +17,6 @@ def shard_rows(H, rank, world):
 
 
 class CSMRI(Problem):
-    _fuses_sigma = False     # pnp_csmri_grad CAN estimate sigma of the iterate it writes (sig_log=); measured
-                             # slower than the separate kernel at 2048^2, so the engine does not use it
-
     def __init__(self, img_path=None, H=256, W=256, sample_prob=0.5, snr=None, sigma=None, *,
                  image=None, mask_type='bernoulli', shard=None):
         super().__init__(img_path, H, W, image=image)
@@ -122,8 +119,7 @@ class CSMRI(Problem):
                                                     D.ptr(counter), D.ptr(idx_out), int(bool(clear)), D.stream()))
 
     def _dev_grad(self, a, b=None, sel=None, with_y=True, gscale=1.0, gscale_ptr=None, step=0.0, step_ptr=None,
-                  g_out=None, vadd=None, v_out=None, z_in=None, z_out=None, phases=0, clear_sel=False,
-                  sig_log=None, sig_slot=None):
+                  g_out=None, vadd=None, v_out=None, z_in=None, z_out=None, phases=0, clear_sel=False):
         """g = Re(ifft2(sel o fft2(a - b) - Ysel)) * gscale ; v = g + vadd ; z_out = z_in - step*v."""
         args = _lib.CsmriGradArgs(
             H=self.H, W=self.W, batch=1, a=D.ptr(a), b=D.ptr(b), S=D.ptr(self._S),
@@ -132,7 +128,7 @@ class CSMRI(Problem):
             Y1n=D.ptr(self._Y1n) if with_y else None, Y2n=D.ptr(self._Y2n) if with_y else None,
             gscale=float(gscale), gscale_ptr=D.ptr(gscale_ptr), step=float(step), step_ptr=D.ptr(step_ptr),
             g_out=D.ptr(g_out), vadd=D.ptr(vadd), v_out=D.ptr(v_out), z_in=D.ptr(z_in), z_out=D.ptr(z_out), phases=int(phases),
-            clear_bits=int(bool(clear_sel) and sel is not None), sig_log=D.ptr(sig_log), sig_slot=D.ptr(sig_slot))
+            clear_bits=int(bool(clear_sel) and sel is not None))
         _lib.check(_lib.load().pnp_csmri_grad(C.byref(args), D.stream()))
 
     # ---- reference API ---------------------------------------------------------------------

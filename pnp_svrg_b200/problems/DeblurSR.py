@@ -160,8 +160,7 @@ class Deblur(Problem):
                                                   D.ptr(counter), D.stream()))
 
     def _dev_grad(self, a, b=None, sel=None, with_y=True, gscale=1.0, gscale_ptr=None, step=0.0, step_ptr=None,
-                  g_out=None, vadd=None, v_out=None, z_in=None, z_out=None, phases=0, clear_sel=False,
-                  sig_log=None, sig_slot=None):
+                  g_out=None, vadd=None, v_out=None, z_in=None, z_out=None, phases=0, clear_sel=False):
         args = _lib.DeblurGradArgs(
             H=self.H, W=self.W, batch=1, a=D.ptr(a), b=D.ptr(b), S=D.ptr(self._S), blurred=D.ptr(self._blurred),
             up=D.ptr(self._up), Bf=D.ptr(self._Bf), twn=D.ptr(self._twn), y=D.ptr(self._y), tl=D.ptr(self._tl),

@@ -161,3 +161,46 @@ def test_device_sampler_matches_host_twin(cuda):
         cnt = torch.tensor([5], dtype=torch.int32, device=dev)
         _lib.check(_lib.load().pnp_sample_indices(D.ptr(out), n, c, 77, D.ptr(cnt), D.stream()))
         assert np.array_equal(out.cpu().numpy().astype(np.int64), feistel_sample(n, c, 77, 5))
+
+
+@pytest.mark.parametrize('H,W', [(32, 32), (96, 40), (256, 256), (130, 67)])
+def test_tv_chambolle(cuda, H, W):
+    """Additive TVDenoiser(method='chambolle') against the skimage restatement (fixed iteration count)."""
+    from oracle.skimage_port import denoise_tv_chambolle
+    from pnp_svrg_b200.denoisers import TVDenoiser
+    rng = np.random.default_rng(H + W)
+    clean = synth_image(H, W, 3).astype(np.float64) / 255
+    z0 = (clean + 0.08 * rng.standard_normal((H, W))).astype(np.float32).astype(np.float64)
+    for w, n_iter in ((0.1, 1), (0.1, 2), (0.05, 7), (0.2, 13), (0.1, 40)):      # 1, 2: edge cases; 7, 13, 40: 1..7 launches
+        want = denoise_tv_chambolle(z0, weight=w, eps=0.0, n_iter_max=n_iter)
+        got = TVDenoiser(method='chambolle', weight=w, n_iter=n_iter).denoise(z0)
+        assert got.shape == (H, W)
+        assert rel_l2(got, want) < 2e-6, (w, n_iter, rel_l2(got, want))
+    # weight from the loops' sigma estimate, and the weight <= 0 identity
+    d = TVDenoiser(method='chambolle', n_iter=10, sigma_modifier=2.0)
+    assert rel_l2(d.denoise(z0, sigma_est=0.04), denoise_tv_chambolle(z0, weight=0.08, eps=0.0, n_iter_max=10)) < 2e-6
+    assert np.allclose(TVDenoiser(method='chambolle').denoise(z0, sigma_est=0), z0.astype(np.float32), atol=0)
+
+
+def test_tv_chambolle_in_svrg_loop(cuda):
+    """The chambolle prox inside PnP-SVRG (paper-mode VR) tracks the oracle loop with the same prox."""
+    from oracle import algorithms_port as AP
+    from oracle.problems_port import CSMRIPort
+    from pnp_svrg_b200.algorithms import pnp_svrg
+    from pnp_svrg_b200.denoisers import TVDenoiser
+    from pnp_svrg_b200.problems import CSMRI
+    H = 64
+    img = synth_image(H, H, 1)
+    np.random.seed(3)
+    ref = CSMRIPort(img, H=H, W=H, sample_prob=0.5, snr=20.)
+    np.random.seed(3)
+    dut = CSMRI(image=img, H=H, W=H, sample_prob=0.5, snr=20.)
+    kw = dict(eta=0.5 * ref.M0 / 1.0, T2=4, mini_batch_size=300)
+    np.random.seed(4)
+    want = AP.pnp_svrg(ref, AP.ChambollePort(n_iter=12, sigma_modifier=1.5), budget=12, vr_mode='paper', converge_check=False,
+                       eta=kw['eta'], T2=4, mini_batch_size=300)
+    np.random.seed(4)
+    got = pnp_svrg(dut, TVDenoiser(method='chambolle', n_iter=12, sigma_modifier=1.5), tt=1e9, max_iters=12, vr_mode='paper',
+                   converge_check=False, verbose=False, **kw)
+    assert rel_l2(got['z'], want['z']) < 1e-4
+    assert abs(got['psnr_per_iter'][-1] - want['psnr_per_iter'][-1]) <= 0.05

@@ -82,3 +82,29 @@ def test_bilinear_adjoint_and_values():
     assert np.allclose(op * ramp, (mh * 2.0 + mw * 3.0).ravel())               # exact on bilinear functions
     ident = pylops_port.Identity(7)
     assert np.array_equal(ident * np.arange(7.), np.arange(7.)) and np.array_equal(ident.H * np.arange(7.), np.arange(7.))
+
+
+def test_tv_chambolle_self_checks():
+    # additive TVDenoiser(method='chambolle') checker (SURVEY section 8(a')): analytic properties only
+    rng = np.random.default_rng(5)
+    const = np.full((17, 23), 0.37)
+    assert np.allclose(S.denoise_tv_chambolle(const, weight=0.2, eps=0.0, n_iter_max=30), const, atol=1e-15)
+    x = np.clip(np.kron(rng.random((4, 5)), np.ones((8, 8))) + 0.1 * rng.standard_normal((32, 40)), 0, 1)
+
+    def tv(u):
+        g0 = np.diff(u, axis=0)[:, :-1]
+        g1 = np.diff(u, axis=1)[:-1, :]
+        return np.sqrt(g0 ** 2 + g1 ** 2).sum()
+    prev = tv(x)
+    for w in (0.02, 0.1, 0.5):
+        y = S.denoise_tv_chambolle(x, weight=w, eps=0.0, n_iter_max=60)
+        assert abs(y.mean() - x.mean()) < 1e-12          # div p sums to zero: the mean is preserved
+        assert tv(y) < prev                              # more weight, less variation
+        prev = tv(y)
+    assert np.array_equal(S.denoise_tv_chambolle(x, weight=0.1, eps=0.0, n_iter_max=1), x)   # first pass returns the input
+    # the eps stop only shortens the same iteration: its result is one of the fixed-count results
+    a = S.denoise_tv_chambolle(x, weight=0.1, eps=2e-4, n_iter_max=200)
+    assert any(np.array_equal(a, S.denoise_tv_chambolle(x, weight=0.1, eps=0.0, n_iter_max=n)) for n in range(1, 201))
+    # transposition symmetry (the device runs on the transposed layout)
+    assert np.allclose(S.denoise_tv_chambolle(x.T, weight=0.1, eps=0.0, n_iter_max=25).T,
+                       S.denoise_tv_chambolle(x, weight=0.1, eps=0.0, n_iter_max=25), atol=1e-13)
