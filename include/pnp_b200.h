@@ -159,6 +159,37 @@ typedef struct {
 } pnp_pr_grad_args;
 int pnp_pr_grad(const pnp_pr_grad_args* args, void* stream);
 
+/* Coded-diffraction phase retrieval with the intensity loss, ADDITIVE mode PhaseRetrieval(model='cdp') -- the
+ * north star's "coded-diffraction |Ax|^2 - y Wirtinger gradient"; no counterpart in the reference (problems/PR.py
+ * is the dense amplitude model above).  A_l x = fft2(d_l o x)/sqrt(N), d_l = i^codes[l], y = |A x|^2:
+ *   g = gscale * Re( sum_l conj(d_l) o ifft2_unitary( m_l o (|A_l z|^2 - y_l) o A_l z ) )   [ - the same at w ]
+ *   v = g + vadd ;  z_out = z_in - step * v
+ * Images in the line layout; codes / y / mask: [L][W][H] in the same layout (int8 0..3 / float / byte).
+ * sel_idx: `count` measurement ids m = l*H*W + ky*W + kx (set *cursor of [sets][count]); null = all M = L*H*W.
+ * mask (L*H*W bytes, zero on entry, left zero) and S (L*H*W complex64) and acc (H*W floats) are scratch. */
+typedef struct {
+    int H, W, L;
+    const signed char* codes;
+    const float* y;
+    const float* z;
+    const float* w;               /* optional second point (SVRG / SARAH difference; not linear) */
+    const int* sel_idx;
+    int count;
+    const int* cursor;
+    unsigned char* mask;
+    float* S;
+    float* acc;
+    float gscale;
+    float step;
+    const float* step_ptr;
+    float* g_out;
+    const float* vadd;
+    float* v_out;
+    const float* z_in;
+    float* z_out;
+} pnp_cdp_grad_args;
+int pnp_cdp_grad(const pnp_cdp_grad_args* args, void* stream);
+
 /* ---- prox step ------------------------------------------------------------------------------
  * estimate_sigma(z0, multichannel=True, average_sigmas=True)  (algorithms/pnp_svrg.py:71 and
  * pnp_gd.py:49, pnp_sgd.py:50, pnp_saga.py:64, pnp_sarah.py:47,89).  ADDS the sum over columns of

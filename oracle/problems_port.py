@@ -217,3 +217,63 @@ class PhaseRetrievalPort(ProblemPort):
     def grad_stoch(self, z, mb):
         idx = np.nonzero(mb)                                      # :81-87
         return self._grad(self.A[idx], self.Y[idx], z)
+
+
+class CDPPort(ProblemPort):
+    """Coded-diffraction phase retrieval, intensity loss: checker of the ADDITIVE mode
+    PhaseRetrieval(model='cdp') (SURVEY section 8(a'); no counterpart in the reference, so PARITY UNPINNED --
+    tests/test_oracle_golden.py checks the gradient against finite differences of f instead).
+    Same RNG call order as the device class: codes, then the noise.
+
+        A_l x = fft2(d_l o x)/sqrt(N), d_l = 1j**codes[l];  f(x) = sum((|Ax|^2 - y)^2) / (4M)
+        grad_full(z) = Re(A^H((|Az|^2 - y) o Az)) / M ;  grad_stoch(z, mb) the same over the minibatch, no 1/B
+    """
+
+    def __init__(self, img=None, H=256, W=256, n_masks=4, snr=None, sigma=None):
+        super().__init__(img, H, W)
+        self.pname = 'pr'
+        self.L, self.snr, self.sigma = n_masks, snr, sigma
+        self.M = self.L * self.N
+        self.codes = np.random.randint(0, 4, size=(self.L, H, W))
+        self.d = 1j ** self.codes
+        self.Y0 = (np.abs(self.A_op(self.X)) ** 2).ravel()
+        self._noise_level()
+        self.Y = self.Y0 + np.random.normal(0, self.sigma, self.Y0.shape)
+        self._spec_init()
+        self.Xinit = (self.Xinit - self.Xinit.min()) / (self.Xinit.max() - self.Xinit.min())
+
+    def A_op(self, w):
+        return np.fft.fft2(self.d * np.asarray(w, dtype=np.float64).reshape(1, self.H, self.W)) / np.sqrt(self.N)
+
+    def AH_op(self, r):
+        return (np.conj(self.d) * np.fft.ifft2(r) * np.sqrt(self.N)).sum(0)
+
+    def _spec_init(self):
+        nrm = np.linalg.norm(self.X)
+        Y = self.Y.reshape(self.L, self.H, self.W)
+        m, mold = 1, 2
+        cur, old = 2 * np.ones(self.N), np.ones(self.N)
+        it = 0
+        while abs(m - mold) > 1e-5 and np.linalg.norm(cur - old) > 1e-5 and it < 500:
+            mold, old = m, cur
+            cur = np.real(self.AH_op(Y * self.A_op(cur))).ravel() / self.M
+            m = np.max(cur)
+            cur = cur / m
+            it += 1
+        self.Xinit = np.sqrt(abs(m)) * cur / np.linalg.norm(cur) * nrm
+
+    def f(self, w):
+        return np.sum((np.abs(self.A_op(w)).ravel() ** 2 - self.Y) ** 2) / 4 / self.M
+
+    def _grad(self, z, mb=None):
+        t = self.A_op(z)
+        q = np.abs(t) ** 2 - self.Y.reshape(t.shape)
+        if mb is not None:
+            q = q * np.asarray(mb).reshape(t.shape)
+        return np.real(self.AH_op(q * t)).ravel()
+
+    def grad_full(self, z):
+        return self._grad(z) / self.M
+
+    def grad_stoch(self, z, mb):
+        return self._grad(z, mb)

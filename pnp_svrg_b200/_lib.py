@@ -50,6 +50,16 @@ class PrGradArgs(C.Structure):
     ]
 
 
+class CdpGradArgs(C.Structure):
+    """mirror of pnp_cdp_grad_args"""
+    _fields_ = [
+        ('H', C.c_int), ('W', C.c_int), ('L', C.c_int), ('codes', C.c_void_p), ('y', C.c_void_p), ('z', C.c_void_p),
+        ('w', C.c_void_p), ('sel_idx', C.c_void_p), ('count', C.c_int), ('cursor', C.c_void_p), ('mask', C.c_void_p),
+        ('S', C.c_void_p), ('acc', C.c_void_p), ('gscale', C.c_float), ('step', C.c_float), ('step_ptr', C.c_void_p),
+        ('g_out', C.c_void_p), ('vadd', C.c_void_p), ('v_out', C.c_void_p), ('z_in', C.c_void_p), ('z_out', C.c_void_p),
+    ]
+
+
 CNN_MAX_LAYERS = 32
 
 
@@ -79,6 +89,7 @@ PROTOTYPES = {
     'pnp_sample_indices_host': (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_uint, C.c_uint, C.c_int, C.c_int, C.c_void_p]),
     'pnp_deblur_grad': (C.c_int, [C.POINTER(DeblurGradArgs), C.c_void_p]),
     'pnp_pr_grad': (C.c_int, [C.POINTER(PrGradArgs), C.c_void_p]),
+    'pnp_cdp_grad': (C.c_int, [C.POINTER(CdpGradArgs), C.c_void_p]),
     'pnp_nlm_denoise': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
                                   C.c_float, C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     'pnp_cnn_forward': (C.c_int, [C.POINTER(CnnNet), C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p,

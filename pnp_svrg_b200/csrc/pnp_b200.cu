@@ -17,6 +17,7 @@
 #include "cnn_fp32.cuh"
 #include "cnn_tc.cuh"
 #include "tv_chambolle.cuh"
+#include "cdp.cuh"
 
 namespace {
 
@@ -207,6 +208,44 @@ int ew_blocks(long long n, int per_thread) {
     return (int)b;
 }
 
+}  // namespace
+
+namespace {
+template <int L>
+int launch_cdp_lines_fwd(const float* u, const signed char* codes, float2* S, int nlines, int nmasks, cudaStream_t st) {
+    constexpr int GL = pnp::cdp_lines_per_cta<L>();
+    dim3 grid((nlines + GL - 1) / GL, nmasks);
+    pnp::k_cdp_lines_fwd<L><<<grid, GL * pnp::fft_threads<L>(), sizeof(float) * GL * 2 * pnp::fft_plane<L>(), st>>>(u, codes, S, nlines);
+    LAUNCH_CHECK();
+    return PNP_OK;
+}
+template <int LW>
+int launch_cdp_cols(float2* S, const float* y, unsigned char* mask, int H, int nmasks, float inv_n, int clear, cudaStream_t st) {
+    constexpr int NC = pnp::cdp_cols_per_cta<LW>();
+    dim3 grid(H / NC, nmasks);
+    pnp::k_cdp_cols<LW><<<grid, NC * pnp::fft_threads<LW>(), sizeof(float) * NC * 2 * pnp::fft_plane<LW>(), st>>>(S, y, mask, H, inv_n, clear);
+    LAUNCH_CHECK();
+    return PNP_OK;
+}
+template <int L>
+int launch_cdp_lines_inv(const float2* S, const signed char* codes, float* acc, int nlines, int nmasks, float sign, int accumulate,
+                         cudaStream_t st) {
+    constexpr int GL = pnp::cdp_lines_per_cta<L>();
+    pnp::k_cdp_lines_inv<L><<<(nlines + GL - 1) / GL, GL * pnp::fft_threads<L>(), sizeof(float) * GL * 2 * pnp::fft_plane<L>(), st>>>(
+        S, codes, acc, nlines, nmasks, sign, accumulate);
+    LAUNCH_CHECK();
+    return PNP_OK;
+}
+int dispatch_cdp_lines_fwd(int n, const float* u, const signed char* codes, float2* S, int nlines, int nmasks, cudaStream_t st) {
+    DISPATCH_POW2(n, launch_cdp_lines_fwd, u, codes, S, nlines, nmasks, st)
+}
+int dispatch_cdp_cols(int n, float2* S, const float* y, unsigned char* mask, int H, int nmasks, float inv_n, int clear, cudaStream_t st) {
+    DISPATCH_POW2(n, launch_cdp_cols, S, y, mask, H, nmasks, inv_n, clear, st)
+}
+int dispatch_cdp_lines_inv(int n, const float2* S, const signed char* codes, float* acc, int nlines, int nmasks, float sign,
+                           int accumulate, cudaStream_t st) {
+    DISPATCH_POW2(n, launch_cdp_lines_inv, S, codes, acc, nlines, nmasks, sign, accumulate, st)
+}
 }  // namespace
 
 namespace {
@@ -512,6 +551,39 @@ int pnp_pr_grad(const pnp_pr_grad_args* args, void* stream) {
     const long long n4 = a.n / 4;
     pnp::k_pr_cols<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(a.A, a.r, a.rows, count, a.n, a.cursor, a.gscale, a.step,
                                                                  a.step_ptr, a.g_out, a.vadd, a.v_out, a.z_in, a.z_out);
+    LAUNCH_CHECK();
+    return PNP_OK;
+}
+
+int pnp_cdp_grad(const pnp_cdp_grad_args* args, void* stream) {
+    if (!args) return fail(PNP_ERR_ARG, "null args");
+    const pnp_cdp_grad_args& a = *args;
+    if (!pow2_ok(a.H) || !pow2_ok(a.W)) return fail(PNP_ERR_ARG, "H and W must be powers of two in [32, 4096]");
+    if (a.L < 1 || !a.codes || !a.y || !a.z || !a.S || !a.acc) return fail(PNP_ERR_ARG, "bad argument");
+    if (a.sel_idx && (!a.mask || a.count < 1)) return fail(PNP_ERR_ARG, "sel_idx needs mask scratch and count >= 1");
+    if (a.z_out && !a.z_in) return fail(PNP_ERR_ARG, "z_out needs z_in");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const long long N = (long long)a.H * a.W;
+    if (N * a.L >= (1ll << 31)) return fail(PNP_ERR_ARG, "L*H*W too large");
+    float2* S = reinterpret_cast<float2*>(a.S);
+    unsigned char* mask = a.sel_idx ? a.mask : nullptr;
+    if (a.sel_idx) {
+        int blocks = (a.count + 255) / 256;
+        if (blocks > 1184) blocks = 1184;
+        pnp::k_cdp_sel<<<blocks, 256, 0, st>>>(a.mask, a.sel_idx, a.count, a.H, a.W, a.cursor);
+        LAUNCH_CHECK();
+    }
+    const float inv_n = (float)(1.0 / (double)N);
+    const int npts = a.w ? 2 : 1;
+    int rc;
+    for (int pt = 0; pt < npts; ++pt) {
+        const float* u = pt == 0 ? a.z : a.w;
+        if ((rc = dispatch_cdp_lines_fwd(a.H, u, a.codes, S, a.W, a.L, st)) != PNP_OK) return rc;
+        if ((rc = dispatch_cdp_cols(a.W, S, a.y, mask, a.H, a.L, inv_n, pt == npts - 1, st)) != PNP_OK) return rc;
+        if ((rc = dispatch_cdp_lines_inv(a.H, S, a.codes, a.acc, a.W, a.L, pt == 0 ? 1.f : -1.f, pt, st)) != PNP_OK) return rc;
+    }
+    pnp::k_cdp_epilogue<<<ew_blocks(N, 1), 256, 0, st>>>(a.acc, N, a.gscale * inv_n, a.step, a.step_ptr, a.g_out, a.vadd, a.v_out,
+                                                         a.z_in, a.z_out);
     LAUNCH_CHECK();
     return PNP_OK;
 }

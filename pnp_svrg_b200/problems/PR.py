@@ -1,5 +1,10 @@
 """Phase retrieval (dense real Gaussian A, amplitude loss) -- same public surface as the
-reference's problems/PR.py:12-87, gradients on the GPU through pnp_pr_grad (csrc/pr.cuh)."""
+reference's problems/PR.py:12-87, gradients on the GPU through pnp_pr_grad (csrc/pr.cuh).
+
+Additive mode (SURVEY section 8(a'), BASELINE config 3): ``model='cdp'`` is coded-diffraction-pattern phase
+retrieval with the intensity loss, ``A_l x = fft2(d_l o x)/sqrt(N)``, ``d_l = 1j**codes[l]``, ``n_masks``
+patterns, ``M = n_masks*N`` measurements ``y = |A x|^2``, gradient ``Re(A^H((|Az|^2 - y) o Az))`` through
+pnp_cdp_grad (csrc/cdp.cuh).  The default stays the reference's dense model."""
 import ctypes as C
 
 import numpy as np
@@ -10,9 +15,20 @@ from .problem import Problem
 
 
 class PhaseRetrieval(Problem):
-    def __init__(self, img_path=None, H=256, W=256, num_meas=-1, snr=None, sigma=None, *, image=None):
+    def __init__(self, img_path=None, H=256, W=256, num_meas=-1, snr=None, sigma=None, *, image=None,
+                 model='dense', n_masks=4, loss=None):
         super().__init__(img_path, H, W, image=image)
         self.pname = 'pr'
+        if model not in ('dense', 'cdp'):
+            raise ValueError("model must be 'dense' (the reference's) or 'cdp'")
+        self.model = model
+        if model == 'cdp':
+            if loss not in (None, 'intensity'):
+                raise NotImplementedError("the coded-diffraction model is built with loss='intensity'")
+            self._init_cdp(int(n_masks), snr, sigma)
+            return
+        if loss not in (None, 'amplitude'):
+            raise NotImplementedError("the dense model is the reference's amplitude loss")
         self.M = num_meas
         self.snr = snr
         self.sigma = sigma
@@ -46,9 +62,13 @@ class PhaseRetrieval(Problem):
         self.Xinit = np.sqrt(m) * cur / np.linalg.norm(cur) * nrm
 
     def forward_model(self, w):
+        if self.model == 'cdp':
+            return np.abs(self._A_cdp(w)) ** 2
         return np.absolute(self.A.dot(np.asarray(w, dtype=np.float64).ravel()))
 
     def f(self, w):
+        if self.model == 'cdp':
+            return np.linalg.norm(self.Y - self.forward_model(w).ravel()) ** 2 / 4 / self.M
         return np.linalg.norm(self.Y - self.forward_model(w)) ** 2 / 2 / self.M
 
     def _upload(self):
@@ -73,12 +93,68 @@ class PhaseRetrieval(Problem):
     def _dev_grad(self, a, b=None, sel=None, with_y=True, gscale=1.0, gscale_ptr=None, step=0.0, step_ptr=None,
                   g_out=None, vadd=None, v_out=None, z_in=None, z_out=None, phases=0, clear_sel=False):
         """g = [A_sel^T r(a)] - [A_sel^T r(b)] (two-point form when b is given), scaled by gscale."""
+        if self.model == 'cdp':
+            return self._dev_grad_cdp(a, b, sel, gscale, step, step_ptr, g_out, vadd, v_out, z_in, z_out)
         args = _lib.PrGradArgs(
             A=D.ptr(self._A), n=self.N, M=int(self.M), z=D.ptr(a), w=D.ptr(b), y=D.ptr(self._y), rows=D.ptr(sel),
             count=0 if sel is None else int(sel.numel()), cursor=None, r=D.ptr(self._r), gscale=float(gscale),
             step=float(step), step_ptr=D.ptr(step_ptr), g_out=D.ptr(g_out), vadd=D.ptr(vadd), v_out=D.ptr(v_out),
             z_in=D.ptr(z_in), z_out=D.ptr(z_out))
         _lib.check(_lib.load().pnp_pr_grad(C.byref(args), D.stream()))
+
+    # ---- coded diffraction patterns (additive) ------------------------------------------------------
+    def _init_cdp(self, n_masks, snr, sigma):
+        if n_masks < 1:
+            raise ValueError('n_masks must be >= 1')
+        self.L = n_masks
+        self.M = self.L * self.N
+        self.snr, self.sigma = snr, sigma
+        self.codes = np.random.randint(0, 4, size=(self.L, self.H, self.W))           # d = 1j ** codes
+        self._d = 1j ** self.codes
+        self.Y0 = self.forward_model(self.X).ravel()
+        self.set_snr_sigma()
+        self.Y = self.Y0 + np.random.normal(0, self.sigma, self.Y0.shape)
+        self.SNR = self.get_snr_from_sigma
+        self._spec_init_cdp()
+        self.Xinit = (self.Xinit - self.Xinit.min()) / (self.Xinit.max() - self.Xinit.min())
+        dev = self._device
+        t = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a.reshape(self.L, self.H, self.W).transpose(0, 2, 1), dtype=dt)).to(dev)
+        self._codes = t(self.codes, np.int8)
+        self._y = t(self.Y, np.float32)
+        self._mask = torch.zeros(self.M, dtype=torch.uint8, device=dev)
+        self._S = torch.empty(2 * self.M, dtype=torch.float32, device=dev)
+        self._acc = torch.empty(self.N, dtype=torch.float32, device=dev)
+
+    def _A_cdp(self, w):
+        return np.fft.fft2(self._d * np.asarray(w, dtype=np.float64).reshape(1, self.H, self.W)) / np.sqrt(self.N)
+
+    def _AH_cdp(self, r):
+        return (np.conj(self._d) * np.fft.ifft2(r) * np.sqrt(self.N)).sum(0)
+
+    def _spec_init_cdp(self):
+        """Spectral initialisation, the reference's power iteration (problems/PR.py:50-63) on
+        D = A^H diag(Y) A / M applied matrix-free with FFTs."""
+        nrm = np.linalg.norm(self.X)
+        Y = self.Y.reshape(self.L, self.H, self.W)
+        m, mold = 1, 2
+        cur, old = 2 * np.ones(self.N), np.ones(self.N)
+        tol = 1e-5
+        it = 0
+        while abs(m - mold) > tol and np.linalg.norm(cur - old) > tol and it < 500:
+            mold, old = m, cur
+            cur = np.real(self._AH_cdp(Y * self._A_cdp(cur))).ravel() / self.M
+            m = np.max(cur)
+            cur = cur / m
+            it += 1
+        self.Xinit = np.sqrt(abs(m)) * cur / np.linalg.norm(cur) * nrm
+
+    def _dev_grad_cdp(self, a, b, sel, gscale, step, step_ptr, g_out, vadd, v_out, z_in, z_out):
+        args = _lib.CdpGradArgs(
+            H=self.H, W=self.W, L=self.L, codes=D.ptr(self._codes), y=D.ptr(self._y), z=D.ptr(a), w=D.ptr(b),
+            sel_idx=D.ptr(sel), count=0 if sel is None else int(sel.numel()), cursor=None, mask=D.ptr(self._mask),
+            S=D.ptr(self._S), acc=D.ptr(self._acc), gscale=float(gscale), step=float(step), step_ptr=D.ptr(step_ptr),
+            g_out=D.ptr(g_out), vadd=D.ptr(vadd), v_out=D.ptr(v_out), z_in=D.ptr(z_in), z_out=D.ptr(z_out))
+        _lib.check(_lib.load().pnp_cdp_grad(C.byref(args), D.stream()))
 
     # ---- reference API -----------------------------------------------------------------------
     def grad_full(self, z):

@@ -204,3 +204,53 @@ def test_tv_chambolle_in_svrg_loop(cuda):
                    converge_check=False, verbose=False, **kw)
     assert rel_l2(got['z'], want['z']) < 1e-4
     assert abs(got['psnr_per_iter'][-1] - want['psnr_per_iter'][-1]) <= 0.05
+
+
+@pytest.mark.parametrize('H,W,L', [(32, 32, 2), (64, 32, 3), (128, 256, 1), (256, 256, 4)])
+def test_cdp_constructor_and_grads(cuda, H, W, L):
+    """Additive PhaseRetrieval(model='cdp') against the float64 restatement."""
+    from oracle.problems_port import CDPPort
+    from pnp_svrg_b200.problems import PhaseRetrieval
+    img = synth_image(H, W, 4)
+    np.random.seed(7)
+    ref = CDPPort(img, H=H, W=W, n_masks=L, snr=20.)
+    np.random.seed(7)
+    dut = PhaseRetrieval(image=img, H=H, W=W, model='cdp', n_masks=L, snr=20.)
+    assert dut.M == ref.M == L * H * W
+    assert np.array_equal(dut.codes, ref.codes) and np.allclose(dut.Y, ref.Y) and np.allclose(dut.Xinit, ref.Xinit)
+    rng = np.random.default_rng(H)
+    z = rng.random(H * W)
+    assert rel_l2(dut.grad_full(z), ref.grad_full(z)) < 5e-6
+    np.random.seed(8)
+    mb_ref = ref.select_mb(200)
+    np.random.seed(8)
+    mb = dut.select_mb(200)
+    assert np.array_equal(np.asarray(mb), mb_ref)
+    assert rel_l2(dut.grad_stoch(z, mb), ref.grad_stoch(z, mb_ref)) < 5e-6
+    assert rel_l2(dut.grad_stoch(z, mb), ref.grad_stoch(z, mb_ref)) < 5e-6      # the selection scratch was left clean
+    assert rel_l2(dut.grad_full(z), ref.grad_full(z)) < 5e-6
+
+
+@pytest.mark.parametrize('algo,kw', [('pnp_svrg', dict(T2=4, mini_batch_size=400, vr_mode='paper')),
+                                     ('pnp_sgd', dict(mini_batch_size=400)),
+                                     ('pnp_sarah', dict(T2=3, mini_batch_size=400))])
+def test_cdp_loops(cuda, algo, kw):
+    from oracle import algorithms_port as AP
+    from oracle.problems_port import CDPPort
+    import pnp_svrg_b200.algorithms as ALG
+    from pnp_svrg_b200.denoisers import TVDenoiser
+    from pnp_svrg_b200.problems import PhaseRetrieval
+    H = 32
+    img = synth_image(H, H, 5)
+    np.random.seed(11)
+    ref = CDPPort(img, H=H, W=H, n_masks=4, snr=25.)
+    np.random.seed(11)
+    dut = PhaseRetrieval(image=img, H=H, W=H, model='cdp', n_masks=4, snr=25.)
+    eta = 0.05 / max(np.linalg.norm(ref.X) ** 2 / ref.N, 1e-9) / 4
+    okw = {k: v for k, v in kw.items()}
+    np.random.seed(12)
+    want = getattr(AP, algo)(ref, AP.TVPort(), eta=eta, budget=9, converge_check=False, **okw)
+    np.random.seed(12)
+    got = getattr(ALG, algo)(dut, TVDenoiser(), eta=eta, tt=1e9, max_iters=9, converge_check=False, verbose=False, **kw)
+    assert rel_l2(got['z'], want['z']) < 1e-4, rel_l2(got['z'], want['z'])
+    assert abs(got['psnr_per_iter'][-1] - want['psnr_per_iter'][-1]) <= 0.05

@@ -108,3 +108,23 @@ def test_tv_chambolle_self_checks():
     # transposition symmetry (the device runs on the transposed layout)
     assert np.allclose(S.denoise_tv_chambolle(x.T, weight=0.1, eps=0.0, n_iter_max=25).T,
                        S.denoise_tv_chambolle(x, weight=0.1, eps=0.0, n_iter_max=25), atol=1e-13)
+
+
+def test_cdp_port_gradient_matches_finite_differences():
+    # additive PhaseRetrieval(model='cdp') checker: grad_full is the gradient of f (Wirtinger, real x)
+    from conftest import synth_image
+    from oracle.problems_port import CDPPort
+    np.random.seed(0)
+    p = CDPPort(synth_image(8, 8, 0), H=8, W=8, n_masks=3, snr=25.)
+    assert p.M == 3 * 64 and p.Y.shape == (p.M,)
+    z = np.random.default_rng(1).random(p.N)
+    g = p.grad_full(z)
+    for k in (0, 7, 31, 63):
+        e = np.zeros(p.N)
+        e[k] = 1e-6
+        fd = (p.f(z + e) - p.f(z - e)) / 2e-6
+        assert abs(fd - g[k]) < 1e-6 * max(1.0, abs(g[k])), (k, fd, g[k])
+    full = np.ones(p.M, dtype=int)
+    assert np.allclose(p.grad_stoch(z, full) / p.M, g)
+    mb = p.select_mb(50)
+    assert mb.sum() == 50 and np.allclose(p.grad_stoch(z, mb) + p.grad_stoch(z, full - mb), p.grad_stoch(z, full))
