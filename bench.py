@@ -202,16 +202,28 @@ class Epoch:
         h = hook or (lambda name: None)
         gk = dict(b=self.w, sel=eng.sel, with_y=False, gscale=1.0 / B, vadd=self.mu, step_ptr=eng.step,
                   z_in=eng.z, z_out=eng.z, clear_sel=True)
+        tail = lambda: FUSED_TAIL and p._dev_update_prox(
+            1.0 / B, eng.step, self.mu, eng.z, eng.z, eng.sig_log, self.den.sigma_modifier,
+            self.den.denoise_strength * self.den.decay ** (self.den.t + 1), p._xrec_dev, eng.mse_log, eng.slot_ptr)
         if hook is None:
             # the minibatch selection only feeds the column pass: draw it on a parallel graph branch
             eng.fork(eng.sample_sel_device, lambda: p._dev_grad(eng.z, phases=1, **gk))
-            p._dev_grad(eng.z, phases=6, **gk)
+            p._dev_grad(eng.z, phases=2, **gk)
+            fused = tail()
+            if not fused:
+                p._dev_grad(eng.z, phases=4, **gk)
         else:                                  # same kernels, launched one by one so each can be timed
             eng.sample_sel_device(); h('sel_sample')
             p._dev_grad(eng.z, phases=1, **gk); h('lines_r2c')
             p._dev_grad(eng.z, phases=2, **gk); h('cols_mask')
-            p._dev_grad(eng.z, phases=4, **gk); h('lines_c2r+update')
-        if FUSED_PROX and self.den._dev_prox_fused(self._ctx()):
+            fused = tail()
+            if fused:
+                h('c2r+update+prox_fused(sigma+haar+psnr)')
+            else:
+                p._dev_grad(eng.z, phases=4, **gk); h('lines_c2r+update')
+        if fused:
+            self.den.t += 1
+        elif FUSED_PROX and self.den._dev_prox_fused(self._ctx()):
             h('prox_fused(sigma+haar+psnr)')
         else:
             eng.check(eng.lib.pnp_estimate_sigma(self.D.ptr(eng.z), eng.H, eng.W, 1, self.D.ptr(eng.sig_log),
@@ -251,8 +263,9 @@ class Epoch:
         eng.stream.synchronize()
 
 
+FUSED_TAIL = os.environ.get('PNP_BENCH_FUSED_TAIL', '1') == '1'      # pass 3 + update + sigma + wavelet + PSNR as one cooperative launch
 FUSED_PROX = os.environ.get('PNP_BENCH_FUSED_PROX', '1') == '1'    # sigma + wavelet + PSNR as one cooperative launch
-LAUNCHES_PER_INNER = 7 - int(FUSED_PROX)   # sel_sample + r2c + cols + c2r + sigma_mad + haar_bayes + advance
+LAUNCHES_PER_INNER = 7 - int(FUSED_PROX) - int(FUSED_TAIL and FUSED_PROX)   # sel_sample + r2c + cols + c2r + sigma_mad + haar_bayes + advance
 LAUNCHES_PER_SNAPSHOT = 4     # r2c + cols + c2r + D2D copy
 
 
@@ -373,13 +386,15 @@ def breakdown(a, cfg, ep, us_inner_graph):
         'lines_c2r+update': 16.0 * N,                # read spectrum, mu, z (12N), write z (4N)
         'sigma_mad': 4.0 * N,                        # read z
         'prox_fused(sigma+haar+psnr)': 12.0 * N,     # read z, xrec (8N), write z (4N)
+        'c2r+update+prox_fused(sigma+haar+psnr)': 20.0 * N,   # read spectrum, mu, z, xrec (16N), write z (4N)
         'haar_bayes+psnr': 12.0 * N,                 # read z, xrec (8N), write z (4N)
     }
     top = max(alg, key=lambda k: per.get(k, 0.0))
     ach = alg[top] / (per[top] * 1e-6) / 1e9
     traffic = ncu_traffic({'lines_r2c': 'k_lines_r2c', 'cols_mask': 'k_cols_mask', 'lines_c2r+update': 'k_lines_c2r',
                            'sigma_mad': 'k_sigma_mad', 'haar_bayes+psnr': 'k_haar_bayes',
-                           'prox_fused(sigma+haar+psnr)': 'k_prox_wavelet_fused'}[top])
+                           'prox_fused(sigma+haar+psnr)': 'k_prox_wavelet_fused',
+                           'c2r+update+prox_fused(sigma+haar+psnr)': 'k_update_prox'}[top])
     iter_bytes = 28.125 * N
     out = {
         'kernel_us': per, 'kernel_us_sum_eager': tot,

@@ -24,6 +24,28 @@ def _grad_update(eng, a, b, sel, with_y, gscale, **kw):
     eng.p._dev_grad(a, b=b, sel=sel, with_y=with_y, gscale=gscale, clear_sel=sel is not None and sel is eng.sel, **kw)
 
 
+def _grad_update_prox(eng, a, b, sel, gscale, vadd, z):
+    """z <- prox(z - step * (g_sel(a - b) * gscale + vadd)).  CSMRI + wavelet prox: the inverse line pass, the update,
+    the sigma estimate and the prox run as ONE cooperative launch on lines resident in shared memory
+    (pnp_csmri_update_prox); otherwise the gradient pass followed by ``eng.prox``."""
+    p, d = eng.p, eng.d
+    own = sel is not None and sel is eng.sel
+    if (eng.fused_tail is not False and eng.uses_sigma and not eng.sigma_ready and getattr(d, 'method', None) == 'wavelet'
+            and hasattr(p, '_dev_update_prox')):
+        kw = dict(b=b, sel=sel, with_y=False, gscale=gscale, vadd=vadd, step_ptr=eng.step, z_in=z, z_out=z, clear_sel=own)
+        p._dev_grad(a, phases=3, **kw)
+        ok = p._dev_update_prox(gscale, eng.step, vadd, z, z, eng.sig_log, d.sigma_modifier,
+                                d.denoise_strength * d.decay ** (d.t + 1), p._xrec_dev, eng.mse_log, eng.slot_ptr)
+        eng.fused_tail = ok
+        if ok:
+            d.t += 1
+            return
+        p._dev_grad(a, phases=4, **kw)              # the spectrum is there: finish with the separate kernels
+    else:
+        _grad_update(eng, a, b, sel, False, gscale, vadd=vadd, step_ptr=eng.step, z_in=z, z_out=z)
+    eng.prox(z, z)
+
+
 class _Faithful:
     """One eager iteration with the reference's wall-clock phase timing and PSNR read-back."""
 
@@ -278,8 +300,10 @@ def pnp_svrg(problem, denoiser, eta, tt, T2, mini_batch_size, verbose=True, lr_d
     def fast_ops():
         if paper:
             _sel_ops(eng)
-        grad_ops()
-        eng.prox(z, z)
+            _grad_update_prox(eng, z, w, eng.sel, 1.0 / B, mu, z)
+        else:
+            grad_ops()
+            eng.prox(z, z)
         eng.advance()
     draw = _host_draw_fn(eng) if (paper or mb_source == 'legacy') else None
 

@@ -408,6 +408,121 @@ k_lines_c2r(const float2* __restrict__ S, int nlines, long long img_stride, floa
     }
 }
 
+// ------------------------------------------------------------------ pass 3 + prox in one cooperative launch
+// Inner-iteration tail  z <- Denoise(z - step * (g * gscale + vadd))  with the wavelet ("TV") prox, for images
+// whose lines fit the SMs' shared memory (2048^2: 14 lines = 112 KiB per CTA).  Every CTA owns a contiguous
+// block of line pairs.  Its z_in lines are staged ONCE by TMA bulk copies straight into a resident buffer; the
+// inverse line transforms (GP pairs per round, same two-for-one scheme as k_lines_c2r) update that buffer in
+// place; the sigma estimate, the grid-wide mean and the BayesShrink then run on the resident lines
+// (prox_phase_* of prox.cuh) and only the denoised iterate is written.  Against k_lines_c2r +
+// k_prox_wavelet_fused this drops one write and one read of the iterate and a launch boundary.
+template <int L> __host__ __device__ constexpr int upd_gp() { return 512 / fft_threads<L>(); }
+
+template <int L>
+__global__ void __launch_bounds__(512, 1)
+k_update_prox(const float2* __restrict__ S, int nlines, float inv_n, float gscale, float step,
+              const float* __restrict__ step_ptr, const float* __restrict__ vadd, const float* __restrict__ z_in,
+              float* __restrict__ z_out, const float* __restrict__ xrec, int pairs_per_cta, float sigma_modifier,
+              float fallback_sigma, double* __restrict__ sig_log, double* __restrict__ mse_log, const int* __restrict__ slot) {
+    constexpr int T = fft_threads<L>();
+    constexpr int EPT = FftPlan<L>::EPT;
+    constexpr int PL = fft_plane<L>();
+    constexpr int GP = upd_gp<L>();
+    constexpr int GS = group_stride<L, GP>();
+    constexpr int NQ = (L / 2) / T;
+    using IX = FftIdx<L>;
+    extern __shared__ __align__(128) float smem[];
+    __shared__ __align__(8) unsigned long long bar;
+    __shared__ unsigned scratch[16][32];
+    float* lines = smem + lines_stage_off<L, GP>();             // resident: 2 * pairs_per_cta lines
+    const int g = threadIdx.x / T, t = threadIdx.x % T;
+    const int npairs = nlines >> 1;
+    const int first_pair = blockIdx.x * pairs_per_cta;
+    int mine = npairs - first_pair;
+    mine = mine < 0 ? 0 : (mine > pairs_per_cta ? pairs_per_cta : mine);
+    const long long first = 2ll * first_pair;                   // first line of this CTA
+    const int cur_slot = slot ? *slot : 0;
+    const SmemBuf sb{smem + g * GS, smem + g * GS + PL};
+    const float4* S4 = reinterpret_cast<const float4*>(S);
+    const float gs = inv_n * gscale;
+    const float st = step_ptr ? *step_ptr : step;
+
+    if (threadIdx.x == 0) {
+        mbar_init(&bar, 1);
+        mbar_fence_init();
+        if (mine > 0) {
+            mbar_expect_tx(&bar, (unsigned)(2 * mine * L * sizeof(float)));
+            for (int l = 0; l < 2 * mine; ++l)
+                bulk_g2s(lines + (long long)l * L, z_in + (first + l) * L, (unsigned)(L * sizeof(float)), &bar);
+        }
+    }
+    __syncthreads();
+
+    auto load_spec = [&](int round, float4 (&q)[NQ]) {
+#pragma unroll
+        for (int n = 0; n < NQ; ++n) {
+            const int i = threadIdx.x + n * GP * T;
+            const int gg = i % GP, k = i / GP;
+            const int pl = round * GP + gg;
+            q[n] = pl < mine ? S4[(long long)k * npairs + first_pair + pl] : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    };
+    const int rounds = (mine + GP - 1) / GP;
+    float4 qn[NQ];
+    if (rounds > 0) load_spec(0, qn);
+    FftTw<L> tw;
+    tw.init(t);
+    for (int round = 0; round < rounds; ++round) {
+        // X[k] = A[k] + i B[k] of the two lines, written re/im swapped for the inverse transform
+#pragma unroll
+        for (int n = 0; n < NQ; ++n) {
+            const int i = threadIdx.x + n * GP * T;
+            const int gg = i % GP, k = i / GP;
+            const SmemBuf sg{smem + gg * GS, smem + gg * GS + PL};
+            const float4 q = qn[n];
+            if (k == 0) {
+                sg.put(0, make_float2(q.z, q.x));
+                sg.put(L / 2, make_float2(q.w, q.y));
+            } else {
+                sg.put(k, make_float2(q.y + q.z, q.x - q.w));
+                sg.put(L - k, make_float2(q.z - q.y, q.x + q.w));
+            }
+        }
+        if (round + 1 < rounds) load_spec(round + 1, qn);
+        __syncthreads();
+        float2 x[EPT];
+#pragma unroll
+        for (int i = 0; i < EPT; ++i) x[i] = sb.get(IX::in(t, i));
+        __syncthreads();
+        fft_regs<L>(t, sb, x, tw);
+        if (round == 0) mbar_wait(&bar, 0);                     // z_in lines have landed in the resident buffer
+        const int pl = round * GP + g;
+        if (pl < mine) {
+            float* lz = lines + (long long)(2 * pl) * L;
+            const float* gv = vadd + (first + 2 * pl) * L;
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+                float va[EPT];
+#pragma unroll
+                for (int i = 0; i < EPT; ++i) va[i] = gv[hh * L + IX::out(t, i)];
+#pragma unroll
+                for (int i = 0; i < EPT; ++i) {
+                    // swapped output: .y = real part -> line 2*pair, .x = imag part -> line 2*pair + 1
+                    const float gval = (hh == 0 ? x[i].y : x[i].x) * gs;
+                    float* pz = lz + hh * L + IX::out(t, i);
+                    *pz = *pz - st * (gval + va[i]);
+                }
+            }
+        }
+        __syncthreads();                            // exchange buffers free for the next round; lines complete
+    }
+
+    prox_phase_sigma<L>(lines, 2 * mine, first, nlines, 1, sig_log, cur_slot, scratch);
+    __threadfence();
+    cooperative_groups::this_grid().sync();
+    prox_phase_shrink<L>(lines, 2 * mine, first, nlines, 1, z_out, xrec, sigma_modifier, fallback_sigma, sig_log, mse_log, cur_slot);
+}
+
 // ------------------------------------------------------------------ selection bits
 __device__ __forceinline__ void or_byte(unsigned char* base, long long byte_idx, unsigned v) {
     unsigned* w = reinterpret_cast<unsigned*>(base) + (byte_idx >> 2);

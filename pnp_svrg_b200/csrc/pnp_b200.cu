@@ -212,6 +212,37 @@ int ew_blocks(long long n, int per_thread) {
 
 namespace {
 template <int L>
+int launch_update_prox(const float* S, int W, float inv_n, float gscale, float step, const float* step_ptr, const float* vadd,
+                       const float* z_in, float* z_out, const float* xrec, float sm, float fb, double* sig_log, double* mse_log,
+                       const int* slot, cudaStream_t st) {
+    constexpr int GP = pnp::upd_gp<L>();
+    const int npairs = W / 2;
+    int grid = g_num_sms < npairs ? g_num_sms : npairs;
+    const int ppc = (npairs + grid - 1) / grid;
+    grid = (npairs + ppc - 1) / ppc;
+    const size_t smem = sizeof(float) * ((size_t)pnp::lines_stage_off<L, GP>() + (size_t)2 * ppc * L);
+    // worth it only when the rounds are reasonably full and everything fits next to the exchange planes
+    if (smem > 220 * 1024 || 2 * ppc < GP) return fail(PNP_ERR_UNSUPPORTED, "update+prox: image does not suit the resident-line kernel");
+    static bool attr = false;
+    if (!attr) {
+        CU_TRY(cudaFuncSetAttribute(pnp::k_update_prox<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        attr = true;
+    }
+    int nl = W, p = ppc;
+    void* args[] = {(void*)&S, (void*)&nl, (void*)&inv_n, (void*)&gscale, (void*)&step, (void*)&step_ptr, (void*)&vadd, (void*)&z_in,
+                    (void*)&z_out, (void*)&xrec, (void*)&p, (void*)&sm, (void*)&fb, (void*)&sig_log, (void*)&mse_log, (void*)&slot};
+    CU_TRY(cudaLaunchCooperativeKernel((const void*)pnp::k_update_prox<L>, dim3(grid), dim3(512), args, smem, st));
+    return PNP_OK;
+}
+int dispatch_update_prox(int n, const float* S, int W, float inv_n, float gscale, float step, const float* step_ptr,
+                         const float* vadd, const float* z_in, float* z_out, const float* xrec, float sm, float fb, double* sig_log,
+                         double* mse_log, const int* slot, cudaStream_t st) {
+    DISPATCH_POW2(n, launch_update_prox, S, W, inv_n, gscale, step, step_ptr, vadd, z_in, z_out, xrec, sm, fb, sig_log, mse_log, slot, st)
+}
+}  // namespace
+
+namespace {
+template <int L>
 int launch_cdp_lines_fwd(const float* u, const signed char* codes, float2* S, int nlines, int nmasks, cudaStream_t st) {
     constexpr int GL = pnp::cdp_lines_per_cta<L>();
     dim3 grid((nlines + GL - 1) / GL, nmasks);
@@ -553,6 +584,17 @@ int pnp_pr_grad(const pnp_pr_grad_args* args, void* stream) {
                                                                  a.step_ptr, a.g_out, a.vadd, a.v_out, a.z_in, a.z_out);
     LAUNCH_CHECK();
     return PNP_OK;
+}
+
+int pnp_csmri_update_prox(const float* S, int H, int W, float gscale, float step, const float* step_ptr, const float* vadd,
+                          const float* z_in, float* z_out, double* sig_log, float sigma_modifier, float fallback_sigma,
+                          const float* xrec, double* mse_log, const int* slot, void* stream) {
+    if (!S || !vadd || !z_in || !z_out || !sig_log) return fail(PNP_ERR_ARG, "bad argument");
+    if (!pow2_ok(H) || W < 2 || (W & 1)) return fail(PNP_ERR_ARG, "H must be a power of two in [32, 4096], W even");
+    if (H < 128) return fail(PNP_ERR_UNSUPPORTED, "update+prox: lines shorter than 128 samples use the separate kernels");
+    const float inv_n = (float)(1.0 / ((double)H * (double)W));
+    return dispatch_update_prox(H, reinterpret_cast<const float*>(S), W, inv_n, gscale, step, step_ptr, vadd, z_in, z_out, xrec,
+                                sigma_modifier, fallback_sigma, sig_log, mse_log, slot, static_cast<cudaStream_t>(stream));
 }
 
 int pnp_cdp_grad(const pnp_cdp_grad_args* args, void* stream) {

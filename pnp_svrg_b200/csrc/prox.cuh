@@ -367,47 +367,27 @@ __device__ __forceinline__ void haar_sub_forward(float (&x)[HaarSub<L>::VPL], fl
     }
 }
 
+// ---- the two phases of the fused prox on lines resident in shared memory (16 warps, one warp per line) ----
 template <int L>
-__global__ void __launch_bounds__(512, 1)
-k_prox_wavelet_fused(const float* __restrict__ zin, float* __restrict__ zout, const float* __restrict__ xrec,
-                     int nlines, int batch, int lines_per_cta, float sigma_modifier, float fallback_sigma,
-                     double* __restrict__ sig_log, double* __restrict__ mse_log, const int* __restrict__ slot) {
-    using C = HaarSub<L>;
-    constexpr int VPL = C::VPL, LEVELS = C::LEVELS, XL = C::XL, LIN = C::LIN, SB = C::SB, NSB = C::NSB;
-    constexpr float RS2 = 0.70710678118654752f;
-    extern __shared__ __align__(128) float lines[];                   // lines_per_cta x L
-    __shared__ __align__(8) unsigned long long bar;
-    __shared__ unsigned scratch[16][32];
+__device__ __forceinline__ void prox_phase_sigma(const float* lines, int mine, long long first, int nlines, int batch,
+                                                 double* __restrict__ sig_log, int cur_slot, unsigned (*scratch)[32]) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const long long total = (long long)nlines * batch;
-    const long long first = (long long)blockIdx.x * lines_per_cta;
-    long long mine = total - first;
-    mine = mine < 0 ? 0 : (mine > lines_per_cta ? lines_per_cta : mine);
-    const int cur_slot = slot ? *slot : 0;
-
-    // ---- stage my lines (contiguous in memory) ----
-    if (threadIdx.x == 0) {
-        mbar_init(&bar, 1);
-        mbar_fence_init();
-        if (mine > 0) {
-            mbar_expect_tx(&bar, (unsigned)(mine * L * sizeof(float)));
-            for (int l = 0; l < (int)mine; ++l)
-                bulk_g2s(lines + (long long)l * L, zin + (first + l) * L, (unsigned)(L * sizeof(float)), &bar);
-        }
-    }
-    __syncthreads();
-    if (mine > 0) mbar_wait(&bar, 0);
-
-    // ---- phase 1: per-line sigma estimate (one warp per line) ----
-    for (int l = warp; l < (int)mine; l += 16) {
+    for (int l = warp; l < mine; l += 16) {
         const double sig = line_sigma_mad<L>(lines + (long long)l * L, lane, scratch[warp]);
         const int img = (int)((first + l) / nlines);
         if (lane == 0) atomicAdd(sig_log + (long long)cur_slot * batch + img, sig);
     }
-    __threadfence();
-    cooperative_groups::this_grid().sync();
+}
 
-    // ---- phase 2: BayesShrink of the resident lines ----
+template <int L>
+__device__ __forceinline__ void prox_phase_shrink(const float* lines, int mine, long long first, int nlines, int batch,
+                                                  float* __restrict__ zout, const float* __restrict__ xrec,
+                                                  float sigma_modifier, float fallback_sigma, const double* sig_log,
+                                                  double* __restrict__ mse_log, int cur_slot) {
+    using C = HaarSub<L>;
+    constexpr int VPL = C::VPL, LEVELS = C::LEVELS, XL = C::XL, LIN = C::LIN, SB = C::SB, NSB = C::NSB;
+    constexpr float RS2 = 0.70710678118654752f;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float err_acc = 0.f;
     int err_img = -1;
     for (int l = warp; l < (int)mine; l += 16) {
@@ -503,6 +483,45 @@ k_prox_wavelet_fused(const float* __restrict__ zin, float* __restrict__ zout, co
         const float e = warp_sum_f(err_acc);
         if (lane == 0) atomicAdd(mse_log + (long long)cur_slot * batch + err_img, (double)e);
     }
+}
+
+template <int L>
+__global__ void __launch_bounds__(512, 1)
+k_prox_wavelet_fused(const float* __restrict__ zin, float* __restrict__ zout, const float* __restrict__ xrec,
+                     int nlines, int batch, int lines_per_cta, float sigma_modifier, float fallback_sigma,
+                     double* __restrict__ sig_log, double* __restrict__ mse_log, const int* __restrict__ slot) {
+    using C = HaarSub<L>;
+    constexpr int VPL = C::VPL, LEVELS = C::LEVELS, XL = C::XL, LIN = C::LIN, SB = C::SB, NSB = C::NSB;
+    constexpr float RS2 = 0.70710678118654752f;
+    extern __shared__ __align__(128) float lines[];                   // lines_per_cta x L
+    __shared__ __align__(8) unsigned long long bar;
+    __shared__ unsigned scratch[16][32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long total = (long long)nlines * batch;
+    const long long first = (long long)blockIdx.x * lines_per_cta;
+    long long mine = total - first;
+    mine = mine < 0 ? 0 : (mine > lines_per_cta ? lines_per_cta : mine);
+    const int cur_slot = slot ? *slot : 0;
+
+    // ---- stage my lines (contiguous in memory) ----
+    if (threadIdx.x == 0) {
+        mbar_init(&bar, 1);
+        mbar_fence_init();
+        if (mine > 0) {
+            mbar_expect_tx(&bar, (unsigned)(mine * L * sizeof(float)));
+            for (int l = 0; l < (int)mine; ++l)
+                bulk_g2s(lines + (long long)l * L, zin + (first + l) * L, (unsigned)(L * sizeof(float)), &bar);
+        }
+    }
+    __syncthreads();
+    if (mine > 0) mbar_wait(&bar, 0);
+
+    // ---- phase 1: per-line sigma estimate (one warp per line) ----
+    prox_phase_sigma<L>(lines, (int)mine, first, nlines, batch, sig_log, cur_slot, scratch);
+    __threadfence();
+    cooperative_groups::this_grid().sync();
+    // ---- phase 2: BayesShrink of the resident lines ----
+    prox_phase_shrink<L>(lines, (int)mine, first, nlines, batch, zout, xrec, sigma_modifier, fallback_sigma, sig_log, mse_log, cur_slot);
 }
 
 }  // namespace pnp

@@ -105,6 +105,7 @@ class Engine:
         self._pending = []          # fast mode: (kind,) markers for slots not yet read back
         self.graph = None
         self.fused_prox = None      # None: try the single-launch prox; False: image too large for it
+        self.fused_tail = None      # same for the single-launch pass 3 + update + prox of CSMRI (algorithms/_loops.py)
         self.deferred = []
         self.since_sync = 0
         self.side = None

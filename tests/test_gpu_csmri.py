@@ -320,3 +320,43 @@ def test_fused_prox_equals_two_kernel_prox(cuda, H, W):
     assert sa[2] > 0 and abs(sa[2] - sb[2]) <= 1e-12 * sa[2] and sb[0] == sb[1] == sb[3] == 0
     assert np.array_equal(a, b) or rel_l2(b, a) < 1e-6
     assert abs(ma[2] - mb[2]) <= 1e-6 * ma[2]
+
+
+@pytest.mark.parametrize('H,W', [(1024, 1024), (2048, 2048), (512, 512)])
+def test_update_prox_single_launch_matches_separate_kernels(cuda, H, W):
+    """pnp_csmri_update_prox == pnp_csmri_grad(phases=4) + pnp_prox_wavelet_fused on the same spectrum."""
+    import torch
+    from pnp_svrg_b200 import device as D
+    from pnp_svrg_b200.denoisers import TVDenoiser
+    from pnp_svrg_b200.engine import ProxCtx
+    from pnp_svrg_b200.problems import CSMRI
+    np.random.seed(5)
+    p = CSMRI(image=synth_image(H, W, 2), H=H, W=W, sample_prob=0.4, snr=20.)
+    dev = p._device
+    rng = np.random.default_rng(1)
+    z = D.to_lines(rng.random((H, W)), H, W, dev)
+    w = D.to_lines(rng.random((H, W)), H, W, dev)
+    mu = D.to_lines(0.01 * rng.standard_normal((H, W)), H, W, dev)
+    step = torch.tensor([0.37], dtype=torch.float32, device=dev)
+    sig = torch.zeros(4, dtype=torch.float64, device=dev)
+    mse = torch.zeros(4, dtype=torch.float64, device=dev)
+    slot = torch.tensor([1], dtype=torch.int32, device=dev)
+    gk = dict(b=w, sel=None, with_y=False, gscale=0.5, vadd=mu, step_ptr=step, z_in=z)
+    # separate kernels
+    z1 = torch.empty_like(z)
+    p._dev_grad(z, phases=3, z_out=z1, **gk)
+    p._dev_grad(z, phases=4, z_out=z1, **gk)
+    den = TVDenoiser(sigma_modifier=1.3)
+    o1 = torch.empty_like(z)
+    assert den._dev_prox_fused(ProxCtx(z1, o1, H, W, sig_log=sig, xrec=p._xrec_dev, mse_log=mse, slot=slot))
+    s1, m1 = float(sig[1]), float(mse[1])
+    # one launch
+    sig.zero_(); mse.zero_()
+    o2 = torch.empty_like(z)
+    p._dev_grad(z, phases=3, z_out=o2, **gk)
+    ok = p._dev_update_prox(0.5, step, mu, z, o2, sig, 1.3, 0.0, p._xrec_dev, mse, slot)
+    torch.cuda.synchronize()
+    if not ok:
+        pytest.skip('image does not suit the resident-line kernel')
+    assert torch.equal(o1, o2)
+    assert float(sig[1]) == pytest.approx(s1, rel=1e-12) and float(mse[1]) == pytest.approx(m1, rel=1e-6)
