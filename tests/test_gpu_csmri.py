@@ -360,3 +360,20 @@ def test_update_prox_single_launch_matches_separate_kernels(cuda, H, W):
         pytest.skip('image does not suit the resident-line kernel')
     assert torch.equal(o1, o2)
     assert float(sig[1]) == pytest.approx(s1, rel=1e-12) and float(mse[1]) == pytest.approx(m1, rel=1e-6)
+
+
+def test_svrg_fast_mode_with_single_launch_tail_matches_eager_loop(cuda):
+    """1024^2 is large enough for the resident-line tail: the graph-replay loop that uses it must reproduce
+    the eager loop (separate kernels, PSNR read back every iteration)."""
+    from pnp_svrg_b200.algorithms import pnp_svrg
+    from pnp_svrg_b200.denoisers import TVDenoiser
+    from pnp_svrg_b200.problems import CSMRI
+    H = 1024
+    np.random.seed(2)
+    p = CSMRI(image=synth_image(H, H, 0), H=H, W=H, sample_prob=0.3, snr=20.)
+    kw = dict(eta=0.15 * p.M0, tt=1e9, T2=3, mini_batch_size=20000, max_iters=7, vr_mode='paper', converge_check=False,
+              verbose=False, mb_source='host', mb_seed=9)
+    a = pnp_svrg(p, TVDenoiser(), fast=False, **kw)
+    b = pnp_svrg(p, TVDenoiser(), fast=True, **kw)
+    assert rel_l2(b['z'], a['z']) < 1e-6
+    assert np.allclose(a['psnr_per_iter'], b['psnr_per_iter'], atol=0.011)
