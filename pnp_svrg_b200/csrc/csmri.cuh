@@ -156,7 +156,7 @@ template <int L, int NC> __host__ __device__ constexpr int cols_stage_off() { re
 // per CTA; the NC rows of an item are one contiguous block, staged by a TMA bulk copy that runs
 // one item ahead.  Columns 1..hp-1 are element-wise in the spectrum: forward FFT, selection and
 // inverse FFT happen in registers + the exchange buffer.  Column 0 (DC + i*Nyquist packed) needs
-// C[kx] and C[-kx] together and is done by CTA 0 after its loop.
+// C[kx] and C[-kx] together and is done by the last CTA after its loop.
 template <int L, int NC>
 __global__ void __launch_bounds__(NC * (L / FftPlan<L>::EPT), (NC * (L / FftPlan<L>::EPT) >= 256 ? 2 : 4))
 k_cols_mask(float2* __restrict__ S, const unsigned char* __restrict__ bits,
@@ -239,7 +239,8 @@ k_cols_mask(float2* __restrict__ S, const unsigned char* __restrict__ bits,
         if (FftPlan<L>::NS > 1) __syncthreads();
     }
 
-    if (blockIdx.x != 0) return;
+    // done by the LAST CTA: with items = 1.73 x CTAs it has a single item, so this extra work is not a straggler
+    if (blockIdx.x != gridDim.x - 1) return;
     // ---- packed column 0: C = FFT(DC + i * Nyq); split, select each row, re-pack ----
     {
         float2 x[EPT];
