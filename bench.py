@@ -337,8 +337,10 @@ def run_b200(a, cfg, rank, world, local_rank):
 
     # ---- end to end through the public API with host buffers ----
     if not a.no_e2e:
-        e2e = run_e2e(a, cfg, ep.prob, dev, world)
+        e2e = run_e2e(a, cfg, ep.prob, dev, world, fast=True)
         if e2e is not None:
+            eager = run_e2e(a, cfg, ep.prob, dev, world, fast=False)
+            e2e['eager_value'] = eager['value']          # same call with fast=False: read-back after every iteration
             line['e2e'] = e2e
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
         line['cpu_baseline'] = cpu_baseline(cfg, a.cpu_iters or T2)
@@ -430,9 +432,10 @@ def ncu_traffic(kernel):
     return None
 
 
-def run_e2e(a, cfg, prob, dev, world):
+def run_e2e(a, cfg, prob, dev, world, fast=True):
     """Public API, host buffers: algorithms.pnp_svrg with host-drawn minibatches copied from pinned
-    memory every inner iteration and the PSNR of every iterate read back."""
+    memory every inner iteration and the PSNR of every iterate read back (fast=True: graph replay, read-back
+    in batches of 64 iterations; fast=False: the reference's loop shape, read-back after every iteration)."""
     import torch
     import torch.distributed as dist
     from pnp_svrg_b200.algorithms import pnp_svrg
@@ -440,7 +443,7 @@ def run_e2e(a, cfg, prob, dev, world):
     T2, B = cfg['T2'], cfg['mini_batch_size']
     iters = a.steps * T2
     kw = dict(eta=cfg['eta'], T2=T2, mini_batch_size=B, vr_mode='paper', verbose=False, converge_check=False,
-              mb_source='host', mb_seed=11)
+              mb_source='host', mb_seed=11, fast=fast)
     pnp_svrg(prob, TVDenoiser(), tt=1e9, max_iters=min(iters, 2 * T2), **kw)          # warm-up
     if world > 1:
         dist.barrier()
@@ -455,9 +458,10 @@ def run_e2e(a, cfg, prob, dev, world):
         dt = float(t.item())
     return {'value': world * iters / dt, 'unit': UNIT, 'h2d_bytes_per_step': T2 * 4 * B + 4 * prob.N // a.steps,
             'd2h_bytes_per_step': T2 * 16 + 8 * prob.N // a.steps, 'seconds': dt, 'inner_iterations': iters,
-            'api': "pnp_svrg_b200.algorithms.pnp_svrg(problem, denoiser, ..., mb_source='host') -- minibatch drawn on "
-                   "the host, copied from pinned memory each inner iteration; PSNR + sigma read back each iteration; "
-                   "Xinit upload and final z download included",
+            'api': "pnp_svrg_b200.algorithms.pnp_svrg(problem, denoiser, ..., mb_source='host', fast=%s) -- minibatch drawn "
+                   "on the host, copied from pinned memory each inner iteration; PSNR + sigma of every iterate read back "
+                   "%s; Xinit upload and final z download included"
+                   % (fast, 'in batches of 64 iterations (graph replay)' if fast else 'after every iteration (eager loop)'),
             'psnr_last': float(out['psnr_per_iter'][-1])}
 
 

@@ -559,19 +559,30 @@ __device__ __forceinline__ unsigned mix32(unsigned x) {
     x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15; x *= 0x846ca68bU; x ^= x >> 16;
     return x;
 }
+// Generalised (unbalanced) Feistel network on Z_b x Z_a with a = 2^hb >= sqrt(n) and b = ceil(n / a): the domain
+// a*b exceeds n by less than a, so cycle walking almost never iterates (a balanced 2^(2 hb) domain needs up to 4
+// passes per index).  Rounds alternate (l, r) -> (r, (l + F(r)) mod b) and (l, r) -> (r, (l + F(r)) mod a); the
+// reduction of F to [0, b) is a multiply-high, so there is no division.  Host twins: h_feistel (pnp_b200.cu) and
+// engine.feistel_sample (NumPy) produce the same sequence bit for bit.
 __device__ __forceinline__ unsigned feistel_perm(unsigned i, unsigned n, unsigned key) {
     int hb = 1;
-    while ((1u << (2 * hb)) < n) ++hb;                 // 2*hb bits cover n
+    while ((1u << (2 * hb)) < n) ++hb;                 // a = 2^hb, a*a >= n
     const unsigned hm = (1u << hb) - 1u;
+    const unsigned b = (n + hm) >> hb;                 // ceil(n / a) <= a
     unsigned x = i;
     do {
-        unsigned l = x >> hb, r = x & hm;
+        unsigned l = x >> hb, r = x & hm;              // l in Z_b, r in Z_a
 #pragma unroll
-        for (int rd = 0; rd < 4; ++rd) {
-            const unsigned f = mix32(r ^ (key + 0x9e3779b9U * (rd + 1))) & hm;
-            const unsigned nl = r;
-            r = l ^ f;
-            l = nl;
+        for (int rd = 0; rd < 4; rd += 2) {
+            const unsigned f0 = __umulhi(mix32(r ^ (key + 0x9e3779b9U * (rd + 1))), b);
+            unsigned t = l + f0;                        // < 2b
+            t = t >= b ? t - b : t;
+            l = r;                                      // (l, r) now in Z_a x Z_b
+            r = t;
+            const unsigned f1 = mix32(r ^ (key + 0x9e3779b9U * (rd + 2))) & hm;
+            t = (l + f1) & hm;
+            l = r;                                      // back in Z_b x Z_a
+            r = t;
         }
         x = (l << hb) | r;
     } while (x >= n);

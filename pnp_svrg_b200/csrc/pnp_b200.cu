@@ -486,16 +486,22 @@ inline unsigned h_mix32(unsigned x) {
     x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15; x *= 0x846ca68bU; x ^= x >> 16;
     return x;
 }
-inline unsigned h_feistel(unsigned i, unsigned n, unsigned key, int hb) {
+inline unsigned h_feistel(unsigned i, unsigned n, unsigned key, int hb) {      // twin of pnp::feistel_perm (csmri.cuh)
     const unsigned hm = (1u << hb) - 1u;
+    const unsigned b = (n + hm) >> hb;
     unsigned x = i;
     do {
         unsigned l = x >> hb, r = x & hm;
-        for (int rd = 0; rd < 4; ++rd) {
-            const unsigned f = h_mix32(r ^ (key + 0x9e3779b9U * (rd + 1))) & hm;
-            const unsigned nl = r;
-            r = l ^ f;
-            l = nl;
+        for (int rd = 0; rd < 4; rd += 2) {
+            const unsigned f0 = (unsigned)(((unsigned long long)h_mix32(r ^ (key + 0x9e3779b9U * (rd + 1))) * b) >> 32);
+            unsigned t = l + f0;
+            t = t >= b ? t - b : t;
+            l = r;
+            r = t;
+            const unsigned f1 = h_mix32(r ^ (key + 0x9e3779b9U * (rd + 2))) & hm;
+            t = (l + f1) & hm;
+            l = r;
+            r = t;
         }
         x = (l << hb) | r;
     } while (x >= n);

@@ -94,11 +94,15 @@ class Engine:
         self._host_draws = 0
         self._draw_queue = []
         self._draw_ahead = 3
+        ncpu = len(os.sched_getaffinity(0)) if hasattr(os, 'sched_getaffinity') else (os.cpu_count() or 1)
         self._draw_pool = None
         if mb_source == 'host':
             from concurrent.futures import ThreadPoolExecutor
-            self._draw_pool = ThreadPoolExecutor(max_workers=3)
-            self._host_threads = max(1, min(4, (os.cpu_count() or 1) // 4))
+            # one single-threaded C call per draw (GIL released), several draws in flight: spawning worker
+            # threads inside every call costs more than the ~1.3 ms a 100k-index draw takes on one core
+            self._draw_ahead = max(2, min(8, ncpu // 2))
+            self._draw_pool = ThreadPoolExecutor(max_workers=self._draw_ahead)
+            self._host_threads = 1
         if mb_source != 'host':
             self._host_threads = max(1, min(8, (os.cpu_count() or 1) // 2))
         self._ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
@@ -370,16 +374,22 @@ def feistel_sample(n, count, seed, counter, img=0):
     while (1 << (2 * hb)) < n:
         hb += 1
     hm = np.uint32((1 << hb) - 1)
+    b = np.uint32((n + (1 << hb) - 1) >> hb)         # unbalanced domain 2^hb x ceil(n / 2^hb), see csrc/csmri.cuh
     key = np.uint32(feistel_key(seed, counter, img))
     x = np.arange(count, dtype=np.uint32)
     out = np.empty(count, dtype=np.uint32)
     pending = np.arange(count)
+    rk = lambda rd: np.uint32((int(key) + 0x9e3779b9 * rd) & 0xffffffff)
     with np.errstate(over='ignore'):
         while pending.size:
             l, r = x >> np.uint32(hb), x & hm
-            for rd in range(4):
-                f = _mix32(r ^ np.uint32((int(key) + 0x9e3779b9 * (rd + 1)) & 0xffffffff)) & hm
-                l, r = r, l ^ f
+            for rd in (0, 2):
+                f0 = ((_mix32(r ^ rk(rd + 1)).astype(np.uint64) * np.uint64(b)) >> np.uint64(32)).astype(np.uint32)
+                t = l + f0
+                t = np.where(t >= b, t - b, t)
+                l, r = r, t
+                f1 = _mix32(r ^ rk(rd + 2)) & hm
+                l, r = r, (l + f1) & hm
             x = (l << np.uint32(hb)) | r
             ok = x < np.uint32(n)
             out[pending[ok]] = x[ok]
