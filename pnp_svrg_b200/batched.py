@@ -42,6 +42,46 @@ def csmri_host_spec(image, H, W, sample_prob, snr, rng=np.random):
                 support=np.flatnonzero(mask).astype(np.int32), data_range=1.0 if xrec.min() >= 0 else 2.0)
 
 
+def csmri_device_batch(images, sample_probs, snrs, H, W, seed=0, device=None):
+    """Construction of a whole batch of CSMRI problems ON THE DEVICE (the step before the hot path, SURVEY section
+    8(f) rank 2): same model as problems/CSMRI.py:12-41 -- Bernoulli(p) mask, Y = mask o (fft2(X) + N(0, sigma)) with
+    sigma from the SNR, Xinit = minmax(|ifft2(Y)|) -- but drawn with a torch CUDA generator and transformed with
+    torch.fft in float32, so the draws differ from the NumPy ones of `csmri_host_spec` (sweeps are unseeded in the
+    reference).  Library calls are confined to this constructor; the iterations run on the package's own kernels.
+    Returns the stacked device tensors BatchedSVRG takes in place of a list of host specs."""
+    from .problems.problem import load_image
+    dev = device or D.require_cuda()
+    nb, hp = len(images), H // 2
+    x = torch.from_numpy(np.stack([load_image(None, im, H, W) for im in images]).astype(np.float32)).to(dev)
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(int(seed))
+    p = torch.tensor(np.asarray(sample_probs, dtype=np.float32), device=dev).view(nb, 1, 1)
+    snr = torch.tensor(np.asarray(snrs, dtype=np.float32), device=dev)
+    mask = torch.rand((nb, H, W), generator=gen, device=dev) < p
+    y0 = torch.fft.fft2(x) * mask
+    # problems/problem.py:58-61: sigma = sqrt(||Y0||_2 / 10^(snr/10) / H / W)   (norm, not norm^2, as in the reference)
+    sigma = torch.sqrt(torch.linalg.vector_norm(y0.reshape(nb, -1), dim=1) / 10 ** (snr / 10) / H / W)
+    y = y0 + mask * (torch.randn((nb, H, W), generator=gen, device=dev) * sigma.view(nb, 1, 1))      # real noise, CSMRI.py:32-33
+    x0 = torch.fft.ifft2(y).abs()
+    lo, hi = x0.amin(dim=(1, 2), keepdim=True), x0.amax(dim=(1, 2), keepdim=True)
+    xinit = (x0 - lo) / (hi - lo)
+    ymir = torch.conj(torch.roll(torch.flip(y, dims=(1, 2)), shifts=(1, 1), dims=(1, 2)))              # conj Y[-ky][-kx]
+    c = lambda t: torch.view_as_real(t.to(torch.complex64).contiguous()).contiguous()
+    m0 = mask.reshape(nb, -1).sum(dim=1).to(torch.int32)
+    # padded support lists: indices of the sampled positions first (ascending), as np.flatnonzero gives them
+    N = H * W
+    key = torch.where(mask.reshape(nb, N), torch.arange(N, device=dev, dtype=torch.int32).expand(nb, N),
+                      torch.full((1,), N, device=dev, dtype=torch.int32).expand(nb, N))
+    m0_host = m0.cpu().numpy()
+    stride = int(m0_host.max())
+    support = torch.sort(key, dim=1).values[:, :stride].contiguous()
+    support = torch.where(support < N, support, torch.zeros_like(support))
+    return dict(device=True, nb=nb, H=H, W=W, m0_host=m0_host.astype(np.int32), m0=m0.contiguous(), support=support,
+                xrec=x.transpose(1, 2).contiguous(), xinit=xinit.transpose(1, 2).contiguous(),
+                Y1=c(y[:, :hp]), Y2=c(ymir[:, :hp]), Y1n=c(y[:, hp]), Y2n=c(ymir[:, hp]),
+                sigma=sigma.cpu().numpy(), data_range=np.ones(nb))
+
+
 class BatchedSVRG:
     """PnP-SVRG (paper-mode VR, algorithms/pnp_svrg.py:8-105 with line 53) + wavelet prox
     (denoisers/TV.py) on a batch of CSMRI problems of one size."""
@@ -49,15 +89,22 @@ class BatchedSVRG:
     def __init__(self, specs, T2, mini_batch_size, etas, seed=0, lr_decay=1.0, sigma_modifier=1.0, max_slots=4096):
         self.lib = _lib.load()
         self.dev = D.require_cuda()
-        self.nb = nb = len(specs)
-        self.H, self.W = specs[0]['H'], specs[0]['W']
-        if any(s['H'] != self.H or s['W'] != self.W for s in specs):
-            raise ValueError('all problems of a batch must have the same size')
+        on_dev = isinstance(specs, dict) and specs.get('device')          # csmri_device_batch() output
+        if on_dev:
+            self.nb = nb = specs['nb']
+            self.H, self.W = specs['H'], specs['W']
+            m0_all = specs['m0_host']
+        else:
+            self.nb = nb = len(specs)
+            self.H, self.W = specs[0]['H'], specs[0]['W']
+            if any(s['H'] != self.H or s['W'] != self.W for s in specs):
+                raise ValueError('all problems of a batch must have the same size')
+            m0_all = np.array([s['M0'] for s in specs], dtype=np.int32)
         self.N = N = self.H * self.W
         hp = self.H // 2
         self.T2, self.B, self.seed, self.lr_decay = int(T2), int(mini_batch_size), int(seed), float(lr_decay)
         self.sigma_modifier = float(sigma_modifier)
-        if any(s['M0'] < self.B for s in specs):
+        if (m0_all < self.B).any():
             raise ValueError('mini_batch_size exceeds the number of measurements of a problem')
         self.stream = torch.cuda.Stream(device=self.dev)
         self.sptr = self.stream.cuda_stream
@@ -68,17 +115,24 @@ class BatchedSVRG:
 
         def stack_c(key):
             return torch.view_as_real(torch.from_numpy(np.ascontiguousarray(np.stack([s[key] for s in specs]))).to(dev)).contiguous()
+        if on_dev:
+            torch.cuda.current_stream(dev).synchronize()                 # the batch was built on the current stream
         with torch.cuda.stream(self.stream):
-            self.xrec = stack('xrec', torch.float32)
-            self.z = stack('xinit', torch.float32)
-            self.Y1, self.Y2, self.Y1n, self.Y2n = stack_c('Y1'), stack_c('Y2'), stack_c('Y1n'), stack_c('Y2n')
-            self.m0_host = np.array([s['M0'] for s in specs], dtype=np.int32)
-            self.m0 = torch.from_numpy(self.m0_host).to(dev)
+            self.m0_host = m0_all
             self.sup_stride = int(self.m0_host.max())
-            sup = np.zeros((nb, self.sup_stride), dtype=np.int32)
-            for i, s in enumerate(specs):
-                sup[i, :s['M0']] = s['support']
-            self.support = torch.from_numpy(sup).to(dev)
+            if on_dev:
+                self.xrec, self.z = specs['xrec'], specs['xinit'].clone()
+                self.Y1, self.Y2, self.Y1n, self.Y2n = specs['Y1'], specs['Y2'], specs['Y1n'], specs['Y2n']
+                self.m0, self.support = specs['m0'], specs['support']
+            else:
+                self.xrec = stack('xrec', torch.float32)
+                self.z = stack('xinit', torch.float32)
+                self.Y1, self.Y2, self.Y1n, self.Y2n = stack_c('Y1'), stack_c('Y2'), stack_c('Y1n'), stack_c('Y2n')
+                self.m0 = torch.from_numpy(self.m0_host).to(dev)
+                sup = np.zeros((nb, self.sup_stride), dtype=np.int32)
+                for i, s in enumerate(specs):
+                    sup[i, :s['M0']] = s['support']
+                self.support = torch.from_numpy(sup).to(dev)
             self.w = torch.empty_like(self.z)
             self.mu = torch.empty_like(self.z)
             self.S = torch.empty(nb * N, dtype=torch.float32, device=dev)
@@ -93,13 +147,13 @@ class BatchedSVRG:
             self.check(self.lib.pnp_csmri_sel_from_indices(D.ptr(self.bits_full), self.H, self.W, nb, D.ptr(self.support), 0,
                                                            self.sup_stride, None, 1, self.sptr))
             # full-mask bits: every problem's own support (counts differ, so one launch per distinct problem)
-            for i, s in enumerate(specs):
+            for i in range(nb):
                 self.check(self.lib.pnp_csmri_sel_from_indices(
                     self.bits_full.data_ptr() + i * self.W * hp, self.H, self.W, 1,
-                    self.support.data_ptr() + 4 * i * self.sup_stride, int(s['M0']), 0, None, 0, self.sptr))
+                    self.support.data_ptr() + 4 * i * self.sup_stride, int(self.m0_host[i]), 0, None, 0, self.sptr))
             self.mse0 = torch.zeros(nb, dtype=torch.float64, device=dev)
             self.check(self.lib.pnp_sq_err(D.ptr(self.z), D.ptr(self.xrec), N, nb, D.ptr(self.mse0), None, self.sptr))
-        self.data_range = np.array([s['data_range'] for s in specs])
+        self.data_range = np.asarray(specs['data_range'], dtype=np.float64) if on_dev else np.array([s['data_range'] for s in specs])
         self.max_slots = max_slots
         self.slots_used = 0
         self.graph = None
@@ -189,7 +243,7 @@ class BatchedSVRG:
                 self.outer += 1
         self.slots_used += n_inner
 
-    def results(self):
+    def results(self, with_z=True):
         """-> dict(z [nb][N] float64 in the reference's raveled order, psnr [slots][nb], sigma_est)"""
         self.stream.synchronize()
         n = self.slots_used
@@ -197,10 +251,11 @@ class BatchedSVRG:
         sig = self.sig_log[:n * self.nb].cpu().numpy().reshape(n, self.nb) / self.W
         with np.errstate(divide='ignore'):
             psnr = np.around(10.0 * np.log10(self.data_range[None, :] ** 2 / (mse / self.N)), 2)
-        z = self.z.reshape(self.nb, self.W, self.H).transpose(1, 2).contiguous().cpu().numpy().astype(np.float64)
+        z = (self.z.reshape(self.nb, self.W, self.H).transpose(1, 2).contiguous().cpu().numpy().astype(np.float64)
+             if with_z else np.zeros((self.nb, 0)))
         with np.errstate(divide='ignore'):
             psnr0 = np.around(10.0 * np.log10(self.data_range ** 2 / (self.mse0.cpu().numpy() / self.N)), 2)
-        return dict(z=z.reshape(self.nb, self.N), psnr=psnr, psnr_init=psnr0, sigma_est=sig)
+        return dict(z=z.reshape(self.nb, -1), psnr=psnr, psnr_init=psnr0, sigma_est=sig)
 
     def close(self):
         if self.graph:

@@ -84,12 +84,38 @@ def reconstruct(job, H=256, W=256, eta_scale=0.15, T2=10, mini_batch_size=1000, 
 
 
 def reconstruct_batch(jobs, H=256, W=256, eta_scale=0.15, T2=10, mini_batch_size=1000, iters=200, images=None,
-                      seed=0, host_threads=8):
-    """A group of same-size CSMRI jobs as ONE batched device run (pnp_svrg_b200.batched); the host-side
-    problem construction (mask, fft2) is spread over a thread pool."""
+                      seed=0, host_threads=8, construct='host'):
+    """A group of same-size CSMRI jobs as ONE batched device run (pnp_svrg_b200.batched).
+    construct='host': problems built with NumPy in the reference's draw order (thread pool);
+    construct='device': the whole batch is built on the GPU (batched.csmri_device_batch) -- the sweeps are
+    unseeded in the reference, so only the distribution of the draws matters there."""
     from concurrent.futures import ThreadPoolExecutor
-    from .batched import BatchedSVRG, csmri_host_spec
+    from .batched import BatchedSVRG, csmri_device_batch, csmri_host_spec
     from .problems.problem import load_image
+
+    def image_of(job):
+        img = images[job['image']] if images is not None and not isinstance(job['image'], str) else None
+        if img is None:
+            from PIL import Image
+            img = np.array(Image.open(job['image']).resize((H, W)))
+        return img
+    if construct == 'device':
+        t0 = time.time()
+        batch = csmri_device_batch([image_of(j) for j in jobs], [j['alpha'] for j in jobs], [j['snr'] for j in jobs], H, W,
+                                   seed=seed + jobs[0]['id'])
+        m0 = batch['m0_host']
+        B = int(min(mini_batch_size, m0.min()))
+        etas = [min(eta_scale * float(m), 3.0 * B) for m in m0]
+        run = BatchedSVRG(batch, T2=T2, mini_batch_size=B, etas=etas, seed=seed + jobs[0]['id'], max_slots=iters)
+        run.run(iters)
+        out = run.results(with_z=False)
+        run.close()
+        dt = time.time() - t0
+        return [dict(id=j['id'], image=str(j['image']), alpha=j['alpha'], snr=j['snr'], algo='pnp_svrg', denoiser='TV',
+                     psnr_init=float(out['psnr_init'][i]), psnr_final=float(out['psnr'][-1, i]), iters=iters,
+                     seconds=dt / len(jobs)) for i, j in enumerate(jobs)]
+    if construct != 'host':
+        raise ValueError("construct must be 'host' or 'device'")
 
     def spec(job):
         img = images[job['image']] if images is not None and not isinstance(job['image'], str) else None

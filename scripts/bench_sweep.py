@@ -25,6 +25,7 @@ def main():
     ap.add_argument('--iters', type=int, default=200)
     ap.add_argument('--size', type=int, default=256)
     ap.add_argument('--batch', type=int, default=28, help='reconstructions per batched launch (0 = per-problem engine)')
+    ap.add_argument('--construct', default='device', choices=['host', 'device'], help='where the problems of a batch are built')
     a = ap.parse_args()
     rank, world = int(os.environ.get('RANK', '0')), int(os.environ.get('WORLD_SIZE', '1'))
     local = int(os.environ.get('LOCAL_RANK', '0'))
@@ -43,7 +44,7 @@ def main():
         dist.barrier()
     torch.cuda.synchronize()
     def batch_runner(group):
-        return sweep.reconstruct_batch(group, H=a.size, W=a.size, iters=a.iters, images=images)
+        return sweep.reconstruct_batch(group, H=a.size, W=a.size, iters=a.iters, images=images, construct=a.construct)
     if a.batch > 0:
         batch_runner(jobs[:min(a.batch, len(jobs))])
         torch.cuda.synchronize()
@@ -61,8 +62,8 @@ def main():
         gain = float(np.mean([r['psnr_final'] - r['psnr_init'] for r in recs if 'error' not in r]))
         print(json.dumps({'metric': 'set12_sweep_reconstructions_per_s', 'value': len(recs) / dt, 'unit': 'recon/s',
                           'n_gpus': world, 'jobs': len(recs), 'failed': len(bad), 'seconds': dt, 'iters_per_recon': a.iters,
-                          'mean_psnr_gain_db': gain, 'size': a.size, 'batch': a.batch,
-                          'note': 'includes host-side problem construction (mask, fft2 measurements, uploads) per job'}))
+                          'mean_psnr_gain_db': gain, 'size': a.size, 'batch': a.batch, 'construct': a.construct,
+                          'note': 'includes the problem construction (mask, fft2 measurements, Xinit) of every job, on the %s' % a.construct}))
         if bad:
             print(bad[0], file=sys.stderr)
     if world > 1:
