@@ -50,10 +50,15 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
         "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
 
-__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
-__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+// Complex arithmetic on the packed fp32 pipe of sm_100 (add/mul/fma.rn.f32x2): FADD2 takes a negated operand,
+// FMUL2 / FFMA2 take a scalar broadcast (`.F32`), swapped halves (`.LO_HI`) and a per-half sign (`.NP`), so a complex
+// add or subtract is ONE instruction and a complex multiply TWO (SASS checked) -- half the issue slots of the
+// scalar forms, and the butterflies are what the FFT passes issue most.
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return __fadd2_rn(a, make_float2(-b.x, -b.y)); }
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
-    return make_float2(fmaf(a.x, b.x, -a.y * b.y), fmaf(a.x, b.y, a.y * b.x));
+    const float2 t = __fmul2_rn(a, make_float2(b.x, b.x));                       // (a.x b.x, a.y b.x)
+    return __ffma2_rn(make_float2(-a.y, a.x), make_float2(b.y, b.y), t);         // + (-a.y b.y, a.x b.y)
 }
 __device__ __forceinline__ float2 cswap(float2 a) { return make_float2(a.y, a.x); }
 

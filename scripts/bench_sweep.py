@@ -25,6 +25,7 @@ def main():
     ap.add_argument('--iters', type=int, default=200)
     ap.add_argument('--size', type=int, default=256)
     ap.add_argument('--batch', type=int, default=28, help='reconstructions per batched launch (0 = per-problem engine)')
+    ap.add_argument('--repeat', type=int, default=1, help='run the 840-job list this many times (fresh draws), to amortise fixed costs')
     ap.add_argument('--construct', default='device', choices=['host', 'device'], help='where the problems of a batch are built')
     a = ap.parse_args()
     rank, world = int(os.environ.get('RANK', '0')), int(os.environ.get('WORLD_SIZE', '1'))
@@ -36,6 +37,7 @@ def main():
     from pnp_svrg_b200 import sweep
     images = {i: synth_image(a.size, a.size, i) for i in range(12)}
     jobs = sweep.make_jobs(list(range(12)))[:a.jobs]
+    jobs = [dict(j, id=j['id'] + r * len(jobs)) for r in range(a.repeat) for j in jobs]
 
     def runner(job):
         return sweep.reconstruct(job, H=a.size, W=a.size, iters=a.iters, images=images)
