@@ -23,7 +23,8 @@ def build(force=False, verbose=False):
         if os.path.getmtime(OUT) >= newest:
             return OUT
     nvcc = os.environ.get('NVCC', 'nvcc')
-    cmd = [nvcc] + NVCC_FLAGS + (['-Xptxas', '-v'] if verbose else []) + ['-o', OUT, SRC]
+    extra = os.environ.get('PNP_NVCC_EXTRA', '').split()          # e.g. -DPNP_PHASE_TIMING for scripts/prof_phases.py
+    cmd = [nvcc] + NVCC_FLAGS + extra + (['-Xptxas', '-v'] if verbose else []) + ['-o', OUT, SRC]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         sys.stderr.write(r.stdout + r.stderr)

@@ -418,6 +418,16 @@ k_lines_c2r(const float2* __restrict__ S, int nlines, long long img_stride, floa
 // (prox_phase_* of prox.cuh) and only the denoised iterate is written.  Against k_lines_c2r +
 // k_prox_wavelet_fused this drops one write and one read of the iterate and a launch boundary.
 template <int L> __host__ __device__ constexpr int upd_gp() { return 512 / fft_threads<L>(); }
+__device__ unsigned long long g_upd_phase_ns[8];      // PNP_PHASE_TIMING builds only: %globaltimer at the phase boundaries of CTA 0
+__device__ __forceinline__ void upd_mark(int i) {
+#ifdef PNP_PHASE_TIMING
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        g_upd_phase_ns[i] = t;
+    }
+#endif
+}
 
 template <int L>
 __global__ void __launch_bounds__(512, 1)
@@ -448,6 +458,7 @@ k_update_prox(const float2* __restrict__ S, int nlines, float inv_n, float gscal
     const float gs = inv_n * gscale;
     const float st = step_ptr ? *step_ptr : step;
 
+    upd_mark(0);
     if (threadIdx.x == 0) {
         mbar_init(&bar, 1);
         mbar_fence_init();
@@ -456,6 +467,13 @@ k_update_prox(const float2* __restrict__ S, int nlines, float inv_n, float gscal
             for (int l = 0; l < 2 * mine; ++l)
                 bulk_g2s(lines + (long long)l * L, z_in + (first + l) * L, (unsigned)(L * sizeof(float)), &bar);
         }
+    }
+    // the operands of the later phases (mu for the update, the ground truth for the PSNR) come from DRAM: start them
+    // towards L2 now, they are first touched ~10 and ~25 us from here
+    if (threadIdx.x >= 32 && threadIdx.x < 32 + 2 * mine) {
+        const long long off = (first + (threadIdx.x - 32)) * L;
+        bulk_prefetch_l2(vadd + off, (unsigned)(L * sizeof(float)));
+        if (xrec) bulk_prefetch_l2(xrec + off, (unsigned)(L * sizeof(float)));
     }
     __syncthreads();
 
@@ -518,10 +536,16 @@ k_update_prox(const float2* __restrict__ S, int nlines, float inv_n, float gscal
         __syncthreads();                            // exchange buffers free for the next round; lines complete
     }
 
+    upd_mark(1);
     prox_phase_sigma<L>(lines, 2 * mine, first, nlines, 1, sig_log, cur_slot, scratch);
+    __syncthreads();
+    upd_mark(2);
     __threadfence();
     cooperative_groups::this_grid().sync();
+    upd_mark(3);
     prox_phase_shrink<L>(lines, 2 * mine, first, nlines, 1, z_out, xrec, sigma_modifier, fallback_sigma, sig_log, mse_log, cur_slot);
+    __syncthreads();
+    upd_mark(4);
 }
 
 // ------------------------------------------------------------------ selection bits

@@ -810,6 +810,12 @@ int pnp_cnn_forward(const pnp_cnn_net* net, const float* img, float* out, int PH
 
 int pnp_debug_set(int key, int value) {
     if (key == 1) g_tc_dbg = value;
+    if (key == 2) {                          // PNP_PHASE_TIMING builds: print the phase boundaries of the last k_update_prox
+        unsigned long long t[8];
+        CU_TRY(cudaMemcpyFromSymbol(t, pnp::g_upd_phase_ns, sizeof(t)));
+        std::fprintf(stderr, "k_update_prox CTA 0 phases (us): c2r+update %.2f  sigma %.2f  grid barrier %.2f  shrink %.2f\n",
+                     (t[1] - t[0]) * 1e-3, (t[2] - t[1]) * 1e-3, (t[3] - t[2]) * 1e-3, (t[4] - t[3]) * 1e-3);
+    }
     return PNP_OK;
 }
 

@@ -124,9 +124,10 @@ k_sigma_mad(const float* __restrict__ z, int nlines, long long img_stride, doubl
     if (lane == 0) atomicAdd(slot_ptr(sig_log, slot, batch, img), sig);
 }
 
+// sign(d) * max(|d| - thr, 0) as d - clamp(d, -thr, thr): the same value bit for bit in three instructions
+// (thr >= 0; fminf / fmaxf drop a NaN threshold, so that case still yields 0 as the compare-and-select form did)
 __device__ __forceinline__ float soft_shrink(float d, float thr) {
-    const float m = fabsf(d) - thr;
-    return m > 0.f ? copysignf(m, d) : 0.f;
+    return d - fminf(fmaxf(d, -thr), thr);
 }
 
 struct ShrinkParams {
@@ -238,10 +239,15 @@ k_haar_bayes(const float* __restrict__ zin, float* __restrict__ zout, const floa
             ss[l] = t;
         }
     }
+    {   // lane l computes the threshold of level l (one division + root per lane instead of LEVELS), then broadcast
+        float mine_ss = ss[0];
 #pragma unroll
-    for (int l = 0; l < LEVELS; ++l) {
-        const float dvar = ss[l] / (float)(L >> (l + 1));
-        thr[l] = var / sqrtf(fmaxf(dvar - var, 2.220446049250313e-16f));
+        for (int l = 1; l < LEVELS; ++l) mine_ss = lane == l ? ss[l] : mine_ss;
+        const int lv = lane < LEVELS ? lane : 0;
+        const float dvar = mine_ss / (float)(L >> (lv + 1));
+        const float tk = var / sqrtf(fmaxf(dvar - var, 2.220446049250313e-16f));
+#pragma unroll
+        for (int l = 0; l < LEVELS; ++l) thr[l] = __shfl_sync(0xffffffffu, tk, l);
     }
 
     // inverse pyramid with soft-thresholded details
@@ -379,6 +385,97 @@ __device__ __forceinline__ void prox_phase_sigma(const float* lines, int mine, l
     }
 }
 
+// ---- 512-sample sub-block in the chunk-cyclic register layout --------------------------------------------------
+// Lane l holds the four float4 chunks f = c*32 + l (c < 4) of the sub-block, i.e. samples 4f .. 4f+3: every load and
+// store of the warp is one contiguous 512-byte row (no shared-memory bank conflicts, fully coalesced global
+// accesses; 16 consecutive samples per lane would be a 16-way conflict per scalar load).  Levels 1-2 stay inside a
+// chunk, levels 3-7 are xor butterflies between lanes (four independent chains), the remaining one or two levels
+// combine the four chunk tops inside a lane.
+template <int LEVELS> struct HaarCC {
+    static constexpr int XC = LEVELS - 2 < 5 ? LEVELS - 2 : 5;     // cross-lane levels
+    static constexpr int TL = LEVELS - 2 - XC;                     // levels above them (0, 1 or 2)
+};
+
+template <int LEVELS>
+__device__ __forceinline__ void haar_cc_forward(float (&x)[4][4], float (&A)[4][6], float (&D)[4][5], float (&T)[4],
+                                                float (&ss)[LEVELS], int lane) {
+    using H = HaarCC<LEVELS>;
+    constexpr float RS2 = 0.70710678118654752f;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        const float a0 = (x[c][0] + x[c][1]) * RS2, d0 = (x[c][0] - x[c][1]) * RS2;
+        const float a1 = (x[c][2] + x[c][3]) * RS2, d1 = (x[c][2] - x[c][3]) * RS2;
+        ss[0] = fmaf(d0, d0, fmaf(d1, d1, ss[0]));
+        const float dd = (a0 - a1) * RS2;
+        ss[1] = fmaf(dd, dd, ss[1]);
+        x[c][1] = d0; x[c][3] = d1; x[c][2] = dd;                  // details stay where the inverse expects them
+        A[c][0] = (a0 + a1) * RS2;
+#pragma unroll
+        for (int q = 0; q < H::XC; ++q) {
+            const float p = __shfl_xor_sync(0xffffffffu, A[c][q], 1 << q);
+            const bool ev = (lane & (1 << q)) == 0;
+            A[c][q + 1] = (A[c][q] + p) * RS2;
+            D[c][q] = (ev ? (A[c][q] - p) : (p - A[c][q])) * RS2;
+            if ((lane & ((2 << q) - 1)) == 0) ss[2 + q] = fmaf(D[c][q], D[c][q], ss[2 + q]);
+        }
+    }
+    if (H::TL >= 1) {                                              // chunks (0,1) and (2,3) are adjacent 128-sample blocks
+        const float t0 = A[0][H::XC], t1 = A[1][H::XC], t2 = A[2][H::XC], t3 = A[3][H::XC];
+        T[0] = (t0 - t1) * RS2;
+        T[1] = (t2 - t3) * RS2;
+        const float u0 = (t0 + t1) * RS2, u1 = (t2 + t3) * RS2;
+        if (lane == 0) ss[2 + H::XC] = fmaf(T[0], T[0], fmaf(T[1], T[1], ss[2 + H::XC]));
+        T[2] = u0;
+        T[3] = u1;
+        if (H::TL >= 2) {
+            const float dd = (u0 - u1) * RS2;
+            if (lane == 0) ss[3 + H::XC] = fmaf(dd, dd, ss[3 + H::XC]);
+            T[2] = (u0 + u1) * RS2;                                 // top approximation
+            T[3] = dd;
+        }
+    }
+}
+
+template <int LEVELS>
+__device__ __forceinline__ void haar_cc_inverse(float (&x)[4][4], float (&A)[4][6], const float (&D)[4][5], const float (&T)[4],
+                                                const float (&thr)[LEVELS], int lane) {
+    using H = HaarCC<LEVELS>;
+    constexpr float RS2 = 0.70710678118654752f;
+    if (H::TL >= 1) {
+        float u0 = T[2], u1 = T[3];
+        if (H::TL >= 2) {
+            const float dd = soft_shrink(T[3], thr[3 + H::XC]);
+            u0 = (T[2] + dd) * RS2;
+            u1 = (T[2] - dd) * RS2;
+        }
+        const float e0 = soft_shrink(T[0], thr[2 + H::XC]), e1 = soft_shrink(T[1], thr[2 + H::XC]);
+        A[0][H::XC] = (u0 + e0) * RS2;
+        A[1][H::XC] = (u0 - e0) * RS2;
+        A[2][H::XC] = (u1 + e1) * RS2;
+        A[3][H::XC] = (u1 - e1) * RS2;
+    }
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+#pragma unroll
+        for (int q = H::XC - 1; q >= 0; --q) {
+            const float d = soft_shrink(D[c][q], thr[2 + q]);
+            const bool ev = (lane & (1 << q)) == 0;
+            A[c][q] = (ev ? (A[c][q + 1] + d) : (A[c][q + 1] - d)) * RS2;
+        }
+        const float dd = soft_shrink(x[c][2], thr[1]);
+        const float a0 = (A[c][0] + dd) * RS2, a1 = (A[c][0] - dd) * RS2;
+        const float d0 = soft_shrink(x[c][1], thr[0]), d1 = soft_shrink(x[c][3], thr[0]);
+        x[c][0] = (a0 + d0) * RS2; x[c][1] = (a0 - d0) * RS2;
+        x[c][2] = (a1 + d1) * RS2; x[c][3] = (a1 - d1) * RS2;
+    }
+}
+
+// Lines of >= 512 samples: the 512-sample sub-blocks of all resident lines are independent tasks spread over the 16
+// warps (no lock step between warps): pass A transforms every sub-block for its per-level detail energies, one CTA
+// barrier, pass B transforms again, shrinks with the line's thresholds, inverts and streams out.  Shorter lines: one
+// warp per line, a single pass.
+#define PROX_MAX_TASKS 112          // sub-blocks per CTA: 200 KiB of lines / 2 KiB
+
 template <int L>
 __device__ __forceinline__ void prox_phase_shrink(const float* lines, int mine, long long first, int nlines, int batch,
                                                   float* __restrict__ zout, const float* __restrict__ xrec,
@@ -390,32 +487,7 @@ __device__ __forceinline__ void prox_phase_shrink(const float* lines, int mine, 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float err_acc = 0.f;
     int err_img = -1;
-    for (int l = warp; l < (int)mine; l += 16) {
-        const long long gl = first + l;
-        const int img = (int)(gl / nlines);
-        const double se = __ldcg(sig_log + (long long)cur_slot * batch + img) / (double)nlines;
-        const float sigma = (se > 0.0) ? (float)(se * (double)sigma_modifier) : fallback_sigma;
-        const float var = sigma * sigma;
-        const float* src = lines + (long long)l * L;
-        float ss[LEVELS];
-#pragma unroll
-        for (int k = 0; k < LEVELS; ++k) ss[k] = 0.f;
-        // pass A: per-level detail energies of the whole line
-#pragma unroll 1
-        for (int sbk = 0; sbk < NSB; ++sbk) {
-            float x[VPL], A[XL + 1], Dx[XL];
-            const float* s0 = src + sbk * SB + lane * VPL;
-#pragma unroll
-            for (int i = 0; i < VPL; ++i) x[i] = s0[i];
-            haar_sub_forward<L>(x, A, Dx, ss, lane);
-        }
-        float thr[LEVELS];
-#pragma unroll
-        for (int k = 0; k < LEVELS; ++k) {
-            const float dvar = warp_sum_f(ss[k]) / (float)(L >> (k + 1));
-            thr[k] = var / sqrtf(fmaxf(dvar - var, 2.220446049250313e-16f));
-        }
-        // pass B: forward again, shrink, inverse, stream out
+    auto flush_err = [&](int img) {
         if (err_img != img) {
             if (err_img >= 0 && xrec && mse_log) {
                 const float e = warp_sum_f(err_acc);
@@ -424,29 +496,93 @@ __device__ __forceinline__ void prox_phase_shrink(const float* lines, int mine, 
             err_acc = 0.f;
             err_img = img;
         }
-#pragma unroll 1
-        for (int sbk = 0; sbk < NSB; ++sbk) {
-            float x[VPL], A[XL + 1], Dx[XL], dummy[LEVELS];
-            const long long goff = gl * L + sbk * SB + lane * VPL;
-            float xr[VPL];
-            if (xrec) {
-                if (VPL >= 4) {
+    };
+    auto sigma_var = [&](int img) {
+        const double se = __ldcg(sig_log + (long long)cur_slot * batch + img) / (double)nlines;
+        const float sigma = (se > 0.0) ? (float)(se * (double)sigma_modifier) : fallback_sigma;
+        return sigma * sigma;
+    };
+    if constexpr (SB == 512) {
+        __shared__ float s_ss[PROX_MAX_TASKS][LEVELS];
+        const int tasks = mine * NSB;
+        for (int t = warp; t < tasks; t += 16) {                                   // pass A: energies
+            const float4* s4 = reinterpret_cast<const float4*>(lines + (long long)t * SB);
+            float x[4][4], A[4][6], D[4][5], T[4], ss[LEVELS];
 #pragma unroll
-                    for (int i = 0; i < VPL / 4; ++i) {
-                        const float4 r = reinterpret_cast<const float4*>(xrec + goff)[i];
-                        xr[4 * i] = r.x; xr[4 * i + 1] = r.y; xr[4 * i + 2] = r.z; xr[4 * i + 3] = r.w;
-                    }
-                } else {
+            for (int c = 0; c < 4; ++c) {
+                const float4 q = s4[c * 32 + lane];
+                x[c][0] = q.x; x[c][1] = q.y; x[c][2] = q.z; x[c][3] = q.w;
+            }
 #pragma unroll
-                    for (int i = 0; i < VPL; ++i) xr[i] = xrec[goff + i];
+            for (int k = 0; k < LEVELS; ++k) ss[k] = 0.f;
+            haar_cc_forward<LEVELS>(x, A, D, T, ss, lane);
+#pragma unroll
+            for (int k = 0; k < LEVELS; ++k) {
+                const float e = warp_sum_f(ss[k]);
+                if (lane == 0) s_ss[t][k] = e;
+            }
+        }
+        __syncthreads();
+        for (int t = warp; t < tasks; t += 16) {                                   // pass B: shrink
+            const int l = t / NSB;
+            const long long gl = first + l;
+            const int img = (int)(gl / nlines);
+            const long long gbase = first * L + (long long)t * SB;                 // sub-blocks are contiguous in memory
+            const float4* s4 = reinterpret_cast<const float4*>(lines + (long long)t * SB);
+            float x[4][4], xr[4][4], A[4][6], D[4][5], T[4], dummy[LEVELS], thr[LEVELS];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                if (xrec) {                                                        // latency hides behind the transform
+                    const float4 r = reinterpret_cast<const float4*>(xrec + gbase)[c * 32 + lane];
+                    xr[c][0] = r.x; xr[c][1] = r.y; xr[c][2] = r.z; xr[c][3] = r.w;
+                }
+                const float4 q = s4[c * 32 + lane];
+                x[c][0] = q.x; x[c][1] = q.y; x[c][2] = q.z; x[c][3] = q.w;
+            }
+            const float var = sigma_var(img);
+            {   // lane k computes the threshold of level k, then it is broadcast (not 32 lanes x 8 divisions and roots)
+                const int k = lane < LEVELS ? lane : LEVELS - 1;
+                float e = 0.f;
+#pragma unroll
+                for (int w = 0; w < NSB; ++w) e += s_ss[l * NSB + w][k];
+                const float dvar = e / (float)(L >> (k + 1));
+                const float tk = var / sqrtf(fmaxf(dvar - var, 2.220446049250313e-16f));
+#pragma unroll
+                for (int kk = 0; kk < LEVELS; ++kk) { thr[kk] = __shfl_sync(0xffffffffu, tk, kk); dummy[kk] = 0.f; }
+            }
+            haar_cc_forward<LEVELS>(x, A, D, T, dummy, lane);
+            haar_cc_inverse<LEVELS>(x, A, D, T, thr, lane);
+            flush_err(img);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                reinterpret_cast<float4*>(zout + gbase)[c * 32 + lane] = make_float4(x[c][0], x[c][1], x[c][2], x[c][3]);
+                if (xrec) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) { const float e = x[c][j] - xr[c][j]; err_acc = fmaf(e, e, err_acc); }
                 }
             }
-            const float* s0 = src + sbk * SB + lane * VPL;
+        }
+    } else {
+        for (int l = warp; l < mine; l += 16) {
+            const long long gl = first + l;
+            const int img = (int)(gl / nlines);
+            const long long goff = gl * L + lane * VPL;
+            float x[VPL], xr[VPL], A[XL + 1], Dx[XL], ss[LEVELS], thr[LEVELS];
+            const float* s0 = lines + (long long)l * L + lane * VPL;
 #pragma unroll
-            for (int i = 0; i < VPL; ++i) x[i] = s0[i];
+            for (int i = 0; i < VPL; ++i) {
+                x[i] = s0[i];
+                if (xrec) xr[i] = xrec[goff + i];
+            }
 #pragma unroll
-            for (int k = 0; k < LEVELS; ++k) dummy[k] = 0.f;
-            haar_sub_forward<L>(x, A, Dx, dummy, lane);
+            for (int k = 0; k < LEVELS; ++k) ss[k] = 0.f;
+            haar_sub_forward<L>(x, A, Dx, ss, lane);
+            const float var = sigma_var(img);
+#pragma unroll
+            for (int k = 0; k < LEVELS; ++k) {
+                const float dvar = warp_sum_f(ss[k]) / (float)(L >> (k + 1));
+                thr[k] = var / sqrtf(fmaxf(dvar - var, 2.220446049250313e-16f));
+            }
 #pragma unroll
             for (int q = XL - 1; q >= 0; --q) {
                 const float d = soft_shrink(Dx[q], thr[LIN + q]);
@@ -465,17 +601,11 @@ __device__ __forceinline__ void prox_phase_shrink(const float* lines, int mine, 
                     x[i * stride + half] = (a - d) * RS2;
                 }
             }
-            if (VPL >= 4) {
+            flush_err(img);
 #pragma unroll
-                for (int i = 0; i < VPL / 4; ++i)
-                    reinterpret_cast<float4*>(zout + goff)[i] = make_float4(x[4 * i], x[4 * i + 1], x[4 * i + 2], x[4 * i + 3]);
-            } else {
-#pragma unroll
-                for (int i = 0; i < VPL; ++i) zout[goff + i] = x[i];
-            }
-            if (xrec) {
-#pragma unroll
-                for (int i = 0; i < VPL; ++i) { const float e = x[i] - xr[i]; err_acc = fmaf(e, e, err_acc); }
+            for (int i = 0; i < VPL; ++i) {
+                zout[goff + i] = x[i];
+                if (xrec) { const float e = x[i] - xr[i]; err_acc = fmaf(e, e, err_acc); }
             }
         }
     }
