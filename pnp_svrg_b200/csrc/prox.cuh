@@ -44,13 +44,20 @@ __device__ __forceinline__ double line_sigma_mad(const float* __restrict__ x, in
         const int o = lane + 32 * i;
         a[i] = 0xffffffffu;
         if (o < NO) {
-            int i0 = 2 * o + 1, i1 = 2 * o, i2 = 2 * o - 1, i3 = 2 * o - 2;
-            // half-sample symmetric extension
-            i0 = i0 >= L ? 2 * L - 1 - i0 : i0;
-            i1 = i1 >= L ? 2 * L - 1 - i1 : i1;
-            i2 = i2 < 0 ? -1 - i2 : (i2 >= L ? 2 * L - 1 - i2 : i2);
-            i3 = i3 < 0 ? -1 - i3 : (i3 >= L ? 2 * L - 1 - i3 : i3);
-            const float d = fmaf(h0, x[i0], fmaf(h1, x[i1], fmaf(h2, x[i2], h3 * x[i3])));
+            float d;
+            if (i > 0 && 32 * i + 31 <= (L - 2) / 2) {
+                // interior (compile-time test): samples 2o-2 .. 2o+1 are in range, two aligned 8-byte loads
+                const float2 lo = *reinterpret_cast<const float2*>(x + 2 * o - 2), hi = *reinterpret_cast<const float2*>(x + 2 * o);
+                d = fmaf(h0, hi.y, fmaf(h1, hi.x, fmaf(h2, lo.y, h3 * lo.x)));
+            } else {
+                int i0 = 2 * o + 1, i1 = 2 * o, i2 = 2 * o - 1, i3 = 2 * o - 2;
+                // half-sample symmetric extension
+                i0 = i0 >= L ? 2 * L - 1 - i0 : i0;
+                i1 = i1 >= L ? 2 * L - 1 - i1 : i1;
+                i2 = i2 < 0 ? -1 - i2 : (i2 >= L ? 2 * L - 1 - i2 : i2);
+                i3 = i3 < 0 ? -1 - i3 : (i3 >= L ? 2 * L - 1 - i3 : i3);
+                d = fmaf(h0, x[i0], fmaf(h1, x[i1], fmaf(h2, x[i2], h3 * x[i3])));
+            }
             if (d != 0.f) { a[i] = __float_as_uint(fabsf(d)); ++nnz; }
         }
     }
