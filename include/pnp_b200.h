@@ -130,6 +130,9 @@ typedef struct {
     float* v_out;
     const float* z_in;
     float* z_out;
+    int ntaps;                    /* > 0 (<= 16): the blur kernel has this many non-zero entries -> both convolutions */
+    const int* tap_pos;           /* run as direct tap sums (HOST arrays: raveled positions p of B and the weights  */
+    const float* tap_w;           /* B[p]*sqrt(N)); Bf / twn / S are then unused.  0: FFT path.                      */
 } pnp_deblur_grad_args;
 int pnp_deblur_grad(const pnp_deblur_grad_args* args, void* stream);
 

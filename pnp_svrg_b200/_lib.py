@@ -37,6 +37,7 @@ class DeblurGradArgs(C.Structure):
         ('identity', C.c_int), ('M', C.c_int), ('sel', C.c_void_p), ('count', C.c_int), ('cursor', C.c_void_p),
         ('use_y', C.c_int), ('gscale', C.c_float), ('step', C.c_float), ('step_ptr', C.c_void_p),
         ('g_out', C.c_void_p), ('vadd', C.c_void_p), ('v_out', C.c_void_p), ('z_in', C.c_void_p), ('z_out', C.c_void_p),
+        ('ntaps', C.c_int), ('tap_pos', C.c_void_p), ('tap_w', C.c_void_p),
     ]
 
 

@@ -114,4 +114,42 @@ k_bilinear_residual(const float* __restrict__ x, float* __restrict__ up, const f
     }
 }
 
+// ---- direct path for blur kernels with a handful of taps (SURVEY section 8(a'): "Minimal" has 4, "Identity" 1) ----
+// fft_blur(m, B)[n] = sqrt(N) * sum_p B[p] m[(n - p) mod N] on the RAVELED image (problems/DeblurSR.py:119-120), so a
+// tap at raveled position p = pr*W + pc shifts by pr rows and pc columns with a borrow into the row index -- the
+// helical boundary the FFT path reproduces.  dir = +1: the blur; dir = -1: its adjoint (kernel roll(flip(B), 1),
+// DeblurSR.py:132,147), i.e. m[(n + p) mod N].  Images are in the transposed line layout (element (r, c) at
+// c*H + r).  The adjoint call carries the variance-reduction epilogue of the gradient.
+#define PNP_MAX_TAPS 16
+struct TapList {
+    int n;
+    int pr[PNP_MAX_TAPS], pc[PNP_MAX_TAPS];
+    float w[PNP_MAX_TAPS];                         // B[p] * sqrt(N)
+};
+
+__global__ void __launch_bounds__(256)
+k_tap_conv(const float* __restrict__ a, const float* __restrict__ b, int H, int W, TapList taps, int dir, float gscale,
+           float step, const float* __restrict__ step_ptr, float* __restrict__ g_out, const float* __restrict__ vadd,
+           float* __restrict__ v_out, const float* __restrict__ z_in, float* __restrict__ z_out) {
+    const long long N = (long long)H * W;
+    const float st = step_ptr ? *step_ptr : step;
+    for (long long d = (long long)blockIdx.x * blockDim.x + threadIdx.x; d < N; d += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(d / H), r = (int)(d - (long long)c * H);
+        float acc = 0.f;
+        for (int j = 0; j < taps.n; ++j) {
+            int cc = c - dir * taps.pc[j], rr = r - dir * taps.pr[j];
+            if (cc < 0) { cc += W; rr -= 1; }          // borrow / carry between the raveled rows
+            if (cc >= W) { cc -= W; rr += 1; }
+            rr = rr < 0 ? rr + H : (rr >= H ? rr - H : rr);
+            const long long s = (long long)cc * H + rr;
+            acc = fmaf(taps.w[j], b ? a[s] - b[s] : a[s], acc);
+        }
+        const float g = acc * gscale;
+        if (g_out) g_out[d] = g;
+        const float v = vadd ? g + vadd[d] : g;
+        if (v_out) v_out[d] = v;
+        if (z_out) z_out[d] = z_in[d] - st * v;
+    }
+}
+
 }  // namespace pnp

@@ -551,7 +551,8 @@ int pnp_deblur_grad(const pnp_deblur_grad_args* args, void* stream) {
     const pnp_deblur_grad_args& a = *args;
     if (!pow2_ok(a.H) || !pow2_ok(a.W)) return fail(PNP_ERR_ARG, "H=%d W=%d must be powers of two in [32, 4096]", a.H, a.W);
     if (a.batch != 1) return fail(PNP_ERR_ARG, "pnp_deblur_grad: batch must be 1 in this revision");
-    if (!a.a || !a.S || !a.blurred || !a.up || !a.Bf || !a.twn || !a.y) return fail(PNP_ERR_ARG, "null pointer");
+    if (!a.a || !a.blurred || !a.up || !a.y) return fail(PNP_ERR_ARG, "null pointer");
+    if (a.ntaps <= 0 && (!a.S || !a.Bf || !a.twn)) return fail(PNP_ERR_ARG, "null pointer (FFT path needs S, Bf, twn)");
     if (!a.identity && (!a.tl || !a.wts)) return fail(PNP_ERR_ARG, "bilinear tables missing");
     if (a.z_out && !a.z_in) return fail(PNP_ERR_ARG, "z_out needs z_in");
     int rc = check_init();
@@ -560,12 +561,30 @@ int pnp_deblur_grad(const pnp_deblur_grad_args* args, void* stream) {
     const long long N = (long long)a.H * a.W;
     pnp_csmri_grad_args f{};
     f.H = a.H; f.W = a.W; f.batch = 1; f.S = a.S;
+    const bool direct = a.ntaps > 0;
+    pnp::TapList taps{};
+    if (direct) {
+        if (a.ntaps > PNP_MAX_TAPS || !a.tap_pos || !a.tap_w) return fail(PNP_ERR_ARG, "ntaps must be <= %d with both tap arrays", PNP_MAX_TAPS);
+        taps.n = a.ntaps;
+        for (int j = 0; j < a.ntaps; ++j) {
+            if (a.tap_pos[j] < 0 || a.tap_pos[j] >= N) return fail(PNP_ERR_ARG, "tap position out of range");
+            taps.pr[j] = a.tap_pos[j] / a.W;
+            taps.pc[j] = a.tap_pos[j] % a.W;
+            taps.w[j] = a.tap_w[j];
+        }
+    }
     // x = fft_blur(a - b, B)
-    f.a = a.a; f.b = a.b; f.gscale = 1.0f; f.g_out = a.blurred;
-    if ((rc = dispatch_r2c(a.H, f, st)) != PNP_OK) return rc;
-    if ((rc = dispatch_conv(a.W, reinterpret_cast<float2*>(a.S), reinterpret_cast<const float2*>(a.Bf),
-                            reinterpret_cast<const float2*>(a.twn), a.H, 1, 0, st)) != PNP_OK) return rc;
-    if ((rc = dispatch_c2r(a.H, f, st)) != PNP_OK) return rc;
+    if (direct) {
+        pnp::k_tap_conv<<<ew_blocks(N, 1), 256, 0, st>>>(a.a, a.b, a.H, a.W, taps, 1, 1.0f, 0.f, nullptr, a.blurred, nullptr, nullptr,
+                                                         nullptr, nullptr);
+        LAUNCH_CHECK();
+    } else {
+        f.a = a.a; f.b = a.b; f.gscale = 1.0f; f.g_out = a.blurred;
+        if ((rc = dispatch_r2c(a.H, f, st)) != PNP_OK) return rc;
+        if ((rc = dispatch_conv(a.W, reinterpret_cast<float2*>(a.S), reinterpret_cast<const float2*>(a.Bf),
+                                reinterpret_cast<const float2*>(a.twn), a.H, 1, 0, st)) != PNP_OK) return rc;
+        if ((rc = dispatch_c2r(a.H, f, st)) != PNP_OK) return rc;
+    }
     // up = S^T (S x - y) on the selection
     CU_TRY(cudaMemsetAsync(a.up, 0, sizeof(float) * (size_t)N, st));
     const int count = a.sel ? a.count : a.M;
@@ -577,6 +596,12 @@ int pnp_deblur_grad(const pnp_deblur_grad_args* args, void* stream) {
         LAUNCH_CHECK();
     }
     // g = fft_blur(up, roll(flip(B), 1)) -> epilogue
+    if (direct) {
+        pnp::k_tap_conv<<<ew_blocks(N, 1), 256, 0, st>>>(a.up, nullptr, a.H, a.W, taps, -1, a.gscale, a.step, a.step_ptr, a.g_out,
+                                                         a.vadd, a.v_out, a.z_in, a.z_out);
+        LAUNCH_CHECK();
+        return PNP_OK;
+    }
     f.a = a.up; f.b = nullptr; f.gscale = a.gscale; f.step = a.step; f.step_ptr = a.step_ptr;
     f.g_out = a.g_out; f.vadd = a.vadd; f.v_out = a.v_out; f.z_in = a.z_in; f.z_out = a.z_out;
     if ((rc = dispatch_r2c(a.H, f, st)) != PNP_OK) return rc;

@@ -58,8 +58,11 @@ class _HostSampler:
 
 class Deblur(Problem):
     def __init__(self, img_path=None, H=64, W=64, kernel_path=None, kernel=None, scale_percent=50,
-                 snr=None, sigma=None, *, image=None):
+                 snr=None, sigma=None, *, image=None, conv='auto'):
         super().__init__(img_path, H, W, image=image)
+        if conv not in ('auto', 'fft', 'direct'):
+            raise ValueError("conv must be 'auto', 'fft' or 'direct'")
+        self.conv = conv          # additive: 'direct' = tap sums for kernels with <= 16 non-zero entries (SURVEY 8(a'))
         self.pname = 'deblur'
         self.scale_percent = scale_percent
         self.snr = snr
@@ -144,6 +147,12 @@ class Deblur(Problem):
             wts = np.stack([self.Bop.wr, self.Bop.wc], axis=1).astype(np.float32)
             self._tl = torch.from_numpy(np.ascontiguousarray(tl)).to(dev)
             self._wts = torch.from_numpy(np.ascontiguousarray(wts)).to(dev)
+        taps = np.flatnonzero(self.B)
+        if self.conv == 'direct' and taps.size > 16:
+            raise ValueError("conv='direct' needs a blur kernel with at most 16 non-zero entries (this one has %d)" % taps.size)
+        self._direct = self.conv != 'fft' and 0 < taps.size <= 16
+        self._tap_pos = np.ascontiguousarray(taps, dtype=np.int32)
+        self._tap_w = np.ascontiguousarray(self.B[taps] * np.sqrt(N), dtype=np.float32)
         self._S = torch.empty(N, dtype=torch.float32, device=dev)
         self._blurred = torch.empty(N, dtype=torch.float32, device=dev)
         self._up = torch.empty(N, dtype=torch.float32, device=dev)
@@ -167,7 +176,10 @@ class Deblur(Problem):
             wts=D.ptr(self._wts), identity=int(self._identity), M=int(self.M), sel=D.ptr(sel),
             count=0 if sel is None else int(sel.numel()), cursor=None, use_y=int(bool(with_y) and b is None),
             gscale=float(gscale), step=float(step), step_ptr=D.ptr(step_ptr), g_out=D.ptr(g_out), vadd=D.ptr(vadd),
-            v_out=D.ptr(v_out), z_in=D.ptr(z_in), z_out=D.ptr(z_out))
+            v_out=D.ptr(v_out), z_in=D.ptr(z_in), z_out=D.ptr(z_out),
+            ntaps=int(self._tap_pos.size) if self._direct else 0,
+            tap_pos=self._tap_pos.ctypes.data if self._direct else None,
+            tap_w=self._tap_w.ctypes.data if self._direct else None)
         _lib.check(_lib.load().pnp_deblur_grad(C.byref(args), D.stream()))
 
     # ---- reference API -----------------------------------------------------------------------

@@ -254,3 +254,34 @@ def test_cdp_loops(cuda, algo, kw):
     got = getattr(ALG, algo)(dut, TVDenoiser(), eta=eta, tt=1e9, max_iters=9, converge_check=False, verbose=False, **kw)
     assert rel_l2(got['z'], want['z']) < 1e-4, rel_l2(got['z'], want['z'])
     assert abs(got['psnr_per_iter'][-1] - want['psnr_per_iter'][-1]) <= 0.05
+
+
+@pytest.mark.parametrize('kernel', ['Minimal', 'Identity', 'sparse'])
+def test_deblur_direct_taps_match_fft_path(cuda, kernel):
+    """Additive conv='direct' (tap sums, SURVEY 8(a')) against the four-step FFT convolution and the oracle."""
+    from oracle.problems_port import DeblurPort
+    from pnp_svrg_b200.problems import Deblur
+    H = 64
+    img = synth_image(H, H, 3)
+    if kernel == 'sparse':                                  # taps that wrap around rows and around the whole image
+        k = np.zeros((H, H))
+        k[0, 0], k[0, H - 1], k[H - 1, H - 1], k[H - 1, 0], k[17, 5], k[40, 63] = 3, 2, 5, 1, 4, 2
+        kd = kp = dict(kernel=k)
+    else:
+        kd = kp = dict(kernel=kernel)
+    kw = dict(H=H, W=H, scale_percent=50, snr=25.)
+    np.random.seed(3)
+    ref = DeblurPort(img, **kw, **({'kernel_path': kp['kernel']} if kernel == 'sparse' else kp))
+    np.random.seed(3)
+    a = Deblur(image=img, conv='direct', **kw, **kd)
+    np.random.seed(3)
+    b = Deblur(image=img, conv='fft', **kw, **kd)
+    assert a._direct and not b._direct
+    z = np.random.default_rng(0).random(H * H)
+    ga, gb, gr = a.grad_full(z), b.grad_full(z), ref.grad_full(z)
+    assert rel_l2(ga, gr) < 5e-6 and rel_l2(gb, gr) < 5e-6 and rel_l2(ga, gb) < 5e-6
+    np.random.seed(4)
+    mb = a.select_mb(150)
+    assert rel_l2(a.grad_stoch(z, mb), ref.grad_stoch(z, np.asarray(mb))) < 5e-6
+    with pytest.raises(ValueError):
+        Deblur(image=img, conv='direct', kernel=np.ones((H, H)), **kw)
