@@ -108,3 +108,15 @@ def test_reference_names_alias():
             sys.modules.pop(k, None)
             if v is not None:
                 sys.modules[k] = v
+
+
+def test_integration_stub_mirrors_the_struct():
+    """INTEGRATION.md shows the ctypes stub a reference maintainer would add: its GradArgs must list the
+    fields of pnp_csmri_grad_args in order (a missing trailing field would make the library read garbage)."""
+    import os
+    import re
+    from pnp_svrg_b200 import _lib
+    text = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'INTEGRATION.md')).read()
+    block = text[text.index('class GradArgs(C.Structure)'):text.index('lib.pnp_init.restype')]
+    names = re.findall(r"\('(\w+)',", block)
+    assert names == [f[0] for f in _lib.CsmriGradArgs._fields_]
