@@ -204,7 +204,8 @@ class Epoch:
                   z_in=eng.z, z_out=eng.z, clear_sel=True)
         tail = lambda: FUSED_TAIL and p._dev_update_prox(
             1.0 / B, eng.step, self.mu, eng.z, eng.z, eng.sig_log, self.den.sigma_modifier,
-            self.den.denoise_strength * self.den.decay ** (self.den.t + 1), p._xrec_dev, eng.mse_log, eng.slot_ptr)
+            self.den.denoise_strength * self.den.decay ** (self.den.t + 1), p._xrec_dev, eng.mse_log, eng.slot_ptr,
+            advance=eng.counters, n_advance=3)
         if hook is None:
             # the minibatch selection only feeds the column pass: draw it on a parallel graph branch
             eng.fork(eng.sample_sel_device, lambda: p._dev_grad(eng.z, phases=1, **gk))
@@ -229,7 +230,8 @@ class Epoch:
             eng.check(eng.lib.pnp_estimate_sigma(self.D.ptr(eng.z), eng.H, eng.W, 1, self.D.ptr(eng.sig_log),
                                                  self.D.ptr(eng.slot_ptr), eng.sptr)); h('sigma_mad')
             self.den._dev_denoise(self._ctx()); h('haar_bayes+psnr')
-        eng.advance(); h('advance')
+        if not fused:                                      # the fused tail bumps the iteration counters itself
+            eng.advance(); h('advance')
 
     def _ctx(self):
         from pnp_svrg_b200.engine import ProxCtx
@@ -265,7 +267,7 @@ class Epoch:
 
 FUSED_TAIL = os.environ.get('PNP_BENCH_FUSED_TAIL', '1') == '1'      # pass 3 + update + sigma + wavelet + PSNR as one cooperative launch
 FUSED_PROX = os.environ.get('PNP_BENCH_FUSED_PROX', '1') == '1'    # sigma + wavelet + PSNR as one cooperative launch
-LAUNCHES_PER_INNER = 7 - int(FUSED_PROX) - int(FUSED_TAIL and FUSED_PROX)   # sel_sample + r2c + cols + c2r + sigma_mad + haar_bayes + advance
+LAUNCHES_PER_INNER = 7 - int(FUSED_PROX) - 2 * int(FUSED_TAIL and FUSED_PROX)   # sel_sample + r2c + cols + c2r + sigma_mad + haar_bayes + advance
 LAUNCHES_PER_SNAPSHOT = 4     # r2c + cols + c2r + D2D copy
 
 

@@ -222,10 +222,13 @@ int pnp_prox_wavelet_fused(const float* z_in, float* z_out, int H, int W, int ba
  * of the spectrum S that passes 1 and 2 left, phases = 3) + update z = z_in - step*(g*gscale + vadd) + sigma
  * estimate + wavelet BayesShrink + PSNR, with the iterate resident in shared memory in between (replaces
  * pnp_csmri_grad(phases = 4) followed by pnp_prox_wavelet_fused; same results).  batch 1.  Returns
- * PNP_ERR_UNSUPPORTED when the image lines do not fit the SMs' shared memory -- use the two calls then. */
+ * PNP_ERR_UNSUPPORTED when the image lines do not fit the SMs' shared memory -- use the two calls then.
+ * advance_counters (optional): the first n_advance ints are incremented at the end, as pnp_advance would (`slot`
+ * may be one of them: it is read before). */
 int pnp_csmri_update_prox(const float* S, int H, int W, float gscale, float step, const float* step_ptr, const float* vadd,
                           const float* z_in, float* z_out, double* sig_log, float sigma_modifier, float fallback_sigma,
-                          const float* xrec, double* mse_log, const int* slot, void* stream);
+                          const float* xrec, double* mse_log, const int* slot, int* advance_counters, int n_advance,
+                          void* stream);
 
 /* TV prox by Chambolle's dual projection, ADDITIVE mode (TVDenoiser(method='chambolle')): the north star's
  * "TV (Chambolle)" kernel; no counterpart in the reference, whose TVDenoiser is the wavelet shrink above

@@ -24,10 +24,11 @@ def _grad_update(eng, a, b, sel, with_y, gscale, **kw):
     eng.p._dev_grad(a, b=b, sel=sel, with_y=with_y, gscale=gscale, clear_sel=sel is not None and sel is eng.sel, **kw)
 
 
-def _grad_update_prox(eng, a, b, sel, gscale, vadd, z):
+def _grad_update_prox(eng, a, b, sel, gscale, vadd, z, advance=0):
     """z <- prox(z - step * (g_sel(a - b) * gscale + vadd)).  CSMRI + wavelet prox: the inverse line pass, the update,
     the sigma estimate and the prox run as ONE cooperative launch on lines resident in shared memory
-    (pnp_csmri_update_prox); otherwise the gradient pass followed by ``eng.prox``."""
+    (pnp_csmri_update_prox); otherwise the gradient pass followed by ``eng.prox``.  ``advance`` > 0 also bumps
+    that many end-of-iteration counters (``eng.advance``), inside the same launch when it is the fused one."""
     p, d = eng.p, eng.d
     own = sel is not None and sel is eng.sel
     if (eng.fused_tail is not False and eng.uses_sigma and not eng.sigma_ready and getattr(d, 'method', None) == 'wavelet'
@@ -35,7 +36,8 @@ def _grad_update_prox(eng, a, b, sel, gscale, vadd, z):
         kw = dict(b=b, sel=sel, with_y=False, gscale=gscale, vadd=vadd, step_ptr=eng.step, z_in=z, z_out=z, clear_sel=own)
         p._dev_grad(a, phases=3, **kw)
         ok = p._dev_update_prox(gscale, eng.step, vadd, z, z, eng.sig_log, d.sigma_modifier,
-                                d.denoise_strength * d.decay ** (d.t + 1), p._xrec_dev, eng.mse_log, eng.slot_ptr)
+                                d.denoise_strength * d.decay ** (d.t + 1), p._xrec_dev, eng.mse_log, eng.slot_ptr,
+                                advance=eng.counters if advance else None, n_advance=advance)
         eng.fused_tail = ok
         if ok:
             d.t += 1
@@ -44,6 +46,8 @@ def _grad_update_prox(eng, a, b, sel, gscale, vadd, z):
     else:
         _grad_update(eng, a, b, sel, False, gscale, vadd=vadd, step_ptr=eng.step, z_in=z, z_out=z)
     eng.prox(z, z)
+    if advance:
+        eng.advance(advance)
 
 
 class _Faithful:
@@ -300,11 +304,11 @@ def pnp_svrg(problem, denoiser, eta, tt, T2, mini_batch_size, verbose=True, lr_d
     def fast_ops():
         if paper:
             _sel_ops(eng)
-            _grad_update_prox(eng, z, w, eng.sel, 1.0 / B, mu, z)
+            _grad_update_prox(eng, z, w, eng.sel, 1.0 / B, mu, z, advance=3)
         else:
             grad_ops()
             eng.prox(z, z)
-        eng.advance()
+            eng.advance()
     draw = _host_draw_fn(eng) if (paper or mb_source == 'legacy') else None
 
     while budget.alive() and not stop:

@@ -434,7 +434,8 @@ __global__ void __launch_bounds__(512, 1)
 k_update_prox(const float2* __restrict__ S, int nlines, float inv_n, float gscale, float step,
               const float* __restrict__ step_ptr, const float* __restrict__ vadd, const float* __restrict__ z_in,
               float* __restrict__ z_out, const float* __restrict__ xrec, int pairs_per_cta, float sigma_modifier,
-              float fallback_sigma, double* __restrict__ sig_log, double* __restrict__ mse_log, const int* __restrict__ slot) {
+              float fallback_sigma, double* __restrict__ sig_log, double* __restrict__ mse_log, const int* __restrict__ slot,
+              int* __restrict__ advance, int n_advance) {
     constexpr int T = fft_threads<L>();
     constexpr int EPT = FftPlan<L>::EPT;
     constexpr int PL = fft_plane<L>();
@@ -542,6 +543,9 @@ k_update_prox(const float2* __restrict__ S, int nlines, float inv_n, float gscal
     upd_mark(2);
     __threadfence();
     cooperative_groups::this_grid().sync();
+    // end-of-iteration counters (pnp_advance) folded in: every CTA has read *slot before the barrier above, and
+    // nothing else of this iteration reads them any more
+    if (advance && blockIdx.x == 0 && threadIdx.x < n_advance) advance[threadIdx.x] += 1;
     upd_mark(3);
     prox_phase_shrink<L>(lines, 2 * mine, first, nlines, 1, z_out, xrec, sigma_modifier, fallback_sigma, sig_log, mse_log, cur_slot);
     __syncthreads();

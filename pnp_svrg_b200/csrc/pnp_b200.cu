@@ -214,7 +214,7 @@ namespace {
 template <int L>
 int launch_update_prox(const float* S, int W, float inv_n, float gscale, float step, const float* step_ptr, const float* vadd,
                        const float* z_in, float* z_out, const float* xrec, float sm, float fb, double* sig_log, double* mse_log,
-                       const int* slot, cudaStream_t st) {
+                       const int* slot, int* adv, int n_adv, cudaStream_t st) {
     constexpr int GP = pnp::upd_gp<L>();
     const int npairs = W / 2;
     int grid = g_num_sms < npairs ? g_num_sms : npairs;
@@ -230,14 +230,15 @@ int launch_update_prox(const float* S, int W, float inv_n, float gscale, float s
     }
     int nl = W, p = ppc;
     void* args[] = {(void*)&S, (void*)&nl, (void*)&inv_n, (void*)&gscale, (void*)&step, (void*)&step_ptr, (void*)&vadd, (void*)&z_in,
-                    (void*)&z_out, (void*)&xrec, (void*)&p, (void*)&sm, (void*)&fb, (void*)&sig_log, (void*)&mse_log, (void*)&slot};
+                    (void*)&z_out, (void*)&xrec, (void*)&p, (void*)&sm, (void*)&fb, (void*)&sig_log, (void*)&mse_log, (void*)&slot,
+                    (void*)&adv, (void*)&n_adv};
     CU_TRY(cudaLaunchCooperativeKernel((const void*)pnp::k_update_prox<L>, dim3(grid), dim3(512), args, smem, st));
     return PNP_OK;
 }
 int dispatch_update_prox(int n, const float* S, int W, float inv_n, float gscale, float step, const float* step_ptr,
                          const float* vadd, const float* z_in, float* z_out, const float* xrec, float sm, float fb, double* sig_log,
-                         double* mse_log, const int* slot, cudaStream_t st) {
-    DISPATCH_POW2(n, launch_update_prox, S, W, inv_n, gscale, step, step_ptr, vadd, z_in, z_out, xrec, sm, fb, sig_log, mse_log, slot, st)
+                         double* mse_log, const int* slot, int* adv, int n_adv, cudaStream_t st) {
+    DISPATCH_POW2(n, launch_update_prox, S, W, inv_n, gscale, step, step_ptr, vadd, z_in, z_out, xrec, sm, fb, sig_log, mse_log, slot, adv, n_adv, st)
 }
 }  // namespace
 
@@ -630,13 +631,16 @@ int pnp_pr_grad(const pnp_pr_grad_args* args, void* stream) {
 
 int pnp_csmri_update_prox(const float* S, int H, int W, float gscale, float step, const float* step_ptr, const float* vadd,
                           const float* z_in, float* z_out, double* sig_log, float sigma_modifier, float fallback_sigma,
-                          const float* xrec, double* mse_log, const int* slot, void* stream) {
+                          const float* xrec, double* mse_log, const int* slot, int* advance_counters, int n_advance,
+                          void* stream) {
     if (!S || !vadd || !z_in || !z_out || !sig_log) return fail(PNP_ERR_ARG, "bad argument");
+    if (advance_counters && (n_advance < 1 || n_advance > 32)) return fail(PNP_ERR_ARG, "n_advance must be in [1, 32]");
     if (!pow2_ok(H) || W < 2 || (W & 1)) return fail(PNP_ERR_ARG, "H must be a power of two in [32, 4096], W even");
     if (H < 128) return fail(PNP_ERR_UNSUPPORTED, "update+prox: lines shorter than 128 samples use the separate kernels");
     const float inv_n = (float)(1.0 / ((double)H * (double)W));
     return dispatch_update_prox(H, reinterpret_cast<const float*>(S), W, inv_n, gscale, step, step_ptr, vadd, z_in, z_out, xrec,
-                                sigma_modifier, fallback_sigma, sig_log, mse_log, slot, static_cast<cudaStream_t>(stream));
+                                sigma_modifier, fallback_sigma, sig_log, mse_log, slot, advance_counters, n_advance,
+                                static_cast<cudaStream_t>(stream));
 }
 
 int pnp_cdp_grad(const pnp_cdp_grad_args* args, void* stream) {
