@@ -140,13 +140,15 @@ def _host_draw_fn(eng, extra_fn=None):
         return None
 
     def draw():
+        # a small ring of pinned staging buffers: the host only waits for the H2D copy that used this buffer four
+        # draws ago, so drawing and staging overlap the GPU's previous iterations instead of a sync per iteration
+        eng.next_host_buffer()
         eng.draw_host()                                   # minibatch first, then the extras
         if extra_fn:                                      # (reference RNG call order, pnp_saga.py:43-44)
             for k, e in enumerate(extra_fn()):
                 eng.idx_host.numpy()[eng.B + k] = e
         eng.idx_dev.copy_(eng.idx_host, non_blocking=True)
-        # the pinned staging buffer is reused by the next draw: wait for the copy only
-        eng.stream.synchronize()
+        eng.mark_host_buffer()
     return draw
 
 

@@ -96,6 +96,7 @@ class Engine:
         self._draw_ahead = 3
         ncpu = len(os.sched_getaffinity(0)) if hasattr(os, 'sched_getaffinity') else (os.cpu_count() or 1)
         self._draw_pool = None
+        self._host_ring = None
         if mb_source == 'host':
             from concurrent.futures import ThreadPoolExecutor
             # one single-threaded C call per draw (GIL released), several draws in flight: spawning worker
@@ -177,6 +178,25 @@ class Engine:
         for i, e in enumerate(extra):
             buf[self.B + i] = e
         return idx
+
+    def next_host_buffer(self):
+        """Rotate to the next pinned staging buffer (``self.idx_host``), waiting only for the H2D copy that read it
+        last time round."""
+        if self._host_ring is None:
+            self._host_ring = [self.idx_host] + [torch.empty_like(self.idx_host).pin_memory() for _ in range(3)]
+            self._host_ev = [None] * len(self._host_ring)
+            self._host_pos = 0
+        self._host_pos = (self._host_pos + 1) % len(self._host_ring)
+        ev = self._host_ev[self._host_pos]
+        if ev is not None:
+            ev.synchronize()
+        self.idx_host = self._host_ring[self._host_pos]
+
+    def mark_host_buffer(self):
+        """Record that the copy just enqueued on the engine stream reads the current staging buffer."""
+        ev = self._host_ev[self._host_pos] or torch.cuda.Event()
+        ev.record(self.stream)
+        self._host_ev[self._host_pos] = ev
 
     def _host_draw_job(self, counter):
         sup = getattr(self.p, '_support_host', None)
