@@ -36,6 +36,8 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 
+#include <cooperative_groups.h>
+
 #include "fft_core.cuh"
 
 namespace pnp {
@@ -366,6 +368,205 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         for (int k = 0; k < TC_EPI_WARPS; ++k) t += ctl->err[k];
         atomicAdd(last.mse_log + (last.slot ? *last.slot : 0), (double)t);
     }
+    if (warp == 1) {
+        asm volatile("tcgen05.fence::after_thread_sync;");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((unsigned)CF::TMEM_COLS));
+    }
+}
+
+// ---- all 64 -> 64 layers of a stack in ONE cooperative launch (small images) ----------------------------------------
+// At 256 x 256 a layer is 548 tiles = 3.7 per SM, ~2.3 us of MMA inside a ~10 us launch (launch latency, TMEM
+// allocation, barrier init, pipeline fill and drain per layer).  Here the CTAs stay resident: per layer they reload
+// the 72 KiB of weights, run the same TMA -> tcgen05 -> epilogue pipeline over their tiles (barrier phases simply
+// continue), make their TMA stores visible and meet at a grid barrier; activations ping-pong between the two
+// buffers (L2 resident at these sizes).
+#define TC_MAX_LAYERS 30
+struct TcStack {
+    CUtensorMap a[2];                  // loads:  layer l reads  a[l & 1]   (a[0] over buffer 0, a[1] over buffer 1)
+    CUtensorMap o[2];                  // stores: layer l writes o[l & 1]   (o[0] over buffer 1, o[1] over buffer 0)
+    CUtensorMap b[TC_MAX_LAYERS];      // packed weights per layer
+    const float* shift[TC_MAX_LAYERS];
+    float slope[TC_MAX_LAYERS];
+    int n_layers;
+};
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+k_conv_tc_stack(const __grid_constant__ TcStack pm, int PW, int S, int n_tiles) {
+    using CF = TcCfg<64>;
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<unsigned long long>(smem_raw) + 1023ull) & ~1023ull);
+    unsigned char* sB = base;
+    unsigned char* sA = base + ((3 * CF::B_BYTES + 1023) & ~1023);
+    unsigned char* sO = sA + TC_STAGES * TC_A_BYTES;
+    TcSmem* ctl = reinterpret_cast<TcSmem*>(sO + TC_O_BYTES);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int pitch = PW + 1;
+    cooperative_groups::grid_group grid = cooperative_groups::this_grid();
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < TC_STAGES; ++i) { mbar_init(&ctl->full[i], 1); mbar_init(&ctl->empty[i], 1); }
+        mbar_init(&ctl->bfull, 1);
+        for (int i = 0; i < 2; ++i) { mbar_init(&ctl->tfull[i], 1); mbar_init(&ctl->tempty[i], TC_EPI_WARPS / 2); }
+        mbar_fence_init();
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&ctl->tmem_base)), "r"((unsigned)CF::TMEM_COLS));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;");
+    const unsigned tmem = ctl->tmem_base;
+
+    // pipeline state that carries over from layer to layer: the phase of the barriers of each group g (a layer with
+    // an odd number of tiles uses group 0 once more than group 1)
+    unsigned ph[2] = {0u, 0u};            // producer / issuer: smem stages 3g .. 3g+2 and accumulator g
+    unsigned aphase = 0;                  // epilogue group: its accumulator
+    const unsigned idesc = umma_idesc_bf16(TC_M, CF::N);
+    unsigned long long da[TC_STAGES], db[3];
+#pragma unroll
+    for (int i = 0; i < TC_STAGES; ++i) da[i] = umma_desc_sw128(sA + i * TC_A_BYTES);
+#pragma unroll
+    for (int kb = 0; kb < 3; ++kb) db[kb] = umma_desc_sw128(sB + kb * CF::B_BYTES);
+
+    for (int layer = 0; layer < pm.n_layers; ++layer) {
+        if (layer > 0) {
+            grid.sync();                                  // every CTA's outputs of the previous layer are in global memory
+            asm volatile("fence.proxy.async.global;" ::: "memory");
+        }
+        if (threadIdx.x >= 64 && threadIdx.x < 128) ctl->shift[threadIdx.x - 64] = pm.shift[layer] ? pm.shift[layer][threadIdx.x - 64] : 0.f;
+        __syncthreads();
+        const CUtensorMap* tmA = &pm.a[layer & 1];
+        const CUtensorMap* tmO = &pm.o[layer & 1];
+        if (warp == 0) {
+            // ===== TMA producer =====
+            if (elect_one()) {
+                mbar_expect_tx(&ctl->bfull, 3 * CF::B_BYTES);
+                for (int kb = 0; kb < 3; ++kb) tma_load_2d(sB + kb * CF::B_BYTES, &pm.b[layer], kb * TC_KBLK, 0, &ctl->bfull);
+            }
+            __syncwarp();
+            for (int tile = blockIdx.x; tile < n_tiles;) {
+#pragma unroll
+                for (int g = 0; g < 2; ++g) {
+                    if (tile < n_tiles) {
+                        const int s0 = tile * TC_OUT_PER_TILE - 1;
+#pragma unroll
+                        for (int kb = 0; kb < 3; ++kb) {
+                            const int stage = 3 * g + kb;
+                            mbar_wait_bounded(&ctl->empty[stage], ph[g] ^ 1);
+                            if (elect_one()) {
+                                mbar_expect_tx(&ctl->full[stage], TC_A_BYTES);
+#pragma unroll
+                                for (int q = 0; q < 4; ++q)
+                                    tma_load_2d(sA + stage * TC_A_BYTES + q * (TC_Q_ROWS * 128), tmA, 0,
+                                                s0 + q * TC_OUT_PER_Q + (kb - 1) * pitch, &ctl->full[stage]);
+                            }
+                            __syncwarp();
+                        }
+                        ph[g] ^= 1;
+                    }
+                    tile += gridDim.x;
+                }
+            }
+        } else if (warp == 1) {
+            // ===== MMA issuer =====
+            mbar_wait_bounded(&ctl->bfull, layer & 1);
+            for (int tile = blockIdx.x; tile < n_tiles;) {
+#pragma unroll
+                for (int g = 0; g < 2; ++g) {
+                    if (tile < n_tiles) {
+                        mbar_wait_bounded(&ctl->tempty[g], ph[g] ^ 1);
+                        asm volatile("tcgen05.fence::after_thread_sync;");
+                        const unsigned d = tmem + g * CF::ACC_COLS;
+#pragma unroll
+                        for (int kb = 0; kb < 3; ++kb) {
+                            const int stage = 3 * g + kb;
+                            mbar_wait_bounded(&ctl->full[stage], ph[g]);
+                            asm volatile("tcgen05.fence::after_thread_sync;");
+                            if (elect_one()) {
+#pragma unroll
+                                for (int k = 0; k < TC_KBLK / 16; ++k)
+                                    umma_f16(d, da[stage] + 2 * k, db[kb] + 2 * k, idesc, (kb | k) ? 1u : 0u);
+                                umma_commit(&ctl->empty[stage]);
+                                if (kb == 2) umma_commit(&ctl->tfull[g]);
+                            }
+                            __syncwarp();
+                        }
+                        ph[g] ^= 1;
+                    }
+                    tile += gridDim.x;
+                }
+            }
+        } else {
+            // ===== epilogue warps: two ping-pong groups of eight, as in k_conv_tc =====
+            const int ew = warp - 2;
+            const int wg = ew >> 3;
+            const int q = warp & 3;
+            const int hf = (ew >> 2) & 1;
+            const bool interior = lane >= 1 && lane <= TC_OUT_PER_Q;
+            const float slope = pm.slope[layer];
+            const bool relu = slope == 0.f;
+            const unsigned t0 = tmem + wg * CF::ACC_COLS + ((unsigned)(q * 32) << 16);
+            for (int tile = blockIdx.x + wg * gridDim.x; tile < n_tiles; tile += 2 * gridDim.x, aphase ^= 1) {
+                const int s = tile * TC_OUT_PER_TILE + q * TC_OUT_PER_Q + lane - 1;
+                mbar_wait_bounded(&ctl->tfull[wg], aphase);
+                asm volatile("tcgen05.fence::after_thread_sync;");
+                const bool pad = (s % pitch) == PW;
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    const int c = 32 * hf + 16 * j;
+                    float tm[16], tz[16], tp[16], sh[16];
+                    tmem_ld16(t0 + c, tm);
+                    tmem_ld16(t0 + 64 + c, tz);
+                    tmem_ld16(t0 + 128 + c, tp);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) reinterpret_cast<float4*>(sh)[i] = reinterpret_cast<const float4*>(ctl->shift + c)[i];
+                    asm volatile("tcgen05.wait::ld.sync.aligned;");
+                    if (j == 1) {
+                        asm volatile("tcgen05.fence::before_thread_sync;");
+                        if (lane == 0) mbar_arrive(&ctl->tempty[wg]);
+                    }
+                    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                    __syncwarp();
+                    uint4 pk[2];
+                    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(pk);
+#pragma unroll
+                    for (int i = 0; i < 16; i += 2) {
+                        float o2[2];
+#pragma unroll
+                        for (int u = 0; u < 2; ++u) {
+                            const float up = __shfl_up_sync(0xffffffffu, tm[i + u], 1);
+                            const float dn = __shfl_down_sync(0xffffffffu, tp[i + u], 1);
+                            const float v = (up + tz[i + u]) + (dn + sh[i + u]);
+                            o2[u] = relu ? fmaxf(v, 0.f) : fmaxf(v, v * slope);
+                        }
+                        h[i >> 1] = __floats2bfloat162_rn(o2[0], o2[1]);
+                    }
+                    if (pad) pk[0] = pk[1] = make_uint4(0u, 0u, 0u, 0u);
+                    unsigned char* stage_o = sO + (ew * 2 + j) * TC_O_WARP_BYTES;
+                    if (interior) {
+                        const int r = lane - 1;
+#pragma unroll
+                        for (int k = 0; k < 2; ++k) *reinterpret_cast<uint4*>(stage_o + r * 32 + ((k ^ ((r >> 2) & 1)) << 4)) = pk[k];
+                    }
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) {
+                        asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                                     ::"l"(tmO), "r"(smem_u32(stage_o)), "r"(c), "r"(s + 1) : "memory");
+                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    }
+                }
+            }
+            if (lane == 0) {                              // this layer's stores are complete before the grid barrier
+                asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+                asm volatile("fence.proxy.async.global;" ::: "memory");
+            }
+        }
+        __threadfence();
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    __syncthreads();
     if (warp == 1) {
         asm volatile("tcgen05.fence::after_thread_sync;");
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((unsigned)CF::TMEM_COLS));

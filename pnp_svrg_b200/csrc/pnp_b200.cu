@@ -784,7 +784,31 @@ int cnn_forward_tc(const pnp_cnn_net* net, const float* img, float* out, int PH,
     const int grid = n_tiles < g_num_sms ? n_tiles : g_num_sms;
     int rc;
     CUtensorMap tmA, tmB, tmO;
-    for (int l = 1; l < L - 1; ++l) {
+    // small images: all middle layers in one cooperative launch (a layer would be a few tiles per SM inside a ~10 us launch)
+    const bool stack = g_tc_dbg != 32 && L - 2 >= 2 && L - 2 <= TC_MAX_LAYERS && n_tiles <= 8 * g_num_sms;
+    if (stack) {
+        static bool stack_attr = false;
+        if (!stack_attr) {
+            CU_TRY(cudaFuncSetAttribute(pnp::k_conv_tc_stack, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pnp::tc_smem<64>()));
+            stack_attr = true;
+        }
+        pnp::TcStack pm{};
+        pm.n_layers = L - 2;
+        if ((rc = make_tmap_bf16_2d(&pm.a[0], cur, 64, (unsigned long long)S, 64, TC_Q_ROWS)) != PNP_OK) return rc;
+        if ((rc = make_tmap_bf16_2d(&pm.a[1], nxt, 64, (unsigned long long)S, 64, TC_Q_ROWS)) != PNP_OK) return rc;
+        if ((rc = make_tmap_bf16_2d(&pm.o[0], nxt, 64, (unsigned long long)S, 16, TC_OUT_PER_Q, CU_TENSOR_MAP_SWIZZLE_32B)) != PNP_OK) return rc;
+        if ((rc = make_tmap_bf16_2d(&pm.o[1], cur, 64, (unsigned long long)S, 16, TC_OUT_PER_Q, CU_TENSOR_MAP_SWIZZLE_32B)) != PNP_OK) return rc;
+        for (int l = 1; l < L - 1; ++l) {
+            if ((rc = make_tmap_bf16_2d(&pm.b[l - 1], net->w_tc[l], 192, 192, 64, 192)) != PNP_OK) return rc;
+            pm.shift[l - 1] = net->shift[l];
+            pm.slope[l - 1] = net->slope[l];
+        }
+        int pw = PW, s32 = (int)S, nt = n_tiles;
+        void* args[] = {(void*)&pm, (void*)&pw, (void*)&s32, (void*)&nt};
+        CU_TRY(cudaLaunchCooperativeKernel((const void*)pnp::k_conv_tc_stack, dim3(grid), dim3(TC_THREADS), args, pnp::tc_smem<64>(), st));
+        if ((L - 2) & 1) { __nv_bfloat16* t = cur; cur = nxt; nxt = t; }      // where the last middle layer wrote
+    }
+    for (int l = 1; l < L - 1 && !stack; ++l) {
         if ((rc = make_tmap_bf16_2d(&tmA, cur, 64, (unsigned long long)S, 64, TC_Q_ROWS)) != PNP_OK) return rc;
         if ((rc = make_tmap_bf16_2d(&tmB, net->w_tc[l], 192, 192, 64, 192)) != PNP_OK) return rc;
         if ((rc = make_tmap_bf16_2d(&tmO, nxt, 64, (unsigned long long)S, 16, TC_OUT_PER_Q, CU_TENSOR_MAP_SWIZZLE_32B)) != PNP_OK) return rc;
