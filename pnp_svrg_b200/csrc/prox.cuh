@@ -403,13 +403,14 @@ template <int LEVELS> struct HaarCC {
     static constexpr int TL = LEVELS - 2 - XC;                     // levels above them (0, 1 or 2)
 };
 
-template <int LEVELS>
-__device__ __forceinline__ void haar_cc_forward(float (&x)[4][4], float (&A)[4][6], float (&D)[4][5], float (&T)[4],
+template <int LEVELS, int NCH>
+__device__ __forceinline__ void haar_cc_forward(float (&x)[NCH][4], float (&A)[NCH][6], float (&D)[NCH][5], float (&T)[4],
                                                 float (&ss)[LEVELS], int lane) {
     using H = HaarCC<LEVELS>;
+    static_assert(H::TL == 0 || NCH == 4, "levels above the lane butterflies need the four chunks of a 512-sample block");
     constexpr float RS2 = 0.70710678118654752f;
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
+    for (int c = 0; c < NCH; ++c) {
         const float a0 = (x[c][0] + x[c][1]) * RS2, d0 = (x[c][0] - x[c][1]) * RS2;
         const float a1 = (x[c][2] + x[c][3]) * RS2, d1 = (x[c][2] - x[c][3]) * RS2;
         ss[0] = fmaf(d0, d0, fmaf(d1, d1, ss[0]));
@@ -426,7 +427,7 @@ __device__ __forceinline__ void haar_cc_forward(float (&x)[4][4], float (&A)[4][
             if ((lane & ((2 << q) - 1)) == 0) ss[2 + q] = fmaf(D[c][q], D[c][q], ss[2 + q]);
         }
     }
-    if (H::TL >= 1) {                                              // chunks (0,1) and (2,3) are adjacent 128-sample blocks
+    if constexpr (H::TL >= 1 && NCH == 4) {                       // chunks (0,1) and (2,3) are adjacent 128-sample blocks
         const float t0 = A[0][H::XC], t1 = A[1][H::XC], t2 = A[2][H::XC], t3 = A[3][H::XC];
         T[0] = (t0 - t1) * RS2;
         T[1] = (t2 - t3) * RS2;
@@ -443,12 +444,12 @@ __device__ __forceinline__ void haar_cc_forward(float (&x)[4][4], float (&A)[4][
     }
 }
 
-template <int LEVELS>
-__device__ __forceinline__ void haar_cc_inverse(float (&x)[4][4], float (&A)[4][6], const float (&D)[4][5], const float (&T)[4],
+template <int LEVELS, int NCH>
+__device__ __forceinline__ void haar_cc_inverse(float (&x)[NCH][4], float (&A)[NCH][6], const float (&D)[NCH][5], const float (&T)[4],
                                                 const float (&thr)[LEVELS], int lane) {
     using H = HaarCC<LEVELS>;
     constexpr float RS2 = 0.70710678118654752f;
-    if (H::TL >= 1) {
+    if constexpr (H::TL >= 1 && NCH == 4) {
         float u0 = T[2], u1 = T[3];
         if (H::TL >= 2) {
             const float dd = soft_shrink(T[3], thr[3 + H::XC]);
@@ -462,7 +463,7 @@ __device__ __forceinline__ void haar_cc_inverse(float (&x)[4][4], float (&A)[4][
         A[3][H::XC] = (u1 - e1) * RS2;
     }
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
+    for (int c = 0; c < NCH; ++c) {
 #pragma unroll
         for (int q = H::XC - 1; q >= 0; --q) {
             const float d = soft_shrink(D[c][q], thr[2 + q]);
@@ -522,7 +523,7 @@ __device__ __forceinline__ void prox_phase_shrink(const float* lines, int mine, 
             }
 #pragma unroll
             for (int k = 0; k < LEVELS; ++k) ss[k] = 0.f;
-            haar_cc_forward<LEVELS>(x, A, D, T, ss, lane);
+            haar_cc_forward<LEVELS, 4>(x, A, D, T, ss, lane);
 #pragma unroll
             for (int k = 0; k < LEVELS; ++k) {
                 const float e = warp_sum_f(ss[k]);
@@ -557,12 +558,57 @@ __device__ __forceinline__ void prox_phase_shrink(const float* lines, int mine, 
 #pragma unroll
                 for (int kk = 0; kk < LEVELS; ++kk) { thr[kk] = __shfl_sync(0xffffffffu, tk, kk); dummy[kk] = 0.f; }
             }
-            haar_cc_forward<LEVELS>(x, A, D, T, dummy, lane);
-            haar_cc_inverse<LEVELS>(x, A, D, T, thr, lane);
+            haar_cc_forward<LEVELS, 4>(x, A, D, T, dummy, lane);
+            haar_cc_inverse<LEVELS, 4>(x, A, D, T, thr, lane);
             flush_err(img);
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
                 reinterpret_cast<float4*>(zout + gbase)[c * 32 + lane] = make_float4(x[c][0], x[c][1], x[c][2], x[c][3]);
+                if (xrec) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) { const float e = x[c][j] - xr[c][j]; err_acc = fmaf(e, e, err_acc); }
+                }
+            }
+        }
+    } else if constexpr (L >= 128) {
+        // 128 or 256 samples: the line is one task of one warp, same chunk-cyclic layout with 1 or 2 chunks per lane
+        constexpr int NCH = L / 128;
+        for (int l = warp; l < mine; l += 16) {
+            const long long gl = first + l;
+            const int img = (int)(gl / nlines);
+            const float4* s4 = reinterpret_cast<const float4*>(lines + (long long)l * L);
+            float x[NCH][4], xr[NCH][4], A[NCH][6], D[NCH][5], T[4], ss[LEVELS], thr[LEVELS];
+#pragma unroll
+            for (int c = 0; c < NCH; ++c) {
+                if (xrec) {
+                    const float4 r = reinterpret_cast<const float4*>(xrec + gl * L)[c * 32 + lane];
+                    xr[c][0] = r.x; xr[c][1] = r.y; xr[c][2] = r.z; xr[c][3] = r.w;
+                }
+                const float4 q = s4[c * 32 + lane];
+                x[c][0] = q.x; x[c][1] = q.y; x[c][2] = q.z; x[c][3] = q.w;
+            }
+#pragma unroll
+            for (int k = 0; k < LEVELS; ++k) ss[k] = 0.f;
+            haar_cc_forward<LEVELS, NCH>(x, A, D, T, ss, lane);
+            const float var = sigma_var(img);
+            {
+                float mine_ss = 0.f;
+#pragma unroll
+                for (int k = 0; k < LEVELS; ++k) {
+                    const float e = warp_sum_f(ss[k]);
+                    mine_ss = lane == k ? e : mine_ss;
+                }
+                const int k = lane < LEVELS ? lane : LEVELS - 1;
+                const float dvar = mine_ss / (float)(L >> (k + 1));
+                const float tk = var / sqrtf(fmaxf(dvar - var, 2.220446049250313e-16f));
+#pragma unroll
+                for (int kk = 0; kk < LEVELS; ++kk) thr[kk] = __shfl_sync(0xffffffffu, tk, kk);
+            }
+            haar_cc_inverse<LEVELS, NCH>(x, A, D, T, thr, lane);
+            flush_err(img);
+#pragma unroll
+            for (int c = 0; c < NCH; ++c) {
+                reinterpret_cast<float4*>(zout + gl * L)[c * 32 + lane] = make_float4(x[c][0], x[c][1], x[c][2], x[c][3]);
                 if (xrec) {
 #pragma unroll
                     for (int j = 0; j < 4; ++j) { const float e = x[c][j] - xr[c][j]; err_acc = fmaf(e, e, err_acc); }
@@ -645,9 +691,13 @@ k_prox_wavelet_fused(const float* __restrict__ zin, float* __restrict__ zout, co
         mbar_init(&bar, 1);
         mbar_fence_init();
         if (mine > 0) {
-            mbar_expect_tx(&bar, (unsigned)(mine * L * sizeof(float)));
-            for (int l = 0; l < (int)mine; ++l)
-                bulk_g2s(lines + (long long)l * L, zin + (first + l) * L, (unsigned)(L * sizeof(float)), &bar);
+            // the CTA's lines are one contiguous block: a few large bulk copies instead of one per (short) line
+            const unsigned total = (unsigned)(mine * L * sizeof(float));
+            mbar_expect_tx(&bar, total);
+            for (unsigned off = 0; off < total; off += 32768u) {
+                const unsigned n = total - off < 32768u ? total - off : 32768u;
+                bulk_g2s(reinterpret_cast<char*>(lines) + off, reinterpret_cast<const char*>(zin + first * L) + off, n, &bar);
+            }
         }
     }
     __syncthreads();
