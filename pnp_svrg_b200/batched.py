@@ -76,7 +76,14 @@ def csmri_device_batch(images, sample_probs, snrs, H, W, seed=0, device=None):
     stride = int(m0_host.max())
     support = torch.sort(key, dim=1).values[:, :stride].contiguous()
     support = torch.where(support < N, support, torch.zeros_like(support))
+    # selection bytes of the full mask in the kernels' packed layout [H/2][W] (csrc/csmri.cuh::set_sel_bits):
+    # bit0 sel[ky][kx], bit1 sel[-ky][-kx]; row 0 also carries the Nyquist row in bits 2 and 3
+    m8 = mask.to(torch.uint8)
+    mir = torch.roll(torch.flip(m8, dims=(1, 2)), shifts=(1, 1), dims=(1, 2))
+    bits = m8[:, :hp] + 2 * mir[:, :hp]
+    bits[:, 0] += 4 * m8[:, hp] + 8 * mir[:, hp]
     return dict(device=True, nb=nb, H=H, W=W, m0_host=m0_host.astype(np.int32), m0=m0.contiguous(), support=support,
+                bits_full=bits.contiguous(),
                 xrec=x.transpose(1, 2).contiguous(), xinit=xinit.transpose(1, 2).contiguous(),
                 Y1=c(y[:, :hp]), Y2=c(ymir[:, :hp]), Y1n=c(y[:, hp]), Y2n=c(ymir[:, hp]),
                 sigma=sigma.cpu().numpy(), data_range=np.ones(nb))
@@ -119,11 +126,13 @@ class BatchedSVRG:
             torch.cuda.current_stream(dev).synchronize()                 # the batch was built on the current stream
         with torch.cuda.stream(self.stream):
             self.m0_host = m0_all
-            self.sup_stride = int(self.m0_host.max())
+            self.sup_stride = N if on_dev else int(self.m0_host.max())      # device batches: fixed stride, the object is reusable
             if on_dev:
-                self.xrec, self.z = specs['xrec'], specs['xinit'].clone()
-                self.Y1, self.Y2, self.Y1n, self.Y2n = specs['Y1'], specs['Y2'], specs['Y1n'], specs['Y2n']
-                self.m0, self.support = specs['m0'], specs['support']
+                self.xrec, self.z = specs['xrec'].clone(), specs['xinit'].clone()
+                self.Y1, self.Y2, self.Y1n, self.Y2n = (specs[k].clone() for k in ('Y1', 'Y2', 'Y1n', 'Y2n'))
+                self.m0 = specs['m0'].clone()
+                self.support = torch.zeros((nb, N), dtype=torch.int32, device=dev)
+                self.support[:, :specs['support'].shape[1]] = specs['support']
             else:
                 self.xrec = stack('xrec', torch.float32)
                 self.z = stack('xinit', torch.float32)
@@ -144,13 +153,16 @@ class BatchedSVRG:
             self.mse_log = torch.zeros(max_slots * nb, dtype=torch.float64, device=dev)
             self.sig_log = torch.zeros(max_slots * nb, dtype=torch.float64, device=dev)
             self.counters = torch.zeros(4, dtype=torch.int32, device=dev)
-            self.check(self.lib.pnp_csmri_sel_from_indices(D.ptr(self.bits_full), self.H, self.W, nb, D.ptr(self.support), 0,
-                                                           self.sup_stride, None, 1, self.sptr))
-            # full-mask bits: every problem's own support (counts differ, so one launch per distinct problem)
-            for i in range(nb):
-                self.check(self.lib.pnp_csmri_sel_from_indices(
-                    self.bits_full.data_ptr() + i * self.W * hp, self.H, self.W, 1,
-                    self.support.data_ptr() + 4 * i * self.sup_stride, int(self.m0_host[i]), 0, None, 0, self.sptr))
+            if on_dev:
+                self.bits_full.copy_(specs['bits_full'].reshape(-1))
+            else:
+                self.check(self.lib.pnp_csmri_sel_from_indices(D.ptr(self.bits_full), self.H, self.W, nb, D.ptr(self.support), 0,
+                                                               self.sup_stride, None, 1, self.sptr))
+                # full-mask bits: every problem's own support (counts differ, so one launch per distinct problem)
+                for i in range(nb):
+                    self.check(self.lib.pnp_csmri_sel_from_indices(
+                        self.bits_full.data_ptr() + i * self.W * hp, self.H, self.W, 1,
+                        self.support.data_ptr() + 4 * i * self.sup_stride, int(self.m0_host[i]), 0, None, 0, self.sptr))
             self.mse0 = torch.zeros(nb, dtype=torch.float64, device=dev)
             self.check(self.lib.pnp_sq_err(D.ptr(self.z), D.ptr(self.xrec), N, nb, D.ptr(self.mse0), None, self.sptr))
         self.data_range = np.asarray(specs['data_range'], dtype=np.float64) if on_dev else np.array([s['data_range'] for s in specs])
@@ -165,6 +177,32 @@ class BatchedSVRG:
     def check(self, rc):
         if rc:
             _lib.check(rc)
+
+    def reload(self, batch, etas):
+        """Load another device-built batch of the same shape into the existing buffers: allocations and the
+        captured iteration graph are reused (sweeps run hundreds of batches)."""
+        if not (isinstance(batch, dict) and batch.get('device')) or batch['nb'] != self.nb or (batch['H'], batch['W']) != (self.H, self.W):
+            raise ValueError('reload needs a csmri_device_batch of the same shape')
+        if (batch['m0_host'] < self.B).any():
+            raise ValueError('mini_batch_size exceeds the number of measurements of a problem')
+        torch.cuda.current_stream(self.dev).synchronize()
+        with torch.cuda.stream(self.stream):
+            self.xrec.copy_(batch['xrec']); self.z.copy_(batch['xinit'])
+            for k in ('Y1', 'Y2', 'Y1n', 'Y2n'):
+                getattr(self, k).copy_(batch[k])
+            self.m0.copy_(batch['m0'])
+            self.m0_host = batch['m0_host']
+            self.support[:, :batch['support'].shape[1]] = batch['support']
+            self.bits_full.copy_(batch['bits_full'].reshape(-1))
+            self.inv_m0.copy_(torch.from_numpy((1.0 / self.m0_host).astype(np.float32)), non_blocking=False)
+            self.eta_host = np.broadcast_to(np.asarray(etas, dtype=np.float64), (self.nb,)).copy()
+            self.step.copy_(torch.from_numpy(self.eta_host.astype(np.float32)), non_blocking=False)
+            self.mse_log.zero_(); self.sig_log.zero_(); self.mse0.zero_()
+            self.counters[0:2].zero_()                      # log slot and cursor; the draw counter keeps running
+            self.check(self.lib.pnp_sq_err(D.ptr(self.z), D.ptr(self.xrec), self.N, self.nb, D.ptr(self.mse0), None, self.sptr))
+        self.data_range = np.asarray(batch['data_range'], dtype=np.float64)
+        self.slots_used = 0
+        self.outer = 0
 
     # ---- the launches -------------------------------------------------------------------------
     def _grad(self, a, b, bits, with_y, stream, phases=0, **kw):

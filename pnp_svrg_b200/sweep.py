@@ -83,6 +83,9 @@ def reconstruct(job, H=256, W=256, eta_scale=0.15, T2=10, mini_batch_size=1000, 
                 denoiser=job['denoiser'], psnr_init=float(ps[0]), psnr_final=float(ps[-1]), iters=iters, seconds=dt)
 
 
+_RUNNERS = {}        # reusable batched engines of device-built sweeps, keyed by shape
+
+
 def reconstruct_batch(jobs, H=256, W=256, eta_scale=0.15, T2=10, mini_batch_size=1000, iters=200, images=None,
                       seed=0, host_threads=8, construct='host'):
     """A group of same-size CSMRI jobs as ONE batched device run (pnp_svrg_b200.batched).
@@ -106,10 +109,14 @@ def reconstruct_batch(jobs, H=256, W=256, eta_scale=0.15, T2=10, mini_batch_size
         m0 = batch['m0_host']
         B = int(min(mini_batch_size, m0.min()))
         etas = [min(eta_scale * float(m), 3.0 * B) for m in m0]
-        run = BatchedSVRG(batch, T2=T2, mini_batch_size=B, etas=etas, seed=seed + jobs[0]['id'], max_slots=iters)
+        key = (len(jobs), H, W, B, T2, iters)
+        run = _RUNNERS.get(key)                      # same shape as an earlier batch: reuse buffers and the captured graph
+        if run is None:
+            run = _RUNNERS[key] = BatchedSVRG(batch, T2=T2, mini_batch_size=B, etas=etas, seed=seed, max_slots=iters)
+        else:
+            run.reload(batch, etas)
         run.run(iters)
         out = run.results(with_z=False)
-        run.close()
         dt = time.time() - t0
         return [dict(id=j['id'], image=str(j['image']), alpha=j['alpha'], snr=j['snr'], algo='pnp_svrg', denoiser='TV',
                      psnr_init=float(out['psnr_init'][i]), psnr_final=float(out['psnr'][-1, i]), iters=iters,
