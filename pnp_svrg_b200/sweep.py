@@ -145,7 +145,7 @@ def reconstruct_batch(jobs, H=256, W=256, eta_scale=0.15, T2=10, mini_batch_size
                  seconds=dt / len(jobs)) for i, j in enumerate(jobs)]
 
 
-def run_partitioned_batched(jobs, batch_runner, rank=0, world=1, batch=28, gather=True):
+def run_partitioned_batched(jobs, batch_runner, rank=0, world=1, batch=56, gather=True):
     """Like run_partitioned, but this rank's share is processed in groups of `batch` jobs."""
     mine = partition(jobs, rank, world)
     local = []
@@ -159,11 +159,41 @@ def run_partitioned_batched(jobs, batch_runner, rank=0, world=1, batch=28, gathe
             r['rank'] = rank
         local.extend(recs)
     if gather and world > 1:
-        import torch.distributed as dist
+        local = _gather_records(jobs, local, rank, world)
+    return sorted(local, key=lambda r: r['id'])
+
+
+def _gather_records(jobs, local, rank, world):
+    """All ranks' records on every rank.  The numeric part (id, PSNRs, seconds, rank) travels as one padded tensor
+    all-gather; the descriptive fields are rebuilt from the job list every rank holds.  Records that carry an error
+    message fall back to the pickling collective (rare, and strings do not fit a tensor)."""
+    import torch
+    import torch.distributed as dist
+    flag = torch.tensor([int(any('error' in r for r in local))], dtype=torch.int32,
+                        device='cuda' if dist.get_backend() == 'nccl' else 'cpu')
+    dist.all_reduce(flag, op=dist.ReduceOp.MAX)
+    if int(flag.item()):
         parts = [None] * world
         dist.all_gather_object(parts, local)
-        local = [r for part in parts for r in part]
-    return sorted(local, key=lambda r: r['id'])
+        return [r for part in parts for r in part]
+    cap = (len(jobs) + world - 1) // world
+    t = torch.full((cap, 5), -1.0, dtype=torch.float64)
+    for k, r in enumerate(local):
+        t[k] = torch.tensor([r['id'], r['psnr_init'], r['psnr_final'], r['seconds'], r['rank']], dtype=torch.float64)
+    t = t.to(flag.device)
+    parts = [torch.empty_like(t) for _ in range(world)]
+    dist.all_gather(parts, t)
+    by_id = {j['id']: j for j in jobs}
+    proto = local[0] if local else {}
+    out = []
+    for row in torch.cat(parts).cpu().numpy():
+        if row[0] < 0:
+            continue
+        j = by_id[int(row[0])]
+        out.append(dict(id=j['id'], image=str(j['image']), alpha=j['alpha'], snr=j['snr'], algo=proto.get('algo', j.get('algo')),
+                        denoiser=proto.get('denoiser', j.get('denoiser')), psnr_init=float(row[1]), psnr_final=float(row[2]),
+                        iters=proto.get('iters'), seconds=float(row[3]), rank=int(row[4])))
+    return out
 
 
 def main():

@@ -24,7 +24,7 @@ def main():
     ap.add_argument('--jobs', type=int, default=840)
     ap.add_argument('--iters', type=int, default=200)
     ap.add_argument('--size', type=int, default=256)
-    ap.add_argument('--batch', type=int, default=28, help='reconstructions per batched launch (0 = per-problem engine)')
+    ap.add_argument('--batch', type=int, default=56, help='reconstructions per batched launch (0 = per-problem engine)')
     ap.add_argument('--repeat', type=int, default=1, help='run the 840-job list this many times (fresh draws), to amortise fixed costs')
     ap.add_argument('--construct', default='device', choices=['host', 'device'], help='where the problems of a batch are built')
     a = ap.parse_args()

@@ -28,6 +28,48 @@ def _worker(rank, world, port, q):
     dist.destroy_process_group()
 
 
+def _worker_batched(rank, world, port, q, fail):
+    sys.path.insert(0, ROOT)
+    from pnp_svrg_b200 import sweep
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    jobs = sweep.make_jobs(['a.png', 'b.png', 'c.png'], alphas=[0.1, 0.5], snrs=[0., 20., 30.])[:17]     # ragged shares
+
+    def batch_runner(group):
+        if fail and any(j['id'] == 6 for j in group):
+            raise RuntimeError('boom')
+        return [dict(id=j['id'], image=str(j['image']), alpha=j['alpha'], snr=j['snr'], algo='pnp_svrg', denoiser='TV',
+                     psnr_init=10.0 + j['id'], psnr_final=20.0 + j['id'], iters=7, seconds=0.5) for j in group]
+    recs = sweep.run_partitioned_batched(jobs, batch_runner, rank, world, batch=4)
+    q.put((rank, recs))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize('fail', [False, True])
+def test_world_size_2_gloo_batched_gather(fail):
+    """run_partitioned_batched: numeric records travel as one tensor all-gather (pickling fallback on errors)."""
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = 31500 + os.getpid() % 2000 + int(fail)
+    procs = [ctx.Process(target=_worker_batched, args=(r, 2, port, q, fail)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = dict(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert got[0] == got[1]
+    recs = got[0]
+    assert [r['id'] for r in recs] == list(range(17))
+    assert all(r['rank'] == r['id'] % 2 for r in recs)
+    ok = [r for r in recs if 'error' not in r]
+    assert all(r['psnr_final'] == 20.0 + r['id'] and r['psnr_init'] == 10.0 + r['id'] and r['iters'] == 7 and r['denoiser'] == 'TV'
+               for r in ok)
+    assert len(ok) == (17 if not fail else 13) and (not fail or all('boom' in r['error'] for r in recs if 'error' in r))
+
+
 def test_partition_covers_every_job_once():
     from pnp_svrg_b200 import sweep
     jobs = sweep.make_jobs(['x'] * 12)
