@@ -113,6 +113,7 @@ def reconstruct_batch(jobs, H=256, W=256, eta_scale=0.15, T2=10, mini_batch_size
         run = _RUNNERS.get(key)                      # same shape as an earlier batch: reuse buffers and the captured graph
         if run is None:
             run = _RUNNERS[key] = BatchedSVRG(batch, T2=T2, mini_batch_size=B, etas=etas, seed=seed, max_slots=iters)
+            run.whole_run_graph = True
         else:
             run.reload(batch, etas)
         run.run(iters)
