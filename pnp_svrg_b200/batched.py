@@ -42,6 +42,9 @@ def csmri_host_spec(image, H, W, sample_prob, snr, rng=np.random):
                 support=np.flatnonzero(mask).astype(np.int32), data_range=1.0 if xrec.min() >= 0 else 2.0)
 
 
+_IMAGE_CACHE = {}
+
+
 def csmri_device_batch(images, sample_probs, snrs, H, W, seed=0, device=None):
     """Construction of a whole batch of CSMRI problems ON THE DEVICE (the step before the hot path, SURVEY section
     8(f) rank 2): same model as problems/CSMRI.py:12-41 -- Bernoulli(p) mask, Y = mask o (fft2(X) + N(0, sigma)) with
@@ -52,7 +55,13 @@ def csmri_device_batch(images, sample_probs, snrs, H, W, seed=0, device=None):
     from .problems.problem import load_image
     dev = device or D.require_cuda()
     nb, hp = len(images), H // 2
-    x = torch.from_numpy(np.stack([load_image(None, im, H, W) for im in images]).astype(np.float32)).to(dev)
+    def normalised(im):                       # sweeps revisit the same few images: normalise each array once
+        key = (id(im), H, W)
+        hit = _IMAGE_CACHE.get(key)
+        if hit is None or hit[0] is not im:
+            hit = _IMAGE_CACHE[key] = (im, load_image(None, im, H, W).astype(np.float32))
+        return hit[1]
+    x = torch.from_numpy(np.stack([normalised(im) for im in images])).to(dev)
     gen = torch.Generator(device=dev)
     gen.manual_seed(int(seed))
     p = torch.tensor(np.asarray(sample_probs, dtype=np.float32), device=dev).view(nb, 1, 1)
