@@ -120,3 +120,26 @@ def test_integration_stub_mirrors_the_struct():
     block = text[text.index('class GradArgs(C.Structure)'):text.index('lib.pnp_init.restype')]
     names = re.findall(r"\('(\w+)',", block)
     assert names == [f[0] for f in _lib.CsmriGradArgs._fields_]
+
+
+def test_feistel_is_a_permutation_and_the_c_twin_agrees():
+    """The unbalanced Feistel network (domain 2^hb x ceil(n / 2^hb) + cycle walking) must be a bijection of [0, n)
+    for every n -- powers of two, one above / below them, primes, tiny -- and the vectorised C sampler of the host
+    path (pnp_sample_indices_host) must reproduce the NumPy twin bit for bit, threads or not, gather or not."""
+    from pnp_svrg_b200 import _lib
+    from pnp_svrg_b200.engine import feistel_sample
+    lib = _lib.load()
+    for n in (1, 2, 3, 4, 5, 15, 16, 17, 63, 64, 65, 97, 1000, 1023, 1024, 1025, 4093, 19661, 65536, 65537):
+        ref = feistel_sample(n, n, seed=5, counter=n)
+        assert np.array_equal(np.sort(ref), np.arange(n)), n
+        out = np.empty(n, dtype=np.int32)
+        assert lib.pnp_sample_indices_host(out.ctypes.data, n, n, 5, n, 0, 1, None) == 0
+        assert np.array_equal(out, ref), n
+    n, c = 1258000, 100000
+    sup = (np.arange(n, dtype=np.int64) * 3 + 1).astype(np.int32)
+    ref = sup[feistel_sample(n, c, 123, 7, 0)]
+    for threads in (1, 4):
+        out = np.empty(c, dtype=np.int32)
+        assert lib.pnp_sample_indices_host(out.ctypes.data, n, c, 123, 7, 0, threads, sup.ctypes.data) == 0
+        assert np.array_equal(out, ref)
+    assert len(np.unique(ref)) == c
