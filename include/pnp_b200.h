@@ -300,7 +300,9 @@ int pnp_advance_scale(int* counters, int n, float* x, float factor, void* stream
 /* dst[0..n) = src[0..n)  (w = copy(z), algorithms/pnp_svrg.py:35; capturable device copy) */
 int pnp_copy_f32(float* dst, const float* src, long long n, void* stream);
 
-/* debugging knobs (key 1: tensor-core conv epilogue ablation bits); not part of the stable surface */
+/* debugging knobs, not part of the stable surface.  key 1: ablation bits of the tensor-core conv (1 no output
+ * shift shuffles, 2 no epilogue arithmetic / stores, 4 load one dl block only, 32 never use the multi-layer launch);
+ * key 2: print the phase times of the last pnp_csmri_update_prox (builds with -DPNP_PHASE_TIMING only). */
 int pnp_debug_set(int key, int value);
 
 /* ---- CUDA-graph helpers ---------------------------------------------------------------------
