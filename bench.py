@@ -222,14 +222,18 @@ class Epoch:
                 h('c2r+update+prox_fused(sigma+haar+psnr)')
             else:
                 p._dev_grad(eng.z, phases=4, **gk); h('lines_c2r+update')
+        # kernels launched by this iteration: sel_sample + r2c + cols + [tail] | [c2r + (prox | sigma + haar) + advance]
         if fused:
             self.den.t += 1
+            self.n_launch_inner = 4
         elif FUSED_PROX and self.den._dev_prox_fused(self._ctx()):
             h('prox_fused(sigma+haar+psnr)')
+            self.n_launch_inner = 6
         else:
             eng.check(eng.lib.pnp_estimate_sigma(self.D.ptr(eng.z), eng.H, eng.W, 1, self.D.ptr(eng.sig_log),
                                                  self.D.ptr(eng.slot_ptr), eng.sptr)); h('sigma_mad')
             self.den._dev_denoise(self._ctx()); h('haar_bayes+psnr')
+            self.n_launch_inner = 7
         if not fused:                                      # the fused tail bumps the iteration counters itself
             eng.advance(); h('advance')
 
@@ -267,7 +271,6 @@ class Epoch:
 
 FUSED_TAIL = os.environ.get('PNP_BENCH_FUSED_TAIL', '1') == '1'      # pass 3 + update + sigma + wavelet + PSNR as one cooperative launch
 FUSED_PROX = os.environ.get('PNP_BENCH_FUSED_PROX', '1') == '1'    # sigma + wavelet + PSNR as one cooperative launch
-LAUNCHES_PER_INNER = 7 - int(FUSED_PROX) - 2 * int(FUSED_TAIL and FUSED_PROX)   # sel_sample + r2c + cols + c2r + sigma_mad + haar_bayes + advance
 LAUNCHES_PER_SNAPSHOT = 4     # r2c + cols + c2r + D2D copy
 
 
@@ -327,7 +330,7 @@ def run_b200(a, cfg, rank, world, local_rank):
         'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': a.steps, 'warmup': a.warmup,
         'ms_per_step': total_ms / a.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
         'dtype': 'f32', 'data': 'synthetic', 'config': cfg,
-        'gpu_launches': a.steps * (T2 * LAUNCHES_PER_INNER + LAUNCHES_PER_SNAPSHOT),
+        'gpu_launches': a.steps * (T2 * ep.n_launch_inner + LAUNCHES_PER_SNAPSHOT),
         'clocks': clocks, 'wall_s_timed_region': t_wall,
         'psnr_first_last': [float(psnr[0]), float(psnr[-1])] if psnr else None,
         'us_per_inner_iteration': 1e3 * total_ms / (a.steps * T2),
