@@ -636,7 +636,8 @@ int pnp_csmri_update_prox(const float* S, int H, int W, float gscale, float step
     if (!S || !vadd || !z_in || !z_out || !sig_log) return fail(PNP_ERR_ARG, "bad argument");
     if (advance_counters && (n_advance < 1 || n_advance > 32)) return fail(PNP_ERR_ARG, "n_advance must be in [1, 32]");
     if (!pow2_ok(H) || W < 2 || (W & 1)) return fail(PNP_ERR_ARG, "H must be a power of two in [32, 4096], W even");
-    if (H < 128) return fail(PNP_ERR_UNSUPPORTED, "update+prox: lines shorter than 128 samples use the separate kernels");
+    // (below 512 samples a round would hold more than 16 transforms, whose exchange planes are only 4-byte aligned)
+    if (H < 512) return fail(PNP_ERR_UNSUPPORTED, "update+prox: lines shorter than 512 samples use the separate kernels");
     const float inv_n = (float)(1.0 / ((double)H * (double)W));
     return dispatch_update_prox(H, reinterpret_cast<const float*>(S), W, inv_n, gscale, step, step_ptr, vadd, z_in, z_out, xrec,
                                 sigma_modifier, fallback_sigma, sig_log, mse_log, slot, advance_counters, n_advance,
