@@ -151,6 +151,62 @@ struct TcLast {
     CnnIo io;
 };
 
+// Epilogue of one 128-position tile of a 64 -> 64 layer for one epilogue warp (TMEM quadrant of accumulator `t0`,
+// channel half hf): two chunks of 16 channels -- TMEM -> registers, output shift by warp shuffles, + shift, activation,
+// bf16 pack, swizzled staging and one TMA tensor store per chunk.  The accumulator is handed back (tempty) as soon as
+// the second chunk has been read.  Shared by k_conv_tc<64> and k_conv_tc_stack.
+__device__ __forceinline__ void tc_epilogue_tile64(unsigned t0, TcSmem* ctl, unsigned char* sO, const CUtensorMap* tmO, int ew,
+                                                   int wg, int hf, int lane, int s, bool pad, bool interior, bool relu,
+                                                   float slope, int dbg) {
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {                                         // two chunks of 16 channels
+        const int c = 32 * hf + 16 * j;
+        float tm[16], tz[16], tp[16], sh[16];
+        tmem_ld16(t0 + c, tm);              // T_-1 of this lane's row
+        tmem_ld16(t0 + 64 + c, tz);         // T_0
+        tmem_ld16(t0 + 128 + c, tp);        // T_+1
+#pragma unroll
+        for (int i = 0; i < 4; ++i) reinterpret_cast<float4*>(sh)[i] = reinterpret_cast<const float4*>(ctl->shift + c)[i];
+        asm volatile("tcgen05.wait::ld.sync.aligned;");
+        if (j == 1) {                                                     // accumulator read: hand it back before the math
+            asm volatile("tcgen05.fence::before_thread_sync;");
+            if (lane == 0) mbar_arrive(&ctl->tempty[wg]);
+        }
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // staging buffer j is free again
+        __syncwarp();
+        if (dbg & 2) continue;
+        uint4 pk[2];
+        __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(pk);
+#pragma unroll
+        for (int i = 0; i < 16; i += 2) {
+            float o2[2];
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const float up = __shfl_up_sync(0xffffffffu, tm[i + u], 1);      // T_-1 of row - 1
+                const float dn = __shfl_down_sync(0xffffffffu, tp[i + u], 1);    // T_+1 of row + 1
+                const float v = (up + tz[i + u]) + (dn + sh[i + u]);
+                o2[u] = relu ? fmaxf(v, 0.f) : fmaxf(v, v * slope);              // leaky ReLU needs slope <= 1
+            }
+            h[i >> 1] = __floats2bfloat162_rn(o2[0], o2[1]);
+        }
+        if (pad) pk[0] = pk[1] = make_uint4(0u, 0u, 0u, 0u);
+        // 30 rows x 32 B per chunk; 16-byte chunk index XOR (row / 4) % 2  ==  CU_TENSOR_MAP_SWIZZLE_32B
+        unsigned char* stage_o = sO + (ew * 2 + j) * TC_O_WARP_BYTES;
+        if (interior) {
+            const int r = lane - 1;
+#pragma unroll
+            for (int k = 0; k < 2; ++k) *reinterpret_cast<uint4*>(stage_o + r * 32 + ((k ^ ((r >> 2) & 1)) << 4)) = pk[k];
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) {
+            asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                         ::"l"(tmO), "r"(smem_u32(stage_o)), "r"(c), "r"(s + 1) : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+    }
+}
+
 // in / out: bf16 [S][64] with S = PH*(PW+1) positions.  tmA over `in` with box 64 x 32: every TMEM lane
 // quadrant (32 rows) of a tile gets its own 32 consecutive positions, overlapping its neighbours by
 // two, so that rows 0 and 31 of each quadrant are halo and the output shift never leaves a warp.
@@ -279,53 +335,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             asm volatile("tcgen05.fence::after_thread_sync;");
             if (CO == 64) {
                 const bool pad = (s % pitch) == PW;                                   // the pad pixel of a line stays zero
-#pragma unroll
-                for (int j = 0; j < 2; ++j) {                                         // two chunks of 16 channels
-                    const int c = 32 * hf + 16 * j;
-                    float tm[16], tz[16], tp[16], sh[16];
-                    tmem_ld16(t0 + c, tm);              // T_-1 of this lane's row
-                    tmem_ld16(t0 + 64 + c, tz);         // T_0
-                    tmem_ld16(t0 + 128 + c, tp);        // T_+1
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) reinterpret_cast<float4*>(sh)[i] = reinterpret_cast<const float4*>(ctl->shift + c)[i];
-                    asm volatile("tcgen05.wait::ld.sync.aligned;");
-                    if (j == 1) {                                                     // accumulator read: hand it back before the math
-                        asm volatile("tcgen05.fence::before_thread_sync;");
-                        if (lane == 0) mbar_arrive(&ctl->tempty[wg]);
-                    }
-                    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // staging buffer j is free again
-                    __syncwarp();
-                    if (dbg & 2) continue;
-                    uint4 pk[2];
-                    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(pk);
-#pragma unroll
-                    for (int i = 0; i < 16; i += 2) {
-                        float o2[2];
-#pragma unroll
-                        for (int u = 0; u < 2; ++u) {
-                            const float up = __shfl_up_sync(0xffffffffu, tm[i + u], 1);      // T_-1 of row - 1
-                            const float dn = __shfl_down_sync(0xffffffffu, tp[i + u], 1);    // T_+1 of row + 1
-                            const float v = (up + tz[i + u]) + (dn + sh[i + u]);
-                            o2[u] = relu ? fmaxf(v, 0.f) : fmaxf(v, v * slope);              // leaky ReLU needs slope <= 1
-                        }
-                        h[i >> 1] = __floats2bfloat162_rn(o2[0], o2[1]);
-                    }
-                    if (pad) pk[0] = pk[1] = make_uint4(0u, 0u, 0u, 0u);
-                    // 30 rows x 32 B per chunk; 16-byte chunk index XOR (row / 4) % 2  ==  CU_TENSOR_MAP_SWIZZLE_32B
-                    unsigned char* stage_o = sO + (ew * 2 + j) * TC_O_WARP_BYTES;
-                    if (interior) {
-                        const int r = lane - 1;
-#pragma unroll
-                        for (int k = 0; k < 2; ++k) *reinterpret_cast<uint4*>(stage_o + r * 32 + ((k ^ ((r >> 2) & 1)) << 4)) = pk[k];
-                    }
-                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                    __syncwarp();
-                    if (lane == 0) {
-                        asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
-                                     ::"l"(&tmO), "r"(smem_u32(stage_o)), "r"(c), "r"(s + 1) : "memory");
-                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-                    }
-                }
+                tc_epilogue_tile64(t0, ctl, sO, &tmO, ew, wg, hf, lane, s, pad, interior, relu, slope, dbg);
             } else {
                 // last layer: one output per position + the wrapper's output map
                 float t[4];
@@ -512,51 +522,7 @@ k_conv_tc_stack(const __grid_constant__ TcStack pm, int PW, int S, int n_tiles) 
                 mbar_wait_bounded(&ctl->tfull[wg], aphase);
                 asm volatile("tcgen05.fence::after_thread_sync;");
                 const bool pad = (s % pitch) == PW;
-#pragma unroll
-                for (int j = 0; j < 2; ++j) {
-                    const int c = 32 * hf + 16 * j;
-                    float tm[16], tz[16], tp[16], sh[16];
-                    tmem_ld16(t0 + c, tm);
-                    tmem_ld16(t0 + 64 + c, tz);
-                    tmem_ld16(t0 + 128 + c, tp);
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) reinterpret_cast<float4*>(sh)[i] = reinterpret_cast<const float4*>(ctl->shift + c)[i];
-                    asm volatile("tcgen05.wait::ld.sync.aligned;");
-                    if (j == 1) {
-                        asm volatile("tcgen05.fence::before_thread_sync;");
-                        if (lane == 0) mbar_arrive(&ctl->tempty[wg]);
-                    }
-                    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-                    __syncwarp();
-                    uint4 pk[2];
-                    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(pk);
-#pragma unroll
-                    for (int i = 0; i < 16; i += 2) {
-                        float o2[2];
-#pragma unroll
-                        for (int u = 0; u < 2; ++u) {
-                            const float up = __shfl_up_sync(0xffffffffu, tm[i + u], 1);
-                            const float dn = __shfl_down_sync(0xffffffffu, tp[i + u], 1);
-                            const float v = (up + tz[i + u]) + (dn + sh[i + u]);
-                            o2[u] = relu ? fmaxf(v, 0.f) : fmaxf(v, v * slope);
-                        }
-                        h[i >> 1] = __floats2bfloat162_rn(o2[0], o2[1]);
-                    }
-                    if (pad) pk[0] = pk[1] = make_uint4(0u, 0u, 0u, 0u);
-                    unsigned char* stage_o = sO + (ew * 2 + j) * TC_O_WARP_BYTES;
-                    if (interior) {
-                        const int r = lane - 1;
-#pragma unroll
-                        for (int k = 0; k < 2; ++k) *reinterpret_cast<uint4*>(stage_o + r * 32 + ((k ^ ((r >> 2) & 1)) << 4)) = pk[k];
-                    }
-                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                    __syncwarp();
-                    if (lane == 0) {
-                        asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
-                                     ::"l"(tmO), "r"(smem_u32(stage_o)), "r"(c), "r"(s + 1) : "memory");
-                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-                    }
-                }
+                tc_epilogue_tile64(t0, ctl, sO, tmO, ew, wg, hf, lane, s, pad, interior, relu, slope, 0);
             }
             if (lane == 0) {                              // this layer's stores are complete before the grid barrier
                 asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
