@@ -197,6 +197,112 @@ def _gather_records(jobs, local, rank, world):
     return out
 
 
+# ------------------------------------------------------------------------------------------ tuning sweeps
+# The reference's sweep scripts do not run fixed hyper-parameters: every grid cell is a hyperopt search over the
+# tune_pnp_* objective (script_diff_sampratio_set12.py:41-134, script_diff_snr_set12.py likewise).  The helpers
+# below keep that shape -- get_problem / get_denoiser / get_proxy_pspace / one CSV row per cell -- on top of
+# pnp_svrg_b200.search, so a cell is `tune_job(job)` and a sweep is run_partitioned(jobs, tune_job, rank, world).
+TIME_PER_TRIAL = 30               # script_diff_sampratio_set12.py:34-35
+MAX_EVALS = 100
+ETA_RANGE, MB_RANGE, T2_RANGE, DSTR_RANGE = (0, 100), (1, 100), (1, 100), (0, 2)      # :37-40
+TUNE_ARGS = {                     # order of the objective's positional tuple (algorithms/pnp_*.py tune_pnp_*)
+    'pnp_gd': ('eta', 'dstrength'),
+    'pnp_sgd': ('eta', 'mini_batch_size', 'dstrength'),
+    'pnp_saga': ('eta', 'mini_batch_size', 'dstrength'),
+    'pnp_sarah': ('eta', 'mini_batch_size', 'T2', 'dstrength'),
+    'pnp_svrg': ('eta', 'mini_batch_size', 'T2', 'dstrength'),
+}
+
+
+def get_problem(prob_name, im_path, alpha, snr, H=256, W=256, kernel='Minimal', image=None, pr_size=32):
+    """script_diff_sampratio_set12.py:41-51.  ``alpha`` is the sampling ratio as a fraction in (0, 1] (the
+    reference's ALPHA_LIST holds 1..10 and divides by ten); PR runs at 32 x 32 there (dense A)."""
+    from . import problems as PR
+    kw = dict(image=image) if image is not None else dict(img_path=im_path)
+    if prob_name == 'CSMRI':
+        return PR.CSMRI(H=H, W=W, sample_prob=alpha, snr=snr, **kw)
+    if prob_name == 'DeblurSR':
+        return PR.Deblur(kernel=kernel, H=H, W=W, scale_percent=int(round(alpha * 100)), snr=snr, **kw)
+    if prob_name == 'PR':
+        return PR.PhaseRetrieval(H=pr_size, W=pr_size, num_meas=int(alpha * 10 * pr_size * pr_size), snr=snr, **kw)
+    raise Exception('Problem name "{0}" not found'.format(prob_name))
+
+
+def get_denoiser(dnr_name):
+    """script_diff_sampratio_set12.py:53-63 (its 'CNN' branch names a class that does not exist there)."""
+    from . import denoisers as DN
+    table = {'BM3D': DN.BM3DDenoiser, 'NLM': DN.NLMDenoiser, 'TV': DN.TVDenoiser}
+    if dnr_name not in table:
+        raise Exception('Denoiser name "{0}" not found'.format(dnr_name))
+    return table[dnr_name]()
+
+
+def get_pspace(algo_name, eta=ETA_RANGE, mb=MB_RANGE, T2=T2_RANGE, dstr=DSTR_RANGE):
+    """The search space of one algorithm as the tuple its tune_pnp_* objective unpacks (:65-107)."""
+    from .search import hp, quniform, scope
+    if algo_name not in TUNE_ARGS:
+        raise Exception('Algorithm name "{0}" not found'.format(algo_name))
+    nodes = {'eta': lambda: hp.uniform('eta', *eta),
+             'mini_batch_size': lambda: scope.int(quniform('mini_batch_size', mb[0], mb[1], q=1)),
+             'T2': lambda: scope.int(quniform('T2', T2[0], T2[1], q=1)),
+             'dstrength': lambda: hp.uniform('dstrength', *dstr)}
+    return tuple(nodes[k]() for k in TUNE_ARGS[algo_name])
+
+
+def get_proxy_pspace(main_problem, algo_name, denoiser, tt=TIME_PER_TRIAL, spaces=None, **extra):
+    """(objective, space) of one grid cell; ``extra`` goes to the loop (max_iters=, fast=, mb_source=, ...)."""
+    from functools import partial
+    from . import algorithms as ALG
+    pspace = get_pspace(algo_name, **(spaces or {}))
+    proxy = partial(getattr(ALG, 'tune_' + algo_name), problem=main_problem, denoiser=denoiser, tt=tt, verbose=False,
+                    lr_decay=1, converge_check=True, diverge_check=True, **extra)
+    return proxy, pspace
+
+
+def tuning_row(job, trials, best):
+    """One CSV row in the reference's layout (:129-133): problem, denoiser, algorithm, alpha, snr, best loss,
+    'PARAMETERS:', then label, value pairs."""
+    row = [job['problem'], job['denoiser'], job['algo'], job['alpha'], job['snr'],
+           trials.best_trial['result']['loss'], 'PARAMETERS:']
+    for key in best:
+        row.append(key)
+        row.append(best[key])
+    return row
+
+
+def tune_job(job, max_evals=MAX_EVALS, tt=TIME_PER_TRIAL, seed=0, H=256, W=256, images=None, spaces=None, algo='tpe',
+             **extra):
+    """Hyper-parameter search of one grid cell on the current GPU; returns a record whose 'row' is the CSV row."""
+    from . import search
+    img = job['image']
+    image = images[img] if images is not None and not isinstance(img, str) else None
+    np.random.seed(seed + job['id'])
+    p = get_problem(job['problem'], img if image is None else None, job['alpha'], job['snr'], H=H, W=W, image=image)
+    dnr = get_denoiser(job['denoiser'])
+    space_kw = dict(spaces or {})
+    if 'mb' not in space_kw:                         # a minibatch cannot exceed the measurements there are
+        cap = int(getattr(p, 'M0', p.M))
+        space_kw['mb'] = (MB_RANGE[0], max(MB_RANGE[0] + 1, min(MB_RANGE[1], cap)))
+    proxy, pspace = get_proxy_pspace(p, job['algo'], dnr, tt=tt, spaces=space_kw, **extra)
+    trials = search.Trials()
+    t0 = time.time()
+    best = search.fmin(proxy, space=pspace, algo={'tpe': search.tpe.suggest, 'rand': search.rand.suggest}[algo],
+                       trials=trials, max_evals=max_evals, rstate=np.random.default_rng(seed + job['id']), catch=True)
+    return dict(id=job['id'], image=str(img), problem=job['problem'], denoiser=job['denoiser'], algo=job['algo'],
+                alpha=job['alpha'], snr=job['snr'], loss=float(trials.best_trial['result']['loss']), best=dict(best),
+                trials=len(trials), seconds=time.time() - t0, row=tuning_row(job, trials, best))
+
+
+def write_tuning_csv(path, records):
+    """The sweep scripts' output file (:155-160): a 'Results:' line, then one row per grid cell."""
+    with open(path, 'w', newline='') as f:
+        w = csv.writer(f, delimiter=',')
+        w.writerow(['Results:'])
+        for r in records:
+            if 'row' in r:
+                w.writerow(r['row'])
+
+
 def main():
     import torch
     import torch.distributed as dist
@@ -205,6 +311,10 @@ def main():
     ap.add_argument('--out', default='sweep.csv')
     ap.add_argument('--iters', type=int, default=200)
     ap.add_argument('--size', type=int, default=256)
+    ap.add_argument('--tune', type=int, default=0, metavar='MAX_EVALS',
+                    help='search the hyper-parameters of every grid cell with this many trials (the reference scripts use 100) '
+                         'and write the tuning CSV instead of fixed-parameter reconstructions')
+    ap.add_argument('--tt', type=float, default=TIME_PER_TRIAL, help='wall-clock budget of one trial in seconds')
     a = ap.parse_args()
     rank = int(os.environ.get('RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
@@ -214,6 +324,14 @@ def main():
     files = sorted(os.path.join(a.images, f) for f in os.listdir(a.images) if f.lower().endswith(('.png', '.jpg')))
     jobs = make_jobs(files)
     t0 = time.time()
+    if a.tune > 0:
+        recs = run_partitioned(jobs, lambda j: tune_job(j, max_evals=a.tune, tt=a.tt, H=a.size, W=a.size), rank, world)
+        if rank == 0:
+            write_tuning_csv(a.out, recs)
+            print('%d grid cells tuned (%d trials each) in %.1f s on %d GPU(s)' % (len(recs), a.tune, time.time() - t0, world))
+        if world > 1:
+            dist.destroy_process_group()
+        return
     recs = run_partitioned(jobs, lambda j: reconstruct(j, H=a.size, W=a.size, iters=a.iters), rank, world)
     if rank == 0:
         with open(a.out, 'w', newline='') as f:

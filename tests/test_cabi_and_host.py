@@ -93,11 +93,18 @@ def test_budget_and_stop_rule():
 def test_reference_names_alias():
     import sys
     import pnp_svrg_b200
-    saved = {k: sys.modules.get(k) for k in ('problems', 'denoisers', 'algorithms')}
+    names = ('problems', 'denoisers', 'algorithms', 'Utilities', 'hyperopt', 'hyperopt.hp', 'hyperopt.pyll')
+    saved = {k: sys.modules.get(k) for k in names}
     try:
         for k in saved:
             sys.modules.pop(k, None)
-        pnp_svrg_b200.install_as_reference()
+        pnp_svrg_b200.install_as_reference(hyperopt=True)
+        # the import block of the sweep scripts (script_diff_sampratio_set12.py:1-5) and of the notebooks
+        from hyperopt import fmin, tpe, hp, Trials          # noqa: F401
+        from hyperopt.hp import quniform
+        from hyperopt.pyll import scope
+        from Utilities import display_results               # noqa: F401
+        assert scope.int(quniform('T2', 1, 100, q=1)).as_int and hp.uniform('eta', 0, 100).label == 'eta'
         from algorithms import pnp_svrg, tune_pnp_svrg      # noqa: F401
         from denoisers import TVDenoiser                    # noqa: F401
         from problems import CSMRI, Deblur, PhaseRetrieval  # noqa: F401
