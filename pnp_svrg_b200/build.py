@@ -5,6 +5,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, 'csrc', 'pnp_b200.cu')
+HOST_SRC = os.path.join(HERE, 'csrc', 'host_sampler.cpp')     # plain C++: nvcc hands it to the host compiler
 OUT = os.path.join(HERE, 'lib', 'libpnp_b200.so')
 NVCC_FLAGS = ['-std=c++17', '-O3', '-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo',
               '-shared', '-Xcompiler', '-fPIC']
@@ -24,7 +25,7 @@ def build(force=False, verbose=False):
             return OUT
     nvcc = os.environ.get('NVCC', 'nvcc')
     extra = os.environ.get('PNP_NVCC_EXTRA', '').split()          # e.g. -DPNP_PHASE_TIMING for scripts/prof_phases.py
-    cmd = [nvcc] + NVCC_FLAGS + extra + (['-Xptxas', '-v'] if verbose else []) + ['-o', OUT, SRC]
+    cmd = [nvcc] + NVCC_FLAGS + extra + (['-Xptxas', '-v'] if verbose else []) + ['-o', OUT, SRC, HOST_SRC]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         sys.stderr.write(r.stdout + r.stderr)

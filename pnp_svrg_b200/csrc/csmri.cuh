@@ -590,7 +590,7 @@ __device__ __forceinline__ unsigned mix32(unsigned x) {
 // Generalised (unbalanced) Feistel network on Z_b x Z_a with a = 2^hb >= sqrt(n) and b = ceil(n / a): the domain
 // a*b exceeds n by less than a, so cycle walking almost never iterates (a balanced 2^(2 hb) domain needs up to 4
 // passes per index).  Rounds alternate (l, r) -> (r, (l + F(r)) mod b) and (l, r) -> (r, (l + F(r)) mod a); the
-// reduction of F to [0, b) is a multiply-high, so there is no division.  Host twins: h_feistel (pnp_b200.cu) and
+// reduction of F to [0, b) is a multiply-high, so there is no division.  Host twins: host_sampler.cpp and
 // engine.feistel_sample (NumPy) produce the same sequence bit for bit.
 __device__ __forceinline__ unsigned feistel_perm(unsigned i, unsigned n, unsigned key) {
     int hb = 1;

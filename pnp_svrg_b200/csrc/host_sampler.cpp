@@ -1,0 +1,163 @@
+// Host twin of the device minibatch sampler (csmri.cuh::feistel_perm): the cycle-walking unbalanced Feistel
+// permutation over a block of consecutive inputs, and the gather through the k-space support.  Plain C++ (compiled by the host compiler, linked into libpnp_b200.so); the
+// AVX2 body is hand-written because the multiply-high that reduces the round function to [0, b) does not
+// auto-vectorise well (gcc widens the whole round to 4 x 64-bit lanes): 8 indices per instruction, even and odd
+// lanes multiplied by vpmuludq and blended back, four independent vectors interleaved to cover the vpmulld latency.
+// Picked at run time; the scalar body is the definition.  100 000 of 1 258 000 positions through the support on one
+// 2 GHz core: 0.57 ms (0.23 ms permutation + 0.34 ms of cache misses in the gather); 0.92 ms auto-vectorised.
+#include "host_sampler.h"
+
+#if defined(__GNUC__) && defined(__x86_64__)
+#include <immintrin.h>
+#define PNP_HAVE_AVX2_PATH 1
+#endif
+
+namespace pnp_host {
+
+unsigned feistel_pass(unsigned x, unsigned n, unsigned key, int hb) {
+    const unsigned hm = (1u << hb) - 1u;
+    const unsigned b = (n + hm) >> hb;
+    unsigned l = x >> hb, r = x & hm;
+    for (int rd = 0; rd < 4; rd += 2) {
+        const unsigned f0 = (unsigned)(((unsigned long long)mix32(r ^ (key + 0x9e3779b9U * (rd + 1))) * b) >> 32);
+        unsigned t = l + f0;
+        t -= (t >= b) ? b : 0u;
+        l = r;
+        r = t;
+        const unsigned f1 = mix32(r ^ (key + 0x9e3779b9U * (rd + 2))) & hm;
+        t = (l + f1) & hm;
+        l = r;
+        r = t;
+    }
+    return (l << hb) | r;
+}
+
+static void feistel_block_scalar(unsigned first, unsigned* out, int cnt, unsigned n, unsigned key, int hb) {
+    for (int j = 0; j < cnt; ++j) {
+        unsigned p = feistel_pass(first + (unsigned)j, n, key, hb);
+        while (p >= n) p = feistel_pass(p, n, key, hb);
+        out[j] = p;
+    }
+}
+
+#ifdef PNP_HAVE_AVX2_PATH
+__attribute__((target("avx2"))) static inline __m256i mix32_v(__m256i x) {
+    x = _mm256_xor_si256(x, _mm256_srli_epi32(x, 16));
+    x = _mm256_mullo_epi32(x, _mm256_set1_epi32((int)0x7feb352dU));
+    x = _mm256_xor_si256(x, _mm256_srli_epi32(x, 15));
+    x = _mm256_mullo_epi32(x, _mm256_set1_epi32((int)0x846ca68bU));
+    x = _mm256_xor_si256(x, _mm256_srli_epi32(x, 16));
+    return x;
+}
+
+// high 32 bits of the unsigned 32 x 32 product, all eight lanes (vb holds b in every lane)
+__attribute__((target("avx2"))) static inline __m256i mulhi_u32_v(__m256i x, __m256i vb) {
+    const __m256i even = _mm256_srli_epi64(_mm256_mul_epu32(x, vb), 32);                 // lanes 0,2,4,6 -> low halves
+    const __m256i odd = _mm256_mul_epu32(_mm256_srli_epi64(x, 32), vb);                  // lanes 1,3,5,7 -> high halves
+    return _mm256_blend_epi32(even, odd, 0xAA);
+}
+
+__attribute__((target("avx2"))) static void feistel_block_avx2(unsigned first, unsigned* out, int cnt, unsigned n,
+                                                                unsigned key, int hb) {
+    const unsigned hm = (1u << hb) - 1u;
+    const unsigned b = (n + hm) >> hb;
+    const __m256i vhm = _mm256_set1_epi32((int)hm), vb = _mm256_set1_epi32((int)b);
+    const __m256i vbm1 = _mm256_set1_epi32((int)(b - 1u));
+    const __m128i sh = _mm_cvtsi32_si128(hb);
+    const __m256i vnm1 = _mm256_set1_epi32((int)(n - 1u));
+    __m256i k[4];
+    for (int rd = 0; rd < 4; ++rd) k[rd] = _mm256_set1_epi32((int)(key + 0x9e3779b9U * (unsigned)(rd + 1)));
+    __m256i x = _mm256_add_epi32(_mm256_set1_epi32((int)first), _mm256_setr_epi32(0, 1, 2, 3, 4, 5, 6, 7));
+    int j = 0;
+    constexpr int U = 4;                                                                  // independent chains in flight
+    const __m256i step = _mm256_set1_epi32(8 * U);
+    __m256i xs[U];
+    for (int u = 0; u < U; ++u) xs[u] = _mm256_add_epi32(x, _mm256_set1_epi32(8 * u));
+    for (; j + 8 * U <= cnt; j += 8 * U) {
+        __m256i l[U], r[U];
+        for (int u = 0; u < U; ++u) {
+            l[u] = _mm256_srl_epi32(xs[u], sh);
+            r[u] = _mm256_and_si256(xs[u], vhm);
+            xs[u] = _mm256_add_epi32(xs[u], step);
+        }
+        for (int rd = 0; rd < 4; rd += 2) {
+            for (int u = 0; u < U; ++u) {
+                const __m256i f0 = mulhi_u32_v(mix32_v(_mm256_xor_si256(r[u], k[rd])), vb);
+                __m256i t = _mm256_add_epi32(l[u], f0);
+                t = _mm256_sub_epi32(t, _mm256_and_si256(_mm256_cmpgt_epi32(t, vbm1), vb));
+                l[u] = r[u];
+                r[u] = t;
+            }
+            for (int u = 0; u < U; ++u) {
+                const __m256i f1 = mix32_v(_mm256_xor_si256(r[u], k[rd + 1]));
+                const __m256i t = _mm256_and_si256(_mm256_add_epi32(l[u], f1), vhm);
+                l[u] = r[u];
+                r[u] = t;
+            }
+        }
+        int over = 0;
+        for (int u = 0; u < U; ++u) {
+            const __m256i v = _mm256_or_si256(_mm256_sll_epi32(l[u], sh), r[u]);
+            over |= _mm256_movemask_epi8(_mm256_cmpgt_epi32(v, vnm1));          // outside [0, n): walk the cycle (rare)
+            _mm256_storeu_si256(reinterpret_cast<__m256i*>(out + j + 8 * u), v);
+        }
+        if (over)
+            for (int q = j; q < j + 8 * U; ++q)
+                while (out[q] >= n) out[q] = feistel_pass(out[q], n, key, hb);
+    }
+    for (; j < cnt; ++j) {
+        unsigned p = feistel_pass(first + (unsigned)j, n, key, hb);
+        while (p >= n) p = feistel_pass(p, n, key, hb);
+        out[j] = p;
+    }
+}
+__attribute__((target("avx2"))) static void gather_avx2(int* out, const unsigned* idx, int cnt, const int* support) {
+    int j = 0;
+    for (; j + 8 <= cnt; j += 8)
+        _mm256_storeu_si256(reinterpret_cast<__m256i*>(out + j),
+                            _mm256_i32gather_epi32(support, _mm256_loadu_si256(reinterpret_cast<const __m256i*>(idx + j)), 4));
+    for (; j < cnt; ++j) out[j] = support[idx[j]];
+}
+#endif
+
+#ifdef PNP_HAVE_AVX2_PATH
+static bool have_avx2() {
+    static const bool v = __builtin_cpu_supports("avx2");
+    return v;
+}
+#endif
+
+void feistel_block(unsigned first, unsigned* out, int cnt, unsigned n, unsigned key, int hb) {
+#ifdef PNP_HAVE_AVX2_PATH
+    if (have_avx2() && n <= 0x7fff0000u) {          // signed lane compares: the domain a*b < n + 2^16 must stay below 2^31
+        feistel_block_avx2(first, out, cnt, n, key, hb);
+        return;
+    }
+#endif
+    feistel_block_scalar(first, out, cnt, n, key, hb);
+}
+
+static void gather(int* out, const unsigned* idx, int cnt, const int* support) {
+#ifdef PNP_HAVE_AVX2_PATH
+    if (have_avx2()) {               // vpgatherdd keeps eight cache misses of one instruction in flight
+        gather_avx2(out, idx, cnt, support);
+        return;
+    }
+#endif
+    for (int j = 0; j < cnt; ++j) out[j] = support[idx[j]];
+}
+
+void sample_range(int* out, int lo, int hi, unsigned n, unsigned key, int hb, const int* support) {
+    if (!support) {
+        feistel_block((unsigned)lo, reinterpret_cast<unsigned*>(out + lo), hi - lo, n, key, hb);
+        return;
+    }
+    unsigned buf[512];
+    for (int i0 = lo; i0 < hi; i0 += 512) {
+        const int cnt = hi - i0 < 512 ? hi - i0 : 512;
+        feistel_block((unsigned)i0, buf, cnt, n, key, hb);
+        gather(out + i0, buf, cnt, support);
+    }
+}
+
+}  // namespace pnp_host

@@ -8,6 +8,7 @@
 #include <vector>
 
 #include "../../include/pnp_b200.h"
+#include "host_sampler.h"
 #include "csmri.cuh"
 #include "prox.cuh"
 #include "vr.cuh"
@@ -482,60 +483,16 @@ int pnp_sample_indices(int* idx_out, int n, int count, unsigned seed, const int*
     return PNP_OK;
 }
 
-namespace {
-inline unsigned h_mix32(unsigned x) {
-    x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15; x *= 0x846ca68bU; x ^= x >> 16;
-    return x;
-}
-// one pass of the network of pnp::feistel_perm (csmri.cuh); the permutation is this pass iterated while x >= n
-inline unsigned h_feistel_pass(unsigned x, unsigned n, unsigned key, int hb) {
-    const unsigned hm = (1u << hb) - 1u;
-    const unsigned b = (n + hm) >> hb;
-    unsigned l = x >> hb, r = x & hm;
-    for (int rd = 0; rd < 4; rd += 2) {
-        const unsigned f0 = (unsigned)(((unsigned long long)h_mix32(r ^ (key + 0x9e3779b9U * (rd + 1))) * b) >> 32);
-        unsigned t = l + f0;
-        t -= (t >= b) ? b : 0u;
-        l = r;
-        r = t;
-        const unsigned f1 = h_mix32(r ^ (key + 0x9e3779b9U * (rd + 2))) & hm;
-        t = (l + f1) & hm;
-        l = r;
-        r = t;
-    }
-    return (l << hb) | r;
-}
-#if defined(__GNUC__) && defined(__x86_64__)
-__attribute__((target_clones("avx2", "default")))
-#endif
-void h_feistel_block(unsigned first, unsigned* out, int cnt, unsigned n, unsigned key, int hb) {
-    for (int j = 0; j < cnt; ++j) out[j] = h_feistel_pass(first + (unsigned)j, n, key, hb);
-}
-}  // namespace
-
 int pnp_sample_indices_host(int* out, int n, int count, unsigned seed, unsigned counter, int img, int threads,
                             const int* support_host) {
     if (!out || n < 1 || count < 1 || count > n) return fail(PNP_ERR_ARG, "bad argument");
-    const unsigned key = h_mix32(seed ^ h_mix32(counter * 0x632be5abU + (unsigned)img));
+    const unsigned key = pnp_host::mix32(seed ^ pnp_host::mix32(counter * 0x632be5abU + (unsigned)img));
     int hb = 1;
     while ((1u << (2 * hb)) < (unsigned)n) ++hb;
     if (threads < 1) threads = 1;
     if (threads > 16) threads = 16;
     if (count < 4096) threads = 1;
-    auto work = [=](int lo, int hi) {
-        // one branch-free Feistel pass over a block (auto-vectorised, AVX2 clone picked at run time), then the rare
-        // cycle-walk fix-ups (the domain exceeds n by < 2^hb) and the support gather
-        unsigned buf[512];
-        for (int i0 = lo; i0 < hi; i0 += 512) {
-            const int cnt = hi - i0 < 512 ? hi - i0 : 512;
-            h_feistel_block((unsigned)i0, buf, cnt, (unsigned)n, key, hb);
-            for (int j = 0; j < cnt; ++j) {
-                unsigned p = buf[j];
-                while (p >= (unsigned)n) p = h_feistel_pass(p, (unsigned)n, key, hb);
-                out[i0 + j] = support_host ? support_host[p] : (int)p;
-            }
-        }
-    };
+    auto work = [=](int lo, int hi) { pnp_host::sample_range(out, lo, hi, (unsigned)n, key, hb, support_host); };
     if (threads == 1) { work(0, count); return PNP_OK; }
     std::vector<std::thread> pool;
     const int per = (count + threads - 1) / threads;

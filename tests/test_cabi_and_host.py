@@ -150,3 +150,9 @@ def test_feistel_is_a_permutation_and_the_c_twin_agrees():
         assert lib.pnp_sample_indices_host(out.ctypes.data, n, c, 123, 7, 0, threads, sup.ctypes.data) == 0
         assert np.array_equal(out, ref)
     assert len(np.unique(ref)) == c
+    # odd per-thread ranges (block starts that are not multiples of the 32-index vector group) and a large domain
+    for n, c, threads in ((16777219, 70001, 3), (4194304, 100000, 7), (33, 33, 1)):
+        ref = feistel_sample(n, c, 77, 11, 2)
+        out = np.empty(c, dtype=np.int32)
+        assert lib.pnp_sample_indices_host(out.ctypes.data, n, c, 77, 11, 2, threads, None) == 0
+        assert np.array_equal(out, ref), (n, c, threads)
