@@ -47,6 +47,55 @@ def _require_device_objects(problem, denoiser):
                         % type(denoiser).__name__)
 
 
+class HostDrawRing:
+    """Look-ahead queue of host minibatch draws (mb_source='host') that land straight in a ring of staging buffers.
+
+    Draw number c is produced by one single-threaded call of the C sampler (``pnp_sample_indices_host``, GIL
+    released) on a helper thread and written into ``buffers[c % len(buffers)]`` -- the pinned buffer its
+    host->device copy will read, so the consuming thread never copies the indices.  ``ahead`` draws are kept in
+    flight.  Before a buffer is handed to a new draw, ``wait(slot)`` must block until whatever consumed its previous
+    contents (the asynchronous copy enqueued ``len(buffers)`` draws earlier) has finished.  The sequence is the
+    same as without threads: draw c is ``feistel_sample(n, B, seed, c)`` gathered through ``support``.  No CUDA in
+    here: the engine passes NumPy views of pinned tensors and an event wait."""
+
+    def __init__(self, lib, n, B, seed, support, buffers, wait, ahead):
+        from concurrent.futures import ThreadPoolExecutor
+        if len(buffers) < ahead + 2:
+            raise ValueError('HostDrawRing needs at least ahead + 2 buffers (%d < %d)' % (len(buffers), ahead + 2))
+        for b in buffers:
+            if b.dtype != np.int32 or b.ndim != 1 or b.size < B or not b.flags['C_CONTIGUOUS'] or not b.flags['WRITEABLE']:
+                raise ValueError('HostDrawRing buffers must be writable contiguous int32 vectors of at least B entries')
+        self.lib, self.n, self.B, self.seed = lib, int(n), int(B), int(seed) & 0xffffffff
+        self.support = support                       # kept alive for the worker threads
+        self.buffers, self.wait, self.ahead = list(buffers), wait, int(ahead)
+        self.drawn = 0                               # draws handed out so far = counter of the next one
+        self._queue = []
+        self._pool = ThreadPoolExecutor(max_workers=self.ahead)
+
+    def _job(self, counter, buf):
+        _lib.check(self.lib.pnp_sample_indices_host(buf.ctypes.data, self.n, self.B, self.seed, counter & 0xffffffff, 0, 1,
+                                                    None if self.support is None else self.support.ctypes.data))
+
+    def next(self):
+        """Slot of the buffer that holds the next draw (blocks until its helper thread has finished)."""
+        while len(self._queue) < self.ahead:
+            c = self.drawn + len(self._queue)
+            slot = c % len(self.buffers)
+            self.wait(slot)
+            self._queue.append((slot, self._pool.submit(self._job, c, self.buffers[slot])))
+        slot, fut = self._queue.pop(0)
+        fut.result()
+        self.drawn += 1
+        return slot
+
+    def close(self):
+        """Let the draws in flight finish (they write into the buffers) and stop the helper threads."""
+        if self._pool is not None:
+            self._pool.shutdown(wait=True)
+            self._pool = None
+            self._queue = []
+
+
 class Engine:
     def __init__(self, problem, denoiser, mini_batch_size=0, mb_source='legacy', mb_seed=0, mb_stream=None,
                  fast=False, n_extra_ints=0):
@@ -77,7 +126,8 @@ class Engine:
             self.sel = problem._dev_new_sel(self.B) if self.B > 0 else None
             self.n_extra = n_extra_ints
             if self.B > 0:
-                self.idx_host = torch.empty(self.B + n_extra_ints, dtype=torch.int32).pin_memory()
+                if mb_source != 'host':          # 'host' stages through the ring of the look-ahead draws (below)
+                    self.idx_host = torch.empty(self.B + n_extra_ints, dtype=torch.int32).pin_memory()
                 self.idx_dev = torch.zeros(self.B + n_extra_ints, dtype=torch.int32, device=self.dev)
         self.slot_ptr = self.counters[0:1]
         self.cursor_ptr = self.counters[1:2]
@@ -91,21 +141,22 @@ class Engine:
         self.gradient_time = 0.0
         self.denoise_time = 0.0
         self._stream_pos = 0
-        self._host_draws = 0
-        self._draw_queue = []
-        self._draw_ahead = 3
         ncpu = len(os.sched_getaffinity(0)) if hasattr(os, 'sched_getaffinity') else (os.cpu_count() or 1)
-        self._draw_pool = None
+        self._draws = None
         self._host_ring = None
-        if mb_source == 'host':
-            from concurrent.futures import ThreadPoolExecutor
-            # one single-threaded C call per draw (GIL released), several draws in flight: spawning worker
-            # threads inside every call costs more than the ~1.3 ms a 100k-index draw takes on one core
-            self._draw_ahead = max(2, min(8, ncpu // 2))
-            self._draw_pool = ThreadPoolExecutor(max_workers=self._draw_ahead)
-            self._host_threads = 1
-        if mb_source != 'host':
-            self._host_threads = max(1, min(8, (os.cpu_count() or 1) // 2))
+        if mb_source == 'host' and self.B > 0:
+            # one single-threaded C call per draw (GIL released), several draws in flight (spawning worker threads
+            # inside every call costs more than the ~0.6 ms a 100k-index draw takes on one core); each draw is written
+            # by its helper thread into the pinned buffer its host->device copy reads.  One pinned allocation, sliced.
+            ahead = max(2, min(8, ncpu // 2))
+            ring = torch.empty(ahead + 4, self.B + n_extra_ints, dtype=torch.int32).pin_memory()
+            self._host_ring = [ring[i] for i in range(ahead + 4)]
+            self._host_ev = [None] * len(self._host_ring)
+            self._host_pos = 0
+            self.idx_host = self._host_ring[0]
+            sup = getattr(problem, '_support_host', None)
+            self._draws = HostDrawRing(self.lib, problem.M if sup is None else sup.size, self.B, self.mb_seed, sup,
+                                       [t.numpy() for t in self._host_ring], self._wait_host_buffer, ahead)
         self._ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
         self._pending = []          # fast mode: (kind,) markers for slots not yet read back
         self.graph = None
@@ -160,12 +211,15 @@ class Engine:
         if self.mb_source == 'legacy':
             idx = self.p._draw_indices(self.B)
         elif self.mb_source == 'host':
-            # the draw for the NEXT iteration is produced by a helper thread (C sampler, GIL released) while the
-            # GPU works on the current one: one draw of look-ahead, same sequence as without the thread
-            while len(self._draw_queue) < self._draw_ahead:
-                self._draw_queue.append(self._draw_pool.submit(self._host_draw_job, self._host_draws + len(self._draw_queue)))
-            idx = self._draw_queue.pop(0).result()
-            self._host_draws += 1
+            # the draws of the next iterations are produced by helper threads (C sampler, GIL released) while the GPU
+            # works on the current one, same sequence as without the threads; the indices are already in the pinned
+            # buffer that becomes the staging buffer of this iteration
+            self._host_pos = self._draws.next()
+            self.idx_host = self._host_ring[self._host_pos]
+            buf = self.idx_host.numpy()
+            for i, e in enumerate(extra):
+                buf[self.B + i] = e
+            return buf[:self.B]
         elif self.mb_source == 'stream':
             idx = np.asarray(self.mb_stream[self._stream_pos])
             self._stream_pos += 1
@@ -181,7 +235,9 @@ class Engine:
 
     def next_host_buffer(self):
         """Rotate to the next pinned staging buffer (``self.idx_host``), waiting only for the H2D copy that read it
-        last time round."""
+        last time round.  (mb_source='host': draw_host itself moves to the buffer the draw was written into.)"""
+        if self._draws is not None:
+            return
         if self._host_ring is None:
             self._host_ring = [self.idx_host] + [torch.empty_like(self.idx_host).pin_memory() for _ in range(3)]
             self._host_ev = [None] * len(self._host_ring)
@@ -198,18 +254,16 @@ class Engine:
         ev.record(self.stream)
         self._host_ev[self._host_pos] = ev
 
-    def _host_draw_job(self, counter):
-        sup = getattr(self.p, '_support_host', None)
-        n = self.p.M if sup is None else sup.size
-        out = np.empty(self.B, dtype=np.int32)
-        _lib.check(self.lib.pnp_sample_indices_host(out.ctypes.data, int(n), self.B, self.mb_seed & 0xffffffff,
-                                                    counter & 0xffffffff, 0, self._host_threads,
-                                                    None if sup is None else sup.ctypes.data))
-        return out
+    def _wait_host_buffer(self, slot):
+        ev = self._host_ev[slot]
+        if ev is not None:
+            ev.synchronize()
 
     def upload_sel(self):
         """pinned -> device copy of the staged minibatch and rebuild of the selection."""
         self.idx_dev.copy_(self.idx_host, non_blocking=True)
+        if self._host_ring is not None:
+            self.mark_host_buffer()
         # the selection buffer is zero on entry: the gradient pass that consumes it clears it again
         self.p._dev_set_sel(self.sel, self.idx_dev, self.B, clear=False)
 
@@ -325,9 +379,8 @@ class Engine:
             self.lib.pnp_graph_destroy(exec_)
 
     def result(self, name):
-        if self._draw_pool is not None:
-            self._draw_pool.shutdown(wait=True)
-            self._draw_pool = None
+        if self._draws is not None:
+            self._draws.close()
         self.resolve()
         self.stream.synchronize()
         z = D.from_lines(self.z, self.H, self.W)

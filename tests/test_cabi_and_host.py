@@ -156,3 +156,38 @@ def test_feistel_is_a_permutation_and_the_c_twin_agrees():
         out = np.empty(c, dtype=np.int32)
         assert lib.pnp_sample_indices_host(out.ctypes.data, n, c, 77, 11, 2, threads, None) == 0
         assert np.array_equal(out, ref), (n, c, threads)
+
+
+def test_host_draw_ring_sequence_and_buffer_reuse():
+    """HostDrawRing (the look-ahead draws of mb_source='host'): draw c lands in buffer c % R and equals the NumPy twin
+    gathered through the support, `ahead` draws are in flight, and a buffer is only handed to a new draw after
+    wait(slot) was called for it (the engine blocks there on the event of the copy that read the buffer)."""
+    from pnp_svrg_b200 import _lib
+    from pnp_svrg_b200.engine import HostDrawRing, feistel_sample
+    lib = _lib.load()
+    n, B, ahead, R = 19661, 1000, 3, 7
+    sup = (np.arange(n, dtype=np.int64) * 2 + 5).astype(np.int32)
+    bufs = [np.full(B + 1, -7, dtype=np.int32) for _ in range(R)]
+    waits = []
+    ring = HostDrawRing(lib, n, B, 9, sup, bufs, waits.append, ahead)
+    try:
+        for c in range(3 * R + 2):
+            slot = ring.next()
+            assert slot == c % R and ring.drawn == c + 1
+            assert np.array_equal(bufs[slot][:B], sup[feistel_sample(n, B, 9, c)]), c
+            assert bufs[slot][B] == -7                       # the extra entries belong to the consumer
+            assert waits == [k % R for k in range(c + ahead)]   # one wait per submitted draw, in submission order
+            assert len(ring._queue) == ahead - 1
+    finally:
+        ring.close()
+    ring.close()                                             # idempotent
+    # no support: positions in [0, n); too few buffers / wrong dtype are refused
+    bufs = [np.empty(B, dtype=np.int32) for _ in range(4)]
+    ring = HostDrawRing(lib, n, B, 1, None, bufs, lambda s: None, 2)
+    assert np.array_equal(bufs[ring.next()], feistel_sample(n, B, 1, 0))
+    assert np.array_equal(bufs[ring.next()], feistel_sample(n, B, 1, 1))
+    ring.close()
+    with pytest.raises(ValueError):
+        HostDrawRing(lib, n, B, 1, None, bufs[:3], lambda s: None, 2)
+    with pytest.raises(ValueError):
+        HostDrawRing(lib, n, B, 1, None, [np.empty(B, dtype=np.int64) for _ in range(4)], lambda s: None, 2)
