@@ -97,6 +97,23 @@ int pnp_sample_indices(int* idx_out, int n, int count, unsigned seed, const int*
 int pnp_sample_indices_host(int* idx_out_host, int n, int count, unsigned seed, unsigned counter, int img, int threads,
                             const int* support_host /* optional: idx_out = support_host[position] */);
 
+/* Look-ahead queue of host draws for mb_source='host' (the reference draws one minibatch per iteration on the host,
+ * problems/CSMRI.py:66-74 / problems/problem.py:110-117, inside the loop that waits for it; here `ahead` CPU worker
+ * threads keep the next draws in flight while the GPU runs the current iteration).  Draw number c = 0, 1, 2, ... is
+ * pnp_sample_indices_host(buffers[c % n_buffers], n, count, seed, c, 0, 1, support_host); the buffers belong to the
+ * caller (pinned memory, count + extras ints each, n_buffers >= ahead + 2) and must outlive the handle.
+ *   next   blocks until the next draw is complete and returns its slot; the caller must be done with a buffer
+ *          n_buffers - ahead calls later (CPU-only use, no CUDA call is made)
+ *   stage  next + write `extras` behind the indices + cudaMemcpyAsync(dst_dev <- buffer, count + n_extras ints) on
+ *          `stream` + one event per slot, so a buffer is only handed to a new draw after the copy that read it
+ *          has finished */
+typedef struct pnp_host_draws pnp_host_draws;
+int pnp_host_draws_create(pnp_host_draws** out, int n, int count, unsigned seed, const int* support_host,
+                          int* const* buffers, int n_buffers, int ahead);
+int pnp_host_draws_next(pnp_host_draws* h, int* slot);
+int pnp_host_draws_stage(pnp_host_draws* h, int* dst_dev, const int* extras, int n_extras, void* stream, int* slot);
+int pnp_host_draws_destroy(pnp_host_draws* h);
+
 /* ---- Deblur + super-resolution gradient ------------------------------------------------------
  * Replaces Deblur.grad_full (problems/DeblurSR.py:126-132), Deblur.grad_stoch (:135-147) and the
  * same update lines as pnp_csmri_grad:

@@ -88,6 +88,11 @@ PROTOTYPES = {
                                        C.c_void_p]),
     'pnp_sample_indices': (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_uint, C.c_void_p, C.c_void_p]),
     'pnp_sample_indices_host': (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_uint, C.c_uint, C.c_int, C.c_int, C.c_void_p]),
+    'pnp_host_draws_create': (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_uint, C.c_void_p, C.c_void_p, C.c_int,
+                                        C.c_int]),
+    'pnp_host_draws_next': (C.c_int, [C.c_void_p, C.POINTER(C.c_int)]),
+    'pnp_host_draws_stage': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.POINTER(C.c_int)]),
+    'pnp_host_draws_destroy': (C.c_int, [C.c_void_p]),
     'pnp_deblur_grad': (C.c_int, [C.POINTER(DeblurGradArgs), C.c_void_p]),
     'pnp_pr_grad': (C.c_int, [C.POINTER(PrGradArgs), C.c_void_p]),
     'pnp_cdp_grad': (C.c_int, [C.POINTER(CdpGradArgs), C.c_void_p]),

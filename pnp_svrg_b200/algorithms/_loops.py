@@ -139,6 +139,13 @@ def _host_draw_fn(eng, extra_fn=None):
     if eng.B <= 0 or eng.mb_source == 'device':
         return None
 
+    if eng.mb_source == 'host':
+        # look-ahead draws: one native call waits for the draw, adds the extras (independent generator, so the order
+        # against the minibatch draw does not matter) and enqueues the pinned -> device copy
+        def draw_native():
+            eng.draw_host(extra_fn() if extra_fn else ())
+        return draw_native
+
     def draw():
         # a small ring of pinned staging buffers: the host only waits for the H2D copy that used this buffer four
         # draws ago, so drawing and staging overlap the GPU's previous iterations instead of a sync per iteration

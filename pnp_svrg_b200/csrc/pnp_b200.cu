@@ -504,6 +504,64 @@ int pnp_sample_indices_host(int* out, int n, int count, unsigned seed, unsigned 
     return PNP_OK;
 }
 
+// ---- look-ahead host draws (mb_source='host') ---------------------------------------------------------------
+struct pnp_host_draws {
+    pnp_host::DrawQueue q;
+    std::vector<cudaEvent_t> ev;          // ev[slot]: recorded after the H2D copy that reads buffers[slot]
+    std::vector<char> recorded;
+    pnp_host_draws(int n, int count, unsigned seed, const int* support, int* const* buffers, int n_buffers, int ahead)
+        : q(n, count, seed, support, buffers, n_buffers, ahead), recorded(n_buffers, 0) {}
+};
+
+int pnp_host_draws_create(pnp_host_draws** out, int n, int count, unsigned seed, const int* support_host,
+                          int* const* buffers, int n_buffers, int ahead) {
+    if (!out || !buffers || n < 1 || count < 1 || count > n) return fail(PNP_ERR_ARG, "bad argument");
+    if (ahead < 1 || ahead > 64 || n_buffers < ahead + 2)
+        return fail(PNP_ERR_ARG, "need 1 <= ahead <= 64 and at least ahead + 2 buffers (ahead=%d, buffers=%d)", ahead, n_buffers);
+    for (int i = 0; i < n_buffers; ++i)
+        if (!buffers[i]) return fail(PNP_ERR_ARG, "null buffer %d", i);
+    *out = new pnp_host_draws(n, count, seed, support_host, buffers, n_buffers, ahead);
+    return PNP_OK;
+}
+
+int pnp_host_draws_next(pnp_host_draws* h, int* slot) {
+    if (!h || !slot) return fail(PNP_ERR_ARG, "null argument");
+    *slot = h->q.wait_next();
+    h->q.release();
+    return PNP_OK;
+}
+
+int pnp_host_draws_stage(pnp_host_draws* h, int* dst_dev, const int* extras, int n_extras, void* stream, int* slot_out) {
+    if (!h || !dst_dev || n_extras < 0 || (n_extras > 0 && !extras)) return fail(PNP_ERR_ARG, "bad argument");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int R = h->q.n_buffers();
+    if (h->ev.empty()) {                  // first staging call: one event per buffer, on the caller's device
+        h->ev.resize(R, nullptr);
+        for (int i = 0; i < R; ++i) CU_TRY(cudaEventCreateWithFlags(&h->ev[i], cudaEventDisableTiming));
+    }
+    const long long c = h->q.consumed();
+    const int slot = h->q.wait_next();
+    int* buf = h->q.buffer(slot);
+    for (int i = 0; i < n_extras; ++i) buf[h->q.count() + i] = extras[i];
+    CU_TRY(cudaMemcpyAsync(dst_dev, buf, sizeof(int) * (size_t)(h->q.count() + n_extras), cudaMemcpyHostToDevice, st));
+    CU_TRY(cudaEventRecord(h->ev[slot], st));
+    h->recorded[slot] = 1;
+    // releasing draw c lets a worker start draw c + ahead: the copy that read that draw's buffer must have finished
+    const int s2 = (int)((c + h->q.ahead()) % R);
+    if (h->recorded[s2] && s2 != slot) CU_TRY(cudaEventSynchronize(h->ev[s2]));
+    h->q.release();
+    if (slot_out) *slot_out = slot;
+    return PNP_OK;
+}
+
+int pnp_host_draws_destroy(pnp_host_draws* h) {
+    if (!h) return PNP_OK;
+    for (cudaEvent_t e : h->ev)
+        if (e) cudaEventDestroy(e);
+    delete h;                             // joins the workers
+    return PNP_OK;
+}
+
 int pnp_deblur_grad(const pnp_deblur_grad_args* args, void* stream) {
     if (!args) return fail(PNP_ERR_ARG, "null args");
     const pnp_deblur_grad_args& a = *args;

@@ -48,52 +48,66 @@ def _require_device_objects(problem, denoiser):
 
 
 class HostDrawRing:
-    """Look-ahead queue of host minibatch draws (mb_source='host') that land straight in a ring of staging buffers.
+    """Look-ahead queue of host minibatch draws (mb_source='host') that land straight in a ring of staging buffers:
+    a handle on the native queue of include/pnp_b200.h (``pnp_host_draws_*``).
 
-    Draw number c is produced by one single-threaded call of the C sampler (``pnp_sample_indices_host``, GIL
-    released) on a helper thread and written into ``buffers[c % len(buffers)]`` -- the pinned buffer its
-    host->device copy will read, so the consuming thread never copies the indices.  ``ahead`` draws are kept in
-    flight.  Before a buffer is handed to a new draw, ``wait(slot)`` must block until whatever consumed its previous
-    contents (the asynchronous copy enqueued ``len(buffers)`` draws earlier) has finished.  The sequence is the
-    same as without threads: draw c is ``feistel_sample(n, B, seed, c)`` gathered through ``support``.  No CUDA in
-    here: the engine passes NumPy views of pinned tensors and an event wait."""
+    Draw number c is produced by one single-threaded run of the C sampler on a native worker thread and written
+    into ``buffers[c % len(buffers)]`` -- the pinned buffer its host->device copy reads, so the loop never copies
+    the indices and never touches Python threads.  ``ahead`` draws are kept in flight.  The sequence is the same as
+    without threads: draw c is ``feistel_sample(n, B, seed, c)`` gathered through ``support``.
+      next()   slot of the next draw (CPU only: the caller must be done with a buffer len(buffers) - ahead calls later)
+      stage()  next + extras behind the indices + asynchronous copy to the device buffer + the event that guards the
+               reuse of the staging buffer, in one native call"""
 
-    def __init__(self, lib, n, B, seed, support, buffers, wait, ahead):
-        from concurrent.futures import ThreadPoolExecutor
-        if len(buffers) < ahead + 2:
-            raise ValueError('HostDrawRing needs at least ahead + 2 buffers (%d < %d)' % (len(buffers), ahead + 2))
+    def __init__(self, lib, n, B, seed, support, buffers, ahead):
+        import ctypes as C
         for b in buffers:
             if b.dtype != np.int32 or b.ndim != 1 or b.size < B or not b.flags['C_CONTIGUOUS'] or not b.flags['WRITEABLE']:
                 raise ValueError('HostDrawRing buffers must be writable contiguous int32 vectors of at least B entries')
-        self.lib, self.n, self.B, self.seed = lib, int(n), int(B), int(seed) & 0xffffffff
-        self.support = support                       # kept alive for the worker threads
-        self.buffers, self.wait, self.ahead = list(buffers), wait, int(ahead)
-        self.drawn = 0                               # draws handed out so far = counter of the next one
-        self._queue = []
-        self._pool = ThreadPoolExecutor(max_workers=self.ahead)
-
-    def _job(self, counter, buf):
-        _lib.check(self.lib.pnp_sample_indices_host(buf.ctypes.data, self.n, self.B, self.seed, counter & 0xffffffff, 0, 1,
-                                                    None if self.support is None else self.support.ctypes.data))
+        if support is not None and (support.dtype != np.int32 or not support.flags['C_CONTIGUOUS']):
+            raise ValueError('HostDrawRing support must be a contiguous int32 vector')
+        self.lib, self.B = lib, int(B)
+        self.support, self.buffers = support, list(buffers)      # kept alive for the worker threads
+        self.n_extra = min(b.size for b in self.buffers) - self.B
+        self.drawn = 0                                             # draws handed out so far = number of the next one
+        self._slot = C.c_int(0)
+        self._extras = (C.c_int * max(self.n_extra, 1))()
+        self._h = C.c_void_p()
+        ptrs = (C.c_void_p * len(self.buffers))(*[b.ctypes.data for b in self.buffers])
+        _lib.check(lib.pnp_host_draws_create(C.byref(self._h), int(n), self.B, int(seed) & 0xffffffff,
+                                             None if support is None else support.ctypes.data, ptrs, len(self.buffers),
+                                             int(ahead)))
 
     def next(self):
-        """Slot of the buffer that holds the next draw (blocks until its helper thread has finished)."""
-        while len(self._queue) < self.ahead:
-            c = self.drawn + len(self._queue)
-            slot = c % len(self.buffers)
-            self.wait(slot)
-            self._queue.append((slot, self._pool.submit(self._job, c, self.buffers[slot])))
-        slot, fut = self._queue.pop(0)
-        fut.result()
+        rc = self.lib.pnp_host_draws_next(self._h, self._slot)
+        if rc:
+            _lib.check(rc)
         self.drawn += 1
-        return slot
+        return self._slot.value
+
+    def stage(self, dst_dev_ptr, extras, stream_ptr):
+        n = len(extras)
+        if n > self.n_extra:
+            raise ValueError('%d extra entries do not fit the staging buffers (%d)' % (n, self.n_extra))
+        for i in range(n):
+            self._extras[i] = int(extras[i])
+        rc = self.lib.pnp_host_draws_stage(self._h, dst_dev_ptr, self._extras, n, stream_ptr, self._slot)
+        if rc:
+            _lib.check(rc)
+        self.drawn += 1
+        return self._slot.value
 
     def close(self):
-        """Let the draws in flight finish (they write into the buffers) and stop the helper threads."""
-        if self._pool is not None:
-            self._pool.shutdown(wait=True)
-            self._pool = None
-            self._queue = []
+        """Let the draws in flight finish (they write into the buffers) and stop the worker threads."""
+        if self._h:
+            self.lib.pnp_host_draws_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 class Engine:
@@ -145,18 +159,17 @@ class Engine:
         self._draws = None
         self._host_ring = None
         if mb_source == 'host' and self.B > 0:
-            # one single-threaded C call per draw (GIL released), several draws in flight (spawning worker threads
-            # inside every call costs more than the ~0.6 ms a 100k-index draw takes on one core); each draw is written
-            # by its helper thread into the pinned buffer its host->device copy reads.  One pinned allocation, sliced.
+            # native look-ahead queue: one single-threaded run of the C sampler per draw, several draws in flight
+            # (a 100k-index draw takes 0.3-0.6 ms on one core), each written into the pinned buffer its host->device
+            # copy reads; draw_host() stages the next one with a single native call.  One pinned allocation, sliced.
             ahead = max(2, min(8, ncpu // 2))
             ring = torch.empty(ahead + 4, self.B + n_extra_ints, dtype=torch.int32).pin_memory()
             self._host_ring = [ring[i] for i in range(ahead + 4)]
-            self._host_ev = [None] * len(self._host_ring)
-            self._host_pos = 0
             self.idx_host = self._host_ring[0]
             sup = getattr(problem, '_support_host', None)
+            self._host_views = [t.numpy() for t in self._host_ring]
             self._draws = HostDrawRing(self.lib, problem.M if sup is None else sup.size, self.B, self.mb_seed, sup,
-                                       [t.numpy() for t in self._host_ring], self._wait_host_buffer, ahead)
+                                       self._host_views, ahead)
         self._ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
         self._pending = []          # fast mode: (kind,) markers for slots not yet read back
         self.graph = None
@@ -211,15 +224,12 @@ class Engine:
         if self.mb_source == 'legacy':
             idx = self.p._draw_indices(self.B)
         elif self.mb_source == 'host':
-            # the draws of the next iterations are produced by helper threads (C sampler, GIL released) while the GPU
-            # works on the current one, same sequence as without the threads; the indices are already in the pinned
-            # buffer that becomes the staging buffer of this iteration
-            self._host_pos = self._draws.next()
-            self.idx_host = self._host_ring[self._host_pos]
-            buf = self.idx_host.numpy()
-            for i, e in enumerate(extra):
-                buf[self.B + i] = e
-            return buf[:self.B]
+            # the draws of the next iterations are produced by native worker threads while the GPU works on the
+            # current one (same sequence as without the threads); the indices are already in the pinned buffer, and
+            # the copy to idx_dev is enqueued here, on the engine stream, by the same native call
+            slot = self._draws.stage(D.ptr(self.idx_dev), extra, self.sptr)
+            self.idx_host = self._host_ring[slot]
+            return self._host_views[slot][:self.B]
         elif self.mb_source == 'stream':
             idx = np.asarray(self.mb_stream[self._stream_pos])
             self._stream_pos += 1
@@ -235,9 +245,7 @@ class Engine:
 
     def next_host_buffer(self):
         """Rotate to the next pinned staging buffer (``self.idx_host``), waiting only for the H2D copy that read it
-        last time round.  (mb_source='host': draw_host itself moves to the buffer the draw was written into.)"""
-        if self._draws is not None:
-            return
+        last time round.  (Not used by mb_source='host': its draws own their ring, see HostDrawRing.)"""
         if self._host_ring is None:
             self._host_ring = [self.idx_host] + [torch.empty_like(self.idx_host).pin_memory() for _ in range(3)]
             self._host_ev = [None] * len(self._host_ring)
@@ -254,16 +262,10 @@ class Engine:
         ev.record(self.stream)
         self._host_ev[self._host_pos] = ev
 
-    def _wait_host_buffer(self, slot):
-        ev = self._host_ev[slot]
-        if ev is not None:
-            ev.synchronize()
-
     def upload_sel(self):
         """pinned -> device copy of the staged minibatch and rebuild of the selection."""
-        self.idx_dev.copy_(self.idx_host, non_blocking=True)
-        if self._host_ring is not None:
-            self.mark_host_buffer()
+        if self._draws is None:                  # mb_source='host': draw_host() has already enqueued the copy
+            self.idx_dev.copy_(self.idx_host, non_blocking=True)
         # the selection buffer is zero on entry: the gradient pass that consumes it clears it again
         self.p._dev_set_sel(self.sel, self.idx_dev, self.B, clear=False)
 

@@ -159,35 +159,38 @@ def test_feistel_is_a_permutation_and_the_c_twin_agrees():
 
 
 def test_host_draw_ring_sequence_and_buffer_reuse():
-    """HostDrawRing (the look-ahead draws of mb_source='host'): draw c lands in buffer c % R and equals the NumPy twin
-    gathered through the support, `ahead` draws are in flight, and a buffer is only handed to a new draw after
-    wait(slot) was called for it (the engine blocks there on the event of the copy that read the buffer)."""
+    """HostDrawRing (the native look-ahead draws of mb_source='host', pnp_host_draws_*): draw c lands in buffer c % R
+    and equals the NumPy twin gathered through the support, whatever the number of draws in flight; entries behind
+    the indices belong to the consumer; the handle can be closed with draws in flight."""
     from pnp_svrg_b200 import _lib
     from pnp_svrg_b200.engine import HostDrawRing, feistel_sample
     lib = _lib.load()
-    n, B, ahead, R = 19661, 1000, 3, 7
+    n, B = 19661, 1000
     sup = (np.arange(n, dtype=np.int64) * 2 + 5).astype(np.int32)
-    bufs = [np.full(B + 1, -7, dtype=np.int32) for _ in range(R)]
-    waits = []
-    ring = HostDrawRing(lib, n, B, 9, sup, bufs, waits.append, ahead)
-    try:
+    for ahead, R in ((1, 3), (3, 7), (8, 12)):
+        bufs = [np.full(B + 1, -7, dtype=np.int32) for _ in range(R)]
+        ring = HostDrawRing(lib, n, B, 9, sup, bufs, ahead)
+        assert ring.n_extra == 1
         for c in range(3 * R + 2):
             slot = ring.next()
             assert slot == c % R and ring.drawn == c + 1
-            assert np.array_equal(bufs[slot][:B], sup[feistel_sample(n, B, 9, c)]), c
-            assert bufs[slot][B] == -7                       # the extra entries belong to the consumer
-            assert waits == [k % R for k in range(c + ahead)]   # one wait per submitted draw, in submission order
-            assert len(ring._queue) == ahead - 1
-    finally:
+            assert np.array_equal(bufs[slot][:B], sup[feistel_sample(n, B, 9, c)]), (ahead, c)
+            assert bufs[slot][B] == -7
         ring.close()
-    ring.close()                                             # idempotent
-    # no support: positions in [0, n); too few buffers / wrong dtype are refused
-    bufs = [np.empty(B, dtype=np.int32) for _ in range(4)]
-    ring = HostDrawRing(lib, n, B, 1, None, bufs, lambda s: None, 2)
-    assert np.array_equal(bufs[ring.next()], feistel_sample(n, B, 1, 0))
-    assert np.array_equal(bufs[ring.next()], feistel_sample(n, B, 1, 1))
+        ring.close()                                         # idempotent
+    # no support: positions in [0, n); a large draw; closing right after creation (draws in flight)
+    n, B = 1258000, 100000
+    bufs = [np.empty(B, dtype=np.int32) for _ in range(6)]
+    ring = HostDrawRing(lib, n, B, 1, None, bufs, 4)
+    for c in range(9):
+        assert np.array_equal(bufs[ring.next()], feistel_sample(n, B, 1, c))
     ring.close()
+    HostDrawRing(lib, n, B, 1, None, bufs, 4).close()
+    del ring
+    # too few buffers / wrong dtype are refused
+    with pytest.raises(_lib.PnpError):
+        HostDrawRing(lib, n, B, 1, None, bufs[:3], 2)
     with pytest.raises(ValueError):
-        HostDrawRing(lib, n, B, 1, None, bufs[:3], lambda s: None, 2)
+        HostDrawRing(lib, n, B, 1, None, [np.empty(B, dtype=np.int64) for _ in range(4)], 2)
     with pytest.raises(ValueError):
-        HostDrawRing(lib, n, B, 1, None, [np.empty(B, dtype=np.int64) for _ in range(4)], lambda s: None, 2)
+        HostDrawRing(lib, n, B, 1, np.zeros(n, dtype=np.int64), bufs, 2)
