@@ -163,7 +163,7 @@ class Engine:
             # (a 100k-index draw takes 0.3-0.6 ms on one core), each written into the pinned buffer its host->device
             # copy reads; draw_host() stages the next one with a single native call.  One pinned allocation, sliced.
             ahead = max(2, min(8, ncpu // 2))
-            depth = ahead + max(2, int(os.environ.get('PNP_HOST_RING_EXTRA', '4')))     # how far the host may run ahead
+            depth = ahead + max(2, int(os.environ.get('PNP_HOST_RING_EXTRA', '12')))     # how far the host may run ahead
             ring = torch.empty(depth, self.B + n_extra_ints, dtype=torch.int32).pin_memory()
             self._host_ring = [ring[i] for i in range(depth)]
             self.idx_host = self._host_ring[0]
