@@ -24,14 +24,20 @@ def to_lines(z, H, W, device=None):
     if isinstance(z, torch.Tensor):
         t = z.detach().to(device=device or 'cuda', dtype=torch.float32).reshape(H, W)
         return t.t().contiguous()
-    a = np.asarray(z, dtype=np.float64).reshape(H, W)
-    t = torch.from_numpy(np.ascontiguousarray(a.T, dtype=np.float32))
-    return t.to(device or 'cuda', non_blocking=False)
+    # cast on the host with torch (multi-threaded, contiguous), transpose on the device: a strided NumPy transpose of a
+    # 2048^2 float64 image costs 20-50 ms of host time, this path well under a millisecond plus the copy
+    a = np.ascontiguousarray(np.asarray(z, dtype=np.float64).reshape(H, W))
+    if not a.flags.writeable:
+        a = a.copy()                                   # torch.from_numpy wants a writable buffer
+    t = torch.from_numpy(a).to(torch.float32).to(device or 'cuda', non_blocking=False).t().contiguous()
+    if t.is_cuda:
+        torch.cuda.current_stream(t.device).synchronize()      # complete on return, like the copy itself (any stream may use it)
+    return t
 
 
 def from_lines(t, H, W):
     """device [W][H] float32 -> host float64 (N,) in the reference's raveled (row-major) order."""
-    return t.reshape(W, H).t().contiguous().cpu().numpy().astype(np.float64).ravel()
+    return t.reshape(W, H).t().contiguous().cpu().to(torch.float64).numpy().ravel()
 
 
 def lines_to_image_tensor(t, H, W):

@@ -194,3 +194,24 @@ def test_host_draw_ring_sequence_and_buffer_reuse():
         HostDrawRing(lib, n, B, 1, None, [np.empty(B, dtype=np.int64) for _ in range(4)], 2)
     with pytest.raises(ValueError):
         HostDrawRing(lib, n, B, 1, np.zeros(n, dtype=np.int64), bufs, 2)
+
+
+def test_line_layout_conversions_are_value_exact():
+    """device.to_lines / from_lines (host float64 raveled image <-> float32 [W][H] line layout): the torch cast +
+    transpose must give exactly what the plain NumPy transpose + cast gives, for vectors, images, tensors and
+    read-only inputs, square or not."""
+    import torch
+    from pnp_svrg_b200 import device as D
+    for H, W in ((64, 64), (32, 128), (256, 64)):
+        z = np.random.default_rng(H).uniform(-1, 1, H * W)
+        want = torch.from_numpy(np.ascontiguousarray(z.reshape(H, W).T, dtype=np.float32))
+        got = D.to_lines(z, H, W, device='cpu')
+        assert got.shape == (W, H) and got.is_contiguous() and got.dtype == torch.float32 and torch.equal(got, want)
+        assert torch.equal(D.to_lines(z.reshape(H, W), H, W, device='cpu'), want)
+        assert torch.equal(D.to_lines(torch.from_numpy(z), H, W, device='cpu'), want)
+        ro = z.copy()
+        ro.flags.writeable = False
+        assert torch.equal(D.to_lines(ro, H, W, device='cpu'), want)
+        back = D.from_lines(got, H, W)
+        assert back.dtype == np.float64 and back.shape == (H * W,)
+        assert np.array_equal(back, z.astype(np.float32).astype(np.float64))
