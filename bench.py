@@ -462,7 +462,7 @@ def run_e2e(a, cfg, prob, dev, world, fast=True):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dt = float(t.item())
     return {'value': world * iters / dt, 'unit': UNIT, 'h2d_bytes_per_step': T2 * 4 * B + 4 * prob.N // a.steps,
-            'd2h_bytes_per_step': T2 * 16 + 8 * prob.N // a.steps, 'seconds': dt, 'inner_iterations': iters,
+            'd2h_bytes_per_step': T2 * 16 + 4 * prob.N // a.steps,      # logs + the final iterate (float32 on the wire) 'seconds': dt, 'inner_iterations': iters,
             'api': "pnp_svrg_b200.algorithms.pnp_svrg(problem, denoiser, ..., mb_source='host', fast=%s) -- minibatch drawn "
                    "on the host, copied from pinned memory each inner iteration; PSNR + sigma of every iterate read back "
                    "%s; Xinit upload and final z download included"
