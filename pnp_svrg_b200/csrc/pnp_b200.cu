@@ -537,7 +537,10 @@ int pnp_host_draws_stage(pnp_host_draws* h, int* dst_dev, const int* extras, int
     const int R = h->q.n_buffers();
     if (h->ev.empty()) {                  // first staging call: one event per buffer, on the caller's device
         h->ev.resize(R, nullptr);
-        for (int i = 0; i < R; ++i) CU_TRY(cudaEventCreateWithFlags(&h->ev[i], cudaEventDisableTiming));
+        // blocking sync: when the loop is GPU-bound the host waits here most of the time, and a spinning wait would take
+        // a core from the sampler threads (eight ranks share the host's cores); the ring absorbs the wake-up latency
+        for (int i = 0; i < R; ++i)
+            CU_TRY(cudaEventCreateWithFlags(&h->ev[i], cudaEventDisableTiming | cudaEventBlockingSync));
     }
     const long long c = h->q.consumed();
     const int slot = h->q.wait_next();
