@@ -215,3 +215,31 @@ def test_line_layout_conversions_are_value_exact():
         back = D.from_lines(got, H, W)
         assert back.dtype == np.float64 and back.shape == (H * W,)
         assert np.array_equal(back, z.astype(np.float32).astype(np.float64))
+
+
+@pytest.mark.parametrize('simd', ['scalar', 'avx2', 'avx512'])
+def test_host_sampler_simd_paths_agree(simd):
+    """The scalar, AVX2 and AVX-512 bodies of the host sampler are picked at run time (the best the CPU has, capped by
+    PNP_HOST_SIMD): each must reproduce the NumPy twin bit for bit.  Fresh interpreter per level: the choice is
+    made once per process."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = r'''
+import numpy as np
+from pnp_svrg_b200 import _lib
+from pnp_svrg_b200.engine import feistel_sample
+lib = _lib.load()
+for n, c, thr in ((1, 1, 1), (5, 5, 1), (97, 97, 1), (1025, 1025, 1), (65537, 40000, 3), (1258000, 100000, 1), (16777219, 70001, 2)):
+    ref = feistel_sample(n, c, 5, n)
+    out = np.empty(c, dtype=np.int32)
+    assert lib.pnp_sample_indices_host(out.ctypes.data, n, c, 5, n, 0, thr, None) == 0
+    assert np.array_equal(out, ref), n
+    sup = ((np.arange(n, dtype=np.int64) * 7 + 3) % 2000000011).astype(np.int32)
+    assert lib.pnp_sample_indices_host(out.ctypes.data, n, c, 5, n, 0, thr, sup.ctypes.data) == 0
+    assert np.array_equal(out, sup[ref]), n
+print('SIMD-OK')
+'''
+    r = subprocess.run([sys.executable, '-c', code], cwd=root, env=dict(os.environ, PNP_HOST_SIMD=simd, PYTHONPATH=root),
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and 'SIMD-OK' in r.stdout, r.stdout[-1000:] + r.stderr[-3000:]
