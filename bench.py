@@ -173,105 +173,22 @@ def cpu_baseline(cfg, iters):
 
 
 # --------------------------------------------------------------------------------------------
-class Epoch:
-    """Device-resident SVRG epoch on the engine primitives (what algorithms.pnp_svrg(fast=True) runs)."""
-
-    def __init__(self, cfg, seed):
-        import torch
-        from pnp_svrg_b200 import device as D
-        from pnp_svrg_b200.denoisers import TVDenoiser
-        from pnp_svrg_b200.engine import Engine
-        from pnp_svrg_b200.problems import CSMRI
-        H = cfg['H']
-        np.random.seed(seed)
-        self.prob = CSMRI(image=make_image(H, seed), H=H, W=H, sample_prob=cfg['sample_prob'], snr=20.)
-        self.den = TVDenoiser()
-        self.cfg, self.torch, self.D = cfg, torch, D
-        self.eng = Engine(self.prob, self.den, cfg['mini_batch_size'], mb_source='device', mb_seed=seed, fast=True)
-        eng = self.eng
-        with torch.cuda.stream(eng.stream):
-            self.w = torch.empty_like(eng.z)
-            self.mu = torch.empty_like(eng.z)
-            eng.set_step(cfg['eta'])
-        self.n_launch_inner = 0
-        self.graph = None
-
-    # the launches of one inner iteration (7 kernels + 1 memset)
-    def inner_ops(self, hook=None):
-        eng, p, B = self.eng, self.prob, self.cfg['mini_batch_size']
-        h = hook or (lambda name: None)
-        gk = dict(b=self.w, sel=eng.sel, with_y=False, gscale=1.0 / B, vadd=self.mu, step_ptr=eng.step,
-                  z_in=eng.z, z_out=eng.z, clear_sel=True)
-        tail = lambda: FUSED_TAIL and p._dev_update_prox(
-            1.0 / B, eng.step, self.mu, eng.z, eng.z, eng.sig_log, self.den.sigma_modifier,
-            self.den.denoise_strength * self.den.decay ** (self.den.t + 1), p._xrec_dev, eng.mse_log, eng.slot_ptr,
-            advance=eng.counters, n_advance=3)
-        if hook is None:
-            # the minibatch selection only feeds the column pass: draw it on a parallel graph branch
-            eng.fork(eng.sample_sel_device, lambda: p._dev_grad(eng.z, phases=1, **gk))
-            p._dev_grad(eng.z, phases=2, **gk)
-            fused = tail()
-            if not fused:
-                p._dev_grad(eng.z, phases=4, **gk)
-        else:                                  # same kernels, launched one by one so each can be timed
-            eng.sample_sel_device(); h('sel_sample')
-            p._dev_grad(eng.z, phases=1, **gk); h('lines_r2c')
-            p._dev_grad(eng.z, phases=2, **gk); h('cols_mask')
-            fused = tail()
-            if fused:
-                h('c2r+update+prox_fused(sigma+haar+psnr)')
-            else:
-                p._dev_grad(eng.z, phases=4, **gk); h('lines_c2r+update')
-        # kernels launched by this iteration: sel_sample + r2c + cols + [tail] | [c2r + (prox | sigma + haar) + advance]
-        if fused:
-            self.den.t += 1
-            self.n_launch_inner = 4
-        elif FUSED_PROX and self.den._dev_prox_fused(self._ctx()):
-            h('prox_fused(sigma+haar+psnr)')
-            self.n_launch_inner = 6
-        else:
-            eng.check(eng.lib.pnp_estimate_sigma(self.D.ptr(eng.z), eng.H, eng.W, 1, self.D.ptr(eng.sig_log),
-                                                 self.D.ptr(eng.slot_ptr), eng.sptr)); h('sigma_mad')
-            self.den._dev_denoise(self._ctx()); h('haar_bayes+psnr')
-            self.n_launch_inner = 7
-        if not fused:                                      # the fused tail bumps the iteration counters itself
-            eng.advance(); h('advance')
-
-    def _ctx(self):
-        from pnp_svrg_b200.engine import ProxCtx
-        eng = self.eng
-        return ProxCtx(eng.z, eng.z, eng.H, eng.W, sig_log=eng.sig_log, xrec=self.prob._xrec_dev,
-                       mse_log=eng.mse_log, slot=eng.slot_ptr)
-
-    def snapshot_ops(self):
-        eng, p = self.eng, self.prob
-        p._dev_grad(eng.z, gscale=1.0 / p.M0, g_out=self.mu)
-        eng.copy(self.w, eng.z)
-
-    def capture(self):
-        self.graph = self.eng.capture(self.inner_ops)
-
-    def step(self):
-        eng = self.eng
-        with self.torch.cuda.stream(eng.stream):
-            self.snapshot_ops()
-            for _ in range(self.cfg['T2']):
-                eng.replay(self.graph)
-        eng.slot_host += self.cfg['T2']
-        if eng.slot_host + self.cfg['T2'] > 4096:
-            eng.flush_fast()
-
-    def reset(self):
-        eng = self.eng
-        with self.torch.cuda.stream(eng.stream):
-            eng.z.copy_(self.D.to_lines(self.prob.Xinit, eng.H, eng.W, eng.dev))
-            eng._reset_logs()
-        eng.stream.synchronize()
+def make_run(cfg, seed, mb_source='device'):
+    """The product path that is timed: pnp_svrg_b200.algorithms.SvrgRun -- the object behind the public
+    ``pnp_svrg(..., fast=True)``; ``run.epoch()`` enqueues one whole SVRG epoch (one CUDA graph)."""
+    from pnp_svrg_b200.algorithms import SvrgRun
+    from pnp_svrg_b200.denoisers import TVDenoiser
+    from pnp_svrg_b200.problems import CSMRI
+    H = cfg['H']
+    np.random.seed(seed)
+    prob = CSMRI(image=make_image(H, seed), H=H, W=H, sample_prob=cfg['sample_prob'], snr=20.)
+    run = SvrgRun(prob, TVDenoiser(), cfg['eta'], cfg['T2'], cfg['mini_batch_size'], lr_decay=1, vr_mode='paper',
+                  mb_source=mb_source, mb_seed=seed, fast=True)
+    return prob, run
 
 
-FUSED_TAIL = os.environ.get('PNP_BENCH_FUSED_TAIL', '1') == '1'      # pass 3 + update + sigma + wavelet + PSNR as one cooperative launch
-FUSED_PROX = os.environ.get('PNP_BENCH_FUSED_PROX', '1') == '1'    # sigma + wavelet + PSNR as one cooperative launch
 LAUNCHES_PER_SNAPSHOT = 4     # r2c + cols + c2r + D2D copy
+LAUNCHES_PER_INNER = 3        # r2c (+ in-pass minibatch selection) + cols + single-launch tail (c2r + update + sigma + prox + PSNR)
 
 
 def run_b200(a, cfg, rank, world, local_rank):
@@ -281,15 +198,11 @@ def run_b200(a, cfg, rank, world, local_rank):
     dev = torch.device('cuda', local_rank)
     if world > 1:
         dist.init_process_group('nccl', device_id=dev)
-    ep = Epoch(cfg, seed=rank)
-    eng = ep.eng
+    prob, run = make_run(cfg, seed=rank)
+    eng = run.eng
     T2, N = cfg['T2'], cfg['H'] * cfg['W']
-    with torch.cuda.stream(eng.stream):
-        ep.snapshot_ops()
-        ep.inner_ops()                     # eager warm iteration before the capture
-    eng.stream.synchronize()
-    ep.capture()
-    ep.reset()
+    if not run.epoch_mode():
+        raise RuntimeError('the whole-epoch graph path is not available for this configuration')
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
     def barrier():
@@ -301,8 +214,11 @@ def run_b200(a, cfg, rank, world, local_rank):
     if rank == 0:
         sampler.start()
         time.sleep(0.6)                    # nvidia-smi needs a moment before its first sample
-    for _ in range(a.warmup):
-        ep.step()
+    eng.time_log.append(0.0)
+    eng.psnr_log.append(eng.psnr_of(eng.z))
+    for _ in range(max(a.warmup, 1)):
+        run.epoch()
+    eng.resolve()
     barrier()
     if rank == 0:
         sampler.mark()
@@ -312,7 +228,7 @@ def run_b200(a, cfg, rank, world, local_rank):
         with torch.cuda.stream(eng.stream):
             flush.fill_(s & 0xff)          # L2 flush, outside the event pair
             evs[s][0].record(eng.stream)
-        ep.step()
+        run.epoch()
         evs[s][1].record(eng.stream)
     barrier()
     t_wall = time.time() - t_wall
@@ -323,28 +239,33 @@ def run_b200(a, cfg, rank, world, local_rank):
         t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         total_ms = float(t.item())
-    psnr = eng.flush_fast()
+    eng.resolve()
+    psnr = eng.psnr_log
     value = world * a.steps * T2 / (total_ms * 1e-3)
+    fused = eng.fused_tail is True
 
     line = {
         'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': a.steps, 'warmup': a.warmup,
         'ms_per_step': total_ms / a.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
         'dtype': 'f32', 'data': 'synthetic', 'config': cfg,
-        'gpu_launches': a.steps * (T2 * ep.n_launch_inner + LAUNCHES_PER_SNAPSHOT),
+        'gpu_launches': a.steps * (T2 * (LAUNCHES_PER_INNER if fused else 7) + LAUNCHES_PER_SNAPSHOT),
         'clocks': clocks, 'wall_s_timed_region': t_wall,
+        'timed_path': "pnp_svrg_b200.algorithms.SvrgRun.epoch() -- the whole-epoch CUDA graph that the public "
+                      "pnp_svrg(..., fast=True) replays (mb_source='device'); parity: tests/test_gpu_epoch.py",
         'psnr_first_last': [float(psnr[0]), float(psnr[-1])] if psnr else None,
         'us_per_inner_iteration': 1e3 * total_ms / (a.steps * T2),
     }
 
     # ---- per-kernel breakdown + roofline (eager launches, CUDA events on the launching stream) ----
     if rank == 0 and not a.no_breakdown:
-        line.update(breakdown(a, cfg, ep, 1e3 * total_ms / (a.steps * T2)))
+        line.update(breakdown(a, cfg, run, 1e3 * total_ms / (a.steps * T2)))
+    run.close()
 
     # ---- end to end through the public API with host buffers ----
     if not a.no_e2e:
-        e2e = run_e2e(a, cfg, ep.prob, dev, world, fast=True)
+        e2e = run_e2e(a, cfg, prob, dev, world, fast=True)
         if e2e is not None:
-            eager = run_e2e(a, cfg, ep.prob, dev, world, fast=False)
+            eager = run_e2e(a, cfg, prob, dev, world, fast=False)
             e2e['eager_value'] = eager['value']          # same call with fast=False: read-back after every iteration
             line['e2e'] = e2e
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
@@ -355,29 +276,44 @@ def run_b200(a, cfg, rank, world, local_rank):
     return line if rank == 0 else None
 
 
-def breakdown(a, cfg, ep, us_inner_graph):
+def breakdown(a, cfg, run, us_inner_graph):
+    """Where the iteration's time goes: the SAME launches as SvrgRun.fast_ops, issued eagerly one by one with a CUDA
+    event after each (attribution only: `value` above is the graph-replayed public path)."""
     import torch
-    eng = ep.eng
-    T2, N = cfg['T2'], cfg['H'] * cfg['W']
+    eng, p, d = run.eng, run.problem, run.denoiser
+    T2, N, B = cfg['T2'], cfg['H'] * cfg['W'], cfg['mini_batch_size']
     peaks_path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
     if os.path.exists(peaks_path):
         peak, peak_src = json.load(open(peaks_path))['hbm_gbs'], 'measured (MEASURED_PEAKS.json hbm_gbs, burst copy)'
     else:
         peak, peak_src = 6650.0, 'fallback (B200_PROFILING.md)'
-    ep.reset()
-    names, events = [], []
+    eng.resolve()
+    events = []
     n_iter = min(a.steps * T2, 100)
 
     def hook(name):
         e = torch.cuda.Event(enable_timing=True)
         e.record(eng.stream)
         events.append((name, e))
+
+    z = run.z
+    kw = dict(b=run.w, sel=eng.sel, with_y=False, gscale=1.0 / B, vadd=run.mu, step_ptr=eng.step, z_in=z, z_out=z, clear_sel=True)
+    fused_name = 'c2r+update+prox_fused(sigma+haar+psnr)'
     with torch.cuda.stream(eng.stream):
-        ep.snapshot_ops()
+        run.snapshot()
         for _ in range(n_iter):
             hook('start')
-            ep.inner_ops(hook)
-    eng.slot_host += n_iter
+            p._dev_grad(z, phases=1, sel_job=eng.sel_job(), **kw); hook('lines_r2c+selection')
+            p._dev_grad(z, phases=2, **kw); hook('cols_mask')
+            ok = p._dev_update_prox(1.0 / B, eng.step, run.mu, z, z, eng.sig_log, d.sigma_modifier, 0.0, p._xrec_dev,
+                                    eng.mse_log, eng.slot_ptr, advance=eng.counters, n_advance=3)
+            if ok:
+                hook(fused_name)
+            else:
+                p._dev_grad(z, phases=4, **kw); hook('lines_c2r+update')
+                eng.prox(z, z); hook('prox_fused(sigma+haar+psnr)')
+                eng.advance(); hook('advance')
+            eng.defer_slots(1)
     eng.stream.synchronize()
     acc = {}
     for (n0, e0), (n1, e1) in zip(events[:-1], events[1:]):
@@ -388,41 +324,42 @@ def breakdown(a, cfg, ep, us_inner_graph):
     tot = sum(per.values())
     # algorithmic (compulsory) bytes per launch, DESIGN.md "Kernels": fp32, N pixels
     alg = {
-        'lines_r2c': 12.0 * N,                       # read z, w (8N), write packed half spectrum (4N)
+        'lines_r2c+selection': 12.0 * N + 4.0 * B,   # read z, w (8N), write packed half spectrum (4N); minibatch positions
         'cols_mask': 8.5 * N,                        # read + write spectrum (8N), selection bytes (N/2)
         'lines_c2r+update': 16.0 * N,                # read spectrum, mu, z (12N), write z (4N)
-        'sigma_mad': 4.0 * N,                        # read z
         'prox_fused(sigma+haar+psnr)': 12.0 * N,     # read z, xrec (8N), write z (4N)
-        'c2r+update+prox_fused(sigma+haar+psnr)': 20.0 * N,   # read spectrum, mu, z, xrec (16N), write z (4N)
-        'haar_bayes+psnr': 12.0 * N,                 # read z, xrec (8N), write z (4N)
+        fused_name: 20.0 * N,                        # read spectrum, mu, z, xrec (16N), write z (4N)
     }
-    top = max(alg, key=lambda k: per.get(k, 0.0))
+    top = max((k for k in alg if k in per), key=lambda k: per[k])
     ach = alg[top] / (per[top] * 1e-6) / 1e9
-    traffic = ncu_traffic({'lines_r2c': 'k_lines_r2c', 'cols_mask': 'k_cols_mask', 'lines_c2r+update': 'k_lines_c2r',
-                           'sigma_mad': 'k_sigma_mad', 'haar_bayes+psnr': 'k_haar_bayes',
-                           'prox_fused(sigma+haar+psnr)': 'k_prox_wavelet_fused',
-                           'c2r+update+prox_fused(sigma+haar+psnr)': 'k_update_prox'}[top])
+    kern = {'lines_r2c+selection': 'k_lines_r2c', 'cols_mask': 'k_cols_mask', 'lines_c2r+update': 'k_lines_c2r',
+            'prox_fused(sigma+haar+psnr)': 'k_prox_wavelet_fused', fused_name: 'k_update_prox'}[top]
+    traffic, traffic_src = ncu_traffic(kern)
     iter_bytes = 28.125 * N
     out = {
         'kernel_us': per, 'kernel_us_sum_eager': tot,
         'roofline': {'bound': 'hbm', 'kernel': top, 'achieved': ach, 'peak': peak, 'unit': 'GB/s', 'frac': ach / peak,
-                     'traffic': traffic, 'traffic_source': 'profiles/r01_ncu_full_iteration_kernels.csv (ncu --set full, one launch, cold L2)',
-                     'peak_source': peak_src,
+                     'traffic': traffic, 'traffic_source': traffic_src, 'peak_source': peak_src,
                      'algorithmic_bytes_per_launch': alg[top], 'us_per_launch': per[top]},
         'roofline_iteration': {'bound': 'hbm', 'algorithmic_bytes': iter_bytes,
                                'achieved': iter_bytes / (us_inner_graph * 1e-6) / 1e9, 'peak': peak, 'unit': 'GB/s',
                                'frac': iter_bytes / (us_inner_graph * 1e-6) / 1e9 / peak,
                                'note': 'whole inner iteration incl. the amortised snapshot gradient, graph replay'},
     }
-    eng.flush_fast()
+    eng.resolve()
     return out
 
 
+NCU_FULL_CSV = 'r02_ncu_full_iteration_kernels.csv'
+
+
 def ncu_traffic(kernel):
-    """dram__bytes_read.sum + dram__bytes_write.sum of one launch of `kernel` from the committed ncu capture"""
-    path = os.path.join(ROOT, 'profiles', 'r01_ncu_full_iteration_kernels.csv')
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch of `kernel` from the committed ncu capture of this
+    round's build (profiles/README.md says which commit); (None, reason) when there is no capture of it."""
+    path = os.path.join(ROOT, 'profiles', NCU_FULL_CSV)
+    src = 'profiles/%s (ncu --set full, one launch, cold L2; a capture, not measured in this run)' % NCU_FULL_CSV
     if not os.path.exists(path):
-        return None
+        return None, 'no capture of this build under profiles/'
     import csv
     rows = list(csv.reader(open(path)))
     hdr, units = rows[0], rows[1]
@@ -433,8 +370,8 @@ def ncu_traffic(kernel):
             for name in ('dram__bytes_read.sum', 'dram__bytes_write.sum'):
                 i = hdr.index(name)
                 tot += float(r[i]) * mult.get(units[i], 1.0)
-            return tot
-    return None
+            return tot, src
+    return None, 'kernel not in ' + src
 
 
 def run_e2e(a, cfg, prob, dev, world, fast=True):

@@ -68,6 +68,22 @@ typedef struct {
                                      bit2 lines c2r + epilogue (used to time the passes one by one) */
     int clear_bits;               /* != 0: the column pass zeroes `bits` after using it (single-use minibatch
                                      selection; the next pnp_csmri_sel_* call then needs clear = 0) */
+    /* Optional: build the minibatch selection INSIDE pass 1 (needs phases bit0), by every thread of the pass while
+     * its first lines are in flight -- replaces a separate pnp_csmri_sel_* launch, which cannot share an SM with the
+     * pass.  `bits` must then be writable and ALL ZERO on entry (clear_bits of the previous use leaves it so).
+     * sel_count = 0: off.  Positions: sel_idx[img][*sel_cursor][0..sel_count) (k = ky*W + kx) when sel_idx is
+     * non-null, else the keyed Feistel draw pnp_csmri_sel_sample makes from sel_support / sel_m0 / sel_seed /
+     * *sel_counter (sel_count must not exceed sel_min_m0, the host-known lower bound of sel_m0[]). */
+    int sel_count;
+    const int* sel_idx;
+    long long sel_idx_img_stride;
+    const int* sel_cursor;
+    const int* sel_support;
+    const int* sel_m0;
+    long long sel_support_img_stride;
+    unsigned sel_seed;
+    const int* sel_counter;
+    int sel_min_m0;
 } pnp_csmri_grad_args;
 int pnp_csmri_grad(const pnp_csmri_grad_args* args, void* stream);
 
@@ -312,7 +328,7 @@ int pnp_saga_update(const float* g_new, float* g_prev, float* table, float* tsum
 /* counters[0..n) += 1 on the device (log slot / minibatch cursor for CUDA-graph replay) */
 int pnp_advance(int* counters, int n, void* stream);
 
-/* counters[0..n) += 1 and *x *= factor (step decay  eta*lr_decay**i  kept on the device) */
+/* counters[0..n) += 1 (n may be 0) and *x *= factor (step decay  eta*lr_decay**i  kept on the device) */
 int pnp_advance_scale(int* counters, int n, float* x, float factor, void* stream);
 /* dst[0..n) = src[0..n)  (w = copy(z), algorithms/pnp_svrg.py:35; capturable device copy) */
 int pnp_copy_f32(float* dst, const float* src, long long n, void* stream);
@@ -321,6 +337,9 @@ int pnp_copy_f32(float* dst, const float* src, long long n, void* stream);
  * shift shuffles, 2 no epilogue arithmetic / stores, 4 load one dl block only, 32 never use the multi-layer launch);
  * key 2: print the phase times of the last pnp_csmri_update_prox (builds with -DPNP_PHASE_TIMING only). */
 int pnp_debug_set(int key, int value);
+/* key 1: copy the event trace of a -DPNP_TRACE build (16-byte records: u64 %globaltimer ns, i32 tag, i16 blockIdx.x,
+ * i16 %smid) to out_host and reset it; returns the number of records (>= 0) or a negative status. */
+int pnp_debug_read(int key, void* out_host, long long bytes);
 
 /* ---- CUDA-graph helpers ---------------------------------------------------------------------
  * One inner iteration is launch-bound at 256x256 (about 2 MB of traffic); the host side captures

@@ -8,7 +8,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'lib', 'libpnp_b200.so')
+# PNP_LIB selects another build of the same library (e.g. the -DPNP_TRACE build used by scripts/trace_iter.py)
+LIB_PATH = os.environ.get('PNP_LIB') or os.path.join(_HERE, 'lib', 'libpnp_b200.so')
 
 c_float_p = C.c_void_p      # all device pointers travel as integers
 c_int_p = C.c_void_p
@@ -25,6 +26,9 @@ class CsmriGradArgs(C.Structure):
         ('g_out', C.c_void_p), ('vadd', C.c_void_p), ('v_out', C.c_void_p),
         ('z_in', C.c_void_p), ('z_out', C.c_void_p),
         ('phases', C.c_int), ('clear_bits', C.c_int),
+        ('sel_count', C.c_int), ('sel_idx', C.c_void_p), ('sel_idx_img_stride', C.c_longlong), ('sel_cursor', C.c_void_p),
+        ('sel_support', C.c_void_p), ('sel_m0', C.c_void_p), ('sel_support_img_stride', C.c_longlong),
+        ('sel_seed', C.c_uint), ('sel_counter', C.c_void_p), ('sel_min_m0', C.c_int),
     ]
 
 
@@ -121,6 +125,7 @@ PROTOTYPES = {
     'pnp_advance_scale': (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_float, C.c_void_p]),
     'pnp_copy_f32': (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p]),
     'pnp_debug_set': (C.c_int, [C.c_int, C.c_int]),
+    'pnp_debug_read': (C.c_int, [C.c_int, C.c_void_p, C.c_longlong]),
     'pnp_graph_begin': (C.c_int, [C.c_void_p]),
     'pnp_graph_end': (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
     'pnp_graph_launch': (C.c_int, [C.c_void_p, C.c_void_p]),

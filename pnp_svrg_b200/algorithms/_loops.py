@@ -24,17 +24,23 @@ def _grad_update(eng, a, b, sel, with_y, gscale, **kw):
     eng.p._dev_grad(a, b=b, sel=sel, with_y=with_y, gscale=gscale, clear_sel=sel is not None and sel is eng.sel, **kw)
 
 
-def _grad_update_prox(eng, a, b, sel, gscale, vadd, z, advance=0):
+def _grad_update_prox(eng, a, b, sel, gscale, vadd, z, advance=0, sel_fn=None):
     """z <- prox(z - step * (g_sel(a - b) * gscale + vadd)).  CSMRI + wavelet prox: the inverse line pass, the update,
     the sigma estimate and the prox run as ONE cooperative launch on lines resident in shared memory
     (pnp_csmri_update_prox); otherwise the gradient pass followed by ``eng.prox``.  ``advance`` > 0 also bumps
-    that many end-of-iteration counters (``eng.advance``), inside the same launch when it is the fused one."""
+    that many end-of-iteration counters (``eng.advance``), inside the same launch when it is the fused one.
+    ``sel_fn`` rebuilds the minibatch selection; on the CSMRI path the forward line pass does it itself
+    (``Engine.sel_job``: a separate selection kernel cannot share an SM with a pass that holds every register, so
+    even on a parallel graph branch it delayed the column pass)."""
     p, d = eng.p, eng.d
     own = sel is not None and sel is eng.sel
     if (eng.fused_tail is not False and eng.uses_sigma and not eng.sigma_ready and getattr(d, 'method', None) == 'wavelet'
             and hasattr(p, '_dev_update_prox')):
         kw = dict(b=b, sel=sel, with_y=False, gscale=gscale, vadd=vadd, step_ptr=eng.step, z_in=z, z_out=z, clear_sel=own)
-        p._dev_grad(a, phases=3, **kw)
+        job = eng.sel_job() if (sel_fn is not None and own) else None
+        if job is None and sel_fn is not None:
+            sel_fn()
+        p._dev_grad(a, phases=3, sel_job=job, **kw)
         ok = p._dev_update_prox(gscale, eng.step, vadd, z, z, eng.sig_log, d.sigma_modifier,
                                 d.denoise_strength * d.decay ** (d.t + 1), p._xrec_dev, eng.mse_log, eng.slot_ptr,
                                 advance=eng.counters if advance else None, n_advance=advance)
@@ -44,6 +50,8 @@ def _grad_update_prox(eng, a, b, sel, gscale, vadd, z, advance=0):
             return
         p._dev_grad(a, phases=4, **kw)              # the spectrum is there: finish with the separate kernels
     else:
+        if sel_fn is not None:
+            sel_fn()
         _grad_update(eng, a, b, sel, False, gscale, vadd=vadd, step_ptr=eng.step, z_in=z, z_out=z)
     eng.prox(z, z)
     if advance:
@@ -92,7 +100,10 @@ def _fast_inner(eng, budget, n_iters, inner_ops, host_draw, sync_every, converge
         # no stop rule needs the PSNR of every iterate: enqueue, count, and read the log back later
         while done < n_iters and budget.alive():
             left = budget.left()
-            room = min(n_iters - done, LOG_CHUNK - eng.slot_host, left if left is not None else 1 << 30)
+            # never enqueue more than sync_every iterations between two looks at the wall clock (``tt`` is the
+            # reference's only loop bound, algorithms/pnp_svrg.py:28; tune_* trials rely on it)
+            room = min(n_iters - done, LOG_CHUNK - eng.slot_host, max(1, sync_every - eng.since_sync),
+                       left if left is not None else 1 << 30)
             if room <= 0:
                 eng.resolve()
                 continue
@@ -274,91 +285,246 @@ def pnp_sgd(problem, denoiser, eta, tt, mini_batch_size, verbose=True, lr_decay=
 
 
 # ---------------------------------------------------------------------------------------- SVRG
+class SvrgRun:
+    """One PnP-SVRG reconstruction resident on the device (algorithms/pnp_svrg.py:8-105): the iterate, the snapshot
+    ``w``, the snapshot gradient ``mu`` and the logs live in HBM, ``loop()`` is the reference's control flow.
+
+    ``fast`` without stop rules runs WHOLE EPOCHS as one CUDA graph each (``epoch()``): snapshot gradient, ``w = z``,
+    T2 inner iterations (minibatch selection on a parallel branch next to the forward line pass, fused gradient +
+    variance-reduced update + sigma estimate + prox + PSNR), step decay.  Host-drawn minibatches ('host', 'legacy',
+    'stream') of epoch e + 1 are staged and copied on a second stream while the graph of epoch e runs: two sets of
+    T2 device index buffers, one graph per set.  ``bench.py`` times exactly this method; ``pnp_svrg(fast=True)`` is a
+    loop around it."""
+
+    def __init__(self, problem, denoiser, eta, T2, mini_batch_size, lr_decay=1, vr_mode='as_committed',
+                 mb_source='legacy', mb_seed=0, mb_stream=None, fast=False):
+        if vr_mode not in ('as_committed', 'paper'):
+            raise ValueError("vr_mode must be 'as_committed' or 'paper'")
+        self.problem, self.denoiser = problem, denoiser
+        self.eta, self.lr_decay = float(eta), float(lr_decay)
+        self.B, self.T2 = int(mini_batch_size), int(T2)
+        self.paper = vr_mode == 'paper'
+        self.mb_source, self.fast = mb_source, fast
+        self.eng = eng = Engine(problem, denoiser, self.B, mb_source, mb_seed, mb_stream, fast)
+        self.z = eng.z
+        with torch.cuda.stream(eng.stream):
+            self.w = torch.empty_like(self.z)
+            self.mu = torch.empty_like(self.z)
+        self.i = 0                      # outer (epoch) index
+        self.draw = _host_draw_fn(eng) if (self.paper or mb_source == 'legacy') else None
+        self._epoch_graphs = {}
+        self._epoch_sets = None         # device index buffers [set][T2][B] for host-drawn minibatches
+        self._step_on_device = False    # epoch graphs keep eta * lr_decay**i on the device
+
+    # ---- the launches ----------------------------------------------------------------------------------------
+    def snapshot(self):
+        """mu = grad_full(z) ; w = copy(z)          (pnp_svrg.py:32-35)"""
+        eng, problem = self.eng, self.problem
+        _grad_update(eng, self.z, None, None, True, 1.0 / _full_norm(problem), g_out=self.mu)
+        if getattr(problem, 'shard', None) is not None:
+            problem._snapshot_allreduce(self.mu)     # measurement-sharded snapshot: partial sums -> full gradient
+        eng.copy(self.w, self.z)
+
+    def grad_ops(self):
+        eng, z = self.eng, self.z
+        if self.paper:
+            _grad_update(eng, z, self.w, eng.sel, False, 1.0 / self.B, vadd=self.mu, step_ptr=eng.step, z_in=z, z_out=z)
+        else:
+            eng.check(eng.lib.pnp_axpy(D.ptr(z), D.ptr(self.mu), D.ptr(z), eng.N, 1, 0.0, D.ptr(eng.step), eng.sptr))
+
+    def fast_ops(self):
+        """one inner iteration as it is captured (per iteration, or T2 times inside an epoch graph)"""
+        eng, z = self.eng, self.z
+        if self.paper:
+            _grad_update_prox(eng, z, self.w, eng.sel, 1.0 / self.B, self.mu, z, advance=3,
+                              sel_fn=lambda: _sel_ops(eng))
+        else:
+            self.grad_ops()
+            eng.prox(z, z)
+            eng.advance()
+
+    # ---- whole epochs as one graph ----------------------------------------------------------------------------
+    def epoch_mode(self, converge_check=False, diverge_check=False):
+        """True when whole epochs can run as one graph: fast mode, no per-iterate stop rule, no sharded snapshot
+        (its NCCL all-reduce stays outside a capture), log capacity for an epoch."""
+        return (self.fast and not (converge_check is True or diverge_check is True) and self.T2 >= 1
+                and getattr(self.problem, 'shard', None) is None and self.T2 <= LOG_CHUNK // 4)
+
+    def _needs_indices(self):
+        return self.B > 0 and self.mb_source != 'device' and (self.paper or self.mb_source == 'legacy')
+
+    def _epoch_ops(self, bufs):
+        eng = self.eng
+        self.snapshot()
+        keep = eng.idx_dev if self.B > 0 else None
+        for j in range(self.T2):
+            if bufs is not None:
+                eng.idx_dev = bufs[j]
+            self.fast_ops()
+        if self.B > 0:
+            eng.idx_dev = keep
+        if self.lr_decay != 1.0:
+            eng.check(eng.lib.pnp_advance_scale(D.ptr(eng.counters), 0, D.ptr(eng.step), self.lr_decay, eng.sptr))
+
+    def _prepare_epochs(self):
+        eng = self.eng
+        if self._epoch_graphs:
+            return
+        n_sets = 2 if self._needs_indices() else 1
+        if n_sets == 2:
+            n = self.B + eng.n_extra
+            with torch.cuda.stream(eng.stream):
+                self._epoch_sets = torch.zeros(2, self.T2, n, dtype=torch.int32, device=eng.dev)
+            self._copy_stream = torch.cuda.Stream(device=eng.dev)
+            self._ev_ready = [torch.cuda.Event() for _ in range(2)]
+            self._ev_done = [None, None]
+            if eng.mb_source != 'host':            # 'legacy' / 'stream': drawn in Python into pinned sets
+                self._pinned_sets = torch.empty(2, self.T2, n, dtype=torch.int32).pin_memory()
+                self._ev_copied = [None, None]
+        with torch.cuda.stream(eng.stream):
+            eng.set_step(self.eta * self.lr_decay ** self.i)
+            # one eager epoch-shaped warm-up is NOT run: the kernels were loaded by pnp_init, and a capture does not execute
+        t_before = self.denoiser.t
+        for s_ in range(n_sets):
+            bufs = None if self._epoch_sets is None else [self._epoch_sets[s_, j] for j in range(self.T2)]
+            self._epoch_graphs[s_] = eng.capture(lambda: self._epoch_ops(bufs))
+        self.denoiser.t = t_before      # a capture runs the host side of fast_ops only
+        self._step_on_device = True
+        self._epochs_launched = 0
+
+    def _stage_epoch(self, s_):
+        """draw the T2 minibatches of the next epoch and copy them into index set ``s_`` on the copy stream"""
+        eng, cs = self.eng, self._copy_stream
+        if self._ev_done[s_] is not None:
+            cs.wait_event(self._ev_done[s_])           # the epoch that last read this set (two epochs ago)
+        if eng.mb_source == 'host':
+            for j in range(self.T2):                   # native look-ahead queue: draw -> pinned ring -> async copy
+                eng._draws.stage(self._epoch_sets[s_, j].data_ptr(), (), cs.cuda_stream)
+        else:
+            if self._ev_copied[s_] is not None:
+                self._ev_copied[s_].synchronize()      # the copy that last read this pinned set
+            host = self._pinned_sets[s_].numpy()
+            for j in range(self.T2):
+                if eng.mb_source == 'legacy':
+                    host[j, :self.B] = eng.p._draw_indices(self.B)      # np.random, the reference's call order
+                else:
+                    idx = np.asarray(eng.mb_stream[eng._stream_pos])
+                    eng._stream_pos += 1
+                    if idx.size != self.B:
+                        raise ValueError('mb_stream entry %d has %d positions, expected %d' % (eng._stream_pos - 1, idx.size, self.B))
+                    host[j, :self.B] = idx
+            with torch.cuda.stream(cs):
+                self._epoch_sets[s_].copy_(self._pinned_sets[s_], non_blocking=True)
+            ev = self._ev_copied[s_] or torch.cuda.Event()
+            ev.record(cs)
+            self._ev_copied[s_] = ev
+        self._ev_ready[s_].record(cs)
+
+    def epoch(self):
+        """Enqueue one whole epoch (snapshot + T2 inner iterations); nothing is read back (``eng.defer_slots``)."""
+        eng = self.eng
+        self._prepare_epochs()
+        if eng.slot_host + self.T2 > LOG_CHUNK:
+            eng.resolve()
+        s_ = 0
+        if self._epoch_sets is not None:
+            s_ = self._epochs_launched & 1
+            self._stage_epoch(s_)
+            eng.stream.wait_event(self._ev_ready[s_])
+        if eng.deferred:
+            eng.defer_dup()                              # PnP-SVRG logs PSNR(z) again at every snapshot (pnp_svrg.py:37-40)
+        else:
+            eng.time_log.append(0.0)
+            eng.psnr_log.append(eng.psnr_log[-1])
+        eng.replay(self._epoch_graphs[s_])
+        if self._epoch_sets is not None:
+            ev = self._ev_done[s_] or torch.cuda.Event()
+            ev.record(eng.stream)
+            self._ev_done[s_] = ev
+        eng.defer_slots(self.T2)
+        self.denoiser.t += self.T2
+        self._epochs_launched += 1
+        self.i += 1
+
+    def close(self):
+        eng = self.eng
+        eng.destroy(eng.graph)
+        eng.graph = None
+        for g in self._epoch_graphs.values():
+            eng.destroy(g)
+        self._epoch_graphs = {}
+
+    # ---- the reference's loop ---------------------------------------------------------------------------------
+    def loop(self, tt, max_iters=None, verbose=True, converge_check=True, diverge_check=False, sync_every=64):
+        eng, z, T2, fast = self.eng, self.z, self.T2, self.fast
+        budget = Budget(tt, max_iters)
+        eng.time_log.append(time.time() - budget.t0)
+        psnr_z = eng.psnr_of(z)
+        eng.psnr_log.append(psnr_z)
+        stop = False
+        it = _Faithful(eng, verbose)
+        epochs = self.epoch_mode(converge_check, diverge_check)
+        while budget.alive() and not stop:
+            left = budget.left()
+            if epochs and (left is None or left >= T2):
+                self.epoch()
+                budget.calls += T2
+                psnr_z = None
+                if eng.since_sync >= sync_every:
+                    eng.resolve()          # bounds how far the host runs ahead of the GPU (wall-clock budget tt)
+                continue
+            t_outer = time.time()
+            with torch.cuda.stream(eng.stream):
+                self.snapshot()
+                if not self._step_on_device:
+                    eng.set_step(self.eta * self.lr_decay ** self.i)
+            if not fast:
+                eng.stream.synchronize()
+            if eng.deferred:
+                eng.defer_dup()
+            else:
+                eng.time_log.append(time.time() - t_outer)
+                eng.psnr_log.append(psnr_z if psnr_z is not None else eng.psnr_log[-1])
+            if fast:
+                psnr_z, stop, _ = _fast_inner(eng, budget, T2, self.fast_ops, self.draw,
+                                              min(sync_every, T2) if converge_check or diverge_check else sync_every,
+                                              converge_check, diverge_check, psnr_z)
+                if self._step_on_device and self.lr_decay != 1.0:
+                    with torch.cuda.stream(eng.stream):
+                        eng.check(eng.lib.pnp_advance_scale(D.ptr(eng.counters), 0, D.ptr(eng.step), self.lr_decay, eng.sptr))
+            else:
+                i = self.i
+                for j in range(T2):
+                    if not budget.alive():
+                        break
+                    start = psnr_z
+
+                    def grad_phase():
+                        if self.mb_source == 'device':
+                            if self.paper:
+                                eng.sample_sel_device()
+                        else:
+                            eng.draw_host()            # drawn even when unused (pnp_svrg.py:52)
+                            if self.paper:
+                                eng.upload_sel()
+                        self.grad_ops()
+                    psnr_z = it.run(grad_phase, z, z, str(i) + " " + str(j) + " Before denoising:  ",
+                                    "After denoising update: " + str(i) + " " + str(j) + " ")
+                    budget.calls += 1
+                    if stop_rule(start, psnr_z, converge_check, diverge_check):
+                        stop = True
+                        break
+            self.i += 1
+        self.close()
+        return eng.result('PnP SVRG')
+
+
 def pnp_svrg(problem, denoiser, eta, tt, T2, mini_batch_size, verbose=True, lr_decay=1, converge_check=True,
              diverge_check=False, max_iters=None, vr_mode='as_committed', mb_source='legacy', mb_seed=0,
              mb_stream=None, fast=False, sync_every=64):
     """algorithms/pnp_svrg.py:8-105."""
-    if vr_mode not in ('as_committed', 'paper'):
-        raise ValueError("vr_mode must be 'as_committed' or 'paper'")
-    B = int(mini_batch_size)
-    T2 = int(T2)
-    eng = Engine(problem, denoiser, B, mb_source, mb_seed, mb_stream, fast)
-    budget = Budget(tt, max_iters)
-    eng.time_log.append(time.time() - budget.t0)
-    psnr_z = eng.psnr_of(eng.z)
-    eng.psnr_log.append(psnr_z)
-    z = eng.z
-    with torch.cuda.stream(eng.stream):
-        w = torch.empty_like(z)
-        mu = torch.empty_like(z)
-    paper = vr_mode == 'paper'
-
-    def snapshot():
-        # mu = grad_full(z) ; w = copy(z)          (pnp_svrg.py:32-35)
-        _grad_update(eng, z, None, None, True, 1.0 / _full_norm(problem), g_out=mu)
-        if getattr(problem, 'shard', None) is not None:
-            problem._snapshot_allreduce(mu)          # measurement-sharded snapshot: partial sums -> full gradient
-        eng.copy(w, z)
-
-    def grad_ops():
-        if paper:
-            _grad_update(eng, z, w, eng.sel, False, 1.0 / B, vadd=mu, step_ptr=eng.step, z_in=z, z_out=z)
-        else:
-            eng.check(eng.lib.pnp_axpy(D.ptr(z), D.ptr(mu), D.ptr(z), eng.N, 1, 0.0, D.ptr(eng.step), eng.sptr))
-
-    i = 0
-    stop = False
-    it = _Faithful(eng, verbose)
-
-    def fast_ops():
-        if paper:
-            _sel_ops(eng)
-            _grad_update_prox(eng, z, w, eng.sel, 1.0 / B, mu, z, advance=3)
-        else:
-            grad_ops()
-            eng.prox(z, z)
-            eng.advance()
-    draw = _host_draw_fn(eng) if (paper or mb_source == 'legacy') else None
-
-    while budget.alive() and not stop:
-        t_outer = time.time()
-        with torch.cuda.stream(eng.stream):
-            snapshot()
-            eng.set_step(eta * lr_decay ** i)
-        if not fast:
-            eng.stream.synchronize()
-        if eng.deferred:
-            eng.defer_dup()
-        else:
-            eng.time_log.append(time.time() - t_outer)
-            eng.psnr_log.append(psnr_z if psnr_z is not None else eng.psnr_log[-1])
-        if fast:
-            psnr_z, stop, _ = _fast_inner(eng, budget, T2, fast_ops, draw, min(sync_every, T2) if converge_check or diverge_check else sync_every,
-                                          converge_check, diverge_check, psnr_z)
-        else:
-            for j in range(T2):
-                if not budget.alive():
-                    break
-                start = psnr_z
-
-                def grad_phase():
-                    if mb_source == 'device':
-                        if paper:
-                            eng.sample_sel_device()
-                    else:
-                        eng.draw_host()            # drawn even when unused (pnp_svrg.py:52)
-                        if paper:
-                            eng.upload_sel()
-                    grad_ops()
-                psnr_z = it.run(grad_phase, z, z, str(i) + " " + str(j) + " Before denoising:  ",
-                                "After denoising update: " + str(i) + " " + str(j) + " ")
-                budget.calls += 1
-                if stop_rule(start, psnr_z, converge_check, diverge_check):
-                    stop = True
-                    break
-        i += 1
-    eng.destroy(eng.graph)
-    return eng.result('PnP SVRG')
+    run = SvrgRun(problem, denoiser, eta, T2, mini_batch_size, lr_decay, vr_mode, mb_source, mb_seed, mb_stream, fast)
+    return run.loop(tt, max_iters, verbose, converge_check, diverge_check, sync_every)
 
 
 # ---------------------------------------------------------------------------------------- SAGA

@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, 'csrc', 'pnp_b200.cu')
 HOST_SRC = os.path.join(HERE, 'csrc', 'host_sampler.cpp')     # plain C++: nvcc hands it to the host compiler
-OUT = os.path.join(HERE, 'lib', 'libpnp_b200.so')
+OUT = os.environ.get('PNP_LIB_OUT') or os.path.join(HERE, 'lib', 'libpnp_b200.so')
 NVCC_FLAGS = ['-std=c++17', '-O3', '-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo',
               '-shared', '-Xcompiler', '-fPIC']
 

@@ -41,6 +41,99 @@ struct GradEpilogue {
     float* z_out;
 };
 
+// ------------------------------------------------------------------ selection bits
+__device__ __forceinline__ void or_byte(unsigned char* base, long long byte_idx, unsigned v) {
+    unsigned* w = reinterpret_cast<unsigned*>(base) + (byte_idx >> 2);
+    atomicOr(w, v << (8 * (int)(byte_idx & 3)));
+}
+
+// k = ky * W + kx is an index into the reference's (H, W) k-space array (problems/CSMRI.py:66-74)
+__device__ __forceinline__ void set_sel_bits(unsigned char* bits, int H, int W, int k) {
+    const int ky = k / W, kx = k % W;
+    const int hp = H / 2;
+    const int kym = (H - ky) % H, kxm = (W - kx) % W;
+    if (ky < hp) or_byte(bits, (long long)ky * W + kx, 1u);
+    else if (ky == hp) or_byte(bits, kx, 4u);
+    if (kym < hp) or_byte(bits, (long long)kym * W + kxm, 2u);
+    else if (kym == hp) or_byte(bits, kxm, 8u);
+}
+
+// explicit minibatch:  idx[img][cursor][0..B)
+// device-drawn minibatch: B distinct positions of the sampled support through a keyed
+// cycle-walking Feistel permutation of [0, M0)  (bench / production mode; the reference draws
+// with np.random.choice(..., replace=False), problems/CSMRI.py:72)
+__device__ __forceinline__ unsigned mix32(unsigned x) {
+    x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15; x *= 0x846ca68bU; x ^= x >> 16;
+    return x;
+}
+// Generalised (unbalanced) Feistel network on Z_b x Z_a with a = 2^hb >= sqrt(n) and b = ceil(n / a): the domain
+// a*b exceeds n by less than a, so cycle walking almost never iterates (a balanced 2^(2 hb) domain needs up to 4
+// passes per index).  Rounds alternate (l, r) -> (r, (l + F(r)) mod b) and (l, r) -> (r, (l + F(r)) mod a); the
+// reduction of F to [0, b) is a multiply-high, so there is no division.  Host twins: host_sampler.cpp and
+// engine.feistel_sample (NumPy) produce the same sequence bit for bit.
+__device__ __forceinline__ unsigned feistel_perm(unsigned i, unsigned n, unsigned key) {
+    int hb = 1;
+    while ((1u << (2 * hb)) < n) ++hb;                 // a = 2^hb, a*a >= n
+    const unsigned hm = (1u << hb) - 1u;
+    const unsigned b = (n + hm) >> hb;                 // ceil(n / a) <= a
+    unsigned x = i;
+    do {
+        unsigned l = x >> hb, r = x & hm;              // l in Z_b, r in Z_a
+#pragma unroll
+        for (int rd = 0; rd < 4; rd += 2) {
+            const unsigned f0 = __umulhi(mix32(r ^ (key + 0x9e3779b9U * (rd + 1))), b);
+            unsigned t = l + f0;                        // < 2b
+            t = t >= b ? t - b : t;
+            l = r;                                      // (l, r) now in Z_a x Z_b
+            r = t;
+            const unsigned f1 = mix32(r ^ (key + 0x9e3779b9U * (rd + 2))) & hm;
+            t = (l + f1) & hm;
+            l = r;                                      // back in Z_b x Z_a
+            r = t;
+        }
+        x = (l << hb) | r;
+    } while (x >= n);
+    return x;
+}
+
+
+// Minibatch selection done INSIDE pass 1 (all threads of the persistent grid, while the first lines are still on
+// their way from HBM): the stand-alone selection kernels cannot share an SM with a pass that holds every register,
+// so on a parallel graph branch they only started when the first line CTAs retired and the column pass waited
+// for them (6 us of an 82 us iteration).  Explicit indices idx[img][*cursor][0..count) when idx != null, else the
+// keyed Feistel draw of `count` positions of support[img][0..m0[img]).  `bits` must be zero on entry.
+struct SelJob {
+    unsigned char* bits;          // null: no selection in this pass
+    const int* idx;
+    long long idx_img_stride;
+    const int* cursor;
+    const int* support;
+    const int* m0;
+    long long support_img_stride;
+    int count;
+    unsigned seed;
+    const int* counter;
+    int* idx_out;                 // optional [batch][count]: the positions drawn by the sampler
+};
+
+__device__ __forceinline__ void run_sel_job(const SelJob& sj, int H, int W, int img, int tid, int nthreads) {
+    unsigned char* bi = sj.bits + (long long)img * W * (H / 2);
+    if (sj.idx) {
+        const int* src = sj.idx + (long long)img * sj.idx_img_stride + (long long)(sj.cursor ? *sj.cursor : 0) * sj.count;
+        for (int i = tid; i < sj.count; i += nthreads) set_sel_bits(bi, H, W, src[i]);
+    } else {
+        const unsigned key = mix32(sj.seed ^ mix32((sj.counter ? (unsigned)*sj.counter : 0u) * 0x632be5abU + (unsigned)img));
+        const int* sup = sj.support + (long long)img * sj.support_img_stride;
+        const unsigned n = (unsigned)sj.m0[img];
+        for (int i = tid; i < sj.count; i += nthreads) {
+            if ((unsigned)i >= n) break;              // count <= m0 is the caller's contract; never walk outside the domain
+            const int k = sup[feistel_perm((unsigned)i, n, key)];
+            if (sj.idx_out) sj.idx_out[(long long)img * sj.count + i] = k;
+            set_sel_bits(bi, H, W, k);
+        }
+    }
+}
+
 // ------------------------------------------------------------------ pass 1
 // group stride (floats) of the per-pair exchange buffers: 2 planes, skewed so that GP groups read
 // at the same in-plane index hit different banks
@@ -57,7 +150,7 @@ template <int L, int GP> __host__ __device__ constexpr int lines_stage_off() { r
 template <int L, int GP>
 __global__ void __launch_bounds__(GP * (L / FftPlan<L>::EPT), (GP * (L / FftPlan<L>::EPT) >= 256 ? 2 : 4))
 k_lines_r2c(const float* __restrict__ a, const float* __restrict__ b, float2* __restrict__ S,
-            int nlines, long long img_stride) {
+            int nlines, long long img_stride, SelJob sj) {
     constexpr int T = fft_threads<L>();
     constexpr int EPT = FftPlan<L>::EPT;
     constexpr int PL = fft_plane<L>();
@@ -82,16 +175,19 @@ k_lines_r2c(const float* __restrict__ a, const float* __restrict__ b, float2* __
         if (b) bulk_g2s(stage_b, b + ibase + (long long)(2 * item * GP) * L, bytes, &bar);
     };
 
+    trace(100);
     if (threadIdx.x == 0) { mbar_init(&bar, 1); mbar_fence_init(); }
     __syncthreads();
     int item = blockIdx.x;
     if (threadIdx.x == 0 && item < items) issue(item);
     FftTw<L> tw;
     tw.init(t);
+    if (sj.bits) run_sel_job(sj, L, nlines, blockIdx.y, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x);
     unsigned parity = 0;
     for (; item < items; item += gridDim.x) {
         float2 x[EPT];
         mbar_wait(&bar, parity);
+        trace(101);
         parity ^= 1;
         if (item * GP + g < npairs) {
             const float* la = stage_a + 2 * g * L;
@@ -133,7 +229,9 @@ k_lines_r2c(const float* __restrict__ a, const float* __restrict__ b, float2* __
             S4[(long long)k * W2 + gg] = o;
         }
         __syncthreads();
+        trace(102);
     }
+    trace(109);
 }
 
 // ------------------------------------------------------------------ pass 2
@@ -189,20 +287,25 @@ k_cols_mask(float2* __restrict__ S, const unsigned char* __restrict__ bits,
         bulk_g2s(stage, Si + (long long)(1 + item * NC) * L, bytes, &bar);
         bulk_g2s(const_cast<unsigned char*>(stage_bits), bi + (long long)(1 + item * NC) * L, (unsigned)(nc * L), &bar);
     };
+    trace(200);
     if (threadIdx.x == 0) { mbar_init(&bar, 1); mbar_fence_init(); }
     __syncthreads();
-    int item = blockIdx.x;
+    // CTA 0 of the grid owns packed column 0 (two transforms through a scalar split: as an appendix of an item CTA
+    // it ended 2 us after everybody else); the others loop over the items
+    const int nct = (int)gridDim.x - 1;
+    int item = blockIdx.x > 0 ? (int)blockIdx.x - 1 : items;
     if (threadIdx.x == 0 && item < items) issue(item);
     FftTw<L> tw;
     tw.init(t);
     unsigned parity = 0;
-    for (; item < items; item += gridDim.x) {
+    for (; item < items; item += nct) {
         const int col = 1 + item * NC + g;
         const bool active = col < hp;
         const long long crow = (long long)(active ? col : 0) * L;
         unsigned long long bbp = 0ull;                                      // 4 selection bits per element
         float2 x[EPT];
         mbar_wait(&bar, parity);
+        trace(201);
         parity ^= 1;
         if (active) {
 #pragma unroll
@@ -214,7 +317,7 @@ k_cols_mask(float2* __restrict__ S, const unsigned char* __restrict__ bits,
             for (int i = 0; i < EPT; ++i) x[i] = make_float2(0.f, 0.f);
         }
         __syncthreads();                            // staging consumed -> refill it for the next item
-        if (threadIdx.x == 0 && item + (int)gridDim.x < items) issue(item + gridDim.x);
+        if (threadIdx.x == 0 && item + nct < items) issue(item + nct);
         if (clear_bits && active) {                 // minibatch selection is single use: leave the row zeroed
             unsigned char* cb = clear_bits + (long long)img * bits_img_stride + crow;
             for (int i = t; i < L / 16; i += T) reinterpret_cast<uint4*>(cb)[i] = make_uint4(0u, 0u, 0u, 0u);
@@ -237,10 +340,11 @@ k_cols_mask(float2* __restrict__ S, const unsigned char* __restrict__ bits,
             for (int i = 0; i < EPT; ++i) Sc[IX::out(t, i)] = cswap(y[i]);
         }
         if (FftPlan<L>::NS > 1) __syncthreads();
+        trace(202);
     }
+    trace(209);
 
-    // done by the LAST CTA: with items = 1.73 x CTAs it has a single item, so this extra work is not a straggler
-    if (blockIdx.x != gridDim.x - 1) return;
+    if (blockIdx.x != 0) return;
     // ---- packed column 0: C = FFT(DC + i * Nyq); split, select each row, re-pack ----
     {
         float2 x[EPT];
@@ -288,6 +392,7 @@ k_cols_mask(float2* __restrict__ S, const unsigned char* __restrict__ bits,
             }
         }
     }
+    trace(210);
 }
 
 // ------------------------------------------------------------------ pass 3
@@ -420,6 +525,7 @@ k_lines_c2r(const float2* __restrict__ S, int nlines, long long img_stride, floa
 template <int L> __host__ __device__ constexpr int upd_gp() { return 512 / fft_threads<L>(); }
 __device__ unsigned long long g_upd_phase_ns[8];      // PNP_PHASE_TIMING builds only: %globaltimer at the phase boundaries of CTA 0
 __device__ __forceinline__ void upd_mark(int i) {
+    trace(300 + i);
 #ifdef PNP_PHASE_TIMING
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         unsigned long long t;
@@ -444,8 +550,7 @@ k_update_prox(const float2* __restrict__ S, int nlines, float inv_n, float gscal
     constexpr int NQ = (L / 2) / T;
     using IX = FftIdx<L>;
     extern __shared__ __align__(128) float smem[];
-    __shared__ __align__(8) unsigned long long bar;
-    __shared__ unsigned scratch[16][32];
+    __shared__ __align__(8) unsigned long long bars[4];         // z_in lines of round 0 / of the later rounds / ground truth
     float* lines = smem + lines_stage_off<L, GP>();             // resident: 2 * pairs_per_cta lines
     const int g = threadIdx.x / T, t = threadIdx.x % T;
     const int npairs = nlines >> 1;
@@ -461,12 +566,22 @@ k_update_prox(const float2* __restrict__ S, int nlines, float inv_n, float gscal
 
     upd_mark(0);
     if (threadIdx.x == 0) {
-        mbar_init(&bar, 1);
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
+        mbar_init(&bars[2], 1);
         mbar_fence_init();
         if (mine > 0) {
-            mbar_expect_tx(&bar, (unsigned)(2 * mine * L * sizeof(float)));
-            for (int l = 0; l < 2 * mine; ++l)
-                bulk_g2s(lines + (long long)l * L, z_in + (first + l) * L, (unsigned)(L * sizeof(float)), &bar);
+            // the first round of transforms only waits for ITS lines (all CTAs start together: the whole iterate is
+            // requested from HBM in the same microsecond, and round 0 used to wait for all of it)
+            const int l0 = 2 * (mine < GP ? mine : GP);
+            mbar_expect_tx(&bars[0], (unsigned)(l0 * L * sizeof(float)));
+            for (int l = 0; l < l0; ++l)
+                bulk_g2s(lines + (long long)l * L, z_in + (first + l) * L, (unsigned)(L * sizeof(float)), &bars[0]);
+            if (2 * mine > l0) {
+                mbar_expect_tx(&bars[1], (unsigned)((2 * mine - l0) * L * sizeof(float)));
+                for (int l = l0; l < 2 * mine; ++l)
+                    bulk_g2s(lines + (long long)l * L, z_in + (first + l) * L, (unsigned)(L * sizeof(float)), &bars[1]);
+            }
         }
     }
     // the operands of the later phases (mu for the update, the ground truth for the PSNR) come from DRAM: start them
@@ -515,7 +630,7 @@ k_update_prox(const float2* __restrict__ S, int nlines, float inv_n, float gscal
         for (int i = 0; i < EPT; ++i) x[i] = sb.get(IX::in(t, i));
         __syncthreads();
         fft_regs<L>(t, sb, x, tw);
-        if (round == 0) mbar_wait(&bar, 0);                     // z_in lines have landed in the resident buffer
+        if (round <= 1) mbar_wait(&bars[round], 0);             // z_in lines of this round (round >= 1: of all later rounds) have landed
         const int pl = round * GP + g;
         if (pl < mine) {
             float* lz = lines + (long long)(2 * pl) * L;
@@ -535,41 +650,19 @@ k_update_prox(const float2* __restrict__ S, int nlines, float inv_n, float gscal
             }
         }
         __syncthreads();                            // exchange buffers free for the next round; lines complete
+        trace(310 + round);
     }
 
     upd_mark(1);
-    prox_phase_sigma<L>(lines, 2 * mine, first, nlines, 1, sig_log, cur_slot, scratch);
-    __syncthreads();
-    upd_mark(2);
-    __threadfence();
-    cooperative_groups::this_grid().sync();
-    // end-of-iteration counters (pnp_advance) folded in: every CTA has read *slot before the barrier above, and
-    // nothing else of this iteration reads them any more
-    if (advance && blockIdx.x == 0 && threadIdx.x < n_advance) advance[threadIdx.x] += 1;
-    upd_mark(3);
-    prox_phase_shrink<L>(lines, 2 * mine, first, nlines, 1, z_out, xrec, sigma_modifier, fallback_sigma, sig_log, mse_log, cur_slot);
-    __syncthreads();
+    // the exchange planes in front of the resident lines are idle from here on: they hold the per-warp scratch of the
+    // prox phases (sigma selection, Haar transposition)
+    static_assert(L < 512 || lines_stage_off<L, GP>() >= 16 * prox_scratch<L>(), "exchange planes too small for the prox scratch");
+    prox_phases<L>(lines, 2 * mine, first, nlines, 1, z_out, xrec, sigma_modifier, fallback_sigma, sig_log, mse_log, cur_slot,
+                   reinterpret_cast<unsigned*>(smem), &bars[2], advance, n_advance);
     upd_mark(4);
 }
 
-// ------------------------------------------------------------------ selection bits
-__device__ __forceinline__ void or_byte(unsigned char* base, long long byte_idx, unsigned v) {
-    unsigned* w = reinterpret_cast<unsigned*>(base) + (byte_idx >> 2);
-    atomicOr(w, v << (8 * (int)(byte_idx & 3)));
-}
-
-// k = ky * W + kx is an index into the reference's (H, W) k-space array (problems/CSMRI.py:66-74)
-__device__ __forceinline__ void set_sel_bits(unsigned char* bits, int H, int W, int k) {
-    const int ky = k / W, kx = k % W;
-    const int hp = H / 2;
-    const int kym = (H - ky) % H, kxm = (W - kx) % W;
-    if (ky < hp) or_byte(bits, (long long)ky * W + kx, 1u);
-    else if (ky == hp) or_byte(bits, kx, 4u);
-    if (kym < hp) or_byte(bits, (long long)kym * W + kxm, 2u);
-    else if (kym == hp) or_byte(bits, kxm, 8u);
-}
-
-// explicit minibatch:  idx[img][cursor][0..B)
+// ------------------------------------------------------------------ selection kernels
 __global__ void k_sel_from_indices(unsigned char* __restrict__ bits, int H, int W, const int* __restrict__ idx,
                                    int B, long long idx_img_stride, const int* __restrict__ cursor) {
     const int img = blockIdx.y;
@@ -580,63 +673,29 @@ __global__ void k_sel_from_indices(unsigned char* __restrict__ bits, int H, int 
         set_sel_bits(bi, H, W, src[i]);
 }
 
-// device-drawn minibatch: B distinct positions of the sampled support through a keyed
-// cycle-walking Feistel permutation of [0, M0)  (bench / production mode; the reference draws
-// with np.random.choice(..., replace=False), problems/CSMRI.py:72)
-__device__ __forceinline__ unsigned mix32(unsigned x) {
-    x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15; x *= 0x846ca68bU; x ^= x >> 16;
-    return x;
-}
-// Generalised (unbalanced) Feistel network on Z_b x Z_a with a = 2^hb >= sqrt(n) and b = ceil(n / a): the domain
-// a*b exceeds n by less than a, so cycle walking almost never iterates (a balanced 2^(2 hb) domain needs up to 4
-// passes per index).  Rounds alternate (l, r) -> (r, (l + F(r)) mod b) and (l, r) -> (r, (l + F(r)) mod a); the
-// reduction of F to [0, b) is a multiply-high, so there is no division.  Host twins: host_sampler.cpp and
-// engine.feistel_sample (NumPy) produce the same sequence bit for bit.
-__device__ __forceinline__ unsigned feistel_perm(unsigned i, unsigned n, unsigned key) {
-    int hb = 1;
-    while ((1u << (2 * hb)) < n) ++hb;                 // a = 2^hb, a*a >= n
-    const unsigned hm = (1u << hb) - 1u;
-    const unsigned b = (n + hm) >> hb;                 // ceil(n / a) <= a
-    unsigned x = i;
-    do {
-        unsigned l = x >> hb, r = x & hm;              // l in Z_b, r in Z_a
-#pragma unroll
-        for (int rd = 0; rd < 4; rd += 2) {
-            const unsigned f0 = __umulhi(mix32(r ^ (key + 0x9e3779b9U * (rd + 1))), b);
-            unsigned t = l + f0;                        // < 2b
-            t = t >= b ? t - b : t;
-            l = r;                                      // (l, r) now in Z_a x Z_b
-            r = t;
-            const unsigned f1 = mix32(r ^ (key + 0x9e3779b9U * (rd + 2))) & hm;
-            t = (l + f1) & hm;
-            l = r;                                      // back in Z_b x Z_a
-            r = t;
-        }
-        x = (l << hb) | r;
-    } while (x >= n);
-    return x;
-}
-
 __global__ void k_sel_from_feistel(unsigned char* __restrict__ bits, int H, int W,
                                    const int* __restrict__ support, const int* __restrict__ m0,
                                    long long support_img_stride, int B, unsigned seed,
                                    const int* __restrict__ counter, int* __restrict__ idx_out) {
     const int img = blockIdx.y;
+    trace(400);
     const unsigned key = mix32(seed ^ mix32((counter ? (unsigned)*counter : 0u) * 0x632be5abU + (unsigned)img));
     const int* sup = support + (long long)img * support_img_stride;
     const unsigned n = (unsigned)m0[img];
     unsigned char* bi = bits + (long long)img * W * (H / 2);
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < B; i += gridDim.x * blockDim.x) {
+        if ((unsigned)i >= n) break;                  // the cycle walk only terminates inside the domain [0, n)
         const int k = sup[feistel_perm((unsigned)i, n, key)];
         if (idx_out) idx_out[(long long)img * B + i] = k;
         set_sel_bits(bi, H, W, k);
     }
+    trace(409);
 }
 
 __global__ void k_sample_indices(int* __restrict__ idx_out, int n, int count, unsigned seed,
                                  const int* __restrict__ counter) {
     const unsigned key = mix32(seed ^ mix32((counter ? (unsigned)*counter : 0u) * 0x632be5abU));
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x)
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < count && i < n; i += gridDim.x * blockDim.x)
         idx_out[i] = (int)feistel_perm((unsigned)i, (unsigned)n, key);
 }
 

@@ -23,6 +23,29 @@ __device__ float2 g_tw[PNP_TW_N];
 
 namespace pnp {
 
+// ------------------------------------------------------------------ optional event trace (builds with -DPNP_TRACE)
+// thread 0 of a CTA records (%globaltimer, tag, blockIdx.x, %smid); read back with pnp_debug_read(1, ...).
+struct TraceEv { unsigned long long t; int tag; short cta; short sm; };
+#ifdef PNP_TRACE
+#define PNP_TRACE_MAX (1 << 20)
+__device__ TraceEv g_trace[PNP_TRACE_MAX];
+__device__ unsigned g_trace_n;
+__device__ __forceinline__ void trace(int tag) {
+    if (threadIdx.x == 0) {
+        const unsigned i = atomicAdd(&g_trace_n, 1u);
+        if (i < PNP_TRACE_MAX) {
+            unsigned long long t;
+            unsigned sm;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+            asm volatile("mov.u32 %0, %%smid;" : "=r"(sm));
+            g_trace[i] = TraceEv{t, tag, (short)blockIdx.x, (short)sm};
+        }
+    }
+}
+#else
+__device__ __forceinline__ void trace(int) {}
+#endif
+
 // ------------------------------------------------------------------ TMA bulk copy + mbarrier (sm_90+)
 // 1-D bulk copies global -> shared issued by ONE thread; completion is signalled on an mbarrier by
 // byte count (complete_tx), every consumer thread waits on the barrier's phase parity.

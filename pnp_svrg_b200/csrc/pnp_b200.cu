@@ -4,7 +4,10 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <map>
+#include <mutex>
 #include <thread>
+#include <tuple>
 #include <vector>
 
 #include "../../include/pnp_b200.h"
@@ -93,19 +96,53 @@ int launch_conv(float2* S, const float2* Bf, const float2* twn, int H, int batch
     return PNP_OK;
 }
 
-int g_num_sms = 148;
+int g_num_sms = 148;              // SM count of the device the calling thread last initialised / used
+int g_sms_of[64] = {0};
 
-template <class K>
-int persistent_ctas(K kernel, int threads, size_t smem, int items, int batch) {
-    static int per_sm = 0;                 // one static per kernel instantiation
-    if (per_sm == 0) {
-        int n = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, threads, smem) != cudaSuccess || n < 1) n = 1;
-        per_sm = n;
+int current_device() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = 0;
+    return dev;
+}
+int num_sms() {
+    const int n = g_sms_of[current_device()];
+    return n > 0 ? n : g_num_sms;
+}
+
+// resident CTAs of a persistent kernel: occupancy is cached per (kernel, threads, shared memory, device)
+int persistent_ctas(const void* kernel, int threads, size_t smem, int items, int batch) {
+    static std::mutex mu;
+    static std::map<std::tuple<const void*, int, size_t, int>, int> cache;
+    const int dev = current_device();
+    int per_sm = 0;
+    {
+        std::lock_guard<std::mutex> lock(mu);
+        const auto key = std::make_tuple(kernel, threads, smem, dev);
+        auto it = cache.find(key);
+        if (it == cache.end()) {
+            int n = 0;
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, threads, smem) != cudaSuccess || n < 1) n = 1;
+            it = cache.emplace(key, n).first;
+        }
+        per_sm = it->second;
     }
-    long long cap = (long long)g_num_sms * per_sm / (batch > 0 ? batch : 1);
+    long long cap = (long long)num_sms() * per_sm / (batch > 0 ? batch : 1);
     if (cap < 1) cap = 1;
     return (int)(items < cap ? items : cap);
+}
+
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per (kernel, device)
+int raise_smem_limit(const void* kernel, int bytes) {
+    static std::mutex mu;
+    static std::map<std::pair<const void*, int>, int> done;
+    const int dev = current_device();
+    std::lock_guard<std::mutex> lock(mu);
+    int& have = done[std::make_pair(kernel, dev)];
+    if (have < bytes) {
+        CU_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+        have = bytes;
+    }
+    return PNP_OK;
 }
 
 template <int L>
@@ -113,9 +150,16 @@ int launch_r2c(const pnp_csmri_grad_args& a, cudaStream_t st) {
     constexpr int GP = lines_gp<L>();
     const int pairs = a.W / 2;
     const int items = (pairs + GP - 1) / GP;
-    dim3 grid(persistent_ctas(pnp::k_lines_r2c<L, GP>, GP * pnp::fft_threads<L>(), lines_smem<L>(), items, a.batch), a.batch);
+    dim3 grid(persistent_ctas((const void*)pnp::k_lines_r2c<L, GP>, GP * pnp::fft_threads<L>(), lines_smem<L>(), items, a.batch), a.batch);
+    pnp::SelJob sj{};
+    if (a.sel_count > 0) {
+        sj.bits = const_cast<unsigned char*>(a.bits);
+        sj.idx = a.sel_idx; sj.idx_img_stride = a.sel_idx_img_stride; sj.cursor = a.sel_cursor;
+        sj.support = a.sel_support; sj.m0 = a.sel_m0; sj.support_img_stride = a.sel_support_img_stride;
+        sj.count = a.sel_count; sj.seed = a.sel_seed; sj.counter = a.sel_counter; sj.idx_out = nullptr;
+    }
     pnp::k_lines_r2c<L, GP><<<grid, GP * pnp::fft_threads<L>(), lines_smem<L>(), st>>>(
-        a.a, a.b, reinterpret_cast<float2*>(a.S), a.W, (long long)a.H * a.W);
+        a.a, a.b, reinterpret_cast<float2*>(a.S), a.W, (long long)a.H * a.W, sj);
     LAUNCH_CHECK();
     return PNP_OK;
 }
@@ -125,7 +169,11 @@ int launch_cols(const pnp_csmri_grad_args& a, cudaStream_t st) {
     constexpr int NC = cols_nc<L>();
     const int hp = a.H / 2;
     const int items = (hp - 1 + NC - 1) / NC;
-    dim3 grid(persistent_ctas(pnp::k_cols_mask<L, NC>, NC * pnp::fft_threads<L>(), cols_smem<L>(), items, a.batch), a.batch);
+    // item CTAs + one CTA per image for packed column 0 (items == 0 only for H = 2: not reachable, H >= 32)
+    // resident CTAs: one of them (CTA 0) owns packed column 0, the others loop over the items
+    int ctas = persistent_ctas((const void*)pnp::k_cols_mask<L, NC>, NC * pnp::fft_threads<L>(), cols_smem<L>(), items + 1, a.batch);
+    if (ctas < 2) ctas = 2;
+    dim3 grid(ctas, a.batch);
     pnp::k_cols_mask<L, NC><<<grid, NC * pnp::fft_threads<L>(), cols_smem<L>(), st>>>(
         reinterpret_cast<float2*>(a.S), a.bits, reinterpret_cast<const float2*>(a.Y1),
         reinterpret_cast<const float2*>(a.Y2), reinterpret_cast<const float2*>(a.Y1n),
@@ -143,11 +191,11 @@ int launch_c2r(const pnp_csmri_grad_args& a, cudaStream_t st) {
     pnp::GradEpilogue ep{a.gscale, a.gscale_ptr, a.step, a.step_ptr, a.g_out, a.vadd, a.v_out, a.z_in, a.z_out};
     const float inv_n = (float)(1.0 / ((double)a.H * (double)a.W));
     if (a.vadd && a.z_in && a.z_out && !a.g_out && !a.v_out) {          // the inner-iteration update
-        dim3 grid(persistent_ctas(pnp::k_lines_c2r<L, GP, true>, GP * pnp::fft_threads<L>(), lines_smem<L>(), items, a.batch), a.batch);
+        dim3 grid(persistent_ctas((const void*)pnp::k_lines_c2r<L, GP, true>, GP * pnp::fft_threads<L>(), lines_smem<L>(), items, a.batch), a.batch);
         pnp::k_lines_c2r<L, GP, true><<<grid, GP * pnp::fft_threads<L>(), lines_smem<L>(), st>>>(
             reinterpret_cast<const float2*>(a.S), a.W, (long long)a.H * a.W, inv_n, ep);
     } else {
-        dim3 grid(persistent_ctas(pnp::k_lines_c2r<L, GP, false>, GP * pnp::fft_threads<L>(), lines_smem<L>(), items, a.batch), a.batch);
+        dim3 grid(persistent_ctas((const void*)pnp::k_lines_c2r<L, GP, false>, GP * pnp::fft_threads<L>(), lines_smem<L>(), items, a.batch), a.batch);
         pnp::k_lines_c2r<L, GP, false><<<grid, GP * pnp::fft_threads<L>(), lines_smem<L>(), st>>>(
             reinterpret_cast<const float2*>(a.S), a.W, (long long)a.H * a.W, inv_n, ep);
     }
@@ -218,17 +266,13 @@ int launch_update_prox(const float* S, int W, float inv_n, float gscale, float s
                        const int* slot, int* adv, int n_adv, cudaStream_t st) {
     constexpr int GP = pnp::upd_gp<L>();
     const int npairs = W / 2;
-    int grid = g_num_sms < npairs ? g_num_sms : npairs;
+    int grid = num_sms() < npairs ? num_sms() : npairs;
     const int ppc = (npairs + grid - 1) / grid;
     grid = (npairs + ppc - 1) / ppc;
     const size_t smem = sizeof(float) * ((size_t)pnp::lines_stage_off<L, GP>() + (size_t)2 * ppc * L);
     // worth it only when the rounds are reasonably full and everything fits next to the exchange planes
     if (smem > 220 * 1024 || 2 * ppc < GP) return fail(PNP_ERR_UNSUPPORTED, "update+prox: image does not suit the resident-line kernel");
-    static bool attr = false;
-    if (!attr) {
-        CU_TRY(cudaFuncSetAttribute(pnp::k_update_prox<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-        attr = true;
-    }
+    { const int rc = raise_smem_limit((const void*)pnp::k_update_prox<L>, 220 * 1024); if (rc != PNP_OK) return rc; }
     int nl = W, p = ppc;
     void* args[] = {(void*)&S, (void*)&nl, (void*)&inv_n, (void*)&gscale, (void*)&step, (void*)&step_ptr, (void*)&vadd, (void*)&z_in,
                     (void*)&z_out, (void*)&xrec, (void*)&p, (void*)&sm, (void*)&fb, (void*)&sig_log, (void*)&mse_log, (void*)&slot,
@@ -286,17 +330,13 @@ template <int L>
 int launch_prox_fused(const float* zin, float* zout, const float* xrec, int W, int batch, float sm, float fb, double* sig_log,
                       double* mse_log, const int* slot, cudaStream_t st) {
     const long long total = (long long)W * batch;
-    int grid = g_num_sms;
+    int grid = num_sms();
     if (total < grid) grid = (int)total;
     int lpc = (int)((total + grid - 1) / grid);
     grid = (int)((total + lpc - 1) / lpc);
     const size_t smem = (size_t)lpc * L * sizeof(float);
-    if (smem > 200 * 1024) return fail(PNP_ERR_UNSUPPORTED, "fused prox: %zu bytes of lines per CTA do not fit shared memory", smem);
-    static size_t attr = 0;
-    if (smem > attr) {
-        CU_TRY(cudaFuncSetAttribute(pnp::k_prox_wavelet_fused<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        attr = 200 * 1024;
-    }
+    if (smem > 176 * 1024) return fail(PNP_ERR_UNSUPPORTED, "fused prox: %zu bytes of lines per CTA do not fit shared memory", smem);
+    { const int rc = raise_smem_limit((const void*)pnp::k_prox_wavelet_fused<L>, 176 * 1024); if (rc != PNP_OK) return rc; }
     int nl = W;
     void* args[] = {(void*)&zin, (void*)&zout, (void*)&xrec, (void*)&nl, (void*)&batch, (void*)&lpc, (void*)&sm, (void*)&fb,
                     (void*)&sig_log, (void*)&mse_log, (void*)&slot};
@@ -320,6 +360,7 @@ int pnp_init(void) {
     if (dev < 0 || dev >= 64) return fail(PNP_ERR_ARG, "device index %d out of range", dev);
     if (g_init[dev]) return PNP_OK;
     CU_TRY(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
+    g_sms_of[dev] = g_num_sms;
     std::vector<float2> tw(PNP_TW_N);
     for (int m = 0; m < PNP_TW_N; ++m) {
         const double ang = -2.0 * M_PI * (double)m / (double)PNP_TW_N;
@@ -364,10 +405,19 @@ int pnp_csmri_grad(const pnp_csmri_grad_args* args, void* stream) {
         (a.Y1 == nullptr) != (a.Y2n == nullptr))
         return fail(PNP_ERR_ARG, "Y1, Y2, Y1n, Y2n must be all null or all non-null");
     if ((a.z_out != nullptr) && !a.z_in) return fail(PNP_ERR_ARG, "z_out needs z_in");
+    const int ph = a.phases ? a.phases : 7;
+    if (a.sel_count < 0) return fail(PNP_ERR_ARG, "sel_count < 0");
+    if (a.sel_count > 0) {
+        if (!(ph & 1)) return fail(PNP_ERR_ARG, "in-pass selection needs pass 1 (phases bit0)");
+        if (!a.sel_idx && (!a.sel_support || !a.sel_m0)) return fail(PNP_ERR_ARG, "in-pass selection needs sel_idx or sel_support + sel_m0");
+        // the sampler's cycle walk only terminates inside [0, m0): refuse oversize minibatches on the host
+        // (the reference: problems/CSMRI.py:68-69 prints a warning and np.random.choice raises ValueError)
+        if (!a.sel_idx && a.sel_count > a.sel_min_m0)
+            return fail(PNP_ERR_ARG, "minibatch of %d exceeds the %d sampled positions", a.sel_count, a.sel_min_m0);
+    }
     int rc = check_init();
     if (rc != PNP_OK) return rc;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    const int ph = a.phases ? a.phases : 7;
     if ((ph & 1) && (rc = dispatch_r2c(a.H, a, st)) != PNP_OK) return rc;
     if ((ph & 2) && (rc = dispatch_cols(a.W, a, st)) != PNP_OK) return rc;
     if (ph & 4) return dispatch_c2r(a.H, a, st);
@@ -462,7 +512,7 @@ int pnp_advance(int* counters, int n, void* stream) {
 }
 
 int pnp_advance_scale(int* counters, int n, float* x, float factor, void* stream) {
-    if (!counters || n < 1 || n > 32) return fail(PNP_ERR_ARG, "bad argument");
+    if (!counters || n < 0 || n > 32) return fail(PNP_ERR_ARG, "bad argument");
     pnp::k_advance<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(counters, n, x, factor);
     LAUNCH_CHECK();
     return PNP_OK;
@@ -701,11 +751,7 @@ int pnp_tv_chambolle(const float* z_in, float* z_out, int H, int W, int batch, f
     if (!z_in || !z_out || !work || H < 1 || W < 1 || batch < 1 || n_iter < 1) return fail(PNP_ERR_ARG, "bad argument");
     if (z_in == z_out) return fail(PNP_ERR_ARG, "z_out must not alias z_in");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    static bool attr = false;
-    if (!attr) {
-        CU_TRY(cudaFuncSetAttribute(pnp::k_tv_chambolle, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TV_SMEM_BYTES));
-        attr = true;
-    }
+    { const int rc = raise_smem_limit((const void*)pnp::k_tv_chambolle, (int)TV_SMEM_BYTES); if (rc != PNP_OK) return rc; }
     // device layout: W lines of H samples; the operator is symmetric under transposition
     const int nl = W, np = H;
     const long long n = (long long)nl * np;
@@ -781,12 +827,9 @@ int cnn_forward_tc(const pnp_cnn_net* net, const float* img, float* out, int PH,
         if (!net->w_tc[l]) return fail(PNP_ERR_ARG, "w_tc[%d] missing: the net was not packed for the tensor-core path", l);
         if (l < L - 1 && !(net->slope[l] <= 1.f)) return fail(PNP_ERR_UNSUPPORTED, "activation slope %g > 1 on the tensor-core path", net->slope[l]);
     }
-    static bool attr_set = false;
-    if (!attr_set) {
-        CU_TRY(cudaFuncSetAttribute(pnp::k_conv_tc<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pnp::tc_smem<64>()));
-        CU_TRY(cudaFuncSetAttribute(pnp::k_conv_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pnp::tc_smem<1>()));
-        attr_set = true;
-    }
+    int rc;
+    if ((rc = raise_smem_limit((const void*)pnp::k_conv_tc<64>, (int)pnp::tc_smem<64>())) != PNP_OK) return rc;
+    if ((rc = raise_smem_limit((const void*)pnp::k_conv_tc<1>, (int)pnp::tc_smem<1>())) != PNP_OK) return rc;
     pnp::CnnIo io{net->mode, stats, net->range, net->shift_in};
     if (net->mode == 0) {
         pnp::k_minmax_init<<<1, 32, 0, st>>>(stats);
@@ -800,17 +843,12 @@ int cnn_forward_tc(const pnp_cnn_net* net, const float* img, float* out, int PH,
         pnp::CnnAct{net->scale[0], net->shift[0], net->slope[0]}, io, PH, PW);
     LAUNCH_CHECK();
     const int n_tiles = (int)((S + TC_OUT_PER_TILE - 1) / TC_OUT_PER_TILE);
-    const int grid = n_tiles < g_num_sms ? n_tiles : g_num_sms;
-    int rc;
+    const int grid = n_tiles < num_sms() ? n_tiles : num_sms();
     CUtensorMap tmA, tmB, tmO;
     // small images: all middle layers in one cooperative launch (a layer would be a few tiles per SM inside a ~10 us launch)
-    const bool stack = g_tc_dbg != 32 && L - 2 >= 2 && L - 2 <= TC_MAX_LAYERS && n_tiles <= 8 * g_num_sms;
+    const bool stack = g_tc_dbg != 32 && L - 2 >= 2 && L - 2 <= TC_MAX_LAYERS && n_tiles <= 8 * num_sms();
     if (stack) {
-        static bool stack_attr = false;
-        if (!stack_attr) {
-            CU_TRY(cudaFuncSetAttribute(pnp::k_conv_tc_stack, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pnp::tc_smem<64>()));
-            stack_attr = true;
-        }
+        if ((rc = raise_smem_limit((const void*)pnp::k_conv_tc_stack, (int)pnp::tc_smem<64>())) != PNP_OK) return rc;
         pnp::TcStack pm{};
         pm.n_layers = L - 2;
         if ((rc = make_tmap_bf16_2d(&pm.a[0], cur, 64, (unsigned long long)S, 64, TC_Q_ROWS)) != PNP_OK) return rc;
@@ -889,6 +927,24 @@ int pnp_debug_set(int key, int value) {
                      (t[1] - t[0]) * 1e-3, (t[2] - t[1]) * 1e-3, (t[3] - t[2]) * 1e-3, (t[4] - t[3]) * 1e-3);
     }
     return PNP_OK;
+}
+
+int pnp_debug_read(int key, void* out_host, long long bytes) {
+    if (key != 1 || !out_host || bytes < 16) return fail(PNP_ERR_ARG, "bad argument");
+#ifdef PNP_TRACE
+    unsigned n = 0;
+    CU_TRY(cudaDeviceSynchronize());
+    CU_TRY(cudaMemcpyFromSymbol(&n, pnp::g_trace_n, sizeof(n)));
+    if (n > PNP_TRACE_MAX) n = PNP_TRACE_MAX;
+    const long long cap = bytes / (long long)sizeof(pnp::TraceEv);
+    if ((long long)n > cap) n = (unsigned)cap;
+    if (n) CU_TRY(cudaMemcpyFromSymbol(out_host, pnp::g_trace, sizeof(pnp::TraceEv) * (size_t)n));
+    const unsigned zero = 0;
+    CU_TRY(cudaMemcpyToSymbol(pnp::g_trace_n, &zero, sizeof(zero)));
+    return (int)n;
+#else
+    return fail(PNP_ERR_UNSUPPORTED, "library built without -DPNP_TRACE");
+#endif
 }
 
 int pnp_graph_begin(void* stream) {

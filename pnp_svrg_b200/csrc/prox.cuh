@@ -28,10 +28,18 @@ __device__ __forceinline__ double* slot_ptr(double* base, const int* slot, int b
 }
 
 // Warp-collective sigma estimate of ONE line x[0..L) (global or shared memory): db2 detail
-// coefficients with half-sample symmetric extension, exact median of |d| over d != 0 by a 31-step
-// bit search on the float bit patterns (values stay in registers), / Phi^-1(0.75).
+// coefficients with half-sample symmetric extension, exact median of |d| over d != 0, / Phi^-1(0.75).
+// The keys (float bit patterns of |d|, monotone in the value) stay in registers.  Selection: ONE pass builds a
+// 256-bin histogram over the keys' own range [min, max] (bins = 2^s consecutive bit patterns, i.e. spaced like the
+// exponent: ~21 bins per octave, so the bin that holds the median has ~1-2 % of the keys), a warp scan finds the
+// bin of rank k1, the <= 32 keys of that bin are gathered and ranked directly.  If a bin holds more than 32 keys
+// the bit search continues inside it (exact for any input; the 31-step search from the top bit that this replaces
+// was 2/3 of the instructions of the estimate).
+#define PNP_SIG_SCRATCH 320          // 32-bit words of shared scratch per warp: 256 bins + 32 candidates (+ pad)
+// per-warp scratch (32-bit words) of the fused prox kernels: sigma selection, then Haar transposition (L/4 padded floats)
+template <int L> __host__ __device__ constexpr int prox_scratch() { return L >= 2048 && L <= 2048 ? 640 : PNP_SIG_SCRATCH; }
 template <int L>
-__device__ __forceinline__ double line_sigma_mad(const float* __restrict__ x, int lane, unsigned* scratch /* 32 words per warp, shared */) {
+__device__ __forceinline__ double line_sigma_mad(const float* __restrict__ x, int lane, unsigned* scratch /* PNP_SIG_SCRATCH words per warp, shared */) {
     constexpr int NO = (L + 3) / 2;            // db2 detail coefficients per line
     constexpr int PER = (NO + 31) / 32;
     // pywt dec_hi of db2; out[o] = sum_j h[j] * x_ext[2o + 1 - j]
@@ -39,6 +47,7 @@ __device__ __forceinline__ double line_sigma_mad(const float* __restrict__ x, in
                 h2 = -0.22414386804185735f, h3 = -0.12940952255092145f;
     unsigned a[PER];
     int nnz = 0;
+    unsigned mn = 0xffffffffu, mx = 0u;
 #pragma unroll
     for (int i = 0; i < PER; ++i) {
         const int o = lane + 32 * i;
@@ -58,17 +67,62 @@ __device__ __forceinline__ double line_sigma_mad(const float* __restrict__ x, in
                 i3 = i3 < 0 ? -1 - i3 : (i3 >= L ? 2 * L - 1 - i3 : i3);
                 d = fmaf(h0, x[i0], fmaf(h1, x[i1], fmaf(h2, x[i2], h3 * x[i3])));
             }
-            if (d != 0.f) { a[i] = __float_as_uint(fabsf(d)); ++nnz; }
+            if (d != 0.f) {
+                a[i] = __float_as_uint(fabsf(d));
+                ++nnz;
+                mn = min(mn, a[i]);
+                mx = max(mx, a[i]);
+            }
         }
     }
     nnz = warp_sum_i(nnz);
     if (nnz == 0) return __longlong_as_double(0x7ff8000000000000LL);      // median of nothing = NaN
     const int k1 = (nnz - 1) >> 1, k2 = nnz >> 1;
-    // Bit search for the k1-th smallest key, tracking how many keys still share the decided prefix
-    // (c_hi - c_lo).  Once at most 32 remain they are gathered, one per lane, and ranked directly.
-    unsigned res = 0;
-    int c_lo = 0, c_hi = nnz;                   // #keys < res  and  #keys < res + 2^(bit+1)  (sentinels excluded)
-    int bit = 30;
+    mn = __reduce_min_sync(0xffffffffu, mn);
+    mx = __reduce_max_sync(0xffffffffu, mx);
+    // state of the search: #keys < res is c_lo, #keys < res + 2^(bit+1) is c_hi, the k1-th smallest key lies in between
+    unsigned res;
+    int c_lo, c_hi, bit;
+    {
+        const int dbits = 32 - __clz(mx ^ mn);           // the keys agree above bit dbits (0 when all are equal)
+        const int s = dbits > 8 ? dbits - 8 : 0;         // (mx >> s) - (mn >> s) < 256
+        const unsigned bin0 = mn >> s;
+        unsigned* hist = scratch;
+        reinterpret_cast<uint4*>(hist)[lane] = make_uint4(0u, 0u, 0u, 0u);
+        reinterpret_cast<uint4*>(hist)[lane + 32] = make_uint4(0u, 0u, 0u, 0u);
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < PER; ++i)
+            if (a[i] != 0xffffffffu) atomicAdd(&hist[(a[i] >> s) - bin0], 1u);
+        __syncwarp();
+        // lane owns bins 8*lane .. 8*lane + 7
+        const uint4 ha = reinterpret_cast<const uint4*>(hist)[2 * lane], hb = reinterpret_cast<const uint4*>(hist)[2 * lane + 1];
+        const int hh[8] = {(int)ha.x, (int)ha.y, (int)ha.z, (int)ha.w, (int)hb.x, (int)hb.y, (int)hb.z, (int)hb.w};
+        const int part = hh[0] + hh[1] + hh[2] + hh[3] + hh[4] + hh[5] + hh[6] + hh[7];
+        int incl = part;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += v;
+        }
+        int below = incl - part;
+        const unsigned hit = __ballot_sync(0xffffffffu, below <= k1 && k1 < incl);
+        const int src = __ffs(hit) - 1;
+        int b = 0, cnt = 0, found = 0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            if (!found && below + hh[j] > k1) { b = 8 * lane + j; cnt = hh[j]; found = 1; }
+            if (!found) below += hh[j];
+        }
+        b = __shfl_sync(0xffffffffu, b, src);
+        cnt = __shfl_sync(0xffffffffu, cnt, src);
+        below = __shfl_sync(0xffffffffu, below, src);
+        __syncwarp();                           // the histogram is dead: its words are reused for the candidates below
+        res = (bin0 + (unsigned)b) << s;
+        c_lo = below;
+        c_hi = below + cnt;
+        bit = s - 1;
+    }
     for (; bit >= 0 && c_hi - c_lo > 32; --bit) {
         const unsigned cand = res | (1u << bit);
         int c = 0;
@@ -82,17 +136,20 @@ __device__ __forceinline__ double line_sigma_mad(const float* __restrict__ x, in
         v1 = res;                               // every bit decided
     } else {
         // candidates: keys in [res, res + 2^(bit+1)); exactly c_hi - c_lo <= 32 of them
-        const unsigned hi = res + (2u << bit);  // bit <= 29 here, no overflow
+        const unsigned width = 2u << bit;       // bit <= 29 here, no overflow; sentinels are >= 2^31 away from res
+        unsigned* cand_buf = scratch + 256;
         int base = 0;
 #pragma unroll
         for (int i = 0; i < PER; ++i) {
-            const bool in = a[i] >= res && a[i] < hi;
+            const bool in = (a[i] - res) < width;
             const unsigned m = __ballot_sync(0xffffffffu, in);
-            if (in) scratch[base + __popc(m & ((1u << lane) - 1u))] = a[i];
-            base += __popc(m);
+            if (m) {
+                if (in) cand_buf[base + __popc(m & ((1u << lane) - 1u))] = a[i];
+                base += __popc(m);
+            }
         }
         __syncwarp();
-        const unsigned mine = lane < base ? scratch[lane] : 0xffffffffu;
+        const unsigned mine = lane < base ? cand_buf[lane] : 0xffffffffu;
         __syncwarp();
         // rank of every candidate among the candidates (ties broken by lane)
         int rnk = 0;
@@ -108,12 +165,12 @@ __device__ __forceinline__ double line_sigma_mad(const float* __restrict__ x, in
     unsigned v2 = v1;
     if (k2 != k1) {
         int c = 0;
-        unsigned mn = 0xffffffffu;
+        unsigned mnv = 0xffffffffu;
 #pragma unroll
-        for (int i = 0; i < PER; ++i) { c += a[i] <= v1; if (a[i] > v1) mn = min(mn, a[i]); }
+        for (int i = 0; i < PER; ++i) { c += a[i] <= v1; if (a[i] > v1) mnv = min(mnv, a[i]); }
         c = warp_sum_i(c);
-        mn = __reduce_min_sync(0xffffffffu, mn);
-        if (c < k2 + 1) v2 = mn;
+        mnv = __reduce_min_sync(0xffffffffu, mnv);
+        if (c < k2 + 1) v2 = mnv;
     }
     return 0.5 * ((double)__uint_as_float(v1) + (double)__uint_as_float(v2)) / 0.6744897501960817;
 }
@@ -122,7 +179,7 @@ template <int L>
 __global__ void __launch_bounds__(128)
 k_sigma_mad(const float* __restrict__ z, int nlines, long long img_stride, double* __restrict__ sig_log,
             const int* __restrict__ slot, int batch) {
-    __shared__ unsigned scratch[4][32];
+    __shared__ __align__(16) unsigned scratch[4][PNP_SIG_SCRATCH];
     const int lane = threadIdx.x & 31;
     const int line = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int img = blockIdx.y;
@@ -382,11 +439,11 @@ __device__ __forceinline__ void haar_sub_forward(float (&x)[HaarSub<L>::VPL], fl
 
 // ---- the two phases of the fused prox on lines resident in shared memory (16 warps, one warp per line) ----
 template <int L>
-__device__ __forceinline__ void prox_phase_sigma(const float* lines, int mine, long long first, int nlines, int batch,
-                                                 double* __restrict__ sig_log, int cur_slot, unsigned (*scratch)[32]) {
+__device__ __noinline__ void prox_phase_sigma(const float* lines, int mine, long long first, int nlines, int batch,
+                                                 double* __restrict__ sig_log, int cur_slot, unsigned* scratch /* 16 x prox_scratch<L>() words */) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int l = warp; l < mine; l += 16) {
-        const double sig = line_sigma_mad<L>(lines + (long long)l * L, lane, scratch[warp]);
+        const double sig = line_sigma_mad<L>(lines + (long long)l * L, lane, scratch + warp * prox_scratch<L>());
         const int img = (int)((first + l) / nlines);
         if (lane == 0) atomicAdd(sig_log + (long long)cur_slot * batch + img, sig);
     }
@@ -484,8 +541,161 @@ __device__ __forceinline__ void haar_cc_inverse(float (&x)[NCH][4], float (&A)[N
 // warp per line, a single pass.
 #define PROX_MAX_TASKS 112          // sub-blocks per CTA: 200 KiB of lines / 2 KiB
 
+// ---- one warp per line for 512 .. 2048 samples ------------------------------------------------------------------
+// The lane holds NCH = L/128 float4 chunks in the chunk-cyclic layout (conflict-free shared-memory rows, coalesced
+// global rows).  Levels 1-2 stay inside a chunk.  The L/4 level-2 approximations are then TRANSPOSED through the
+// line's own shared memory (free once the samples sit in registers) so that every lane owns NCH consecutive ones:
+// log2(NCH) more levels run inside the lane on a single chain, and only the last two levels are butterflies between
+// lanes.  All per-level energies of the line live in one warp, so the thresholds need no second pass over the data
+// and no cross-warp exchange: the sub-block version this replaces ran 4x the instructions (5 shuffle levels on four
+// chains per 512 samples, the forward transform twice).
+template <int L> struct HaarWL {
+    static constexpr int NCH = L / 128;                                   // float4 chunks per lane: 4, 8, 16
+    static constexpr int LG = NCH == 4 ? 2 : (NCH == 8 ? 3 : 4);          // in-lane levels after the transposition
+    static constexpr int LEVELS = HaarCfg<L>::LEVELS;                     // = 2 + LG + 2
+};
+// index of approximation f in the transposition scratch: 4 pad floats per 16 keep the 16-byte block reads of a
+// quarter warp on distinct banks
+__device__ __forceinline__ int haar_wl_pad(int f) { return f + ((f >> 4) << 2); }
+
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// What a warp keeps in REGISTERS across the grid barrier of the fused prox: the forward Haar pyramid of its line
+// (details only: the transform does not need sigma), and the per-level energies (lane k holds level k).
+template <int L> struct ProxLine {
+    static constexpr int NCH = HaarWL<L>::NCH;
+    float x[NCH][4];            // [c][1], [c][3]: level-1 details, [c][2]: level-2 detail of chunk c
+    float v[NCH];               // in-lane pyramid over the lane's NCH level-2 approximations (v[0]: superseded by A)
+    float A[3], Dx[2];          // the two cross-lane levels
+    float level_ss;             // lane k < LEVELS: sum of squares of the level-(k+1) details of the line
+};
+
+// forward pyramid of the line at `sl` (shared memory; it becomes scratch)
 template <int L>
-__device__ __forceinline__ void prox_phase_shrink(const float* lines, int mine, long long first, int nlines, int batch,
+__device__ __forceinline__ void prox_line_forward(float* sl, int lane, ProxLine<L>& st) {
+    using W = HaarWL<L>;
+    constexpr int NCH = W::NCH, LG = W::LG, LEVELS = W::LEVELS;
+    constexpr float RS2 = 0.70710678118654752f;
+    static_assert(LEVELS == LG + 4, "level split of the one-warp-per-line shrink");
+    const float4* s4 = reinterpret_cast<const float4*>(sl);
+    float ss[LEVELS];
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+        const float4 q = s4[c * 32 + lane];
+        st.x[c][0] = q.x; st.x[c][1] = q.y; st.x[c][2] = q.z; st.x[c][3] = q.w;
+    }
+#pragma unroll
+    for (int k = 0; k < LEVELS; ++k) ss[k] = 0.f;
+    __syncwarp();                      // every lane holds its samples: the line's shared memory is scratch now
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {    // levels 1, 2; details stay where the inverse expects them
+        const float a0 = (st.x[c][0] + st.x[c][1]) * RS2, d0 = (st.x[c][0] - st.x[c][1]) * RS2;
+        const float a1 = (st.x[c][2] + st.x[c][3]) * RS2, d1 = (st.x[c][2] - st.x[c][3]) * RS2;
+        ss[0] = fmaf(d0, d0, fmaf(d1, d1, ss[0]));
+        const float dd = (a0 - a1) * RS2;
+        ss[1] = fmaf(dd, dd, ss[1]);
+        st.x[c][1] = d0; st.x[c][3] = d1; st.x[c][2] = dd;
+        sl[haar_wl_pad(c * 32 + lane)] = (a0 + a1) * RS2;
+    }
+    __syncwarp();
+    {
+        const float4* b4 = reinterpret_cast<const float4*>(sl + haar_wl_pad(lane * NCH));
+#pragma unroll
+        for (int j = 0; j < NCH / 4; ++j) {
+            const float4 q = b4[j];
+            st.v[4 * j] = q.x; st.v[4 * j + 1] = q.y; st.v[4 * j + 2] = q.z; st.v[4 * j + 3] = q.w;
+        }
+    }
+#pragma unroll
+    for (int lv = 1; lv <= LG; ++lv) {
+        const int stride = 1 << lv, half = stride >> 1;
+#pragma unroll
+        for (int i = 0; i < NCH / stride; ++i) {
+            const float p = st.v[i * stride], q = st.v[i * stride + half];
+            const float d = (p - q) * RS2;
+            st.v[i * stride] = (p + q) * RS2;
+            st.v[i * stride + half] = d;
+            ss[1 + lv] = fmaf(d, d, ss[1 + lv]);
+        }
+    }
+    st.A[0] = st.v[0];
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+        const float p = __shfl_xor_sync(0xffffffffu, st.A[q], 1 << q);
+        const bool ev = (lane & (1 << q)) == 0;
+        st.A[q + 1] = (st.A[q] + p) * RS2;
+        st.Dx[q] = (ev ? (st.A[q] - p) : (p - st.A[q])) * RS2;
+        if ((lane & ((2 << q) - 1)) == 0) ss[2 + LG + q] = st.Dx[q] * st.Dx[q];
+    }
+    float mine_ss = 0.f;
+#pragma unroll
+    for (int k = 0; k < LEVELS; ++k) {
+        const float e = warp_sum_f(ss[k]);
+        mine_ss = lane == k ? e : mine_ss;
+    }
+    st.level_ss = mine_ss;
+}
+
+// thresholds from the energies, shrink, inverse pyramid, store; returns the lane's part of sum((out - xrec)^2).
+// `tscr`: prox_scratch<L>() floats of shared scratch of this warp; `xr4`: ground truth of the line (shared or global).
+template <int L>
+__device__ __forceinline__ float prox_line_inverse(ProxLine<L>& st, float* tscr, int lane, float var, float4* zo4, const float4* xr4) {
+    using W = HaarWL<L>;
+    constexpr int NCH = W::NCH, LG = W::LG, LEVELS = W::LEVELS;
+    constexpr float RS2 = 0.70710678118654752f;
+    float thr[LEVELS];
+    {   // lane k computes the threshold of level k, then it is broadcast
+        const int k = lane < LEVELS ? lane : LEVELS - 1;
+        const float dvar = st.level_ss / (float)(L >> (k + 1));
+        const float tk = var / sqrtf(fmaxf(dvar - var, 2.220446049250313e-16f));
+#pragma unroll
+        for (int kk = 0; kk < LEVELS; ++kk) thr[kk] = __shfl_sync(0xffffffffu, tk, kk);
+    }
+#pragma unroll
+    for (int q = 1; q >= 0; --q) {
+        const float d = soft_shrink(st.Dx[q], thr[2 + LG + q]);
+        const bool ev = (lane & (1 << q)) == 0;
+        st.A[q] = (ev ? (st.A[q + 1] + d) : (st.A[q + 1] - d)) * RS2;
+    }
+    st.v[0] = st.A[0];
+#pragma unroll
+    for (int lv = LG; lv >= 1; --lv) {
+        const int stride = 1 << lv, half = stride >> 1;
+#pragma unroll
+        for (int i = 0; i < NCH / stride; ++i) {
+            const float a = st.v[i * stride];
+            const float d = soft_shrink(st.v[i * stride + half], thr[1 + lv]);
+            st.v[i * stride] = (a + d) * RS2;
+            st.v[i * stride + half] = (a - d) * RS2;
+        }
+    }
+    {   // back to the chunk-cyclic layout through the warp's scratch
+        float4* b4 = reinterpret_cast<float4*>(tscr + haar_wl_pad(lane * NCH));
+#pragma unroll
+        for (int j = 0; j < NCH / 4; ++j) b4[j] = make_float4(st.v[4 * j], st.v[4 * j + 1], st.v[4 * j + 2], st.v[4 * j + 3]);
+    }
+    __syncwarp();
+    float err = 0.f;
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+        const float aa = tscr[haar_wl_pad(c * 32 + lane)];
+        const float dd = soft_shrink(st.x[c][2], thr[1]);
+        const float a0 = (aa + dd) * RS2, a1 = (aa - dd) * RS2;
+        const float d0 = soft_shrink(st.x[c][1], thr[0]), d1 = soft_shrink(st.x[c][3], thr[0]);
+        const float4 o = make_float4((a0 + d0) * RS2, (a0 - d0) * RS2, (a1 + d1) * RS2, (a1 - d1) * RS2);
+        zo4[c * 32 + lane] = o;
+        if (xr4) {
+            const float4 r = xr4[c * 32 + lane];
+            const float e0 = o.x - r.x, e1 = o.y - r.y, e2 = o.z - r.z, e3 = o.w - r.w;
+            err = fmaf(e0, e0, fmaf(e1, e1, fmaf(e2, e2, fmaf(e3, e3, err))));
+        }
+    }
+    __syncwarp();                      // the scratch may be rewritten by the caller's next line
+    return err;
+}
+
+template <int L>
+__device__ __noinline__ void prox_phase_shrink(float* lines, int mine, long long first, int nlines, int batch,
                                                   float* __restrict__ zout, const float* __restrict__ xrec,
                                                   float sigma_modifier, float fallback_sigma, const double* sig_log,
                                                   double* __restrict__ mse_log, int cur_slot) {
@@ -510,7 +720,140 @@ __device__ __forceinline__ void prox_phase_shrink(const float* lines, int mine, 
         const float sigma = (se > 0.0) ? (float)(se * (double)sigma_modifier) : fallback_sigma;
         return sigma * sigma;
     };
-    if constexpr (SB == 512) {
+    if constexpr (L >= 512 && L <= 2048) {
+        using W = HaarWL<L>;
+        constexpr int NCH = W::NCH, LG = W::LG;
+        static_assert(LEVELS == LG + 4, "level split of the one-warp-per-line shrink");
+        for (int l = warp; l < mine; l += 16) {
+            const long long gl = first + l;
+            const int img = (int)(gl / nlines);
+            float* sl = lines + (long long)l * L;
+            const float4* s4 = reinterpret_cast<const float4*>(sl);
+            const float4* xr4 = xrec ? reinterpret_cast<const float4*>(xrec + gl * L) : nullptr;
+            float4* zo4 = reinterpret_cast<float4*>(zout + gl * L);
+            float x[NCH][4], ss[LEVELS], thr[LEVELS];
+#pragma unroll
+            for (int c = 0; c < NCH; ++c) {
+                const float4 q = s4[c * 32 + lane];
+                x[c][0] = q.x; x[c][1] = q.y; x[c][2] = q.z; x[c][3] = q.w;
+            }
+#pragma unroll
+            for (int k = 0; k < LEVELS; ++k) ss[k] = 0.f;
+            __syncwarp();                      // every lane holds its samples: the line's shared memory is scratch now
+#pragma unroll
+            for (int c = 0; c < NCH; ++c) {    // levels 1, 2; details stay where the inverse expects them
+                const float a0 = (x[c][0] + x[c][1]) * RS2, d0 = (x[c][0] - x[c][1]) * RS2;
+                const float a1 = (x[c][2] + x[c][3]) * RS2, d1 = (x[c][2] - x[c][3]) * RS2;
+                ss[0] = fmaf(d0, d0, fmaf(d1, d1, ss[0]));
+                const float dd = (a0 - a1) * RS2;
+                ss[1] = fmaf(dd, dd, ss[1]);
+                x[c][1] = d0; x[c][3] = d1; x[c][2] = dd;
+                sl[haar_wl_pad(c * 32 + lane)] = (a0 + a1) * RS2;
+            }
+            __syncwarp();
+            float v[NCH];                      // approximations lane * NCH .. lane * NCH + NCH - 1
+            {
+                const float4* b4 = reinterpret_cast<const float4*>(sl + haar_wl_pad(lane * NCH));
+#pragma unroll
+                for (int j = 0; j < NCH / 4; ++j) {
+                    const float4 q = b4[j];
+                    v[4 * j] = q.x; v[4 * j + 1] = q.y; v[4 * j + 2] = q.z; v[4 * j + 3] = q.w;
+                }
+            }
+            float4 xr[2];                      // ground truth of the first two chunks: in flight during the pyramid top
+            if (xrec) {
+#pragma unroll
+                for (int j = 0; j < 2; ++j) xr[j] = xr4[j * 32 + lane];
+            }
+#pragma unroll
+            for (int lv = 1; lv <= LG; ++lv) {
+                const int stride = 1 << lv, half = stride >> 1;
+#pragma unroll
+                for (int i = 0; i < NCH / stride; ++i) {
+                    const float p = v[i * stride], q = v[i * stride + half];
+                    const float d = (p - q) * RS2;
+                    v[i * stride] = (p + q) * RS2;
+                    v[i * stride + half] = d;
+                    ss[1 + lv] = fmaf(d, d, ss[1 + lv]);
+                }
+            }
+            float A[3], Dx[2];
+            A[0] = v[0];
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                const float p = __shfl_xor_sync(0xffffffffu, A[q], 1 << q);
+                const bool ev = (lane & (1 << q)) == 0;
+                A[q + 1] = (A[q] + p) * RS2;
+                Dx[q] = (ev ? (A[q] - p) : (p - A[q])) * RS2;
+                if ((lane & ((2 << q) - 1)) == 0) ss[2 + LG + q] = Dx[q] * Dx[q];
+            }
+            const float var = sigma_var(img);
+            {   // lane k computes the threshold of level k, then it is broadcast
+                float mine_ss = 0.f;
+#pragma unroll
+                for (int k = 0; k < LEVELS; ++k) {
+                    const float e = warp_sum_f(ss[k]);
+                    mine_ss = lane == k ? e : mine_ss;
+                }
+                const int k = lane < LEVELS ? lane : LEVELS - 1;
+                const float dvar = mine_ss / (float)(L >> (k + 1));
+                const float tk = var / sqrtf(fmaxf(dvar - var, 2.220446049250313e-16f));
+#pragma unroll
+                for (int kk = 0; kk < LEVELS; ++kk) thr[kk] = __shfl_sync(0xffffffffu, tk, kk);
+            }
+#pragma unroll
+            for (int q = 1; q >= 0; --q) {
+                const float d = soft_shrink(Dx[q], thr[2 + LG + q]);
+                const bool ev = (lane & (1 << q)) == 0;
+                A[q] = (ev ? (A[q + 1] + d) : (A[q + 1] - d)) * RS2;
+            }
+            v[0] = A[0];
+#pragma unroll
+            for (int lv = LG; lv >= 1; --lv) {
+                const int stride = 1 << lv, half = stride >> 1;
+#pragma unroll
+                for (int i = 0; i < NCH / stride; ++i) {
+                    const float a = v[i * stride];
+                    const float d = soft_shrink(v[i * stride + half], thr[1 + lv]);
+                    v[i * stride] = (a + d) * RS2;
+                    v[i * stride + half] = (a - d) * RS2;
+                }
+            }
+            {   // back to the chunk-cyclic layout (a lane rewrites the block only it has read)
+                float4* b4 = reinterpret_cast<float4*>(sl + haar_wl_pad(lane * NCH));
+#pragma unroll
+                for (int j = 0; j < NCH / 4; ++j) b4[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            }
+            __syncwarp();
+            flush_err(img);
+#pragma unroll
+            for (int g = 0; g < NCH / 2; ++g) {
+                float4 nx[2];
+                if (xrec && g + 1 < NCH / 2) {
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) nx[j] = xr4[((g + 1) * 2 + j) * 32 + lane];
+                }
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    const int c = g * 2 + j;
+                    const float aa = sl[haar_wl_pad(c * 32 + lane)];
+                    const float dd = soft_shrink(x[c][2], thr[1]);
+                    const float a0 = (aa + dd) * RS2, a1 = (aa - dd) * RS2;
+                    const float d0 = soft_shrink(x[c][1], thr[0]), d1 = soft_shrink(x[c][3], thr[0]);
+                    const float4 o = make_float4((a0 + d0) * RS2, (a0 - d0) * RS2, (a1 + d1) * RS2, (a1 - d1) * RS2);
+                    zo4[c * 32 + lane] = o;
+                    if (xrec) {
+                        const float e0 = o.x - xr[j].x, e1 = o.y - xr[j].y, e2 = o.z - xr[j].z, e3 = o.w - xr[j].w;
+                        err_acc = fmaf(e0, e0, fmaf(e1, e1, fmaf(e2, e2, fmaf(e3, e3, err_acc))));
+                    }
+                }
+                if (g + 1 < NCH / 2) {
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) xr[j] = nx[j];
+                }
+            }
+        }
+    } else if constexpr (SB == 512) {
         __shared__ float s_ss[PROX_MAX_TASKS][LEVELS];
         const int tasks = mine * NSB;
         for (int t = warp; t < tasks; t += 16) {                                   // pass A: energies
@@ -668,6 +1011,69 @@ __device__ __forceinline__ void prox_phase_shrink(const float* lines, int mine, 
     }
 }
 
+// Both fused kernels (k_prox_wavelet_fused, k_update_prox) end with this on lines resident in shared memory:
+//   sigma estimate per line -> [grid barrier: mean over all lines] -> BayesShrink -> store + squared error.
+// 512 .. 2048 samples with at most one line per warp: the warp also runs the FORWARD Haar pyramid before the barrier
+// and keeps it in registers (it does not depend on sigma), so the lines' shared memory is free during the barrier:
+// the ground-truth lines are pulled into it by TMA bulk copies meanwhile (one warp streaming them with plain loads
+// had ~1 KiB in flight and was bound by DRAM latency), and after the barrier only thresholds + inverse remain.
+// `scratch`: 16 x prox_scratch<L>() words; `xbar`: an initialised mbarrier (count 1, phase 0) not used otherwise.
+template <int L>
+__device__ __forceinline__ void prox_phases(float* lines, int mine, long long first, int nlines, int batch, float* __restrict__ zout,
+                                            const float* __restrict__ xrec, float sigma_modifier, float fallback_sigma,
+                                            double* __restrict__ sig_log, double* __restrict__ mse_log, int cur_slot,
+                                            unsigned* scratch, unsigned long long* xbar, int* __restrict__ advance, int n_advance) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if constexpr (L >= 512 && L <= 2048) {
+        if (mine <= 16) {
+            ProxLine<L> st;
+            const bool active = warp < mine;
+            const long long gl = first + warp;
+            const int img = active ? (int)(gl / nlines) : 0;
+            float* sl = lines + (long long)warp * L;
+            if (active) {
+                const double sig = line_sigma_mad<L>(sl, lane, scratch + warp * prox_scratch<L>());
+                if (lane == 0) atomicAdd(sig_log + (long long)cur_slot * batch + img, sig);
+                prox_line_forward<L>(sl, lane, st);
+            }
+            __syncthreads();
+            if (xrec && mine > 0 && threadIdx.x == 0) {
+                fence_proxy_async_smem();              // the lines were read / written through the generic proxy
+                const unsigned total = (unsigned)(mine * L * sizeof(float));
+                mbar_expect_tx(xbar, total);
+                for (unsigned off = 0; off < total; off += 32768u) {
+                    const unsigned n = total - off < 32768u ? total - off : 32768u;
+                    bulk_g2s(reinterpret_cast<char*>(lines) + off, reinterpret_cast<const char*>(xrec + first * L) + off, n, xbar);
+                }
+            }
+            __threadfence();
+            cooperative_groups::this_grid().sync();
+            if (advance && blockIdx.x == 0 && threadIdx.x < n_advance) advance[threadIdx.x] += 1;
+            if (active) {
+                const double se = __ldcg(sig_log + (long long)cur_slot * batch + img) / (double)nlines;
+                const float sigma = (se > 0.0) ? (float)(se * (double)sigma_modifier) : fallback_sigma;
+                if (xrec) mbar_wait(xbar, 0);
+                float err = prox_line_inverse<L>(st, reinterpret_cast<float*>(scratch + warp * prox_scratch<L>()), lane, sigma * sigma,
+                                                 reinterpret_cast<float4*>(zout + gl * L),
+                                                 xrec ? reinterpret_cast<const float4*>(sl) : nullptr);
+                if (xrec && mse_log) {
+                    err = warp_sum_f(err);
+                    if (lane == 0) atomicAdd(mse_log + (long long)cur_slot * batch + img, (double)err);
+                }
+            }
+            return;
+        }
+    }
+    prox_phase_sigma<L>(lines, mine, first, nlines, batch, sig_log, cur_slot, scratch);
+    __syncthreads();
+    __threadfence();
+    cooperative_groups::this_grid().sync();
+    // end-of-iteration counters (pnp_advance) folded in: every CTA has read *slot before the barrier above, and
+    // nothing else of this iteration reads them any more
+    if (advance && blockIdx.x == 0 && threadIdx.x < n_advance) advance[threadIdx.x] += 1;
+    prox_phase_shrink<L>(lines, mine, first, nlines, batch, zout, xrec, sigma_modifier, fallback_sigma, sig_log, mse_log, cur_slot);
+}
+
 template <int L>
 __global__ void __launch_bounds__(512, 1)
 k_prox_wavelet_fused(const float* __restrict__ zin, float* __restrict__ zout, const float* __restrict__ xrec,
@@ -677,9 +1083,8 @@ k_prox_wavelet_fused(const float* __restrict__ zin, float* __restrict__ zout, co
     constexpr int VPL = C::VPL, LEVELS = C::LEVELS, XL = C::XL, LIN = C::LIN, SB = C::SB, NSB = C::NSB;
     constexpr float RS2 = 0.70710678118654752f;
     extern __shared__ __align__(128) float lines[];                   // lines_per_cta x L
-    __shared__ __align__(8) unsigned long long bar;
-    __shared__ unsigned scratch[16][32];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    __shared__ __align__(8) unsigned long long bar, xbar;
+    __shared__ __align__(16) unsigned scratch[16 * prox_scratch<L>()];
     const long long total = (long long)nlines * batch;
     const long long first = (long long)blockIdx.x * lines_per_cta;
     long long mine = total - first;
@@ -689,6 +1094,7 @@ k_prox_wavelet_fused(const float* __restrict__ zin, float* __restrict__ zout, co
     // ---- stage my lines (contiguous in memory) ----
     if (threadIdx.x == 0) {
         mbar_init(&bar, 1);
+        mbar_init(&xbar, 1);
         mbar_fence_init();
         if (mine > 0) {
             // the CTA's lines are one contiguous block: a few large bulk copies instead of one per (short) line
@@ -703,12 +1109,9 @@ k_prox_wavelet_fused(const float* __restrict__ zin, float* __restrict__ zout, co
     __syncthreads();
     if (mine > 0) mbar_wait(&bar, 0);
 
-    // ---- phase 1: per-line sigma estimate (one warp per line) ----
-    prox_phase_sigma<L>(lines, (int)mine, first, nlines, batch, sig_log, cur_slot, scratch);
-    __threadfence();
-    cooperative_groups::this_grid().sync();
-    // ---- phase 2: BayesShrink of the resident lines ----
-    prox_phase_shrink<L>(lines, (int)mine, first, nlines, batch, zout, xrec, sigma_modifier, fallback_sigma, sig_log, mse_log, cur_slot);
+    // ---- sigma estimate, grid-wide mean, BayesShrink of the resident lines ----
+    prox_phases<L>(lines, (int)mine, first, nlines, batch, zout, xrec, sigma_modifier, fallback_sigma, sig_log, mse_log, cur_slot,
+                   scratch, &xbar, nullptr, 0);
 }
 
 }  // namespace pnp

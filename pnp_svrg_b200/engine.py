@@ -126,6 +126,10 @@ class Engine:
             raise ValueError("mb_source must be 'legacy', 'host', 'device' or 'stream'")
         if mb_source == 'stream' and mb_stream is None:
             raise ValueError("mb_source='stream' needs mb_stream (a sequence of index arrays)")
+        n_meas = getattr(problem, 'M0', None) if getattr(problem, 'pname', '') == 'csmri' else getattr(problem, 'M', None)
+        if self.B > 0 and mb_source in ('device', 'host') and n_meas is not None and self.B > int(n_meas):
+            # problems/problem.py:112-115: the reference warns and np.random.choice(replace=False) raises
+            raise ValueError('Cannot take a larger sample (%d) than the %d measurements' % (self.B, int(n_meas)))
         self.rng = np.random.default_rng(mb_seed) if mb_source == 'host' else None
         self.mb_seed = int(mb_seed)
         self.stream = torch.cuda.Stream(device=self.dev)
@@ -272,6 +276,15 @@ class Engine:
 
     def sample_sel_device(self):
         self.p._dev_sample_sel(self.sel, self.B, self.mb_seed, counter=self.draw_ptr, clear=False)
+
+    def sel_job(self):
+        """Descriptor of the current minibatch for problems whose gradient pass builds the selection itself
+        (CSMRI: ``_dev_grad(..., sel_job=)``, no separate selection launch); None otherwise."""
+        if self.B <= 0 or not getattr(self.p, '_inpass_sel', False):
+            return None
+        if self.mb_source == 'device':
+            return dict(count=self.B, idx=None, seed=self.mb_seed, counter=self.draw_ptr)
+        return dict(count=self.B, idx=self.idx_dev, cursor=None)
 
     # ------------------------------------------------------------------ prox + log
     def prox(self, z_in, z_out):

@@ -114,13 +114,32 @@ class CSMRI(Problem):
                                                           int(stride), D.ptr(cursor), int(bool(clear)), D.stream()))
 
     def _dev_sample_sel(self, sel, count, seed, counter=None, idx_out=None, clear=True):
+        if int(count) > self.M0:
+            # the reference prints a warning and np.random.choice raises (problems/CSMRI.py:68-72); the device
+            # sampler's cycle walk is only defined inside [0, M0)
+            raise ValueError('Cannot take a larger sample (%d) than the %d sampled k-space positions' % (count, self.M0))
         _lib.check(_lib.load().pnp_csmri_sel_sample(D.ptr(sel), self.H, self.W, 1, D.ptr(self._support),
                                                     D.ptr(self._m0_dev), 0, int(count), int(seed) & 0xffffffff,
                                                     D.ptr(counter), D.ptr(idx_out), int(bool(clear)), D.stream()))
 
+    _inpass_sel = True      # the forward line pass can build the minibatch selection itself (sel_job)
+
     def _dev_grad(self, a, b=None, sel=None, with_y=True, gscale=1.0, gscale_ptr=None, step=0.0, step_ptr=None,
-                  g_out=None, vadd=None, v_out=None, z_in=None, z_out=None, phases=0, clear_sel=False):
-        """g = Re(ifft2(sel o fft2(a - b) - Ysel)) * gscale ; v = g + vadd ; z_out = z_in - step*v."""
+                  g_out=None, vadd=None, v_out=None, z_in=None, z_out=None, phases=0, clear_sel=False, sel_job=None):
+        """g = Re(ifft2(sel o fft2(a - b) - Ysel)) * gscale ; v = g + vadd ; z_out = z_in - step*v.
+        ``sel_job`` = dict(count, idx | None, cursor, seed, counter): pass 1 also builds the minibatch selection in
+        ``sel`` (all zero on entry) -- from explicit positions ``idx`` or by the device sampler."""
+        sj = {}
+        if sel_job is not None:
+            if sel is None:
+                raise ValueError('sel_job needs the selection buffer it fills')
+            if sel_job.get('idx') is None and int(sel_job['count']) > self.M0:
+                raise ValueError('Cannot take a larger sample (%d) than the %d sampled k-space positions'
+                                 % (sel_job['count'], self.M0))
+            sj = dict(sel_count=int(sel_job['count']), sel_idx=D.ptr(sel_job.get('idx')), sel_idx_img_stride=0,
+                      sel_cursor=D.ptr(sel_job.get('cursor')), sel_support=D.ptr(self._support), sel_m0=D.ptr(self._m0_dev),
+                      sel_support_img_stride=0, sel_seed=int(sel_job.get('seed', 0)) & 0xffffffff,
+                      sel_counter=D.ptr(sel_job.get('counter')), sel_min_m0=int(self.M0))
         args = _lib.CsmriGradArgs(
             H=self.H, W=self.W, batch=1, a=D.ptr(a), b=D.ptr(b), S=D.ptr(self._S),
             bits=D.ptr(self._bits_full if sel is None else sel),
@@ -128,7 +147,7 @@ class CSMRI(Problem):
             Y1n=D.ptr(self._Y1n) if with_y else None, Y2n=D.ptr(self._Y2n) if with_y else None,
             gscale=float(gscale), gscale_ptr=D.ptr(gscale_ptr), step=float(step), step_ptr=D.ptr(step_ptr),
             g_out=D.ptr(g_out), vadd=D.ptr(vadd), v_out=D.ptr(v_out), z_in=D.ptr(z_in), z_out=D.ptr(z_out), phases=int(phases),
-            clear_bits=int(bool(clear_sel) and sel is not None))
+            clear_bits=int(bool(clear_sel) and sel is not None), **sj)
         _lib.check(_lib.load().pnp_csmri_grad(C.byref(args), D.stream()))
 
     def _dev_update_prox(self, gscale, step_ptr, vadd, z_in, z_out, sig_log, sigma_modifier, fallback_sigma, xrec, mse_log,

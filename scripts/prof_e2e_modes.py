@@ -9,8 +9,8 @@ from pnp_svrg_b200.denoisers import TVDenoiser
 
 ba = argparse.Namespace(size=2048, batch_size=0, sample_prob=0.3, eta=0.0, T2=10, gpus=1)
 cfg = bench.workload(ba)
-ep = bench.Epoch(cfg, seed=0)
-prob = ep.prob
+prob_, run_ = bench.make_run(cfg, seed=0)
+prob = prob_
 res = {}
 for fast in (False, True):
     for src in ('host', 'device'):

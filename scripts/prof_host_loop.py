@@ -13,7 +13,7 @@ from pnp_svrg_b200.denoisers import TVDenoiser
 iters = int(sys.argv[1]) if len(sys.argv) > 1 else 2000
 ba = argparse.Namespace(size=2048, batch_size=0, sample_prob=0.3, eta=0.0, T2=10, gpus=1)
 cfg = bench.workload(ba)
-prob = bench.Epoch(cfg, seed=0).prob
+prob = bench.make_run(cfg, seed=0)[0]
 kw = dict(eta=cfg['eta'], T2=10, mini_batch_size=cfg['mini_batch_size'], vr_mode='paper', verbose=False,
           converge_check=False, mb_seed=11, fast=True)
 res = {'iters': iters, 'cpus': os.cpu_count()}

@@ -1,4 +1,5 @@
-"""Profile target: a few eager PnP-SVRG inner iterations of the bench workload (for ncu)."""
+"""Profile target: a few eager PnP-SVRG inner iterations of the bench workload (for ncu): the launches of
+SvrgRun.fast_ops() -- line pass (+ in-pass minibatch selection), column pass, single-launch tail."""
 import os
 import sys
 
@@ -18,14 +19,15 @@ def main():
     a = ap.parse_args()
     ba = argparse.Namespace(size=a.size, batch_size=0, sample_prob=0.3, eta=0.0, T2=10, gpus=1)
     cfg = bench.workload(ba)
-    ep = bench.Epoch(cfg, seed=0)
-    eng = ep.eng
+    prob, run = bench.make_run(cfg, seed=0)
+    eng = run.eng
     with torch.cuda.stream(eng.stream):
-        ep.snapshot_ops()
+        eng.set_step(cfg['eta'])
+        run.snapshot()
         for _ in range(a.iters):
-            ep.inner_ops()
+            run.fast_ops()
     eng.stream.synchronize()
-    print('ok', eng.flush_fast() if False else '')
+    print('ok')
 
 
 if __name__ == '__main__':
