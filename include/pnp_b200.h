@@ -84,7 +84,12 @@ typedef struct {
     unsigned sel_seed;
     const int* sel_counter;
     int sel_min_m0;
+    int flags;                    /* PNP_FLAG_* */
 } pnp_csmri_grad_args;
+/* flags bit 0: launch the passes with programmatic dependent launch -- each kernel may begin (prologue, loads of data
+ * older than its predecessor) while the previous kernel on the stream is finishing, and waits for it before it reads
+ * its output.  Always safe; pays off when the stream is a chain of this library's passes (e.g. inside a CUDA graph). */
+#define PNP_FLAG_CHAIN 1
 int pnp_csmri_grad(const pnp_csmri_grad_args* args, void* stream);
 
 /* Selection bits from explicit k-space indices (k = ky*W + kx, the flat index into the
@@ -257,11 +262,15 @@ int pnp_prox_wavelet_fused(const float* z_in, float* z_out, int H, int W, int ba
  * pnp_csmri_grad(phases = 4) followed by pnp_prox_wavelet_fused; same results).  batch 1.  Returns
  * PNP_ERR_UNSUPPORTED when the image lines do not fit the SMs' shared memory -- use the two calls then.
  * advance_counters (optional): the first n_advance ints are incremented at the end, as pnp_advance would (`slot`
- * may be one of them: it is read before). */
+ * may be one of them: it is read before).
+ * barrier_ws (optional): two zero-initialised 32-bit words owned by the caller.  When given, the kernel is launched
+ * normally and synchronises its CTAs (all co-resident: one per SM) with a software barrier on these words instead of a
+ * cooperative launch -- the caller guarantees that no other kernel using such a barrier runs on the device at the same
+ * time -- and `chain` != 0 adds programmatic dependent launch (see PNP_FLAG_CHAIN). */
 int pnp_csmri_update_prox(const float* S, int H, int W, float gscale, float step, const float* step_ptr, const float* vadd,
                           const float* z_in, float* z_out, double* sig_log, float sigma_modifier, float fallback_sigma,
                           const float* xrec, double* mse_log, const int* slot, int* advance_counters, int n_advance,
-                          void* stream);
+                          unsigned* barrier_ws, int chain, void* stream);
 
 /* TV prox by Chambolle's dual projection, ADDITIVE mode (TVDenoiser(method='chambolle')): the north star's
  * "TV (Chambolle)" kernel; no counterpart in the reference, whose TVDenoiser is the wavelet shrink above

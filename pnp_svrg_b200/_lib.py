@@ -28,7 +28,7 @@ class CsmriGradArgs(C.Structure):
         ('phases', C.c_int), ('clear_bits', C.c_int),
         ('sel_count', C.c_int), ('sel_idx', C.c_void_p), ('sel_idx_img_stride', C.c_longlong), ('sel_cursor', C.c_void_p),
         ('sel_support', C.c_void_p), ('sel_m0', C.c_void_p), ('sel_support_img_stride', C.c_longlong),
-        ('sel_seed', C.c_uint), ('sel_counter', C.c_void_p), ('sel_min_m0', C.c_int),
+        ('sel_seed', C.c_uint), ('sel_counter', C.c_void_p), ('sel_min_m0', C.c_int), ('flags', C.c_int),
     ]
 
 
@@ -106,7 +106,7 @@ PROTOTYPES = {
                                   C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     'pnp_csmri_update_prox': (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p,
                                         C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p,
-                                        C.c_void_p, C.c_int, C.c_void_p]),
+                                        C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p]),
     'pnp_tv_chambolle': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p, C.c_float,
                                    C.c_float, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     'pnp_estimate_sigma': (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),

@@ -10,6 +10,7 @@ Additive keyword arguments (all optional, defaults reproduce the reference behav
   fast        replay a captured CUDA graph per inner iteration and defer the PSNR read-back to the
               end / every ``sync_every`` iterations (stop rules are then applied at those points)
 """
+import os
 import time
 
 import numpy as np
@@ -21,6 +22,8 @@ from ..engine import LOG_CHUNK, Budget, Engine, stop_rule
 
 def _grad_update(eng, a, b, sel, with_y, gscale, **kw):
     # the engine's minibatch selection is single use: the pass that consumes it leaves it zeroed
+    if eng.chain:
+        kw['chain'] = True
     eng.p._dev_grad(a, b=b, sel=sel, with_y=with_y, gscale=gscale, clear_sel=sel is not None and sel is eng.sel, **kw)
 
 
@@ -40,10 +43,13 @@ def _grad_update_prox(eng, a, b, sel, gscale, vadd, z, advance=0, sel_fn=None):
         job = eng.sel_job() if (sel_fn is not None and own) else None
         if job is None and sel_fn is not None:
             sel_fn()
+        if eng.chain:
+            kw['chain'] = True
         p._dev_grad(a, phases=3, sel_job=job, **kw)
         ok = p._dev_update_prox(gscale, eng.step, vadd, z, z, eng.sig_log, d.sigma_modifier,
                                 d.denoise_strength * d.decay ** (d.t + 1), p._xrec_dev, eng.mse_log, eng.slot_ptr,
-                                advance=eng.counters if advance else None, n_advance=advance)
+                                advance=eng.counters if advance else None, n_advance=advance,
+                                barrier_ws=eng.barrier_ws if (eng.chain or eng.sw_barrier) else None, chain=eng.chain)
         eng.fused_tail = ok
         if ok:
             d.t += 1
@@ -385,9 +391,20 @@ class SvrgRun:
             eng.set_step(self.eta * self.lr_decay ** self.i)
             # one eager epoch-shaped warm-up is NOT run: the kernels were loaded by pnp_init, and a capture does not execute
         t_before = self.denoiser.t
-        for s_ in range(n_sets):
-            bufs = None if self._epoch_sets is None else [self._epoch_sets[s_, j] for j in range(self.T2)]
-            self._epoch_graphs[s_] = eng.capture(lambda: self._epoch_ops(bufs))
+        # inside the epoch graph the passes form one chain on one stream: programmatic dependent launch lets every
+        # kernel start its prologue (and the loads that do not depend on its predecessor) while the previous one drains
+        # (measured on B200, profiles/README.md: neither it nor the software grid barrier it needs in the tail kernel
+        # gains anything over plain / cooperative launches -- the cost of a kernel boundary here is the drain and fill
+        # of the persistent grids, not the launch latency -- so both stay off unless PNP_CHAIN=1 / PNP_SW_BARRIER=1)
+        eng.chain = bool(getattr(self.problem, '_chain_ok', False)) and os.environ.get('PNP_CHAIN', '0') == '1'
+        eng.sw_barrier = bool(getattr(self.problem, '_chain_ok', False)) and os.environ.get('PNP_SW_BARRIER', '0') == '1'
+        try:
+            for s_ in range(n_sets):
+                bufs = None if self._epoch_sets is None else [self._epoch_sets[s_, j] for j in range(self.T2)]
+                self._epoch_graphs[s_] = eng.capture(lambda: self._epoch_ops(bufs))
+        finally:
+            eng.chain = False
+            eng.sw_barrier = False
         self.denoiser.t = t_before      # a capture runs the host side of fast_ops only
         self._step_on_device = True
         self._epochs_launched = 0

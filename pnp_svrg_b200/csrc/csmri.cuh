@@ -175,14 +175,21 @@ k_lines_r2c(const float* __restrict__ a, const float* __restrict__ b, float2* __
         if (b) bulk_g2s(stage_b, b + ibase + (long long)(2 * item * GP) * L, bytes, &bar);
     };
 
-    trace(100);
+    trace(100, true);
     if (threadIdx.x == 0) { mbar_init(&bar, 1); mbar_fence_init(); }
-    __syncthreads();
-    int item = blockIdx.x;
-    if (threadIdx.x == 0 && item < items) issue(item);
     FftTw<L> tw;
     tw.init(t);
-    if (sj.bits) run_sel_job(sj, L, nlines, blockIdx.y, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x);
+    __syncthreads();
+    griddep_wait();                                 // the iterate comes from the previous kernel of the chain
+    griddep_launch();
+    int item = blockIdx.x;
+    if (threadIdx.x == 0 && item < items) issue(item);
+    // In-pass minibatch selection: when the items do not divide evenly, the CTAs with one item fewer do it AFTER their
+    // loop (they would idle there anyway; at the start it sat in front of everybody's first transform: its dependent
+    // global loads cost 3 us).  Otherwise every CTA takes a slice before its first item.
+    const int n_heavy = items % (int)gridDim.x;                  // CTAs [0, n_heavy) have one item more
+    const bool sel_late = sj.bits && n_heavy != 0;
+    if (sj.bits && !sel_late) run_sel_job(sj, L, nlines, blockIdx.y, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x);
     unsigned parity = 0;
     for (; item < items; item += gridDim.x) {
         float2 x[EPT];
@@ -226,12 +233,15 @@ k_lines_r2c(const float* __restrict__ a, const float* __restrict__ b, float2* __
             } else {
                 o = make_float4(0.5f * (xk.x + xm.x), 0.5f * (xk.y - xm.y), 0.5f * (xk.y + xm.y), 0.5f * (xm.x - xk.x));
             }
-            S4[(long long)k * W2 + gg] = o;
+            stg_stream(S4 + (long long)k * W2 + gg, o);
         }
         __syncthreads();
         trace(102);
     }
+    if (sel_late && (int)blockIdx.x >= n_heavy)
+        run_sel_job(sj, L, nlines, blockIdx.y, ((int)blockIdx.x - n_heavy) * blockDim.x + threadIdx.x, ((int)gridDim.x - n_heavy) * blockDim.x);
     trace(109);
+    trace_flush();
 }
 
 // ------------------------------------------------------------------ pass 2
@@ -287,16 +297,18 @@ k_cols_mask(float2* __restrict__ S, const unsigned char* __restrict__ bits,
         bulk_g2s(stage, Si + (long long)(1 + item * NC) * L, bytes, &bar);
         bulk_g2s(const_cast<unsigned char*>(stage_bits), bi + (long long)(1 + item * NC) * L, (unsigned)(nc * L), &bar);
     };
-    trace(200);
+    trace(200, true);
     if (threadIdx.x == 0) { mbar_init(&bar, 1); mbar_fence_init(); }
+    FftTw<L> tw;
+    tw.init(t);
     __syncthreads();
+    griddep_wait();
+    griddep_launch();
     // CTA 0 of the grid owns packed column 0 (two transforms through a scalar split: as an appendix of an item CTA
     // it ended 2 us after everybody else); the others loop over the items
     const int nct = (int)gridDim.x - 1;
     int item = blockIdx.x > 0 ? (int)blockIdx.x - 1 : items;
     if (threadIdx.x == 0 && item < items) issue(item);
-    FftTw<L> tw;
-    tw.init(t);
     unsigned parity = 0;
     for (; item < items; item += nct) {
         const int col = 1 + item * NC + g;
@@ -337,14 +349,14 @@ k_cols_mask(float2* __restrict__ S, const unsigned char* __restrict__ bits,
         if (active) {
             float2* Sc = Si + crow;
 #pragma unroll
-            for (int i = 0; i < EPT; ++i) Sc[IX::out(t, i)] = cswap(y[i]);
+            for (int i = 0; i < EPT; ++i) stg_stream(Sc + IX::out(t, i), cswap(y[i]));
         }
         if (FftPlan<L>::NS > 1) __syncthreads();
         trace(202);
     }
     trace(209);
 
-    if (blockIdx.x != 0) return;
+    if (blockIdx.x != 0) { trace_flush(); return; }
     // ---- packed column 0: C = FFT(DC + i * Nyq); split, select each row, re-pack ----
     {
         float2 x[EPT];
@@ -385,7 +397,7 @@ k_cols_mask(float2* __restrict__ S, const unsigned char* __restrict__ bits,
         fft_regs<L>(t, sb, x);
         if (g == 0) {
 #pragma unroll
-            for (int i = 0; i < EPT; ++i) Si[IX::out(t, i)] = cswap(x[i]);
+            for (int i = 0; i < EPT; ++i) stg_stream(Si + IX::out(t, i), cswap(x[i]));
             if (clear_bits) {
                 unsigned char* cb = clear_bits + (long long)img * bits_img_stride;
                 for (int i = t; i < L / 16; i += T) reinterpret_cast<uint4*>(cb)[i] = make_uint4(0u, 0u, 0u, 0u);
@@ -393,6 +405,7 @@ k_cols_mask(float2* __restrict__ S, const unsigned char* __restrict__ bits,
         }
     }
     trace(210);
+    trace_flush();
 }
 
 // ------------------------------------------------------------------ pass 3
@@ -437,7 +450,7 @@ k_lines_c2r(const float2* __restrict__ S, int nlines, long long img_stride, floa
         for (int n = 0; n < NQ; ++n) {
             const int i = threadIdx.x + n * GP * T;
             const int gg = i % GP, k = i / GP;
-            q[n] = (item * GP + gg < npairs) ? S4[(long long)k * W2 + item * GP + gg] : make_float4(0.f, 0.f, 0.f, 0.f);
+            q[n] = (item * GP + gg < npairs) ? ldg_stream(S4 + (long long)k * W2 + item * GP + gg) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
     };
     auto issue = [&](int item) {                    // one thread: TMA bulk copies of the epilogue operands
@@ -451,6 +464,8 @@ k_lines_c2r(const float2* __restrict__ S, int nlines, long long img_stride, floa
     };
     if (threadIdx.x == 0) { mbar_init(&bar, 1); mbar_fence_init(); }
     __syncthreads();
+    griddep_wait();
+    griddep_launch();
     unsigned parity = 0;
 
     float4 qn[NQ];
@@ -499,13 +514,13 @@ k_lines_c2r(const float2* __restrict__ S, int nlines, long long img_stride, floa
                     const int sh = idx + (h ? L : 0);
                     const long long eh = base + sh;
                     if (UPD) {
-                        p_zout[eh] = sz[sh] - step * (gval + sv[sh]);
+                        stg_stream(p_zout + eh, sz[sh] - step * (gval + sv[sh]));
                     } else {
-                        if (p_gout) p_gout[eh] = gval;
+                        if (p_gout) stg_stream(p_gout + eh, gval);
                         float v = gval;
                         if (p_vadd) v += sv[sh];
-                        if (p_vout) p_vout[eh] = v;
-                        if (p_zout) p_zout[eh] = sz[sh] - step * v;
+                        if (p_vout) stg_stream(p_vout + eh, v);
+                        if (p_zout) stg_stream(p_zout + eh, sz[sh] - step * v);
                     }
                 }
             }
@@ -525,7 +540,7 @@ k_lines_c2r(const float2* __restrict__ S, int nlines, long long img_stride, floa
 template <int L> __host__ __device__ constexpr int upd_gp() { return 512 / fft_threads<L>(); }
 __device__ unsigned long long g_upd_phase_ns[8];      // PNP_PHASE_TIMING builds only: %globaltimer at the phase boundaries of CTA 0
 __device__ __forceinline__ void upd_mark(int i) {
-    trace(300 + i);
+    trace(300 + i, i == 0);
 #ifdef PNP_PHASE_TIMING
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         unsigned long long t;
@@ -541,7 +556,7 @@ k_update_prox(const float2* __restrict__ S, int nlines, float inv_n, float gscal
               const float* __restrict__ step_ptr, const float* __restrict__ vadd, const float* __restrict__ z_in,
               float* __restrict__ z_out, const float* __restrict__ xrec, int pairs_per_cta, float sigma_modifier,
               float fallback_sigma, double* __restrict__ sig_log, double* __restrict__ mse_log, const int* __restrict__ slot,
-              int* __restrict__ advance, int n_advance) {
+              int* __restrict__ advance, int n_advance, unsigned* __restrict__ gbar) {
     constexpr int T = fft_threads<L>();
     constexpr int EPT = FftPlan<L>::EPT;
     constexpr int PL = fft_plane<L>();
@@ -558,11 +573,9 @@ k_update_prox(const float2* __restrict__ S, int nlines, float inv_n, float gscal
     int mine = npairs - first_pair;
     mine = mine < 0 ? 0 : (mine > pairs_per_cta ? pairs_per_cta : mine);
     const long long first = 2ll * first_pair;                   // first line of this CTA
-    const int cur_slot = slot ? *slot : 0;
     const SmemBuf sb{smem + g * GS, smem + g * GS + PL};
     const float4* S4 = reinterpret_cast<const float4*>(S);
     const float gs = inv_n * gscale;
-    const float st = step_ptr ? *step_ptr : step;
 
     upd_mark(0);
     if (threadIdx.x == 0) {
@@ -577,21 +590,22 @@ k_update_prox(const float2* __restrict__ S, int nlines, float inv_n, float gscal
             mbar_expect_tx(&bars[0], (unsigned)(l0 * L * sizeof(float)));
             for (int l = 0; l < l0; ++l)
                 bulk_g2s(lines + (long long)l * L, z_in + (first + l) * L, (unsigned)(L * sizeof(float)), &bars[0]);
-            if (2 * mine > l0) {
-                mbar_expect_tx(&bars[1], (unsigned)((2 * mine - l0) * L * sizeof(float)));
-                for (int l = l0; l < 2 * mine; ++l)
-                    bulk_g2s(lines + (long long)l * L, z_in + (first + l) * L, (unsigned)(L * sizeof(float)), &bars[1]);
-            }
         }
     }
-    // the operands of the later phases (mu for the update, the ground truth for the PSNR) come from DRAM: start them
-    // towards L2 now, they are first touched ~10 and ~25 us from here
-    if (threadIdx.x >= 32 && threadIdx.x < 32 + 2 * mine) {
-        const long long off = (first + (threadIdx.x - 32)) * L;
-        bulk_prefetch_l2(vadd + off, (unsigned)(L * sizeof(float)));
-        if (xrec) bulk_prefetch_l2(xrec + off, (unsigned)(L * sizeof(float)));
-    }
+    // mu (the update's operand) comes from DRAM: start it towards L2 now, it is first touched after the first transform.
+    // (The ground truth is pulled into shared memory by TMA during the grid barrier of the prox phases; requesting it
+    // here as well put 16 MB in front of the data the first round of transforms waits for.)
+    if (threadIdx.x >= 32 && threadIdx.x < 32 + 2 * (mine < GP ? mine : GP))
+        bulk_prefetch_l2(vadd + (first + (threadIdx.x - 32)) * L, (unsigned)(L * sizeof(float)));
+    FftTw<L> tw;
+    tw.init(t);
     __syncthreads();
+    // Everything above reads data that is older than the previous kernel of the chain (the iterate and mu were written
+    // before the column pass started); the spectrum, the log slot and the step come from it or may change with it.
+    griddep_wait();
+    griddep_launch();
+    const int cur_slot = slot ? *slot : 0;
+    const float st = step_ptr ? *step_ptr : step;
 
     auto load_spec = [&](int round, float4 (&q)[NQ]) {
 #pragma unroll
@@ -599,14 +613,20 @@ k_update_prox(const float2* __restrict__ S, int nlines, float inv_n, float gscal
             const int i = threadIdx.x + n * GP * T;
             const int gg = i % GP, k = i / GP;
             const int pl = round * GP + gg;
-            q[n] = pl < mine ? S4[(long long)k * npairs + first_pair + pl] : make_float4(0.f, 0.f, 0.f, 0.f);
+            q[n] = pl < mine ? ldg_stream(S4 + (long long)k * npairs + first_pair + pl) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
     };
     const int rounds = (mine + GP - 1) / GP;
     float4 qn[NQ];
     if (rounds > 0) load_spec(0, qn);
-    FftTw<L> tw;
-    tw.init(t);
+    if (threadIdx.x == 0 && mine > GP) {            // lines of the later rounds: requested behind the first round's data
+        const int l0 = 2 * GP;
+        mbar_expect_tx(&bars[1], (unsigned)((2 * mine - l0) * L * sizeof(float)));
+        for (int l = l0; l < 2 * mine; ++l)
+            bulk_g2s(lines + (long long)l * L, z_in + (first + l) * L, (unsigned)(L * sizeof(float)), &bars[1]);
+    }
+    if (threadIdx.x >= 32 + 2 * GP && threadIdx.x < 32 + 2 * mine)
+        bulk_prefetch_l2(vadd + (first + (threadIdx.x - 32)) * L, (unsigned)(L * sizeof(float)));
     for (int round = 0; round < rounds; ++round) {
         // X[k] = A[k] + i B[k] of the two lines, written re/im swapped for the inverse transform
 #pragma unroll
@@ -639,7 +659,7 @@ k_update_prox(const float2* __restrict__ S, int nlines, float inv_n, float gscal
             for (int hh = 0; hh < 2; ++hh) {
                 float va[EPT];
 #pragma unroll
-                for (int i = 0; i < EPT; ++i) va[i] = gv[hh * L + IX::out(t, i)];
+                for (int i = 0; i < EPT; ++i) va[i] = ldg_stream(gv + hh * L + IX::out(t, i));
 #pragma unroll
                 for (int i = 0; i < EPT; ++i) {
                     // swapped output: .y = real part -> line 2*pair, .x = imag part -> line 2*pair + 1
@@ -658,8 +678,9 @@ k_update_prox(const float2* __restrict__ S, int nlines, float inv_n, float gscal
     // prox phases (sigma selection, Haar transposition)
     static_assert(L < 512 || lines_stage_off<L, GP>() >= 16 * prox_scratch<L>(), "exchange planes too small for the prox scratch");
     prox_phases<L>(lines, 2 * mine, first, nlines, 1, z_out, xrec, sigma_modifier, fallback_sigma, sig_log, mse_log, cur_slot,
-                   reinterpret_cast<unsigned*>(smem), &bars[2], advance, n_advance);
+                   reinterpret_cast<unsigned*>(smem), &bars[2], advance, n_advance, gbar);
     upd_mark(4);
+    trace_flush();
 }
 
 // ------------------------------------------------------------------ selection kernels
@@ -678,7 +699,7 @@ __global__ void k_sel_from_feistel(unsigned char* __restrict__ bits, int H, int 
                                    long long support_img_stride, int B, unsigned seed,
                                    const int* __restrict__ counter, int* __restrict__ idx_out) {
     const int img = blockIdx.y;
-    trace(400);
+    trace(400, true);
     const unsigned key = mix32(seed ^ mix32((counter ? (unsigned)*counter : 0u) * 0x632be5abU + (unsigned)img));
     const int* sup = support + (long long)img * support_img_stride;
     const unsigned n = (unsigned)m0[img];
@@ -690,6 +711,7 @@ __global__ void k_sel_from_feistel(unsigned char* __restrict__ bits, int H, int 
         set_sel_bits(bi, H, W, k);
     }
     trace(409);
+    trace_flush();
 }
 
 __global__ void k_sample_indices(int* __restrict__ idx_out, int n, int count, unsigned seed,

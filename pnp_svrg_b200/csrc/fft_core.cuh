@@ -24,26 +24,53 @@ __device__ float2 g_tw[PNP_TW_N];
 namespace pnp {
 
 // ------------------------------------------------------------------ optional event trace (builds with -DPNP_TRACE)
-// thread 0 of a CTA records (%globaltimer, tag, blockIdx.x, %smid); read back with pnp_debug_read(1, ...).
+// thread 0 of a CTA stamps (%globaltimer, tag) into a small shared-memory list (no global traffic while the kernel
+// works); trace_flush() at the end of the kernel appends the list to a global buffer with ONE atomic per CTA.
+// Read back with pnp_debug_read(1, ...): 16-byte records (u64 ns, i32 tag, i16 blockIdx.x, i16 %smid).
 struct TraceEv { unsigned long long t; int tag; short cta; short sm; };
 #ifdef PNP_TRACE
 #define PNP_TRACE_MAX (1 << 20)
+#define PNP_TRACE_CTA 40
 __device__ TraceEv g_trace[PNP_TRACE_MAX];
 __device__ unsigned g_trace_n;
-__device__ __forceinline__ void trace(int tag) {
+__device__ int g_dbg_flags;          // experiment switches of trace builds (pnp_debug_set key 3)
+#define PNP_DBG(bit) (g_dbg_flags & (bit))
+struct TraceLocal { unsigned long long t[PNP_TRACE_CTA]; int tag[PNP_TRACE_CTA]; int n; };
+__device__ __forceinline__ TraceLocal* trace_local() {
+    __shared__ TraceLocal s_tl;
+    return &s_tl;
+}
+// first = true on the first call of a kernel (resets the CTA's list)
+__device__ __forceinline__ void trace(int tag, bool first = false) {
     if (threadIdx.x == 0) {
-        const unsigned i = atomicAdd(&g_trace_n, 1u);
-        if (i < PNP_TRACE_MAX) {
+        TraceLocal* tl = trace_local();
+        if (first) tl->n = 0;
+        const int i = tl->n;
+        if (i < PNP_TRACE_CTA) {
             unsigned long long t;
-            unsigned sm;
             asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-            asm volatile("mov.u32 %0, %%smid;" : "=r"(sm));
-            g_trace[i] = TraceEv{t, tag, (short)blockIdx.x, (short)sm};
+            tl->t[i] = t;
+            tl->tag[i] = tag;
+            tl->n = i + 1;
         }
     }
 }
+__device__ __forceinline__ void trace_flush() {
+    if (threadIdx.x == 0) {
+        TraceLocal* tl = trace_local();
+        const int n = tl->n;
+        unsigned sm;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(sm));
+        const unsigned base = atomicAdd(&g_trace_n, (unsigned)n);
+        for (int i = 0; i < n; ++i)
+            if (base + i < PNP_TRACE_MAX) g_trace[base + i] = TraceEv{tl->t[i], tl->tag[i], (short)blockIdx.x, (short)sm};
+        tl->n = 0;
+    }
+}
 #else
-__device__ __forceinline__ void trace(int) {}
+__device__ __forceinline__ void trace(int, bool = false) {}
+__device__ __forceinline__ void trace_flush() {}
+#define PNP_DBG(bit) 0
 #endif
 
 // ------------------------------------------------------------------ TMA bulk copy + mbarrier (sm_90+)
@@ -57,13 +84,76 @@ __device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier
 __device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+// L2 eviction policy for the image-sized data streams (iterate, snapshot, spectrum, ground truth ...): evict-first.
+// One inner iteration at 2048^2 moves ~130 MB through an L2 whose useful capacity is about half of its 126 MB, so with
+// the default policy NOTHING survives from one iteration to the next -- including the kernels' own code, which is
+// straight-line and run once or twice per CTA: its instruction fetches then come from DRAM (measured: the same
+// 450-instruction block took 4.1 us the first time and 0.8 us the second).  With the streams marked evict-first the
+// code, the twiddle table and the small per-iteration state stay resident.
+__device__ __forceinline__ unsigned long long l2_stream_policy() {
+    unsigned long long p;
+    asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+#ifndef PNP_NO_L2_HINTS
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(l2_stream_policy()) : "memory");
+#else
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+#endif
+}
+// streaming global loads / stores with the same policy
+__device__ __forceinline__ float4 ldg_stream(const float4* p) {
+    float4 v;
+#ifndef PNP_NO_L2_HINTS
+    asm volatile("ld.global.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p), "l"(l2_stream_policy()));
+#else
+    v = *p;
+#endif
+    return v;
+}
+__device__ __forceinline__ float ldg_stream(const float* p) {
+    float v;
+#ifndef PNP_NO_L2_HINTS
+    asm volatile("ld.global.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(v) : "l"(p), "l"(l2_stream_policy()));
+#else
+    v = *p;
+#endif
+    return v;
+}
+__device__ __forceinline__ void stg_stream(float4* p, float4 v) {
+#ifndef PNP_NO_L2_HINTS
+    asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1, %2, %3, %4}, %5;"
+                 ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "l"(l2_stream_policy()) : "memory");
+#else
+    *p = v;
+#endif
+}
+__device__ __forceinline__ void stg_stream(float2* p, float2 v) {
+#ifndef PNP_NO_L2_HINTS
+    asm volatile("st.global.L2::cache_hint.v2.f32 [%0], {%1, %2}, %3;"
+                 ::"l"(p), "f"(v.x), "f"(v.y), "l"(l2_stream_policy()) : "memory");
+#else
+    *p = v;
+#endif
+}
+__device__ __forceinline__ void stg_stream(float* p, float v) {
+#ifndef PNP_NO_L2_HINTS
+    asm volatile("st.global.L2::cache_hint.f32 [%0], %1, %2;" ::"l"(p), "f"(v), "l"(l2_stream_policy()) : "memory");
+#else
+    *p = v;
+#endif
 }
 // bring `bytes` (multiple of 16) at `src` into L2 ahead of use; no destination, nothing to wait for
 __device__ __forceinline__ void bulk_prefetch_l2(const void* src, unsigned bytes) {
+#ifndef PNP_NO_L2_HINTS
+    asm volatile("cp.async.bulk.prefetch.L2.global.L2::cache_hint [%0], %1, %2;" ::"l"(src), "r"(bytes), "l"(l2_stream_policy()) : "memory");
+#else
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+#endif
 }
 __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
     asm volatile(
@@ -75,6 +165,38 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
         "bra MBAR_WAIT_%=;\n\t"
         "MBAR_DONE_%=:\n\t"
         "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+
+// ------------------------------------------------------------------ programmatic dependent launch + software grid barrier
+// A pass launched with the programmatic-stream-serialization attribute may START while the previous kernel of the
+// stream is still finishing (its CTAs become resident as SMs free up and run their prologue); griddep_wait() returns
+// once that kernel has completed and flushed.  Rule used by every pass here: griddep_launch() only AFTER the own
+// griddep_wait(), so a kernel that runs at all knows that everything older than its direct predecessor is complete
+// and may read such data (the iterate of the previous iteration, the snapshot, mu, the ground truth) BEFORE the wait.
+// Both are no-ops in a normal launch.
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void griddep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+// Grid-wide barrier of a persistent kernel whose CTAs are all co-resident (grid <= SMs x occupancy; the caller
+// guarantees that no other kernel spinning on such a barrier shares the device).  ws[0]: arrivals, ws[1]: generation;
+// both zero before the first use, left consistent for the next one.
+__device__ __forceinline__ void sw_grid_sync(unsigned* ws, unsigned nblocks) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned gen, g;
+        asm volatile("ld.acquire.gpu.u32 %0, [%1];" : "=r"(gen) : "l"(ws + 1) : "memory");
+        __threadfence();
+        if (atomicAdd(ws, 1u) == nblocks - 1) {
+            atomicExch(ws, 0u);
+            __threadfence();
+            asm volatile("st.release.gpu.u32 [%0], %1;" ::"l"(ws + 1), "r"(gen + 1) : "memory");
+        } else {
+            do {
+                asm volatile("ld.acquire.gpu.u32 %0, [%1];" : "=r"(g) : "l"(ws + 1) : "memory");
+            } while (g == gen);
+        }
+    }
+    __syncthreads();
 }
 
 // Complex arithmetic on the packed fp32 pipe of sm_100 (add/mul/fma.rn.f32x2): FADD2 takes a negated operand,

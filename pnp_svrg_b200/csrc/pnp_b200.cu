@@ -57,7 +57,11 @@ int check_init() {
 
 // ---- per-size launch geometry ------------------------------------------------------------
 template <int L> constexpr int lines_gp() {            // line pairs per CTA in passes 1 and 3
+#ifdef PNP_LINES_GP1
+    return pnp::fft_threads<L>() >= 128 ? 1 : 4;
+#else
     return pnp::fft_threads<L>() >= 256 ? 1 : (pnp::fft_threads<L>() >= 128 ? 2 : 4);
+#endif
 }
 template <int L> constexpr int cols_nc() {             // packed columns per CTA in pass 2
     return pnp::fft_threads<L>() >= 128 ? 1 : (pnp::fft_threads<L>() >= 64 ? 2 : (64 / pnp::fft_threads<L>() > 8 ? 8 : 64 / pnp::fft_threads<L>()));
@@ -145,6 +149,25 @@ int raise_smem_limit(const void* kernel, int bytes) {
     return PNP_OK;
 }
 
+// Kernel launch with the optional programmatic-stream-serialization attribute (the kernel may begin while its
+// predecessor on the stream is finishing; it calls griddepcontrol.wait before it touches that kernel's output).
+int launch_ex(const void* kernel, dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool chain, void** args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    if (chain) {
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = at;
+        cfg.numAttrs = 1;
+    }
+    CU_TRY(cudaLaunchKernelExC(&cfg, kernel, args));
+    return PNP_OK;
+}
+
 template <int L>
 int launch_r2c(const pnp_csmri_grad_args& a, cudaStream_t st) {
     constexpr int GP = lines_gp<L>();
@@ -158,10 +181,14 @@ int launch_r2c(const pnp_csmri_grad_args& a, cudaStream_t st) {
         sj.support = a.sel_support; sj.m0 = a.sel_m0; sj.support_img_stride = a.sel_support_img_stride;
         sj.count = a.sel_count; sj.seed = a.sel_seed; sj.counter = a.sel_counter; sj.idx_out = nullptr;
     }
-    pnp::k_lines_r2c<L, GP><<<grid, GP * pnp::fft_threads<L>(), lines_smem<L>(), st>>>(
-        a.a, a.b, reinterpret_cast<float2*>(a.S), a.W, (long long)a.H * a.W, sj);
-    LAUNCH_CHECK();
-    return PNP_OK;
+    const float* pa = a.a;
+    const float* pb = a.b;
+    float2* pS = reinterpret_cast<float2*>(a.S);
+    int nl = a.W;
+    long long stride = (long long)a.H * a.W;
+    void* args[] = {(void*)&pa, (void*)&pb, (void*)&pS, (void*)&nl, (void*)&stride, (void*)&sj};
+    return launch_ex((const void*)pnp::k_lines_r2c<L, GP>, grid, dim3(GP * pnp::fft_threads<L>()), lines_smem<L>(), st,
+                     (a.flags & PNP_FLAG_CHAIN) != 0, args);
 }
 
 template <int L>
@@ -174,13 +201,17 @@ int launch_cols(const pnp_csmri_grad_args& a, cudaStream_t st) {
     int ctas = persistent_ctas((const void*)pnp::k_cols_mask<L, NC>, NC * pnp::fft_threads<L>(), cols_smem<L>(), items + 1, a.batch);
     if (ctas < 2) ctas = 2;
     dim3 grid(ctas, a.batch);
-    pnp::k_cols_mask<L, NC><<<grid, NC * pnp::fft_threads<L>(), cols_smem<L>(), st>>>(
-        reinterpret_cast<float2*>(a.S), a.bits, reinterpret_cast<const float2*>(a.Y1),
-        reinterpret_cast<const float2*>(a.Y2), reinterpret_cast<const float2*>(a.Y1n),
-        reinterpret_cast<const float2*>(a.Y2n), hp, (long long)a.W * hp, (long long)a.W * hp,
-        a.clear_bits ? const_cast<unsigned char*>(a.bits) : nullptr);
-    LAUNCH_CHECK();
-    return PNP_OK;
+    float2* pS = reinterpret_cast<float2*>(a.S);
+    const unsigned char* pbits = a.bits;
+    const float2 *y1 = reinterpret_cast<const float2*>(a.Y1), *y2 = reinterpret_cast<const float2*>(a.Y2),
+                 *y1n = reinterpret_cast<const float2*>(a.Y1n), *y2n = reinterpret_cast<const float2*>(a.Y2n);
+    int hp_ = hp;
+    long long bstride = (long long)a.W * hp, ystride = (long long)a.W * hp;
+    unsigned char* clr = a.clear_bits ? const_cast<unsigned char*>(a.bits) : nullptr;
+    void* args[] = {(void*)&pS, (void*)&pbits, (void*)&y1, (void*)&y2, (void*)&y1n, (void*)&y2n, (void*)&hp_, (void*)&bstride,
+                    (void*)&ystride, (void*)&clr};
+    return launch_ex((const void*)pnp::k_cols_mask<L, NC>, grid, dim3(NC * pnp::fft_threads<L>()), cols_smem<L>(), st,
+                     (a.flags & PNP_FLAG_CHAIN) != 0, args);
 }
 
 template <int L>
@@ -190,17 +221,18 @@ int launch_c2r(const pnp_csmri_grad_args& a, cudaStream_t st) {
     const int items = (pairs + GP - 1) / GP;
     pnp::GradEpilogue ep{a.gscale, a.gscale_ptr, a.step, a.step_ptr, a.g_out, a.vadd, a.v_out, a.z_in, a.z_out};
     const float inv_n = (float)(1.0 / ((double)a.H * (double)a.W));
+    const float2* pS = reinterpret_cast<const float2*>(a.S);
+    int nl = a.W;
+    long long stride = (long long)a.H * a.W;
+    float inv = inv_n;
+    void* args[] = {(void*)&pS, (void*)&nl, (void*)&stride, (void*)&inv, (void*)&ep};
+    const bool chain = (a.flags & PNP_FLAG_CHAIN) != 0;
     if (a.vadd && a.z_in && a.z_out && !a.g_out && !a.v_out) {          // the inner-iteration update
         dim3 grid(persistent_ctas((const void*)pnp::k_lines_c2r<L, GP, true>, GP * pnp::fft_threads<L>(), lines_smem<L>(), items, a.batch), a.batch);
-        pnp::k_lines_c2r<L, GP, true><<<grid, GP * pnp::fft_threads<L>(), lines_smem<L>(), st>>>(
-            reinterpret_cast<const float2*>(a.S), a.W, (long long)a.H * a.W, inv_n, ep);
-    } else {
-        dim3 grid(persistent_ctas((const void*)pnp::k_lines_c2r<L, GP, false>, GP * pnp::fft_threads<L>(), lines_smem<L>(), items, a.batch), a.batch);
-        pnp::k_lines_c2r<L, GP, false><<<grid, GP * pnp::fft_threads<L>(), lines_smem<L>(), st>>>(
-            reinterpret_cast<const float2*>(a.S), a.W, (long long)a.H * a.W, inv_n, ep);
+        return launch_ex((const void*)pnp::k_lines_c2r<L, GP, true>, grid, dim3(GP * pnp::fft_threads<L>()), lines_smem<L>(), st, chain, args);
     }
-    LAUNCH_CHECK();
-    return PNP_OK;
+    dim3 grid(persistent_ctas((const void*)pnp::k_lines_c2r<L, GP, false>, GP * pnp::fft_threads<L>(), lines_smem<L>(), items, a.batch), a.batch);
+    return launch_ex((const void*)pnp::k_lines_c2r<L, GP, false>, grid, dim3(GP * pnp::fft_threads<L>()), lines_smem<L>(), st, chain, args);
 }
 
 #define DISPATCH_POW2(n, FN, ...)                                 \
@@ -263,7 +295,7 @@ namespace {
 template <int L>
 int launch_update_prox(const float* S, int W, float inv_n, float gscale, float step, const float* step_ptr, const float* vadd,
                        const float* z_in, float* z_out, const float* xrec, float sm, float fb, double* sig_log, double* mse_log,
-                       const int* slot, int* adv, int n_adv, cudaStream_t st) {
+                       const int* slot, int* adv, int n_adv, unsigned* gbar, int chain, cudaStream_t st) {
     constexpr int GP = pnp::upd_gp<L>();
     const int npairs = W / 2;
     int grid = num_sms() < npairs ? num_sms() : npairs;
@@ -276,14 +308,17 @@ int launch_update_prox(const float* S, int W, float inv_n, float gscale, float s
     int nl = W, p = ppc;
     void* args[] = {(void*)&S, (void*)&nl, (void*)&inv_n, (void*)&gscale, (void*)&step, (void*)&step_ptr, (void*)&vadd, (void*)&z_in,
                     (void*)&z_out, (void*)&xrec, (void*)&p, (void*)&sm, (void*)&fb, (void*)&sig_log, (void*)&mse_log, (void*)&slot,
-                    (void*)&adv, (void*)&n_adv};
+                    (void*)&adv, (void*)&n_adv, (void*)&gbar};
+    // with a barrier workspace: plain launch + software grid barrier (all CTAs are co-resident: grid <= SM count, one
+    // CTA per SM), which is what lets the kernel join a programmatic-dependent-launch chain; else cooperative launch
+    if (gbar) return launch_ex((const void*)pnp::k_update_prox<L>, dim3(grid), dim3(512), smem, st, chain != 0, args);
     CU_TRY(cudaLaunchCooperativeKernel((const void*)pnp::k_update_prox<L>, dim3(grid), dim3(512), args, smem, st));
     return PNP_OK;
 }
 int dispatch_update_prox(int n, const float* S, int W, float inv_n, float gscale, float step, const float* step_ptr,
                          const float* vadd, const float* z_in, float* z_out, const float* xrec, float sm, float fb, double* sig_log,
-                         double* mse_log, const int* slot, int* adv, int n_adv, cudaStream_t st) {
-    DISPATCH_POW2(n, launch_update_prox, S, W, inv_n, gscale, step, step_ptr, vadd, z_in, z_out, xrec, sm, fb, sig_log, mse_log, slot, adv, n_adv, st)
+                         double* mse_log, const int* slot, int* adv, int n_adv, unsigned* gbar, int chain, cudaStream_t st) {
+    DISPATCH_POW2(n, launch_update_prox, S, W, inv_n, gscale, step, step_ptr, vadd, z_in, z_out, xrec, sm, fb, sig_log, mse_log, slot, adv, n_adv, gbar, chain, st)
 }
 }  // namespace
 
@@ -338,8 +373,9 @@ int launch_prox_fused(const float* zin, float* zout, const float* xrec, int W, i
     if (smem > 176 * 1024) return fail(PNP_ERR_UNSUPPORTED, "fused prox: %zu bytes of lines per CTA do not fit shared memory", smem);
     { const int rc = raise_smem_limit((const void*)pnp::k_prox_wavelet_fused<L>, 176 * 1024); if (rc != PNP_OK) return rc; }
     int nl = W;
+    unsigned* gbar = nullptr;
     void* args[] = {(void*)&zin, (void*)&zout, (void*)&xrec, (void*)&nl, (void*)&batch, (void*)&lpc, (void*)&sm, (void*)&fb,
-                    (void*)&sig_log, (void*)&mse_log, (void*)&slot};
+                    (void*)&sig_log, (void*)&mse_log, (void*)&slot, (void*)&gbar};
     CU_TRY(cudaLaunchCooperativeKernel((const void*)pnp::k_prox_wavelet_fused<L>, dim3(grid), dim3(512), args, smem, st));
     return PNP_OK;
 }
@@ -700,7 +736,7 @@ int pnp_pr_grad(const pnp_pr_grad_args* args, void* stream) {
 int pnp_csmri_update_prox(const float* S, int H, int W, float gscale, float step, const float* step_ptr, const float* vadd,
                           const float* z_in, float* z_out, double* sig_log, float sigma_modifier, float fallback_sigma,
                           const float* xrec, double* mse_log, const int* slot, int* advance_counters, int n_advance,
-                          void* stream) {
+                          unsigned* barrier_ws, int chain, void* stream) {
     if (!S || !vadd || !z_in || !z_out || !sig_log) return fail(PNP_ERR_ARG, "bad argument");
     if (advance_counters && (n_advance < 1 || n_advance > 32)) return fail(PNP_ERR_ARG, "n_advance must be in [1, 32]");
     if (!pow2_ok(H) || W < 2 || (W & 1)) return fail(PNP_ERR_ARG, "H must be a power of two in [32, 4096], W even");
@@ -709,7 +745,7 @@ int pnp_csmri_update_prox(const float* S, int H, int W, float gscale, float step
     const float inv_n = (float)(1.0 / ((double)H * (double)W));
     return dispatch_update_prox(H, reinterpret_cast<const float*>(S), W, inv_n, gscale, step, step_ptr, vadd, z_in, z_out, xrec,
                                 sigma_modifier, fallback_sigma, sig_log, mse_log, slot, advance_counters, n_advance,
-                                static_cast<cudaStream_t>(stream));
+                                barrier_ws, chain, static_cast<cudaStream_t>(stream));
 }
 
 int pnp_cdp_grad(const pnp_cdp_grad_args* args, void* stream) {
@@ -920,6 +956,9 @@ int pnp_cnn_forward(const pnp_cnn_net* net, const float* img, float* out, int PH
 
 int pnp_debug_set(int key, int value) {
     if (key == 1) g_tc_dbg = value;
+#ifdef PNP_TRACE
+    if (key == 3) CU_TRY(cudaMemcpyToSymbol(pnp::g_dbg_flags, &value, sizeof(int)));
+#endif
     if (key == 2) {                          // PNP_PHASE_TIMING builds: print the phase boundaries of the last k_update_prox
         unsigned long long t[8];
         CU_TRY(cudaMemcpyFromSymbol(t, pnp::g_upd_phase_ns, sizeof(t)));

@@ -651,6 +651,7 @@ __device__ __forceinline__ float prox_line_inverse(ProxLine<L>& st, float* tscr,
 #pragma unroll
         for (int kk = 0; kk < LEVELS; ++kk) thr[kk] = __shfl_sync(0xffffffffu, tk, kk);
     }
+    if (threadIdx.x < 32) trace(320);
 #pragma unroll
     for (int q = 1; q >= 0; --q) {
         const float d = soft_shrink(st.Dx[q], thr[2 + LG + q]);
@@ -675,7 +676,12 @@ __device__ __forceinline__ float prox_line_inverse(ProxLine<L>& st, float* tscr,
         for (int j = 0; j < NCH / 4; ++j) b4[j] = make_float4(st.v[4 * j], st.v[4 * j + 1], st.v[4 * j + 2], st.v[4 * j + 3]);
     }
     __syncwarp();
+    if (threadIdx.x < 32) trace(321);
     float err = 0.f;
+#ifdef PNP_TRACE
+    for (int rep = 0; rep < (PNP_DBG(4) ? 2 : 1); ++rep) {       // experiment: is the second pass over the same code faster?
+    if (rep && threadIdx.x < 32) trace(323);
+#endif
 #pragma unroll
     for (int c = 0; c < NCH; ++c) {
         const float aa = tscr[haar_wl_pad(c * 32 + lane)];
@@ -683,14 +689,18 @@ __device__ __forceinline__ float prox_line_inverse(ProxLine<L>& st, float* tscr,
         const float a0 = (aa + dd) * RS2, a1 = (aa - dd) * RS2;
         const float d0 = soft_shrink(st.x[c][1], thr[0]), d1 = soft_shrink(st.x[c][3], thr[0]);
         const float4 o = make_float4((a0 + d0) * RS2, (a0 - d0) * RS2, (a1 + d1) * RS2, (a1 - d1) * RS2);
-        zo4[c * 32 + lane] = o;
-        if (xr4) {
+        if (!PNP_DBG(1)) stg_stream(zo4 + c * 32 + lane, o);
+        if (xr4 && !PNP_DBG(2)) {
             const float4 r = xr4[c * 32 + lane];
             const float e0 = o.x - r.x, e1 = o.y - r.y, e2 = o.z - r.z, e3 = o.w - r.w;
             err = fmaf(e0, e0, fmaf(e1, e1, fmaf(e2, e2, fmaf(e3, e3, err))));
         }
     }
+#ifdef PNP_TRACE
+    }
+#endif
     __syncwarp();                      // the scratch may be rewritten by the caller's next line
+    if (threadIdx.x < 32) trace(322);
     return err;
 }
 
@@ -1022,8 +1032,17 @@ template <int L>
 __device__ __forceinline__ void prox_phases(float* lines, int mine, long long first, int nlines, int batch, float* __restrict__ zout,
                                             const float* __restrict__ xrec, float sigma_modifier, float fallback_sigma,
                                             double* __restrict__ sig_log, double* __restrict__ mse_log, int cur_slot,
-                                            unsigned* scratch, unsigned long long* xbar, int* __restrict__ advance, int n_advance) {
+                                            unsigned* scratch, unsigned long long* xbar, int* __restrict__ advance, int n_advance,
+                                            unsigned* __restrict__ gbar /* software grid barrier workspace, or null: cooperative launch */) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    auto grid_sync = [&]() {
+        if (gbar) {
+            sw_grid_sync(gbar, gridDim.x);
+        } else {
+            __threadfence();
+            cooperative_groups::this_grid().sync();
+        }
+    };
     if constexpr (L >= 512 && L <= 2048) {
         if (mine <= 16) {
             ProxLine<L> st;
@@ -1034,9 +1053,11 @@ __device__ __forceinline__ void prox_phases(float* lines, int mine, long long fi
             if (active) {
                 const double sig = line_sigma_mad<L>(sl, lane, scratch + warp * prox_scratch<L>());
                 if (lane == 0) atomicAdd(sig_log + (long long)cur_slot * batch + img, sig);
+                if (warp == 0) trace(302);
                 prox_line_forward<L>(sl, lane, st);
             }
             __syncthreads();
+            trace(305);
             if (xrec && mine > 0 && threadIdx.x == 0) {
                 fence_proxy_async_smem();              // the lines were read / written through the generic proxy
                 const unsigned total = (unsigned)(mine * L * sizeof(float));
@@ -1046,13 +1067,14 @@ __device__ __forceinline__ void prox_phases(float* lines, int mine, long long fi
                     bulk_g2s(reinterpret_cast<char*>(lines) + off, reinterpret_cast<const char*>(xrec + first * L) + off, n, xbar);
                 }
             }
-            __threadfence();
-            cooperative_groups::this_grid().sync();
+            grid_sync();
+            trace(303);
             if (advance && blockIdx.x == 0 && threadIdx.x < n_advance) advance[threadIdx.x] += 1;
             if (active) {
                 const double se = __ldcg(sig_log + (long long)cur_slot * batch + img) / (double)nlines;
                 const float sigma = (se > 0.0) ? (float)(se * (double)sigma_modifier) : fallback_sigma;
                 if (xrec) mbar_wait(xbar, 0);
+                if (warp == 0) trace(306);
                 float err = prox_line_inverse<L>(st, reinterpret_cast<float*>(scratch + warp * prox_scratch<L>()), lane, sigma * sigma,
                                                  reinterpret_cast<float4*>(zout + gl * L),
                                                  xrec ? reinterpret_cast<const float4*>(sl) : nullptr);
@@ -1066,8 +1088,7 @@ __device__ __forceinline__ void prox_phases(float* lines, int mine, long long fi
     }
     prox_phase_sigma<L>(lines, mine, first, nlines, batch, sig_log, cur_slot, scratch);
     __syncthreads();
-    __threadfence();
-    cooperative_groups::this_grid().sync();
+    grid_sync();
     // end-of-iteration counters (pnp_advance) folded in: every CTA has read *slot before the barrier above, and
     // nothing else of this iteration reads them any more
     if (advance && blockIdx.x == 0 && threadIdx.x < n_advance) advance[threadIdx.x] += 1;
@@ -1078,7 +1099,8 @@ template <int L>
 __global__ void __launch_bounds__(512, 1)
 k_prox_wavelet_fused(const float* __restrict__ zin, float* __restrict__ zout, const float* __restrict__ xrec,
                      int nlines, int batch, int lines_per_cta, float sigma_modifier, float fallback_sigma,
-                     double* __restrict__ sig_log, double* __restrict__ mse_log, const int* __restrict__ slot) {
+                     double* __restrict__ sig_log, double* __restrict__ mse_log, const int* __restrict__ slot,
+                     unsigned* __restrict__ gbar) {
     using C = HaarSub<L>;
     constexpr int VPL = C::VPL, LEVELS = C::LEVELS, XL = C::XL, LIN = C::LIN, SB = C::SB, NSB = C::NSB;
     constexpr float RS2 = 0.70710678118654752f;
@@ -1089,6 +1111,8 @@ k_prox_wavelet_fused(const float* __restrict__ zin, float* __restrict__ zout, co
     const long long first = (long long)blockIdx.x * lines_per_cta;
     long long mine = total - first;
     mine = mine < 0 ? 0 : (mine > lines_per_cta ? lines_per_cta : mine);
+    griddep_wait();
+    griddep_launch();
     const int cur_slot = slot ? *slot : 0;
 
     // ---- stage my lines (contiguous in memory) ----
@@ -1111,7 +1135,7 @@ k_prox_wavelet_fused(const float* __restrict__ zin, float* __restrict__ zout, co
 
     // ---- sigma estimate, grid-wide mean, BayesShrink of the resident lines ----
     prox_phases<L>(lines, (int)mine, first, nlines, batch, zout, xrec, sigma_modifier, fallback_sigma, sig_log, mse_log, cur_slot,
-                   scratch, &xbar, nullptr, 0);
+                   scratch, &xbar, nullptr, 0, gbar);
 }
 
 }  // namespace pnp

@@ -147,6 +147,9 @@ class Engine:
                 if mb_source != 'host':          # 'host' stages through the ring of the look-ahead draws (below)
                     self.idx_host = torch.empty(self.B + n_extra_ints, dtype=torch.int32).pin_memory()
                 self.idx_dev = torch.zeros(self.B + n_extra_ints, dtype=torch.int32, device=self.dev)
+            self.barrier_ws = torch.zeros(2, dtype=torch.int32, device=self.dev)   # software grid barrier of chained launches
+        self.chain = False          # set while an epoch graph is captured: passes use programmatic dependent launch
+        self.sw_barrier = False     # set while an epoch graph is captured: the tail kernel uses the software grid barrier
         self.slot_ptr = self.counters[0:1]
         self.cursor_ptr = self.counters[1:2]
         self.draw_ptr = self.counters[2:3]

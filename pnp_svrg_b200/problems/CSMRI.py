@@ -123,9 +123,11 @@ class CSMRI(Problem):
                                                     D.ptr(counter), D.ptr(idx_out), int(bool(clear)), D.stream()))
 
     _inpass_sel = True      # the forward line pass can build the minibatch selection itself (sel_job)
+    _chain_ok = True        # the passes take chain=True (programmatic dependent launch)
 
     def _dev_grad(self, a, b=None, sel=None, with_y=True, gscale=1.0, gscale_ptr=None, step=0.0, step_ptr=None,
-                  g_out=None, vadd=None, v_out=None, z_in=None, z_out=None, phases=0, clear_sel=False, sel_job=None):
+                  g_out=None, vadd=None, v_out=None, z_in=None, z_out=None, phases=0, clear_sel=False, sel_job=None,
+                  chain=False):
         """g = Re(ifft2(sel o fft2(a - b) - Ysel)) * gscale ; v = g + vadd ; z_out = z_in - step*v.
         ``sel_job`` = dict(count, idx | None, cursor, seed, counter): pass 1 also builds the minibatch selection in
         ``sel`` (all zero on entry) -- from explicit positions ``idx`` or by the device sampler."""
@@ -147,18 +149,18 @@ class CSMRI(Problem):
             Y1n=D.ptr(self._Y1n) if with_y else None, Y2n=D.ptr(self._Y2n) if with_y else None,
             gscale=float(gscale), gscale_ptr=D.ptr(gscale_ptr), step=float(step), step_ptr=D.ptr(step_ptr),
             g_out=D.ptr(g_out), vadd=D.ptr(vadd), v_out=D.ptr(v_out), z_in=D.ptr(z_in), z_out=D.ptr(z_out), phases=int(phases),
-            clear_bits=int(bool(clear_sel) and sel is not None), **sj)
+            clear_bits=int(bool(clear_sel) and sel is not None), flags=1 if chain else 0, **sj)
         _lib.check(_lib.load().pnp_csmri_grad(C.byref(args), D.stream()))
 
     def _dev_update_prox(self, gscale, step_ptr, vadd, z_in, z_out, sig_log, sigma_modifier, fallback_sigma, xrec, mse_log,
-                         slot, advance=None, n_advance=0):
+                         slot, advance=None, n_advance=0, barrier_ws=None, chain=False):
         """Tail of an inner iteration in one cooperative launch, after ``_dev_grad(..., phases=3)`` left the masked
         spectrum in the scratch: inverse line pass + update + sigma estimate + wavelet prox + PSNR
         (pnp_csmri_update_prox).  Returns False when the image does not suit the resident-line kernel."""
         rc = _lib.load().pnp_csmri_update_prox(D.ptr(self._S), self.H, self.W, float(gscale), 0.0, D.ptr(step_ptr), D.ptr(vadd),
                                                D.ptr(z_in), D.ptr(z_out), D.ptr(sig_log), float(sigma_modifier),
                                                float(fallback_sigma), D.ptr(xrec), D.ptr(mse_log), D.ptr(slot), D.ptr(advance),
-                                               int(n_advance), D.stream())
+                                               int(n_advance), D.ptr(barrier_ws), int(bool(chain)), D.stream())
         if rc == -4:            # PNP_ERR_UNSUPPORTED
             return False
         _lib.check(rc)

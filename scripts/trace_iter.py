@@ -33,6 +33,8 @@ def read():
     return t, tag, cta, sm
 
 
+if os.environ.get('DBG'):
+    eng.lib.pnp_debug_set(3, int(os.environ['DBG']))
 for _ in range(3):
     run.epoch()
 eng.stream.synchronize()
@@ -81,8 +83,17 @@ for k, (a, b) in {'r2c_item': (101, 102), 'cols_item': (201, 202)}.items():
         tb = np.sort(rel[(tag == b) & (cta == c)])
         d.extend(list(tb[:len(ta)] - ta[:len(tb)]))
     out[k + '_us'] = {'mean': float(np.mean(d)), 'max': float(np.max(d)), 'n': len(d)}
+    first, later = [], []
+    for c in np.unique(cta[tag == a]):
+        ta = np.sort(rel[(tag == a) & (cta == c)])
+        tb = np.sort(rel[(tag == b) & (cta == c)])
+        dd = list(tb[:len(ta)] - ta[:len(tb)])
+        first.extend(dd[:1])
+        later.extend(dd[1:])
+    out[k + '_us']['first_item_mean'] = float(np.mean(first)) if first else None
+    out[k + '_us']['later_items_mean'] = float(np.mean(later)) if later else None
 ph = {}
-names = {300: 'start', 310: 'fft_round0_done', 311: 'fft_round1_done', 301: 'fft_done', 302: 'sigma_done', 303: 'barrier_done', 304: 'shrink_done'}
+names = {300: 'start', 310: 'fft_round0_done', 311: 'fft_round1_done', 301: 'fft_done', 302: 'sigma_done(warp0)', 305: 'haar_forward_done', 303: 'barrier_done', 306: 'xrec_landed(warp0)', 320: 'thresholds(warp0)', 321: 'inverse_top(warp0)', 323: 'chunk_loop_first_pass(warp0)', 322: 'stored(warp0)', 304: 'shrink_done'}
 for tg, nm in names.items():
     v = rel[tag == tg]
     if len(v):
