@@ -45,6 +45,8 @@ def parse():
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--no-breakdown', action='store_true')
     ap.add_argument('--cpu-iters', type=int, default=0, help='inner iterations of the CPU sample (default: one epoch)')
+    ap.add_argument('--sections', default='small,sweep,sharded,configs_2_3',
+                    help='extra sections of the line (bench_sections.py): the other BASELINE.json configurations; "" = none')
     return ap.parse_args()
 
 
@@ -60,6 +62,14 @@ def workload(a):
         'l2': 'flushed between steps (256 MiB write, outside the per-step event pairs)',
         'parallelism': 'dp%d independent reconstructions, no collective' % a.gpus,
     }
+
+
+def hbm_peak():
+    """(GB/s, source): the measured copy bandwidth of this pool's B200s when the driver wrote it, else the guide's fallback"""
+    path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(path):
+        return json.load(open(path))['hbm_gbs'], 'measured (MEASURED_PEAKS.json hbm_gbs, burst copy)'
+    return 6650.0, 'fallback (B200_PROFILING.md)'
 
 
 def make_image(H, seed):
@@ -270,6 +280,30 @@ def run_b200(a, cfg, rank, world, local_rank):
             line['e2e'] = e2e
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
         line['cpu_baseline'] = cpu_baseline(cfg, a.cpu_iters or T2)
+    # ---- the other configurations of BASELINE.json, in the same run (every rank takes part in the collective ones) ----
+    if a.size == 2048:
+        import bench_sections as BS
+        want = [s for s in a.sections.split(',') if s]
+        for name in want:
+            t0 = time.time()
+            try:
+                if name == 'small':
+                    sec = BS.small(rank, world, dev)
+                elif name == 'sweep':
+                    sec = BS.sweep(rank, world, dev, with_cpu=not a.no_cpu_baseline)
+                elif name == 'sharded':
+                    sec = BS.sharded(rank, world, dev)
+                elif name == 'configs_2_3':
+                    sec = BS.configs_2_3(rank, world, dev)
+                else:
+                    raise ValueError('unknown section %r' % name)
+            except Exception as e:                       # a failing extra must not take the headline number down
+                sec = {'error': repr(e)}
+                if world > 1:
+                    raise
+            if rank == 0 and sec is not None:
+                sec['section_seconds'] = time.time() - t0
+                line[name] = sec
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -282,11 +316,7 @@ def breakdown(a, cfg, run, us_inner_graph):
     import torch
     eng, p, d = run.eng, run.problem, run.denoiser
     T2, N, B = cfg['T2'], cfg['H'] * cfg['W'], cfg['mini_batch_size']
-    peaks_path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
-    if os.path.exists(peaks_path):
-        peak, peak_src = json.load(open(peaks_path))['hbm_gbs'], 'measured (MEASURED_PEAKS.json hbm_gbs, burst copy)'
-    else:
-        peak, peak_src = 6650.0, 'fallback (B200_PROFILING.md)'
+    peak, peak_src = hbm_peak()
     eng.resolve()
     events = []
     n_iter = min(a.steps * T2, 100)
@@ -375,18 +405,23 @@ def ncu_traffic(kernel):
 
 
 def run_e2e(a, cfg, prob, dev, world, fast=True):
-    """Public API, host buffers: algorithms.pnp_svrg with host-drawn minibatches copied from pinned
-    memory every inner iteration and the PSNR of every iterate read back (fast=True: graph replay, read-back
-    in batches of 64 iterations; fast=False: the reference's loop shape, read-back after every iteration)."""
+    """Public API, host buffers: algorithms.pnp_svrg with host-drawn minibatches.  fast=True: whole epochs as CUDA
+    graphs; the T2 minibatches of the next epoch are drawn by native worker threads into pinned memory and copied
+    (one H2D copy per inner iteration, on a copy stream) while the current epoch runs; PSNR + sigma logs of every
+    iterate are read back; Xinit upload (pinned staging) and z download are inside the timed region.  fast=False: the
+    reference's loop shape, one launch sequence and one read-back per iteration.  An e2e "step" is an epoch like a
+    `value` step; the call runs max(steps, 100) epochs so that its fixed cost (allocation, capture, upload, download:
+    about 10 ms) is amortised as it would be in a real reconstruction."""
     import torch
     import torch.distributed as dist
     from pnp_svrg_b200.algorithms import pnp_svrg
     from pnp_svrg_b200.denoisers import TVDenoiser
     T2, B = cfg['T2'], cfg['mini_batch_size']
-    iters = a.steps * T2
+    epochs = max(a.steps, 100) if fast else max(a.steps, 20)
+    iters = epochs * T2
     kw = dict(eta=cfg['eta'], T2=T2, mini_batch_size=B, vr_mode='paper', verbose=False, converge_check=False,
               mb_source='host', mb_seed=11, fast=fast)
-    pnp_svrg(prob, TVDenoiser(), tt=1e9, max_iters=min(iters, 2 * T2), **kw)          # warm-up
+    pnp_svrg(prob, TVDenoiser(), tt=1e9, max_iters=2 * T2, **kw)          # warm-up
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize(dev)
@@ -398,12 +433,12 @@ def run_e2e(a, cfg, prob, dev, world, fast=True):
         t = torch.tensor([dt], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dt = float(t.item())
-    return {'value': world * iters / dt, 'unit': UNIT, 'h2d_bytes_per_step': T2 * 4 * B + 4 * prob.N // a.steps,
-            'd2h_bytes_per_step': T2 * 16 + 4 * prob.N // a.steps,      # logs + the final iterate (float32 on the wire) 'seconds': dt, 'inner_iterations': iters,
-            'api': "pnp_svrg_b200.algorithms.pnp_svrg(problem, denoiser, ..., mb_source='host', fast=%s) -- minibatch drawn "
-                   "on the host, copied from pinned memory each inner iteration; PSNR + sigma of every iterate read back "
-                   "%s; Xinit upload and final z download included"
-                   % (fast, 'in batches of 64 iterations (graph replay)' if fast else 'after every iteration (eager loop)'),
+    return {'value': world * iters / dt, 'unit': UNIT,
+            'h2d_bytes_per_step': T2 * 4 * B + 4 * prob.N // epochs,          # minibatch positions + the share of the Xinit upload
+            'd2h_bytes_per_step': T2 * 16 + 4 * prob.N // epochs,             # PSNR / sigma logs + the share of the z download
+            'steps': epochs, 'inner_iterations': iters, 'seconds': dt,
+            'api': "pnp_svrg_b200.algorithms.pnp_svrg(problem, denoiser, eta, tt, T2, mini_batch_size, vr_mode='paper', "
+                   "mb_source='host', fast=%s)" % fast,
             'psnr_last': float(out['psnr_per_iter'][-1])}
 
 

@@ -1,0 +1,286 @@
+"""Extra sections of the bench line (bench.py imports this): the other configurations BASELINE.json names, measured in
+the SAME run so that they reach the driver's records.
+
+  small         config 1: PnP-SVRG CSMRI 256x256, wavelet prox -- device-resident it/s and the public-API e2e
+  sweep         config 4: 12 images x 10 sampling ratios x 7 SNRs = 840 CSMRI 256x256 reconstructions (200 inner
+                iterations each) partitioned over the ranks, recon/s; at N = 1 also the reference's
+                multiprocessing.Pool(min(12, cores)) pattern (script_diff_sampratio_set12.py:142-146) on a bounded sample
+  sharded       config 5: CSMRI 2048x2048 + DnCNN-17 prox on tensor cores, measurements sharded over the ranks for the
+                snapshot gradient: partial gradient + NCCL all-reduce vs the unsharded gradient, all-reduce bus GB/s,
+                rel-L2 of the summed gradient, inner it/s with the CNN prox
+  configs_2_3   config 2 (PnP-SAGA Deblur 256x256 + NLM) and config 3 (PnP-SVRG coded-diffraction PR 256x256 + DnCNN-17)
+Everything is synthetic (no network, no Set12 on the GPU box); every section says what it ran."""
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (ROOT, os.path.join(ROOT, 'tests')):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+
+def _barrier(world, dev):
+    import torch
+    import torch.distributed as dist
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+
+
+# ------------------------------------------------------------------------------------------------ config 1
+def small(rank, world, dev, steps=200):
+    """256x256 single image (launch bound: ~2 MB per iteration): device-resident epochs and the public call."""
+    import torch
+    import bench
+    from pnp_svrg_b200.algorithms import pnp_svrg
+    from pnp_svrg_b200.denoisers import TVDenoiser
+    import argparse
+    if rank != 0:
+        return None
+    a = argparse.Namespace(size=256, batch_size=0, sample_prob=0.3, eta=0.0, T2=10, gpus=1)
+    cfg = bench.workload(a)
+    prob, run = bench.make_run(cfg, seed=0)
+    eng = run.eng
+    eng.time_log.append(0.0)
+    eng.psnr_log.append(eng.psnr_of(eng.z))
+    for _ in range(5):
+        run.epoch()
+    eng.resolve()
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(eng.stream)
+    for _ in range(steps):
+        run.epoch()
+    e1.record(eng.stream)
+    torch.cuda.synchronize(dev)
+    ms = e0.elapsed_time(e1)
+    eng.resolve()
+    psnr = eng.psnr_log
+    run.close()
+    T2 = cfg['T2']
+    kw = dict(eta=cfg['eta'], T2=T2, mini_batch_size=cfg['mini_batch_size'], vr_mode='paper', verbose=False,
+              converge_check=False, mb_source='host', mb_seed=5, fast=True)
+    pnp_svrg(prob, TVDenoiser(), tt=1e9, max_iters=2 * T2, **kw)
+    torch.cuda.synchronize(dev)
+    t0 = time.time()
+    out = pnp_svrg(prob, TVDenoiser(), tt=1e9, max_iters=steps * T2, **kw)
+    torch.cuda.synchronize(dev)
+    dt = time.time() - t0
+    N = cfg['H'] * cfg['W']
+    us = 1e3 * ms / (steps * T2)
+    return {'workload': cfg['workload'], 'value': steps * T2 / (ms * 1e-3), 'unit': 'inner_iterations/s', 'us_per_inner_iteration': us,
+            'steps': steps, 'e2e_value': steps * T2 / dt, 'psnr_first_last': [float(psnr[0]), float(psnr[-1])],
+            'e2e_psnr_last': float(out['psnr_per_iter'][-1]),
+            'roofline_iteration_frac': 28.125 * N / (us * 1e-6) / 1e9 / bench.hbm_peak()[0],
+            'note': 'one 256x256 image is launch / latency bound (1.8 MB per iteration); the sweeps batch many images per launch'}
+
+
+# ------------------------------------------------------------------------------------------------ config 4
+def _sweep_cpu_job(args):
+    """one reconstruction of the sweep with the NumPy oracle port, as the reference's process_img would run it"""
+    seed, alpha, snr, iters, T2, B = args
+    from conftest import synth_image
+    from oracle import algorithms_port as AP
+    from oracle.problems_port import CSMRIPort
+    np.random.seed(1000 + seed)
+    p = CSMRIPort(synth_image(256, 256, seed), H=256, W=256, sample_prob=alpha, snr=snr)
+    b = min(B, p.M0)
+    o = AP.pnp_svrg(p, AP.TVPort(), eta=min(0.15 * p.M0, 3.0 * b), budget=iters, T2=T2, mini_batch_size=b, vr_mode='paper',
+                    converge_check=False)
+    return float(o['psnr_per_iter'][-1])
+
+
+def sweep_cpu_baseline(iters=200, T2=10, B=1000):
+    """The reference's pattern: multiprocessing.Pool(len(SET12_LIST)).map(process_img, ...) -- one process per image
+    (script_diff_sampratio_set12.py:142-146) -- here Pool(min(12, cores)) over 12 jobs of the grid (one per image)."""
+    import multiprocessing as mp
+    cores = len(os.sched_getaffinity(0))
+    nproc = min(12, cores)
+    jobs = [(i, [0.3, 0.5, 0.7, 1.0][i % 4], [10., 20., 30.][i % 3], iters, T2, B) for i in range(12)]
+    ctx = mp.get_context('fork')
+    t0 = time.time()
+    with ctx.Pool(nproc) as pool:
+        res = pool.map(_sweep_cpu_job, jobs)
+    dt = time.time() - t0
+    return {'value': len(jobs) / dt, 'unit': 'recon/s', 'cores': nproc, 'kind': 'port', 'seconds': dt,
+            'sample': '12 of the 840 jobs (one per image, %d inner iterations each) through multiprocessing.Pool(%d), NumPy '
+                      'float64 oracle port' % (iters, nproc), 'mean_psnr_final': float(np.mean(res))}
+
+
+def sweep(rank, world, dev, iters=200, size=256, batch=56, with_cpu=True):
+    import torch
+    from conftest import synth_image
+    from pnp_svrg_b200 import sweep as SW
+    images = {i: synth_image(size, size, i) for i in range(12)}
+    jobs = SW.make_jobs(list(range(12)))                     # 12 x 10 x 7 = 840
+    batch_runner = lambda group: SW.reconstruct_batch(group, H=size, W=size, iters=iters, images=images, construct='device')
+    batch_runner(jobs[:batch])                               # warm-up: allocations, graph capture
+    _barrier(world, dev)
+    t0 = time.time()
+    recs = SW.run_partitioned_batched(jobs, batch_runner, rank, world, batch=batch, gather=True)
+    _barrier(world, dev)
+    dt = time.time() - t0
+    if world > 1:
+        import torch.distributed as dist
+        t = torch.tensor([dt], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = float(t.item())
+    if rank != 0:
+        return None
+    ok = [r for r in recs if 'error' not in r]
+    out = {'workload': '12 synthetic images x 10 sampling ratios x 7 SNRs = %d CSMRI %dx%d PnP-SVRG (paper mode) + wavelet-prox '
+                       'reconstructions, %d inner iterations each, batches of %d per launch, problems built on the device; '
+                       'jobs dealt round-robin over the ranks, no data-path collective' % (len(jobs), size, size, iters, batch),
+           'value': len(recs) / dt, 'unit': 'recon/s', 'jobs': len(recs), 'failed': len(recs) - len(ok), 'seconds': dt, 'n_gpus': world,
+           'inner_iterations_per_s': len(recs) * iters / dt,
+           'mean_psnr_gain_db': float(np.mean([r['psnr_final'] - r['psnr_init'] for r in ok])) if ok else None}
+    if with_cpu and world == 1:
+        out['cpu_baseline'] = sweep_cpu_baseline(iters=iters)
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ config 5
+def sharded(rank, world, dev, size=2048, inner=20):
+    """Config 5.  Every rank builds the SAME problem (same seed) and holds the measurements of its band of packed ky rows;
+    the snapshot gradient is the all-reduced sum of the partial gradients; the inner loop is replicated."""
+    import torch
+    import torch.distributed as dist
+    from conftest import synth_image
+    from pnp_svrg_b200 import device as D
+    from pnp_svrg_b200.algorithms import SvrgRun
+    from pnp_svrg_b200.denoisers import RealSN_DnCNNDenoiser
+    from pnp_svrg_b200.problems import CSMRI
+    from test_gpu_cnn import _random_dncnn_sd
+    H = size
+    img = synth_image(H, H, 0)
+    np.random.seed(0)
+    full = CSMRI(image=img, H=H, W=H, sample_prob=0.3, snr=20.)
+    np.random.seed(0)
+    part = CSMRI(image=img, H=H, W=H, sample_prob=0.3, snr=20., shard=(rank, world)) if world > 1 else full
+    z = D.to_lines(full.Xinit, H, H, dev)
+    g_full, g_part = torch.empty_like(z), torch.empty_like(z)
+
+    def timed(fn, n=20):
+        for _ in range(3):
+            fn()
+        _barrier(world, dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        torch.cuda.synchronize(dev)
+        t = torch.tensor([e0.elapsed_time(e1) * 1e3 / n], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    us_full = timed(lambda: full._dev_grad(z, gscale=1.0 / full.M0, g_out=g_full))
+    out = {'workload': 'CSMRI %dx%d, p=0.3, snr 20 dB; snapshot gradient with the measurements in %d band(s) of packed ky rows '
+                       '(one per rank) + NCCL all-reduce of 4N bytes; inner loop replicated, DnCNN-17 prox (bf16, tcgen05), '
+                       'T2=10, B=100000' % (H, H, world),
+           'n_gpus': world, 'snapshot_us_unsharded': us_full}
+    if world > 1:
+        us_part = timed(lambda: part._dev_grad(z, gscale=1.0 / part.M0, g_out=g_part, partial_ok=True))
+        us_ar = timed(lambda: dist.all_reduce(g_part, op=dist.ReduceOp.SUM))
+        part._dev_grad(z, gscale=1.0 / part.M0, g_out=g_part, partial_ok=True)
+        dist.all_reduce(g_part, op=dist.ReduceOp.SUM)
+        err = float((torch.linalg.vector_norm(g_part - g_full) / torch.linalg.vector_norm(g_full)).item())
+        t = torch.tensor([err], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        nbytes = 4.0 * H * H
+        out.update({'snapshot_us_partial': us_part, 'allreduce_us': us_ar,
+                    'allreduce_bus_gb_s': 2.0 * (world - 1) / world * nbytes / (us_ar * 1e-6) / 1e9,
+                    'snapshot_us_sharded_total': us_part + us_ar, 'rel_l2_sum_vs_unsharded': float(t.item()),
+                    'speedup_vs_unsharded': us_full / (us_part + us_ar),
+                    'verdict': 'sharding the snapshot shards the HBM-resident measurements, not time: a rank still runs both '
+                               'full-size line passes, only the column pass shrinks to its band, and the all-reduce of the '
+                               '4N-byte gradient costs more than the whole unsharded gradient at this size'})
+    # inner iterations with the CNN prox (what an epoch costs next to the snapshot), on the rank's problem object
+    sd = _random_dncnn_sd(17, True, False, seed=1)
+    last = max((k for k in sd if k.endswith('.weight') and sd[k].ndim == 4), key=lambda k: int(k.split('.')[-2]))
+    sd[last] = sd[last] * 1e-3                  # random weights are no denoiser: keep the residual small
+    den = RealSN_DnCNNDenoiser('DnCNN', 15, state_dict=sd, precision='bf16')
+    run = SvrgRun(part, den, 0.15 * part.M0, 10, 100000, vr_mode='paper', mb_source='device', mb_seed=rank, fast=True)
+    eng = run.eng
+    with torch.cuda.stream(eng.stream):
+        eng.set_step(0.15 * part.M0)
+        run.snapshot()
+        for _ in range(2):
+            run.fast_ops()
+    eng.stream.synchronize()
+    _barrier(world, dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.cuda.stream(eng.stream):
+        e0.record(eng.stream)
+        run.snapshot()
+        for _ in range(inner):
+            run.fast_ops()
+        e1.record(eng.stream)
+    eng.stream.synchronize()
+    us_it = e0.elapsed_time(e1) * 1e3 / inner
+    t = torch.tensor([us_it], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    flop = 1108224.0 * H * H
+    out.update({'inner_us_with_dncnn_prox': float(t.item()), 'inner_iterations_per_s_per_replica': 1e6 / float(t.item()),
+                'dncnn_tflops_lower_bound': flop / (float(t.item()) * 1e-6) / 1e12,
+                'note_inner': 'one snapshot + %d eager inner iterations (gradient passes + DnCNN-17 forward); the CNN is '
+                              '1.108 MFLOP/px, so the iteration is tensor-core bound' % inner})
+    run.close()
+    return out if rank == 0 else None
+
+
+# ------------------------------------------------------------------------------------------------ configs 2, 3
+def configs_2_3(rank, world, dev):
+    import torch
+    from conftest import synth_image
+    from pnp_svrg_b200.algorithms import pnp_saga, pnp_svrg
+    from pnp_svrg_b200.denoisers import NLMDenoiser, RealSN_DnCNNDenoiser
+    from pnp_svrg_b200.problems import Deblur, PhaseRetrieval
+    from test_gpu_cnn import _random_dncnn_sd
+    if rank != 0:
+        return None
+
+    def timed(fn, iters):
+        fn(max(iters // 4, 1))
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        out = fn(iters)
+        torch.cuda.synchronize(dev)
+        return iters / (time.perf_counter() - t0), out
+    res = {}
+    H = 256
+    img = synth_image(H, H, 0)
+    np.random.seed(0)
+    p = PhaseRetrieval(image=img, H=H, W=H, model='cdp', n_masks=4, snr=20.)
+    sd = _random_dncnn_sd(17, True, False, seed=1)
+    last = max((k for k in sd if k.endswith('.weight') and sd[k].ndim == 4), key=lambda k: int(k.split('.')[-2]))
+    sd[last] = sd[last] * 1e-3
+    den = RealSN_DnCNNDenoiser('DnCNN', 15, state_dict=sd, precision='bf16')
+    eta = 0.03 * p.N / (3 * np.mean(p.X ** 2))
+    run = lambda n: pnp_svrg(p, den, eta=eta, tt=1e9, T2=8, mini_batch_size=800, lr_decay=0.99, max_iters=n, vr_mode='paper',
+                             converge_check=False, verbose=False, mb_source='device', fast=True)
+    ips, out = timed(run, 400)
+    res['config3_cdp256_svrg_dncnn17_bf16'] = {
+        'value': ips, 'unit': 'inner_iterations/s', 'psnr_first': float(out['psnr_per_iter'][0]), 'psnr_last': float(out['psnr_per_iter'][-1]),
+        'workload': 'PnP-SVRG, coded-diffraction phase retrieval 256x256 (4 masks, intensity loss), DnCNN-17 prox on tensor '
+                    'cores (bf16, random weights), T2=8, B=800, lr_decay 0.99, public API, device-drawn minibatches'}
+    yy, xx = np.mgrid[0:H, 0:H]
+    k = np.zeros((H, H))
+    k[H // 2 - 12:H // 2 + 13, H // 2 - 12:H // 2 + 13] = np.round(255 * np.exp(-((yy[:25, :25] - 12) ** 2 + (xx[:25, :25] - 12) ** 2) / 50.0))
+    np.random.seed(0)
+    q = Deblur(image=img, H=H, W=H, kernel=k.astype(np.uint8), scale_percent=50, snr=20.)
+    nlm = NLMDenoiser()
+    lip = (np.abs(np.fft.fft(q.B)).max() * np.sqrt(q.N)) ** 2
+    run2 = lambda n: pnp_saga(q, nlm, eta=0.5 * q.M / lip, tt=1e9, mini_batch_size=100, hist_size=10, max_iters=n, converge_check=False,
+                              verbose=False, mb_source='device', fast=True)
+    ips2, out2 = timed(run2, 200)
+    res['config2_deblur256_saga_nlm'] = {
+        'value': ips2, 'unit': 'iterations/s', 'psnr_first': float(out2['psnr_per_iter'][0]), 'psnr_last': float(out2['psnr_per_iter'][-1]),
+        'workload': 'PnP-SAGA, Deblur 256x256 (25x25 Gaussian kernel image, scale 50 %), NLM prox (patch 4 -> 5, distance 5), '
+                    'B=100, hist_size=10, public API, device-drawn minibatches'}
+    return res

@@ -85,6 +85,11 @@ typedef struct {
     const int* sel_counter;
     int sel_min_m0;
     int flags;                    /* PNP_FLAG_* */
+    /* Measurement shard (config 5): when row_hi > row_lo only the packed ky rows kyp in [row_lo, row_hi) of the half
+     * spectrum are produced, masked and inverted -- kyp = min(ky, H - ky); row 0 also carries the Nyquist row -- i.e.
+     * the result is the PARTIAL gradient of the measurements in that band (`bits` must select nothing outside it).
+     * Pass 1 stores, pass 2 transforms and pass 3 loads only those rows.  0, 0: all rows. */
+    int row_lo, row_hi;
 } pnp_csmri_grad_args;
 /* flags bit 0: launch the passes with programmatic dependent launch -- each kernel may begin (prologue, loads of data
  * older than its predecessor) while the previous kernel on the stream is finishing, and waits for it before it reads

@@ -29,6 +29,7 @@ class CsmriGradArgs(C.Structure):
         ('sel_count', C.c_int), ('sel_idx', C.c_void_p), ('sel_idx_img_stride', C.c_longlong), ('sel_cursor', C.c_void_p),
         ('sel_support', C.c_void_p), ('sel_m0', C.c_void_p), ('sel_support_img_stride', C.c_longlong),
         ('sel_seed', C.c_uint), ('sel_counter', C.c_void_p), ('sel_min_m0', C.c_int), ('flags', C.c_int),
+        ('row_lo', C.c_int), ('row_hi', C.c_int),
     ]
 
 

@@ -319,6 +319,8 @@ class SvrgRun:
         self.i = 0                      # outer (epoch) index
         self.draw = _host_draw_fn(eng) if (self.paper or mb_source == 'legacy') else None
         self._epoch_graphs = {}
+        self._inflight = []             # one event per epoch in flight
+        self.max_ahead = 4              # epochs the host may run ahead of the GPU
         self._epoch_sets = None         # device index buffers [set][T2][B] for host-drawn minibatches
         self._step_on_device = False    # epoch graphs keep eta * lr_decay**i on the device
 
@@ -326,9 +328,13 @@ class SvrgRun:
     def snapshot(self):
         """mu = grad_full(z) ; w = copy(z)          (pnp_svrg.py:32-35)"""
         eng, problem = self.eng, self.problem
-        _grad_update(eng, self.z, None, None, True, 1.0 / _full_norm(problem), g_out=self.mu)
         if getattr(problem, 'shard', None) is not None:
-            problem._snapshot_allreduce(self.mu)     # measurement-sharded snapshot: partial sums -> full gradient
+            # measurement-sharded snapshot: every rank transforms its band of packed ky rows, the partial gradients are
+            # summed by one NCCL all-reduce of 4N bytes
+            _grad_update(eng, self.z, None, None, True, 1.0 / _full_norm(problem), g_out=self.mu, partial_ok=True)
+            problem._snapshot_allreduce(self.mu)
+        else:
+            _grad_update(eng, self.z, None, None, True, 1.0 / _full_norm(problem), g_out=self.mu)
         eng.copy(self.w, self.z)
 
     def grad_ops(self):
@@ -458,6 +464,14 @@ class SvrgRun:
             ev = self._ev_done[s_] or torch.cuda.Event()
             ev.record(eng.stream)
             self._ev_done[s_] = ev
+        # bound how far the host runs ahead of the GPU without draining the stream: wait for the epoch launched
+        # `max_ahead` epochs ago (the wall-clock budget tt is looked at between epochs)
+        ring = self._inflight
+        ev = torch.cuda.Event()
+        ev.record(eng.stream)
+        ring.append(ev)
+        if len(ring) > self.max_ahead:
+            ring.pop(0).synchronize()
         eng.defer_slots(self.T2)
         self.denoiser.t += self.T2
         self._epochs_launched += 1
@@ -484,11 +498,10 @@ class SvrgRun:
         while budget.alive() and not stop:
             left = budget.left()
             if epochs and (left is None or left >= T2):
+                self.max_ahead = max(1, min(8, int(sync_every) // T2))    # run-ahead bound, in epochs (wall-clock budget tt)
                 self.epoch()
                 budget.calls += T2
                 psnr_z = None
-                if eng.since_sync >= sync_every:
-                    eng.resolve()          # bounds how far the host runs ahead of the GPU (wall-clock budget tt)
                 continue
             t_outer = time.time()
             with torch.cuda.stream(eng.stream):

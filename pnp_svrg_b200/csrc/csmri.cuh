@@ -150,7 +150,7 @@ template <int L, int GP> __host__ __device__ constexpr int lines_stage_off() { r
 template <int L, int GP>
 __global__ void __launch_bounds__(GP * (L / FftPlan<L>::EPT), (GP * (L / FftPlan<L>::EPT) >= 256 ? 2 : 4))
 k_lines_r2c(const float* __restrict__ a, const float* __restrict__ b, float2* __restrict__ S,
-            int nlines, long long img_stride, SelJob sj) {
+            int nlines, long long img_stride, SelJob sj, int row_lo, int row_hi) {
     constexpr int T = fft_threads<L>();
     constexpr int EPT = FftPlan<L>::EPT;
     constexpr int PL = fft_plane<L>();
@@ -224,6 +224,7 @@ k_lines_r2c(const float* __restrict__ a, const float* __restrict__ b, float2* __
         for (int i = threadIdx.x; i < GP * (L / 2); i += GP * T) {
             const int gg = i % GP, k = i / GP;
             if (pair0 + gg >= npairs) continue;
+            if (k < row_lo || k >= row_hi) continue;               // measurement shard: only the rank's packed ky rows are used
             const SmemBuf sg{smem + gg * GS, smem + gg * GS + PL};
             const float2 xk = sg.get(k);
             const float2 xm = sg.get(k == 0 ? L / 2 : L - k);
@@ -270,7 +271,8 @@ __global__ void __launch_bounds__(NC * (L / FftPlan<L>::EPT), (NC * (L / FftPlan
 k_cols_mask(float2* __restrict__ S, const unsigned char* __restrict__ bits,
             const float2* __restrict__ Y1, const float2* __restrict__ Y2,
             const float2* __restrict__ Y1n, const float2* __restrict__ Y2n,
-            int hp, long long bits_img_stride, long long y_img_stride, unsigned char* __restrict__ clear_bits) {
+            int hp, long long bits_img_stride, long long y_img_stride, unsigned char* __restrict__ clear_bits,
+            int row_lo, int row_hi) {
     constexpr int T = fft_threads<L>();
     constexpr int EPT = FftPlan<L>::EPT;
     constexpr int PL = fft_plane<L>();
@@ -287,15 +289,17 @@ k_cols_mask(float2* __restrict__ S, const unsigned char* __restrict__ bits,
     const bool use_y = Y1 != nullptr;
     const float2* y1i = use_y ? Y1 + (long long)img * y_img_stride : nullptr;
     const float2* y2i = use_y ? Y2 + (long long)img * y_img_stride : nullptr;
-    const int items = (hp - 1 + NC - 1) / NC;
+    // packed rows [c_lo, c_hi) (a measurement shard owns a band of them; everything for an unsharded problem)
+    const int c_lo = row_lo > 1 ? row_lo : 1, c_hi = row_hi < hp ? row_hi : hp;
+    const int items = c_hi > c_lo ? (c_hi - c_lo + NC - 1) / NC : 0;
 
     auto issue = [&](int item) {
-        int nc = hp - 1 - item * NC;
+        int nc = c_hi - c_lo - item * NC;
         nc = nc < NC ? nc : NC;
         const unsigned bytes = (unsigned)(nc * L * sizeof(float2));
         mbar_expect_tx(&bar, bytes + (unsigned)(nc * L));
-        bulk_g2s(stage, Si + (long long)(1 + item * NC) * L, bytes, &bar);
-        bulk_g2s(const_cast<unsigned char*>(stage_bits), bi + (long long)(1 + item * NC) * L, (unsigned)(nc * L), &bar);
+        bulk_g2s(stage, Si + (long long)(c_lo + item * NC) * L, bytes, &bar);
+        bulk_g2s(const_cast<unsigned char*>(stage_bits), bi + (long long)(c_lo + item * NC) * L, (unsigned)(nc * L), &bar);
     };
     trace(200, true);
     if (threadIdx.x == 0) { mbar_init(&bar, 1); mbar_fence_init(); }
@@ -311,8 +315,8 @@ k_cols_mask(float2* __restrict__ S, const unsigned char* __restrict__ bits,
     if (threadIdx.x == 0 && item < items) issue(item);
     unsigned parity = 0;
     for (; item < items; item += nct) {
-        const int col = 1 + item * NC + g;
-        const bool active = col < hp;
+        const int col = c_lo + item * NC + g;
+        const bool active = col < c_hi;
         const long long crow = (long long)(active ? col : 0) * L;
         unsigned long long bbp = 0ull;                                      // 4 selection bits per element
         float2 x[EPT];
@@ -356,7 +360,7 @@ k_cols_mask(float2* __restrict__ S, const unsigned char* __restrict__ bits,
     }
     trace(209);
 
-    if (blockIdx.x != 0) { trace_flush(); return; }
+    if (blockIdx.x != 0 || row_lo > 0) { trace_flush(); return; }
     // ---- packed column 0: C = FFT(DC + i * Nyq); split, select each row, re-pack ----
     {
         float2 x[EPT];
@@ -417,7 +421,7 @@ k_cols_mask(float2* __restrict__ S, const unsigned char* __restrict__ bits,
 // epilogue with its five optional pointers unrolls to >100 KiB of code and stalls on instruction fetch.
 template <int L, int GP, bool UPD>
 __global__ void __launch_bounds__(GP * (L / FftPlan<L>::EPT), (GP * (L / FftPlan<L>::EPT) >= 256 ? 2 : 4))
-k_lines_c2r(const float2* __restrict__ S, int nlines, long long img_stride, float inv_n, GradEpilogue ep) {
+k_lines_c2r(const float2* __restrict__ S, int nlines, long long img_stride, float inv_n, GradEpilogue ep, int row_lo, int row_hi) {
     constexpr int T = fft_threads<L>();
     constexpr int EPT = FftPlan<L>::EPT;
     constexpr int PL = fft_plane<L>();
@@ -450,7 +454,8 @@ k_lines_c2r(const float2* __restrict__ S, int nlines, long long img_stride, floa
         for (int n = 0; n < NQ; ++n) {
             const int i = threadIdx.x + n * GP * T;
             const int gg = i % GP, k = i / GP;
-            q[n] = (item * GP + gg < npairs) ? ldg_stream(S4 + (long long)k * W2 + item * GP + gg) : make_float4(0.f, 0.f, 0.f, 0.f);
+            q[n] = (item * GP + gg < npairs && k >= row_lo && k < row_hi) ? ldg_stream(S4 + (long long)k * W2 + item * GP + gg)
+                                                                          : make_float4(0.f, 0.f, 0.f, 0.f);
         }
     };
     auto issue = [&](int item) {                    // one thread: TMA bulk copies of the epilogue operands

@@ -186,7 +186,8 @@ int launch_r2c(const pnp_csmri_grad_args& a, cudaStream_t st) {
     float2* pS = reinterpret_cast<float2*>(a.S);
     int nl = a.W;
     long long stride = (long long)a.H * a.W;
-    void* args[] = {(void*)&pa, (void*)&pb, (void*)&pS, (void*)&nl, (void*)&stride, (void*)&sj};
+    int rlo = a.row_hi > a.row_lo ? a.row_lo : 0, rhi = a.row_hi > a.row_lo ? a.row_hi : a.H / 2;
+    void* args[] = {(void*)&pa, (void*)&pb, (void*)&pS, (void*)&nl, (void*)&stride, (void*)&sj, (void*)&rlo, (void*)&rhi};
     return launch_ex((const void*)pnp::k_lines_r2c<L, GP>, grid, dim3(GP * pnp::fft_threads<L>()), lines_smem<L>(), st,
                      (a.flags & PNP_FLAG_CHAIN) != 0, args);
 }
@@ -195,8 +196,9 @@ template <int L>
 int launch_cols(const pnp_csmri_grad_args& a, cudaStream_t st) {
     constexpr int NC = cols_nc<L>();
     const int hp = a.H / 2;
-    const int items = (hp - 1 + NC - 1) / NC;
-    // item CTAs + one CTA per image for packed column 0 (items == 0 only for H = 2: not reachable, H >= 32)
+    int rlo = a.row_hi > a.row_lo ? a.row_lo : 0, rhi = a.row_hi > a.row_lo ? a.row_hi : hp;
+    const int c_lo = rlo > 1 ? rlo : 1, c_hi = rhi < hp ? rhi : hp;
+    const int items = c_hi > c_lo ? (c_hi - c_lo + NC - 1) / NC : 0;
     // resident CTAs: one of them (CTA 0) owns packed column 0, the others loop over the items
     int ctas = persistent_ctas((const void*)pnp::k_cols_mask<L, NC>, NC * pnp::fft_threads<L>(), cols_smem<L>(), items + 1, a.batch);
     if (ctas < 2) ctas = 2;
@@ -209,7 +211,7 @@ int launch_cols(const pnp_csmri_grad_args& a, cudaStream_t st) {
     long long bstride = (long long)a.W * hp, ystride = (long long)a.W * hp;
     unsigned char* clr = a.clear_bits ? const_cast<unsigned char*>(a.bits) : nullptr;
     void* args[] = {(void*)&pS, (void*)&pbits, (void*)&y1, (void*)&y2, (void*)&y1n, (void*)&y2n, (void*)&hp_, (void*)&bstride,
-                    (void*)&ystride, (void*)&clr};
+                    (void*)&ystride, (void*)&clr, (void*)&rlo, (void*)&rhi};
     return launch_ex((const void*)pnp::k_cols_mask<L, NC>, grid, dim3(NC * pnp::fft_threads<L>()), cols_smem<L>(), st,
                      (a.flags & PNP_FLAG_CHAIN) != 0, args);
 }
@@ -225,7 +227,8 @@ int launch_c2r(const pnp_csmri_grad_args& a, cudaStream_t st) {
     int nl = a.W;
     long long stride = (long long)a.H * a.W;
     float inv = inv_n;
-    void* args[] = {(void*)&pS, (void*)&nl, (void*)&stride, (void*)&inv, (void*)&ep};
+    int rlo = a.row_hi > a.row_lo ? a.row_lo : 0, rhi = a.row_hi > a.row_lo ? a.row_hi : a.H / 2;
+    void* args[] = {(void*)&pS, (void*)&nl, (void*)&stride, (void*)&inv, (void*)&ep, (void*)&rlo, (void*)&rhi};
     const bool chain = (a.flags & PNP_FLAG_CHAIN) != 0;
     if (a.vadd && a.z_in && a.z_out && !a.g_out && !a.v_out) {          // the inner-iteration update
         dim3 grid(persistent_ctas((const void*)pnp::k_lines_c2r<L, GP, true>, GP * pnp::fft_threads<L>(), lines_smem<L>(), items, a.batch), a.batch);
@@ -443,6 +446,7 @@ int pnp_csmri_grad(const pnp_csmri_grad_args* args, void* stream) {
     if ((a.z_out != nullptr) && !a.z_in) return fail(PNP_ERR_ARG, "z_out needs z_in");
     const int ph = a.phases ? a.phases : 7;
     if (a.sel_count < 0) return fail(PNP_ERR_ARG, "sel_count < 0");
+    if (a.row_hi > a.row_lo && (a.row_lo < 0 || a.row_hi > a.H / 2)) return fail(PNP_ERR_ARG, "row range outside [0, H/2]");
     if (a.sel_count > 0) {
         if (!(ph & 1)) return fail(PNP_ERR_ARG, "in-pass selection needs pass 1 (phases bit0)");
         if (!a.sel_idx && (!a.sel_support || !a.sel_m0)) return fail(PNP_ERR_ARG, "in-pass selection needs sel_idx or sel_support + sel_m0");

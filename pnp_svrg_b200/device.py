@@ -18,6 +18,20 @@ def ptr(t):
     return None if t is None else t.data_ptr()
 
 
+_PINNED = {}
+
+
+def pinned_buffer(key, shape, dtype):
+    """A reusable pinned host buffer (allocating page-locked memory costs milliseconds; the loops upload Xinit and
+    download z on every call).  One buffer per key: callers use it synchronously, between a copy and its wait."""
+    want = (tuple(shape), dtype)
+    hit = _PINNED.get(key)
+    if hit is None or hit[0] != want:
+        hit = (want, torch.empty(shape, dtype=dtype).pin_memory())
+        _PINNED[key] = hit
+    return hit[1]
+
+
 def to_lines(z, H, W, device=None):
     """host/device (N,) or (H, W) array -> float32 device tensor in the transposed line layout
     [W][H] (line c = original column c)."""
@@ -29,15 +43,26 @@ def to_lines(z, H, W, device=None):
     a = np.ascontiguousarray(np.asarray(z, dtype=np.float64).reshape(H, W))
     if not a.flags.writeable:
         a = a.copy()                                   # torch.from_numpy wants a writable buffer
-    t = torch.from_numpy(a).to(torch.float32).to(device or 'cuda', non_blocking=False).t().contiguous()
-    if t.is_cuda:
-        torch.cuda.current_stream(t.device).synchronize()      # complete on return, like the copy itself (any stream may use it)
+    dev = torch.device(device or 'cuda')
+    if dev.type != 'cuda':
+        return torch.from_numpy(a).to(torch.float32).to(dev).t().contiguous()
+    # float64 -> float32 straight into a pinned staging buffer (one pass on the host), DMA from there
+    stage = pinned_buffer(('up', H * W), (H, W), torch.float32)
+    stage.copy_(torch.from_numpy(a))
+    t = stage.to(dev, non_blocking=True).t().contiguous()
+    torch.cuda.current_stream(dev).synchronize()       # complete on return (any stream may use it; the staging buffer is free again)
     return t
 
 
 def from_lines(t, H, W):
     """device [W][H] float32 -> host float64 (N,) in the reference's raveled (row-major) order."""
-    return t.reshape(W, H).t().contiguous().cpu().to(torch.float64).numpy().ravel()
+    d = t.reshape(W, H).t().contiguous()
+    if not d.is_cuda:
+        return d.to(torch.float64).numpy().ravel()
+    stage = pinned_buffer(('down', H * W), (H, W), torch.float32)
+    stage.copy_(d, non_blocking=True)
+    torch.cuda.current_stream(d.device).synchronize()
+    return stage.to(torch.float64).numpy().ravel()
 
 
 def lines_to_image_tensor(t, H, W):

@@ -171,7 +171,9 @@ class Engine:
             # copy reads; draw_host() stages the next one with a single native call.  One pinned allocation, sliced.
             ahead = max(2, min(8, ncpu // 2))
             depth = ahead + max(2, int(os.environ.get('PNP_HOST_RING_EXTRA', '12')))     # how far the host may run ahead
-            ring = torch.empty(depth, self.B + n_extra_ints, dtype=torch.int32).pin_memory()
+            # (page-locked allocations cost milliseconds: the ring is kept on the problem object between calls; the
+            # previous owner's queue has been closed by its result(), nothing writes into it any more)
+            ring = D.pinned_buffer(('draw_ring', id(problem)), (depth, self.B + n_extra_ints), torch.int32)
             self._host_ring = [ring[i] for i in range(depth)]
             self.idx_host = self._host_ring[0]
             sup = getattr(problem, '_support_host', None)
@@ -368,12 +370,12 @@ class Engine:
         lo, n = self.slot_base, self.slot_host
         if n == lo:
             return []
-        mse = self.mse_log[lo:n].cpu().numpy()
-        sig = self.sig_log[lo:n].cpu().numpy()
-        self.sig_hist.extend(list(sig / self.W))
+        both = torch.stack([self.mse_log[lo:n], self.sig_log[lo:n]]).cpu().numpy()     # one read-back for both logs
+        mse, sig = both[0], both[1]
+        self.sig_hist.extend((sig / self.W).tolist())
         with torch.cuda.stream(self.stream):
             self._reset_logs()
-        return [self._psnr_from_sum(float(v)) for v in mse]
+        return list(self._psnr_from_sum(mse))          # vectorised: same arithmetic as per value
 
     # ------------------------------------------------------------------ graphs
     def capture(self, fn):

@@ -10,10 +10,21 @@ from .problem import MiniBatch, Problem
 
 
 def shard_rows(H, rank, world):
-    """contiguous block of ky rows owned by `rank` (last rank takes the remainder)"""
-    per = H // world
+    """Band [lo, hi) of PACKED ky rows owned by `rank`: kyp = min(ky, H - ky) in [0, H/2); the Nyquist row ky = H/2
+    rides in packed row 0 and belongs to rank 0.  The bands are contiguous, disjoint and cover [0, H/2) (the last rank
+    takes the remainder).  A measurement at (ky, kx) and its Hermitian mirror land on the same rank, so the column
+    pass of a rank only transforms its own packed rows (pnp_csmri_grad_args.row_lo / row_hi)."""
+    hp = H // 2
+    per = hp // world
     lo = rank * per
-    return lo, (H if rank == world - 1 else lo + per)
+    return lo, (hp if rank == world - 1 else lo + per)
+
+
+def packed_row_of(ky, H):
+    """packed half-spectrum row of k-space row ky (see shard_rows)"""
+    ky = np.asarray(ky)
+    hp = H // 2
+    return np.where(ky < hp, ky, np.where(ky == hp, 0, H - ky))
 
 
 class CSMRI(Problem):
@@ -87,8 +98,9 @@ class CSMRI(Problem):
             self._dev_set_sel(self._bits_full, self._support, self.M0)
         else:
             lo, hi = shard_rows(self.H, *self.shard)
-            rows = self._support_host // W
+            rows = packed_row_of(self._support_host // W, self.H)
             own = np.ascontiguousarray(self._support_host[(rows >= lo) & (rows < hi)])
+            self._shard_rows = (int(lo), int(hi))
             self._shard_count = int(own.size)
             own_dev = torch.from_numpy(own).to(dev)
             if own.size:
@@ -127,18 +139,24 @@ class CSMRI(Problem):
 
     def _dev_grad(self, a, b=None, sel=None, with_y=True, gscale=1.0, gscale_ptr=None, step=0.0, step_ptr=None,
                   g_out=None, vadd=None, v_out=None, z_in=None, z_out=None, phases=0, clear_sel=False, sel_job=None,
-                  chain=False):
+                  chain=False, partial_ok=False):
         """g = Re(ifft2(sel o fft2(a - b) - Ysel)) * gscale ; v = g + vadd ; z_out = z_in - step*v.
         ``sel_job`` = dict(count, idx | None, cursor, seed, counter): pass 1 also builds the minibatch selection in
         ``sel`` (all zero on entry) -- from explicit positions ``idx`` or by the device sampler."""
         sj = {}
+        if sel is None and self.shard is not None:
+            # measurement shard: the full-mask gradient of this rank is a PARTIAL sum over its band of packed rows
+            if not partial_ok:
+                raise NotImplementedError('CSMRI(shard=...): the full gradient of a sharded problem is a partial sum; only '
+                                          'pnp_svrg (which all-reduces its snapshot) and grad_full() handle it')
+            sj = dict(row_lo=self._shard_rows[0], row_hi=self._shard_rows[1])
         if sel_job is not None:
             if sel is None:
                 raise ValueError('sel_job needs the selection buffer it fills')
             if sel_job.get('idx') is None and int(sel_job['count']) > self.M0:
                 raise ValueError('Cannot take a larger sample (%d) than the %d sampled k-space positions'
                                  % (sel_job['count'], self.M0))
-            sj = dict(sel_count=int(sel_job['count']), sel_idx=D.ptr(sel_job.get('idx')), sel_idx_img_stride=0,
+            sj.update(sel_count=int(sel_job['count']), sel_idx=D.ptr(sel_job.get('idx')), sel_idx_img_stride=0,
                       sel_cursor=D.ptr(sel_job.get('cursor')), sel_support=D.ptr(self._support), sel_m0=D.ptr(self._m0_dev),
                       sel_support_img_stride=0, sel_seed=int(sel_job.get('seed', 0)) & 0xffffffff,
                       sel_counter=D.ptr(sel_job.get('counter')), sel_min_m0=int(self.M0))
@@ -183,7 +201,12 @@ class CSMRI(Problem):
         """problems/CSMRI.py:76-81."""
         zl = D.to_lines(z, self.H, self.W, self._device)
         g = torch.empty_like(zl)
-        self._dev_grad(zl, gscale=1.0 / self.M0, g_out=g)
+        self._dev_grad(zl, gscale=1.0 / self.M0, g_out=g, partial_ok=True)
+        if self.shard is not None:
+            import torch.distributed as dist
+            if dist.is_available() and dist.is_initialized() and self.shard[1] > 1:
+                self._snapshot_allreduce(g)        # every rank returns the FULL gradient
+            # (without a process group the caller gets this shard's partial gradient: the single-process shard tests)
         return D.from_lines(g, self.H, self.W)
 
     def grad_stoch(self, z, mb):

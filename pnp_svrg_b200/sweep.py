@@ -74,9 +74,14 @@ def reconstruct(job, H=256, W=256, eta_scale=0.15, T2=10, mini_batch_size=1000, 
     B = min(mini_batch_size, p.M0)
     t0 = time.time()
     eta = min(eta_scale * p.M0, 3.0 * B)          # full-gradient step ~0.15 * M0, capped by the minibatch term
-    out = getattr(ALG, job['algo'])(p, den, eta=eta, tt=1e9, T2=T2, mini_batch_size=B, verbose=False,
-                                    converge_check=False, max_iters=iters, vr_mode='paper', mb_source='device',
-                                    mb_seed=job['id'], fast=True, sync_every=iters)
+    kw = dict(eta=eta, tt=1e9, verbose=False, converge_check=False, max_iters=iters, fast=True, sync_every=iters)
+    if job['algo'] != 'pnp_gd':
+        kw.update(mini_batch_size=B, mb_source='device', mb_seed=job['id'])
+    if job['algo'] in ('pnp_svrg', 'pnp_sarah'):
+        kw['T2'] = T2
+    if job['algo'] == 'pnp_svrg':
+        kw['vr_mode'] = 'paper'
+    out = getattr(ALG, job['algo'])(p, den, **kw)
     dt = time.time() - t0
     ps = out['psnr_per_iter']
     return dict(id=job['id'], image=str(img), alpha=job['alpha'], snr=job['snr'], algo=job['algo'],
@@ -208,7 +213,9 @@ ETA_RANGE, MB_RANGE, T2_RANGE, DSTR_RANGE = (0, 100), (1, 100), (1, 100), (0, 2)
 TUNE_ARGS = {                     # order of the objective's positional tuple (algorithms/pnp_*.py tune_pnp_*)
     'pnp_gd': ('eta', 'dstrength'),
     'pnp_sgd': ('eta', 'mini_batch_size', 'dstrength'),
-    'pnp_saga': ('eta', 'mini_batch_size', 'dstrength'),
+    # the reference's sweep script builds a 3-tuple here while tune_pnp_saga unpacks four values (every SAGA trial of the
+    # original raises ValueError); the table size is searched like the other integer parameters
+    'pnp_saga': ('eta', 'mini_batch_size', 'dstrength', 'hist_size'),
     'pnp_sarah': ('eta', 'mini_batch_size', 'T2', 'dstrength'),
     'pnp_svrg': ('eta', 'mini_batch_size', 'T2', 'dstrength'),
 }
@@ -245,7 +252,8 @@ def get_pspace(algo_name, eta=ETA_RANGE, mb=MB_RANGE, T2=T2_RANGE, dstr=DSTR_RAN
     nodes = {'eta': lambda: hp.uniform('eta', *eta),
              'mini_batch_size': lambda: scope.int(quniform('mini_batch_size', mb[0], mb[1], q=1)),
              'T2': lambda: scope.int(quniform('T2', T2[0], T2[1], q=1)),
-             'dstrength': lambda: hp.uniform('dstrength', *dstr)}
+             'dstrength': lambda: hp.uniform('dstrength', *dstr),
+             'hist_size': lambda: scope.int(quniform('hist_size', 1, 100, q=1))}
     return tuple(nodes[k]() for k in TUNE_ARGS[algo_name])
 
 

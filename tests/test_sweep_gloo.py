@@ -103,14 +103,25 @@ def test_world_size_2_gloo_gather():
 
 
 def test_measurement_shards_partition_the_rows():
-    """config 5: k-space rows are split into disjoint contiguous blocks that cover every row."""
+    """config 5: the packed half-spectrum rows are split into disjoint contiguous bands that cover [0, H/2), and every
+    k-space row (with its Hermitian mirror, and the Nyquist row with DC) falls into exactly one band."""
     import importlib.util
+    import numpy as np
     spec = importlib.util.spec_from_file_location('csmri_mod', os.path.join(ROOT, 'pnp_svrg_b200', 'problems', 'CSMRI.py'))
     src = open(spec.origin).read()
-    ns = {}
+    ns = {'np': np}
     exec(src[src.index('def shard_rows'):src.index('class CSMRI')], ns)
     for H in (32, 256, 2048):
         for world in (1, 2, 4, 8, 3):
             blocks = [ns['shard_rows'](H, r, world) for r in range(world)]
-            assert blocks[0][0] == 0 and blocks[-1][1] == H
+            assert blocks[0][0] == 0 and blocks[-1][1] == H // 2
             assert all(blocks[i][1] == blocks[i + 1][0] for i in range(world - 1))
+            kyp = ns['packed_row_of'](np.arange(H), H)
+            assert kyp.min() == 0 and kyp.max() == H // 2 - 1
+            assert np.array_equal(kyp[1:H // 2], kyp[H - 1:H // 2:-1])          # ky and H - ky share a packed row
+            owner = np.full(H, -1)
+            for r, (lo, hi) in enumerate(blocks):
+                sel = (kyp >= lo) & (kyp < hi)
+                assert (owner[sel] == -1).all()
+                owner[sel] = r
+            assert (owner >= 0).all()
