@@ -410,14 +410,14 @@ def run_e2e(a, cfg, prob, dev, world, fast=True):
     (one H2D copy per inner iteration, on a copy stream) while the current epoch runs; PSNR + sigma logs of every
     iterate are read back; Xinit upload (pinned staging) and z download are inside the timed region.  fast=False: the
     reference's loop shape, one launch sequence and one read-back per iteration.  An e2e "step" is an epoch like a
-    `value` step; the call runs max(steps, 100) epochs so that its fixed cost (allocation, capture, upload, download:
-    about 10 ms) is amortised as it would be in a real reconstruction."""
+    `value` step; the call runs max(steps, 300) epochs so that its fixed cost (allocation, capture, upload, download:
+    about 20 ms) is amortised as it is in a real reconstruction (the reference runs for tt = 10 .. 100 s)."""
     import torch
     import torch.distributed as dist
     from pnp_svrg_b200.algorithms import pnp_svrg
     from pnp_svrg_b200.denoisers import TVDenoiser
     T2, B = cfg['T2'], cfg['mini_batch_size']
-    epochs = max(a.steps, 100) if fast else max(a.steps, 20)
+    epochs = max(a.steps, 300) if fast else max(a.steps, 20)
     iters = epochs * T2
     kw = dict(eta=cfg['eta'], T2=T2, mini_batch_size=B, vr_mode='paper', verbose=False, converge_check=False,
               mb_source='host', mb_seed=11, fast=fast)
