@@ -375,7 +375,7 @@ class Engine:
         self.sig_hist.extend((sig / self.W).tolist())
         with torch.cuda.stream(self.stream):
             self._reset_logs()
-        return list(self._psnr_from_sum(mse))          # vectorised: same arithmetic as per value
+        return list(np.atleast_1d(self._psnr_from_sum(mse)))          # vectorised: same arithmetic as per value
 
     # ------------------------------------------------------------------ graphs
     def capture(self, fn):

@@ -75,7 +75,7 @@ class Problem():
 
     def _psnr_from_sum(self, sq_sum):
         with np.errstate(divide='ignore'):
-            return np.around(10.0 * np.log10(self._data_range ** 2 / (np.float64(sq_sum) / self.N)), decimals=2)
+            return np.around(10.0 * np.log10(self._data_range ** 2 / (np.asarray(sq_sum, dtype=np.float64) / self.N)), decimals=2)[()]
 
     def set_snr_sigma(self):
         if self.snr is not None and self.sigma is None:
