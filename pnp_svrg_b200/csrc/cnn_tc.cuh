@@ -540,58 +540,88 @@ k_conv_tc_stack(const __grid_constant__ TcStack pm, int PW, int S, int n_tiles) 
 }
 
 // ---- thin first layer for the bf16 path (CUDA cores; writes padded bf16 NHWC activations) ----
-// first layer (1 -> 64): one thread per pixel, 16 channels at a time (576 FMAs per pixel, the nine inputs
-// transformed once), 32-byte sector stores
+// first layer (1 -> 64).  A thread owns 8 output channels and keeps their 72 weights in REGISTERS; a warp is 4 adjacent
+// pixels of a line x the 8 channel groups, so every store instruction of the warp writes 4 complete 128-byte pixels
+// (512 contiguous bytes).  The thread walks down FL_R lines with a sliding 3x3 window (3 new inputs per step).  The
+// version this replaces (one thread per pixel, weights re-read from shared memory for every pixel: 144 LDS.128 and
+// eight 16-byte stores to eight different lines per pixel) ran 1107 warp instructions per 32 pixels, 40 % issue-active,
+// 331 us at 2048^2 for a 537 MB write; this one runs ~600.
+#define FL_R 16
 __global__ void __launch_bounds__(256)
 k_conv_first_bf16(const float* __restrict__ img, __nv_bfloat16* __restrict__ out, const float* __restrict__ w, CnnAct a,
                   CnnIo io, int PH, int PW) {
-    __shared__ __align__(16) float sw[9 * CNN_C];
-    __shared__ __align__(16) float s_scale[CNN_C], s_shift[CNN_C];
-    for (int i = threadIdx.x; i < 9 * CNN_C; i += blockDim.x) sw[i] = w[i];
-    for (int i = threadIdx.x; i < CNN_C; i += blockDim.x) {
-        s_scale[i] = a.scale ? a.scale[i] : 1.f;
-        s_shift[i] = a.shift ? a.shift[i] : 0.f;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int cg = lane & 7;                                   // channels 8*cg .. 8*cg + 7
+    const int p = blockIdx.x * 32 + warp * 4 + (lane >> 3);    // pixel within the line
+    const int l0 = blockIdx.y * FL_R;
+    float2 wt[9][4];
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+        const float4 lo = *reinterpret_cast<const float4*>(w + t * CNN_C + cg * 8), hi = *reinterpret_cast<const float4*>(w + t * CNN_C + cg * 8 + 4);
+        wt[t][0] = make_float2(lo.x, lo.y); wt[t][1] = make_float2(lo.z, lo.w);
+        wt[t][2] = make_float2(hi.x, hi.y); wt[t][3] = make_float2(hi.z, hi.w);
+    }
+    float2 sc[4], sf[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        sc[k] = a.scale ? *reinterpret_cast<const float2*>(a.scale + cg * 8 + 2 * k) : make_float2(1.f, 1.f);
+        sf[k] = a.shift ? *reinterpret_cast<const float2*>(a.shift + cg * 8 + 2 * k) : make_float2(0.f, 0.f);
+    }
+    // input map  x -> x * ia + ib  (mode 0: min/max normalisation to [shift, shift + range]; mode 1: clamp to [0, 1])
+    float ia = 1.f, ib = 0.f;
+    if (io.mode == 0) {
+        const float mn = ord2f(io.stats[0]), mx = ord2f(io.stats[1]);
+        ia = io.range / (mx - mn);
+        ib = io.shift - mn * ia;
+    }
+    // the CTA's input tile (FL_R + 2 lines x 34 pixels, already transformed, zero outside the image) goes through
+    // shared memory: one coalesced load phase instead of three dependent global loads per step of every thread
+    __shared__ float tile[FL_R + 2][36];
+    for (int i = threadIdx.x; i < (FL_R + 2) * 34; i += blockDim.x) {
+        const int r = i / 34, c = i - r * 34;
+        const int ll = l0 - 1 + r, pp = blockIdx.x * 32 - 1 + c;
+        float v = 0.f;
+        if (ll >= 0 && ll < PH && pp >= 0 && pp < PW) {
+            const float x = img[(long long)ll * PW + pp];
+            v = io.mode == 0 ? fmaf(x, ia, ib) : fminf(fmaxf(x, 0.f), 1.f);
+        }
+        tile[r][c] = v;
     }
     __syncthreads();
-    const long long total = (long long)PH * PW;
-    for (long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x; pix < total; pix += (long long)gridDim.x * blockDim.x) {
-        const int l = (int)(pix / PW), p = (int)(pix - (long long)l * PW);
-        float x[9];
+    const int pc = warp * 4 + (lane >> 3);                     // pixel within the tile; tile column pc + 1
+    auto load3 = [&](int r, float (&o)[3]) {
 #pragma unroll
-        for (int dl = -1; dl <= 1; ++dl)
+        for (int d = 0; d < 3; ++d) o[d] = tile[r][pc + d];
+    };
+    if (p >= PW) return;
+    float win[3][3];
+    load3(0, win[0]);
+    load3(1, win[1]);
+    const float slope = a.slope;
+#pragma unroll 2
+    for (int l = l0; l < l0 + FL_R && l < PH; ++l) {
+        load3(l - l0 + 2, win[2]);
+        float2 acc[4];
 #pragma unroll
-            for (int dp = -1; dp <= 1; ++dp) {
-                const int ll = l + dl, pp = p + dp;
-                const bool in = ll >= 0 && ll < PH && pp >= 0 && pp < PW;
-                x[(dl + 1) * 3 + dp + 1] = in ? cnn_input(io, img[(long long)ll * PW + pp]) : 0.f;
+        for (int k = 0; k < 4; ++k) acc[k] = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int dl = 0; dl < 3; ++dl)
+#pragma unroll
+            for (int dp = 0; dp < 3; ++dp) {
+                const float2 xx = make_float2(win[dl][dp], win[dl][dp]);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) acc[k] = __ffma2_rn(xx, wt[dl * 3 + dp][k], acc[k]);
             }
-        __nv_bfloat16* dst = out + ((long long)l * (PW + 1) + p) * CNN_C;
-#pragma unroll 1
-        for (int c = 0; c < CNN_C; c += 16) {
-            float2 acc[8];                                  // channel pairs: fma.rn.f32x2, two FMAs per issue slot
+        uint4 pk;
+        __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&pk);
 #pragma unroll
-            for (int k = 0; k < 8; ++k) acc[k] = make_float2(0.f, 0.f);
-#pragma unroll
-            for (int t = 0; t < 9; ++t) {
-                const float2 xx = make_float2(x[t], x[t]);
-#pragma unroll
-                for (int k = 0; k < 16; k += 4) {
-                    const float4 ww = *reinterpret_cast<const float4*>(sw + t * CNN_C + c + k);
-                    acc[k >> 1] = __ffma2_rn(xx, make_float2(ww.x, ww.y), acc[k >> 1]);
-                    acc[(k >> 1) + 1] = __ffma2_rn(xx, make_float2(ww.z, ww.w), acc[(k >> 1) + 1]);
-                }
-            }
-            uint4 pk[2];
-            __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(pk);
-#pragma unroll
-            for (int k = 0; k < 16; k += 2) {
-                const float2 sc = *reinterpret_cast<const float2*>(s_scale + c + k), sf = *reinterpret_cast<const float2*>(s_shift + c + k);
-                const float2 v = __ffma2_rn(acc[k >> 1], sc, sf);
-                h[k >> 1] = __floats2bfloat162_rn(act(v.x, a.slope), act(v.y, a.slope));
-            }
-            reinterpret_cast<uint4*>(dst + c)[0] = pk[0];
-            reinterpret_cast<uint4*>(dst + c)[1] = pk[1];
+        for (int k = 0; k < 4; ++k) {
+            const float2 v = __ffma2_rn(acc[k], sc[k], sf[k]);
+            h[k] = __floats2bfloat162_rn(act(v.x, slope), act(v.y, slope));
         }
+        *reinterpret_cast<uint4*>(out + ((long long)l * (PW + 1) + p) * CNN_C + cg * 8) = pk;
+#pragma unroll
+        for (int d = 0; d < 3; ++d) { win[0][d] = win[1][d]; win[1][d] = win[2][d]; }
     }
 }
 

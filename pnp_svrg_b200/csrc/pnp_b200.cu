@@ -879,7 +879,7 @@ int cnn_forward_tc(const pnp_cnn_net* net, const float* img, float* out, int PH,
     }
     __nv_bfloat16* cur = static_cast<__nv_bfloat16*>(act0);
     __nv_bfloat16* nxt = static_cast<__nv_bfloat16*>(act1);
-    pnp::k_conv_first_bf16<<<ew_blocks(npix, 1), 256, 0, st>>>(img, cur, net->w[0],
+    pnp::k_conv_first_bf16<<<dim3((PW + 31) / 32, (PH + FL_R - 1) / FL_R), 256, 0, st>>>(img, cur, net->w[0],
         pnp::CnnAct{net->scale[0], net->shift[0], net->slope[0]}, io, PH, PW);
     LAUNCH_CHECK();
     const int n_tiles = (int)((S + TC_OUT_PER_TILE - 1) / TC_OUT_PER_TILE);
