@@ -277,6 +277,47 @@ int pnp_csmri_update_prox(const float* S, int H, int W, float gscale, float step
                           const float* xrec, double* mse_log, const int* slot, int* advance_counters, int n_advance,
                           unsigned* barrier_ws, int chain, void* stream);
 
+/* ---- whole PnP-SVRG runs of SMALL CSMRI images, one thread-block cluster per image ----------------------------
+ * Replaces, for square images of 128 or 256 pixels a side, the whole loop of algorithms/pnp_svrg.py:26-95 in its
+ * paper mode (v = (g_B(z) - g_B(w)) / B + mu, line 53) with the wavelet "TV" prox (denoisers/TV.py:21-26 after
+ * estimate_sigma, pnp_svrg.py:71): `n_inner` inner iterations in ONE launch, a snapshot (mu = grad_full(z) *
+ * snap_scale, w = z; pnp_svrg.py:32-35) before iteration 0 and then every T2 iterations, the step of epoch e being
+ * step[img] * lr_decay**e.  The image, w and mu stay in the shared memory of a cluster of 8 CTAs for the whole run; the
+ * transpositions of the 2-D transform go through distributed shared memory (csrc/small.cuh).  Same arithmetic as
+ * pnp_csmri_grad + pnp_csmri_update_prox / pnp_prox_wavelet_fused.  `batch` images = `batch` clusters.
+ * Minibatch of inner iteration t: idx[img * idx_img_stride + t * idx_iter_stride + 0..B) when idx is non-null, else the
+ * keyed Feistel draw of pnp_csmri_sel_sample with counter  *draw_counter + t.  Logs: sig_log / mse_log[(*slot + t) *
+ * batch + img] += the sum over lines of the sigma estimates / the squared error against xrec (mse_log and xrec
+ * optional).  The counters are only read: advance them afterwards (pnp_advance_by).  fallback_sigma *
+ * fallback_decay**t replaces a non-positive sigma estimate in iteration t.
+ * Returns PNP_ERR_UNSUPPORTED for other sizes (use the per-pass entry points). */
+typedef struct {
+    int H, W, batch;
+    float* z;                     /* [batch][W][H] iterate, updated in place */
+    const float* xrec;            /* optional ground truth (PSNR log) */
+    const float *Y1, *Y2, *Y1n, *Y2n;     /* as in pnp_csmri_grad_args */
+    const unsigned char* bits_full;       /* selection bytes of the full mask [batch][H/2][W] */
+    const int* support;           /* device sampler (idx == null): [batch][support_img_stride], m0[batch] */
+    const int* m0;
+    long long support_img_stride;
+    const int* idx;               /* optional explicit minibatches */
+    long long idx_img_stride, idx_iter_stride;
+    const float* snap_scale_ptr;  /* optional [batch] (1 / M0), replaces snap_scale */
+    float snap_scale;
+    const float* step;            /* [batch] (step_img_stride = 1) or one value (0) */
+    long long step_img_stride;
+    double* sig_log;
+    double* mse_log;
+    const int* slot;              /* optional: first log slot (device int); null = 0 */
+    const int* draw_counter;      /* optional: first draw counter (device int); null = 0 */
+    int n_inner, T2, mini_batch_size;
+    unsigned seed;
+    float lr_decay, sigma_modifier, fallback_sigma, fallback_decay;
+} pnp_csmri_svrg_small_args;
+int pnp_csmri_svrg_small(const pnp_csmri_svrg_small_args* args, void* stream);
+/* 1 when pnp_csmri_svrg_small handles H x W images, else 0 (host-side query, no launch) */
+int pnp_csmri_svrg_small_supported(int H, int W);
+
 /* TV prox by Chambolle's dual projection, ADDITIVE mode (TVDenoiser(method='chambolle')): the north star's
  * "TV (Chambolle)" kernel; no counterpart in the reference, whose TVDenoiser is the wavelet shrink above
  * (denoisers/TV.py:24,26).  Arithmetic of scikit-image 0.18.2 denoise_tv_chambolle with a fixed n_iter >= 1
@@ -341,6 +382,8 @@ int pnp_saga_update(const float* g_new, float* g_prev, float* table, float* tsum
                     const int* cursor, float step, const float* step_ptr, void* stream);
 /* counters[0..n) += 1 on the device (log slot / minibatch cursor for CUDA-graph replay) */
 int pnp_advance(int* counters, int n, void* stream);
+/* counters[0..n) += delta (after a pnp_csmri_svrg_small run of delta iterations) */
+int pnp_advance_by(int* counters, int n, int delta, void* stream);
 
 /* counters[0..n) += 1 (n may be 0) and *x *= factor (step decay  eta*lr_decay**i  kept on the device) */
 int pnp_advance_scale(int* counters, int n, float* x, float factor, void* stream);

@@ -66,6 +66,22 @@ class CdpGradArgs(C.Structure):
     ]
 
 
+class SvrgSmallArgs(C.Structure):
+    """mirror of pnp_csmri_svrg_small_args"""
+    _fields_ = [
+        ('H', C.c_int), ('W', C.c_int), ('batch', C.c_int),
+        ('z', C.c_void_p), ('xrec', C.c_void_p),
+        ('Y1', C.c_void_p), ('Y2', C.c_void_p), ('Y1n', C.c_void_p), ('Y2n', C.c_void_p),
+        ('bits_full', C.c_void_p), ('support', C.c_void_p), ('m0', C.c_void_p), ('support_img_stride', C.c_longlong),
+        ('idx', C.c_void_p), ('idx_img_stride', C.c_longlong), ('idx_iter_stride', C.c_longlong),
+        ('snap_scale_ptr', C.c_void_p), ('snap_scale', C.c_float),
+        ('step', C.c_void_p), ('step_img_stride', C.c_longlong),
+        ('sig_log', C.c_void_p), ('mse_log', C.c_void_p), ('slot', C.c_void_p), ('draw_counter', C.c_void_p),
+        ('n_inner', C.c_int), ('T2', C.c_int), ('mini_batch_size', C.c_int), ('seed', C.c_uint),
+        ('lr_decay', C.c_float), ('sigma_modifier', C.c_float), ('fallback_sigma', C.c_float), ('fallback_decay', C.c_float),
+    ]
+
+
 CNN_MAX_LAYERS = 32
 
 
@@ -122,7 +138,10 @@ PROTOTYPES = {
     'pnp_saga_update': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong,
                                   C.c_int, C.c_int, C.c_void_p, C.c_longlong, C.c_void_p, C.c_float, C.c_void_p,
                                   C.c_void_p]),
+    'pnp_csmri_svrg_small': (C.c_int, [C.POINTER(SvrgSmallArgs), C.c_void_p]),
+    'pnp_csmri_svrg_small_supported': (C.c_int, [C.c_int, C.c_int]),
     'pnp_advance': (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
+    'pnp_advance_by': (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     'pnp_advance_scale': (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_float, C.c_void_p]),
     'pnp_copy_f32': (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p]),
     'pnp_debug_set': (C.c_int, [C.c_int, C.c_int]),

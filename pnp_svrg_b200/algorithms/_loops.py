@@ -365,8 +365,44 @@ class SvrgRun:
     def _needs_indices(self):
         return self.B > 0 and self.mb_source != 'device' and (self.paper or self.mb_source == 'legacy')
 
+    def _small_ok(self):
+        """True when a whole epoch runs as ONE launch of the cluster kernel (pnp_csmri_svrg_small, csrc/small.cuh):
+        paper-mode PnP-SVRG on a square CSMRI image of 128 or 256 pixels a side with the wavelet prox.
+        ``PNP_SMALL=0`` keeps the three-pass path (comparison runs, tests)."""
+        p, d, eng = self.problem, self.denoiser, self.eng
+        return (self.paper and self.B > 0 and os.environ.get('PNP_SMALL', '1') != '0'
+                and getattr(p, 'pname', '') == 'csmri' and getattr(p, 'shard', None) is None
+                and getattr(d, 'method', None) == 'wavelet' and eng.uses_sigma and hasattr(p, '_bits_full')
+                and eng.lib.pnp_csmri_svrg_small_supported(int(p.H), int(p.W)) == 1)
+
+    def _small_epoch(self, bufs):
+        """snapshot + T2 inner iterations + counters (+ step decay) with the image resident in a cluster's shared memory"""
+        import ctypes as C
+        from .. import _lib
+        eng, p, d = self.eng, self.problem, self.denoiser
+        idx, stride = None, 0
+        if bufs is not None:                    # host-drawn minibatches: the T2 index sets of this epoch, contiguous
+            idx, stride = bufs[0], int(bufs[0].numel())
+        args = _lib.SvrgSmallArgs(
+            H=p.H, W=p.W, batch=1, z=D.ptr(self.z), xrec=D.ptr(p._xrec_dev),
+            Y1=D.ptr(p._Y1), Y2=D.ptr(p._Y2), Y1n=D.ptr(p._Y1n), Y2n=D.ptr(p._Y2n), bits_full=D.ptr(p._bits_full),
+            support=D.ptr(p._support), m0=D.ptr(p._m0_dev), support_img_stride=0,
+            idx=D.ptr(idx), idx_img_stride=0, idx_iter_stride=stride,
+            snap_scale_ptr=None, snap_scale=1.0 / _full_norm(p), step=D.ptr(eng.step), step_img_stride=0,
+            sig_log=D.ptr(eng.sig_log), mse_log=D.ptr(eng.mse_log), slot=D.ptr(eng.slot_ptr), draw_counter=D.ptr(eng.draw_ptr),
+            n_inner=self.T2, T2=self.T2, mini_batch_size=self.B, seed=eng.mb_seed & 0xffffffff, lr_decay=1.0,
+            sigma_modifier=float(d.sigma_modifier), fallback_sigma=float(d.denoise_strength * d.decay ** (d.t + 1)),
+            fallback_decay=float(d.decay))
+        eng.check(eng.lib.pnp_csmri_svrg_small(C.byref(args), eng.sptr))
+        eng.check(eng.lib.pnp_advance_by(D.ptr(eng.counters), 3, self.T2, eng.sptr))
+        if self.lr_decay != 1.0:
+            eng.check(eng.lib.pnp_advance_scale(D.ptr(eng.counters), 0, D.ptr(eng.step), self.lr_decay, eng.sptr))
+
     def _epoch_ops(self, bufs):
         eng = self.eng
+        if self._small_ok():
+            self._small_epoch(bufs)
+            return
         self.snapshot()
         keep = eng.idx_dev if self.B > 0 else None
         for j in range(self.T2):

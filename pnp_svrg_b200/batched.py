@@ -12,6 +12,7 @@ Only the paper-mode SVRG + wavelet-prox combination (config 1 / 4) is batched he
 combination goes through the per-problem engine.
 """
 import ctypes as C
+import os
 import time
 
 import numpy as np
@@ -183,6 +184,9 @@ class BatchedSVRG:
         self.outer = 0
         self.fused_prox = True
         self.whole_run_graph = False     # sweeps set it: capture all iterations of a run as one graph (see _capture_run)
+        # 128^2 / 256^2: the whole run is ONE launch, one thread-block cluster per problem (csrc/small.cuh)
+        self.use_small = (os.environ.get('PNP_SMALL', '1') != '0'
+                          and self.lib.pnp_csmri_svrg_small_supported(int(self.H), int(self.W)) == 1)
         self._run_graph, self._run_graph_n = None, None
 
     def check(self, rc):
@@ -296,6 +300,8 @@ class BatchedSVRG:
         """n_inner inner iterations in total (snapshot every T2), nothing is read back."""
         if self.slots_used + n_inner > self.max_slots:
             raise ValueError('log capacity exceeded')
+        if self.use_small:
+            return self._run_small(n_inner)
         if self.lr_decay == 1.0 and self.whole_run_graph:
             if getattr(self, '_run_graph_n', None) != n_inner:
                 if getattr(self, '_run_graph', None):
@@ -320,6 +326,26 @@ class BatchedSVRG:
                     self.check(self.lib.pnp_graph_launch(self.graph, self.sptr))
                 done += k
                 self.outer += 1
+        self.slots_used += n_inner
+
+    def _run_small(self, n_inner):
+        """the whole run in one launch: every problem is a cluster of 8 CTAs that keeps its image, snapshot and snapshot
+        gradient in shared memory (pnp_csmri_svrg_small)"""
+        with torch.cuda.stream(self.stream):
+            if self.lr_decay != 1.0:
+                self.step.copy_(torch.from_numpy((self.eta_host * self.lr_decay ** self.outer).astype(np.float32)), non_blocking=True)
+            args = _lib.SvrgSmallArgs(
+                H=self.H, W=self.W, batch=self.nb, z=D.ptr(self.z), xrec=D.ptr(self.xrec),
+                Y1=D.ptr(self.Y1), Y2=D.ptr(self.Y2), Y1n=D.ptr(self.Y1n), Y2n=D.ptr(self.Y2n), bits_full=D.ptr(self.bits_full),
+                support=D.ptr(self.support), m0=D.ptr(self.m0), support_img_stride=self.sup_stride,
+                idx=None, idx_img_stride=0, idx_iter_stride=0, snap_scale_ptr=D.ptr(self.inv_m0), snap_scale=0.0,
+                step=D.ptr(self.step), step_img_stride=1, sig_log=D.ptr(self.sig_log), mse_log=D.ptr(self.mse_log),
+                slot=D.ptr(self.counters[0:1]), draw_counter=D.ptr(self.counters[2:3]),
+                n_inner=int(n_inner), T2=self.T2, mini_batch_size=self.B, seed=self.seed & 0xffffffff,
+                lr_decay=self.lr_decay, sigma_modifier=self.sigma_modifier, fallback_sigma=0.0, fallback_decay=1.0)
+            self.check(self.lib.pnp_csmri_svrg_small(C.byref(args), self.sptr))
+            self.check(self.lib.pnp_advance_by(D.ptr(self.counters), 3, int(n_inner), self.sptr))
+        self.outer += -(-n_inner // self.T2)
         self.slots_used += n_inner
 
     def results(self, with_z=True):

@@ -350,7 +350,9 @@ __device__ __forceinline__ void fft_reg_stage(int t, float2 (&x)[FftPlan<L>::EPT
 }
 
 // exchange between a stage of radix RA (prefix NSP) and the next stage of radix RB
-template <int L, int RA, int NSP, int RB>
+// WS: the T cooperating threads live in ONE warp (T <= 32): warp barriers instead of CTA barriers, so transforms of
+// different warps need not run in lock step (csrc/small.cuh)
+template <int L, int RA, int NSP, int RB, bool WS = false>
 __device__ __forceinline__ void fft_reg_exchange(int t, const SmemBuf& sb, float2 (&x)[FftPlan<L>::EPT]) {
     constexpr int EPT = FftPlan<L>::EPT;
     constexpr int T = L / EPT;
@@ -361,7 +363,7 @@ __device__ __forceinline__ void fft_reg_exchange(int t, const SmemBuf& sb, float
 #pragma unroll
         for (int r = 0; r < RA; ++r) sb.put(base + r * NSP, x[b * RA + r]);
     }
-    __syncthreads();
+    if (WS) __syncwarp(); else __syncthreads();
 #pragma unroll
     for (int b = 0; b < EPT / RB; ++b) {
         const int j = t + b * T;
@@ -372,17 +374,18 @@ __device__ __forceinline__ void fft_reg_exchange(int t, const SmemBuf& sb, float
 
 // In-register forward FFT.  The exchange buffer must be free on entry; on exit the LAST exchange's
 // reads may still be in flight in other threads: callers sync before writing the buffer again.
-template <int L>
+template <int L, bool WS = false>
 __device__ __forceinline__ void fft_regs(int t, const SmemBuf& sb, float2 (&x)[FftPlan<L>::EPT], const FftTw<L>& tw) {
     using P = FftPlan<L>;
+    static_assert(!WS || L / P::EPT <= 32, "warp-synchronous transform: the cooperating threads must fit one warp");
     fft_reg_stage<L, P::R0, 1>(t, x, tw.s1);
     if constexpr (P::NS >= 2) {
-        fft_reg_exchange<L, P::R0, 1, P::R1>(t, sb, x);
+        fft_reg_exchange<L, P::R0, 1, P::R1, WS>(t, sb, x);
         fft_reg_stage<L, P::R1, P::R0>(t, x, tw.s1);
     }
     if constexpr (P::NS >= 3) {
-        __syncthreads();                         // reads of the first exchange done before the second writes
-        fft_reg_exchange<L, P::R1, P::R0, P::R2>(t, sb, x);
+        if (WS) __syncwarp(); else __syncthreads();   // reads of the first exchange done before the second writes
+        fft_reg_exchange<L, P::R1, P::R0, P::R2, WS>(t, sb, x);
         fft_reg_stage<L, P::R2, P::R0 * P::R1>(t, x, tw.s2);
     }
 }

@@ -22,6 +22,7 @@
 #include "cnn_tc.cuh"
 #include "tv_chambolle.cuh"
 #include "cdp.cuh"
+#include "small.cuh"
 
 namespace {
 
@@ -1018,4 +1019,65 @@ int pnp_graph_destroy(void* exec) {
     return PNP_OK;
 }
 
+}  // extern "C"
+
+namespace {
+constexpr int SMALL_C = 8;           // CTAs per cluster = per image
+template <int L>
+int launch_svrg_small(const pnp_csmri_svrg_small_args& a, cudaStream_t st) {
+    using K = pnp::SmallCfg<L, SMALL_C>;
+    const void* kernel = (const void*)pnp::k_csmri_svrg_small<L, SMALL_C>;
+    { const int rc = raise_smem_limit(kernel, (int)K::SMEM); if (rc != PNP_OK) return rc; }
+    pnp::SmallArgs k{};
+    k.z = a.z; k.xrec = a.xrec;
+    k.Y1 = reinterpret_cast<const float2*>(a.Y1); k.Y2 = reinterpret_cast<const float2*>(a.Y2);
+    k.Y1n = reinterpret_cast<const float2*>(a.Y1n); k.Y2n = reinterpret_cast<const float2*>(a.Y2n);
+    k.bits_full = a.bits_full; k.support = a.support; k.m0 = a.m0; k.support_img_stride = a.support_img_stride;
+    k.idx = a.idx; k.idx_img_stride = a.idx_img_stride; k.idx_iter_stride = a.idx_iter_stride;
+    k.snap_scale_ptr = a.snap_scale_ptr; k.snap_scale = a.snap_scale; k.step = a.step; k.step_img_stride = a.step_img_stride;
+    k.sig_log = a.sig_log; k.mse_log = a.mse_log; k.slot = a.slot; k.draw_counter = a.draw_counter;
+    k.batch = a.batch; k.n_inner = a.n_inner; k.T2 = a.T2; k.B = a.mini_batch_size; k.seed = a.seed;
+    k.lr_decay = a.lr_decay; k.sigma_modifier = a.sigma_modifier; k.fallback_sigma = a.fallback_sigma;
+    k.fallback_decay = a.fallback_decay;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)(a.batch * SMALL_C));
+    cfg.blockDim = dim3(K::NT);
+    cfg.dynamicSmemBytes = K::SMEM;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = SMALL_C; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    void* args[] = {(void*)&k};
+    CU_TRY(cudaLaunchKernelExC(&cfg, kernel, args));
+    return PNP_OK;
+}
+}  // namespace
+
+extern "C" {
+int pnp_csmri_svrg_small_supported(int H, int W) { return (H == W && (H == 128 || H == 256)) ? 1 : 0; }
+
+int pnp_csmri_svrg_small(const pnp_csmri_svrg_small_args* args, void* stream) {
+    if (!args) return fail(PNP_ERR_ARG, "null args");
+    const pnp_csmri_svrg_small_args& a = *args;
+    { const int rc = check_init(); if (rc != PNP_OK) return rc; }
+    if (!pnp_csmri_svrg_small_supported(a.H, a.W))
+        return fail(PNP_ERR_UNSUPPORTED, "pnp_csmri_svrg_small: %d x %d is not a square image of 128 or 256 pixels a side", a.H, a.W);
+    if (!a.z || !a.Y1 || !a.Y2 || !a.Y1n || !a.Y2n || !a.bits_full || !a.step || !a.sig_log)
+        return fail(PNP_ERR_ARG, "pnp_csmri_svrg_small: null pointer");
+    if (!a.idx && (!a.support || !a.m0)) return fail(PNP_ERR_ARG, "pnp_csmri_svrg_small: neither explicit minibatches nor a support list");
+    if (a.batch < 1 || a.n_inner < 0 || a.T2 < 1 || a.mini_batch_size < 1)
+        return fail(PNP_ERR_ARG, "pnp_csmri_svrg_small: batch, T2 and mini_batch_size must be >= 1, n_inner >= 0");
+    if (a.n_inner == 0) return PNP_OK;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    return a.H == 256 ? launch_svrg_small<256>(a, st) : launch_svrg_small<128>(a, st);
+}
+
+int pnp_advance_by(int* counters, int n, int delta, void* stream) {
+    if (!counters || n < 1 || n > 32) return fail(PNP_ERR_ARG, "bad argument");
+    pnp::k_advance_by<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(counters, n, delta);
+    LAUNCH_CHECK();
+    return PNP_OK;
+}
 }  // extern "C"

@@ -1,0 +1,437 @@
+// PnP-SVRG (paper-mode variance reduction) + wavelet prox for SMALL CSMRI images: one thread-block CLUSTER per image,
+// the whole run -- every snapshot gradient and every inner iteration -- in ONE launch, the image resident in the
+// cluster's shared memory.
+//
+// Reference: algorithms/pnp_svrg.py:26-95 (the loop), problems/CSMRI.py:76-89 (gradients), denoisers/TV.py:21-26 and
+// the estimate_sigma call at pnp_svrg.py:71 (prox).  Same arithmetic as the three-pass path of csmri.cuh + prox.cuh
+// (same FFT plan, same unpacking, same selection, same epilogues, same sigma estimate and shrink), so the two paths
+// agree to fp32 rounding of a few reductions.
+//
+// WHY.  A 256x256 iteration moves ~2 MB: on the multi-launch path it is five dependent grid-wide steps of ~4 us each
+// (launch + drain + first-load latency), 1 % of the HBM roofline.  Here nothing leaves the SMs:
+//   * cluster of C = 8 CTAs, CTA q owns the lines [q L/C, (q+1) L/C) of z, w and mu (shared memory, padded rows) and
+//     the packed spectrum rows [q L/(2C), (q+1) L/(2C));
+//   * the two transpositions of the 2-D transform are 16-byte stores into the shared memory of the CTA that owns the
+//     destination row / line pair (distributed shared memory), followed by a cluster barrier;
+//   * an FFT of length L <= 256 is done by T = L/16 <= 16 threads, i.e. inside one warp: the Stockham exchanges need
+//     warp barriers only (fft_regs<L, true>), the warps of a phase do not run in lock step;
+//   * the minibatch selection of iteration t is built in shared memory by the warps that have no transform in the
+//     forward line phase (every CTA scans the B drawn positions and keeps the bits of its own rows);
+//   * the sigma estimate's mean over lines is a cluster reduction: every CTA writes its partial sum into a slot of
+//     every peer and all of them add the C slots in the same order (deterministic, identical in all CTAs).
+// Per inner iteration: 3 cluster barriers, no global traffic except the ground truth (L2) for the PSNR log.
+// Batches: blockIdx.x / C = image; the sweeps launch one cluster per reconstruction.
+#pragma once
+#include <cooperative_groups.h>
+#include "csmri.cuh"
+#include "prox.cuh"
+
+namespace pnp {
+
+struct SmallArgs {
+    float* z;                         // [batch][L lines][L] iterate, in / out
+    const float* xrec;                // optional ground truth, same layout (PSNR log)
+    const float2 *Y1, *Y2, *Y1n, *Y2n;
+    const unsigned char* bits_full;   // [batch][L/2][L] selection bytes of the full mask (set_sel_bits layout)
+    const int* support;               // device sampler: sampled positions per image
+    const int* m0;
+    long long support_img_stride;
+    const int* idx;                   // explicit minibatches (optional): idx[img * img_stride + t * iter_stride + i]
+    long long idx_img_stride, idx_iter_stride;
+    const float* snap_scale_ptr;      // per image 1/M0 (or null: snap_scale)
+    float snap_scale;
+    const float* step;                // per image step of the first epoch of this launch
+    long long step_img_stride;        // 0: one step for all images
+    double* sig_log;                  // [slot][batch] accumulated (+=), slots slot0 .. slot0 + n_inner - 1
+    double* mse_log;
+    const int* slot;                  // optional device counters: first log slot, first draw counter
+    const int* draw_counter;
+    int batch, n_inner, T2, B;
+    unsigned seed;
+    float lr_decay, sigma_modifier, fallback_sigma, fallback_decay;
+};
+
+template <int L, int C> struct SmallCfg {
+    static constexpr int T = fft_threads<L>();
+    static constexpr int EPT = FftPlan<L>::EPT;
+    static constexpr int NT = 512, NW = NT / 32;
+    static constexpr int LPC = L / C;                       // lines per CTA
+    static constexpr int PPC = LPC / 2;                     // line pairs per CTA = transforms per line phase
+    static constexpr int RPC = (L / 2) / C;                 // packed spectrum rows per CTA (== PPC)
+    static constexpr int LS = L + 8;                        // line stride (floats): the two lines of the half-warps of a warp sit 16 banks apart
+    static constexpr int PL2 = 2 * fft_plane<L>();
+    static constexpr int GS = PL2 + ((2 - PL2 % 32) + 32) % 32;   // exchange-buffer stride == 2 (mod 32): group g is shifted by g float2
+    static constexpr int GPW = 32 / T;                      // transforms per warp
+    static constexpr int FW = PPC * T / 32;                 // warps that transform in a phase
+    static constexpr int NEX = PPC + GPW;                   // + the warp of packed row 0
+    static constexpr int NLW = LPC / NW;                    // lines per warp in the prox phases
+    static constexpr int EXF = NEX * GS > NW * PNP_SIG_SCRATCH ? NEX * GS : NW * PNP_SIG_SCRATCH;
+    static constexpr int OFF_Z = 0;
+    static constexpr int OFF_W = OFF_Z + LPC * LS;
+    static constexpr int OFF_MU = OFF_W + LPC * LS;
+    static constexpr int OFF_S = OFF_MU + LPC * LS;         // float2 [RPC][L]
+    static constexpr int OFF_T = OFF_S + RPC * L * 2;       // float4 [L/2][PPC]
+    static constexpr int OFF_EX = OFF_T + (L / 2) * PPC * 4;
+    static constexpr int OFF_BITS = (OFF_EX + EXF + 3) & ~3;          // 2 x RPC x L bytes
+    static constexpr int OFF_RED = OFF_BITS + 2 * RPC * L / 4;        // doubles: [C] sigma slots, [NW] + [NW] per-warp partials
+    static constexpr int FLOATS = OFF_RED + 2 * (C + 2 * NW);
+    static constexpr size_t SMEM = sizeof(float) * (size_t)FLOATS;
+    static_assert(PPC == RPC, "line pairs and packed rows per CTA");
+    static_assert(T <= 32 && 32 % T == 0 && (PPC * T) % 32 == 0 && FW + 1 <= NW, "transform groups must tile whole warps");
+    static_assert(LPC % NW == 0 && NLW >= 1 && NLW <= 2, "one or two lines per warp in the prox phases");
+    static_assert(L % 128 == 0 && L <= 256, "chunk-cyclic Haar layout: 128 or 256 samples per line");
+    static_assert(OFF_RED % 2 == 0, "double alignment");
+};
+
+__device__ __forceinline__ void named_bar(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+
+// the two packed targets of k-space position k (set_sel_bits of csmri.cuh), kept when they fall into rows [row0, row0 + nrows)
+__device__ __forceinline__ void or_local(unsigned char* bits, int L, int row0, int nrows, int row, int col, unsigned v) {
+    const int r = row - row0;
+    if (r < 0 || r >= nrows) return;
+    const int byte_idx = r * L + col;
+    atomicOr(reinterpret_cast<unsigned*>(bits) + (byte_idx >> 2), v << (8 * (byte_idx & 3)));
+}
+__device__ __forceinline__ void set_sel_bits_local(unsigned char* bits, int L, int row0, int nrows, int k) {
+    const int ky = k / L, kx = k % L, hp = L / 2;
+    const int kym = (L - ky) % L, kxm = (L - kx) % L;
+    if (ky < hp) or_local(bits, L, row0, nrows, ky, kx, 1u);
+    else if (ky == hp) or_local(bits, L, row0, nrows, 0, kx, 4u);
+    if (kym < hp) or_local(bits, L, row0, nrows, kym, kxm, 2u);
+    else if (kym == hp) or_local(bits, L, row0, nrows, 0, kxm, 8u);
+}
+
+template <int L, int C>
+__global__ void __launch_bounds__(512, 1) k_csmri_svrg_small(SmallArgs a) {
+    using K = SmallCfg<L, C>;
+    using IX = FftIdx<L>;
+    constexpr int T = K::T, EPT = K::EPT, LPC = K::LPC, PPC = K::PPC, RPC = K::RPC, LS = K::LS, GS = K::GS, FW = K::FW,
+                  NW = K::NW, NLW = K::NLW, GPW = K::GPW;
+    constexpr int FT = FW * 32;                                  // threads that transform
+    constexpr int LEVELS = HaarCfg<L>::LEVELS, NCH = L / 128;
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    const int q = (int)cluster.block_rank();
+    const int img = blockIdx.x / C;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    extern __shared__ __align__(128) float smem[];
+    float* zl = smem + K::OFF_Z;
+    float* wl = smem + K::OFF_W;
+    float* mul = smem + K::OFF_MU;
+    float2* Sb = reinterpret_cast<float2*>(smem + K::OFF_S);
+    float4* Tb = reinterpret_cast<float4*>(smem + K::OFF_T);
+    float* ex = smem + K::OFF_EX;
+    unsigned char* bits_mb = reinterpret_cast<unsigned char*>(smem + K::OFF_BITS);
+    unsigned char* bits_fu = bits_mb + RPC * L;
+    double* red_sig = reinterpret_cast<double*>(smem + K::OFF_RED);
+    double* red_w = red_sig + C;
+    double* red_e = red_w + NW;
+
+    const long long N = (long long)L * L;
+    float* zg = a.z + (long long)img * N + (long long)q * LPC * L;
+    const float* xg = a.xrec ? a.xrec + (long long)img * N + (long long)q * LPC * L : nullptr;
+    const long long yoff = (long long)img * (L / 2) * L;
+    const bool is_fft = tid < FT;
+    const int g = is_fft ? tid / T : 0, t = tid % T;
+    const SmemBuf sb{ex + g * GS, nullptr};
+    FftTw<L> tw;
+    tw.init(t);
+
+    // ---- resident state: my lines of z, my rows of the full-mask selection ----
+    for (int i = tid; i < LPC * (L / 4); i += K::NT) {
+        const int l = i / (L / 4), c = i % (L / 4);
+        reinterpret_cast<float4*>(zl + l * LS)[c] = reinterpret_cast<const float4*>(zg + (long long)l * L)[c];
+    }
+    {
+        const uint4* src = reinterpret_cast<const uint4*>(a.bits_full + yoff + (long long)q * RPC * L);
+        for (int i = tid; i < RPC * L / 16; i += K::NT) reinterpret_cast<uint4*>(bits_fu)[i] = src[i];
+    }
+    const int slot0 = a.slot ? *a.slot : 0;
+    const unsigned draw0 = a.draw_counter ? (unsigned)*a.draw_counter : 0u;
+    const float inv_n = (float)(1.0 / ((double)L * (double)L));
+    const float gs_snap = inv_n * (a.snap_scale_ptr ? a.snap_scale_ptr[img] : a.snap_scale);
+    const float gs_in = inv_n * (1.0f / (float)a.B);
+    double step_d = (double)a.step[(long long)img * a.step_img_stride];
+    float st = (float)step_d;
+    cluster.sync();                                              // every CTA of the cluster runs: remote stores may begin
+
+    // ================================================================= phases
+    // forward line pass: two real lines -> one complex transform, unpacked rows sent to their owners (k_lines_r2c)
+    auto phase_a = [&](bool sub) {
+        float2 x[EPT];
+        const float* la = zl + (2 * g) * LS;
+        const float* lw = wl + (2 * g) * LS;
+#pragma unroll
+        for (int i = 0; i < EPT; ++i) {
+            const int idx = IX::in(t, i);
+            float re = la[idx], im = la[idx + LS];
+            if (sub) { re -= lw[idx]; im -= lw[idx + LS]; }
+            x[i] = make_float2(re, im);
+        }
+        fft_regs<L, true>(t, sb, x, tw);
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < EPT; ++i) sb.put(IX::out(t, i), x[i]);
+        named_bar(1, FT);
+        float4* S4 = reinterpret_cast<float4*>(Sb);
+        for (int i = tid; i < PPC * (L / 2); i += FT) {
+            const int gg = i % PPC, k = i / PPC;
+            const SmemBuf sg{ex + gg * GS, nullptr};
+            const float2 xk = sg.get(k);
+            const float2 xm = sg.get(k == 0 ? L / 2 : L - k);
+            float4 o;
+            if (k == 0) o = make_float4(xk.x, xm.x, xk.y, xm.y);
+            else o = make_float4(0.5f * (xk.x + xm.x), 0.5f * (xk.y - xm.y), 0.5f * (xk.y + xm.y), 0.5f * (xm.x - xk.x));
+            float4* dst = cluster.map_shared_rank(S4, k / RPC) + (k % RPC) * (L / 2) + q * PPC + gg;
+            *dst = o;
+        }
+    };
+
+    // minibatch selection of inner iteration `it` into my rows (the warps without a transform in the line phase)
+    auto select = [&](int it) {
+        constexpr int NS = K::NT - FT;
+        const int sid = tid - FT;
+        for (int i = sid; i < RPC * L / 16; i += NS) reinterpret_cast<uint4*>(bits_mb)[i] = make_uint4(0u, 0u, 0u, 0u);
+        named_bar(2, NS);
+        if (a.idx) {
+            const int* src = a.idx + (long long)img * a.idx_img_stride + (long long)it * a.idx_iter_stride;
+            for (int i = sid; i < a.B; i += NS) set_sel_bits_local(bits_mb, L, q * RPC, RPC, src[i]);
+        } else {
+            const unsigned key = mix32(a.seed ^ mix32((draw0 + (unsigned)it) * 0x632be5abU + (unsigned)img));
+            const int* sup = a.support + (long long)img * a.support_img_stride;
+            const unsigned n = (unsigned)a.m0[img];
+            for (int i = sid; i < a.B; i += NS) {
+                if ((unsigned)i >= n) break;
+                set_sel_bits_local(bits_mb, L, q * RPC, RPC, sup[feistel_perm((unsigned)i, n, key)]);
+            }
+        }
+    };
+
+    // column pass on my packed rows: forward, selection (and measurements), inverse, sent to the owners of the lines
+    auto phase_b = [&](const unsigned char* bits, bool use_y) {
+        float2* T2f = reinterpret_cast<float2*>(Tb);             // [L/2][LPC]
+        if (is_fft) {
+            const int kyp = q * RPC + g;
+            const long long crow = yoff + (long long)kyp * L;
+            float2 x[EPT], y[EPT];
+            unsigned long long bbp = 0ull;
+#pragma unroll
+            for (int i = 0; i < EPT; ++i) x[i] = Sb[g * L + IX::in(t, i)];
+#pragma unroll
+            for (int m = 0; m < EPT; ++m) bbp |= (unsigned long long)(bits[g * L + t + T * m] & 0xFu) << (4 * m);
+            fft_regs<L, true>(t, sb, x, tw);
+#pragma unroll
+            for (int m = 0; m < EPT; ++m) {
+                const int kx = t + T * m;
+                const float2 o = apply_sel(x[IX::out_slot(m)], (unsigned)(bbp >> (4 * m)) & 0xFu, use_y, a.Y1 + crow + kx, a.Y2 + crow + kx);
+                y[IX::in_slot(m)] = cswap(o);
+            }
+            __syncwarp();
+            fft_regs<L, true>(t, sb, y, tw);
+            if (kyp != 0) {
+#pragma unroll
+                for (int i = 0; i < EPT; ++i) {
+                    const int c = IX::out(t, i);
+                    float2* dst = cluster.map_shared_rank(T2f, c / LPC) + kyp * LPC + (c % LPC);
+                    *dst = cswap(y[i]);
+                }
+            }
+        } else if (warp == FW && q == 0) {
+            // packed row 0: C = FFT(DC + i * Nyquist); split, select each of the two rows, re-pack (k_cols_mask, column 0)
+            const int g0 = lane / T;
+            const SmemBuf s0{ex + (PPC + g0) * GS, nullptr};
+            float2 x[EPT];
+#pragma unroll
+            for (int i = 0; i < EPT; ++i) x[i] = g0 == 0 ? Sb[IX::in(t, i)] : make_float2(0.f, 0.f);
+            fft_regs<L, true>(t, s0, x, tw);
+            __syncwarp();
+#pragma unroll
+            for (int i = 0; i < EPT; ++i) s0.put(IX::out(t, i), x[i]);
+            __syncwarp();
+            if (g0 == 0) {
+                const float2* y1i = a.Y1 + yoff;
+                const float2* y2i = a.Y2 + yoff;
+                const float2* y1n = a.Y1n + (long long)img * L;
+                const float2* y2n = a.Y2n + (long long)img * L;
+                for (int kx = t; kx <= L / 2; kx += T) {
+                    const int km = (L - kx) % L;
+                    const float2 ck = s0.get(kx), cm = s0.get(km);
+                    const float2 fdc = make_float2(0.5f * (ck.x + cm.x), 0.5f * (ck.y - cm.y));
+                    const float2 fny = make_float2(0.5f * (ck.y + cm.y), 0.5f * (cm.x - ck.x));
+                    const unsigned bk = bits[kx], bm = bits[km];
+                    const float2 dk = apply_sel(fdc, bk, use_y, y1i + kx, y2i + kx);
+                    const float2 nk = apply_sel(fny, bk >> 2, use_y, y1n + kx, y2n + kx);
+                    const float2 dm = apply_sel(make_float2(fdc.x, -fdc.y), bm, use_y, y1i + km, y2i + km);
+                    const float2 nm = apply_sel(make_float2(fny.x, -fny.y), bm >> 2, use_y, y1n + km, y2n + km);
+                    s0.put(kx, make_float2(dk.y + nk.x, dk.x - nk.y));
+                    if (km != kx) s0.put(km, make_float2(dm.y + nm.x, dm.x - nm.y));
+                }
+            }
+            __syncwarp();
+#pragma unroll
+            for (int i = 0; i < EPT; ++i) x[i] = s0.get(IX::in(t, i));
+            __syncwarp();
+            fft_regs<L, true>(t, s0, x, tw);
+            if (g0 == 0) {
+#pragma unroll
+                for (int i = 0; i < EPT; ++i) {
+                    const int c = IX::out(t, i);
+                    float2* dst = cluster.map_shared_rank(T2f, c / LPC) + (c % LPC);
+                    *dst = cswap(x[i]);
+                }
+            }
+        }
+    };
+
+    // inverse line pass + epilogue on my lines (k_lines_c2r): snap: mu = g * gs, w = z ; else z -= st * (g * gs + mu)
+    auto phase_c = [&](bool snap, float gs) {
+        if (!is_fft) return;
+        constexpr int NQ = (L / 2) / T;
+#pragma unroll
+        for (int n = 0; n < NQ; ++n) {
+            const int i = tid + n * FT;
+            const int gg = i % PPC, k = i / PPC;
+            const SmemBuf sg{ex + gg * GS, nullptr};
+            const float4 v = Tb[k * PPC + gg];
+            if (k == 0) {
+                sg.put(0, make_float2(v.z, v.x));
+                sg.put(L / 2, make_float2(v.w, v.y));
+            } else {
+                sg.put(k, make_float2(v.y + v.z, v.x - v.w));
+                sg.put(L - k, make_float2(v.z - v.y, v.x + v.w));
+            }
+        }
+        named_bar(1, FT);
+        float2 x[EPT];
+#pragma unroll
+        for (int i = 0; i < EPT; ++i) x[i] = sb.get(IX::in(t, i));
+        __syncwarp();
+        fft_regs<L, true>(t, sb, x, tw);
+        float* lz = zl + (2 * g) * LS;
+        float* lm = mul + (2 * g) * LS;
+        float* lw = wl + (2 * g) * LS;
+#pragma unroll
+        for (int i = 0; i < EPT; ++i) {
+            const int idx = IX::out(t, i);
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const float gval = (h == 0 ? x[i].y : x[i].x) * gs;          // swapped output: .y real -> line 2g, .x imag -> line 2g + 1
+                const int o = idx + h * LS;
+                if (snap) { lm[o] = gval; lw[o] = lz[o]; }
+                else lz[o] = lz[o] - st * (gval + lm[o]);
+            }
+        }
+        named_bar(1, FT);                                        // the exchange buffers become the prox scratch
+    };
+
+    // ================================================================= the run
+    // One pass of the loop body is either a snapshot (mu = grad_full(z) * snap_scale, w = z; pnp_svrg.py:32-35) or an
+    // inner iteration (v = g_B(z - w) / B + mu ; z <- prox(z - step * v); pnp_svrg.py:52-57, 71-76): both are the same
+    // three phases with different operands, so every phase has ONE call site (and is inlined).
+    bool need_snap = true;
+    for (int it = 0; it < a.n_inner;) {
+        const bool snap = need_snap;
+        if (snap && it > 0) { step_d *= (double)a.lr_decay; st = (float)step_d; }
+        if (is_fft) phase_a(!snap); else if (!snap) select(it);
+        cluster.sync();
+        phase_b(snap ? bits_fu : bits_mb, snap);
+        cluster.sync();
+        phase_c(snap, snap ? gs_snap : gs_in);
+        __syncthreads();
+        if (snap) { need_snap = false; continue; }
+
+        // sigma estimate per line + forward Haar pyramid kept in registers (neither needs the mean)
+        float hx[NLW][NCH][4], hA[NLW][NCH][6], hD[NLW][NCH][5], hT[NLW][4], level_ss[NLW];
+        float4 xr[NLW][NCH];
+        double sig_sum = 0.0;
+        unsigned* scratch = reinterpret_cast<unsigned*>(ex) + warp * PNP_SIG_SCRATCH;
+#pragma unroll
+        for (int j = 0; j < NLW; ++j) {
+            const int l = warp + NW * j;
+            float* sl = zl + l * LS;
+            sig_sum += line_sigma_mad<L>(sl, lane, scratch);
+            __syncwarp();
+            float ss[LEVELS];
+#pragma unroll
+            for (int c = 0; c < NCH; ++c) {
+                const float4 v = reinterpret_cast<const float4*>(sl)[c * 32 + lane];
+                hx[j][c][0] = v.x; hx[j][c][1] = v.y; hx[j][c][2] = v.z; hx[j][c][3] = v.w;
+                if (xg) xr[j][c] = reinterpret_cast<const float4*>(xg + (long long)l * L)[c * 32 + lane];
+            }
+#pragma unroll
+            for (int k = 0; k < LEVELS; ++k) ss[k] = 0.f;
+            haar_cc_forward<LEVELS, NCH>(hx[j], hA[j], hD[j], hT[j], ss, lane);
+            float mine_ss = 0.f;
+#pragma unroll
+            for (int k = 0; k < LEVELS; ++k) {
+                const float e = warp_sum_f(ss[k]);
+                mine_ss = lane == k ? e : mine_ss;
+            }
+            level_ss[j] = mine_ss;
+        }
+        if (lane == 0) red_w[warp] = sig_sum;
+        __syncthreads();
+        if (tid < C) {
+            double s = 0.0;
+#pragma unroll
+            for (int w = 0; w < NW; ++w) s += red_w[w];
+            *(cluster.map_shared_rank(red_sig, tid) + q) = s;    // my partial sum into slot q of CTA `tid`
+        }
+        cluster.sync();
+        double tot = 0.0;
+#pragma unroll
+        for (int r = 0; r < C; ++r) tot += red_sig[r];
+        const double se = tot / (double)L;
+        const float fb = a.fallback_decay == 1.0f ? a.fallback_sigma : a.fallback_sigma * powf(a.fallback_decay, (float)it);
+        const float sigma = (se > 0.0) ? (float)(se * (double)a.sigma_modifier) : fb;
+        const float var = sigma * sigma;
+        if (q == 0 && tid == 0) atomicAdd(a.sig_log + (long long)(slot0 + it) * a.batch + img, tot);
+
+        // BayesShrink thresholds, inverse pyramid, new iterate into the resident lines, squared error
+        float err = 0.f;
+#pragma unroll
+        for (int j = 0; j < NLW; ++j) {
+            const int l = warp + NW * j;
+            float thr[LEVELS];
+            {
+                const int k = lane < LEVELS ? lane : LEVELS - 1;
+                const float dvar = level_ss[j] / (float)(L >> (k + 1));
+                const float tk = var / sqrtf(fmaxf(dvar - var, 2.220446049250313e-16f));
+#pragma unroll
+                for (int kk = 0; kk < LEVELS; ++kk) thr[kk] = __shfl_sync(0xffffffffu, tk, kk);
+            }
+            haar_cc_inverse<LEVELS, NCH>(hx[j], hA[j], hD[j], hT[j], thr, lane);
+            float* sl = zl + l * LS;
+#pragma unroll
+            for (int c = 0; c < NCH; ++c) {
+                reinterpret_cast<float4*>(sl)[c * 32 + lane] = make_float4(hx[j][c][0], hx[j][c][1], hx[j][c][2], hx[j][c][3]);
+                if (xg) {
+                    const float e0 = hx[j][c][0] - xr[j][c].x, e1 = hx[j][c][1] - xr[j][c].y, e2 = hx[j][c][2] - xr[j][c].z,
+                                e3 = hx[j][c][3] - xr[j][c].w;
+                    err = fmaf(e0, e0, fmaf(e1, e1, fmaf(e2, e2, fmaf(e3, e3, err))));
+                }
+            }
+        }
+        if (xg && a.mse_log) {
+            err = warp_sum_f(err);
+            if (lane == 0) red_e[warp] = (double)err;
+        }
+        __syncthreads();                                         // my lines are complete: the next line pass may read them
+        if (xg && a.mse_log && tid == 0) {
+            double s = 0.0;
+#pragma unroll
+            for (int w = 0; w < NW; ++w) s += red_e[w];
+            atomicAdd(a.mse_log + (long long)(slot0 + it) * a.batch + img, s);
+        }
+        ++it;
+        need_snap = it % a.T2 == 0;
+    }
+
+    for (int i = tid; i < LPC * (L / 4); i += K::NT) {
+        const int l = i / (L / 4), c = i % (L / 4);
+        reinterpret_cast<float4*>(zg + (long long)l * L)[c] = reinterpret_cast<const float4*>(zl + l * LS)[c];
+    }
+}
+
+}  // namespace pnp

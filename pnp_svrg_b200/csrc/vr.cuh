@@ -67,6 +67,10 @@ k_saga_init(const float* __restrict__ g0, float* __restrict__ table, float* __re
     }
 }
 
+__global__ void k_advance_by(int* __restrict__ counters, int n, int delta) {
+    if (threadIdx.x < n) counters[threadIdx.x] += delta;
+}
+
 __global__ void k_advance(int* __restrict__ counters, int n, float* __restrict__ x, float factor) {
     if (threadIdx.x < n) counters[threadIdx.x] += 1;
     if (x && threadIdx.x == 0) *x *= factor;

@@ -86,7 +86,7 @@ def test_pspace_matches_the_objectives_argument_order():
         sp = sweep.get_pspace(algo)
         assert tuple(n.label for n in sp) == labels
         for n in sp:
-            if n.label in ('mini_batch_size', 'T2'):
+            if n.label in ('mini_batch_size', 'T2', 'hist_size'):      # hist_size: the 4th value tune_pnp_saga unpacks
                 assert n.as_int and n.kind == 'quniform' and (n.lo, n.hi, n.q) == (1, 100, 1)
             elif n.label == 'eta':
                 assert (n.lo, n.hi) == (0, 100)
