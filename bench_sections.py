@@ -110,14 +110,21 @@ def sweep_cpu_baseline(iters=200, T2=10, B=1000):
                       'float64 oracle port' % (iters, nproc), 'mean_psnr_final': float(np.mean(res))}
 
 
-def sweep(rank, world, dev, iters=200, size=256, batch=56, with_cpu=True):
+def sweep(rank, world, dev, iters=200, size=256, batch=60, with_cpu=True, pipelined=True):
     import torch
     from conftest import synth_image
     from pnp_svrg_b200 import sweep as SW
     images = {i: synth_image(size, size, i) for i in range(12)}
     jobs = SW.make_jobs(list(range(12)))                     # 12 x 10 x 7 = 840
-    batch_runner = lambda group: SW.reconstruct_batch(group, H=size, W=size, iters=iters, images=images, construct='device')
-    batch_runner(jobs[:batch])                               # warm-up: allocations, graph capture
+    if pipelined:
+        # double-buffered engines: batch k + 1 is built on the device while batch k runs
+        batch_runner = SW.DeviceBatchPipeline(H=size, W=size, iters=iters, images=images)
+        batch_runner.submit(jobs[:batch])                    # warm-up: allocations of both engines
+        batch_runner.submit(jobs[batch:2 * batch])
+        batch_runner.drain()
+    else:
+        batch_runner = lambda group: SW.reconstruct_batch(group, H=size, W=size, iters=iters, images=images, construct='device')
+        batch_runner(jobs[:batch])                           # warm-up: allocations, graph capture
     _barrier(world, dev)
     t0 = time.time()
     recs = SW.run_partitioned_batched(jobs, batch_runner, rank, world, batch=batch, gather=True)
@@ -132,7 +139,7 @@ def sweep(rank, world, dev, iters=200, size=256, batch=56, with_cpu=True):
         return None
     ok = [r for r in recs if 'error' not in r]
     out = {'workload': '12 synthetic images x 10 sampling ratios x 7 SNRs = %d CSMRI %dx%d PnP-SVRG (paper mode) + wavelet-prox '
-                       'reconstructions, %d inner iterations each, batches of %d per launch, problems built on the device; '
+                       'reconstructions, %d inner iterations each, batches of %d per launch (one thread-block cluster per reconstruction), problems built on the device while the previous batch runs; '
                        'jobs dealt round-robin over the ranks, no data-path collective' % (len(jobs), size, size, iters, batch),
            'value': len(recs) / dt, 'unit': 'recon/s', 'jobs': len(recs), 'failed': len(recs) - len(ok), 'seconds': dt, 'n_gpus': world,
            'inner_iterations_per_s': len(recs) * iters / dt,

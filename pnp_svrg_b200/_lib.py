@@ -140,6 +140,7 @@ PROTOTYPES = {
                                   C.c_void_p]),
     'pnp_csmri_svrg_small': (C.c_int, [C.POINTER(SvrgSmallArgs), C.c_void_p]),
     'pnp_csmri_svrg_small_supported': (C.c_int, [C.c_int, C.c_int]),
+    'pnp_csmri_svrg_small_capacity': (C.c_int, [C.c_int, C.c_int]),
     'pnp_advance': (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
     'pnp_advance_by': (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     'pnp_advance_scale': (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_float, C.c_void_p]),

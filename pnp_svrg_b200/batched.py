@@ -184,9 +184,13 @@ class BatchedSVRG:
         self.outer = 0
         self.fused_prox = True
         self.whole_run_graph = False     # sweeps set it: capture all iterations of a run as one graph (see _capture_run)
-        # 128^2 / 256^2: the whole run is ONE launch, one thread-block cluster per problem (csrc/small.cuh)
-        self.use_small = (os.environ.get('PNP_SMALL', '1') != '0'
-                          and self.lib.pnp_csmri_svrg_small_supported(int(self.H), int(self.W)) == 1)
+        # 128^2 / 256^2, and no more problems than clusters fit the device (15 on a B200): the whole run is ONE launch, one
+        # thread-block cluster per problem (csrc/small.cuh).  Larger batches would run in waves of 15 clusters on 120 of
+        # the 148 SMs; the three-pass kernels with the batch dimension (and two batches in flight, sweep.DeviceBatchPipeline)
+        # then use the device better.  PNP_SMALL=0: never, PNP_SMALL=2: always (tests, measurements).
+        mode = os.environ.get('PNP_SMALL', '1')
+        self.use_small = (mode != '0' and self.lib.pnp_csmri_svrg_small_supported(int(self.H), int(self.W)) == 1
+                          and (mode == '2' or nb <= self.lib.pnp_csmri_svrg_small_capacity(int(self.H), int(self.W))))
         self._run_graph, self._run_graph_n = None, None
 
     def check(self, rc):

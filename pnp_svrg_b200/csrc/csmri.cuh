@@ -71,29 +71,39 @@ __device__ __forceinline__ unsigned mix32(unsigned x) {
 // passes per index).  Rounds alternate (l, r) -> (r, (l + F(r)) mod b) and (l, r) -> (r, (l + F(r)) mod a); the
 // reduction of F to [0, b) is a multiply-high, so there is no division.  Host twins: host_sampler.cpp and
 // engine.feistel_sample (NumPy) produce the same sequence bit for bit.
-__device__ __forceinline__ unsigned feistel_perm(unsigned i, unsigned n, unsigned key) {
+struct FeistelDom { int hb; unsigned hm, b; };          // domain of the permutation of [0, n): depends on n only
+__device__ __forceinline__ FeistelDom feistel_domain(unsigned n) {
     int hb = 1;
     while ((1u << (2 * hb)) < n) ++hb;                 // a = 2^hb, a*a >= n
     const unsigned hm = (1u << hb) - 1u;
-    const unsigned b = (n + hm) >> hb;                 // ceil(n / a) <= a
-    unsigned x = i;
-    do {
-        unsigned l = x >> hb, r = x & hm;              // l in Z_b, r in Z_a
+    return FeistelDom{hb, hm, (n + hm) >> hb};         // b = ceil(n / a) <= a
+}
+// one pass of the network over the domain a*b (a bijection of [0, a*b))
+__device__ __forceinline__ unsigned feistel_pass(unsigned x, unsigned key, const FeistelDom& d) {
+    const int hb = d.hb;
+    const unsigned hm = d.hm, b = d.b;
+    unsigned l = x >> hb, r = x & hm;                  // l in Z_b, r in Z_a
 #pragma unroll
-        for (int rd = 0; rd < 4; rd += 2) {
-            const unsigned f0 = __umulhi(mix32(r ^ (key + 0x9e3779b9U * (rd + 1))), b);
-            unsigned t = l + f0;                        // < 2b
-            t = t >= b ? t - b : t;
-            l = r;                                      // (l, r) now in Z_a x Z_b
-            r = t;
-            const unsigned f1 = mix32(r ^ (key + 0x9e3779b9U * (rd + 2))) & hm;
-            t = (l + f1) & hm;
-            l = r;                                      // back in Z_b x Z_a
-            r = t;
-        }
-        x = (l << hb) | r;
-    } while (x >= n);
+    for (int rd = 0; rd < 4; rd += 2) {
+        const unsigned f0 = __umulhi(mix32(r ^ (key + 0x9e3779b9U * (rd + 1))), b);
+        unsigned t = l + f0;                            // < 2b
+        t = t >= b ? t - b : t;
+        l = r;                                          // (l, r) now in Z_a x Z_b
+        r = t;
+        const unsigned f1 = mix32(r ^ (key + 0x9e3779b9U * (rd + 2))) & hm;
+        t = (l + f1) & hm;
+        l = r;                                          // back in Z_b x Z_a
+        r = t;
+    }
+    return (l << hb) | r;
+}
+__device__ __forceinline__ unsigned feistel_perm(unsigned i, unsigned n, unsigned key, const FeistelDom& d) {
+    unsigned x = i;
+    do { x = feistel_pass(x, key, d); } while (x >= n);          // cycle walking
     return x;
+}
+__device__ __forceinline__ unsigned feistel_perm(unsigned i, unsigned n, unsigned key) {
+    return feistel_perm(i, n, key, feistel_domain(n));
 }
 
 

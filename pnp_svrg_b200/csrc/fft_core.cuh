@@ -30,7 +30,9 @@ namespace pnp {
 struct TraceEv { unsigned long long t; int tag; short cta; short sm; };
 #ifdef PNP_TRACE
 #define PNP_TRACE_MAX (1 << 20)
+#ifndef PNP_TRACE_CTA
 #define PNP_TRACE_CTA 40
+#endif
 __device__ TraceEv g_trace[PNP_TRACE_MAX];
 __device__ unsigned g_trace_n;
 __device__ int g_dbg_flags;          // experiment switches of trace builds (pnp_debug_set key 3)

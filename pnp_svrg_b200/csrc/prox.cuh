@@ -175,6 +175,178 @@ __device__ __forceinline__ double line_sigma_mad(const float* __restrict__ x, in
     return 0.5 * ((double)__uint_as_float(v1) + (double)__uint_as_float(v2)) / 0.6744897501960817;
 }
 
+// NL lines by ONE warp, step by step side by side: the estimate of a short line is a chain of ~60 dependent warp
+// collectives (reductions, scans, ballots, shuffles) whose latency nothing hides when a warp works on a single line;
+// with the lines interleaved the chains overlap.  Same arithmetic, same result as line_sigma_mad, line by line.
+// x[j]: line j (shared memory); scratch[j]: PNP_SIG_SCRATCH words each.
+// NORM = false returns the median itself (the caller divides the SUM over its lines by Phi^-1(0.75) once: a double
+// division per line is ~10 % of the estimate's instructions for a 256-sample line).
+template <int L, int NL, bool NORM = true>
+__device__ __forceinline__ void line_sigma_mad_n(const float* const (&x)[NL], int lane, unsigned* const (&scratch)[NL], double (&out)[NL]) {
+    constexpr int NO = (L + 3) / 2;
+    constexpr int PER = (NO + 31) / 32;
+    const float h0 = -0.48296291314469025f, h1 = 0.836516303737469f,
+                h2 = -0.22414386804185735f, h3 = -0.12940952255092145f;
+    unsigned a[NL][PER], mn[NL], mx[NL], res[NL], v1[NL];
+    int nnz[NL], c_lo[NL], c_hi[NL], bit[NL], k1[NL], k2[NL];
+    bool empty[NL];
+#pragma unroll
+    for (int j = 0; j < NL; ++j) {
+        nnz[j] = 0; mn[j] = 0xffffffffu; mx[j] = 0u;
+#pragma unroll
+        for (int i = 0; i < PER; ++i) {
+            const int o = lane + 32 * i;
+            a[j][i] = 0xffffffffu;
+            if (o < NO) {
+                float d;
+                if (i > 0 && 32 * i + 31 <= (L - 2) / 2) {
+                    const float2 lo = *reinterpret_cast<const float2*>(x[j] + 2 * o - 2), hi = *reinterpret_cast<const float2*>(x[j] + 2 * o);
+                    d = fmaf(h0, hi.y, fmaf(h1, hi.x, fmaf(h2, lo.y, h3 * lo.x)));
+                } else {
+                    int i0 = 2 * o + 1, i1 = 2 * o, i2 = 2 * o - 1, i3 = 2 * o - 2;
+                    i0 = i0 >= L ? 2 * L - 1 - i0 : i0;
+                    i1 = i1 >= L ? 2 * L - 1 - i1 : i1;
+                    i2 = i2 < 0 ? -1 - i2 : (i2 >= L ? 2 * L - 1 - i2 : i2);
+                    i3 = i3 < 0 ? -1 - i3 : (i3 >= L ? 2 * L - 1 - i3 : i3);
+                    d = fmaf(h0, x[j][i0], fmaf(h1, x[j][i1], fmaf(h2, x[j][i2], h3 * x[j][i3])));
+                }
+                if (d != 0.f) {
+                    a[j][i] = __float_as_uint(fabsf(d));
+                    ++nnz[j];
+                    mn[j] = min(mn[j], a[j][i]);
+                    mx[j] = max(mx[j], a[j][i]);
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < NL; ++j) nnz[j] = warp_sum_i(nnz[j]);
+#pragma unroll
+    for (int j = 0; j < NL; ++j) {
+        empty[j] = nnz[j] == 0;                 // median of nothing = NaN: run the steps on one dummy key, discard the result
+        if (empty[j]) { nnz[j] = 1; if (lane == 0) { a[j][0] = 0x3f800000u; mn[j] = mx[j] = a[j][0]; } }
+        k1[j] = (nnz[j] - 1) >> 1; k2[j] = nnz[j] >> 1;
+    }
+#pragma unroll
+    for (int j = 0; j < NL; ++j) { mn[j] = __reduce_min_sync(0xffffffffu, mn[j]); mx[j] = __reduce_max_sync(0xffffffffu, mx[j]); }
+    int s[NL];
+    unsigned bin0[NL];
+#pragma unroll
+    for (int j = 0; j < NL; ++j) {
+        const int dbits = 32 - __clz(mx[j] ^ mn[j]);
+        s[j] = dbits > 8 ? dbits - 8 : 0;
+        bin0[j] = mn[j] >> s[j];
+        reinterpret_cast<uint4*>(scratch[j])[lane] = make_uint4(0u, 0u, 0u, 0u);
+        reinterpret_cast<uint4*>(scratch[j])[lane + 32] = make_uint4(0u, 0u, 0u, 0u);
+    }
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < NL; ++j) {
+#pragma unroll
+        for (int i = 0; i < PER; ++i)
+            if (a[j][i] != 0xffffffffu) atomicAdd(&scratch[j][(a[j][i] >> s[j]) - bin0[j]], 1u);
+    }
+    __syncwarp();
+    int hh[NL][8], part[NL], incl[NL];
+#pragma unroll
+    for (int j = 0; j < NL; ++j) {
+        const uint4 ha = reinterpret_cast<const uint4*>(scratch[j])[2 * lane], hb = reinterpret_cast<const uint4*>(scratch[j])[2 * lane + 1];
+        hh[j][0] = (int)ha.x; hh[j][1] = (int)ha.y; hh[j][2] = (int)ha.z; hh[j][3] = (int)ha.w;
+        hh[j][4] = (int)hb.x; hh[j][5] = (int)hb.y; hh[j][6] = (int)hb.z; hh[j][7] = (int)hb.w;
+        part[j] = hh[j][0] + hh[j][1] + hh[j][2] + hh[j][3] + hh[j][4] + hh[j][5] + hh[j][6] + hh[j][7];
+        incl[j] = part[j];
+    }
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+#pragma unroll
+        for (int j = 0; j < NL; ++j) {
+            const int v = __shfl_up_sync(0xffffffffu, incl[j], o);
+            if (lane >= o) incl[j] += v;
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < NL; ++j) {
+        int below = incl[j] - part[j];
+        const unsigned hit = __ballot_sync(0xffffffffu, below <= k1[j] && k1[j] < incl[j]);
+        const int src = __ffs(hit) - 1;
+        int b = 0, cnt = 0, found = 0;
+#pragma unroll
+        for (int jj = 0; jj < 8; ++jj) {
+            if (!found && below + hh[j][jj] > k1[j]) { b = 8 * lane + jj; cnt = hh[j][jj]; found = 1; }
+            if (!found) below += hh[j][jj];
+        }
+        b = __shfl_sync(0xffffffffu, b, src);
+        cnt = __shfl_sync(0xffffffffu, cnt, src);
+        below = __shfl_sync(0xffffffffu, below, src);
+        res[j] = (bin0[j] + (unsigned)b) << s[j];
+        c_lo[j] = below;
+        c_hi[j] = below + cnt;
+        bit[j] = s[j] - 1;
+    }
+    __syncwarp();                               // the histograms are dead: their words are reused for the candidates below
+#pragma unroll
+    for (int j = 0; j < NL; ++j) {              // rare: more than 32 keys in the median's bin
+        for (; bit[j] >= 0 && c_hi[j] - c_lo[j] > 32; --bit[j]) {
+            const unsigned cand = res[j] | (1u << bit[j]);
+            int c = 0;
+#pragma unroll
+            for (int i = 0; i < PER; ++i) c += a[j][i] < cand;
+            c = warp_sum_i(c);
+            if (c <= k1[j]) { res[j] = cand; c_lo[j] = c; } else { c_hi[j] = c; }
+        }
+    }
+    int base[NL];
+#pragma unroll
+    for (int j = 0; j < NL; ++j) {
+        const unsigned width = bit[j] >= 0 ? (2u << bit[j]) : 0u;       // bit < 0: every bit decided, no candidates
+        unsigned* cand_buf = scratch[j] + 256;
+        base[j] = 0;
+#pragma unroll
+        for (int i = 0; i < PER; ++i) {
+            const bool in = (a[j][i] - res[j]) < width;
+            const unsigned m = __ballot_sync(0xffffffffu, in);
+            if (in) cand_buf[base[j] + __popc(m & ((1u << lane) - 1u))] = a[j][i];
+            base[j] += __popc(m);
+        }
+    }
+    __syncwarp();
+    unsigned mine[NL];
+    int rnk[NL];
+#pragma unroll
+    for (int j = 0; j < NL; ++j) { mine[j] = lane < base[j] ? scratch[j][256 + lane] : 0xffffffffu; rnk[j] = 0; }
+    __syncwarp();
+    int nb = base[0];
+#pragma unroll
+    for (int j = 1; j < NL; ++j) nb = max(nb, base[j]);
+    for (int jj = 0; jj < nb; ++jj) {           // lanes >= base hold the sentinel, which ranks below nothing: stop at the last candidate
+#pragma unroll
+        for (int j = 0; j < NL; ++j) {
+            const unsigned u = __shfl_sync(0xffffffffu, mine[j], jj);
+            rnk[j] += (u < mine[j]) || (u == mine[j] && jj < lane);
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < NL; ++j) {
+        const int target = k1[j] - c_lo[j];
+        const unsigned hit = __ballot_sync(0xffffffffu, rnk[j] == target && mine[j] != 0xffffffffu);
+        const unsigned vc = __shfl_sync(0xffffffffu, mine[j], hit ? __ffs(hit) - 1 : 0);
+        v1[j] = bit[j] < 0 ? res[j] : vc;
+    }
+#pragma unroll
+    for (int j = 0; j < NL; ++j) {
+        unsigned v2 = v1[j];
+        int c = 0;
+        unsigned mnv = 0xffffffffu;
+#pragma unroll
+        for (int i = 0; i < PER; ++i) { c += a[j][i] <= v1[j]; if (a[j][i] > v1[j]) mnv = min(mnv, a[j][i]); }
+        c = warp_sum_i(c);
+        mnv = __reduce_min_sync(0xffffffffu, mnv);
+        if (k2[j] != k1[j] && c < k2[j] + 1) v2 = mnv;
+        const double med = 0.5 * ((double)__uint_as_float(v1[j]) + (double)__uint_as_float(v2));
+        out[j] = empty[j] ? __longlong_as_double(0x7ff8000000000000LL) : (NORM ? med / 0.6744897501960817 : med);
+    }
+}
+
 template <int L>
 __global__ void __launch_bounds__(128)
 k_sigma_mad(const float* __restrict__ z, int nlines, long long img_stride, double* __restrict__ sig_log,

@@ -51,10 +51,10 @@ struct SmallArgs {
     float lr_decay, sigma_modifier, fallback_sigma, fallback_decay;
 };
 
-template <int L, int C> struct SmallCfg {
+template <int L, int C, int NT_ = 512> struct SmallCfg {
     static constexpr int T = fft_threads<L>();
     static constexpr int EPT = FftPlan<L>::EPT;
-    static constexpr int NT = 512, NW = NT / 32;
+    static constexpr int NT = NT_, NW = NT / 32;
     static constexpr int LPC = L / C;                       // lines per CTA
     static constexpr int PPC = LPC / 2;                     // line pairs per CTA = transforms per line phase
     static constexpr int RPC = (L / 2) / C;                 // packed spectrum rows per CTA (== PPC)
@@ -65,15 +65,15 @@ template <int L, int C> struct SmallCfg {
     static constexpr int FW = PPC * T / 32;                 // warps that transform in a phase
     static constexpr int NEX = PPC + GPW;                   // + the warp of packed row 0
     static constexpr int NLW = LPC / NW;                    // lines per warp in the prox phases
-    static constexpr int EXF = NEX * GS > NW * PNP_SIG_SCRATCH ? NEX * GS : NW * PNP_SIG_SCRATCH;
+    static constexpr int EXF = NEX * GS > NW * NLW * PNP_SIG_SCRATCH ? NEX * GS : NW * NLW * PNP_SIG_SCRATCH;
     static constexpr int OFF_Z = 0;
     static constexpr int OFF_W = OFF_Z + LPC * LS;
     static constexpr int OFF_MU = OFF_W + LPC * LS;
     static constexpr int OFF_S = OFF_MU + LPC * LS;         // float2 [RPC][L]
     static constexpr int OFF_T = OFF_S + RPC * L * 2;       // float4 [L/2][PPC]
     static constexpr int OFF_EX = OFF_T + (L / 2) * PPC * 4;
-    static constexpr int OFF_BITS = (OFF_EX + EXF + 3) & ~3;          // 2 x RPC x L bytes
-    static constexpr int OFF_RED = OFF_BITS + 2 * RPC * L / 4;        // doubles: [C] sigma slots, [NW] + [NW] per-warp partials
+    static constexpr int OFF_BITS = (OFF_EX + EXF + 3) & ~3;          // 3 x RPC x L bytes: minibatch (double buffered), full mask
+    static constexpr int OFF_RED = OFF_BITS + 3 * RPC * L / 4;        // doubles: [C] sigma slots, [NW] + [NW] per-warp partials
     static constexpr int FLOATS = OFF_RED + 2 * (C + 2 * NW);
     static constexpr size_t SMEM = sizeof(float) * (size_t)FLOATS;
     static_assert(PPC == RPC, "line pairs and packed rows per CTA");
@@ -85,25 +85,57 @@ template <int L, int C> struct SmallCfg {
 
 __device__ __forceinline__ void named_bar(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 
-// the two packed targets of k-space position k (set_sel_bits of csmri.cuh), kept when they fall into rows [row0, row0 + nrows)
-__device__ __forceinline__ void or_local(unsigned char* bits, int L, int row0, int nrows, int row, int col, unsigned v) {
-    const int r = row - row0;
-    if (r < 0 || r >= nrows) return;
-    const int byte_idx = r * L + col;
-    atomicOr(reinterpret_cast<unsigned*>(bits) + (byte_idx >> 2), v << (8 * (byte_idx & 3)));
-}
-__device__ __forceinline__ void set_sel_bits_local(unsigned char* bits, int L, int row0, int nrows, int k) {
-    const int ky = k / L, kx = k % L, hp = L / 2;
+// see "Minibatch selection" in the kernel below; threads FT + 32 .. NT - 1 of the CTA take part.
+// or the bits of k-space position k (set_sel_bits of csmri.cuh) into the selection rows of their owner CTAs
+template <int L, int C, int NT, class Cluster>
+__device__ __forceinline__ void set_sel_bits_cluster(Cluster& cluster, unsigned char* bits, int k) {
+    constexpr int hp = L / 2, RPC = SmallCfg<L, C, NT>::RPC;
+    const int ky = k / L, kx = k % L;                              // L is a power of two: shifts and masks
     const int kym = (L - ky) % L, kxm = (L - kx) % L;
-    if (ky < hp) or_local(bits, L, row0, nrows, ky, kx, 1u);
-    else if (ky == hp) or_local(bits, L, row0, nrows, 0, kx, 4u);
-    if (kym < hp) or_local(bits, L, row0, nrows, kym, kxm, 2u);
-    else if (kym == hp) or_local(bits, L, row0, nrows, 0, kxm, 8u);
+    auto put = [&](int row, int col, unsigned v) {
+        const int byte_idx = (row % RPC) * L + col;
+        unsigned* w = cluster.map_shared_rank(reinterpret_cast<unsigned*>(bits), row / RPC) + (byte_idx >> 2);
+        atomicOr(w, v << (8 * (byte_idx & 3)));
+    };
+    if (ky < hp) put(ky, kx, 1u);
+    else if (ky == hp) put(0, kx, 4u);
+    if (kym < hp) put(kym, kxm, 2u);
+    else if (kym == hp) put(0, kxm, 8u);
 }
 
-template <int L, int C>
-__global__ void __launch_bounds__(512, 1) k_csmri_svrg_small(SmallArgs a) {
-    using K = SmallCfg<L, C>;
+// CTA q of the cluster draws positions q, q + C, ... of minibatch `it` and ORs their bits into buffer it & 1 of the CTAs
+// that own the rows (distributed shared-memory atomics; the buffers were zeroed a cluster barrier earlier)
+template <int L, int C, int NT, class Cluster>
+__device__ __forceinline__ void small_select(Cluster& cluster, const SmallArgs& a, unsigned char* bits_mb, int img, int q, unsigned draw0,
+                                             unsigned sel_n, const FeistelDom& sel_dom, int sel_count, int it) {
+    using K = SmallCfg<L, C, NT>;
+    constexpr int RPC = K::RPC, FT = K::FW * 32, NS = K::NT - FT - 32;
+    const int sid = (int)threadIdx.x - FT - 32;
+    if (sid < 0) return;
+    unsigned char* bits = bits_mb + (it & 1) * (RPC * L);
+    const int* src = a.idx ? a.idx + (long long)img * a.idx_img_stride + (long long)it * a.idx_iter_stride : nullptr;
+    const unsigned key = mix32(a.seed ^ mix32((draw0 + (unsigned)it) * 0x632be5abU + (unsigned)img));
+    const int* sup = a.support + (long long)img * a.support_img_stride;
+    for (int i = q + C * sid; i < sel_count; i += C * NS) {
+        int k;
+        if (src) k = src[i];
+        else k = sup[feistel_perm((unsigned)i, sel_n, key, sel_dom)];
+        set_sel_bits_cluster<L, C, NT>(cluster, bits, k);
+    }
+}
+template <int L, int C, int NT>
+__device__ __forceinline__ void small_select_clear(unsigned char* bits_mb, int buf) {
+    using K = SmallCfg<L, C, NT>;
+    constexpr int RPC = K::RPC, FT = K::FW * 32, NS = K::NT - FT - 32;
+    const int sid = (int)threadIdx.x - FT - 32;
+    if (sid < 0) return;
+    unsigned char* bits = bits_mb + buf * (RPC * L);
+    for (int i = sid; i < RPC * L / 16; i += NS) reinterpret_cast<uint4*>(bits)[i] = make_uint4(0u, 0u, 0u, 0u);
+}
+
+template <int L, int C, int NT = 512>
+__global__ void __launch_bounds__(NT, NT <= 256 ? 2 : 1) k_csmri_svrg_small(SmallArgs a) {
+    using K = SmallCfg<L, C, NT>;
     using IX = FftIdx<L>;
     constexpr int T = K::T, EPT = K::EPT, LPC = K::LPC, PPC = K::PPC, RPC = K::RPC, LS = K::LS, GS = K::GS, FW = K::FW,
                   NW = K::NW, NLW = K::NLW, GPW = K::GPW;
@@ -122,8 +154,8 @@ __global__ void __launch_bounds__(512, 1) k_csmri_svrg_small(SmallArgs a) {
     float2* Sb = reinterpret_cast<float2*>(smem + K::OFF_S);
     float4* Tb = reinterpret_cast<float4*>(smem + K::OFF_T);
     float* ex = smem + K::OFF_EX;
-    unsigned char* bits_mb = reinterpret_cast<unsigned char*>(smem + K::OFF_BITS);
-    unsigned char* bits_fu = bits_mb + RPC * L;
+    unsigned char* bits_mb = reinterpret_cast<unsigned char*>(smem + K::OFF_BITS);       // [2][RPC][L]
+    unsigned char* bits_fu = bits_mb + 2 * RPC * L;
     double* red_sig = reinterpret_cast<double*>(smem + K::OFF_RED);
     double* red_w = red_sig + C;
     double* red_e = red_w + NW;
@@ -154,7 +186,11 @@ __global__ void __launch_bounds__(512, 1) k_csmri_svrg_small(SmallArgs a) {
     const float gs_in = inv_n * (1.0f / (float)a.B);
     double step_d = (double)a.step[(long long)img * a.step_img_stride];
     float st = (float)step_d;
+    trace(500, true);
+    small_select_clear<L, C, NT>(bits_mb, 0);
+    small_select_clear<L, C, NT>(bits_mb, 1);
     cluster.sync();                                              // every CTA of the cluster runs: remote stores may begin
+    trace(501);
 
     // ================================================================= phases
     // forward line pass: two real lines -> one complex transform, unpacked rows sent to their owners (k_lines_r2c)
@@ -188,25 +224,17 @@ __global__ void __launch_bounds__(512, 1) k_csmri_svrg_small(SmallArgs a) {
         }
     };
 
-    // minibatch selection of inner iteration `it` into my rows (the warps without a transform in the line phase)
-    auto select = [&](int it) {
-        constexpr int NS = K::NT - FT;
-        const int sid = tid - FT;
-        for (int i = sid; i < RPC * L / 16; i += NS) reinterpret_cast<uint4*>(bits_mb)[i] = make_uint4(0u, 0u, 0u, 0u);
-        named_bar(2, NS);
-        if (a.idx) {
-            const int* src = a.idx + (long long)img * a.idx_img_stride + (long long)it * a.idx_iter_stride;
-            for (int i = sid; i < a.B; i += NS) set_sel_bits_local(bits_mb, L, q * RPC, RPC, src[i]);
-        } else {
-            const unsigned key = mix32(a.seed ^ mix32((draw0 + (unsigned)it) * 0x632be5abU + (unsigned)img));
-            const int* sup = a.support + (long long)img * a.support_img_stride;
-            const unsigned n = (unsigned)a.m0[img];
-            for (int i = sid; i < a.B; i += NS) {
-                if ((unsigned)i >= n) break;
-                set_sel_bits_local(bits_mb, L, q * RPC, RPC, sup[feistel_perm((unsigned)i, n, key)]);
-            }
-        }
-    };
+    // Minibatch selection of inner iteration `it`: selection bytes of my rows in buffer it & 1.  Built one iteration AHEAD
+    // by the warps that never transform (warp FW + 1 ..: warp FW owns packed row 0 in the column phase): every CTA draws
+    // 1/C of the positions and ORs the bits into the rows' owners through distributed shared memory, during the column
+    // phase of iteration it - 1; the buffer was zeroed by its owner during the inverse line phase of iteration it - 2,
+    // right after its last use.  Cluster barriers separate zeroing, filling and use.  (Inside the forward line phase,
+    // every CTA scanning all B positions for its own rows, the selection took 3.3 us for B = 1000 against 1.9 us of
+    // transforms; spread over the other phases the same work slowed those down by as much.)
+    const unsigned sel_n = a.idx ? 0u : (unsigned)a.m0[img];
+    const FeistelDom sel_dom = feistel_domain(sel_n > 1u ? sel_n : 2u);
+    const int sel_count = a.idx ? a.B : ((unsigned)a.B < sel_n ? a.B : (int)sel_n);
+    auto select = [&](int it) { small_select<L, C, NT>(cluster, a, bits_mb, img, q, draw0, sel_n, sel_dom, sel_count, it); };
 
     // column pass on my packed rows: forward, selection (and measurements), inverse, sent to the owners of the lines
     auto phase_b = [&](const unsigned char* bits, bool use_y) {
@@ -249,14 +277,16 @@ __global__ void __launch_bounds__(512, 1) k_csmri_svrg_small(SmallArgs a) {
 #pragma unroll
             for (int i = 0; i < EPT; ++i) s0.put(IX::out(t, i), x[i]);
             __syncwarp();
-            if (g0 == 0) {
+            {
+                // all lanes of the warp split / select / re-pack the spectrum of group 0
+                const SmemBuf sz{ex + PPC * GS, nullptr};
                 const float2* y1i = a.Y1 + yoff;
                 const float2* y2i = a.Y2 + yoff;
                 const float2* y1n = a.Y1n + (long long)img * L;
                 const float2* y2n = a.Y2n + (long long)img * L;
-                for (int kx = t; kx <= L / 2; kx += T) {
+                for (int kx = lane; kx <= L / 2; kx += 32) {
                     const int km = (L - kx) % L;
-                    const float2 ck = s0.get(kx), cm = s0.get(km);
+                    const float2 ck = sz.get(kx), cm = sz.get(km);
                     const float2 fdc = make_float2(0.5f * (ck.x + cm.x), 0.5f * (ck.y - cm.y));
                     const float2 fny = make_float2(0.5f * (ck.y + cm.y), 0.5f * (cm.x - ck.x));
                     const unsigned bk = bits[kx], bm = bits[km];
@@ -264,8 +294,8 @@ __global__ void __launch_bounds__(512, 1) k_csmri_svrg_small(SmallArgs a) {
                     const float2 nk = apply_sel(fny, bk >> 2, use_y, y1n + kx, y2n + kx);
                     const float2 dm = apply_sel(make_float2(fdc.x, -fdc.y), bm, use_y, y1i + km, y2i + km);
                     const float2 nm = apply_sel(make_float2(fny.x, -fny.y), bm >> 2, use_y, y1n + km, y2n + km);
-                    s0.put(kx, make_float2(dk.y + nk.x, dk.x - nk.y));
-                    if (km != kx) s0.put(km, make_float2(dm.y + nm.x, dm.x - nm.y));
+                    sz.put(kx, make_float2(dk.y + nk.x, dk.x - nk.y));
+                    if (km != kx) sz.put(km, make_float2(dm.y + nm.x, dm.x - nm.y));
                 }
             }
             __syncwarp();
@@ -329,15 +359,24 @@ __global__ void __launch_bounds__(512, 1) k_csmri_svrg_small(SmallArgs a) {
     // One pass of the loop body is either a snapshot (mu = grad_full(z) * snap_scale, w = z; pnp_svrg.py:32-35) or an
     // inner iteration (v = g_B(z - w) / B + mu ; z <- prox(z - step * v); pnp_svrg.py:52-57, 71-76): both are the same
     // three phases with different operands, so every phase has ONE call site (and is inlined).
+    if (a.n_inner > 0) select(0);                                // the first minibatch (a snapshot pass and its barriers come before its use)
     bool need_snap = true;
     for (int it = 0; it < a.n_inner;) {
         const bool snap = need_snap;
         if (snap && it > 0) { step_d *= (double)a.lr_decay; st = (float)step_d; }
-        if (is_fft) phase_a(!snap); else if (!snap) select(it);
+        trace(510);
+        if (is_fft) phase_a(!snap);
+        trace(511);
         cluster.sync();
-        phase_b(snap ? bits_fu : bits_mb, snap);
+        trace(512);
+        phase_b(snap ? bits_fu : bits_mb + (it & 1) * (RPC * L), snap);
+        if (!snap && it + 1 < a.n_inner) select(it + 1);
+        trace(513);
         cluster.sync();
+        trace(514);
         phase_c(snap, snap ? gs_snap : gs_in);
+        if (!snap) small_select_clear<L, C, NT>(bits_mb, it & 1);   // used by the column phase above; filled again next iteration
+        trace(515);
         __syncthreads();
         if (snap) { need_snap = false; continue; }
 
@@ -345,32 +384,61 @@ __global__ void __launch_bounds__(512, 1) k_csmri_svrg_small(SmallArgs a) {
         float hx[NLW][NCH][4], hA[NLW][NCH][6], hD[NLW][NCH][5], hT[NLW][4], level_ss[NLW];
         float4 xr[NLW][NCH];
         double sig_sum = 0.0;
-        unsigned* scratch = reinterpret_cast<unsigned*>(ex) + warp * PNP_SIG_SCRATCH;
+        {
+            const float* lx[NLW];
+            unsigned* scr[NLW];
+            double sg[NLW];
+#pragma unroll
+            for (int j = 0; j < NLW; ++j) {
+                lx[j] = zl + (warp + NW * j) * LS;
+                scr[j] = reinterpret_cast<unsigned*>(ex) + (warp * NLW + j) * PNP_SIG_SCRATCH;
+            }
+#ifndef PNP_SMALL_INTERLEAVE
+            // (two lines side by side in one warp -- line_sigma_mad_n<L, 2> -- measured 4 % slower: register pressure)
+#pragma unroll
+            for (int j = 0; j < NLW; ++j) {
+                const float* l1[1] = {lx[j]};
+                unsigned* s1[1] = {scr[j]};
+                double o1[1];
+                line_sigma_mad_n<L, 1, false>(l1, lane, s1, o1);
+                sg[j] = o1[0];
+            }
+#else
+            line_sigma_mad_n<L, NLW, false>(lx, lane, scr, sg);
+#endif
+#pragma unroll
+            for (int j = 0; j < NLW; ++j) sig_sum += sg[j];        // medians; / Phi^-1(0.75) once, after the cluster reduction
+        }
 #pragma unroll
         for (int j = 0; j < NLW; ++j) {
             const int l = warp + NW * j;
-            float* sl = zl + l * LS;
-            sig_sum += line_sigma_mad<L>(sl, lane, scratch);
-            __syncwarp();
-            float ss[LEVELS];
+            const float* sl = zl + l * LS;
 #pragma unroll
             for (int c = 0; c < NCH; ++c) {
                 const float4 v = reinterpret_cast<const float4*>(sl)[c * 32 + lane];
                 hx[j][c][0] = v.x; hx[j][c][1] = v.y; hx[j][c][2] = v.z; hx[j][c][3] = v.w;
                 if (xg) xr[j][c] = reinterpret_cast<const float4*>(xg + (long long)l * L)[c * 32 + lane];
             }
+        }
+        float ss[NLW][LEVELS];
 #pragma unroll
-            for (int k = 0; k < LEVELS; ++k) ss[k] = 0.f;
-            haar_cc_forward<LEVELS, NCH>(hx[j], hA[j], hD[j], hT[j], ss, lane);
+        for (int j = 0; j < NLW; ++j) {
+#pragma unroll
+            for (int k = 0; k < LEVELS; ++k) ss[j][k] = 0.f;
+            haar_cc_forward<LEVELS, NCH>(hx[j], hA[j], hD[j], hT[j], ss[j], lane);
+        }
+#pragma unroll
+        for (int j = 0; j < NLW; ++j) {
             float mine_ss = 0.f;
 #pragma unroll
             for (int k = 0; k < LEVELS; ++k) {
-                const float e = warp_sum_f(ss[k]);
+                const float e = warp_sum_f(ss[j][k]);
                 mine_ss = lane == k ? e : mine_ss;
             }
             level_ss[j] = mine_ss;
         }
         if (lane == 0) red_w[warp] = sig_sum;
+        trace(516);
         __syncthreads();
         if (tid < C) {
             double s = 0.0;
@@ -378,10 +446,13 @@ __global__ void __launch_bounds__(512, 1) k_csmri_svrg_small(SmallArgs a) {
             for (int w = 0; w < NW; ++w) s += red_w[w];
             *(cluster.map_shared_rank(red_sig, tid) + q) = s;    // my partial sum into slot q of CTA `tid`
         }
+        trace(517);
         cluster.sync();
+        trace(518);
         double tot = 0.0;
 #pragma unroll
         for (int r = 0; r < C; ++r) tot += red_sig[r];
+        tot /= 0.6744897501960817;
         const double se = tot / (double)L;
         const float fb = a.fallback_decay == 1.0f ? a.fallback_sigma : a.fallback_sigma * powf(a.fallback_decay, (float)it);
         const float sigma = (se > 0.0) ? (float)(se * (double)a.sigma_modifier) : fb;
@@ -417,6 +488,7 @@ __global__ void __launch_bounds__(512, 1) k_csmri_svrg_small(SmallArgs a) {
             err = warp_sum_f(err);
             if (lane == 0) red_e[warp] = (double)err;
         }
+        trace(519);
         __syncthreads();                                         // my lines are complete: the next line pass may read them
         if (xg && a.mse_log && tid == 0) {
             double s = 0.0;
@@ -432,6 +504,8 @@ __global__ void __launch_bounds__(512, 1) k_csmri_svrg_small(SmallArgs a) {
         const int l = i / (L / 4), c = i % (L / 4);
         reinterpret_cast<float4*>(zg + (long long)l * L)[c] = reinterpret_cast<const float4*>(zl + l * LS)[c];
     }
+    trace(520);
+    trace_flush();
 }
 
 }  // namespace pnp

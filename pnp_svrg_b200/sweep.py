@@ -151,10 +151,94 @@ def reconstruct_batch(jobs, H=256, W=256, eta_scale=0.15, T2=10, mini_batch_size
                  seconds=dt / len(jobs)) for i, j in enumerate(jobs)]
 
 
+class DeviceBatchPipeline:
+    """Device-built sweep batches, double buffered: while the batched engine of group k runs (its own stream), group
+    k + 1 is built on the current stream (batched.csmri_device_batch: mask, measurements, Xinit, support lists) and
+    loaded into the OTHER engine; the host only waits for a run when it needs its engine back or its records.
+    ``submit(group)`` enqueues a group and returns the records of the group that finished meanwhile (or None);
+    ``drain()`` returns the rest.  Same arguments and records as ``reconstruct_batch(..., construct='device')``."""
+
+    def __init__(self, H=256, W=256, eta_scale=0.15, T2=10, mini_batch_size=1000, iters=200, images=None, seed=0, depth=2):
+        self.kw = dict(H=H, W=W, eta_scale=eta_scale, T2=T2, mini_batch_size=mini_batch_size, iters=iters, images=images, seed=seed)
+        self.depth = depth
+        self.engines = {}            # (slot, shape key) -> BatchedSVRG
+        self.inflight = []           # (slot, run, jobs, t0)
+        self.n = 0
+
+    def _image(self, job):
+        images, H, W = self.kw['images'], self.kw['H'], self.kw['W']
+        img = images[job['image']] if images is not None and not isinstance(job['image'], str) else None
+        if img is None:
+            from PIL import Image
+            img = np.array(Image.open(job['image']).resize((H, W)))
+        return img
+
+    def _collect(self, entry):
+        slot, run, jobs, t0 = entry
+        out = run.results(with_z=False)
+        dt = time.time() - t0
+        iters = self.kw['iters']
+        return [dict(id=j['id'], image=str(j['image']), alpha=j['alpha'], snr=j['snr'], algo='pnp_svrg', denoiser='TV',
+                     psnr_init=float(out['psnr_init'][i]), psnr_final=float(out['psnr'][-1, i]), iters=iters,
+                     seconds=dt / len(jobs)) for i, j in enumerate(jobs)]
+
+    def submit(self, jobs):
+        from .batched import BatchedSVRG, csmri_device_batch
+        k = self.kw
+        t0 = time.time()
+        batch = csmri_device_batch([self._image(j) for j in jobs], [j['alpha'] for j in jobs], [j['snr'] for j in jobs], k['H'], k['W'],
+                                   seed=k['seed'] + jobs[0]['id'])
+        done = None
+        if len(self.inflight) >= self.depth:         # the engine this group needs: its previous run finished `depth` groups ago
+            done = self._collect(self.inflight.pop(0))
+        m0 = batch['m0_host']
+        B = int(min(k['mini_batch_size'], m0.min()))
+        etas = [min(k['eta_scale'] * float(m), 3.0 * B) for m in m0]
+        slot = self.n % self.depth
+        key = (slot, len(jobs), B)
+        run = self.engines.get(key)
+        if run is None:
+            run = self.engines[key] = BatchedSVRG(batch, T2=k['T2'], mini_batch_size=B, etas=etas, seed=k['seed'], max_slots=k['iters'])
+            run.whole_run_graph = True
+        else:
+            if any(e[1] is run for e in self.inflight):                  # same engine still in flight (depth 1 or odd shapes)
+                i = next(i for i, e in enumerate(self.inflight) if e[1] is run)
+                extra = self._collect(self.inflight.pop(i))
+                done = (done or []) + extra
+            run.reload(batch, etas)
+        run.run(k['iters'])
+        self.inflight.append((slot, run, jobs, t0))
+        self.n += 1
+        return done
+
+    def drain(self):
+        out = []
+        while self.inflight:
+            out.extend(self._collect(self.inflight.pop(0)))
+        return out
+
+    def close(self):
+        for run in self.engines.values():
+            run.close()
+        self.engines = {}
+
+
 def run_partitioned_batched(jobs, batch_runner, rank=0, world=1, batch=56, gather=True):
-    """Like run_partitioned, but this rank's share is processed in groups of `batch` jobs."""
+    """Like run_partitioned, but this rank's share is processed in groups of `batch` jobs.  ``batch_runner`` is a callable
+    group -> records, or a pipeline object with submit(group) / drain() (DeviceBatchPipeline)."""
     mine = partition(jobs, rank, world)
     local = []
+    if hasattr(batch_runner, 'submit'):
+        for k in range(0, len(mine), batch):
+            recs = batch_runner.submit(mine[k:k + batch])
+            if recs:
+                local.extend(recs)
+        local.extend(batch_runner.drain())
+        for r in local:
+            r['rank'] = rank
+        if gather and world > 1:
+            local = _gather_records(jobs, local, rank, world)
+        return sorted(local, key=lambda r: r['id'])
     for k in range(0, len(mine), batch):
         group = mine[k:k + batch]
         try:

@@ -19,7 +19,8 @@ def main():
     for tag, flag in (('three_pass', '0'), ('cluster', '1')):
         os.environ['PNP_SMALL'] = flag
         out[tag] = {'small': BS.small(0, 1, dev), 'sweep': BS.sweep(0, 1, dev, with_cpu=False),
-                    'sweep_batch148': BS.sweep(0, 1, dev, with_cpu=False, batch=148)}
+                    'sweep_serial_batches': BS.sweep(0, 1, dev, with_cpu=False, pipelined=False),
+                    'sweep_batch120': BS.sweep(0, 1, dev, with_cpu=False, batch=120)}
     os.environ.pop('PNP_SMALL', None)
     a, b = out['three_pass'], out['cluster']
     out['speedup'] = {'single_image': b['small']['value'] / a['small']['value'],

@@ -133,6 +133,23 @@ def test_small_kernel_equals_three_pass_path(cuda, H, src):
     assert np.allclose(a['psnr_per_iter'], b['psnr_per_iter'], atol=0.011)
 
 
+def test_small_batches_use_the_cluster_kernel_up_to_the_device_capacity(cuda):
+    from pnp_svrg_b200 import _lib
+    from pnp_svrg_b200.batched import BatchedSVRG, csmri_host_spec
+    H = 128
+    cap = _lib.load().pnp_csmri_svrg_small_capacity(H, H)
+    assert 1 <= cap <= 148 // 8 and _lib.load().pnp_csmri_svrg_small_capacity(64, 64) == 0
+    spec = csmri_host_spec(synth_image(H, H, 0), H, H, 0.5, 20., rng=np.random.RandomState(0))
+    for nb, want in ((cap, True), (cap + 1, False)):
+        b = BatchedSVRG([spec] * nb, T2=3, mini_batch_size=200, etas=[500.0] * nb, seed=1)
+        assert b.use_small == want
+        b.run(4)
+        out = b.results()
+        b.close()
+        assert np.all(out['psnr'][-1] > out['psnr_init'])
+        assert not np.array_equal(out['z'][0], out['z'][1])                # same problem, different sampler key (image index)
+
+
 def test_small_kernel_batch_equals_three_pass_batch(cuda):
     """one cluster per problem, a whole multi-epoch run with step decay in one launch == the batched three-pass engine"""
     from pnp_svrg_b200.batched import BatchedSVRG, csmri_host_spec
@@ -143,10 +160,10 @@ def test_small_kernel_batch_equals_three_pass_batch(cuda):
     specs = [csmri_host_spec(synth_image(H, H, s), H, H, a, snr, rng=np.random.RandomState(s)) for s, a, snr in cases]
     etas = [min(0.15 * s['M0'], 3.0 * 1000) for s in specs]
     outs = []
-    for small in ('0', '1'):
+    for small in ('0', '2'):           # 2: also for more problems than clusters fit the device (they run in waves)
         with _env(PNP_SMALL=small):
             b = BatchedSVRG(specs, T2=7, mini_batch_size=1000, etas=etas, seed=5, lr_decay=0.9, sigma_modifier=0.9)
-            assert b.use_small == (small == '1')
+            assert b.use_small == (small == '2')
             b.run(10)                  # 2 epochs, the second one cut short
             b.run(11)                  # continues: log slots, draw counters and the decayed step carry over
             outs.append(b.results())
