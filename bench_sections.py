@@ -110,12 +110,14 @@ def sweep_cpu_baseline(iters=200, T2=10, B=1000):
                       'float64 oracle port' % (iters, nproc), 'mean_psnr_final': float(np.mean(res))}
 
 
-def sweep(rank, world, dev, iters=200, size=256, batch=60, with_cpu=True, pipelined=True):
+def sweep(rank, world, dev, iters=200, size=256, batch=120, with_cpu=True, pipelined=True):
     import torch
     from conftest import synth_image
     from pnp_svrg_b200 import sweep as SW
     images = {i: synth_image(size, size, i) for i in range(12)}
     jobs = SW.make_jobs(list(range(12)))                     # 12 x 10 x 7 = 840
+    share = -(-len(jobs) // world)                           # jobs of one rank: equal groups of at most `batch`
+    batch = -(-share // -(-share // batch))
     if pipelined:
         # double-buffered engines: batch k + 1 is built on the device while batch k runs
         batch_runner = SW.DeviceBatchPipeline(H=size, W=size, iters=iters, images=images)
@@ -125,6 +127,8 @@ def sweep(rank, world, dev, iters=200, size=256, batch=60, with_cpu=True, pipeli
     else:
         batch_runner = lambda group: SW.reconstruct_batch(group, H=size, W=size, iters=iters, images=images, construct='device')
         batch_runner(jobs[:batch])                           # warm-up: allocations, graph capture
+    if world > 1:
+        SW._gather_records(jobs, [], rank, world)             # warm-up of the two collectives of the record gather (same shapes)
     _barrier(world, dev)
     t0 = time.time()
     recs = SW.run_partitioned_batched(jobs, batch_runner, rank, world, batch=batch, gather=True)

@@ -202,6 +202,11 @@ typedef struct {
     float* v_out;
     const float* z_in;
     float* z_out;
+    /* Optional scratch of partial_chunks * n floats: the transposed product A_sel^T r is then split over row chunks as
+     * well as columns (partial sums per chunk, added in order by a finishing kernel: deterministic) -- without it the
+     * column pass has n / 1024 CTAs, 4 for a 64 x 64 image.  partial_chunks >= 1; 64 is what the Python layer passes. */
+    float* partial;
+    int partial_chunks;
 } pnp_pr_grad_args;
 int pnp_pr_grad(const pnp_pr_grad_args* args, void* stream);
 

@@ -53,6 +53,7 @@ class PrGradArgs(C.Structure):
         ('rows', C.c_void_p), ('count', C.c_int), ('cursor', C.c_void_p), ('r', C.c_void_p),
         ('gscale', C.c_float), ('step', C.c_float), ('step_ptr', C.c_void_p),
         ('g_out', C.c_void_p), ('vadd', C.c_void_p), ('v_out', C.c_void_p), ('z_in', C.c_void_p), ('z_out', C.c_void_p),
+        ('partial', C.c_void_p), ('partial_chunks', C.c_int),
     ]
 
 

@@ -540,7 +540,7 @@ int pnp_saga_update(const float* g_new, float* g_prev, float* table, float* tsum
                     float step, const float* step_ptr, void* stream) {
     if (!g_new || !g_prev || !table || !tsum || !z || !slot_idx || n < 1 || batch < 1 || hist < 1)
         return fail(PNP_ERR_ARG, "bad argument");
-    pnp::k_saga_update<<<dim3(ew_blocks(n, 1), batch), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+    pnp::k_saga_update<<<dim3(ew_blocks(n, 4), batch), 256, 0, static_cast<cudaStream_t>(stream)>>>(
         g_new, g_prev, table, tsum, z, n, n, hist, slot_idx, slot_img_stride, cursor, step, step_ptr);
     LAUNCH_CHECK();
     return PNP_OK;
@@ -733,6 +733,16 @@ int pnp_pr_grad(const pnp_pr_grad_args* args, void* stream) {
     pnp::k_pr_rows<<<blocks, 256, 0, st>>>(a.A, a.z, a.w, a.y, a.rows, count, a.n, a.r, a.cursor);
     LAUNCH_CHECK();
     const long long n4 = a.n / 4;
+    if (a.partial && a.partial_chunks >= 1) {
+        int chunks = a.partial_chunks < count ? a.partial_chunks : count;
+        dim3 grid((unsigned)((n4 + 127) / 128), (unsigned)chunks);
+        pnp::k_pr_cols_split<<<grid, 128, 0, st>>>(a.A, a.r, a.rows, count, a.n, a.cursor, a.partial);
+        LAUNCH_CHECK();
+        pnp::k_pr_cols_finish<<<(unsigned)((n4 + 31) / 32), 256, 0, st>>>(a.partial, chunks, a.n, a.gscale, a.step, a.step_ptr,
+                                                                            a.g_out, a.vadd, a.v_out, a.z_in, a.z_out);
+        LAUNCH_CHECK();
+        return PNP_OK;
+    }
     pnp::k_pr_cols<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(a.A, a.r, a.rows, count, a.n, a.cursor, a.gscale, a.step,
                                                                  a.step_ptr, a.g_out, a.vadd, a.v_out, a.z_in, a.z_out);
     LAUNCH_CHECK();

@@ -14,14 +14,33 @@ from .. import _lib, device as D
 from .problem import Problem
 
 
+def shard_block(M, rank, world):
+    """rows [lo, hi) of A owned by `rank`: contiguous, disjoint, covering [0, M) (the last rank takes the remainder)"""
+    per = M // world
+    lo = rank * per
+    return lo, (M if rank == world - 1 else lo + per)
+
+
 class PhaseRetrieval(Problem):
     def __init__(self, img_path=None, H=256, W=256, num_meas=-1, snr=None, sigma=None, *, image=None,
-                 model='dense', n_masks=4, loss=None):
+                 model='dense', n_masks=4, loss=None, shard=None):
         super().__init__(img_path, H, W, image=image)
         self.pname = 'pr'
         if model not in ('dense', 'cdp'):
             raise ValueError("model must be 'dense' (the reference's) or 'cdp'")
         self.model = model
+        # shard = (rank, world): the FULL gradient (problems/PR.py:75-79, the M*N*4-byte stream that dominates an SVRG
+        # epoch) is cut into contiguous row blocks of A, one per rank; every rank computes the partial sum of its rows
+        # (already divided by the global M) and the partial gradients are summed by one all-reduce of 4N bytes
+        # (``_snapshot_allreduce``, used by pnp_svrg's snapshot and by grad_full).  Minibatch gradients are replicated.
+        if shard is not None:
+            if model != 'dense':
+                raise NotImplementedError('shard= is built for the dense model')
+            rank, world = int(shard[0]), int(shard[1])
+            if not (0 <= rank < world):
+                raise ValueError('shard = (rank, world) with 0 <= rank < world')
+            shard = (rank, world)
+        self.shard = shard
         if model == 'cdp':
             if loss not in (None, 'intensity'):
                 raise NotImplementedError("the coded-diffraction model is built with loss='intensity'")
@@ -78,6 +97,21 @@ class PhaseRetrieval(Problem):
         self._A = torch.from_numpy(np.ascontiguousarray(At, dtype=np.float32)).to(dev)
         self._y = torch.from_numpy(self.Y.astype(np.float32)).to(dev)
         self._r = torch.empty(self.M, dtype=torch.float32, device=dev)
+        # row-chunk partial sums of the transposed product (pnp_pr_grad_args.partial): without them the column pass of a
+        # 64 x 64 image is 4 CTAs (measured 492 us for a 33.6 MB matrix; 13.8 us for the row pass over the same bytes)
+        self._chunks = 64
+        self._partial = torch.empty(self._chunks * self.N, dtype=torch.float32, device=dev)
+        self._shard_sel = None
+        if self.shard is not None:
+            lo, hi = shard_block(int(self.M), *self.shard)
+            self._shard_block = (lo, hi)
+            self._shard_sel = torch.arange(lo, hi, dtype=torch.int32, device=dev)
+
+    def _snapshot_allreduce(self, mu):
+        """sum the per-rank partial full gradients (NCCL all-reduce of 4N bytes)"""
+        if self.shard is not None and self.shard[1] > 1:
+            import torch.distributed as dist
+            dist.all_reduce(mu, op=dist.ReduceOp.SUM)
 
     # ---- device protocol -----------------------------------------------------------------------
     def _dev_new_sel(self, count=0):
@@ -91,15 +125,24 @@ class PhaseRetrieval(Problem):
                                                   D.ptr(counter), D.stream()))
 
     def _dev_grad(self, a, b=None, sel=None, with_y=True, gscale=1.0, gscale_ptr=None, step=0.0, step_ptr=None,
-                  g_out=None, vadd=None, v_out=None, z_in=None, z_out=None, phases=0, clear_sel=False):
+                  g_out=None, vadd=None, v_out=None, z_in=None, z_out=None, phases=0, clear_sel=False, partial_ok=False):
         """g = [A_sel^T r(a)] - [A_sel^T r(b)] (two-point form when b is given), scaled by gscale."""
         if self.model == 'cdp':
             return self._dev_grad_cdp(a, b, sel, gscale, step, step_ptr, g_out, vadd, v_out, z_in, z_out)
+        if sel is None and self._shard_sel is not None:
+            if not partial_ok:
+                raise NotImplementedError('PhaseRetrieval(shard=...): the full gradient of a sharded problem is a partial sum; '
+                                          'only pnp_svrg (which all-reduces its snapshot) and grad_full() handle it')
+            if self._shard_sel.numel() == 0:
+                if g_out is not None:
+                    g_out.zero_()
+                return
+            sel = self._shard_sel
         args = _lib.PrGradArgs(
             A=D.ptr(self._A), n=self.N, M=int(self.M), z=D.ptr(a), w=D.ptr(b), y=D.ptr(self._y), rows=D.ptr(sel),
             count=0 if sel is None else int(sel.numel()), cursor=None, r=D.ptr(self._r), gscale=float(gscale),
             step=float(step), step_ptr=D.ptr(step_ptr), g_out=D.ptr(g_out), vadd=D.ptr(vadd), v_out=D.ptr(v_out),
-            z_in=D.ptr(z_in), z_out=D.ptr(z_out))
+            z_in=D.ptr(z_in), z_out=D.ptr(z_out), partial=D.ptr(self._partial), partial_chunks=self._chunks)
         _lib.check(_lib.load().pnp_pr_grad(C.byref(args), D.stream()))
 
     # ---- coded diffraction patterns (additive) ------------------------------------------------------
@@ -161,7 +204,12 @@ class PhaseRetrieval(Problem):
         """problems/PR.py:75-79."""
         zl = D.to_lines(z, self.H, self.W, self._device)
         g = torch.empty_like(zl)
-        self._dev_grad(zl, gscale=1.0 / self.M, g_out=g)
+        self._dev_grad(zl, gscale=1.0 / self.M, g_out=g, partial_ok=True)
+        if getattr(self, 'shard', None) is not None:
+            import torch.distributed as dist
+            if dist.is_available() and dist.is_initialized() and self.shard[1] > 1:
+                self._snapshot_allreduce(g)        # every rank returns the FULL gradient
+            # (without a process group the caller gets this shard's partial gradient: the single-process shard tests)
         return D.from_lines(g, self.H, self.W)
 
     def grad_stoch(self, z, mb):

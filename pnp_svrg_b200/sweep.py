@@ -164,6 +164,7 @@ class DeviceBatchPipeline:
         self.engines = {}            # (slot, shape key) -> BatchedSVRG
         self.inflight = []           # (slot, run, jobs, t0)
         self.n = 0
+        self.batch_size = None       # size of the first group: shorter groups (the tail of a rank's share) are padded to it
 
     def _image(self, job):
         images, H, W = self.kw['images'], self.kw['H'], self.kw['W']
@@ -175,6 +176,7 @@ class DeviceBatchPipeline:
 
     def _collect(self, entry):
         slot, run, jobs, t0 = entry
+        jobs = [j for j in jobs if not j.get('_pad')]
         out = run.results(with_z=False)
         dt = time.time() - t0
         iters = self.kw['iters']
@@ -186,6 +188,12 @@ class DeviceBatchPipeline:
         from .batched import BatchedSVRG, csmri_device_batch
         k = self.kw
         t0 = time.time()
+        if self.batch_size is None:
+            self.batch_size = len(jobs)
+        elif len(jobs) < self.batch_size:
+            # same shape as the engines that exist (no allocation, no new launch geometry inside a sweep): repeat the last job;
+            # the copies' records are dropped
+            jobs = list(jobs) + [dict(jobs[-1], _pad=True)] * (self.batch_size - len(jobs))
         batch = csmri_device_batch([self._image(j) for j in jobs], [j['alpha'] for j in jobs], [j['snr'] for j in jobs], k['H'], k['W'],
                                    seed=k['seed'] + jobs[0]['id'])
         done = None
