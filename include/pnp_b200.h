@@ -273,6 +273,9 @@ int pnp_prox_wavelet_fused(const float* z_in, float* z_out, int H, int W, int ba
  * PNP_ERR_UNSUPPORTED when the image lines do not fit the SMs' shared memory -- use the two calls then.
  * advance_counters (optional): the first n_advance ints are incremented at the end, as pnp_advance would (`slot`
  * may be one of them: it is read before).
+ * S = NULL means a zero spectrum: z_out = Denoise(z_in - step * vadd) without the inverse transforms.  That is the
+ * first inner iteration of every PnP-SVRG epoch (algorithms/pnp_svrg.py:53 with z == w: g_B(z) - g_B(w) is exactly 0,
+ * so the three transform passes of that iteration are skipped; same bits as running them on zeros).
  * barrier_ws (optional): two zero-initialised 32-bit words owned by the caller.  When given, the kernel is launched
  * normally and synchronises its CTAs (all co-resident: one per SM) with a software barrier on these words instead of a
  * cooperative launch -- the caller guarantees that no other kernel using such a barrier runs on the device at the same
@@ -281,6 +284,8 @@ int pnp_csmri_update_prox(const float* S, int H, int W, float gscale, float step
                           const float* z_in, float* z_out, double* sig_log, float sigma_modifier, float fallback_sigma,
                           const float* xrec, double* mse_log, const int* slot, int* advance_counters, int n_advance,
                           unsigned* barrier_ws, int chain, void* stream);
+/* 1 when pnp_csmri_update_prox handles H x W images on the current device, else 0 (host-side query, no launch) */
+int pnp_csmri_update_prox_supported(int H, int W);
 
 /* ---- whole PnP-SVRG runs of SMALL CSMRI images, one thread-block cluster per image ----------------------------
  * Replaces, for square images of 128 or 256 pixels a side, the whole loop of algorithms/pnp_svrg.py:26-95 in its

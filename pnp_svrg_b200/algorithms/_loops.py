@@ -27,29 +27,36 @@ def _grad_update(eng, a, b, sel, with_y, gscale, **kw):
     eng.p._dev_grad(a, b=b, sel=sel, with_y=with_y, gscale=gscale, clear_sel=sel is not None and sel is eng.sel, **kw)
 
 
-def _grad_update_prox(eng, a, b, sel, gscale, vadd, z, advance=0, sel_fn=None):
+def _grad_update_prox(eng, a, b, sel, gscale, vadd, z, advance=0, sel_fn=None, zero_grad=False):
     """z <- prox(z - step * (g_sel(a - b) * gscale + vadd)).  CSMRI + wavelet prox: the inverse line pass, the update,
     the sigma estimate and the prox run as ONE cooperative launch on lines resident in shared memory
     (pnp_csmri_update_prox); otherwise the gradient pass followed by ``eng.prox``.  ``advance`` > 0 also bumps
     that many end-of-iteration counters (``eng.advance``), inside the same launch when it is the fused one.
     ``sel_fn`` rebuilds the minibatch selection; on the CSMRI path the forward line pass does it itself
     (``Engine.sel_job``: a separate selection kernel cannot share an SM with a pass that holds every register, so
-    even on a parallel graph branch it delayed the column pass)."""
+    even on a parallel graph branch it delayed the column pass).
+    ``zero_grad``: the caller knows that a == b bit for bit (first inner iteration of an SVRG epoch, right after
+    ``w = copy(z)``), so g_sel(a - b) is exactly zero whatever the minibatch: on the fused CSMRI path the forward line
+    pass, the column pass and the inverse transforms are skipped (the tail kernel runs on a zero spectrum; same bits as
+    transforming zeros), the minibatch counters still advance.  Other paths ignore the hint."""
     p, d = eng.p, eng.d
     own = sel is not None and sel is eng.sel
     if (eng.fused_tail is not False and eng.uses_sigma and not eng.sigma_ready and getattr(d, 'method', None) == 'wavelet'
             and hasattr(p, '_dev_update_prox')):
         kw = dict(b=b, sel=sel, with_y=False, gscale=gscale, vadd=vadd, step_ptr=eng.step, z_in=z, z_out=z, clear_sel=own)
-        job = eng.sel_job() if (sel_fn is not None and own) else None
-        if job is None and sel_fn is not None:
-            sel_fn()
-        if eng.chain:
-            kw['chain'] = True
-        p._dev_grad(a, phases=3, sel_job=job, **kw)
+        skip = bool(zero_grad) and eng.fused_tail is True and own          # (the first fused call decides whether the tail applies)
+        if not skip:
+            job = eng.sel_job() if (sel_fn is not None and own) else None
+            if job is None and sel_fn is not None:
+                sel_fn()
+            if eng.chain:
+                kw['chain'] = True
+            p._dev_grad(a, phases=3, sel_job=job, **kw)
         ok = p._dev_update_prox(gscale, eng.step, vadd, z, z, eng.sig_log, d.sigma_modifier,
                                 d.denoise_strength * d.decay ** (d.t + 1), p._xrec_dev, eng.mse_log, eng.slot_ptr,
                                 advance=eng.counters if advance else None, n_advance=advance,
-                                barrier_ws=eng.barrier_ws if (eng.chain or eng.sw_barrier) else None, chain=eng.chain)
+                                barrier_ws=eng.barrier_ws if (eng.chain or eng.sw_barrier) else None, chain=eng.chain,
+                                zero_spectrum=skip)
         eng.fused_tail = ok
         if ok:
             d.t += 1
@@ -344,12 +351,13 @@ class SvrgRun:
         else:
             eng.check(eng.lib.pnp_axpy(D.ptr(z), D.ptr(self.mu), D.ptr(z), eng.N, 1, 0.0, D.ptr(eng.step), eng.sptr))
 
-    def fast_ops(self):
-        """one inner iteration as it is captured (per iteration, or T2 times inside an epoch graph)"""
+    def fast_ops(self, first_of_epoch=False):
+        """one inner iteration as it is captured (per iteration, or T2 times inside an epoch graph).
+        ``first_of_epoch``: z == w (the snapshot has just copied it), the stochastic term of line 53 is exactly zero"""
         eng, z = self.eng, self.z
         if self.paper:
             _grad_update_prox(eng, z, self.w, eng.sel, 1.0 / self.B, self.mu, z, advance=3,
-                              sel_fn=lambda: _sel_ops(eng))
+                              sel_fn=lambda: _sel_ops(eng), zero_grad=first_of_epoch)
         else:
             self.grad_ops()
             eng.prox(z, z)
@@ -408,7 +416,7 @@ class SvrgRun:
         for j in range(self.T2):
             if bufs is not None:
                 eng.idx_dev = bufs[j]
-            self.fast_ops()
+            self.fast_ops(first_of_epoch=(j == 0))
         if self.B > 0:
             eng.idx_dev = keep
         if self.lr_decay != 1.0:
@@ -432,6 +440,9 @@ class SvrgRun:
         with torch.cuda.stream(eng.stream):
             eng.set_step(self.eta * self.lr_decay ** self.i)
             # one eager epoch-shaped warm-up is NOT run: the kernels were loaded by pnp_init, and a capture does not execute
+        if eng.fused_tail is None and hasattr(self.problem, '_dev_update_prox'):
+            # known before the capture, so that the first inner iteration of every captured epoch can skip its transforms
+            eng.fused_tail = True if eng.lib.pnp_csmri_update_prox_supported(int(self.problem.H), int(self.problem.W)) == 1 else None
         t_before = self.denoiser.t
         # inside the epoch graph the passes form one chain on one stream: programmatic dependent launch lets every
         # kernel start its prologue (and the loads that do not depend on its predecessor) while the previous one drains

@@ -628,7 +628,7 @@ k_update_prox(const float2* __restrict__ S, int nlines, float inv_n, float gscal
             const int i = threadIdx.x + n * GP * T;
             const int gg = i % GP, k = i / GP;
             const int pl = round * GP + gg;
-            q[n] = pl < mine ? ldg_stream(S4 + (long long)k * npairs + first_pair + pl) : make_float4(0.f, 0.f, 0.f, 0.f);
+            q[n] = (S4 && pl < mine) ? ldg_stream(S4 + (long long)k * npairs + first_pair + pl) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
     };
     const int rounds = (mine + GP - 1) / GP;
@@ -643,28 +643,35 @@ k_update_prox(const float2* __restrict__ S, int nlines, float inv_n, float gscal
     if (threadIdx.x >= 32 + 2 * GP && threadIdx.x < 32 + 2 * mine)
         bulk_prefetch_l2(vadd + (first + (threadIdx.x - 32)) * L, (unsigned)(L * sizeof(float)));
     for (int round = 0; round < rounds; ++round) {
-        // X[k] = A[k] + i B[k] of the two lines, written re/im swapped for the inverse transform
-#pragma unroll
-        for (int n = 0; n < NQ; ++n) {
-            const int i = threadIdx.x + n * GP * T;
-            const int gg = i % GP, k = i / GP;
-            const SmemBuf sg{smem + gg * GS, smem + gg * GS + PL};
-            const float4 q = qn[n];
-            if (k == 0) {
-                sg.put(0, make_float2(q.z, q.x));
-                sg.put(L / 2, make_float2(q.w, q.y));
-            } else {
-                sg.put(k, make_float2(q.y + q.z, q.x - q.w));
-                sg.put(L - k, make_float2(q.z - q.y, q.x + q.w));
-            }
-        }
-        if (round + 1 < rounds) load_spec(round + 1, qn);
-        __syncthreads();
         float2 x[EPT];
+        if (S) {
+            // X[k] = A[k] + i B[k] of the two lines, written re/im swapped for the inverse transform
 #pragma unroll
-        for (int i = 0; i < EPT; ++i) x[i] = sb.get(IX::in(t, i));
-        __syncthreads();
-        fft_regs<L>(t, sb, x, tw);
+            for (int n = 0; n < NQ; ++n) {
+                const int i = threadIdx.x + n * GP * T;
+                const int gg = i % GP, k = i / GP;
+                const SmemBuf sg{smem + gg * GS, smem + gg * GS + PL};
+                const float4 q = qn[n];
+                if (k == 0) {
+                    sg.put(0, make_float2(q.z, q.x));
+                    sg.put(L / 2, make_float2(q.w, q.y));
+                } else {
+                    sg.put(k, make_float2(q.y + q.z, q.x - q.w));
+                    sg.put(L - k, make_float2(q.z - q.y, q.x + q.w));
+                }
+            }
+            if (round + 1 < rounds) load_spec(round + 1, qn);
+            __syncthreads();
+#pragma unroll
+            for (int i = 0; i < EPT; ++i) x[i] = sb.get(IX::in(t, i));
+            __syncthreads();
+            fft_regs<L>(t, sb, x, tw);
+        } else {
+            // no spectrum: the gradient term is exactly zero (first inner iteration of an SVRG epoch: z == w, so
+            // g_B(z) - g_B(w) = 0 and v = mu); the transform of zeros is skipped, the update below is unchanged
+#pragma unroll
+            for (int i = 0; i < EPT; ++i) x[i] = make_float2(0.f, 0.f);
+        }
         if (round <= 1) mbar_wait(&bars[round], 0);             // z_in lines of this round (round >= 1: of all later rounds) have landed
         const int pl = round * GP + g;
         if (pl < mine) {

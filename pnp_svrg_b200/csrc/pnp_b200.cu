@@ -749,11 +749,32 @@ int pnp_pr_grad(const pnp_pr_grad_args* args, void* stream) {
     return PNP_OK;
 }
 
+}  // extern "C"
+namespace {
+template <int L>
+int update_prox_fits(int W) {
+    constexpr int GP = pnp::upd_gp<L>();
+    const int npairs = W / 2;
+    int grid = num_sms() < npairs ? num_sms() : npairs;
+    const int ppc = (npairs + grid - 1) / grid;
+    const size_t smem = sizeof(float) * ((size_t)pnp::lines_stage_off<L, GP>() + (size_t)2 * ppc * L);
+    return (smem <= 220 * 1024 && 2 * ppc >= GP) ? 1 : 0;
+}
+int dispatch_update_prox_fits(int n, int W) { DISPATCH_POW2(n, update_prox_fits, W) }
+}  // namespace
+extern "C" {
+
+int pnp_csmri_update_prox_supported(int H, int W) {
+    if (!pow2_ok(H) || W < 2 || (W & 1) || H < 512) return 0;
+    const int r = dispatch_update_prox_fits(H, W);
+    return r > 0 ? 1 : 0;
+}
+
 int pnp_csmri_update_prox(const float* S, int H, int W, float gscale, float step, const float* step_ptr, const float* vadd,
                           const float* z_in, float* z_out, double* sig_log, float sigma_modifier, float fallback_sigma,
                           const float* xrec, double* mse_log, const int* slot, int* advance_counters, int n_advance,
                           unsigned* barrier_ws, int chain, void* stream) {
-    if (!S || !vadd || !z_in || !z_out || !sig_log) return fail(PNP_ERR_ARG, "bad argument");
+    if (!vadd || !z_in || !z_out || !sig_log) return fail(PNP_ERR_ARG, "bad argument");      // S may be null: zero spectrum
     if (advance_counters && (n_advance < 1 || n_advance > 32)) return fail(PNP_ERR_ARG, "n_advance must be in [1, 32]");
     if (!pow2_ok(H) || W < 2 || (W & 1)) return fail(PNP_ERR_ARG, "H must be a power of two in [32, 4096], W even");
     // (below 512 samples a round would hold more than 16 transforms, whose exchange planes are only 4-byte aligned)

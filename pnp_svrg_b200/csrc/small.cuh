@@ -364,17 +364,28 @@ __global__ void __launch_bounds__(NT, NT <= 256 ? 2 : 1) k_csmri_svrg_small(Smal
     for (int it = 0; it < a.n_inner;) {
         const bool snap = need_snap;
         if (snap && it > 0) { step_d *= (double)a.lr_decay; st = (float)step_d; }
+        // First inner iteration of an epoch: z == w bit for bit (the snapshot pass has just copied it), so the transform of
+        // z - w, its selection and its inverse are exactly zero and v = mu: the three phases reduce to the update.  The two
+        // cluster barriers stay (they order the selection buffers: zeroing, remote filling, use).
+        const bool zero = !snap && it % a.T2 == 0;
         trace(510);
-        if (is_fft) phase_a(!snap);
+        if (is_fft && !zero) phase_a(!snap);
         trace(511);
         cluster.sync();
         trace(512);
-        phase_b(snap ? bits_fu : bits_mb + (it & 1) * (RPC * L), snap);
+        if (!zero) phase_b(snap ? bits_fu : bits_mb + (it & 1) * (RPC * L), snap);
         if (!snap && it + 1 < a.n_inner) select(it + 1);
         trace(513);
         cluster.sync();
         trace(514);
-        phase_c(snap, snap ? gs_snap : gs_in);
+        if (zero) {
+            for (int i = tid; i < LPC * L; i += K::NT) {
+                const int o = (i / L) * LS + (i % L);
+                zl[o] = zl[o] - st * (0.f * gs_in + mul[o]);
+            }
+        } else {
+            phase_c(snap, snap ? gs_snap : gs_in);
+        }
         if (!snap) small_select_clear<L, C, NT>(bits_mb, it & 1);   // used by the column phase above; filled again next iteration
         trace(515);
         __syncthreads();

@@ -171,11 +171,11 @@ class CSMRI(Problem):
         _lib.check(_lib.load().pnp_csmri_grad(C.byref(args), D.stream()))
 
     def _dev_update_prox(self, gscale, step_ptr, vadd, z_in, z_out, sig_log, sigma_modifier, fallback_sigma, xrec, mse_log,
-                         slot, advance=None, n_advance=0, barrier_ws=None, chain=False):
+                         slot, advance=None, n_advance=0, barrier_ws=None, chain=False, zero_spectrum=False):
         """Tail of an inner iteration in one cooperative launch, after ``_dev_grad(..., phases=3)`` left the masked
         spectrum in the scratch: inverse line pass + update + sigma estimate + wavelet prox + PSNR
         (pnp_csmri_update_prox).  Returns False when the image does not suit the resident-line kernel."""
-        rc = _lib.load().pnp_csmri_update_prox(D.ptr(self._S), self.H, self.W, float(gscale), 0.0, D.ptr(step_ptr), D.ptr(vadd),
+        rc = _lib.load().pnp_csmri_update_prox(None if zero_spectrum else D.ptr(self._S), self.H, self.W, float(gscale), 0.0, D.ptr(step_ptr), D.ptr(vadd),
                                                D.ptr(z_in), D.ptr(z_out), D.ptr(sig_log), float(sigma_modifier),
                                                float(fallback_sigma), D.ptr(xrec), D.ptr(mse_log), D.ptr(slot), D.ptr(advance),
                                                int(n_advance), D.ptr(barrier_ws), int(bool(chain)), D.stream())

@@ -42,7 +42,7 @@ def launches(src, dst):
 
 
 def full(src, dst):
-    rows = list(csv.reader(open(src)))
+    rows = [r for r in csv.reader(open(src)) if len(r) > 10]        # ncu's "==PROF==" lines and blank lines drop out
     hdr, units = rows[0], rows[1]
     cols = [hdr.index(m) for m in FULL if m in hdr]
     ki = hdr.index('Kernel Name')
