@@ -284,6 +284,31 @@ int pnp_csmri_update_prox(const float* S, int H, int W, float gscale, float step
                           const float* z_in, float* z_out, double* sig_log, float sigma_modifier, float fallback_sigma,
                           const float* xrec, double* mse_log, const int* slot, int* advance_counters, int n_advance,
                           unsigned* barrier_ws, int chain, void* stream);
+/* The same launch, optionally followed -- inside the kernel, on the lines that are still in shared memory -- by the
+ * FORWARD LINE PASS OF THE NEXT INNER ITERATION: S_out = packed half spectrum of (z_out - w), exactly what
+ * pnp_csmri_grad(phases = 1, a = z_out, b = w) would store (the next iteration then starts at phases = 2), and by the
+ * minibatch selection of that iteration (sel_* as in pnp_csmri_grad_args; the device sampler's draw counter is
+ * *sel_counter + sel_counter_add because the counters advance inside this kernel).  Saves a kernel boundary (drain,
+ * launch and cold start of a persistent pass: ~6 us at 2048 x 2048) and the re-read of the iterate.  S_out may be the
+ * buffer S points to.  next = NULL: exactly pnp_csmri_update_prox.  PNP_ERR_UNSUPPORTED when a CTA holds more than 16
+ * lines (one line per warp is what the kernel keeps resident). */
+typedef struct {
+    const float* w;
+    float* S_out;
+    unsigned char* bits;          /* selection bytes of the NEXT iteration (all zero on entry); used when sel_count > 0 */
+    int sel_count;
+    const int* sel_idx;           /* explicit positions [sel_count], or null: device sampler */
+    const int* sel_support;
+    const int* sel_m0;
+    unsigned sel_seed;
+    const int* sel_counter;
+    int sel_counter_add;
+    int sel_min_m0;
+} pnp_csmri_next_pass;
+int pnp_csmri_update_prox_next(const float* S, int H, int W, float gscale, float step, const float* step_ptr, const float* vadd,
+                               const float* z_in, float* z_out, double* sig_log, float sigma_modifier, float fallback_sigma,
+                               const float* xrec, double* mse_log, const int* slot, int* advance_counters, int n_advance,
+                               unsigned* barrier_ws, int chain, const pnp_csmri_next_pass* next, void* stream);
 /* 1 when pnp_csmri_update_prox handles H x W images on the current device, else 0 (host-side query, no launch) */
 int pnp_csmri_update_prox_supported(int H, int W);
 

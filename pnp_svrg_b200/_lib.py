@@ -67,6 +67,15 @@ class CdpGradArgs(C.Structure):
     ]
 
 
+class CsmriNextPass(C.Structure):
+    """mirror of pnp_csmri_next_pass"""
+    _fields_ = [
+        ('w', C.c_void_p), ('S_out', C.c_void_p), ('bits', C.c_void_p), ('sel_count', C.c_int), ('sel_idx', C.c_void_p),
+        ('sel_support', C.c_void_p), ('sel_m0', C.c_void_p), ('sel_seed', C.c_uint), ('sel_counter', C.c_void_p),
+        ('sel_counter_add', C.c_int), ('sel_min_m0', C.c_int),
+    ]
+
+
 class SvrgSmallArgs(C.Structure):
     """mirror of pnp_csmri_svrg_small_args"""
     _fields_ = [
@@ -125,6 +134,9 @@ PROTOTYPES = {
     'pnp_csmri_update_prox': (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p,
                                         C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p,
                                         C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p]),
+    'pnp_csmri_update_prox_next': (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p,
+                                             C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p,
+                                             C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.POINTER(CsmriNextPass), C.c_void_p]),
     'pnp_csmri_update_prox_supported': (C.c_int, [C.c_int, C.c_int]),
     'pnp_tv_chambolle': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p, C.c_float,
                                    C.c_float, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),

@@ -27,7 +27,7 @@ def _grad_update(eng, a, b, sel, with_y, gscale, **kw):
     eng.p._dev_grad(a, b=b, sel=sel, with_y=with_y, gscale=gscale, clear_sel=sel is not None and sel is eng.sel, **kw)
 
 
-def _grad_update_prox(eng, a, b, sel, gscale, vadd, z, advance=0, sel_fn=None, zero_grad=False):
+def _grad_update_prox(eng, a, b, sel, gscale, vadd, z, advance=0, sel_fn=None, zero_grad=False, r2c_done=False, next_pass=None):
     """z <- prox(z - step * (g_sel(a - b) * gscale + vadd)).  CSMRI + wavelet prox: the inverse line pass, the update,
     the sigma estimate and the prox run as ONE cooperative launch on lines resident in shared memory
     (pnp_csmri_update_prox); otherwise the gradient pass followed by ``eng.prox``.  ``advance`` > 0 also bumps
@@ -38,25 +38,41 @@ def _grad_update_prox(eng, a, b, sel, gscale, vadd, z, advance=0, sel_fn=None, z
     ``zero_grad``: the caller knows that a == b bit for bit (first inner iteration of an SVRG epoch, right after
     ``w = copy(z)``), so g_sel(a - b) is exactly zero whatever the minibatch: on the fused CSMRI path the forward line
     pass, the column pass and the inverse transforms are skipped (the tail kernel runs on a zero spectrum; same bits as
-    transforming zeros), the minibatch counters still advance.  Other paths ignore the hint."""
+    transforming zeros), the minibatch counters still advance.  Other paths ignore the hint.
+    ``next_pass`` = dict(idx=positions of the NEXT minibatch or None for the device sampler): the tail kernel also runs the
+    forward line pass of the next iteration (z_new - b) and builds its selection (pnp_csmri_update_prox_next); the call for
+    that iteration then says ``r2c_done=True`` and starts at the column pass.  Only honoured on the fused CSMRI path
+    (``eng.fused_tail is True``); whole-epoch graphs use it (SvrgRun._epoch_ops)."""
     p, d = eng.p, eng.d
     own = sel is not None and sel is eng.sel
     if (eng.fused_tail is not False and eng.uses_sigma and not eng.sigma_ready and getattr(d, 'method', None) == 'wavelet'
             and hasattr(p, '_dev_update_prox')):
         kw = dict(b=b, sel=sel, with_y=False, gscale=gscale, vadd=vadd, step_ptr=eng.step, z_in=z, z_out=z, clear_sel=own)
         skip = bool(zero_grad) and eng.fused_tail is True and own          # (the first fused call decides whether the tail applies)
-        if not skip:
+        if eng.chain:
+            kw['chain'] = True
+        if skip:
+            pass
+        elif r2c_done and eng.fused_tail is True and own:
+            p._dev_grad(a, phases=2, **kw)          # spectrum of a - b and the selection were left by the previous tail launch
+        else:
             job = eng.sel_job() if (sel_fn is not None and own) else None
             if job is None and sel_fn is not None:
                 sel_fn()
-            if eng.chain:
-                kw['chain'] = True
             p._dev_grad(a, phases=3, sel_job=job, **kw)
+        nxt = None
+        if next_pass is not None and eng.fused_tail is True and own:
+            job = eng.sel_job()
+            if job is not None:
+                job = dict(job, counter_add=1)
+                if job.get('idx') is not None:
+                    job['idx'] = next_pass.get('idx')
+            nxt = dict(w=b, sel=sel, job=job)
         ok = p._dev_update_prox(gscale, eng.step, vadd, z, z, eng.sig_log, d.sigma_modifier,
                                 d.denoise_strength * d.decay ** (d.t + 1), p._xrec_dev, eng.mse_log, eng.slot_ptr,
                                 advance=eng.counters if advance else None, n_advance=advance,
                                 barrier_ws=eng.barrier_ws if (eng.chain or eng.sw_barrier) else None, chain=eng.chain,
-                                zero_spectrum=skip)
+                                zero_spectrum=skip, next_pass=nxt)
         eng.fused_tail = ok
         if ok:
             d.t += 1
@@ -351,13 +367,14 @@ class SvrgRun:
         else:
             eng.check(eng.lib.pnp_axpy(D.ptr(z), D.ptr(self.mu), D.ptr(z), eng.N, 1, 0.0, D.ptr(eng.step), eng.sptr))
 
-    def fast_ops(self, first_of_epoch=False):
+    def fast_ops(self, first_of_epoch=False, r2c_done=False, next_pass=None):
         """one inner iteration as it is captured (per iteration, or T2 times inside an epoch graph).
-        ``first_of_epoch``: z == w (the snapshot has just copied it), the stochastic term of line 53 is exactly zero"""
+        ``first_of_epoch``: z == w (the snapshot has just copied it), the stochastic term of line 53 is exactly zero;
+        ``r2c_done`` / ``next_pass``: see _grad_update_prox (forward line pass fused into the previous tail launch)"""
         eng, z = self.eng, self.z
         if self.paper:
             _grad_update_prox(eng, z, self.w, eng.sel, 1.0 / self.B, self.mu, z, advance=3,
-                              sel_fn=lambda: _sel_ops(eng), zero_grad=first_of_epoch)
+                              sel_fn=lambda: _sel_ops(eng), zero_grad=first_of_epoch, r2c_done=r2c_done, next_pass=next_pass)
         else:
             self.grad_ops()
             eng.prox(z, z)
@@ -413,10 +430,19 @@ class SvrgRun:
             return
         self.snapshot()
         keep = eng.idx_dev if self.B > 0 else None
+        # CSMRI + wavelet prox, PNP_FUSE_R2C=1: the tail launch of iteration j also runs the forward line pass and the
+        # selection of iteration j + 1 (pnp_csmri_update_prox_next).  Bit-identical and tested, but OFF by default: measured
+        # on B200 at 2048^2 it is 63.7 us per inner iteration against 62.6-63.8 with the separate pass -- the two fused
+        # rounds of transforms take 11.4 us inside the 16-warp cooperative kernel (snapshot lines from DRAM without a TMA
+        # double buffer, cold instruction cache), as long as the stand-alone pass with its launch and cold start.
+        fuse = self.paper and eng.fused_tail is True and os.environ.get('PNP_FUSE_R2C', '0') == '1'
         for j in range(self.T2):
             if bufs is not None:
                 eng.idx_dev = bufs[j]
-            self.fast_ops(first_of_epoch=(j == 0))
+            nxt = None
+            if fuse and j + 1 < self.T2:
+                nxt = dict(idx=bufs[j + 1] if bufs is not None else None)
+            self.fast_ops(first_of_epoch=(j == 0), r2c_done=(fuse and j >= 1), next_pass=nxt)
         if self.B > 0:
             eng.idx_dev = keep
         if self.lr_decay != 1.0:

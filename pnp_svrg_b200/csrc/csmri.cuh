@@ -124,6 +124,7 @@ struct SelJob {
     unsigned seed;
     const int* counter;
     int* idx_out;                 // optional [batch][count]: the positions drawn by the sampler
+    int counter_add;              // added to *counter (a pass that draws the minibatch of the NEXT iteration before the counters advance)
 };
 
 __device__ __forceinline__ void run_sel_job(const SelJob& sj, int H, int W, int img, int tid, int nthreads) {
@@ -132,7 +133,7 @@ __device__ __forceinline__ void run_sel_job(const SelJob& sj, int H, int W, int 
         const int* src = sj.idx + (long long)img * sj.idx_img_stride + (long long)(sj.cursor ? *sj.cursor : 0) * sj.count;
         for (int i = tid; i < sj.count; i += nthreads) set_sel_bits(bi, H, W, src[i]);
     } else {
-        const unsigned key = mix32(sj.seed ^ mix32((sj.counter ? (unsigned)*sj.counter : 0u) * 0x632be5abU + (unsigned)img));
+        const unsigned key = mix32(sj.seed ^ mix32(((sj.counter ? (unsigned)*sj.counter : 0u) + (unsigned)sj.counter_add) * 0x632be5abU + (unsigned)img));
         const int* sup = sj.support + (long long)img * sj.support_img_stride;
         const unsigned n = (unsigned)sj.m0[img];
         for (int i = tid; i < sj.count; i += nthreads) {
@@ -181,7 +182,7 @@ k_lines_r2c(const float* __restrict__ a, const float* __restrict__ b, float2* __
         np = np < GP ? np : GP;
         const unsigned bytes = (unsigned)(np * 2 * L * sizeof(float));
         mbar_expect_tx(&bar, b ? 2 * bytes : bytes);
-        bulk_g2s(stage_a, a + ibase + (long long)(2 * item * GP) * L, bytes, &bar);
+        bulk_g2s_keep(stage_a, a + ibase + (long long)(2 * item * GP) * L, bytes, &bar);     // the iterate: read again by the tail
         if (b) bulk_g2s(stage_b, b + ibase + (long long)(2 * item * GP) * L, bytes, &bar);
     };
 
@@ -244,7 +245,7 @@ k_lines_r2c(const float* __restrict__ a, const float* __restrict__ b, float2* __
             } else {
                 o = make_float4(0.5f * (xk.x + xm.x), 0.5f * (xk.y - xm.y), 0.5f * (xk.y + xm.y), 0.5f * (xm.x - xk.x));
             }
-            stg_stream(S4 + (long long)k * W2 + gg, o);
+            stg_keep(S4 + (long long)k * W2 + gg, o);
         }
         __syncthreads();
         trace(102);
@@ -308,7 +309,7 @@ k_cols_mask(float2* __restrict__ S, const unsigned char* __restrict__ bits,
         nc = nc < NC ? nc : NC;
         const unsigned bytes = (unsigned)(nc * L * sizeof(float2));
         mbar_expect_tx(&bar, bytes + (unsigned)(nc * L));
-        bulk_g2s(stage, Si + (long long)(c_lo + item * NC) * L, bytes, &bar);
+        bulk_g2s_keep(stage, Si + (long long)(c_lo + item * NC) * L, bytes, &bar);
         bulk_g2s(const_cast<unsigned char*>(stage_bits), bi + (long long)(c_lo + item * NC) * L, (unsigned)(nc * L), &bar);
     };
     trace(200, true);
@@ -363,7 +364,7 @@ k_cols_mask(float2* __restrict__ S, const unsigned char* __restrict__ bits,
         if (active) {
             float2* Sc = Si + crow;
 #pragma unroll
-            for (int i = 0; i < EPT; ++i) stg_stream(Sc + IX::out(t, i), cswap(y[i]));
+            for (int i = 0; i < EPT; ++i) stg_keep(Sc + IX::out(t, i), cswap(y[i]));
         }
         if (FftPlan<L>::NS > 1) __syncthreads();
         trace(202);
@@ -411,7 +412,7 @@ k_cols_mask(float2* __restrict__ S, const unsigned char* __restrict__ bits,
         fft_regs<L>(t, sb, x);
         if (g == 0) {
 #pragma unroll
-            for (int i = 0; i < EPT; ++i) stg_stream(Si + IX::out(t, i), cswap(x[i]));
+            for (int i = 0; i < EPT; ++i) stg_keep(Si + IX::out(t, i), cswap(x[i]));
             if (clear_bits) {
                 unsigned char* cb = clear_bits + (long long)img * bits_img_stride;
                 for (int i = t; i < L / 16; i += T) reinterpret_cast<uint4*>(cb)[i] = make_uint4(0u, 0u, 0u, 0u);
@@ -565,13 +566,14 @@ __device__ __forceinline__ void upd_mark(int i) {
 #endif
 }
 
-template <int L>
+template <int L, bool NEXT = false>
 __global__ void __launch_bounds__(512, 1)
 k_update_prox(const float2* __restrict__ S, int nlines, float inv_n, float gscale, float step,
               const float* __restrict__ step_ptr, const float* __restrict__ vadd, const float* __restrict__ z_in,
               float* __restrict__ z_out, const float* __restrict__ xrec, int pairs_per_cta, float sigma_modifier,
               float fallback_sigma, double* __restrict__ sig_log, double* __restrict__ mse_log, const int* __restrict__ slot,
-              int* __restrict__ advance, int n_advance, unsigned* __restrict__ gbar) {
+              int* __restrict__ advance, int n_advance, unsigned* __restrict__ gbar,
+              const float* __restrict__ w_next, float2* __restrict__ S_next, SelJob sj_next) {
     constexpr int T = fft_threads<L>();
     constexpr int EPT = FftPlan<L>::EPT;
     constexpr int PL = fft_plane<L>();
@@ -621,6 +623,10 @@ k_update_prox(const float2* __restrict__ S, int nlines, float inv_n, float gscal
     griddep_launch();
     const int cur_slot = slot ? *slot : 0;
     const float st = step_ptr ? *step_ptr : step;
+    // minibatch selection of the NEXT iteration (its forward line pass is fused below): a slice per thread of the whole
+    // grid, while the first lines and spectrum entries of this CTA are on their way.  The column pass of THIS iteration
+    // has consumed and zeroed the selection bytes; the counters advance after the grid barrier, long after this read.
+    if (NEXT && sj_next.bits) run_sel_job(sj_next, L, nlines, 0, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x);
 
     auto load_spec = [&](int round, float4 (&q)[NQ]) {
 #pragma unroll
@@ -699,9 +705,57 @@ k_update_prox(const float2* __restrict__ S, int nlines, float inv_n, float gscal
     // the exchange planes in front of the resident lines are idle from here on: they hold the per-warp scratch of the
     // prox phases (sigma selection, Haar transposition)
     static_assert(L < 512 || lines_stage_off<L, GP>() >= 16 * prox_scratch<L>(), "exchange planes too small for the prox scratch");
+    // the snapshot lines of the fused forward pass below: towards L2 now (default policy: they are used ~15 us from here),
+    // DRAM is idle during the sigma phase and the grid barrier
+    if (NEXT && threadIdx.x < 2 * mine)
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(w_next + (first + threadIdx.x) * L), "r"((unsigned)(L * sizeof(float))) : "memory");
     prox_phases<L>(lines, 2 * mine, first, nlines, 1, z_out, xrec, sigma_modifier, fallback_sigma, sig_log, mse_log, cur_slot,
-                   reinterpret_cast<unsigned*>(smem), &bars[2], advance, n_advance, gbar);
+                   reinterpret_cast<unsigned*>(smem), &bars[2], advance, n_advance, gbar, NEXT);
     upd_mark(4);
+    if constexpr (NEXT) {
+        // ---- forward line pass of the NEXT inner iteration on the lines that are still in shared memory ----
+        // (k_lines_r2c on z_new - w: same transform, same unpacking, same stores; what it saves is a kernel boundary --
+        // drain of this grid, launch, cold start of a persistent pass, ~6 us at 2048^2 -- and the 4N-byte re-read of z)
+        FftTw<L> tw2;                               // (reloaded: keeping the twiddles of the inverse rounds alive across the prox phases spills)
+        tw2.init(t);
+        __syncthreads();                            // every warp has written its new line; the prox scratch (exchange planes) is idle
+        float4* S4o = reinterpret_cast<float4*>(S_next);
+        for (int round = 0; round < rounds; ++round) {
+            const int pl = round * GP + g;
+            float2 x[EPT];
+            if (pl < mine) {
+                const float* la = lines + (long long)(2 * pl) * L;
+                const float* lw = w_next + (first + 2 * pl) * L;
+#pragma unroll
+                for (int i = 0; i < EPT; ++i) {
+                    const int idx = IX::in(t, i);
+                    x[i] = make_float2(la[idx] - ldg_stream(lw + idx), la[idx + L] - ldg_stream(lw + idx + L));
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < EPT; ++i) x[i] = make_float2(0.f, 0.f);
+            }
+            fft_regs<L>(t, sb, x, tw2);
+            if (FftPlan<L>::NS > 1) __syncthreads();
+#pragma unroll
+            for (int i = 0; i < EPT; ++i) sb.put(IX::out(t, i), x[i]);
+            __syncthreads();
+            const int pair0 = first_pair + round * GP;
+            for (int i = threadIdx.x; i < GP * (L / 2); i += GP * T) {
+                const int gg = i % GP, k = i / GP;
+                if (round * GP + gg >= mine) continue;
+                const SmemBuf sg{smem + gg * GS, smem + gg * GS + PL};
+                const float2 xk = sg.get(k);
+                const float2 xm = sg.get(k == 0 ? L / 2 : L - k);
+                float4 o;
+                if (k == 0) o = make_float4(xk.x, xm.x, xk.y, xm.y);
+                else o = make_float4(0.5f * (xk.x + xm.x), 0.5f * (xk.y - xm.y), 0.5f * (xk.y + xm.y), 0.5f * (xm.x - xk.x));
+                stg_keep(S4o + (long long)k * npairs + pair0 + gg, o);
+            }
+            __syncthreads();
+            trace(330 + round);
+        }
+    }
     trace_flush();
 }
 

@@ -149,6 +149,23 @@ __device__ __forceinline__ void stg_stream(float* p, float v) {
     *p = v;
 #endif
 }
+// Hand-off data -- written by one pass and read by the NEXT one (the spectrum between the three passes, the iterate
+// between the tail and the next forward line pass: 34 MB of the 126 MB L2 at 2048^2).  -DPNP_L2_KEEP gives it the
+// default policy instead of evict-first so that it is still in L2 when its consumer starts -- measured on B200: 64.0 us
+// per inner iteration against 63.2 with everything evict-first (the passes are latency / issue bound, and the data
+// mostly survives anyway), so it is off.
+#ifdef PNP_L2_KEEP
+__device__ __forceinline__ void stg_keep(float4* p, float4 v) { *p = v; }
+__device__ __forceinline__ void stg_keep(float2* p, float2 v) { *p = v; }
+__device__ __forceinline__ void bulk_g2s_keep(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+#else
+__device__ __forceinline__ void stg_keep(float4* p, float4 v) { stg_stream(p, v); }
+__device__ __forceinline__ void stg_keep(float2* p, float2 v) { stg_stream(p, v); }
+__device__ __forceinline__ void bulk_g2s_keep(void* dst, const void* src, unsigned bytes, unsigned long long* bar) { bulk_g2s(dst, src, bytes, bar); }
+#endif
 // bring `bytes` (multiple of 16) at `src` into L2 ahead of use; no destination, nothing to wait for
 __device__ __forceinline__ void bulk_prefetch_l2(const void* src, unsigned bytes) {
 #ifndef PNP_NO_L2_HINTS

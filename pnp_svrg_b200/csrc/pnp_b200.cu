@@ -300,7 +300,7 @@ namespace {
 template <int L>
 int launch_update_prox(const float* S, int W, float inv_n, float gscale, float step, const float* step_ptr, const float* vadd,
                        const float* z_in, float* z_out, const float* xrec, float sm, float fb, double* sig_log, double* mse_log,
-                       const int* slot, int* adv, int n_adv, unsigned* gbar, int chain, cudaStream_t st) {
+                       const int* slot, int* adv, int n_adv, unsigned* gbar, int chain, const pnp_csmri_next_pass* next, cudaStream_t st) {
     constexpr int GP = pnp::upd_gp<L>();
     const int npairs = W / 2;
     int grid = num_sms() < npairs ? num_sms() : npairs;
@@ -311,19 +311,37 @@ int launch_update_prox(const float* S, int W, float inv_n, float gscale, float s
     if (smem > 220 * 1024 || 2 * ppc < GP) return fail(PNP_ERR_UNSUPPORTED, "update+prox: image does not suit the resident-line kernel");
     { const int rc = raise_smem_limit((const void*)pnp::k_update_prox<L>, 220 * 1024); if (rc != PNP_OK) return rc; }
     int nl = W, p = ppc;
+    const float* w_next = nullptr;
+    float2* S_next = nullptr;
+    pnp::SelJob sj{};
+    if (next) {
+        if (2 * ppc > 16) return fail(PNP_ERR_UNSUPPORTED, "update+prox: the fused next line pass needs at most one line per warp");
+        w_next = next->w;
+        S_next = reinterpret_cast<float2*>(next->S_out);
+        if (next->sel_count > 0) {
+            sj.bits = next->bits;
+            sj.idx = next->sel_idx; sj.idx_img_stride = 0; sj.cursor = nullptr;
+            sj.support = next->sel_support; sj.m0 = next->sel_m0; sj.support_img_stride = 0;
+            sj.count = next->sel_count; sj.seed = next->sel_seed; sj.counter = next->sel_counter; sj.idx_out = nullptr;
+            sj.counter_add = next->sel_counter_add;
+        }
+    }
     void* args[] = {(void*)&S, (void*)&nl, (void*)&inv_n, (void*)&gscale, (void*)&step, (void*)&step_ptr, (void*)&vadd, (void*)&z_in,
                     (void*)&z_out, (void*)&xrec, (void*)&p, (void*)&sm, (void*)&fb, (void*)&sig_log, (void*)&mse_log, (void*)&slot,
-                    (void*)&adv, (void*)&n_adv, (void*)&gbar};
+                    (void*)&adv, (void*)&n_adv, (void*)&gbar, (void*)&w_next, (void*)&S_next, (void*)&sj};
     // with a barrier workspace: plain launch + software grid barrier (all CTAs are co-resident: grid <= SM count, one
     // CTA per SM), which is what lets the kernel join a programmatic-dependent-launch chain; else cooperative launch
-    if (gbar) return launch_ex((const void*)pnp::k_update_prox<L>, dim3(grid), dim3(512), smem, st, chain != 0, args);
-    CU_TRY(cudaLaunchCooperativeKernel((const void*)pnp::k_update_prox<L>, dim3(grid), dim3(512), args, smem, st));
+    const void* kernel = next ? (const void*)pnp::k_update_prox<L, true> : (const void*)pnp::k_update_prox<L, false>;
+    if (next) { const int rc = raise_smem_limit(kernel, 220 * 1024); if (rc != PNP_OK) return rc; }
+    if (gbar) return launch_ex(kernel, dim3(grid), dim3(512), smem, st, chain != 0, args);
+    CU_TRY(cudaLaunchCooperativeKernel(kernel, dim3(grid), dim3(512), args, smem, st));
     return PNP_OK;
 }
 int dispatch_update_prox(int n, const float* S, int W, float inv_n, float gscale, float step, const float* step_ptr,
                          const float* vadd, const float* z_in, float* z_out, const float* xrec, float sm, float fb, double* sig_log,
-                         double* mse_log, const int* slot, int* adv, int n_adv, unsigned* gbar, int chain, cudaStream_t st) {
-    DISPATCH_POW2(n, launch_update_prox, S, W, inv_n, gscale, step, step_ptr, vadd, z_in, z_out, xrec, sm, fb, sig_log, mse_log, slot, adv, n_adv, gbar, chain, st)
+                         double* mse_log, const int* slot, int* adv, int n_adv, unsigned* gbar, int chain,
+                         const pnp_csmri_next_pass* next, cudaStream_t st) {
+    DISPATCH_POW2(n, launch_update_prox, S, W, inv_n, gscale, step, step_ptr, vadd, z_in, z_out, xrec, sm, fb, sig_log, mse_log, slot, adv, n_adv, gbar, chain, next, st)
 }
 }  // namespace
 
@@ -774,6 +792,23 @@ int pnp_csmri_update_prox(const float* S, int H, int W, float gscale, float step
                           const float* z_in, float* z_out, double* sig_log, float sigma_modifier, float fallback_sigma,
                           const float* xrec, double* mse_log, const int* slot, int* advance_counters, int n_advance,
                           unsigned* barrier_ws, int chain, void* stream) {
+    return pnp_csmri_update_prox_next(S, H, W, gscale, step, step_ptr, vadd, z_in, z_out, sig_log, sigma_modifier, fallback_sigma, xrec,
+                                      mse_log, slot, advance_counters, n_advance, barrier_ws, chain, nullptr, stream);
+}
+
+int pnp_csmri_update_prox_next(const float* S, int H, int W, float gscale, float step, const float* step_ptr, const float* vadd,
+                               const float* z_in, float* z_out, double* sig_log, float sigma_modifier, float fallback_sigma,
+                               const float* xrec, double* mse_log, const int* slot, int* advance_counters, int n_advance,
+                               unsigned* barrier_ws, int chain, const pnp_csmri_next_pass* next, void* stream) {
+    if (next) {
+        if (!next->w || !next->S_out) return fail(PNP_ERR_ARG, "next pass: w and S_out are required");
+        if (next->sel_count > 0) {
+            if (!next->bits) return fail(PNP_ERR_ARG, "next pass: selection needs the bits buffer");
+            if (!next->sel_idx && (!next->sel_support || !next->sel_m0)) return fail(PNP_ERR_ARG, "next pass: neither positions nor a support list");
+            if (!next->sel_idx && next->sel_count > next->sel_min_m0)
+                return fail(PNP_ERR_ARG, "next pass: sel_count %d exceeds the %d sampled positions", next->sel_count, next->sel_min_m0);
+        }
+    }
     if (!vadd || !z_in || !z_out || !sig_log) return fail(PNP_ERR_ARG, "bad argument");      // S may be null: zero spectrum
     if (advance_counters && (n_advance < 1 || n_advance > 32)) return fail(PNP_ERR_ARG, "n_advance must be in [1, 32]");
     if (!pow2_ok(H) || W < 2 || (W & 1)) return fail(PNP_ERR_ARG, "H must be a power of two in [32, 4096], W even");
@@ -782,7 +817,7 @@ int pnp_csmri_update_prox(const float* S, int H, int W, float gscale, float step
     const float inv_n = (float)(1.0 / ((double)H * (double)W));
     return dispatch_update_prox(H, reinterpret_cast<const float*>(S), W, inv_n, gscale, step, step_ptr, vadd, z_in, z_out, xrec,
                                 sigma_modifier, fallback_sigma, sig_log, mse_log, slot, advance_counters, n_advance,
-                                barrier_ws, chain, static_cast<cudaStream_t>(stream));
+                                barrier_ws, chain, next, static_cast<cudaStream_t>(stream));
 }
 
 int pnp_cdp_grad(const pnp_cdp_grad_args* args, void* stream) {

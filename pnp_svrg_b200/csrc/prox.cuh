@@ -810,8 +810,11 @@ __device__ __forceinline__ void prox_line_forward(float* sl, int lane, ProxLine<
 
 // thresholds from the energies, shrink, inverse pyramid, store; returns the lane's part of sum((out - xrec)^2).
 // `tscr`: prox_scratch<L>() floats of shared scratch of this warp; `xr4`: ground truth of the line (shared or global).
+// `keep4` (optional): shared-memory copy of the result in the line's own layout (may be the buffer xr4 points to: a lane
+// reads a ground-truth chunk before it overwrites it)
 template <int L>
-__device__ __forceinline__ float prox_line_inverse(ProxLine<L>& st, float* tscr, int lane, float var, float4* zo4, const float4* xr4) {
+__device__ __forceinline__ float prox_line_inverse(ProxLine<L>& st, float* tscr, int lane, float var, float4* zo4, const float4* xr4,
+                                                   float4* keep4 = nullptr) {
     using W = HaarWL<L>;
     constexpr int NCH = W::NCH, LG = W::LG, LEVELS = W::LEVELS;
     constexpr float RS2 = 0.70710678118654752f;
@@ -861,12 +864,13 @@ __device__ __forceinline__ float prox_line_inverse(ProxLine<L>& st, float* tscr,
         const float a0 = (aa + dd) * RS2, a1 = (aa - dd) * RS2;
         const float d0 = soft_shrink(st.x[c][1], thr[0]), d1 = soft_shrink(st.x[c][3], thr[0]);
         const float4 o = make_float4((a0 + d0) * RS2, (a0 - d0) * RS2, (a1 + d1) * RS2, (a1 - d1) * RS2);
-        if (!PNP_DBG(1)) stg_stream(zo4 + c * 32 + lane, o);
+        if (!PNP_DBG(1)) stg_keep(zo4 + c * 32 + lane, o);           // the new iterate: the next forward line pass reads it
         if (xr4 && !PNP_DBG(2)) {
             const float4 r = xr4[c * 32 + lane];
             const float e0 = o.x - r.x, e1 = o.y - r.y, e2 = o.z - r.z, e3 = o.w - r.w;
             err = fmaf(e0, e0, fmaf(e1, e1, fmaf(e2, e2, fmaf(e3, e3, err))));
         }
+        if (keep4) keep4[c * 32 + lane] = o;
     }
 #ifdef PNP_TRACE
     }
@@ -1205,7 +1209,8 @@ __device__ __forceinline__ void prox_phases(float* lines, int mine, long long fi
                                             const float* __restrict__ xrec, float sigma_modifier, float fallback_sigma,
                                             double* __restrict__ sig_log, double* __restrict__ mse_log, int cur_slot,
                                             unsigned* scratch, unsigned long long* xbar, int* __restrict__ advance, int n_advance,
-                                            unsigned* __restrict__ gbar /* software grid barrier workspace, or null: cooperative launch */) {
+                                            unsigned* __restrict__ gbar /* software grid barrier workspace, or null: cooperative launch */,
+                                            bool keep_lines = false /* leave the new lines in `lines` (one line per warp only) */) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     auto grid_sync = [&]() {
         if (gbar) {
@@ -1249,7 +1254,8 @@ __device__ __forceinline__ void prox_phases(float* lines, int mine, long long fi
                 if (warp == 0) trace(306);
                 float err = prox_line_inverse<L>(st, reinterpret_cast<float*>(scratch + warp * prox_scratch<L>()), lane, sigma * sigma,
                                                  reinterpret_cast<float4*>(zout + gl * L),
-                                                 xrec ? reinterpret_cast<const float4*>(sl) : nullptr);
+                                                 xrec ? reinterpret_cast<const float4*>(sl) : nullptr,
+                                                 keep_lines ? reinterpret_cast<float4*>(sl) : nullptr);
                 if (xrec && mse_log) {
                     err = warp_sum_f(err);
                     if (lane == 0) atomicAdd(mse_log + (long long)cur_slot * batch + img, (double)err);

@@ -171,14 +171,29 @@ class CSMRI(Problem):
         _lib.check(_lib.load().pnp_csmri_grad(C.byref(args), D.stream()))
 
     def _dev_update_prox(self, gscale, step_ptr, vadd, z_in, z_out, sig_log, sigma_modifier, fallback_sigma, xrec, mse_log,
-                         slot, advance=None, n_advance=0, barrier_ws=None, chain=False, zero_spectrum=False):
+                         slot, advance=None, n_advance=0, barrier_ws=None, chain=False, zero_spectrum=False, next_pass=None):
         """Tail of an inner iteration in one cooperative launch, after ``_dev_grad(..., phases=3)`` left the masked
         spectrum in the scratch: inverse line pass + update + sigma estimate + wavelet prox + PSNR
         (pnp_csmri_update_prox).  Returns False when the image does not suit the resident-line kernel."""
-        rc = _lib.load().pnp_csmri_update_prox(None if zero_spectrum else D.ptr(self._S), self.H, self.W, float(gscale), 0.0, D.ptr(step_ptr), D.ptr(vadd),
-                                               D.ptr(z_in), D.ptr(z_out), D.ptr(sig_log), float(sigma_modifier),
-                                               float(fallback_sigma), D.ptr(xrec), D.ptr(mse_log), D.ptr(slot), D.ptr(advance),
-                                               int(n_advance), D.ptr(barrier_ws), int(bool(chain)), D.stream())
+        nxt = None
+        if next_pass is not None:
+            # the forward line pass (and the minibatch selection) of the NEXT inner iteration, fused into this launch:
+            # next_pass = dict(w=snapshot, sel=selection bytes, job=Engine.sel_job()-style dict or None)
+            job = next_pass.get('job')
+            if job is not None and job.get('idx') is None and int(job['count']) > self.M0:
+                raise ValueError('Cannot take a larger sample (%d) than the %d sampled k-space positions' % (job['count'], self.M0))
+            nxt = _lib.CsmriNextPass(
+                w=D.ptr(next_pass['w']), S_out=D.ptr(self._S), bits=D.ptr(next_pass.get('sel')),
+                sel_count=0 if job is None else int(job['count']), sel_idx=None if job is None else D.ptr(job.get('idx')),
+                sel_support=D.ptr(self._support), sel_m0=D.ptr(self._m0_dev),
+                sel_seed=0 if job is None else int(job.get('seed', 0)) & 0xffffffff,
+                sel_counter=None if job is None else D.ptr(job.get('counter')),
+                sel_counter_add=0 if job is None else int(job.get('counter_add', 0)), sel_min_m0=int(self.M0))
+        rc = _lib.load().pnp_csmri_update_prox_next(None if zero_spectrum else D.ptr(self._S), self.H, self.W, float(gscale), 0.0,
+                                                    D.ptr(step_ptr), D.ptr(vadd), D.ptr(z_in), D.ptr(z_out), D.ptr(sig_log),
+                                                    float(sigma_modifier), float(fallback_sigma), D.ptr(xrec), D.ptr(mse_log),
+                                                    D.ptr(slot), D.ptr(advance), int(n_advance), D.ptr(barrier_ws), int(bool(chain)),
+                                                    None if nxt is None else C.byref(nxt), D.stream())
         if rc == -4:            # PNP_ERR_UNSUPPORTED
             return False
         _lib.check(rc)

@@ -128,3 +128,32 @@ def test_as_committed_mode_epoch_graph(cuda):
     b = pnp_svrg(dut, TVDenoiser(), fast=True, **kw)
     assert rel_l2(b['z'], a['z']) < 1e-6
     assert np.allclose(a['psnr_per_iter'], b['psnr_per_iter'], atol=0.011)
+
+
+@pytest.mark.parametrize('H,B,src', [(512, 5000, 'device'), (1024, 20000, 'stream'), (2048, 100000, 'host')])
+def test_fused_next_line_pass_equals_separate_passes(cuda, H, B, src):
+    """With PNP_FUSE_R2C=1 whole-epoch graphs run the forward line pass and the minibatch selection of iteration j + 1
+    inside the tail launch of iteration j (pnp_csmri_update_prox_next); all epoch graphs skip the transforms of the first
+    iteration of an epoch (z == w).  The default keeps the separate passes; the eager loop (fast=False) runs every pass of
+    every iteration.  Same minibatches -> the same iterates (the arithmetic is the same, only its place changes)."""
+    import os
+    from pnp_svrg_b200.algorithms import pnp_svrg
+    from pnp_svrg_b200.denoisers import TVDenoiser
+    _, dut = _pair(H)
+    T2, n = 4, 11                                   # two whole epochs + 3 iterations through the per-iteration graph
+    kw = dict(eta=0.15 * dut.M0, T2=T2, mini_batch_size=B, vr_mode='paper', converge_check=False, verbose=False, tt=1e9,
+              max_iters=n, lr_decay=0.9, mb_source=src, mb_seed=9)
+    if src == 'stream':
+        kw['mb_stream'] = _stream(dut, B, n, seed=2)
+    b = pnp_svrg(dut, TVDenoiser(), fast=True, **kw)
+    os.environ['PNP_FUSE_R2C'] = '1'
+    try:
+        a = pnp_svrg(dut, TVDenoiser(), fast=True, **kw)
+    finally:
+        os.environ.pop('PNP_FUSE_R2C', None)
+    assert rel_l2(a['z'], b['z']) < 1e-6, rel_l2(a['z'], b['z'])
+    assert np.allclose(a['psnr_per_iter'], b['psnr_per_iter'], atol=0.011)
+    if H <= 1024:
+        c = pnp_svrg(dut, TVDenoiser(), fast=False, **kw)
+        assert rel_l2(a['z'], c['z']) < 2e-6, rel_l2(a['z'], c['z'])
+        assert np.allclose(a['psnr_per_iter'], c['psnr_per_iter'], atol=0.011)
