@@ -208,6 +208,8 @@ def run_b200(a, cfg, rank, world, local_rank):
     dev = torch.device('cuda', local_rank)
     if world > 1:
         dist.init_process_group('nccl', device_id=dev)
+        from pnp_svrg_b200.device import pin_to_local_rank
+        pin_to_local_rank(local_rank)                 # the ranks' sampler threads and Python loops get disjoint cores
     prob, run = make_run(cfg, seed=rank)
     eng = run.eng
     T2, N = cfg['T2'], cfg['H'] * cfg['W']
@@ -258,7 +260,8 @@ def run_b200(a, cfg, rank, world, local_rank):
         'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': a.steps, 'warmup': a.warmup,
         'ms_per_step': total_ms / a.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
         'dtype': 'f32', 'data': 'synthetic', 'config': cfg,
-        'gpu_launches': a.steps * (T2 * (LAUNCHES_PER_INNER if fused else 7) + LAUNCHES_PER_SNAPSHOT),
+        # fused tail: the first inner iteration of an epoch is ONE launch (z == w: no transform passes), the others three
+        'gpu_launches': a.steps * (((T2 - 1) * LAUNCHES_PER_INNER + 1 if fused else T2 * 7) + LAUNCHES_PER_SNAPSHOT),
         'clocks': clocks, 'wall_s_timed_region': t_wall,
         'timed_path': "pnp_svrg_b200.algorithms.SvrgRun.epoch() -- the whole-epoch CUDA graph that the public "
                       "pnp_svrg(..., fast=True) replays (mb_source='device'); parity: tests/test_gpu_epoch.py",

@@ -130,6 +130,8 @@ def sweep(rank, world, dev, iters=200, size=256, batch=120, with_cpu=True, pipel
     if world > 1:
         SW._gather_records(jobs, [], rank, world)             # warm-up of the two collectives of the record gather (same shapes)
     _barrier(world, dev)
+    if pipelined:
+        batch_runner.build_seconds = 0.0
     t0 = time.time()
     recs = SW.run_partitioned_batched(jobs, batch_runner, rank, world, batch=batch, gather=True)
     _barrier(world, dev)
@@ -148,6 +150,11 @@ def sweep(rank, world, dev, iters=200, size=256, batch=120, with_cpu=True, pipel
            'value': len(recs) / dt, 'unit': 'recon/s', 'jobs': len(recs), 'failed': len(recs) - len(ok), 'seconds': dt, 'n_gpus': world,
            'inner_iterations_per_s': len(recs) * iters / dt,
            'mean_psnr_gain_db': float(np.mean([r['psnr_final'] - r['psnr_init'] for r in ok])) if ok else None}
+    if pipelined:
+        out['construct_seconds'] = batch_runner.build_seconds
+        out['construct_note'] = ('time rank 0 spent inside batched.csmri_device_batch (masks, measurements, Xinit, support lists: torch RNG / '
+                                 'torch.fft / torch.sort -- library calls, in the CONSTRUCTOR only) during the timed sweep; every batch but '
+                                 'the first is built while the previous one runs')
     if with_cpu and world == 1:
         out['cpu_baseline'] = sweep_cpu_baseline(iters=iters)
     return out

@@ -10,6 +10,28 @@ def require_cuda():
     return torch.device('cuda', torch.cuda.current_device())
 
 
+def pin_to_local_rank(local_rank=None, local_world=None):
+    """One process per GPU on a shared host: give every local rank its own slice of the cores this process may run on
+    (``sched_setaffinity``), so that the ranks' host-side sampler threads (``pnp_host_draws_*``) and Python loops do not
+    fight over the same cores -- the worker-thread count of the look-ahead draw queue follows the affinity mask.
+    Arguments default to torchrun's LOCAL_RANK / LOCAL_WORLD_SIZE.  Returns the cores kept (None: nothing changed)."""
+    import os
+    if not hasattr(os, 'sched_setaffinity'):
+        return None
+    try:
+        lr = int(os.environ.get('LOCAL_RANK', '0')) if local_rank is None else int(local_rank)
+        lw = int(os.environ.get('LOCAL_WORLD_SIZE', os.environ.get('WORLD_SIZE', '1'))) if local_world is None else int(local_world)
+        cores = sorted(os.sched_getaffinity(0))
+        if lw <= 1 or len(cores) < 2 * lw:
+            return None
+        share = len(cores) // lw
+        mine = cores[lr * share:(lr + 1) * share]
+        os.sched_setaffinity(0, mine)
+        return mine
+    except (OSError, ValueError):
+        return None
+
+
 def stream():
     return torch.cuda.current_stream().cuda_stream
 

@@ -165,6 +165,7 @@ class DeviceBatchPipeline:
         self.inflight = []           # (slot, run, jobs, t0)
         self.n = 0
         self.batch_size = None       # size of the first group: shorter groups (the tail of a rank's share) are padded to it
+        self.build_seconds = 0.0     # host time inside csmri_device_batch (ends with a device->host read of M0: ~ its GPU time)
 
     def _image(self, job):
         images, H, W = self.kw['images'], self.kw['H'], self.kw['W']
@@ -194,8 +195,10 @@ class DeviceBatchPipeline:
             # same shape as the engines that exist (no allocation, no new launch geometry inside a sweep): repeat the last job;
             # the copies' records are dropped
             jobs = list(jobs) + [dict(jobs[-1], _pad=True)] * (self.batch_size - len(jobs))
+        tb = time.time()
         batch = csmri_device_batch([self._image(j) for j in jobs], [j['alpha'] for j in jobs], [j['snr'] for j in jobs], k['H'], k['W'],
                                    seed=k['seed'] + jobs[0]['id'])
+        self.build_seconds += time.time() - tb
         done = None
         if len(self.inflight) >= self.depth:         # the engine this group needs: its previous run finished `depth` groups ago
             done = self._collect(self.inflight.pop(0))

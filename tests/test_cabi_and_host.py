@@ -243,3 +243,27 @@ print('SIMD-OK')
     r = subprocess.run([sys.executable, '-c', code], cwd=root, env=dict(os.environ, PNP_HOST_SIMD=simd, PYTHONPATH=root),
                        capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and 'SIMD-OK' in r.stdout, r.stdout[-1000:] + r.stderr[-3000:]
+
+
+def test_pin_to_local_rank_gives_disjoint_core_slices():
+    """one process per GPU on one host: the local ranks' sampler threads get disjoint slices of the allowed cores"""
+    import os
+    from pnp_svrg_b200.device import pin_to_local_rank
+    if not hasattr(os, 'sched_setaffinity'):
+        pytest.skip('no sched_setaffinity on this platform')
+    before = sorted(os.sched_getaffinity(0))
+    try:
+        if len(before) < 4:
+            assert pin_to_local_rank(0, 2) is None and sorted(os.sched_getaffinity(0)) == before
+            return
+        seen = []
+        for r in range(2):
+            os.sched_setaffinity(0, before)
+            mine = pin_to_local_rank(r, 2)
+            assert mine == sorted(os.sched_getaffinity(0)) and len(mine) == len(before) // 2
+            seen.append(set(mine))
+        assert not (seen[0] & seen[1])
+        os.sched_setaffinity(0, before)
+        assert pin_to_local_rank(0, 1) is None and sorted(os.sched_getaffinity(0)) == before       # single process: untouched
+    finally:
+        os.sched_setaffinity(0, before)
