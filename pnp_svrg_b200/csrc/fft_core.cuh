@@ -267,19 +267,23 @@ struct Dft<1> {
 };
 
 // ------------------------------------------------------------------ plans
-template <int L> struct FftPlan;
-template <> struct FftPlan<8>    { static constexpr int NS = 1, R0 = 8,  R1 = 1,  R2 = 1,  EPT = 8;  };
-template <> struct FftPlan<16>   { static constexpr int NS = 1, R0 = 16, R1 = 1,  R2 = 1,  EPT = 16; };
-template <> struct FftPlan<32>   { static constexpr int NS = 2, R0 = 8,  R1 = 4,  R2 = 1,  EPT = 8;  };
-template <> struct FftPlan<64>   { static constexpr int NS = 2, R0 = 8,  R1 = 8,  R2 = 1,  EPT = 8;  };
-template <> struct FftPlan<128>  { static constexpr int NS = 2, R0 = 16, R1 = 8,  R2 = 1,  EPT = 16; };
-template <> struct FftPlan<256>  { static constexpr int NS = 2, R0 = 16, R1 = 16, R2 = 1,  EPT = 16; };
-template <> struct FftPlan<512>  { static constexpr int NS = 3, R0 = 8,  R1 = 8,  R2 = 8,  EPT = 8;  };
-template <> struct FftPlan<1024> { static constexpr int NS = 3, R0 = 16, R1 = 8,  R2 = 8,  EPT = 16; };
-template <> struct FftPlan<2048> { static constexpr int NS = 3, R0 = 16, R1 = 16, R2 = 8,  EPT = 16; };
-template <> struct FftPlan<4096> { static constexpr int NS = 3, R0 = 16, R1 = 16, R2 = 16, EPT = 16; };
+// V = plan variant (0 everywhere but the cluster kernel of csrc/small.cuh): variant 1 of length 256 is 8 x 8 x 4 with 8
+// values per thread, i.e. 32 threads = one whole warp per transform -- half the dependent work per thread of the 16 x 16
+// plan (16 threads), for a phase that has only as many transforms as the CTA has warps.
+template <int L, int V = 0> struct FftPlan;
+template <> struct FftPlan<8, 0>    { static constexpr int NS = 1, R0 = 8,  R1 = 1,  R2 = 1,  EPT = 8;  };
+template <> struct FftPlan<16, 0>   { static constexpr int NS = 1, R0 = 16, R1 = 1,  R2 = 1,  EPT = 16; };
+template <> struct FftPlan<32, 0>   { static constexpr int NS = 2, R0 = 8,  R1 = 4,  R2 = 1,  EPT = 8;  };
+template <> struct FftPlan<64, 0>   { static constexpr int NS = 2, R0 = 8,  R1 = 8,  R2 = 1,  EPT = 8;  };
+template <> struct FftPlan<128, 0>  { static constexpr int NS = 2, R0 = 16, R1 = 8,  R2 = 1,  EPT = 16; };
+template <> struct FftPlan<256, 0>  { static constexpr int NS = 2, R0 = 16, R1 = 16, R2 = 1,  EPT = 16; };
+template <> struct FftPlan<256, 1>  { static constexpr int NS = 3, R0 = 8,  R1 = 8,  R2 = 4,  EPT = 8;  };
+template <> struct FftPlan<512, 0>  { static constexpr int NS = 3, R0 = 8,  R1 = 8,  R2 = 8,  EPT = 8;  };
+template <> struct FftPlan<1024, 0> { static constexpr int NS = 3, R0 = 16, R1 = 8,  R2 = 8,  EPT = 16; };
+template <> struct FftPlan<2048, 0> { static constexpr int NS = 3, R0 = 16, R1 = 16, R2 = 8,  EPT = 16; };
+template <> struct FftPlan<4096, 0> { static constexpr int NS = 3, R0 = 16, R1 = 16, R2 = 16, EPT = 16; };
 
-template <int L> __host__ __device__ constexpr int fft_threads() { return L / FftPlan<L>::EPT; }
+template <int L, int V = 0> __host__ __device__ constexpr int fft_threads() { return L / FftPlan<L, V>::EPT; }
 
 // padded index into the complex exchange buffer: one extra float2 every 16 spreads the
 // power-of-two strides of the Stockham exchanges over the banks (64-bit accesses: 16 lanes per phase)
@@ -300,8 +304,8 @@ struct SmemBuf {
 // a following inverse transform need no shared-memory exchange at all.
 //   input  order: x[b*R0 + r]            holds element  (t + b*T) + r*(L/R0)
 //   output order: x[b*RL + r] (RL last radix) holds element  (t + b*T) + r*(L/RL)
-template <int L> struct FftIdx {
-    using P = FftPlan<L>;
+template <int L, int V = 0> struct FftIdx {
+    using P = FftPlan<L, V>;
     static constexpr int EPT = P::EPT, T = L / P::EPT;
     static constexpr int RL = P::NS == 1 ? P::R0 : (P::NS == 2 ? P::R1 : P::R2);
     __host__ __device__ static constexpr int in(int t, int i) { return t + (i / P::R0) * T + (i % P::R0) * (L / P::R0); }
@@ -329,8 +333,8 @@ __device__ __forceinline__ void twiddle_powers(float2 w1, float2 (&w)[16]) {
 
 // per-thread base twiddles exp(-2*pi*i*k/(NSP*R)), k = (t + b*T) % NSP, of the stages after the
 // first.  They depend on the thread only, so persistent kernels load them once.
-template <int L> struct FftTw {
-    using P = FftPlan<L>;
+template <int L, int V = 0> struct FftTw {
+    using P = FftPlan<L, V>;
     static constexpr int EPT = P::EPT, T = L / P::EPT;
     static constexpr int NB1 = P::NS >= 2 ? EPT / P::R1 : 1;
     static constexpr int NB2 = P::NS >= 3 ? EPT / P::R2 : 1;
@@ -347,9 +351,9 @@ template <int L> struct FftTw {
     }
 };
 
-template <int L, int R, int NSP, int NBW>
-__device__ __forceinline__ void fft_reg_stage(int t, float2 (&x)[FftPlan<L>::EPT], const float2 (&w1)[NBW]) {
-    constexpr int EPT = FftPlan<L>::EPT;
+template <int L, int R, int NSP, int NBW, int V = 0>
+__device__ __forceinline__ void fft_reg_stage(int t, float2 (&x)[FftPlan<L, V>::EPT], const float2 (&w1)[NBW]) {
+    constexpr int EPT = FftPlan<L, V>::EPT;
     constexpr int NB = EPT / R;
 #pragma unroll
     for (int b = 0; b < NB; ++b) {
@@ -371,9 +375,9 @@ __device__ __forceinline__ void fft_reg_stage(int t, float2 (&x)[FftPlan<L>::EPT
 // exchange between a stage of radix RA (prefix NSP) and the next stage of radix RB
 // WS: the T cooperating threads live in ONE warp (T <= 32): warp barriers instead of CTA barriers, so transforms of
 // different warps need not run in lock step (csrc/small.cuh)
-template <int L, int RA, int NSP, int RB, bool WS = false>
-__device__ __forceinline__ void fft_reg_exchange(int t, const SmemBuf& sb, float2 (&x)[FftPlan<L>::EPT]) {
-    constexpr int EPT = FftPlan<L>::EPT;
+template <int L, int RA, int NSP, int RB, bool WS = false, int V = 0>
+__device__ __forceinline__ void fft_reg_exchange(int t, const SmemBuf& sb, float2 (&x)[FftPlan<L, V>::EPT]) {
+    constexpr int EPT = FftPlan<L, V>::EPT;
     constexpr int T = L / EPT;
 #pragma unroll
     for (int b = 0; b < EPT / RA; ++b) {
@@ -393,19 +397,19 @@ __device__ __forceinline__ void fft_reg_exchange(int t, const SmemBuf& sb, float
 
 // In-register forward FFT.  The exchange buffer must be free on entry; on exit the LAST exchange's
 // reads may still be in flight in other threads: callers sync before writing the buffer again.
-template <int L, bool WS = false>
-__device__ __forceinline__ void fft_regs(int t, const SmemBuf& sb, float2 (&x)[FftPlan<L>::EPT], const FftTw<L>& tw) {
-    using P = FftPlan<L>;
+template <int L, bool WS = false, int V = 0>
+__device__ __forceinline__ void fft_regs(int t, const SmemBuf& sb, float2 (&x)[FftPlan<L, V>::EPT], const FftTw<L, V>& tw) {
+    using P = FftPlan<L, V>;
     static_assert(!WS || L / P::EPT <= 32, "warp-synchronous transform: the cooperating threads must fit one warp");
-    fft_reg_stage<L, P::R0, 1>(t, x, tw.s1);
+    fft_reg_stage<L, P::R0, 1, FftTw<L, V>::NB1, V>(t, x, tw.s1);
     if constexpr (P::NS >= 2) {
-        fft_reg_exchange<L, P::R0, 1, P::R1, WS>(t, sb, x);
-        fft_reg_stage<L, P::R1, P::R0>(t, x, tw.s1);
+        fft_reg_exchange<L, P::R0, 1, P::R1, WS, V>(t, sb, x);
+        fft_reg_stage<L, P::R1, P::R0, FftTw<L, V>::NB1, V>(t, x, tw.s1);
     }
     if constexpr (P::NS >= 3) {
         if (WS) __syncwarp(); else __syncthreads();   // reads of the first exchange done before the second writes
-        fft_reg_exchange<L, P::R1, P::R0, P::R2, WS>(t, sb, x);
-        fft_reg_stage<L, P::R2, P::R0 * P::R1>(t, x, tw.s2);
+        fft_reg_exchange<L, P::R1, P::R0, P::R2, WS, V>(t, sb, x);
+        fft_reg_stage<L, P::R2, P::R0 * P::R1, FftTw<L, V>::NB2, V>(t, x, tw.s2);
     }
 }
 template <int L>

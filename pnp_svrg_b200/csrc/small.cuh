@@ -4,8 +4,8 @@
 //
 // Reference: algorithms/pnp_svrg.py:26-95 (the loop), problems/CSMRI.py:76-89 (gradients), denoisers/TV.py:21-26 and
 // the estimate_sigma call at pnp_svrg.py:71 (prox).  Same arithmetic as the three-pass path of csmri.cuh + prox.cuh
-// (same FFT plan, same unpacking, same selection, same epilogues, same sigma estimate and shrink), so the two paths
-// agree to fp32 rounding of a few reductions.
+// (same unpacking, same selection, same epilogues, same sigma estimate and shrink; at 256 a transform plan with other
+// radices), so the two paths agree to fp32 rounding.
 //
 // WHY.  A 256x256 iteration moves ~2 MB: on the multi-launch path it is five dependent grid-wide steps of ~4 us each
 // (launch + drain + first-load latency), 1 % of the HBM roofline.  Here nothing leaves the SMs:
@@ -13,8 +13,9 @@
 //     the packed spectrum rows [q L/(2C), (q+1) L/(2C));
 //   * the two transpositions of the 2-D transform are 16-byte stores into the shared memory of the CTA that owns the
 //     destination row / line pair (distributed shared memory), followed by a cluster barrier;
-//   * an FFT of length L <= 256 is done by T = L/16 <= 16 threads, i.e. inside one warp: the Stockham exchanges need
-//     warp barriers only (fft_regs<L, true>), the warps of a phase do not run in lock step;
+//   * an FFT of length L <= 256 is done by at most 32 threads, i.e. inside one warp (length 256: the 8 x 8 x 4 plan
+//     variant, one whole warp per transform, so that all 16 warps of a CTA of a cluster of 8 transform at once): the
+//     Stockham exchanges need warp barriers only (fft_regs<L, true, V>), the warps of a phase do not run in lock step;
 //   * the minibatch selection of iteration t is built in shared memory by the warps that have no transform in the
 //     forward line phase (every CTA scans the B drawn positions and keeps the bits of its own rows);
 //   * the sigma estimate's mean over lines is a cluster reduction: every CTA writes its partial sum into a slot of
@@ -52,8 +53,9 @@ struct SmallArgs {
 };
 
 template <int L, int C, int NT_ = 512> struct SmallCfg {
-    static constexpr int T = fft_threads<L>();
-    static constexpr int EPT = FftPlan<L>::EPT;
+    static constexpr int V = L == 256 ? 1 : 0;              // transform plan variant (fft_core.cuh): 256 = 8 x 8 x 4 on 32 threads
+    static constexpr int T = fft_threads<L, V>();
+    static constexpr int EPT = FftPlan<L, V>::EPT;
     static constexpr int NT = NT_, NW = NT / 32;
     static constexpr int LPC = L / C;                       // lines per CTA
     static constexpr int PPC = LPC / 2;                     // line pairs per CTA = transforms per line phase
@@ -62,8 +64,12 @@ template <int L, int C, int NT_ = 512> struct SmallCfg {
     static constexpr int PL2 = 2 * fft_plane<L>();
     static constexpr int GS = PL2 + ((2 - PL2 % 32) + 32) % 32;   // exchange-buffer stride == 2 (mod 32): group g is shifted by g float2
     static constexpr int GPW = 32 / T;                      // transforms per warp
-    static constexpr int FW = PPC * T / 32;                 // warps that transform in a phase
-    static constexpr int NEX = PPC + GPW;                   // + the warp of packed row 0
+    static constexpr int FT = PPC * T;                      // threads that transform in a line phase
+    // column phase: warp 0 holds packed row 0 of the CTA alone (in CTA 0 that row is the DC + i Nyquist packing and takes
+    // another code path: a warp must not diverge around the warp barriers of the transforms), rows 1 .. RPC - 1 follow
+    static constexpr int BT = ((RPC - 1 + GPW) * T + 31) / 32 * 32;     // threads of the column phase (whole warps)
+    static constexpr int BG = BT / T;                       // its transform groups (the last ones may have no row)
+    static constexpr int NEX = BG > PPC ? BG : PPC;
     static constexpr int NLW = LPC / NW;                    // lines per warp in the prox phases
     static constexpr int EXF = NEX * GS > NW * NLW * PNP_SIG_SCRATCH ? NEX * GS : NW * NLW * PNP_SIG_SCRATCH;
     static constexpr int OFF_Z = 0;
@@ -77,7 +83,7 @@ template <int L, int C, int NT_ = 512> struct SmallCfg {
     static constexpr int FLOATS = OFF_RED + 2 * (C + 2 * NW);
     static constexpr size_t SMEM = sizeof(float) * (size_t)FLOATS;
     static_assert(PPC == RPC, "line pairs and packed rows per CTA");
-    static_assert(T <= 32 && 32 % T == 0 && (PPC * T) % 32 == 0 && FW + 1 <= NW, "transform groups must tile whole warps");
+    static_assert(T <= 32 && 32 % T == 0 && FT % 32 == 0 && FT <= NT && BT <= NT, "transform groups must tile whole warps of the CTA");
     static_assert(LPC % NW == 0 && NLW >= 1 && NLW <= 2, "one or two lines per warp in the prox phases");
     static_assert(L % 128 == 0 && L <= 256, "chunk-cyclic Haar layout: 128 or 256 samples per line");
     static_assert(OFF_RED % 2 == 0, "double alignment");
@@ -85,7 +91,7 @@ template <int L, int C, int NT_ = 512> struct SmallCfg {
 
 __device__ __forceinline__ void named_bar(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 
-// see "Minibatch selection" in the kernel below; threads FT + 32 .. NT - 1 of the CTA take part.
+// see "Minibatch selection" in the kernel below
 // or the bits of k-space position k (set_sel_bits of csmri.cuh) into the selection rows of their owner CTAs
 template <int L, int C, int NT, class Cluster>
 __device__ __forceinline__ void set_sel_bits_cluster(Cluster& cluster, unsigned char* bits, int k) {
@@ -104,42 +110,35 @@ __device__ __forceinline__ void set_sel_bits_cluster(Cluster& cluster, unsigned 
 }
 
 // CTA q of the cluster draws positions q, q + C, ... of minibatch `it` and ORs their bits into buffer it & 1 of the CTAs
-// that own the rows (distributed shared-memory atomics; the buffers were zeroed a cluster barrier earlier)
-template <int L, int C, int NT, class Cluster>
-__device__ __forceinline__ void small_select(Cluster& cluster, const SmallArgs& a, unsigned char* bits_mb, int img, int q, unsigned draw0,
-                                             unsigned sel_n, const FeistelDom& sel_dom, int sel_count, int it) {
-    using K = SmallCfg<L, C, NT>;
-    constexpr int RPC = K::RPC, FT = K::FW * 32, NS = K::NT - FT - 32;
-    const int sid = (int)threadIdx.x - FT - 32;
-    if (sid < 0) return;
-    unsigned char* bits = bits_mb + (it & 1) * (RPC * L);
-    const int* src = a.idx ? a.idx + (long long)img * a.idx_img_stride + (long long)it * a.idx_iter_stride : nullptr;
-    const unsigned key = mix32(a.seed ^ mix32((draw0 + (unsigned)it) * 0x632be5abU + (unsigned)img));
-    const int* sup = a.support + (long long)img * a.support_img_stride;
-    for (int i = q + C * sid; i < sel_count; i += C * NS) {
-        int k;
-        if (src) k = src[i];
-        else k = sup[feistel_perm((unsigned)i, sel_n, key, sel_dom)];
-        set_sel_bits_cluster<L, C, NT>(cluster, bits, k);
+// that own the rows (distributed shared-memory atomics; the buffers were zeroed a cluster barrier earlier).  Two halves
+// around the transforms of the column phase: `fetch` (permutation + support lookup: a dependent global load whose latency
+// the transforms hide) and `commit` (the atomics); every thread of the CTA takes positions q + C * (tid + n * NT).
+template <int L, int C, int NT>
+struct SmallSel {
+    const int* src;
+    const int* sup;
+    unsigned key, n;
+    int count, q;
+    FeistelDom dom;
+    __device__ __forceinline__ int fetch(int i) const {
+        if (i >= count) return -1;
+        return src ? src[i] : sup[feistel_perm((unsigned)i, n, key, dom)];
     }
-}
+};
 template <int L, int C, int NT>
 __device__ __forceinline__ void small_select_clear(unsigned char* bits_mb, int buf) {
     using K = SmallCfg<L, C, NT>;
-    constexpr int RPC = K::RPC, FT = K::FW * 32, NS = K::NT - FT - 32;
-    const int sid = (int)threadIdx.x - FT - 32;
-    if (sid < 0) return;
-    unsigned char* bits = bits_mb + buf * (RPC * L);
-    for (int i = sid; i < RPC * L / 16; i += NS) reinterpret_cast<uint4*>(bits)[i] = make_uint4(0u, 0u, 0u, 0u);
+    unsigned char* bits = bits_mb + buf * (K::RPC * L);
+    for (int i = threadIdx.x; i < K::RPC * L / 16; i += NT) reinterpret_cast<uint4*>(bits)[i] = make_uint4(0u, 0u, 0u, 0u);
 }
 
 template <int L, int C, int NT = 512>
 __global__ void __launch_bounds__(NT, NT <= 256 ? 2 : 1) k_csmri_svrg_small(SmallArgs a) {
     using K = SmallCfg<L, C, NT>;
-    using IX = FftIdx<L>;
-    constexpr int T = K::T, EPT = K::EPT, LPC = K::LPC, PPC = K::PPC, RPC = K::RPC, LS = K::LS, GS = K::GS, FW = K::FW,
-                  NW = K::NW, NLW = K::NLW, GPW = K::GPW;
-    constexpr int FT = FW * 32;                                  // threads that transform
+    constexpr int V = K::V;
+    using IX = FftIdx<L, V>;
+    constexpr int T = K::T, EPT = K::EPT, LPC = K::LPC, PPC = K::PPC, RPC = K::RPC, LS = K::LS, GS = K::GS, FT = K::FT,
+                  BT = K::BT, NW = K::NW, NLW = K::NLW, GPW = K::GPW;
     constexpr int LEVELS = HaarCfg<L>::LEVELS, NCH = L / 128;
     namespace cg = cooperative_groups;
     cg::cluster_group cluster = cg::this_cluster();
@@ -167,7 +166,7 @@ __global__ void __launch_bounds__(NT, NT <= 256 ? 2 : 1) k_csmri_svrg_small(Smal
     const bool is_fft = tid < FT;
     const int g = is_fft ? tid / T : 0, t = tid % T;
     const SmemBuf sb{ex + g * GS, nullptr};
-    FftTw<L> tw;
+    FftTw<L, V> tw;
     tw.init(t);
 
     // ---- resident state: my lines of z, my rows of the full-mask selection ----
@@ -205,7 +204,7 @@ __global__ void __launch_bounds__(NT, NT <= 256 ? 2 : 1) k_csmri_svrg_small(Smal
             if (sub) { re -= lw[idx]; im -= lw[idx + LS]; }
             x[i] = make_float2(re, im);
         }
-        fft_regs<L, true>(t, sb, x, tw);
+        fft_regs<L, true, V>(t, sb, x, tw);
         __syncwarp();
 #pragma unroll
         for (int i = 0; i < EPT; ++i) sb.put(IX::out(t, i), x[i]);
@@ -224,40 +223,56 @@ __global__ void __launch_bounds__(NT, NT <= 256 ? 2 : 1) k_csmri_svrg_small(Smal
         }
     };
 
-    // Minibatch selection of inner iteration `it`: selection bytes of my rows in buffer it & 1.  Built one iteration AHEAD
-    // by the warps that never transform (warp FW + 1 ..: warp FW owns packed row 0 in the column phase): every CTA draws
-    // 1/C of the positions and ORs the bits into the rows' owners through distributed shared memory, during the column
-    // phase of iteration it - 1; the buffer was zeroed by its owner during the inverse line phase of iteration it - 2,
-    // right after its last use.  Cluster barriers separate zeroing, filling and use.  (Inside the forward line phase,
-    // every CTA scanning all B positions for its own rows, the selection took 3.3 us for B = 1000 against 1.9 us of
-    // transforms; spread over the other phases the same work slowed those down by as much.)
+    // Minibatch selection of inner iteration `it`: selection bytes of my rows in buffer it & 1.  Built one iteration AHEAD,
+    // during the column phase of iteration it - 1: every CTA draws 1/C of the positions (fetched before its transforms,
+    // so that the dependent support lookup is hidden) and ORs the bits into the rows' owners through distributed
+    // shared-memory atomics after them; the buffer was zeroed by its owner during the inverse line phase of iteration
+    // it - 2, right after its last use.  Cluster barriers separate zeroing, filling and use.  (Inside the forward line
+    // phase, every CTA scanning all B positions for its own rows, the selection took 3.3 us for B = 1000 against 1.9 us
+    // of transforms; spread over the other phases the same work slowed those down by as much.)
     const unsigned sel_n = a.idx ? 0u : (unsigned)a.m0[img];
-    const FeistelDom sel_dom = feistel_domain(sel_n > 1u ? sel_n : 2u);
     const int sel_count = a.idx ? a.B : ((unsigned)a.B < sel_n ? a.B : (int)sel_n);
-    auto select = [&](int it) { small_select<L, C, NT>(cluster, a, bits_mb, img, q, draw0, sel_n, sel_dom, sel_count, it); };
+    SmallSel<L, C, NT> ss;
+    ss.sup = a.support + (long long)img * a.support_img_stride;
+    ss.n = sel_n; ss.count = sel_count; ss.q = q; ss.dom = feistel_domain(sel_n > 1u ? sel_n : 2u);
+    auto sel_begin = [&](int it) {                               // -> first position of this thread (or -1)
+        ss.src = a.idx ? a.idx + (long long)img * a.idx_img_stride + (long long)it * a.idx_iter_stride : nullptr;
+        ss.key = mix32(a.seed ^ mix32((draw0 + (unsigned)it) * 0x632be5abU + (unsigned)img));
+        return ss.fetch(q + C * (NT - 1 - tid));                 // from the last warp down: those have no transform when warps are spare
+    };
+    auto sel_end = [&](int it, int k0) {
+        unsigned char* bits = bits_mb + (it & 1) * (RPC * L);
+        if (k0 >= 0) set_sel_bits_cluster<L, C, NT>(cluster, bits, k0);
+        for (int i = q + C * (NT - 1 - tid + NT); i < sel_count; i += C * NT) set_sel_bits_cluster<L, C, NT>(cluster, bits, ss.fetch(i));
+    };
 
     // column pass on my packed rows: forward, selection (and measurements), inverse, sent to the owners of the lines
     auto phase_b = [&](const unsigned char* bits, bool use_y) {
         float2* T2f = reinterpret_cast<float2*>(Tb);             // [L/2][LPC]
-        if (is_fft) {
-            const int kyp = q * RPC + g;
+        const int gb = tid / T;                                  // transform group of the column phase
+        const int rl = gb < GPW ? (gb == 0 ? 0 : -1) : gb - (GPW - 1);      // my packed row of this CTA (warp 0: row 0 only)
+        if (tid < BT && !(warp == 0 && q == 0)) {
+            const bool active = rl >= 0 && rl < RPC;
+            const int r = active ? rl : 0;
+            const int kyp = q * RPC + r;
             const long long crow = yoff + (long long)kyp * L;
+            const SmemBuf sbb{ex + gb * GS, nullptr};
             float2 x[EPT], y[EPT];
             unsigned long long bbp = 0ull;
 #pragma unroll
-            for (int i = 0; i < EPT; ++i) x[i] = Sb[g * L + IX::in(t, i)];
+            for (int i = 0; i < EPT; ++i) x[i] = active ? Sb[r * L + IX::in(t, i)] : make_float2(0.f, 0.f);
 #pragma unroll
-            for (int m = 0; m < EPT; ++m) bbp |= (unsigned long long)(bits[g * L + t + T * m] & 0xFu) << (4 * m);
-            fft_regs<L, true>(t, sb, x, tw);
+            for (int m = 0; m < EPT; ++m) bbp |= (unsigned long long)(bits[r * L + t + T * m] & 0xFu) << (4 * m);
+            fft_regs<L, true, V>(t, sbb, x, tw);
 #pragma unroll
             for (int m = 0; m < EPT; ++m) {
                 const int kx = t + T * m;
-                const float2 o = apply_sel(x[IX::out_slot(m)], (unsigned)(bbp >> (4 * m)) & 0xFu, use_y, a.Y1 + crow + kx, a.Y2 + crow + kx);
+                const float2 o = apply_sel(x[IX::out_slot(m)], active ? (unsigned)(bbp >> (4 * m)) & 0xFu : 0u, use_y, a.Y1 + crow + kx, a.Y2 + crow + kx);
                 y[IX::in_slot(m)] = cswap(o);
             }
             __syncwarp();
-            fft_regs<L, true>(t, sb, y, tw);
-            if (kyp != 0) {
+            fft_regs<L, true, V>(t, sbb, y, tw);
+            if (active) {
 #pragma unroll
                 for (int i = 0; i < EPT; ++i) {
                     const int c = IX::out(t, i);
@@ -265,21 +280,21 @@ __global__ void __launch_bounds__(NT, NT <= 256 ? 2 : 1) k_csmri_svrg_small(Smal
                     *dst = cswap(y[i]);
                 }
             }
-        } else if (warp == FW && q == 0) {
+        } else if (warp == 0 && q == 0) {
             // packed row 0: C = FFT(DC + i * Nyquist); split, select each of the two rows, re-pack (k_cols_mask, column 0)
             const int g0 = lane / T;
-            const SmemBuf s0{ex + (PPC + g0) * GS, nullptr};
+            const SmemBuf s0{ex + g0 * GS, nullptr};
             float2 x[EPT];
 #pragma unroll
             for (int i = 0; i < EPT; ++i) x[i] = g0 == 0 ? Sb[IX::in(t, i)] : make_float2(0.f, 0.f);
-            fft_regs<L, true>(t, s0, x, tw);
+            fft_regs<L, true, V>(t, s0, x, tw);
             __syncwarp();
 #pragma unroll
             for (int i = 0; i < EPT; ++i) s0.put(IX::out(t, i), x[i]);
             __syncwarp();
             {
                 // all lanes of the warp split / select / re-pack the spectrum of group 0
-                const SmemBuf sz{ex + PPC * GS, nullptr};
+                const SmemBuf sz{ex, nullptr};
                 const float2* y1i = a.Y1 + yoff;
                 const float2* y2i = a.Y2 + yoff;
                 const float2* y1n = a.Y1n + (long long)img * L;
@@ -302,7 +317,7 @@ __global__ void __launch_bounds__(NT, NT <= 256 ? 2 : 1) k_csmri_svrg_small(Smal
 #pragma unroll
             for (int i = 0; i < EPT; ++i) x[i] = s0.get(IX::in(t, i));
             __syncwarp();
-            fft_regs<L, true>(t, s0, x, tw);
+            fft_regs<L, true, V>(t, s0, x, tw);
             if (g0 == 0) {
 #pragma unroll
                 for (int i = 0; i < EPT; ++i) {
@@ -337,7 +352,7 @@ __global__ void __launch_bounds__(NT, NT <= 256 ? 2 : 1) k_csmri_svrg_small(Smal
 #pragma unroll
         for (int i = 0; i < EPT; ++i) x[i] = sb.get(IX::in(t, i));
         __syncwarp();
-        fft_regs<L, true>(t, sb, x, tw);
+        fft_regs<L, true, V>(t, sb, x, tw);
         float* lz = zl + (2 * g) * LS;
         float* lm = mul + (2 * g) * LS;
         float* lw = wl + (2 * g) * LS;
@@ -359,7 +374,7 @@ __global__ void __launch_bounds__(NT, NT <= 256 ? 2 : 1) k_csmri_svrg_small(Smal
     // One pass of the loop body is either a snapshot (mu = grad_full(z) * snap_scale, w = z; pnp_svrg.py:32-35) or an
     // inner iteration (v = g_B(z - w) / B + mu ; z <- prox(z - step * v); pnp_svrg.py:52-57, 71-76): both are the same
     // three phases with different operands, so every phase has ONE call site (and is inlined).
-    if (a.n_inner > 0) select(0);                                // the first minibatch (a snapshot pass and its barriers come before its use)
+    if (a.n_inner > 0) sel_end(0, sel_begin(0));                 // the first minibatch (a snapshot pass and its barriers come before its use)
     bool need_snap = true;
     for (int it = 0; it < a.n_inner;) {
         const bool snap = need_snap;
@@ -373,8 +388,10 @@ __global__ void __launch_bounds__(NT, NT <= 256 ? 2 : 1) k_csmri_svrg_small(Smal
         trace(511);
         cluster.sync();
         trace(512);
+        const bool sel_next = !snap && it + 1 < a.n_inner;
+        const int k0 = sel_next ? sel_begin(it + 1) : -1;
         if (!zero) phase_b(snap ? bits_fu : bits_mb + (it & 1) * (RPC * L), snap);
-        if (!snap && it + 1 < a.n_inner) select(it + 1);
+        if (sel_next) sel_end(it + 1, k0);
         trace(513);
         cluster.sync();
         trace(514);
