@@ -65,14 +65,17 @@ def small(rank, world, dev, steps=200):
               converge_check=False, mb_source='host', mb_seed=5, fast=True)
     pnp_svrg(prob, TVDenoiser(), tt=1e9, max_iters=2 * T2, **kw)
     torch.cuda.synchronize(dev)
+    # the public call pays ~20 ms of fixed cost (engine, pinned ring, upload, download): run long enough that it is
+    # amortised as in a real reconstruction (the reference runs for tt = 10 .. 100 s); 10 x the device-timed epochs
+    e2e_steps = 10 * steps
     t0 = time.time()
-    out = pnp_svrg(prob, TVDenoiser(), tt=1e9, max_iters=steps * T2, **kw)
+    out = pnp_svrg(prob, TVDenoiser(), tt=1e9, max_iters=e2e_steps * T2, **kw)
     torch.cuda.synchronize(dev)
     dt = time.time() - t0
     N = cfg['H'] * cfg['W']
     us = 1e3 * ms / (steps * T2)
     return {'workload': cfg['workload'], 'value': steps * T2 / (ms * 1e-3), 'unit': 'inner_iterations/s', 'us_per_inner_iteration': us,
-            'steps': steps, 'e2e_value': steps * T2 / dt, 'psnr_first_last': [float(psnr[0]), float(psnr[-1])],
+            'steps': steps, 'e2e_value': e2e_steps * T2 / dt, 'e2e_steps': e2e_steps, 'psnr_first_last': [float(psnr[0]), float(psnr[-1])],
             'e2e_psnr_last': float(out['psnr_per_iter'][-1]),
             'roofline_iteration_frac': ((T2 - 1) * 28.125 + 16.0) / T2 * N / (us * 1e-6) / 1e9 / bench.hbm_peak()[0],
             'note': 'one 256x256 image: the whole epoch is ONE launch of the cluster kernel (csrc/small.cuh), the image lives in the shared memory of 16 CTAs; the HBM roofline fraction is nominal (nothing but the PSNR ground truth is read in the loop)'}

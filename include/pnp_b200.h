@@ -138,6 +138,11 @@ int pnp_host_draws_create(pnp_host_draws** out, int n, int count, unsigned seed,
                           int* const* buffers, int n_buffers, int ahead);
 int pnp_host_draws_next(pnp_host_draws* h, int* slot);
 int pnp_host_draws_stage(pnp_host_draws* h, int* dst_dev, const int* extras, int n_extras, void* stream, int* slot);
+/* n_draws consecutive draws (no extras) to dst_dev[j * dst_stride + 0 .. count), j = 0 .. n_draws - 1: like n_draws calls
+ * of pnp_host_draws_stage, but draws that sit in consecutive staging buffers which are consecutive rows of ONE
+ * allocation with row length dst_stride travel as one copy with one reuse event (the T2 minibatches of an SVRG epoch:
+ * one or two copies instead of T2; at 256 x 256 the per-draw calls were 80 of the 140 us of host time per epoch). */
+int pnp_host_draws_stage_many(pnp_host_draws* h, int* dst_dev, int n_draws, long long dst_stride, void* stream);
 int pnp_host_draws_destroy(pnp_host_draws* h);
 
 /* ---- Deblur + super-resolution gradient ------------------------------------------------------

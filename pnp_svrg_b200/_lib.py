@@ -123,6 +123,7 @@ PROTOTYPES = {
                                         C.c_int]),
     'pnp_host_draws_next': (C.c_int, [C.c_void_p, C.POINTER(C.c_int)]),
     'pnp_host_draws_stage': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.POINTER(C.c_int)]),
+    'pnp_host_draws_stage_many': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_longlong, C.c_void_p]),
     'pnp_host_draws_destroy': (C.c_int, [C.c_void_p]),
     'pnp_deblur_grad': (C.c_int, [C.POINTER(DeblurGradArgs), C.c_void_p]),
     'pnp_pr_grad': (C.c_int, [C.POINTER(PrGradArgs), C.c_void_p]),

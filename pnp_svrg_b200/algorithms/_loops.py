@@ -494,8 +494,13 @@ class SvrgRun:
         if self._ev_done[s_] is not None:
             cs.wait_event(self._ev_done[s_])           # the epoch that last read this set (two epochs ago)
         if eng.mb_source == 'host':
-            for j in range(self.T2):                   # native look-ahead queue: draw -> pinned ring -> async copy
-                eng._draws.stage(self._epoch_sets[s_, j].data_ptr(), (), cs.cuda_stream)
+            # native look-ahead queue: draw -> pinned ring -> async copy
+            if os.environ.get('PNP_STAGE_MANY', '1') != '0':
+                # the T2 draws of the epoch in one call
+                eng._draws.stage_many(self._epoch_sets[s_].data_ptr(), self.T2, int(self._epoch_sets.shape[2]), cs.cuda_stream)
+            else:
+                for j in range(self.T2):
+                    eng._draws.stage(self._epoch_sets[s_, j].data_ptr(), (), cs.cuda_stream)
         else:
             if self._ev_copied[s_] is not None:
                 self._ev_copied[s_].synchronize()      # the copy that last read this pinned set

@@ -619,8 +619,11 @@ struct pnp_host_draws {
     pnp_host::DrawQueue q;
     std::vector<cudaEvent_t> ev;          // ev[slot]: recorded after the H2D copy that reads buffers[slot]
     std::vector<char> recorded;
+    std::vector<int> guard;               // guard[slot]: the event recorded after the copy that read buffers[slot] (stage_many: one per run)
     pnp_host_draws(int n, int count, unsigned seed, const int* support, int* const* buffers, int n_buffers, int ahead)
-        : q(n, count, seed, support, buffers, n_buffers, ahead), recorded(n_buffers, 0) {}
+        : q(n, count, seed, support, buffers, n_buffers, ahead), recorded(n_buffers, 0), guard(n_buffers, 0) {
+        for (int i = 0; i < n_buffers; ++i) guard[i] = i;
+    }
 };
 
 int pnp_host_draws_create(pnp_host_draws** out, int n, int count, unsigned seed, const int* support_host,
@@ -659,12 +662,59 @@ int pnp_host_draws_stage(pnp_host_draws* h, int* dst_dev, const int* extras, int
     CU_TRY(cudaMemcpyAsync(dst_dev, buf, sizeof(int) * (size_t)(h->q.count() + n_extras), cudaMemcpyHostToDevice, st));
     CU_TRY(cudaEventRecord(h->ev[slot], st));
     h->recorded[slot] = 1;
+    h->guard[slot] = slot;
     // releasing draw c lets a worker start draw c + ahead: the copy that read that draw's buffer must have finished
     const int s2 = (int)((c + h->q.ahead()) % R);
-    if (h->recorded[s2] && s2 != slot) CU_TRY(cudaEventSynchronize(h->ev[s2]));
+    if (h->recorded[s2] && s2 != slot) CU_TRY(cudaEventSynchronize(h->ev[h->guard[s2]]));
     h->q.release();
     if (slot_out) *slot_out = slot;
     return PNP_OK;
+}
+
+int pnp_host_draws_stage_many(pnp_host_draws* h, int* dst_dev, int n_draws, long long dst_stride, void* stream) {
+    if (!h || !dst_dev || n_draws < 1 || dst_stride < h->q.count()) return fail(PNP_ERR_ARG, "bad argument");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int R = h->q.n_buffers();
+    if (h->ev.empty()) {
+        h->ev.resize(R, nullptr);
+        for (int i = 0; i < R; ++i)
+            CU_TRY(cudaEventCreateWithFlags(&h->ev[i], cudaEventDisableTiming | cudaEventBlockingSync));
+    }
+    // Consecutive draws whose staging buffers are consecutive rows of one allocation with the destination's row length go
+    // out as ONE copy and one event (an epoch of T2 small minibatches: 1-2 copies instead of T2).  A run never grows past
+    // R - ahead - 1 draws: the buffer of a draw in it must not become claimable before the run's copy is enqueued.
+    const int max_run = R - h->q.ahead() - 1 > 1 ? R - h->q.ahead() - 1 : 1;
+    int run_slot = -1, run_len = 0;
+    long long done = 0;
+    auto flush = [&]() -> int {
+        if (run_len == 0) return PNP_OK;
+        const size_t bytes = run_len == 1 ? sizeof(int) * (size_t)h->q.count() : sizeof(int) * (size_t)dst_stride * (size_t)run_len;
+        CU_TRY(cudaMemcpyAsync(dst_dev + done * dst_stride, h->q.buffer(run_slot), bytes, cudaMemcpyHostToDevice, st));
+        const int last = run_slot + run_len - 1;
+        CU_TRY(cudaEventRecord(h->ev[last], st));
+        for (int s = run_slot; s <= last; ++s) { h->recorded[s] = 1; h->guard[s] = last; }
+        done += run_len;
+        run_len = 0;
+        return PNP_OK;
+    };
+    for (int j = 0; j < n_draws; ++j) {
+        const long long c = h->q.consumed();
+        const int slot = h->q.wait_next();
+        const bool joins = run_len > 0 && run_len < max_run && slot == run_slot + run_len &&
+                           h->q.buffer(slot) == h->q.buffer(run_slot) + (long long)run_len * dst_stride;
+        if (!joins) {
+            const int rc = flush();
+            if (rc != PNP_OK) return rc;
+            run_slot = slot;
+            run_len = 1;
+        } else {
+            ++run_len;
+        }
+        const int s2 = (int)((c + h->q.ahead()) % R);
+        if (h->recorded[s2] && !(s2 >= run_slot && s2 < run_slot + run_len)) CU_TRY(cudaEventSynchronize(h->ev[h->guard[s2]]));
+        h->q.release();
+    }
+    return flush();
 }
 
 int pnp_host_draws_destroy(pnp_host_draws* h) {

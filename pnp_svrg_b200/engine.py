@@ -97,6 +97,13 @@ class HostDrawRing:
         self.drawn += 1
         return self._slot.value
 
+    def stage_many(self, dst_dev_ptr, n_draws, dst_stride, stream_ptr):
+        """the next ``n_draws`` draws to ``dst[j * dst_stride + ...]`` in one native call (consecutive ring rows: one copy)"""
+        rc = self.lib.pnp_host_draws_stage_many(self._h, dst_dev_ptr, int(n_draws), int(dst_stride), stream_ptr)
+        if rc:
+            _lib.check(rc)
+        self.drawn += int(n_draws)
+
     def close(self):
         """Let the draws in flight finish (they write into the buffers) and stop the worker threads."""
         if self._h:
