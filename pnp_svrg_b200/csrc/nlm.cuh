@@ -120,4 +120,135 @@ k_nlm(const float* __restrict__ zin, float* __restrict__ zout, const float* __re
     }
 }
 
+// ---- the reference's configuration (patch 4 -> 5, any patch distance <= 13): specialised -------------------------------------
+// The generic kernel above spends ~16 instructions per (candidate, tap) pair -- two shared loads per tap for the two
+// patches, a third for the weight, loop and address arithmetic of run-time s -- at 14 warps per SM for a 256 x 256 image
+// (ncu: 102 M warp instructions, 169 us).  Here:
+//   * the pixel's OWN patch (25 values) is read once into registers, the six distinct Gaussian weights (they depend on
+//     dy^2 + dx^2 only) live in registers, the 5 x 5 loops are unrolled: 25 loads + 75 FP instructions per candidate;
+//   * FOUR threads share a pixel: the candidate rows di are dealt round-robin over blockDim.z = 4, the partial sums
+//     (sum w v, sum w) are added in a fixed order through shared memory: 4x the warps for the same image;
+//   * tile 16 x 8 pixels, shared row stride 48 floats: the two tile rows of a warp sit 16 banks apart (no conflicts).
+// Per candidate the arithmetic and its order are the generic kernel's (row by row, left to right, the same fmaf chain,
+// the same early-exit test at the start of every patch row), so distances and exit decisions are bit-identical; only
+// the order in which the 121 candidate terms are added differs (four partial sums).
+#define NLM5_TX 16
+#define NLM5_TY 8
+#define NLM5_G 4
+__device__ __forceinline__ constexpr int nlm5_cls(int pi, int pj) {       // class of dy^2 + dx^2 in {0, 1, 2, 4, 5, 8}
+    const int q = (pi - 2) * (pi - 2) + (pj - 2) * (pj - 2);
+    return q == 0 ? 0 : q == 1 ? 1 : q == 2 ? 2 : q == 4 ? 3 : q == 5 ? 4 : 5;
+}
+
+__global__ void __launch_bounds__(NLM5_TX * NLM5_TY * NLM5_G)
+k_nlm5(const float* __restrict__ zin, float* __restrict__ zout, const float* __restrict__ xrec, int H, int W,
+       long long img_stride, NlmParams np_, double* __restrict__ mse_log, const int* __restrict__ slot, int batch) {
+    constexpr int S = 5, OFF = 2;
+    extern __shared__ float tile[];                       // [TH][TWP]
+    __shared__ float wgt[S * S];
+    __shared__ float s_acc[NLM5_G][NLM5_TY][NLM5_TX], s_ws[NLM5_G][NLM5_TY][NLM5_TX];
+    __shared__ float s_err[NLM5_TX * NLM5_TY / 32];
+    const int d = np_.d, halo = d + OFF;
+    const int TWd = NLM5_TX + 2 * halo, TH = NLM5_TY + 2 * halo;
+    const int TWP = ((TWd + 31) / 32) * 32 + 16;          // == 16 (mod 32)
+    const int img = blockIdx.z;
+    const float* zi = zin + (long long)img * img_stride;
+    const int r0 = blockIdx.y * NLM5_TY, c0 = blockIdx.x * NLM5_TX;
+    const int tid = (threadIdx.z * NLM5_TY + threadIdx.y) * NLM5_TX + threadIdx.x;
+    constexpr int NTH = NLM5_TX * NLM5_TY * NLM5_G;
+
+    double se = np_.sig_log ? *slot_ptr(const_cast<double*>(np_.sig_log), slot, batch, img) / (double)W
+                            : (double)np_.sigma_est;
+    float h, var;
+    if (se > 0.0) {
+        const float sg = (float)(se * (double)np_.sigma_modifier);
+        h = sg;
+        var = 2.f * sg * sg;
+    } else {
+        h = np_.fallback_h;
+        var = 0.f;
+    }
+    for (int i = tid; i < TH * TWd; i += NTH) {
+        const int rr = i / TWd, cc = i - rr * TWd;
+        const int r = reflect_idx(r0 - halo + rr, H), c = reflect_idx(c0 - halo + cc, W);
+        tile[rr * TWP + cc] = zi[(long long)c * H + r];
+    }
+    if (tid < S * S) {
+        const float A = (float)(S - 1) * 0.25f;
+        float sum = 0.f;
+        for (int q = 0; q < S * S; ++q) {
+            const float dy = (float)(q / S - OFF), dx = (float)(q % S - OFF);
+            sum += expf(-(dy * dy + dx * dx) / (2.f * A * A));
+        }
+        const float dy = (float)(tid / S - OFF), dx = (float)(tid % S - OFF);
+        wgt[tid] = expf(-(dy * dy + dx * dx) / (2.f * A * A)) / (sum * h * h);
+    }
+    __syncthreads();
+    const int r = r0 + threadIdx.y, c = c0 + threadIdx.x;
+    const bool inside = r < H && c < W;
+    float acc = 0.f, wsum = 0.f;
+    if (inside) {
+        // the six distinct weights: entries (2,2) (2,3) (3,3) (2,4) (3,4) (4,4) of the 5 x 5 table
+        const float wc[6] = {wgt[12], wgt[13], wgt[18], wgt[14], wgt[19], wgt[24]};
+        const int pr = threadIdx.y + halo, pc = threadIdx.x + halo;
+        float p1[S][S];
+#pragma unroll
+        for (int pi = 0; pi < S; ++pi)
+#pragma unroll
+            for (int pj = 0; pj < S; ++pj) p1[pi][pj] = tile[(pr - OFF + pi) * TWP + (pc - OFF + pj)];
+        const int i_lo = -min(d, r), i_hi = min(d + 1, H - r);
+        const int j_lo = -min(d, c), j_hi = min(d + 1, W - c);
+        for (int di = i_lo + (int)threadIdx.z; di < i_hi; di += NLM5_G) {
+            const float* base = tile + (pr - OFF + di) * TWP + (pc - OFF);
+            for (int dj = j_lo; dj < j_hi; ++dj) {
+                const float* p2 = base + dj;
+                float dist = 0.f;
+                bool dead = false;
+#pragma unroll
+                for (int pi = 0; pi < S; ++pi) {
+                    if (!dead) {
+                        if (dist > 5.0f) {
+                            dead = true;
+                        } else {
+#pragma unroll
+                            for (int pj = 0; pj < S; ++pj) {
+                                const float df = p1[pi][pj] - p2[pi * TWP + pj];
+                                dist = fmaf(wc[nlm5_cls(pi, pj)], fmaf(df, df, -var), dist);
+                            }
+                        }
+                    }
+                }
+                if (!dead) {
+                    const float wv = expf(-fmaxf(0.f, dist));
+                    wsum += wv;
+                    acc = fmaf(wv, p2[OFF * TWP + OFF], acc);
+                }
+            }
+        }
+    }
+    s_acc[threadIdx.z][threadIdx.y][threadIdx.x] = acc;
+    s_ws[threadIdx.z][threadIdx.y][threadIdx.x] = wsum;
+    __syncthreads();
+    float err = 0.f;
+    if (threadIdx.z == 0 && inside) {
+        float a = 0.f, w = 0.f;
+#pragma unroll
+        for (int g = 0; g < NLM5_G; ++g) { a += s_acc[g][threadIdx.y][threadIdx.x]; w += s_ws[g][threadIdx.y][threadIdx.x]; }
+        const float o = a / w;
+        const long long e = (long long)img * img_stride + (long long)c * H + r;
+        zout[e] = o;
+        if (xrec) { const float df = o - xrec[e]; err = df * df; }
+    }
+    if (xrec && mse_log && threadIdx.z == 0) {            // warps 0 .. TX*TY/32 - 1 (whole warps: z == 0 covers tid < 128)
+        err = warp_sum_f(err);
+        if ((tid & 31) == 0) s_err[tid >> 5] = err;
+    }
+    __syncthreads();
+    if (xrec && mse_log && tid == 0) {
+        float t = 0.f;
+        for (int k = 0; k < NLM5_TX * NLM5_TY / 32; ++k) t += s_err[k];
+        atomicAdd(slot_ptr(mse_log, slot, batch, img), (double)t);
+    }
+}
+
 }  // namespace pnp

@@ -443,6 +443,7 @@ int pnp_init(void) {
         CU_TRY(cudaFuncGetAttributes(&fa, pnp::k_pr_rows));
         CU_TRY(cudaFuncGetAttributes(&fa, pnp::k_pr_cols));
         CU_TRY(cudaFuncGetAttributes(&fa, pnp::k_nlm));
+        CU_TRY(cudaFuncGetAttributes(&fa, pnp::k_nlm5));
         CU_TRY(cudaFuncGetAttributes(&fa, pnp::k_sample_indices));
         CU_TRY(cudaFuncGetAttributes(&fa, pnp::k_minmax_init));
         CU_TRY(cudaFuncGetAttributes(&fa, pnp::k_minmax));
@@ -938,6 +939,17 @@ int pnp_nlm_denoise(const float* z_in, float* z_out, int H, int W, int batch, in
     if (s < 1 || s > NLM_MAX_S || patch_distance < 0 || patch_distance + s / 2 > NLM_MAX_HALO)
         return fail(PNP_ERR_ARG, "patch_size %d / patch_distance %d not supported", patch_size, patch_distance);
     pnp::NlmParams np_{s, patch_distance, sig_log, sigma_est, sigma_modifier, fallback_h};
+    static const bool generic_only = [] { const char* e = std::getenv("PNP_NLM_GENERIC"); return e && std::atoi(e) != 0; }();
+    if (s == 5 && !generic_only) {        // the reference's patch size (denoisers/NLM.py:11: 4 -> 5): specialised kernel
+        const int halo = patch_distance + 2;
+        const int TWd = NLM5_TX + 2 * halo, TH = NLM5_TY + 2 * halo;
+        const int TWP = ((TWd + 31) / 32) * 32 + 16;
+        dim3 grid((W + NLM5_TX - 1) / NLM5_TX, (H + NLM5_TY - 1) / NLM5_TY, batch);
+        pnp::k_nlm5<<<grid, dim3(NLM5_TX, NLM5_TY, NLM5_G), sizeof(float) * (size_t)TH * TWP, static_cast<cudaStream_t>(stream)>>>(
+            z_in, z_out, xrec, H, W, (long long)H * W, np_, mse_log, slot, batch);
+        LAUNCH_CHECK();
+        return PNP_OK;
+    }
     const int TW = NLM_TILE + 2 * (patch_distance + s / 2);
     dim3 grid((W + NLM_TILE - 1) / NLM_TILE, (H + NLM_TILE - 1) / NLM_TILE, batch);
     pnp::k_nlm<<<grid, dim3(NLM_TILE, NLM_TILE), sizeof(float) * TW * TW, static_cast<cudaStream_t>(stream)>>>(
