@@ -136,6 +136,12 @@ int pnp_sample_indices_host(int* idx_out_host, int n, int count, unsigned seed, 
 typedef struct pnp_host_draws pnp_host_draws;
 int pnp_host_draws_create(pnp_host_draws** out, int n, int count, unsigned seed, const int* support_host,
                           int* const* buffers, int n_buffers, int ahead);
+/* Draws of a queue created WITHOUT a host support list are ranks in [0, n).  With a device-resident support list set
+ * here (the list of sampled k-space positions the device sampler uses; replaces the flatnonzero + choice of
+ * problems/CSMRI.py:70-71), every _stage / _stage_many copy is followed, on the same stream, by an in-place
+ * rank -> position gather on the device: the host decides WHICH measurements form the minibatch, the device resolves
+ * where they sit -- the cache-missing gather (70 % of a 100k draw on one host core) leaves the host. */
+int pnp_host_draws_set_device_support(pnp_host_draws* h, const int* support_dev);
 int pnp_host_draws_next(pnp_host_draws* h, int* slot);
 int pnp_host_draws_stage(pnp_host_draws* h, int* dst_dev, const int* extras, int n_extras, void* stream, int* slot);
 /* n_draws consecutive draws (no extras) to dst_dev[j * dst_stride + 0 .. count), j = 0 .. n_draws - 1: like n_draws calls

@@ -121,6 +121,7 @@ PROTOTYPES = {
     'pnp_sample_indices_host': (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_uint, C.c_uint, C.c_int, C.c_int, C.c_void_p]),
     'pnp_host_draws_create': (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_uint, C.c_void_p, C.c_void_p, C.c_int,
                                         C.c_int]),
+    'pnp_host_draws_set_device_support': (C.c_int, [C.c_void_p, C.c_void_p]),
     'pnp_host_draws_next': (C.c_int, [C.c_void_p, C.POINTER(C.c_int)]),
     'pnp_host_draws_stage': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.POINTER(C.c_int)]),
     'pnp_host_draws_stage_many': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_longlong, C.c_void_p]),

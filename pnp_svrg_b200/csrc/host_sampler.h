@@ -34,6 +34,7 @@ public:
     int n_buffers() const { return (int)bufs_.size(); }
     int ahead() const { return ahead_; }
     int count() const { return count_; }
+    bool has_support() const { return support_ != nullptr; }
     int* buffer(int slot) const { return bufs_[slot]; }
 
 private:

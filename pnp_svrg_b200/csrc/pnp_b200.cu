@@ -621,6 +621,7 @@ struct pnp_host_draws {
     std::vector<cudaEvent_t> ev;          // ev[slot]: recorded after the H2D copy that reads buffers[slot]
     std::vector<char> recorded;
     std::vector<int> guard;               // guard[slot]: the event recorded after the copy that read buffers[slot] (stage_many: one per run)
+    const int* support_dev = nullptr;     // set: the draws are RANKS into this device-resident list, resolved on the device after each copy
     pnp_host_draws(int n, int count, unsigned seed, const int* support, int* const* buffers, int n_buffers, int ahead)
         : q(n, count, seed, support, buffers, n_buffers, ahead), recorded(n_buffers, 0), guard(n_buffers, 0) {
         for (int i = 0; i < n_buffers; ++i) guard[i] = i;
@@ -635,6 +636,23 @@ int pnp_host_draws_create(pnp_host_draws** out, int n, int count, unsigned seed,
     for (int i = 0; i < n_buffers; ++i)
         if (!buffers[i]) return fail(PNP_ERR_ARG, "null buffer %d", i);
     *out = new pnp_host_draws(n, count, seed, support_host, buffers, n_buffers, ahead);
+    return PNP_OK;
+}
+
+int pnp_host_draws_set_device_support(pnp_host_draws* h, const int* support_dev) {
+    if (!h) return fail(PNP_ERR_ARG, "null handle");
+    if (support_dev && h->q.has_support()) return fail(PNP_ERR_ARG, "the queue already gathers through a host support list");
+    h->support_dev = support_dev;
+    return PNP_OK;
+}
+
+// ranks -> positions behind the copy that brought them (same stream, before the event that frees the staging buffer)
+static int gather_support(const pnp_host_draws* h, int* dst, int rows, long long stride, cudaStream_t st) {
+    if (!h->support_dev) return PNP_OK;
+    const int count = h->q.count();
+    dim3 grid(std::min((count + 255) / 256, 64), rows);
+    pnp::k_gather_support<<<grid, 256, 0, st>>>(dst, h->support_dev, count, stride);
+    LAUNCH_CHECK();
     return PNP_OK;
 }
 
@@ -661,6 +679,7 @@ int pnp_host_draws_stage(pnp_host_draws* h, int* dst_dev, const int* extras, int
     int* buf = h->q.buffer(slot);
     for (int i = 0; i < n_extras; ++i) buf[h->q.count() + i] = extras[i];
     CU_TRY(cudaMemcpyAsync(dst_dev, buf, sizeof(int) * (size_t)(h->q.count() + n_extras), cudaMemcpyHostToDevice, st));
+    { const int rc = gather_support(h, dst_dev, 1, 0, st); if (rc != PNP_OK) return rc; }
     CU_TRY(cudaEventRecord(h->ev[slot], st));
     h->recorded[slot] = 1;
     h->guard[slot] = slot;
@@ -691,6 +710,7 @@ int pnp_host_draws_stage_many(pnp_host_draws* h, int* dst_dev, int n_draws, long
         if (run_len == 0) return PNP_OK;
         const size_t bytes = run_len == 1 ? sizeof(int) * (size_t)h->q.count() : sizeof(int) * (size_t)dst_stride * (size_t)run_len;
         CU_TRY(cudaMemcpyAsync(dst_dev + done * dst_stride, h->q.buffer(run_slot), bytes, cudaMemcpyHostToDevice, st));
+        { const int rc = gather_support(h, dst_dev + done * dst_stride, run_len, dst_stride, st); if (rc != PNP_OK) return rc; }
         const int last = run_slot + run_len - 1;
         CU_TRY(cudaEventRecord(h->ev[last], st));
         for (int s = run_slot; s <= last; ++s) { h->recorded[s] = 1; h->guard[s] = last; }

@@ -83,6 +83,14 @@ k_saga_init(const float* __restrict__ g0, float* __restrict__ table, float* __re
     }
 }
 
+// rank -> k-space position of host-drawn minibatches, in place (mb_source='host' with the support list resident in HBM:
+// the host draws WHICH measurements, the device resolves where they sit): rows of `stride` ints, `count` ranks each
+__global__ void __launch_bounds__(256)
+k_gather_support(int* __restrict__ idx, const int* __restrict__ support, int count, long long stride) {
+    int* row = idx + (long long)blockIdx.y * stride;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) row[i] = __ldg(support + row[i]);
+}
+
 __global__ void k_advance_by(int* __restrict__ counters, int n, int delta) {
     if (threadIdx.x < n) counters[threadIdx.x] += delta;
 }

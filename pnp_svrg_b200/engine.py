@@ -59,8 +59,10 @@ class HostDrawRing:
       stage()  next + extras behind the indices + asynchronous copy to the device buffer + the event that guards the
                reuse of the staging buffer, in one native call"""
 
-    def __init__(self, lib, n, B, seed, support, buffers, ahead):
+    def __init__(self, lib, n, B, seed, support, buffers, ahead, support_dev_ptr=None):
         import ctypes as C
+        if support is not None and support_dev_ptr:
+            raise ValueError('HostDrawRing: give the support list on the host or on the device, not both')
         for b in buffers:
             if b.dtype != np.int32 or b.ndim != 1 or b.size < B or not b.flags['C_CONTIGUOUS'] or not b.flags['WRITEABLE']:
                 raise ValueError('HostDrawRing buffers must be writable contiguous int32 vectors of at least B entries')
@@ -77,6 +79,9 @@ class HostDrawRing:
         _lib.check(lib.pnp_host_draws_create(C.byref(self._h), int(n), self.B, int(seed) & 0xffffffff,
                                              None if support is None else support.ctypes.data, ptrs, len(self.buffers),
                                              int(ahead)))
+        if support_dev_ptr:
+            # the staging buffers then hold RANKS; the device maps them through its own copy of the list after each copy
+            _lib.check(lib.pnp_host_draws_set_device_support(self._h, support_dev_ptr))
 
     def next(self):
         rc = self.lib.pnp_host_draws_next(self._h, self._slot)
@@ -176,7 +181,7 @@ class Engine:
             # native look-ahead queue: one single-threaded run of the C sampler per draw, several draws in flight
             # (a 100k-index draw takes 0.3-0.6 ms on one core), each written into the pinned buffer its host->device
             # copy reads; draw_host() stages the next one with a single native call.  One pinned allocation, sliced.
-            ahead = max(2, min(8, ncpu // 2))
+            ahead = int(os.environ.get('PNP_HOST_AHEAD', '0')) or max(2, min(8, ncpu // 2))
             depth = ahead + max(2, int(os.environ.get('PNP_HOST_RING_EXTRA', '12')))     # how far the host may run ahead
             # (page-locked allocations cost milliseconds: the ring is kept on the problem object between calls; the
             # previous owner's queue has been closed by its result(), nothing writes into it any more)
@@ -185,8 +190,18 @@ class Engine:
             self.idx_host = self._host_ring[0]
             sup = getattr(problem, '_support_host', None)
             self._host_views = [t.numpy() for t in self._host_ring]
-            self._draws = HostDrawRing(self.lib, problem.M if sup is None else sup.size, self.B, self.mb_seed, sup,
-                                       self._host_views, ahead)
+            sup_dev = getattr(problem, '_support', None)
+            if sup is not None and sup_dev is not None and os.environ.get('PNP_HOST_GATHER', '0') != '1':
+                # the host draws WHICH of the M0 measurements form the minibatch (distinct ranks); the device resolves rank ->
+                # k-space position through the support list it holds anyway (the device sampler's), right behind the H2D
+                # copy: the gather through a 5 MB table was 70 % of a 100k draw on one host core (cache misses)
+                self._draws = HostDrawRing(self.lib, sup.size, self.B, self.mb_seed, None, self._host_views, ahead,
+                                           support_dev_ptr=D.ptr(sup_dev))
+                self._host_support = sup
+            else:
+                self._host_support = None
+                self._draws = HostDrawRing(self.lib, problem.M if sup is None else sup.size, self.B, self.mb_seed, sup,
+                                           self._host_views, ahead)
         self._ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
         self._pending = []          # fast mode: (kind,) markers for slots not yet read back
         self.graph = None
@@ -246,6 +261,7 @@ class Engine:
             # the copy to idx_dev is enqueued here, on the engine stream, by the same native call
             slot = self._draws.stage(D.ptr(self.idx_dev), extra, self.sptr)
             self.idx_host = self._host_ring[slot]
+            # (ranks into the support list when the device resolves them: self._host_support[...] gives the positions)
             return self._host_views[slot][:self.B]
         elif self.mb_source == 'stream':
             idx = np.asarray(self.mb_stream[self._stream_pos])

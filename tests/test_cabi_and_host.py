@@ -194,6 +194,9 @@ def test_host_draw_ring_sequence_and_buffer_reuse():
         HostDrawRing(lib, n, B, 1, None, [np.empty(B, dtype=np.int64) for _ in range(4)], 2)
     with pytest.raises(ValueError):
         HostDrawRing(lib, n, B, 1, np.zeros(n, dtype=np.int64), bufs, 2)
+    with pytest.raises(ValueError):                          # support on the host AND on the device
+        HostDrawRing(lib, 100, 10, 1, np.arange(100, dtype=np.int32), [np.empty(10, dtype=np.int32) for _ in range(4)], 2,
+                     support_dev_ptr=4096)
 
 
 def test_line_layout_conversions_are_value_exact():

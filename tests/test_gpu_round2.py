@@ -211,3 +211,38 @@ def test_wall_clock_budget_is_respected_in_deferred_fast_mode(cuda):
     o = pnp_svrg(p, TVDenoiser(), eta=0.15 * p.M0, tt=0.4, T2=10, mini_batch_size=1000, vr_mode='paper', verbose=False,
                  converge_check=False, fast=True, mb_source='device')
     assert 0.35 < time.time() - t < 1.5, time.time() - t
+
+
+@pytest.mark.gpu
+def test_host_draws_resolved_through_the_device_support(cuda):
+    """mb_source='host' with the support list on the device (pnp_host_draws_set_device_support): the host draws ranks,
+    the gather behind every staged copy turns them into the positions the host-gathering queue delivers -- one draw per
+    call (stage, with an extra entry behind the indices) and an epoch per call (stage_many, consecutive ring rows)."""
+    import torch
+    from pnp_svrg_b200 import _lib, device as D
+    from pnp_svrg_b200.engine import HostDrawRing, feistel_sample
+    lib = _lib.load()
+    dev = D.require_cuda()
+    n, B, R, T2 = 19661, 1000, 16, 5
+    sup = (np.arange(n, dtype=np.int64) * 3 + 7).astype(np.int32)
+    sup_dev = torch.from_numpy(sup).to(dev)
+    ring_t = torch.empty((R, B + 1), dtype=torch.int32).pin_memory()
+    views = [ring_t[i].numpy() for i in range(R)]
+    ring = HostDrawRing(lib, n, B, 9, None, views, 4, support_dev_ptr=D.ptr(sup_dev))
+    st = torch.cuda.current_stream(dev).cuda_stream
+    dst = torch.zeros(B + 1, dtype=torch.int32, device=dev)
+    for c in range(3):
+        slot = ring.stage(D.ptr(dst), (41 + c,), st)
+        torch.cuda.synchronize(dev)
+        got = dst.cpu().numpy()
+        assert np.array_equal(got[:B], sup[feistel_sample(n, B, 9, c)]), c
+        assert got[B] == 41 + c                                   # the extra entry is not a rank: left alone
+        assert np.array_equal(views[slot][:B], feistel_sample(n, B, 9, c))     # ranks in the staging buffer
+    many = torch.zeros((T2, B + 1), dtype=torch.int32, device=dev)
+    for e in range(4):                                            # wraps round the ring: runs of several rows and single rows
+        ring.stage_many(D.ptr(many), T2, B + 1, st)
+        torch.cuda.synchronize(dev)
+        got = many.cpu().numpy()
+        for j in range(T2):
+            assert np.array_equal(got[j, :B], sup[feistel_sample(n, B, 9, 3 + e * T2 + j)]), (e, j)
+    ring.close()
