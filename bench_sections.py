@@ -120,7 +120,7 @@ def sweep(rank, world, dev, iters=200, size=256, batch=120, with_cpu=True, pipel
     images = {i: synth_image(size, size, i) for i in range(12)}
     jobs = SW.make_jobs(list(range(12)))                     # 12 x 10 x 7 = 840
     share = -(-len(jobs) // world)                           # jobs of one rank: equal groups of at most `batch`
-    batch = -(-share // -(-share // batch))
+    batch = -(-share // max(2, -(-share // batch)))          # at least two groups per rank: the second is built while the first runs
     if pipelined:
         # double-buffered engines: batch k + 1 is built on the device while batch k runs
         batch_runner = SW.DeviceBatchPipeline(H=size, W=size, iters=iters, images=images)
@@ -155,9 +155,10 @@ def sweep(rank, world, dev, iters=200, size=256, batch=120, with_cpu=True, pipel
            'mean_psnr_gain_db': float(np.mean([r['psnr_final'] - r['psnr_init'] for r in ok])) if ok else None}
     if pipelined:
         out['construct_seconds'] = batch_runner.build_seconds
-        out['construct_note'] = ('time rank 0 spent inside batched.csmri_device_batch (masks, measurements, Xinit, support lists: torch RNG / '
-                                 'torch.fft / torch.sort -- library calls, in the CONSTRUCTOR only) during the timed sweep; every batch but '
-                                 'the first is built while the previous one runs')
+        out['construct_note'] = ('host time rank 0 spent inside batched.csmri_device_batch during the timed sweep: masks, measurements, Xinit and '
+                                 'support lists are built by the package\'s own kernels (pnp_csmri_build_batch: counter-based RNG, the iteration\'s '
+                                 'FFT passes, stream compaction; no torch.fft / torch.sort / torch RNG) without a device->host read-back; every '
+                                 'batch but the first is built while the previous one runs')
     if with_cpu and world == 1:
         out['cpu_baseline'] = sweep_cpu_baseline(iters=iters)
     return out

@@ -97,6 +97,38 @@ typedef struct {
 #define PNP_FLAG_CHAIN 1
 int pnp_csmri_grad(const pnp_csmri_grad_args* args, void* stream);
 
+/* ---- construction of a batch of CSMRI problems on the device (the step before the hot path) -------------------
+ * Replaces, for sweeps that build hundreds of problems (script_diff_sampratio_set12.py:109-140 -> problems/CSMRI.py:12-41,
+ * problems/problem.py:58-61), the NumPy constructor: mask ~ Bernoulli(p[img]), Y = mask o (fft2(X) + N(0, sigma)) with
+ * sigma = sqrt(||mask o fft2(X)||_2 / 10^(snr/10) / H / W), Xinit = minmax(|ifft2(Y)|), support = flatnonzero(mask) --
+ * with the library's own transforms and counter-based random numbers (a hash of seed, problem and k-space position; the
+ * reference's sweeps are unseeded), straight into the layouts of pnp_csmri_grad / pnp_csmri_svrg_small.  No host
+ * synchronisation: M0 and sigma stay on the device.
+ *   x        [batch][W][H] float32 ground truth, line layout (in)
+ *   p, snr   [batch] sampling probability / SNR in dB (device, in)
+ *   bits_full [batch][H/2][W]; m0 [batch]; inv_m0 [batch] (optional); support [batch][support_img_stride] ascending, entries
+ *            past m0 untouched (support_img_stride >= H*W guarantees room); Y1, Y2 [batch][H/2][W][2]; Y1n, Y2n
+ *            [batch][W][2]; xinit [batch][W][H]; sigma [batch]
+ *   work     scratch of pnp_csmri_build_batch_workspace(H, W, batch) bytes, 256-byte aligned */
+typedef struct {
+    int H, W, batch;
+    unsigned seed;
+    const float* x;
+    const float* p;
+    const float* snr;
+    unsigned char* bits_full;
+    int* m0;
+    float* inv_m0;
+    int* support;
+    long long support_img_stride;
+    float *Y1, *Y2, *Y1n, *Y2n;
+    float* xinit;
+    float* sigma;
+    void* work;
+} pnp_csmri_build_args;
+long long pnp_csmri_build_batch_workspace(int H, int W, int batch);
+int pnp_csmri_build_batch(const pnp_csmri_build_args* args, void* stream);
+
 /* Selection bits from explicit k-space indices (k = ky*W + kx, the flat index into the
  * reference's (H, W) mask / minibatch arrays).  Replaces the dense 0/1 (H, W) minibatch array of
  * CSMRI.select_mb (problems/CSMRI.py:66-74) and the mask itself (:45).

@@ -33,6 +33,17 @@ class CsmriGradArgs(C.Structure):
     ]
 
 
+class CsmriBuildArgs(C.Structure):
+    """mirror of pnp_csmri_build_args"""
+    _fields_ = [
+        ('H', C.c_int), ('W', C.c_int), ('batch', C.c_int), ('seed', C.c_uint),
+        ('x', C.c_void_p), ('p', C.c_void_p), ('snr', C.c_void_p), ('bits_full', C.c_void_p), ('m0', C.c_void_p),
+        ('inv_m0', C.c_void_p), ('support', C.c_void_p), ('support_img_stride', C.c_longlong),
+        ('Y1', C.c_void_p), ('Y2', C.c_void_p), ('Y1n', C.c_void_p), ('Y2n', C.c_void_p),
+        ('xinit', C.c_void_p), ('sigma', C.c_void_p), ('work', C.c_void_p),
+    ]
+
+
 class DeblurGradArgs(C.Structure):
     """mirror of pnp_deblur_grad_args"""
     _fields_ = [
@@ -112,6 +123,8 @@ PROTOTYPES = {
     'pnp_last_error': (C.c_char_p, []),
     'pnp_version': (C.c_int, []),
     'pnp_csmri_grad': (C.c_int, [C.POINTER(CsmriGradArgs), C.c_void_p]),
+    'pnp_csmri_build_batch_workspace': (C.c_longlong, [C.c_int, C.c_int, C.c_int]),
+    'pnp_csmri_build_batch': (C.c_int, [C.POINTER(CsmriBuildArgs), C.c_void_p]),
     'pnp_csmri_sel_from_indices': (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int,
                                              C.c_longlong, C.c_void_p, C.c_int, C.c_void_p]),
     'pnp_csmri_sel_sample': (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,

@@ -46,7 +46,72 @@ def csmri_host_spec(image, H, W, sample_prob, snr, rng=np.random):
 _IMAGE_CACHE = {}
 
 
-def csmri_device_batch(images, sample_probs, snrs, H, W, seed=0, device=None):
+_DEV_IMAGE_CACHE = {}
+
+
+def _device_lines(im, H, W, dev):
+    """normalised ground truth of one source image as a device tensor in line layout [W][H]; sweeps revisit the same few
+    images hundreds of times, so each one is normalised and uploaded once per process and device"""
+    from .problems.problem import load_image
+    key = (id(im), H, W, str(dev))
+    hit = _DEV_IMAGE_CACHE.get(key)
+    if hit is None or hit[0] is not im:
+        x = load_image(None, im, H, W).astype(np.float32)
+        hit = _DEV_IMAGE_CACHE[key] = (im, torch.from_numpy(np.ascontiguousarray(x.T)).to(dev), bool(x.min() >= 0))
+    return hit
+
+
+def csmri_device_batch_native(images, sample_probs, snrs, H, W, seed=0, device=None, sync=True):
+    """Construction of a whole batch of CSMRI problems on the device with the package's own kernels
+    (pnp_csmri_build_batch, csrc/build.cuh): same model as problems/CSMRI.py:12-41 + problems/problem.py:58-61 --
+    Bernoulli(p) mask, Y = mask o (fft2(X) + N(0, sigma)), sigma from the SNR, Xinit = minmax(|ifft2(Y)|), ascending
+    support lists -- with counter-based random numbers and the iteration's own FFT passes; no torch.fft / torch.sort /
+    torch RNG.  ``sync=False``: nothing is read back (``m0_host`` is None; M0, 1 / M0 and sigma stay device tensors), so a
+    sweep can build batch k + 1 without ever waiting for the device."""
+    import ctypes as C
+    dev = device or D.require_cuda()
+    lib = _lib.load()
+    nb, hp, N = len(images), H // 2, H * W
+    hits = [_device_lines(im, H, W, dev) for im in images]
+    xrec = torch.stack([h[1] for h in hits])                                     # [nb][W][H]
+    p = torch.from_numpy(np.asarray(sample_probs, dtype=np.float32)).to(dev, non_blocking=True)
+    snr = torch.from_numpy(np.asarray(snrs, dtype=np.float32)).to(dev, non_blocking=True)
+    f32 = lambda *shape: torch.empty(shape, dtype=torch.float32, device=dev)
+    out = dict(device=True, native=True, nb=nb, H=H, W=W, xrec=xrec, xinit=f32(nb, W, H),
+               Y1=f32(nb, hp, W, 2), Y2=f32(nb, hp, W, 2), Y1n=f32(nb, W, 2), Y2n=f32(nb, W, 2),
+               bits_full=torch.empty((nb, hp, W), dtype=torch.uint8, device=dev),
+               m0=torch.empty(nb, dtype=torch.int32, device=dev), inv_m0=f32(nb), sigma_dev=f32(nb),
+               # the lists are N wide (M0 is only known on the device); entries past M0 are never read
+               support=torch.empty((nb, N), dtype=torch.int32, device=dev),
+               data_range=np.array([1.0 if h[2] else 2.0 for h in hits]))
+    work = torch.empty(int(lib.pnp_csmri_build_batch_workspace(H, W, nb)), dtype=torch.uint8, device=dev)
+    args = _lib.CsmriBuildArgs(
+        H=H, W=W, batch=nb, seed=int(seed) & 0xffffffff, x=D.ptr(xrec), p=D.ptr(p), snr=D.ptr(snr),
+        bits_full=D.ptr(out['bits_full']), m0=D.ptr(out['m0']), inv_m0=D.ptr(out['inv_m0']), support=D.ptr(out['support']),
+        support_img_stride=N, Y1=D.ptr(out['Y1']), Y2=D.ptr(out['Y2']), Y1n=D.ptr(out['Y1n']), Y2n=D.ptr(out['Y2n']),
+        xinit=D.ptr(out['xinit']), sigma=D.ptr(out['sigma_dev']), work=D.ptr(work))
+    _lib.check(lib.pnp_csmri_build_batch(C.byref(args), D.stream()))
+    out['_keep'] = (p, snr, work)                    # alive until the stream has run the launches above
+    if sync:
+        out['m0_host'] = out['m0'].cpu().numpy().astype(np.int32)
+        out['sigma'] = out['sigma_dev'].cpu().numpy()
+    else:
+        out['m0_host'] = None
+        out['sigma'] = None
+    return out
+
+
+def csmri_device_batch(images, sample_probs, snrs, H, W, seed=0, device=None, native=None, sync=True):
+    """A batch of CSMRI problems built on the device: the package's own constructor (csmri_device_batch_native) unless
+    ``native=False`` / PNP_BUILD_TORCH=1 asks for the round-1 torch.fft one below (kept as a cross-check)."""
+    if native is None:
+        native = os.environ.get('PNP_BUILD_TORCH', '0') != '1'
+    if native:
+        return csmri_device_batch_native(images, sample_probs, snrs, H, W, seed=seed, device=device, sync=sync)
+    return csmri_device_batch_torch(images, sample_probs, snrs, H, W, seed=seed, device=device)
+
+
+def csmri_device_batch_torch(images, sample_probs, snrs, H, W, seed=0, device=None):
     """Construction of a whole batch of CSMRI problems ON THE DEVICE (the step before the hot path, SURVEY section
     8(f) rank 2): same model as problems/CSMRI.py:12-41 -- Bernoulli(p) mask, Y = mask o (fft2(X) + N(0, sigma)) with
     sigma from the SNR, Xinit = minmax(|ifft2(Y)|) -- but drawn with a torch CUDA generator and transformed with
@@ -110,7 +175,7 @@ class BatchedSVRG:
         if on_dev:
             self.nb = nb = specs['nb']
             self.H, self.W = specs['H'], specs['W']
-            m0_all = specs['m0_host']
+            m0_all = specs['m0_host']                  # None: built without a read-back (csmri_device_batch(sync=False))
         else:
             self.nb = nb = len(specs)
             self.H, self.W = specs[0]['H'], specs[0]['W']
@@ -121,7 +186,7 @@ class BatchedSVRG:
         hp = self.H // 2
         self.T2, self.B, self.seed, self.lr_decay = int(T2), int(mini_batch_size), int(seed), float(lr_decay)
         self.sigma_modifier = float(sigma_modifier)
-        if (m0_all < self.B).any():
+        if m0_all is not None and (m0_all < self.B).any():
             raise ValueError('mini_batch_size exceeds the number of measurements of a problem')
         self.stream = torch.cuda.Stream(device=self.dev)
         self.sptr = self.stream.cuda_stream
@@ -138,6 +203,9 @@ class BatchedSVRG:
             self.m0_host = m0_all
             self.sup_stride = N if on_dev else int(self.m0_host.max())      # device batches: fixed stride, the object is reusable
             if on_dev:
+                for v in specs.values():
+                    if isinstance(v, torch.Tensor) and v.is_cuda:
+                        v.record_stream(self.stream)
                 self.xrec, self.z = specs['xrec'].clone(), specs['xinit'].clone()
                 self.Y1, self.Y2, self.Y1n, self.Y2n = (specs[k].clone() for k in ('Y1', 'Y2', 'Y1n', 'Y2n'))
                 self.m0 = specs['m0'].clone()
@@ -157,9 +225,12 @@ class BatchedSVRG:
             self.S = torch.empty(nb * N, dtype=torch.float32, device=dev)
             self.bits_full = torch.zeros(nb * self.W * hp, dtype=torch.uint8, device=dev)
             self.bits_mb = torch.zeros(nb * self.W * hp, dtype=torch.uint8, device=dev)
-            self.inv_m0 = torch.from_numpy((1.0 / self.m0_host).astype(np.float32)).to(dev)
-            self.eta_host = np.broadcast_to(np.asarray(etas, dtype=np.float64), (nb,)).copy()
-            self.step = torch.from_numpy(self.eta_host.astype(np.float32)).to(dev)
+            if on_dev and specs.get('inv_m0') is not None:
+                self.inv_m0 = specs['inv_m0'].clone()
+            else:
+                self.inv_m0 = torch.from_numpy((1.0 / self.m0_host).astype(np.float32)).to(dev)
+            self.step = torch.empty(nb, dtype=torch.float32, device=dev)
+            self._set_etas(etas)
             self.mse_log = torch.zeros(max_slots * nb, dtype=torch.float64, device=dev)
             self.sig_log = torch.zeros(max_slots * nb, dtype=torch.float64, device=dev)
             self.counters = torch.zeros(4, dtype=torch.int32, device=dev)
@@ -197,15 +268,35 @@ class BatchedSVRG:
         if rc:
             _lib.check(rc)
 
+    def _set_etas(self, etas):
+        """step sizes per problem: host numbers, or a device tensor (sweeps derive them from M0 without a read-back)"""
+        if isinstance(etas, torch.Tensor):
+            self.eta_host, self.eta_dev = None, etas.to(torch.float32).reshape(self.nb)
+            self.step.copy_(self.eta_dev)
+        else:
+            self.eta_host = np.broadcast_to(np.asarray(etas, dtype=np.float64), (self.nb,)).copy()
+            self.eta_dev = None
+            self.step.copy_(torch.from_numpy(self.eta_host.astype(np.float32)), non_blocking=False)
+
+    def _decayed_step(self):
+        if self.eta_host is None:
+            self.step.copy_(self.eta_dev * float(self.lr_decay ** self.outer))
+        else:
+            self.step.copy_(torch.from_numpy((self.eta_host * self.lr_decay ** self.outer).astype(np.float32)), non_blocking=True)
+
     def reload(self, batch, etas):
         """Load another device-built batch of the same shape into the existing buffers: allocations and the
         captured iteration graph are reused (sweeps run hundreds of batches)."""
         if not (isinstance(batch, dict) and batch.get('device')) or batch['nb'] != self.nb or (batch['H'], batch['W']) != (self.H, self.W):
             raise ValueError('reload needs a csmri_device_batch of the same shape')
-        if (batch['m0_host'] < self.B).any():
+        if batch['m0_host'] is not None and (batch['m0_host'] < self.B).any():
             raise ValueError('mini_batch_size exceeds the number of measurements of a problem')
-        torch.cuda.current_stream(self.dev).synchronize()
+        # the batch was built on the current stream: this engine's stream waits for it on the device, the host does not
+        self.stream.wait_stream(torch.cuda.current_stream(self.dev))
         with torch.cuda.stream(self.stream):
+            for v in batch.values():                       # read on this engine's stream: not to be recycled before that
+                if isinstance(v, torch.Tensor) and v.is_cuda:
+                    v.record_stream(self.stream)
             self.xrec.copy_(batch['xrec']); self.z.copy_(batch['xinit'])
             for k in ('Y1', 'Y2', 'Y1n', 'Y2n'):
                 getattr(self, k).copy_(batch[k])
@@ -213,13 +304,55 @@ class BatchedSVRG:
             self.m0_host = batch['m0_host']
             self.support[:, :batch['support'].shape[1]] = batch['support']
             self.bits_full.copy_(batch['bits_full'].reshape(-1))
-            self.inv_m0.copy_(torch.from_numpy((1.0 / self.m0_host).astype(np.float32)), non_blocking=False)
-            self.eta_host = np.broadcast_to(np.asarray(etas, dtype=np.float64), (self.nb,)).copy()
-            self.step.copy_(torch.from_numpy(self.eta_host.astype(np.float32)), non_blocking=False)
+            if batch.get('inv_m0') is not None:
+                self.inv_m0.copy_(batch['inv_m0'])
+            else:
+                self.inv_m0.copy_(torch.from_numpy((1.0 / self.m0_host).astype(np.float32)), non_blocking=False)
+            self._set_etas(etas)
             self.mse_log.zero_(); self.sig_log.zero_(); self.mse0.zero_()
             self.counters[0:2].zero_()                      # log slot and cursor; the draw counter keeps running
             self.check(self.lib.pnp_sq_err(D.ptr(self.z), D.ptr(self.xrec), self.N, self.nb, D.ptr(self.mse0), None, self.sptr))
         self.data_range = np.asarray(batch['data_range'], dtype=np.float64)
+        self.slots_used = 0
+        self.outer = 0
+
+    def build_from_images(self, images, sample_probs, snrs, seed, eta_scale, eta_cap):
+        """The next batch of a sweep built STRAIGHT INTO this engine's buffers by the package's own constructor
+        (pnp_csmri_build_batch) on this engine's stream: no allocation, no copy, no read-back -- the host only enqueues, and
+        the build overlaps whatever other engines are running.  Step sizes min(eta_scale * M0, eta_cap) are formed on the
+        device from the M0 the constructor counted.  The engine must hold device-built problems (support lists N wide)."""
+        import ctypes as C
+        if len(images) != self.nb or self.sup_stride != self.N:
+            raise ValueError('build_from_images needs %d images and an engine created from a device-built batch' % self.nb)
+        hits = [_device_lines(im, self.H, self.W, self.dev) for im in images]
+        if getattr(self, '_build_work', None) is None:
+            self._build_work = torch.empty(int(self.lib.pnp_csmri_build_batch_workspace(self.H, self.W, self.nb)), dtype=torch.uint8,
+                                           device=self.dev)
+            self._build_ps = torch.empty((2, self.nb), dtype=torch.float32, device=self.dev)
+            self._build_ps_host = torch.empty((2, self.nb), dtype=torch.float32).pin_memory()
+            self._build_ps_ev = None
+            self.sigma_dev = torch.empty(self.nb, dtype=torch.float32, device=self.dev)
+        if self._build_ps_ev is not None:
+            self._build_ps_ev.synchronize()                 # the copy that last read the pinned parameters (long done)
+        self._build_ps_host[0] = torch.from_numpy(np.asarray(sample_probs, dtype=np.float32))
+        self._build_ps_host[1] = torch.from_numpy(np.asarray(snrs, dtype=np.float32))
+        with torch.cuda.stream(self.stream):
+            self._build_ps.copy_(self._build_ps_host, non_blocking=True)
+            self._build_ps_ev = self._build_ps_ev or torch.cuda.Event()
+            self._build_ps_ev.record(self.stream)
+            torch.stack([h[1] for h in hits], out=self.xrec.view(self.nb, self.W, self.H))
+            args = _lib.CsmriBuildArgs(
+                H=self.H, W=self.W, batch=self.nb, seed=int(seed) & 0xffffffff, x=D.ptr(self.xrec), p=D.ptr(self._build_ps[0]),
+                snr=D.ptr(self._build_ps[1]), bits_full=D.ptr(self.bits_full), m0=D.ptr(self.m0), inv_m0=D.ptr(self.inv_m0),
+                support=D.ptr(self.support), support_img_stride=self.N, Y1=D.ptr(self.Y1), Y2=D.ptr(self.Y2), Y1n=D.ptr(self.Y1n),
+                Y2n=D.ptr(self.Y2n), xinit=D.ptr(self.z), sigma=D.ptr(self.sigma_dev), work=D.ptr(self._build_work))
+            self.check(self.lib.pnp_csmri_build_batch(C.byref(args), self.sptr))
+            self.m0_host = None
+            self._set_etas(torch.clamp(self.m0.to(torch.float32) * float(eta_scale), max=float(eta_cap)))
+            self.mse_log.zero_(); self.sig_log.zero_(); self.mse0.zero_()
+            self.counters[0:2].zero_()
+            self.check(self.lib.pnp_sq_err(D.ptr(self.z), D.ptr(self.xrec), self.N, self.nb, D.ptr(self.mse0), None, self.sptr))
+        self.data_range = np.array([1.0 if h[2] else 2.0 for h in hits])
         self.slots_used = 0
         self.outer = 0
 
@@ -322,8 +455,7 @@ class BatchedSVRG:
             done = 0
             while done < n_inner:
                 if self.lr_decay != 1.0:
-                    self.step.copy_(torch.from_numpy((self.eta_host * self.lr_decay ** self.outer).astype(np.float32)),
-                                    non_blocking=True)
+                    self._decayed_step()
                 self._snapshot()
                 k = min(self.T2, n_inner - done)
                 for _ in range(k):
@@ -337,7 +469,7 @@ class BatchedSVRG:
         gradient in shared memory (pnp_csmri_svrg_small)"""
         with torch.cuda.stream(self.stream):
             if self.lr_decay != 1.0:
-                self.step.copy_(torch.from_numpy((self.eta_host * self.lr_decay ** self.outer).astype(np.float32)), non_blocking=True)
+                self._decayed_step()
             args = _lib.SvrgSmallArgs(
                 H=self.H, W=self.W, batch=self.nb, z=D.ptr(self.z), xrec=D.ptr(self.xrec),
                 Y1=D.ptr(self.Y1), Y2=D.ptr(self.Y2), Y1n=D.ptr(self.Y1n), Y2n=D.ptr(self.Y2n), bits_full=D.ptr(self.bits_full),
@@ -364,7 +496,7 @@ class BatchedSVRG:
              if with_z else np.zeros((self.nb, 0)))
         with np.errstate(divide='ignore'):
             psnr0 = np.around(10.0 * np.log10(self.data_range ** 2 / (self.mse0.cpu().numpy() / self.N)), 2)
-        return dict(z=z.reshape(self.nb, -1), psnr=psnr, psnr_init=psnr0, sigma_est=sig)
+        return dict(z=z.reshape(self.nb, -1), psnr=psnr, psnr_init=psnr0, sigma_est=sig, m0=self.m0.cpu().numpy())
 
     def close(self):
         if self.graph:

@@ -24,6 +24,7 @@
 #include "tv_chambolle.cuh"
 #include "cdp.cuh"
 #include "small.cuh"
+#include "build.cuh"
 
 namespace {
 
@@ -408,6 +409,42 @@ int dispatch_prox_fused(int n, const float* zin, float* zout, const float* xrec,
 }
 }  // namespace
 
+// ---- device-side construction of CSMRI problem batches (csrc/build.cuh) ----------------------------------------------
+namespace {
+struct BuildWork {                 // carve-up of the caller's scratch (all offsets 256-byte aligned)
+    size_t S, im, Y1r, Y2r, Y1nr, Y2nr, chunks, norm2, minmax, total;
+    BuildWork(int H, int W, int batch) {
+        const size_t N = (size_t)H * W, nb = (size_t)batch;
+        auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
+        size_t o = 0;
+        S = o;      o = al(o + nb * N * 4);                     // packed half spectrum (complex64 [H/2][W])
+        im = o;     o = al(o + nb * N * 4);
+        Y1r = o;    o = al(o + nb * N * 4);
+        Y2r = o;    o = al(o + nb * N * 4);
+        Y1nr = o;   o = al(o + nb * (size_t)W * 8);
+        Y2nr = o;   o = al(o + nb * (size_t)W * 8);
+        chunks = o; o = al(o + nb * ((N + BUILD_CHUNK - 1) / BUILD_CHUNK) * 4);
+        norm2 = o;  o = al(o + nb * 8);
+        minmax = o; o = al(o + nb * 8);
+        total = o;
+    }
+};
+
+template <int L>
+int launch_cols_build(const float2* S, const unsigned char* bits, float2* Y1, float2* Y1n, int hp, int batch, double* norm2,
+                      cudaStream_t st) {
+    constexpr int NC = cols_nc<L>();
+    dim3 grid((hp + NC - 1) / NC, batch);
+    pnp::k_cols_build<L, NC><<<grid, NC * pnp::fft_threads<L>(), conv_smem<L>(), st>>>(S, bits, Y1, Y1n, hp, norm2);
+    LAUNCH_CHECK();
+    return PNP_OK;
+}
+int dispatch_cols_build(int n, const float2* S, const unsigned char* bits, float2* Y1, float2* Y1n, int hp, int batch,
+                        double* norm2, cudaStream_t st) {
+    DISPATCH_POW2(n, launch_cols_build, S, bits, Y1, Y1n, hp, batch, norm2, st)
+}
+}  // namespace
+
 extern "C" {
 
 int pnp_version(void) { return 100; }
@@ -482,6 +519,79 @@ int pnp_csmri_grad(const pnp_csmri_grad_args* args, void* stream) {
     if ((ph & 1) && (rc = dispatch_r2c(a.H, a, st)) != PNP_OK) return rc;
     if ((ph & 2) && (rc = dispatch_cols(a.W, a, st)) != PNP_OK) return rc;
     if (ph & 4) return dispatch_c2r(a.H, a, st);
+    return PNP_OK;
+}
+
+long long pnp_csmri_build_batch_workspace(int H, int W, int batch) {
+    if (!pow2_ok(H) || !pow2_ok(W) || batch < 1) return -1;
+    return (long long)BuildWork(H, W, batch).total;
+}
+
+int pnp_csmri_build_batch(const pnp_csmri_build_args* args, void* stream) {
+    if (!args) return fail(PNP_ERR_ARG, "null args");
+    const pnp_csmri_build_args& a = *args;
+    if (!pow2_ok(a.H) || !pow2_ok(a.W)) return fail(PNP_ERR_ARG, "H=%d W=%d must be powers of two in [32, 4096]", a.H, a.W);
+    if (a.batch < 1 || a.batch > 65535) return fail(PNP_ERR_ARG, "batch=%d out of range", a.batch);
+    if (!a.x || !a.p || !a.snr || !a.bits_full || !a.m0 || !a.support || !a.Y1 || !a.Y2 || !a.Y1n || !a.Y2n || !a.xinit ||
+        !a.sigma || !a.work)
+        return fail(PNP_ERR_ARG, "null pointer");
+    const long long N = (long long)a.H * a.W;
+    // a list shorter than the plane only fits when M0 <= stride, and M0 is only known on the device
+    if (a.support_img_stride < N) return fail(PNP_ERR_ARG, "support_img_stride must be >= H*W");
+    if ((reinterpret_cast<unsigned long long>(a.work) & 255ull) != 0) return fail(PNP_ERR_ARG, "work must be 256-byte aligned");
+    int rc = check_init();
+    if (rc != PNP_OK) return rc;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const BuildWork w(a.H, a.W, a.batch);
+    char* wk = static_cast<char*>(a.work);
+    float* S = reinterpret_cast<float*>(wk + w.S);
+    float* im = reinterpret_cast<float*>(wk + w.im);
+    float2 *Y1r = reinterpret_cast<float2*>(wk + w.Y1r), *Y2r = reinterpret_cast<float2*>(wk + w.Y2r);
+    float2 *Y1nr = reinterpret_cast<float2*>(wk + w.Y1nr), *Y2nr = reinterpret_cast<float2*>(wk + w.Y2nr);
+    int* chunks = reinterpret_cast<int*>(wk + w.chunks);
+    double* norm2 = reinterpret_cast<double*>(wk + w.norm2);
+    unsigned* minmax = reinterpret_cast<unsigned*>(wk + w.minmax);
+    const int hp = a.H / 2, nchunks = (int)((N + BUILD_CHUNK - 1) / BUILD_CHUNK);
+    const int eb = (int)std::min<long long>((hp * (long long)a.W + 255) / 256, 1184);
+
+    pnp::k_build_init<<<(a.batch + 255) / 256, 256, 0, st>>>(norm2, minmax, a.batch);
+    LAUNCH_CHECK();
+    pnp::k_build_bits<<<dim3(eb, a.batch), 256, 0, st>>>(a.bits_full, a.H, a.W, a.seed, a.p);
+    LAUNCH_CHECK();
+    // support lists (np.flatnonzero order) + M0
+    pnp::k_support_count<<<dim3(nchunks, a.batch), 256, 0, st>>>(chunks, (int)N, a.seed, a.p);
+    LAUNCH_CHECK();
+    pnp::k_support_scan<<<a.batch, 1024, 0, st>>>(chunks, nchunks, a.m0, a.inv_m0);
+    LAUNCH_CHECK();
+    pnp::k_support_write<<<dim3(nchunks, a.batch), 256, 0, st>>>(a.support, a.support_img_stride, chunks, (int)N, a.seed, a.p);
+    LAUNCH_CHECK();
+    // F = fft2(X): the iteration's forward line pass, then the transform across the lines of every packed row
+    pnp_csmri_grad_args g{};
+    g.H = a.H; g.W = a.W; g.batch = a.batch; g.a = a.x; g.S = S; g.bits = a.bits_full; g.gscale = 1.f;
+    if ((rc = dispatch_r2c(a.H, g, st)) != PNP_OK) return rc;
+    if ((rc = dispatch_cols_build(a.W, reinterpret_cast<const float2*>(S), a.bits_full, reinterpret_cast<float2*>(a.Y1),
+                                  reinterpret_cast<float2*>(a.Y1n), hp, a.batch, norm2, st)) != PNP_OK) return rc;
+    pnp::k_build_noise<<<dim3(eb, a.batch), 256, 0, st>>>(
+        reinterpret_cast<float2*>(a.Y1), reinterpret_cast<float2*>(a.Y2), reinterpret_cast<float2*>(a.Y1n),
+        reinterpret_cast<float2*>(a.Y2n), Y1r, Y2r, Y1nr, Y2nr, a.bits_full, a.H, a.W, a.seed, a.snr, norm2, a.sigma);
+    LAUNCH_CHECK();
+    // Re ifft2(Y) and Im ifft2(Y) = Re ifft2(-iY): the iteration's column + inverse line passes on a ZERO spectrum with the
+    // measurement term (they return -Re ifft2 of the Hermitian part of the measurements; the sign drops out of |.|)
+    for (int part = 0; part < 2; ++part) {
+        CU_TRY(cudaMemsetAsync(S, 0, (size_t)a.batch * N * 4, st));
+        g.Y1 = part ? reinterpret_cast<const float*>(Y1r) : a.Y1;
+        g.Y2 = part ? reinterpret_cast<const float*>(Y2r) : a.Y2;
+        g.Y1n = part ? reinterpret_cast<const float*>(Y1nr) : a.Y1n;
+        g.Y2n = part ? reinterpret_cast<const float*>(Y2nr) : a.Y2n;
+        g.g_out = part ? im : a.xinit;
+        if ((rc = dispatch_cols(a.W, g, st)) != PNP_OK) return rc;
+        if ((rc = dispatch_c2r(a.H, g, st)) != PNP_OK) return rc;
+    }
+    const int xb = (int)std::min<long long>((N + 255) / 256, 1184);
+    pnp::k_build_abs<<<dim3(xb, a.batch), 256, 0, st>>>(a.xinit, im, N, minmax);
+    LAUNCH_CHECK();
+    pnp::k_build_norm<<<dim3(xb, a.batch), 256, 0, st>>>(a.xinit, N, minmax);
+    LAUNCH_CHECK();
     return PNP_OK;
 }
 

@@ -94,3 +94,99 @@ def test_device_constructed_batch_is_consistent_and_reconstructs(cuda):
     # (the fully sampled problem starts from an almost exact Xinit; the prox can only lose there)
     assert np.all(out['psnr'][-1][:4] > out['psnr_init'][:4] + 0.5), (out['psnr_init'], out['psnr'][-1])
     assert np.all(np.isfinite(out['psnr'][-1]))
+
+
+@pytest.mark.parametrize('H', [64, 256])
+def test_native_batch_constructor_against_numpy(cuda, H):
+    """pnp_csmri_build_batch (the package's own device constructor: counter-based RNG, own FFT passes, compaction) against a
+    float64 NumPy recomputation of problems/CSMRI.py:12-41 from the mask and the noise it drew: the measurements are
+    mask o (fft2(X) + real noise) with the noise level of problems/problem.py:58-61, the mirrored planes, the packed
+    selection bytes, M0 / 1 / M0 / the support lists and Xinit = minmax(|ifft2(Y)|) all agree; the torch.fft constructor
+    of round 1 (native=False) stays available and gives the same statistics."""
+    import torch
+    from pnp_svrg_b200.batched import csmri_device_batch
+    imgs = [synth_image(H, H, k) for k in range(3)]
+    alphas, snrs = [0.3, 0.6, 1.0], [10., 20., 30.]
+    b = csmri_device_batch(imgs, alphas, snrs, H, H, seed=5, native=True)
+    assert b.get('native') is True
+    N, hp = H * H, H // 2
+    m0 = b['m0_host']
+    Y1 = torch.view_as_complex(b['Y1']).cpu().numpy().astype(np.complex128)
+    Y2 = torch.view_as_complex(b['Y2']).cpu().numpy().astype(np.complex128)
+    Y1n = torch.view_as_complex(b['Y1n']).cpu().numpy().astype(np.complex128)
+    Y2n = torch.view_as_complex(b['Y2n']).cpu().numpy().astype(np.complex128)
+    bits = b['bits_full'].cpu().numpy()
+    sup = b['support'].cpu().numpy()
+    inv_m0 = b['inv_m0'].cpu().numpy()
+    xinit = b['xinit'].cpu().numpy()
+    kk = (-np.arange(H)) % H
+    for i in range(3):
+        x = b['xrec'][i].cpu().numpy().T.astype(np.float64)
+        assert np.allclose(x, (imgs[i] - imgs[i].min()) / (imgs[i].max() - imgs[i].min()), atol=1e-6)
+        s = sup[i, :m0[i]]
+        assert np.all(np.diff(s) > 0)
+        mask = np.zeros(N, bool)
+        mask[s] = True
+        mask = mask.reshape(H, H)
+        assert abs(m0[i] - alphas[i] * N) < 5 * np.sqrt(N * alphas[i] * (1 - alphas[i])) + 1
+        assert abs(inv_m0[i] * m0[i] - 1) < 1e-6
+        # packed selection bytes of the full mask (csrc/csmri.cuh::set_sel_bits layout)
+        mir = mask[kk][:, kk]
+        want_bits = mask[:hp].astype(np.uint8) + 2 * mir[:hp].astype(np.uint8)
+        want_bits[0] += 4 * mask[hp].astype(np.uint8) + 8 * mir[hp].astype(np.uint8)
+        assert np.array_equal(bits[i], want_bits)
+        # the full measurement plane from the two packed halves: rows < hp and hp from Y1 / Y1n, rows > hp from conj(Y2)
+        Y = np.zeros((H, H), np.complex128)
+        Y[:hp] = Y1[i]
+        Y[hp] = Y1n[i]
+        Ymir = np.conj(Y2[i])                                      # = Ym[-ky][-kx] for ky < hp
+        for ky in range(1, hp):
+            Y[H - ky] = Ymir[ky][kk]
+        assert np.allclose(np.conj(Y2[i][0]), Y[0][kk]) and np.allclose(np.conj(Y2n[i]), Y[hp][kk])
+        assert np.array_equal(np.abs(Y) > 0, mask)
+        F = np.fft.fft2(x)
+        noise = (Y - F)[mask]
+        sigma = np.sqrt(np.linalg.norm((mask * F).ravel()) / 10 ** (snrs[i] / 10) / H / H)
+        assert abs(b['sigma'][i] / sigma - 1) < 1e-4, (b['sigma'][i], sigma)
+        scale = np.abs(F).max()
+        assert np.abs(noise.imag).max() < 2e-6 * scale             # the noise is real (CSMRI.py:32-33); fp32 transform error
+        assert abs(noise.real.std() / sigma - 1) < 0.05 and abs(noise.real.mean()) < 0.05 * sigma
+        x0 = np.abs(np.fft.ifft2(Y))
+        want = (x0 - x0.min()) / (x0.max() - x0.min())
+        assert rel_l2(xinit[i].T, want) < 2e-5, rel_l2(xinit[i].T, want)
+    # no read-back variant: same device results, nothing on the host
+    b2 = csmri_device_batch(imgs, alphas, snrs, H, H, seed=5, native=True, sync=False)
+    assert b2['m0_host'] is None and torch.equal(b2['m0'], b['m0']) and torch.equal(b2['Y1'], b['Y1'])
+    assert torch.equal(b2['xinit'], b['xinit']) and torch.equal(b2['support'][0, :m0[0]], b['support'][0, :m0[0]])
+    # another seed draws another mask
+    b3 = csmri_device_batch(imgs, alphas, snrs, H, H, seed=6, native=True)
+    assert not torch.equal(b3['bits_full'][0], b['bits_full'][0])
+    # (fully sampled problem: the noise level does not depend on the mask draw, e.g. on whether it holds the DC coefficient)
+    t = csmri_device_batch(imgs, alphas, snrs, H, H, seed=5, native=False)
+    assert abs(t['sigma'][2] / b['sigma'][2] - 1) < 1e-4
+
+
+def test_pipeline_builds_groups_inside_the_engines(cuda):
+    """sweep.DeviceBatchPipeline: after the two engines exist, every further group is built straight into the idle engine's
+    buffers (BatchedSVRG.build_from_images, no read-back) while the other engine runs.  Every job comes back once, with the
+    PSNR gains of a working reconstruction, short tail groups are padded, and a group rebuilt with the same seed reproduces
+    its problems exactly (the constructor is counter based)."""
+    from pnp_svrg_b200 import sweep as SW
+    H = 64
+    images = {i: synth_image(H, H, i) for i in range(3)}
+    jobs = [dict(id=n, image=n % 3, alpha=[0.3, 0.5, 0.8][n % 3], snr=[15., 25.][n % 2], algo='pnp_svrg', denoiser='TV') for n in range(22)]
+    pipe = SW.DeviceBatchPipeline(H=H, W=H, iters=40, T2=5, mini_batch_size=200, images=images, seed=3)
+    recs = SW.run_partitioned_batched(jobs, pipe, 0, 1, batch=4, gather=False)          # 6 groups: 4, 4, 4, 4, 4, 2 (padded)
+    assert [r['id'] for r in recs] == list(range(22))
+    gain = np.array([r['psnr_final'] - r['psnr_init'] for r in recs])
+    assert np.all(np.isfinite(gain)) and np.mean(gain > 0.3) > 0.8, gain
+    # groups 2.. were built inside the engines; group 4 again (ids 16..19, same seed) -> identical records
+    again = SW.run_partitioned_batched(jobs[16:20], pipe, 0, 1, batch=4, gather=False)
+    for a, b in zip(again, recs[16:20]):                 # (the sampler's draw counter keeps running: other minibatches)
+        assert (a['id'], a['psnr_init']) == (b['id'], b['psnr_init']) and abs(a['psnr_final'] - b['psnr_final']) < 0.5
+    pipe.close()
+    # a minibatch larger than a problem's measurement count is reported when the records come back
+    pipe = SW.DeviceBatchPipeline(H=H, W=H, iters=10, T2=5, mini_batch_size=3000, images=images, seed=3)
+    with pytest.raises(ValueError):
+        SW.run_partitioned_batched(jobs[:8], pipe, 0, 1, batch=4, gather=False)
+    pipe.close()
