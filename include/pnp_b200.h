@@ -430,7 +430,11 @@ int pnp_nlm_denoise(const float* z_in, float* z_out, int H, int W, int batch, in
  * mode 1 = MMO (clamp, net + input, clamp).  act0/act1: scratch, PH*PW*64 floats each; stats: 2 ints.
  * precision 0 = fp32 CUDA cores (exact-parity path); 1 = bf16 operands / fp32 accumulation on the tcgen05
  * tensor cores for the 64->64 layers: act0/act1 are then bf16 buffers of PH*(PW+1)*64 elements that the
- * caller ZEROES ONCE (one zero pad pixel per line is never written), and net->w_tc must be set. */
+ * caller ZEROES ONCE (one zero pad pixel per line is never written), and net->w_tc must be set;
+ * 2 = error-compensated tensor-core mode ("bf16x3"): activations and weights as hi + lo bf16 pairs, three products per
+ * tile into the fp32 accumulator -- fp32-path results to ~1e-5 (the reference runs these nets in fp32,
+ * denoisers/RealSN_DnCNN.py:32-35): act0/act1 hold TWO such planes each (2*PH*(PW+1)*64 elements, zeroed once), and
+ * net->w_tc_lo must be set as well. */
 #define PNP_CNN_MAX_LAYERS 32
 typedef struct {
     int n_layers;
@@ -444,6 +448,7 @@ typedef struct {
     const void* w_tc[PNP_CNN_MAX_LAYERS];   /* tensor-core path only (null otherwise), bf16, K = (dl, ci) contiguous:
                                                middle layers [192 rows (dp, co)][192] with scale[l] folded in,
                                                last layer [16 rows (dp, then zeros)][192] */
+    const void* w_tc_lo[PNP_CNN_MAX_LAYERS]; /* precision 2 only: bf16(w - float(w_tc)), same layouts */
 } pnp_cnn_net;
 int pnp_cnn_forward(const pnp_cnn_net* net, const float* img, float* out, int PH, int PW, float* act0, float* act1,
                     int* stats, const float* xrec, double* mse_log, const int* slot, int precision, void* stream);

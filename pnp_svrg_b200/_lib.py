@@ -113,7 +113,7 @@ class CnnNet(C.Structure):
         ('w', C.c_void_p * CNN_MAX_LAYERS), ('scale', C.c_void_p * CNN_MAX_LAYERS), ('shift', C.c_void_p * CNN_MAX_LAYERS),
         ('slope', C.c_float * CNN_MAX_LAYERS),
         ('last_bias', C.c_float), ('mode', C.c_int), ('range', C.c_float), ('shift_in', C.c_float),
-        ('w_tc', C.c_void_p * CNN_MAX_LAYERS),
+        ('w_tc', C.c_void_p * CNN_MAX_LAYERS), ('w_tc_lo', C.c_void_p * CNN_MAX_LAYERS),
     ]
 
 

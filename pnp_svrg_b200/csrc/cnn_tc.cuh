@@ -68,8 +68,12 @@ struct TcSmem {
     __align__(16) float shift[64];   // per output channel shift (bias / folded BatchNorm; the scale is folded into the weights)
 };
 
-template <int CO> constexpr size_t tc_smem() {
-    return ((3 * TcCfg<CO>::B_BYTES + 1023) & ~(size_t)1023) + TC_STAGES * TC_A_BYTES + (CO == 64 ? TC_O_BYTES : 0) + sizeof(TcSmem) + 1024;
+// SPLIT (error-compensated mode, see k_conv_tc): hi AND lo halves of the weights stay resident (6 K blocks), and the
+// activation ring shrinks to three stages so that a 64 -> 64 layer still fits the 227 KiB of an SM
+#define TC_SPLIT_STAGES 3
+template <int CO, bool SPLIT = false> constexpr size_t tc_smem() {
+    return (((SPLIT ? 6 : 3) * TcCfg<CO>::B_BYTES + 1023) & ~(size_t)1023) + (SPLIT ? TC_SPLIT_STAGES : TC_STAGES) * TC_A_BYTES +
+           (CO == 64 ? TC_O_BYTES : 0) + sizeof(TcSmem) + 1024;
 }
 
 __device__ __forceinline__ void mbar_wait_bounded(unsigned long long* bar, unsigned parity) {
@@ -155,9 +159,12 @@ struct TcLast {
 // channel half hf): two chunks of 16 channels -- TMEM -> registers, output shift by warp shuffles, + shift, activation,
 // bf16 pack, swizzled staging and one TMA tensor store per chunk.  The accumulator is handed back (tempty) as soon as
 // the second chunk has been read.  Shared by k_conv_tc<64> and k_conv_tc_stack.
+// SPLIT: the fp32 result leaves as TWO bf16 planes, hi = bf16(v) through tmO and lo = bf16(v - hi) through tmOl (the
+// error-compensated mode of k_conv_tc); the two staging buffers of the warp are then used alternately by the four stores.
+template <bool SPLIT = false>
 __device__ __forceinline__ void tc_epilogue_tile64(unsigned t0, TcSmem* ctl, unsigned char* sO, const CUtensorMap* tmO, int ew,
                                                    int wg, int hf, int lane, int s, bool pad, bool interior, bool relu,
-                                                   float slope, int dbg) {
+                                                   float slope, int dbg, const CUtensorMap* tmOl = nullptr) {
 #pragma unroll
     for (int j = 0; j < 2; ++j) {                                         // two chunks of 16 channels
         const int c = 32 * hf + 16 * j;
@@ -175,8 +182,9 @@ __device__ __forceinline__ void tc_epilogue_tile64(unsigned t0, TcSmem* ctl, uns
         if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // staging buffer j is free again
         __syncwarp();
         if (dbg & 2) continue;
-        uint4 pk[2];
+        uint4 pk[2], pl[2];
         __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(pk);
+        __nv_bfloat162* hl = reinterpret_cast<__nv_bfloat162*>(pl);
 #pragma unroll
         for (int i = 0; i < 16; i += 2) {
             float o2[2];
@@ -188,8 +196,38 @@ __device__ __forceinline__ void tc_epilogue_tile64(unsigned t0, TcSmem* ctl, uns
                 o2[u] = relu ? fmaxf(v, 0.f) : fmaxf(v, v * slope);              // leaky ReLU needs slope <= 1
             }
             h[i >> 1] = __floats2bfloat162_rn(o2[0], o2[1]);
+            if (SPLIT) {
+                const float2 hf2 = __bfloat1622float2(h[i >> 1]);
+                hl[i >> 1] = __floats2bfloat162_rn(o2[0] - hf2.x, o2[1] - hf2.y);
+            }
         }
-        if (pad) pk[0] = pk[1] = make_uint4(0u, 0u, 0u, 0u);
+        if (pad) pk[0] = pk[1] = pl[0] = pl[1] = make_uint4(0u, 0u, 0u, 0u);
+        if (SPLIT) {
+            // hi through staging buffer 0, lo through buffer 1, both chunks: a buffer is rewritten once at most one store
+            // (the other buffer's) may still be reading
+#pragma unroll
+            for (int part = 0; part < 2; ++part) {
+                unsigned char* stage_o = sO + (ew * 2 + part) * TC_O_WARP_BYTES;
+                if (part == 1) {
+                    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                    __syncwarp();
+                }
+                if (interior) {
+                    const int r = lane - 1;
+#pragma unroll
+                    for (int k = 0; k < 2; ++k)
+                        *reinterpret_cast<uint4*>(stage_o + r * 32 + ((k ^ ((r >> 2) & 1)) << 4)) = part ? pl[k] : pk[k];
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) {
+                    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                                 ::"l"(part ? tmOl : tmO), "r"(smem_u32(stage_o)), "r"(c), "r"(s + 1) : "memory");
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                }
+            }
+            continue;
+        }
         // 30 rows x 32 B per chunk; 16-byte chunk index XOR (row / 4) % 2  ==  CU_TENSOR_MAP_SWIZZLE_32B
         unsigned char* stage_o = sO + (ew * 2 + j) * TC_O_WARP_BYTES;
         if (interior) {
@@ -214,17 +252,28 @@ __device__ __forceinline__ void tc_epilogue_tile64(unsigned t0, TcSmem* ctl, uns
 // tmO over `out` with box 16 x 30, 32-byte swizzle: every epilogue warp stages 30 rows x 16 channels in shared
 // memory and stores them with one TMA tensor store (a per-lane 16-byte store to rows 128 B apart is 32 LSU
 // wavefronts per instruction, which made the LSU data pipe the bound; staging + coalesced st.global was slower).
-template <int CO>
+//
+// SPLIT = true is the ERROR-COMPENSATED mode (precision 2, "bf16x3"): every fp32 activation and weight travels as two bf16
+// numbers, x = hi + lo with hi = bf16(x), lo = bf16(x - hi) (16 mantissa bits together), and a tile accumulates the three
+// products  Ah Wh + Ah Wl + Al Wh  into the same fp32 TMEM accumulator (the dropped Al Wl term is 2^-16 of the result):
+// 36 MMAs per tile instead of 12, activations read as two planes (tmA hi, tmAl lo) through a ring of three stages in the
+// order  Ah(dl=-1) Al(-1) Ah(0) Al(0) Ah(+1) Al(+1), weights hi (tmB) and lo (tmBl) both resident, results written as two
+// planes (tmO, tmOl).  The reference runs these nets in fp32 (denoisers/RealSN_DnCNN.py:32-35); this mode gives its
+// numbers to ~1e-5 on the tensor cores, the plain bf16 mode (~1e-2) stays the fast one.
+template <int CO, bool SPLIT = false>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
           const __grid_constant__ CUtensorMap tmO, const float* __restrict__ shift, float slope, int PW, int S, int n_tiles,
-          TcLast last, int dbg) {
+          TcLast last, int dbg, const __grid_constant__ CUtensorMap tmAl, const __grid_constant__ CUtensorMap tmBl,
+          const __grid_constant__ CUtensorMap tmOl) {
     using CF = TcCfg<CO>;
+    constexpr int NKB = SPLIT ? 6 : 3;                                         // resident weight blocks: (hi | lo) x dl
+    constexpr int NST = SPLIT ? TC_SPLIT_STAGES : TC_STAGES;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<unsigned long long>(smem_raw) + 1023ull) & ~1023ull);
-    unsigned char* sB = base;                                                  // 3 K blocks
-    unsigned char* sA = base + ((3 * CF::B_BYTES + 1023) & ~1023);             // TC_STAGES x 16 KiB
-    unsigned char* sO = sA + TC_STAGES * TC_A_BYTES;                           // output staging, 4 quadrants x 2 x 4 KiB (CO = 64)
+    unsigned char* sB = base;                                                  // 3 K blocks (SPLIT: hi blocks, then lo blocks)
+    unsigned char* sA = base + ((NKB * CF::B_BYTES + 1023) & ~1023);           // NST x 16 KiB
+    unsigned char* sO = sA + NST * TC_A_BYTES;                                 // output staging, 4 quadrants x 2 x 4 KiB (CO = 64)
     TcSmem* ctl = reinterpret_cast<TcSmem*>(sO + (CO == 64 ? TC_O_BYTES : 0));
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int pitch = PW + 1;
@@ -253,11 +302,33 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     if (warp == 0) {
         // ===== TMA producer =====
         if (elect_one()) {
-            mbar_expect_tx(&ctl->bfull, 3 * CF::B_BYTES);
+            mbar_expect_tx(&ctl->bfull, NKB * CF::B_BYTES);
             for (int kb = 0; kb < 3; ++kb) tma_load_2d(sB + kb * CF::B_BYTES, &tmB, kb * TC_KBLK, 0, &ctl->bfull);
+            if (SPLIT)
+                for (int kb = 0; kb < 3; ++kb) tma_load_2d(sB + (3 + kb) * CF::B_BYTES, &tmBl, kb * TC_KBLK, 0, &ctl->bfull);
         }
         __syncwarp();
         unsigned ph = 0;
+        if constexpr (SPLIT) {
+            // six loads per tile through a ring of three stages: load q = 2 * kb + (lo plane ? 1 : 0) uses stage q % 3 for the
+            // (q / 3)-th time in this tile, and every stage is used exactly twice per tile, so the barrier parities are static
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                const int s0 = tile * TC_OUT_PER_TILE - 1;
+#pragma unroll
+                for (int q6 = 0; q6 < 6; ++q6) {
+                    const int stage = q6 % 3, use = q6 / 3, kb = q6 >> 1;
+                    mbar_wait_bounded(&ctl->empty[stage], (unsigned)(use ^ 1));
+                    if (elect_one()) {
+                        mbar_expect_tx(&ctl->full[stage], TC_A_BYTES);
+#pragma unroll
+                        for (int q = 0; q < 4; ++q)
+                            tma_load_2d(sA + stage * TC_A_BYTES + q * (TC_Q_ROWS * 128), (q6 & 1) ? &tmAl : &tmA, 0,
+                                        s0 + q * TC_OUT_PER_Q + (kb - 1) * pitch, &ctl->full[stage]);
+                    }
+                    __syncwarp();
+                }
+            }
+        } else
         for (int tile = blockIdx.x; tile < n_tiles; ph ^= 1) {
 #pragma unroll
             for (int g = 0; g < 2; ++g) {
@@ -283,11 +354,11 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     } else if (warp == 1) {
         // ===== MMA issuer =====
         const unsigned idesc = umma_idesc_bf16(TC_M, CF::N);
-        unsigned long long da[TC_STAGES], db[3];
+        unsigned long long da[NST], db[NKB];
 #pragma unroll
-        for (int i = 0; i < TC_STAGES; ++i) da[i] = umma_desc_sw128(sA + i * TC_A_BYTES);
+        for (int i = 0; i < NST; ++i) da[i] = umma_desc_sw128(sA + i * TC_A_BYTES);
 #pragma unroll
-        for (int kb = 0; kb < 3; ++kb) db[kb] = umma_desc_sw128(sB + kb * CF::B_BYTES);
+        for (int kb = 0; kb < NKB; ++kb) db[kb] = umma_desc_sw128(sB + kb * CF::B_BYTES);
         mbar_wait_bounded(&ctl->bfull, 0);
         unsigned ph = 0;
         for (int tile = blockIdx.x; tile < n_tiles; ph ^= 1) {
@@ -297,6 +368,31 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                     mbar_wait_bounded(&ctl->tempty[g], ph ^ 1);            // epilogue has drained this accumulator
                     asm volatile("tcgen05.fence::after_thread_sync;");
                     const unsigned d = tmem + g * CF::ACC_COLS;
+                    if constexpr (SPLIT) {
+#pragma unroll
+                        for (int q6 = 0; q6 < 6; ++q6) {
+                            const int stage = q6 % 3, use = q6 / 3, kb = q6 >> 1;
+                            mbar_wait_bounded(&ctl->full[stage], (unsigned)use);
+                            asm volatile("tcgen05.fence::after_thread_sync;");
+                            if (elect_one()) {
+                                if ((q6 & 1) == 0) {                       // Ah: against Wh and Wl
+#pragma unroll
+                                    for (int k = 0; k < TC_KBLK / 16; ++k)
+                                        umma_f16(d, da[stage] + 2 * k, db[kb] + 2 * k, idesc, (kb | k) ? 1u : 0u);
+#pragma unroll
+                                    for (int k = 0; k < TC_KBLK / 16; ++k)
+                                        umma_f16(d, da[stage] + 2 * k, db[3 + kb] + 2 * k, idesc, 1u);
+                                } else {                                   // Al: against Wh
+#pragma unroll
+                                    for (int k = 0; k < TC_KBLK / 16; ++k)
+                                        umma_f16(d, da[stage] + 2 * k, db[kb] + 2 * k, idesc, 1u);
+                                }
+                                umma_commit(&ctl->empty[stage]);
+                                if (q6 == 5) umma_commit(&ctl->tfull[g]);
+                            }
+                            __syncwarp();
+                        }
+                    } else {
 #pragma unroll
                     for (int kb = 0; kb < 3; ++kb) {
                         const int stage = 3 * g + kb;
@@ -310,6 +406,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                             if (kb == 2) umma_commit(&ctl->tfull[g]);      // accumulator ready for the epilogue
                         }
                         __syncwarp();
+                    }
                     }
                 }
                 tile += gridDim.x;
@@ -335,7 +432,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             asm volatile("tcgen05.fence::after_thread_sync;");
             if (CO == 64) {
                 const bool pad = (s % pitch) == PW;                                   // the pad pixel of a line stays zero
-                tc_epilogue_tile64(t0, ctl, sO, &tmO, ew, wg, hf, lane, s, pad, interior, relu, slope, dbg);
+                tc_epilogue_tile64<SPLIT>(t0, ctl, sO, &tmO, ew, wg, hf, lane, s, pad, interior, relu, slope, dbg, &tmOl);
             } else {
                 // last layer: one output per position + the wrapper's output map
                 float t[4];
@@ -549,7 +646,7 @@ k_conv_tc_stack(const __grid_constant__ TcStack pm, int PW, int S, int n_tiles) 
 #define FL_R 16
 __global__ void __launch_bounds__(256)
 k_conv_first_bf16(const float* __restrict__ img, __nv_bfloat16* __restrict__ out, const float* __restrict__ w, CnnAct a,
-                  CnnIo io, int PH, int PW) {
+                  CnnIo io, int PH, int PW, __nv_bfloat16* __restrict__ out_lo) {       // out_lo: the residual plane of the split mode
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int cg = lane & 7;                                   // channels 8*cg .. 8*cg + 7
     const int p = blockIdx.x * 32 + warp * 4 + (lane >> 3);    // pixel within the line
@@ -612,14 +709,19 @@ k_conv_first_bf16(const float* __restrict__ img, __nv_bfloat16* __restrict__ out
 #pragma unroll
                 for (int k = 0; k < 4; ++k) acc[k] = __ffma2_rn(xx, wt[dl * 3 + dp][k], acc[k]);
             }
-        uint4 pk;
+        uint4 pk, pl;
         __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&pk);
+        __nv_bfloat162* hl = reinterpret_cast<__nv_bfloat162*>(&pl);
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             const float2 v = __ffma2_rn(acc[k], sc[k], sf[k]);
-            h[k] = __floats2bfloat162_rn(act(v.x, slope), act(v.y, slope));
+            const float a0 = act(v.x, slope), a1 = act(v.y, slope);
+            h[k] = __floats2bfloat162_rn(a0, a1);
+            const float2 hf2 = __bfloat1622float2(h[k]);
+            hl[k] = __floats2bfloat162_rn(a0 - hf2.x, a1 - hf2.y);
         }
         *reinterpret_cast<uint4*>(out + ((long long)l * (PW + 1) + p) * CNN_C + cg * 8) = pk;
+        if (out_lo) *reinterpret_cast<uint4*>(out_lo + ((long long)l * (PW + 1) + p) * CNN_C + cg * 8) = pl;
 #pragma unroll
         for (int d = 0; d < 3; ++d) { win[0][d] = win[1][d]; win[1][d] = win[2][d]; }
     }

@@ -1118,16 +1118,21 @@ int make_tmap_bf16_2d(CUtensorMap* map, const void* base, unsigned long long inn
 int g_tc_dbg = 0;
 
 int cnn_forward_tc(const pnp_cnn_net* net, const float* img, float* out, int PH, int PW, void* act0, void* act1, int* stats,
-                   const float* xrec, double* mse_log, const int* slot, cudaStream_t st) {
+                   const float* xrec, double* mse_log, const int* slot, cudaStream_t st, bool split) {
     const long long npix = (long long)PH * PW;
     const long long S = (long long)PH * (PW + 1);
     if (S >= (1ll << 31) - 4096) return fail(PNP_ERR_ARG, "image too large");
     const int L = net->n_layers;
     for (int l = 1; l < L; ++l) {
         if (!net->w_tc[l]) return fail(PNP_ERR_ARG, "w_tc[%d] missing: the net was not packed for the tensor-core path", l);
+        if (split && !net->w_tc_lo[l]) return fail(PNP_ERR_ARG, "w_tc_lo[%d] missing: the net was not packed for the split mode", l);
         if (l < L - 1 && !(net->slope[l] <= 1.f)) return fail(PNP_ERR_UNSUPPORTED, "activation slope %g > 1 on the tensor-core path", net->slope[l]);
     }
     int rc;
+    if (split) {
+        if ((rc = raise_smem_limit((const void*)pnp::k_conv_tc<64, true>, (int)pnp::tc_smem<64, true>())) != PNP_OK) return rc;
+        if ((rc = raise_smem_limit((const void*)pnp::k_conv_tc<1, true>, (int)pnp::tc_smem<1, true>())) != PNP_OK) return rc;
+    }
     if ((rc = raise_smem_limit((const void*)pnp::k_conv_tc<64>, (int)pnp::tc_smem<64>())) != PNP_OK) return rc;
     if ((rc = raise_smem_limit((const void*)pnp::k_conv_tc<1>, (int)pnp::tc_smem<1>())) != PNP_OK) return rc;
     pnp::CnnIo io{net->mode, stats, net->range, net->shift_in};
@@ -1139,12 +1144,38 @@ int cnn_forward_tc(const pnp_cnn_net* net, const float* img, float* out, int PH,
     }
     __nv_bfloat16* cur = static_cast<__nv_bfloat16*>(act0);
     __nv_bfloat16* nxt = static_cast<__nv_bfloat16*>(act1);
+    const long long plane = S * 64;                  // split mode: the lo plane of an activation buffer follows its hi plane
     pnp::k_conv_first_bf16<<<dim3((PW + 31) / 32, (PH + FL_R - 1) / FL_R), 256, 0, st>>>(img, cur, net->w[0],
-        pnp::CnnAct{net->scale[0], net->shift[0], net->slope[0]}, io, PH, PW);
+        pnp::CnnAct{net->scale[0], net->shift[0], net->slope[0]}, io, PH, PW, split ? cur + plane : nullptr);
     LAUNCH_CHECK();
     const int n_tiles = (int)((S + TC_OUT_PER_TILE - 1) / TC_OUT_PER_TILE);
     const int grid = n_tiles < num_sms() ? n_tiles : num_sms();
     CUtensorMap tmA, tmB, tmO;
+    if (split) {
+        // error-compensated mode: one launch per layer, hi and lo planes of activations and weights (csrc/cnn_tc.cuh)
+        CUtensorMap tmAl, tmBl, tmOl;
+        for (int l = 1; l < L - 1; ++l) {
+            if ((rc = make_tmap_bf16_2d(&tmA, cur, 64, (unsigned long long)S, 64, TC_Q_ROWS)) != PNP_OK) return rc;
+            if ((rc = make_tmap_bf16_2d(&tmAl, cur + plane, 64, (unsigned long long)S, 64, TC_Q_ROWS)) != PNP_OK) return rc;
+            if ((rc = make_tmap_bf16_2d(&tmB, net->w_tc[l], 192, 192, 64, 192)) != PNP_OK) return rc;
+            if ((rc = make_tmap_bf16_2d(&tmBl, net->w_tc_lo[l], 192, 192, 64, 192)) != PNP_OK) return rc;
+            if ((rc = make_tmap_bf16_2d(&tmO, nxt, 64, (unsigned long long)S, 16, TC_OUT_PER_Q, CU_TENSOR_MAP_SWIZZLE_32B)) != PNP_OK) return rc;
+            if ((rc = make_tmap_bf16_2d(&tmOl, nxt + plane, 64, (unsigned long long)S, 16, TC_OUT_PER_Q, CU_TENSOR_MAP_SWIZZLE_32B)) != PNP_OK) return rc;
+            pnp::k_conv_tc<64, true><<<grid, TC_THREADS, pnp::tc_smem<64, true>(), st>>>(
+                tmA, tmB, tmO, net->shift[l], net->slope[l], PW, (int)S, n_tiles, pnp::TcLast{}, 0, tmAl, tmBl, tmOl);
+            LAUNCH_CHECK();
+            __nv_bfloat16* t = cur; cur = nxt; nxt = t;
+        }
+        if ((rc = make_tmap_bf16_2d(&tmA, cur, 64, (unsigned long long)S, 64, TC_Q_ROWS)) != PNP_OK) return rc;
+        if ((rc = make_tmap_bf16_2d(&tmAl, cur + plane, 64, (unsigned long long)S, 64, TC_Q_ROWS)) != PNP_OK) return rc;
+        if ((rc = make_tmap_bf16_2d(&tmB, net->w_tc[L - 1], 192, 16, 64, 16)) != PNP_OK) return rc;
+        if ((rc = make_tmap_bf16_2d(&tmBl, net->w_tc_lo[L - 1], 192, 16, 64, 16)) != PNP_OK) return rc;
+        pnp::k_conv_tc<1, true><<<grid, TC_THREADS, pnp::tc_smem<1, true>(), st>>>(
+            tmA, tmB, tmA, nullptr, 0.f, PW, (int)S, n_tiles, pnp::TcLast{img, out, xrec, mse_log, slot, net->last_bias, io}, 0,
+            tmAl, tmBl, tmA);
+        LAUNCH_CHECK();
+        return PNP_OK;
+    }
     // small images: all middle layers in one cooperative launch (a layer would be a few tiles per SM inside a ~10 us launch)
     const bool stack = g_tc_dbg != 32 && L - 2 >= 2 && L - 2 <= TC_MAX_LAYERS && n_tiles <= 8 * num_sms();
     if (stack) {
@@ -1170,14 +1201,15 @@ int cnn_forward_tc(const pnp_cnn_net* net, const float* img, float* out, int PH,
         if ((rc = make_tmap_bf16_2d(&tmB, net->w_tc[l], 192, 192, 64, 192)) != PNP_OK) return rc;
         if ((rc = make_tmap_bf16_2d(&tmO, nxt, 64, (unsigned long long)S, 16, TC_OUT_PER_Q, CU_TENSOR_MAP_SWIZZLE_32B)) != PNP_OK) return rc;
         pnp::k_conv_tc<64><<<grid, TC_THREADS, pnp::tc_smem<64>(), st>>>(tmA, tmB, tmO, net->shift[l], net->slope[l], PW, (int)S, n_tiles,
-                                                                         pnp::TcLast{}, g_tc_dbg);
+                                                                         pnp::TcLast{}, g_tc_dbg, tmA, tmB, tmO);
         LAUNCH_CHECK();
         __nv_bfloat16* t = cur; cur = nxt; nxt = t;
     }
     if ((rc = make_tmap_bf16_2d(&tmA, cur, 64, (unsigned long long)S, 64, TC_Q_ROWS)) != PNP_OK) return rc;
     if ((rc = make_tmap_bf16_2d(&tmB, net->w_tc[L - 1], 192, 16, 64, 16)) != PNP_OK) return rc;
     pnp::k_conv_tc<1><<<grid, TC_THREADS, pnp::tc_smem<1>(), st>>>(tmA, tmB, tmA, nullptr, 0.f, PW, (int)S, n_tiles,
-                                                              pnp::TcLast{img, out, xrec, mse_log, slot, net->last_bias, io}, 0);
+                                                              pnp::TcLast{img, out, xrec, mse_log, slot, net->last_bias, io}, 0,
+                                                              tmA, tmB, tmA);
     LAUNCH_CHECK();
     return PNP_OK;
 }
@@ -1188,9 +1220,9 @@ int pnp_cnn_forward(const pnp_cnn_net* net, const float* img, float* out, int PH
                     int* stats, const float* xrec, double* mse_log, const int* slot, int precision, void* stream) {
     if (!net || !img || !out || !act0 || !act1 || !stats || PH < 1 || PW < 1) return fail(PNP_ERR_ARG, "bad argument");
     if (net->n_layers < 2 || net->n_layers > PNP_CNN_MAX_LAYERS) return fail(PNP_ERR_ARG, "n_layers out of range");
-    if (precision != 0 && precision != 1) return fail(PNP_ERR_ARG, "precision %d unknown", precision);
+    if (precision < 0 || precision > 2) return fail(PNP_ERR_ARG, "precision %d unknown", precision);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (precision == 1) return cnn_forward_tc(net, img, out, PH, PW, act0, act1, stats, xrec, mse_log, slot, st);
+    if (precision >= 1) return cnn_forward_tc(net, img, out, PH, PW, act0, act1, stats, xrec, mse_log, slot, st, precision == 2);
     const long long npix = (long long)PH * PW;
     pnp::CnnIo io{net->mode, stats, net->range, net->shift_in};
     if (net->mode == 0) {

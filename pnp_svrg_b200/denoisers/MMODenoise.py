@@ -38,7 +38,7 @@ class MMODenoiser(Denoise):
     def __init__(self, model=None, channels=3, path=None, cuda=True, sigma=0.01, root_path='.', *, precision='fp32'):
         super().__init__()
         self.sigma = sigma
-        self.precision = {'fp32': 0, 'bf16': 1}[precision]
+        self.precision = {'fp32': 0, 'bf16': 1, 'bf16x3': 2}[precision]
         if model is None:
             if channels != 1:
                 raise NotImplementedError('only the single-channel (grey) networks are built on the GPU path')

@@ -29,7 +29,7 @@ class RealSN_DnCNNDenoiser(Denoise):
         super().__init__()
         self.model_type = model_type
         self.sigma = sigma
-        self.precision = {'fp32': 0, 'bf16': 1}[precision]
+        self.precision = {'fp32': 0, 'bf16': 1, 'bf16x3': 2}[precision]
         sd = state_dict if state_dict is not None else load_state_dict(model_type, sigma, weights_dir)
         dev = D.require_cuda()
         # denoisers/RealSN_DnCNN.py:27-29

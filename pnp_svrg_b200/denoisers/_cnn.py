@@ -76,9 +76,13 @@ class PackedNet:
                 w2 = np.zeros((16, 3 * 64))                                 # rows dp, padded to a legal UMMA N
                 w2[:3] = w[0].transpose(2, 1, 0).reshape(3, 3 * 64)         # [dp][dl][ci]
             if i > 0:
-                t = torch.from_numpy(np.ascontiguousarray(w2, dtype=np.float32)).to(self.device).to(torch.bfloat16).contiguous()
-                self.keep.append(t)
+                w32 = torch.from_numpy(np.ascontiguousarray(w2, dtype=np.float32)).to(self.device)
+                t = w32.to(torch.bfloat16).contiguous()
+                # error-compensated mode (precision 2): the part of the fp32 weight that bf16 dropped, as a second bf16 operand
+                t_lo = (w32 - t.to(torch.float32)).to(torch.bfloat16).contiguous()
+                self.keep += [t, t_lo]
                 net.w_tc[i] = t.data_ptr()
+                net.w_tc_lo[i] = t_lo.data_ptr()
             last = i == len(layers) - 1
             if not last:
                 net.scale[i] = self._up(lay['scale']) if lay['scale'] is not None else None
@@ -99,8 +103,9 @@ class PackedNet:
         return t.data_ptr()
 
     def forward(self, img, out, PH, PW, xrec=None, mse_log=None, slot=None, precision=0):
-        if precision == 1:
-            n, dt = PH * (PW + 1) * 64, torch.bfloat16      # one zero pad pixel per line, zeroed once
+        if precision >= 1:
+            # one zero pad pixel per line, zeroed once; precision 2 keeps a hi and a lo plane per buffer
+            n, dt = PH * (PW + 1) * 64 * (2 if precision == 2 else 1), torch.bfloat16
         else:
             n, dt = PH * PW * 64, torch.float32
         if self._act is None or self._act[0].numel() != n or self._act[0].dtype != dt:

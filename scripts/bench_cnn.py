@@ -1,4 +1,5 @@
-"""DnCNN-17 forward timing: fp32 CUDA-core path vs bf16 tcgen05 path (CUDA events, L2 flushed)."""
+"""DnCNN-17 forward timing: fp32 CUDA-core path vs the bf16 and the error-compensated bf16x3 tcgen05 paths (CUDA events, L2
+flushed), and the agreement of the tensor-core paths with the fp32 path."""
 import argparse
 import json
 import os
@@ -26,7 +27,7 @@ def main():
     sd = _random_dncnn_sd(17, True, False, seed=1)
     peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json'))) if os.path.exists(os.path.join(ROOT, 'MEASURED_PEAKS.json')) else {}
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    out = {}
+    out, outs, errs = {}, {}, {}
     for H in [int(x) for x in a.sizes.split(',')]:
         z = D.to_lines(synth_image(H, H, 0).astype(np.float64) / 255, H, H, dev)
         o = torch.empty_like(z)
@@ -37,7 +38,7 @@ def main():
                 den._dev_denoise(ctx)
             torch.cuda.synchronize()
             ts = []
-            for _ in range(a.iters if (prec == 'bf16' or H <= 512) else 2):
+            for _ in range(a.iters if (prec != 'fp32' or H <= 512) else 2):
                 flush.fill_(1)
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()
@@ -46,10 +47,15 @@ def main():
                 torch.cuda.synchronize()
                 ts.append(e0.elapsed_time(e1))
             ms = float(np.median(ts))
+            if H <= 512:                    # agreement with the fp32 CUDA-core path (same weights, same input)
+                ref_out = outs.setdefault(H, o.clone()) if prec == 'fp32' else outs.get(H)
+                if ref_out is not None and prec != 'fp32':
+                    errs['%d_%s' % (H, prec)] = float((o - ref_out).norm() / ref_out.norm())
             flop = 1108224.0 * H * H
             mid = 15 * 2 * 9 * 64 * 64 * H * H
             out['%d_%s' % (H, prec)] = dict(ms=ms, tflops_all=flop / ms / 1e9, tflops_mid_layers_only=mid / ms / 1e9,
                                             frac_of_measured_bf16_sustained=(flop / ms / 1e9) / peaks.get('bf16_tflops_sustained', 1417.2))
+    out['rel_l2_vs_fp32_path'] = errs
     print(json.dumps(out))
 
 

@@ -142,3 +142,43 @@ def test_tensor_core_dncnn17_reference_weights_psnr(cuda):
     mse = np.mean((got - clean) ** 2)
     assert 10 * np.log10(1.0 / mse) > 40.0, 10 * np.log10(1.0 / mse)     # > 40 dB agreement with the reference output
     assert rel_l2(got, d['denoised']) < 5e-3
+
+
+@pytest.mark.parametrize('depth,H,W', [(3, 64, 64), (4, 32, 128), (17, 64, 64), (17, 256, 256), (17, 512, 128)])
+def test_error_compensated_tensor_core_mode_matches_fp32_path(cuda, depth, H, W):
+    """precision='bf16x3' (hi + lo bf16 operands, three tcgen05 products per tile into the fp32 accumulator) against the
+    fp32 CUDA-core stack, same weights, same input: <= 1e-4 through 17 layers (the plain bf16 mode: ~1e-2), so the
+    tensor cores also serve the exact mode (the reference runs the nets in fp32, denoisers/RealSN_DnCNN.py:32-35)."""
+    from pnp_svrg_b200.denoisers import RealSN_DnCNNDenoiser
+    sd = _random_dncnn_sd(depth, depth > 4, False, seed=100 + depth)
+    noisy = synth_image(H, W, 2).astype(np.float64) / 255
+    a = RealSN_DnCNNDenoiser('DnCNN', 15, state_dict=sd).denoise(noisy)
+    b = RealSN_DnCNNDenoiser('DnCNN', 15, state_dict=sd, precision='bf16x3').denoise(noisy)
+    c = RealSN_DnCNNDenoiser('DnCNN', 15, state_dict=sd, precision='bf16').denoise(noisy)
+    err, err_fast = rel_l2(b, a), rel_l2(c, a)
+    assert err < 1e-4, (err, err_fast)
+    assert err < 0.05 * err_fast, (err, err_fast)           # two orders of magnitude closer than the fast mode
+
+
+def test_error_compensated_mode_reference_weights(cuda):
+    """DnCNN-17 with the reference's own weights and the reference's own output (tests/golden/ref_cnn_dncnn15.npz, made
+    by the unmodified torch model): the error-compensated tensor-core mode holds the tolerance of the fp32 path."""
+    from pnp_svrg_b200.denoisers import RealSN_DnCNNDenoiser
+    meta, d, sd = _fixture('ref_cnn_dncnn15.npz')
+    got = RealSN_DnCNNDenoiser('DnCNN', 15, state_dict=sd, precision='bf16x3').denoise(d['noisy'])
+    fp32 = RealSN_DnCNNDenoiser('DnCNN', 15, state_dict=sd).denoise(d['noisy'])
+    assert rel_l2(got, d['denoised']) < 1e-4, rel_l2(got, d['denoised'])
+    assert rel_l2(got, fp32) < 1e-4, rel_l2(got, fp32)
+
+
+def test_mmo_error_compensated_mode(cuda):
+    """MMODenoiser(precision='bf16x3') (20-layer DnCNN_nobn, bias + LeakyReLU) against the reference's own output at the
+    fp32 path's tolerance."""
+    from pnp_svrg_b200.denoisers.MMODenoise import MMODenoiser
+    from pnp_svrg_b200.denoisers.models.basic_models import simple_CNN
+    meta, d, sd = _fixture('ref_cnn_mmo_nobn.npz')
+    mod = simple_CNN(n_ch_in=1, n_ch_out=1, n_ch=64, nl_type='relu', depth=meta['depth'], bn=False)
+    mod.load_state_dict(sd)
+    got = MMODenoiser(model=mod, channels=1, precision='bf16x3').denoise(d['noisy'])
+    assert got.min() >= 0.0 and got.max() <= 1.0
+    assert rel_l2(got, d['denoised']) < 1e-4, rel_l2(got, d['denoised'])
