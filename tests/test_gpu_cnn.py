@@ -182,3 +182,27 @@ def test_mmo_error_compensated_mode(cuda):
     got = MMODenoiser(model=mod, channels=1, precision='bf16x3').denoise(d['noisy'])
     assert got.min() >= 0.0 and got.max() <= 1.0
     assert rel_l2(got, d['denoised']) < 1e-4, rel_l2(got, d['denoised'])
+
+
+def test_pnp_svrg_with_dncnn_prox_on_tensor_cores_exact_mode(cuda):
+    """The loop-level parity test of test_pnp_svrg_with_dncnn_prox with the prox on the tensor cores in the
+    error-compensated mode: same tolerance against the oracle loop (torch CPU fp32 forward as the prox)."""
+    from oracle import algorithms_port as AP
+    from oracle.problems_port import CSMRIPort
+    from pnp_svrg_b200.algorithms import pnp_svrg
+    from pnp_svrg_b200.denoisers import RealSN_DnCNNDenoiser
+    from pnp_svrg_b200.problems import CSMRI
+    meta, d, sd = _fixture('ref_cnn_dncnn15.npz')
+    img = synth_image(64, 64, 0)
+    np.random.seed(0)
+    ref = CSMRIPort(img, H=64, W=64, sample_prob=0.5, snr=20.)
+    np.random.seed(0)
+    dut = CSMRI(image=img, H=64, W=64, sample_prob=0.5, snr=20.)
+    port, _ = _torch_wrapper_forward(sd, np.zeros((8, 8)) + np.arange(8), 15)
+    kw = dict(eta=800.0, T2=4, mini_batch_size=300, vr_mode='paper', converge_check=False)
+    np.random.seed(1)
+    want = AP.pnp_svrg(ref, port, budget=8, **kw)
+    np.random.seed(1)
+    got = pnp_svrg(dut, RealSN_DnCNNDenoiser('DnCNN', 15, state_dict=sd, precision='bf16x3'), tt=1e9, max_iters=8, verbose=False, **kw)
+    assert rel_l2(got['z'], want['z']) < 1e-4, rel_l2(got['z'], want['z'])
+    assert abs(got['psnr_per_iter'][-1] - want['psnr_per_iter'][-1]) <= 0.05
