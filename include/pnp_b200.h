@@ -281,6 +281,8 @@ typedef struct {
     float* v_out;
     const float* z_in;
     float* z_out;
+    float* S2;                    /* optional second scratch like S: with w given, both points share the three passes'
+                                     launches (same result as the two-sequence form) */
 } pnp_cdp_grad_args;
 int pnp_cdp_grad(const pnp_cdp_grad_args* args, void* stream);
 

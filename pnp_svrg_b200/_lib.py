@@ -75,6 +75,7 @@ class CdpGradArgs(C.Structure):
         ('w', C.c_void_p), ('sel_idx', C.c_void_p), ('count', C.c_int), ('cursor', C.c_void_p), ('mask', C.c_void_p),
         ('S', C.c_void_p), ('acc', C.c_void_p), ('gscale', C.c_float), ('step', C.c_float), ('step_ptr', C.c_void_p),
         ('g_out', C.c_void_p), ('vadd', C.c_void_p), ('v_out', C.c_void_p), ('z_in', C.c_void_p), ('z_out', C.c_void_p),
+        ('S2', C.c_void_p),
     ]
 
 

@@ -45,12 +45,14 @@ __global__ void k_cdp_sel(unsigned char* __restrict__ mask, const int* __restric
 // pass 1: S[l][line][:] = FFT_L( i^code o u[line][:] )
 template <int L>
 __global__ void __launch_bounds__(cdp_lines_per_cta<L>() * fft_threads<L>())
-k_cdp_lines_fwd(const float* __restrict__ u, const signed char* __restrict__ codes, float2* __restrict__ S, int nlines) {
+k_cdp_lines_fwd(const float* __restrict__ u, const signed char* __restrict__ codes, float2* __restrict__ S, int nlines,
+                const float* __restrict__ u2, float2* __restrict__ S2) {          // blockIdx.z = 1: the second point (u2 -> S2)
     constexpr int T = fft_threads<L>(), EPT = FftPlan<L>::EPT, PL = fft_plane<L>();
     using IX = FftIdx<L>;
     extern __shared__ __align__(16) float smem[];
     const int g = threadIdx.x / T, t = threadIdx.x % T;
     const int line = blockIdx.x * cdp_lines_per_cta<L>() + g, l = blockIdx.y;
+    if (blockIdx.z) { u = u2; S = S2; }
     const bool active = line < nlines;
     const SmemBuf sb{smem + g * 2 * PL, smem + g * 2 * PL + PL};
     const long long lo = (long long)(active ? line : 0) * L, so = ((long long)l * nlines + (active ? line : 0)) * L;
@@ -72,7 +74,7 @@ k_cdp_lines_fwd(const float* __restrict__ u, const signed char* __restrict__ cod
 template <int LW>
 __global__ void __launch_bounds__(cdp_cols_per_cta<LW>() * fft_threads<LW>())
 k_cdp_cols(float2* __restrict__ S, const float* __restrict__ y, unsigned char* __restrict__ mask, int H, float inv_n,
-           int clear_mask) {
+           int clear_mask, float2* __restrict__ S2) {      // S2: the second point's planes, done by the same CTA after S
     constexpr int T = fft_threads<LW>(), EPT = FftPlan<LW>::EPT, PL = fft_plane<LW>(), NC = cdp_cols_per_cta<LW>();
     using IX = FftIdx<LW>;
     extern __shared__ __align__(16) float smem[];
@@ -80,33 +82,38 @@ k_cdp_cols(float2* __restrict__ S, const float* __restrict__ y, unsigned char* _
     const int ky = blockIdx.x * NC + g, l = blockIdx.y;
     const SmemBuf sb{smem + g * 2 * PL, smem + g * 2 * PL + PL};
     const long long base = (long long)l * LW * H + ky;
-    float2 x[EPT];
+    const int npts = S2 ? 2 : 1;
+    for (int pt = 0; pt < npts; ++pt) {
+        float2* Sp = pt ? S2 : S;
+        float2 x[EPT];
 #pragma unroll
-    for (int i = 0; i < EPT; ++i) x[i] = S[base + (long long)IX::in(t, i) * H];
-    fft_regs<LW>(t, sb, x);
-    float2 v[EPT];
+        for (int i = 0; i < EPT; ++i) x[i] = Sp[base + (long long)IX::in(t, i) * H];
+        fft_regs<LW>(t, sb, x);
+        float2 v[EPT];
 #pragma unroll
-    for (int m = 0; m < EPT; ++m) {
-        const long long e = base + (long long)(t + T * m) * H;               // this thread owns kx = t + T*m before and after
-        const float2 F = x[IX::out_slot(m)];
-        float q = fmaf(F.x * F.x + F.y * F.y, inv_n, -y[e]);
-        if (mask) {
-            if (!mask[e]) q = 0.f;
-            else if (clear_mask) mask[e] = 0;                                 // single-use minibatch selection
+        for (int m = 0; m < EPT; ++m) {
+            const long long e = base + (long long)(t + T * m) * H;           // this thread owns kx = t + T*m before and after
+            const float2 F = x[IX::out_slot(m)];
+            float q = fmaf(F.x * F.x + F.y * F.y, inv_n, -y[e]);
+            if (mask) {
+                if (!mask[e]) q = 0.f;
+                else if (clear_mask && pt == npts - 1) mask[e] = 0;           // single-use minibatch selection
+            }
+            v[IX::in_slot(m)] = make_float2(q * F.y, q * F.x);                // re/im swapped: inverse by the forward core
         }
-        v[IX::in_slot(m)] = make_float2(q * F.y, q * F.x);                    // re/im swapped: inverse by the forward core
-    }
-    if (FftPlan<LW>::NS > 1) __syncthreads();
-    fft_regs<LW>(t, sb, v);
+        if (FftPlan<LW>::NS > 1) __syncthreads();
+        fft_regs<LW>(t, sb, v);
 #pragma unroll
-    for (int i = 0; i < EPT; ++i) S[base + (long long)IX::out(t, i) * H] = cswap(v[i]);
+        for (int i = 0; i < EPT; ++i) Sp[base + (long long)IX::out(t, i) * H] = cswap(v[i]);
+        if (pt + 1 < npts) __syncthreads();       // exchange buffer free for the second point
+    }
 }
 
 // pass 3: acc[line][:] (+)= sign * sum_l Re( conj(i^code) o IFFT_L(S[l][line][:]) )
 template <int L>
 __global__ void __launch_bounds__(cdp_lines_per_cta<L>() * fft_threads<L>())
 k_cdp_lines_inv(const float2* __restrict__ S, const signed char* __restrict__ codes, float* __restrict__ acc, int nlines,
-                int nmasks, float sign, int accumulate) {
+                int nmasks, float sign, int accumulate, const float2* __restrict__ S2) {   // S2: acc = sum(S) - sum(S2)
     constexpr int T = fft_threads<L>(), EPT = FftPlan<L>::EPT, PL = fft_plane<L>();
     using IX = FftIdx<L>;
     extern __shared__ __align__(16) float smem[];
@@ -128,6 +135,27 @@ k_cdp_lines_inv(const float2* __restrict__ S, const signed char* __restrict__ co
             for (int i = 0; i < EPT; ++i) sum[i] += cdp_decode_re(cswap(x[i]), codes[so + IX::out(t, i)]);
         }
         __syncthreads();                          // exchange buffer free for the next mask
+    }
+    if (S2) {
+        // the second point in the same launch: its masks are summed separately and subtracted once, which is what the
+        // two-launch sequence (acc = sum, then acc = fma(-1, sum2, acc)) computes
+        float sum2[EPT];
+#pragma unroll
+        for (int i = 0; i < EPT; ++i) sum2[i] = 0.f;
+        for (int l = 0; l < nmasks; ++l) {
+            const long long so = ((long long)l * nlines + (active ? line : 0)) * L;
+            float2 x[EPT];
+#pragma unroll
+            for (int i = 0; i < EPT; ++i) x[i] = active ? cswap(S2[so + IX::in(t, i)]) : make_float2(0.f, 0.f);
+            fft_regs<L>(t, sb, x);
+            if (active) {
+#pragma unroll
+                for (int i = 0; i < EPT; ++i) sum2[i] += cdp_decode_re(cswap(x[i]), codes[so + IX::out(t, i)]);
+            }
+            __syncthreads();
+        }
+#pragma unroll
+        for (int i = 0; i < EPT; ++i) sum[i] = sum[i] - sum2[i];
     }
     if (active) {
         const long long lo = (long long)line * L;

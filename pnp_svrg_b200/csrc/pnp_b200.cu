@@ -348,39 +348,45 @@ int dispatch_update_prox(int n, const float* S, int W, float inv_n, float gscale
 
 namespace {
 template <int L>
-int launch_cdp_lines_fwd(const float* u, const signed char* codes, float2* S, int nlines, int nmasks, cudaStream_t st) {
+int launch_cdp_lines_fwd(const float* u, const signed char* codes, float2* S, int nlines, int nmasks, const float* u2, float2* S2,
+                         cudaStream_t st) {
     constexpr int GL = pnp::cdp_lines_per_cta<L>();
-    dim3 grid((nlines + GL - 1) / GL, nmasks);
-    pnp::k_cdp_lines_fwd<L><<<grid, GL * pnp::fft_threads<L>(), sizeof(float) * GL * 2 * pnp::fft_plane<L>(), st>>>(u, codes, S, nlines);
+    dim3 grid((nlines + GL - 1) / GL, nmasks, S2 ? 2 : 1);
+    pnp::k_cdp_lines_fwd<L><<<grid, GL * pnp::fft_threads<L>(), sizeof(float) * GL * 2 * pnp::fft_plane<L>(), st>>>(u, codes, S, nlines,
+                                                                                                                   u2, S2);
     LAUNCH_CHECK();
     return PNP_OK;
 }
 template <int LW>
-int launch_cdp_cols(float2* S, const float* y, unsigned char* mask, int H, int nmasks, float inv_n, int clear, cudaStream_t st) {
+int launch_cdp_cols(float2* S, const float* y, unsigned char* mask, int H, int nmasks, float inv_n, int clear, float2* S2,
+                    cudaStream_t st) {
     constexpr int NC = pnp::cdp_cols_per_cta<LW>();
     dim3 grid(H / NC, nmasks);
-    pnp::k_cdp_cols<LW><<<grid, NC * pnp::fft_threads<LW>(), sizeof(float) * NC * 2 * pnp::fft_plane<LW>(), st>>>(S, y, mask, H, inv_n, clear);
+    pnp::k_cdp_cols<LW><<<grid, NC * pnp::fft_threads<LW>(), sizeof(float) * NC * 2 * pnp::fft_plane<LW>(), st>>>(S, y, mask, H, inv_n, clear,
+                                                                                                                 S2);
     LAUNCH_CHECK();
     return PNP_OK;
 }
 template <int L>
 int launch_cdp_lines_inv(const float2* S, const signed char* codes, float* acc, int nlines, int nmasks, float sign, int accumulate,
-                         cudaStream_t st) {
+                         const float2* S2, cudaStream_t st) {
     constexpr int GL = pnp::cdp_lines_per_cta<L>();
     pnp::k_cdp_lines_inv<L><<<(nlines + GL - 1) / GL, GL * pnp::fft_threads<L>(), sizeof(float) * GL * 2 * pnp::fft_plane<L>(), st>>>(
-        S, codes, acc, nlines, nmasks, sign, accumulate);
+        S, codes, acc, nlines, nmasks, sign, accumulate, S2);
     LAUNCH_CHECK();
     return PNP_OK;
 }
-int dispatch_cdp_lines_fwd(int n, const float* u, const signed char* codes, float2* S, int nlines, int nmasks, cudaStream_t st) {
-    DISPATCH_POW2(n, launch_cdp_lines_fwd, u, codes, S, nlines, nmasks, st)
+int dispatch_cdp_lines_fwd(int n, const float* u, const signed char* codes, float2* S, int nlines, int nmasks, const float* u2,
+                           float2* S2, cudaStream_t st) {
+    DISPATCH_POW2(n, launch_cdp_lines_fwd, u, codes, S, nlines, nmasks, u2, S2, st)
 }
-int dispatch_cdp_cols(int n, float2* S, const float* y, unsigned char* mask, int H, int nmasks, float inv_n, int clear, cudaStream_t st) {
-    DISPATCH_POW2(n, launch_cdp_cols, S, y, mask, H, nmasks, inv_n, clear, st)
+int dispatch_cdp_cols(int n, float2* S, const float* y, unsigned char* mask, int H, int nmasks, float inv_n, int clear, float2* S2,
+                      cudaStream_t st) {
+    DISPATCH_POW2(n, launch_cdp_cols, S, y, mask, H, nmasks, inv_n, clear, S2, st)
 }
 int dispatch_cdp_lines_inv(int n, const float2* S, const signed char* codes, float* acc, int nlines, int nmasks, float sign,
-                           int accumulate, cudaStream_t st) {
-    DISPATCH_POW2(n, launch_cdp_lines_inv, S, codes, acc, nlines, nmasks, sign, accumulate, st)
+                           int accumulate, const float2* S2, cudaStream_t st) {
+    DISPATCH_POW2(n, launch_cdp_lines_inv, S, codes, acc, nlines, nmasks, sign, accumulate, S2, st)
 }
 }  // namespace
 
@@ -1022,11 +1028,19 @@ int pnp_cdp_grad(const pnp_cdp_grad_args* args, void* stream) {
     const float inv_n = (float)(1.0 / (double)N);
     const int npts = a.w ? 2 : 1;
     int rc;
+    if (npts == 2 && a.S2) {
+        // both points in the same three launches (second scratch given): the transforms of z and w are independent, the
+        // column pass keeps the single-use selection until its second point, the inverse pass forms the difference
+        float2* S2 = reinterpret_cast<float2*>(a.S2);
+        if ((rc = dispatch_cdp_lines_fwd(a.H, a.z, a.codes, S, a.W, a.L, a.w, S2, st)) != PNP_OK) return rc;
+        if ((rc = dispatch_cdp_cols(a.W, S, a.y, mask, a.H, a.L, inv_n, 1, S2, st)) != PNP_OK) return rc;
+        if ((rc = dispatch_cdp_lines_inv(a.H, S, a.codes, a.acc, a.W, a.L, 1.f, 0, S2, st)) != PNP_OK) return rc;
+    } else
     for (int pt = 0; pt < npts; ++pt) {
         const float* u = pt == 0 ? a.z : a.w;
-        if ((rc = dispatch_cdp_lines_fwd(a.H, u, a.codes, S, a.W, a.L, st)) != PNP_OK) return rc;
-        if ((rc = dispatch_cdp_cols(a.W, S, a.y, mask, a.H, a.L, inv_n, pt == npts - 1, st)) != PNP_OK) return rc;
-        if ((rc = dispatch_cdp_lines_inv(a.H, S, a.codes, a.acc, a.W, a.L, pt == 0 ? 1.f : -1.f, pt, st)) != PNP_OK) return rc;
+        if ((rc = dispatch_cdp_lines_fwd(a.H, u, a.codes, S, a.W, a.L, nullptr, nullptr, st)) != PNP_OK) return rc;
+        if ((rc = dispatch_cdp_cols(a.W, S, a.y, mask, a.H, a.L, inv_n, pt == npts - 1, nullptr, st)) != PNP_OK) return rc;
+        if ((rc = dispatch_cdp_lines_inv(a.H, S, a.codes, a.acc, a.W, a.L, pt == 0 ? 1.f : -1.f, pt, nullptr, st)) != PNP_OK) return rc;
     }
     pnp::k_cdp_epilogue<<<ew_blocks(N, 1), 256, 0, st>>>(a.acc, N, a.gscale * inv_n, a.step, a.step_ptr, a.g_out, a.vadd, a.v_out,
                                                          a.z_in, a.z_out);

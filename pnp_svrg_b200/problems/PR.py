@@ -7,6 +7,8 @@ patterns, ``M = n_masks*N`` measurements ``y = |A x|^2``, gradient ``Re(A^H((|Az
 pnp_cdp_grad (csrc/cdp.cuh).  The default stays the reference's dense model."""
 import ctypes as C
 
+import os
+
 import numpy as np
 import torch
 
@@ -166,6 +168,7 @@ class PhaseRetrieval(Problem):
         self._y = t(self.Y, np.float32)
         self._mask = torch.zeros(self.M, dtype=torch.uint8, device=dev)
         self._S = torch.empty(2 * self.M, dtype=torch.float32, device=dev)
+        self._S2 = torch.empty(2 * self.M, dtype=torch.float32, device=dev)      # second point (SVRG / SARAH differences)
         self._acc = torch.empty(self.N, dtype=torch.float32, device=dev)
 
     def _A_cdp(self, w):
@@ -196,7 +199,8 @@ class PhaseRetrieval(Problem):
             H=self.H, W=self.W, L=self.L, codes=D.ptr(self._codes), y=D.ptr(self._y), z=D.ptr(a), w=D.ptr(b),
             sel_idx=D.ptr(sel), count=0 if sel is None else int(sel.numel()), cursor=None, mask=D.ptr(self._mask),
             S=D.ptr(self._S), acc=D.ptr(self._acc), gscale=float(gscale), step=float(step), step_ptr=D.ptr(step_ptr),
-            g_out=D.ptr(g_out), vadd=D.ptr(vadd), v_out=D.ptr(v_out), z_in=D.ptr(z_in), z_out=D.ptr(z_out))
+            g_out=D.ptr(g_out), vadd=D.ptr(vadd), v_out=D.ptr(v_out), z_in=D.ptr(z_in), z_out=D.ptr(z_out),
+            S2=D.ptr(self._S2) if (b is not None and os.environ.get('PNP_CDP_TWO_PASS', '0') != '1') else None)
         _lib.check(_lib.load().pnp_cdp_grad(C.byref(args), D.stream()))
 
     # ---- reference API -----------------------------------------------------------------------

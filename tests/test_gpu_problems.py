@@ -285,3 +285,34 @@ def test_deblur_direct_taps_match_fft_path(cuda, kernel):
     assert rel_l2(a.grad_stoch(z, mb), ref.grad_stoch(z, np.asarray(mb))) < 5e-6
     with pytest.raises(ValueError):
         Deblur(image=img, conv='direct', kernel=np.ones((H, H)), **kw)
+
+
+@pytest.mark.parametrize('H,W,L', [(64, 64, 4), (128, 32, 2), (256, 256, 4)])
+def test_cdp_two_points_in_one_launch_sequence(cuda, monkeypatch, H, W, L):
+    """The SVRG / SARAH difference g_B(z) - g_B(w) of the coded-diffraction model (not linear: two evaluations): with the
+    second scratch both points share the three passes' launches (pnp_cdp_grad, S2) -- bit-identical to the two-sequence
+    form (PNP_CDP_TWO_PASS=1), for a minibatch and for the full set, and the single-use selection is left cleared."""
+    import torch
+    from pnp_svrg_b200 import device as D
+    from pnp_svrg_b200.problems import PhaseRetrieval
+    np.random.seed(2)
+    p = PhaseRetrieval(image=synth_image(H, W, 1), H=H, W=W, model='cdp', n_masks=L, snr=20.)
+    dev = p._device
+    rng = np.random.default_rng(0)
+    z = D.to_lines(p.Xinit + 0.05 * rng.standard_normal(p.N), H, W, dev)
+    w = D.to_lines(p.Xinit, H, W, dev)
+    mu = D.to_lines(0.01 * rng.standard_normal(p.N), H, W, dev)
+    sel = torch.from_numpy(rng.choice(p.M, size=min(500, p.M // 4), replace=False).astype(np.int32)).to(dev)
+    outs = {}
+    for mode in ('0', '1'):
+        monkeypatch.setenv('PNP_CDP_TWO_PASS', mode)
+        for name, s in (('mb', sel), ('full', None)):
+            g, v, zo = torch.empty_like(z), torch.empty_like(z), torch.empty_like(z)
+            p._dev_grad_cdp(z, w, s, 1.0 / 500, 0.3, None, g, mu, v, z, zo)
+            torch.cuda.synchronize()
+            outs[(mode, name)] = (g.clone(), v.clone(), zo.clone())
+            assert int(p._mask.sum()) == 0
+    for name in ('mb', 'full'):
+        for a, b in zip(outs[('0', name)], outs[('1', name)]):
+            assert torch.equal(a, b), name
+    assert float(outs[('0', 'mb')][0].abs().max()) > 0
