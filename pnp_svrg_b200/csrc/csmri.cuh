@@ -171,6 +171,7 @@ k_lines_r2c(const float* __restrict__ a, const float* __restrict__ b, float2* __
     float* stage_a = smem + lines_stage_off<L, GP>();
     float* stage_b = stage_a + 2 * GP * L;
     const int g = threadIdx.x / T, t = threadIdx.x % T;
+    const int gbar = fft_group_bar<T>(g, GP);        // the barriers inside a transform involve its T threads only
     const int npairs = nlines >> 1;
     const int items = (npairs + GP - 1) / GP;
     const long long ibase = (long long)blockIdx.y * img_stride;
@@ -223,8 +224,8 @@ k_lines_r2c(const float* __restrict__ a, const float* __restrict__ b, float2* __
         }
         __syncthreads();                            // staging consumed -> refill it for the next item
         if (threadIdx.x == 0 && item + (int)gridDim.x < items) issue(item + gridDim.x);
-        fft_regs<L>(t, sb, x, tw);
-        if (FftPlan<L>::NS > 1) __syncthreads();
+        fft_regs<L>(t, sb, x, tw, gbar);
+        if (FftPlan<L>::NS > 1) fft_sync(gbar, T);
 #pragma unroll
         for (int i = 0; i < EPT; ++i) sb.put(FftIdx<L>::out(t, i), x[i]);
         __syncthreads();
@@ -291,6 +292,7 @@ k_cols_mask(float2* __restrict__ S, const unsigned char* __restrict__ bits,
     extern __shared__ __align__(128) float smem[];
     __shared__ __align__(8) unsigned long long bar;
     const int g = threadIdx.x / T, t = threadIdx.x % T;
+    const int gbar = fft_group_bar<T>(g, NC);        // the barriers inside a transform involve its T threads only
     const int img = blockIdx.y;
     const SmemBuf sb{smem + g * 2 * PL, smem + g * 2 * PL + PL};
     float2* stage = reinterpret_cast<float2*>(smem + cols_stage_off<L, NC>());      // NC columns of L complex
@@ -349,7 +351,7 @@ k_cols_mask(float2* __restrict__ S, const unsigned char* __restrict__ bits,
             unsigned char* cb = clear_bits + (long long)img * bits_img_stride + crow;
             for (int i = t; i < L / 16; i += T) reinterpret_cast<uint4*>(cb)[i] = make_uint4(0u, 0u, 0u, 0u);
         }
-        fft_regs<L>(t, sb, x, tw);
+        fft_regs<L>(t, sb, x, tw, gbar);
         // selection in registers, then reorder (same elements t + T*m) into the inverse's input order
         float2 y[EPT];
 #pragma unroll
@@ -359,8 +361,8 @@ k_cols_mask(float2* __restrict__ S, const unsigned char* __restrict__ bits,
                                        y2i + crow + kx);
             y[IX::in_slot(m)] = cswap(o);
         }
-        if (FftPlan<L>::NS > 1) __syncthreads();
-        fft_regs<L>(t, sb, y, tw);
+        if (FftPlan<L>::NS > 1) fft_sync(gbar, T);
+        fft_regs<L>(t, sb, y, tw, gbar);
         if (active) {
             float2* Sc = Si + crow;
 #pragma unroll
@@ -444,6 +446,7 @@ k_lines_c2r(const float2* __restrict__ S, int nlines, long long img_stride, floa
     float* stage_v = smem + lines_stage_off<L, GP>();      // vadd lines of the item
     float* stage_z = stage_v + 2 * GP * L;                  // z_in lines of the item
     const int g = threadIdx.x / T, t = threadIdx.x % T;
+    const int gbar = fft_group_bar<T>(g, GP);        // the barriers inside a transform involve its T threads only
     const int img = blockIdx.y;
     const int npairs = nlines >> 1;
     const int items = (npairs + GP - 1) / GP;
@@ -511,8 +514,8 @@ k_lines_c2r(const float2* __restrict__ S, int nlines, long long img_stride, floa
         float2 x[EPT];
 #pragma unroll
         for (int i = 0; i < EPT; ++i) x[i] = sb.get(IX::in(t, i));
-        __syncthreads();
-        fft_regs<L>(t, sb, x, tw);
+        fft_sync(gbar, T);
+        fft_regs<L>(t, sb, x, tw, gbar);
         if (staged) mbar_wait(&bar, parity);
         parity ^= 1;
         const int pair = item * GP + g;
@@ -585,6 +588,7 @@ k_update_prox(const float2* __restrict__ S, int nlines, float inv_n, float gscal
     __shared__ __align__(8) unsigned long long bars[4];         // z_in lines of round 0 / of the later rounds / ground truth
     float* lines = smem + lines_stage_off<L, GP>();             // resident: 2 * pairs_per_cta lines
     const int g = threadIdx.x / T, t = threadIdx.x % T;
+    const int fbar = fft_group_bar<T>(g, GP);        // the barriers inside a transform involve its T threads only
     const int npairs = nlines >> 1;
     const int first_pair = blockIdx.x * pairs_per_cta;
     int mine = npairs - first_pair;
@@ -670,8 +674,8 @@ k_update_prox(const float2* __restrict__ S, int nlines, float inv_n, float gscal
             __syncthreads();
 #pragma unroll
             for (int i = 0; i < EPT; ++i) x[i] = sb.get(IX::in(t, i));
-            __syncthreads();
-            fft_regs<L>(t, sb, x, tw);
+            fft_sync(fbar, T);
+            fft_regs<L>(t, sb, x, tw, fbar);
         } else {
             // no spectrum: the gradient term is exactly zero (first inner iteration of an SVRG epoch: z == w, so
             // g_B(z) - g_B(w) = 0 and v = mu); the transform of zeros is skipped, the update below is unchanged
@@ -735,8 +739,8 @@ k_update_prox(const float2* __restrict__ S, int nlines, float inv_n, float gscal
 #pragma unroll
                 for (int i = 0; i < EPT; ++i) x[i] = make_float2(0.f, 0.f);
             }
-            fft_regs<L>(t, sb, x, tw2);
-            if (FftPlan<L>::NS > 1) __syncthreads();
+            fft_regs<L>(t, sb, x, tw2, fbar);
+            if (FftPlan<L>::NS > 1) fft_sync(fbar, T);
 #pragma unroll
             for (int i = 0; i < EPT; ++i) sb.put(IX::out(t, i), x[i]);
             __syncthreads();

@@ -375,8 +375,23 @@ __device__ __forceinline__ void fft_reg_stage(int t, float2 (&x)[FftPlan<L, V>::
 // exchange between a stage of radix RA (prefix NSP) and the next stage of radix RB
 // WS: the T cooperating threads live in ONE warp (T <= 32): warp barriers instead of CTA barriers, so transforms of
 // different warps need not run in lock step (csrc/small.cuh)
+// barrier among the T threads of ONE transform: bar = 0 is the CTA barrier; bar > 0 a named barrier of `nthreads` threads (the
+// transforms of a CTA that holds several -- GP line pairs, NC columns -- then run out of lock step: one group's exchange
+// latency overlaps another group's butterflies instead of all 16 warps of the SM waiting at the same point)
+#ifndef PNP_GROUP_BAR
+#define PNP_GROUP_BAR 1
+#endif
+__device__ __forceinline__ void fft_sync(int bar, int nthreads) {
+    if (bar) asm volatile("bar.sync %0, %1;" ::"r"(bar), "r"(nthreads) : "memory");
+    else __syncthreads();
+}
+// named barrier of group g of a CTA with `groups` transforms of T threads each (0: use the CTA barrier)
+template <int T> __device__ __forceinline__ int fft_group_bar(int g, int groups) {
+    return (PNP_GROUP_BAR && T >= 64 && T % 32 == 0 && groups > 1 && groups <= 15) ? g + 1 : 0;
+}
+
 template <int L, int RA, int NSP, int RB, bool WS = false, int V = 0>
-__device__ __forceinline__ void fft_reg_exchange(int t, const SmemBuf& sb, float2 (&x)[FftPlan<L, V>::EPT]) {
+__device__ __forceinline__ void fft_reg_exchange(int t, const SmemBuf& sb, float2 (&x)[FftPlan<L, V>::EPT], int bar = 0) {
     constexpr int EPT = FftPlan<L, V>::EPT;
     constexpr int T = L / EPT;
 #pragma unroll
@@ -386,7 +401,7 @@ __device__ __forceinline__ void fft_reg_exchange(int t, const SmemBuf& sb, float
 #pragma unroll
         for (int r = 0; r < RA; ++r) sb.put(base + r * NSP, x[b * RA + r]);
     }
-    if (WS) __syncwarp(); else __syncthreads();
+    if (WS) __syncwarp(); else fft_sync(bar, T);
 #pragma unroll
     for (int b = 0; b < EPT / RB; ++b) {
         const int j = t + b * T;
@@ -398,17 +413,18 @@ __device__ __forceinline__ void fft_reg_exchange(int t, const SmemBuf& sb, float
 // In-register forward FFT.  The exchange buffer must be free on entry; on exit the LAST exchange's
 // reads may still be in flight in other threads: callers sync before writing the buffer again.
 template <int L, bool WS = false, int V = 0>
-__device__ __forceinline__ void fft_regs(int t, const SmemBuf& sb, float2 (&x)[FftPlan<L, V>::EPT], const FftTw<L, V>& tw) {
+__device__ __forceinline__ void fft_regs(int t, const SmemBuf& sb, float2 (&x)[FftPlan<L, V>::EPT], const FftTw<L, V>& tw,
+                                         int bar = 0) {
     using P = FftPlan<L, V>;
     static_assert(!WS || L / P::EPT <= 32, "warp-synchronous transform: the cooperating threads must fit one warp");
     fft_reg_stage<L, P::R0, 1, FftTw<L, V>::NB1, V>(t, x, tw.s1);
     if constexpr (P::NS >= 2) {
-        fft_reg_exchange<L, P::R0, 1, P::R1, WS, V>(t, sb, x);
+        fft_reg_exchange<L, P::R0, 1, P::R1, WS, V>(t, sb, x, bar);
         fft_reg_stage<L, P::R1, P::R0, FftTw<L, V>::NB1, V>(t, x, tw.s1);
     }
     if constexpr (P::NS >= 3) {
-        if (WS) __syncwarp(); else __syncthreads();   // reads of the first exchange done before the second writes
-        fft_reg_exchange<L, P::R1, P::R0, P::R2, WS, V>(t, sb, x);
+        if (WS) __syncwarp(); else fft_sync(bar, L / P::EPT);   // reads of the first exchange done before the second writes
+        fft_reg_exchange<L, P::R1, P::R0, P::R2, WS, V>(t, sb, x, bar);
         fft_reg_stage<L, P::R2, P::R0 * P::R1, FftTw<L, V>::NB2, V>(t, x, tw.s2);
     }
 }

@@ -27,7 +27,8 @@ def main():
             continue
         key = (cur, int(r[0]))
         a = agg.get(key, (0, 0, ''))
-        agg[key] = (a[0] + int(r[ii] or 0), a[1] + int(r[si] or 0), r[1].strip()[:100])
+        num = lambda v: int(v) if v not in ('', '-') else 0
+        agg[key] = (a[0] + num(r[ii]), a[1] + num(r[si]), r[1].strip()[:100])
     tot = sum(v[0] for v in agg.values())
     tots = max(sum(v[1] for v in agg.values()), 1)
     print('kernel: %s' % fn)
