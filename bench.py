@@ -45,7 +45,7 @@ def parse():
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--no-breakdown', action='store_true')
     ap.add_argument('--cpu-iters', type=int, default=0, help='inner iterations of the CPU sample (default: one epoch)')
-    ap.add_argument('--sections', default='small,sweep,sharded,configs_2_3',
+    ap.add_argument('--sections', default='small,sweep,sharded,configs_2_3,cnn',
                     help='extra sections of the line (bench_sections.py): the other BASELINE.json configurations; "" = none')
     return ap.parse_args()
 
@@ -298,6 +298,8 @@ def run_b200(a, cfg, rank, world, local_rank):
                     sec = BS.sharded(rank, world, dev)
                 elif name == 'configs_2_3':
                     sec = BS.configs_2_3(rank, world, dev)
+                elif name == 'cnn':
+                    sec = BS.cnn(rank, world, dev)
                 else:
                     raise ValueError('unknown section %r' % name)
             except Exception as e:                       # a failing extra must not take the headline number down

@@ -306,3 +306,62 @@ def configs_2_3(rank, world, dev):
         'workload': 'PnP-SAGA, Deblur 256x256 (25x25 Gaussian kernel image, scale 50 %), NLM prox (patch 4 -> 5, distance 5), '
                     'B=100, hist_size=10, public API, device-drawn minibatches'}
     return res
+
+
+# ------------------------------------------------------------------------------------------------ CNN prox by itself
+def cnn(rank, world, dev, size=2048, iters=5):
+    """DnCNN-17 prox (the prox of BASELINE configs 3 / 4 / 5) timed by itself at `size`^2 in the three precisions of
+    pnp_cnn_forward -- fp32 CUDA cores (exact-parity path), bf16 tensor cores (fast mode), bf16x3 tensor cores
+    (error-compensated) -- with CUDA events and the L2 flushed, and the agreement of the two tensor-core modes with the
+    fp32 path at 256^2 (same random weights, same input)."""
+    import json as _json
+    import torch
+    from conftest import synth_image
+    from pnp_svrg_b200 import device as D
+    from pnp_svrg_b200.denoisers import RealSN_DnCNNDenoiser
+    from pnp_svrg_b200.engine import ProxCtx
+    from test_gpu_cnn import _random_dncnn_sd
+    if rank != 0:
+        return None
+    sd = _random_dncnn_sd(17, True, False, seed=1)
+    peaks = {}
+    pk = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(pk):
+        peaks = _json.load(open(pk))
+    peak = float(peaks.get('bf16_tflops_sustained', 1417.2))
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    res = {'workload': 'DnCNN-17 (64 features, folded BatchNorm, random weights) forward on a %dx%d image: min/max normalisation, '
+                       '1->64, 15 x 64->64, 64->1 + residual + PSNR' % (size, size),
+           'flop_per_forward': 1108224.0 * size * size, 'peak_tflops': peak,
+           'peak_source': 'MEASURED_PEAKS.json bf16_tflops_sustained' if peaks else 'fallback (cuBLAS bf16 sustained on this pool)'}
+    outs = {}
+    for H, tag in ((256, 'err'), (size, 'time')):
+        z = D.to_lines(synth_image(H, H, 0).astype(np.float64) / 255, H, H, dev)
+        o = torch.empty_like(z)
+        for prec in ('fp32', 'bf16', 'bf16x3'):
+            den = RealSN_DnCNNDenoiser('DnCNN', 15, state_dict=sd, precision=prec)
+            ctx = ProxCtx(z, o, H, H)
+            den._dev_denoise(ctx)
+            torch.cuda.synchronize(dev)
+            if tag == 'err':
+                outs[prec] = o.clone()
+                continue
+            ts = []
+            for _ in range(2 if prec == 'fp32' else iters):
+                flush.fill_(1)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                den._dev_denoise(ctx)
+                e1.record()
+                torch.cuda.synchronize(dev)
+                ts.append(e0.elapsed_time(e1))
+            ms = float(np.median(ts))
+            mma = {'fp32': 0.0, 'bf16': 1.0, 'bf16x3': 3.0}[prec]
+            res[prec] = {'ms': ms, 'useful_tflops': res['flop_per_forward'] / ms / 1e9,
+                         'frac_of_bf16_peak_useful': res['flop_per_forward'] / ms / 1e9 / peak if mma else None,
+                         'frac_of_bf16_peak_issued': mma * res['flop_per_forward'] / ms / 1e9 / peak if mma else None}
+    ref = outs['fp32']
+    res['rel_l2_vs_fp32_at_256'] = {p: float((outs[p] - ref).norm() / ref.norm()) for p in ('bf16', 'bf16x3')}
+    res['note'] = ('frac_of_bf16_peak_issued counts the three tensor-core products of the error-compensated mode; useful = the '
+                   "network's own 1.108 MFLOP per pixel")
+    return res

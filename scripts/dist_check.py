@@ -17,8 +17,15 @@ import torch.distributed as dist
 
 def main():
     rank, world = int(os.environ['RANK']), int(os.environ['WORLD_SIZE'])
-    torch.cuda.set_device(int(os.environ['LOCAL_RANK']))
-    dist.init_process_group('nccl', device_id=torch.device('cuda', int(os.environ['LOCAL_RANK'])))
+    # PNP_DIST_BACKEND=gloo: the ranks may share one GPU (NCCL refuses two ranks on a device; gloo stages the CUDA tensor of
+    # the all-reduce through the host) -- the multi-rank code path on a one-GPU box (tests/test_gpu_sharded.py)
+    backend = os.environ.get('PNP_DIST_BACKEND', 'nccl')
+    local = int(os.environ['LOCAL_RANK']) % max(torch.cuda.device_count(), 1)
+    torch.cuda.set_device(local)
+    if backend == 'nccl':
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+    else:
+        dist.init_process_group(backend)
     from conftest import rel_l2, synth_image
     from pnp_svrg_b200.algorithms import pnp_svrg
     from pnp_svrg_b200.denoisers import TVDenoiser

@@ -81,3 +81,22 @@ def test_pr_split_column_pass_equals_the_unsplit_one(cuda):
             outs.append(g.cpu().numpy())
         for o in outs[1:]:
             assert rel_l2(o, outs[0]) < 1e-6
+
+
+def test_two_ranks_sharded_snapshot_allreduce(cuda):
+    """config 5 with TWO PROCESSES: every rank holds the measurements of its band of k-space rows, the snapshot gradients of
+    pnp_svrg are summed by torch.distributed.all_reduce (CSMRI._snapshot_allreduce), the iterates match the unsharded run
+    (scripts/dist_check.py, launched through torch.distributed.run).  NCCL when two GPUs are visible; on a one-GPU box both
+    ranks use cuda:0 and the collective runs over gloo (NCCL refuses two ranks on one device) -- same code path above it."""
+    import os
+    import subprocess
+    import sys
+    import torch
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    backend = 'nccl' if torch.cuda.device_count() >= 2 else 'gloo'
+    env = dict(os.environ, PNP_DIST_BACKEND=backend, PNP_DIST_SIZE='256')
+    cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', '2', '--master-addr', '127.0.0.1',
+           '--master-port', '29533', os.path.join(root, 'scripts', 'dist_check.py')]
+    r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, (r.stdout[-2000:], r.stderr[-2000:])
+    assert 'OK' in r.stdout and 'sharded snapshot over 2 ranks' in r.stdout, r.stdout[-1000:]
