@@ -182,26 +182,46 @@ __device__ __forceinline__ void tc_epilogue_tile64(unsigned t0, TcSmem* ctl, uns
         if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // staging buffer j is free again
         __syncwarp();
         if (dbg & 2) continue;
-        uint4 pk[2], pl[2];
-        __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(pk);
-        __nv_bfloat162* hl = reinterpret_cast<__nv_bfloat162*>(pl);
+        unsigned hw[8], lw[8];                           // 16 bf16 channels as 8 packed words: hi plane, lo plane (SPLIT)
+#pragma unroll
+        for (int k = 0; k < 8; ++k) lw[k] = 0u;
+        // Two channels per step on the packed fp32 pipe (add.f32x2: the three additions of a value cost 1.5 instructions), and
+        // in the ReLU case the activation is the .relu of the bf16 conversion (cvt.rn.relu.bf16x2.f32) instead of a multiply and
+        // a max per value: the epilogue's instructions, not the MMAs, fill most of the issue slots of a tile period.  The
+        // two activation forms are separate loops under one uniform branch (if-converted, both would issue).
+        float2 vv[8];
 #pragma unroll
         for (int i = 0; i < 16; i += 2) {
-            float o2[2];
+            float2 up2, dn2;
+            up2.x = __shfl_up_sync(0xffffffffu, tm[i], 1);                       // T_-1 of row - 1
+            up2.y = __shfl_up_sync(0xffffffffu, tm[i + 1], 1);
+            dn2.x = __shfl_down_sync(0xffffffffu, tp[i], 1);                     // T_+1 of row + 1
+            dn2.y = __shfl_down_sync(0xffffffffu, tp[i + 1], 1);
+            vv[i >> 1] = __fadd2_rn(__fadd2_rn(up2, make_float2(tz[i], tz[i + 1])), __fadd2_rn(dn2, make_float2(sh[i], sh[i + 1])));
+        }
+        if (!SPLIT && relu) {
 #pragma unroll
-            for (int u = 0; u < 2; ++u) {
-                const float up = __shfl_up_sync(0xffffffffu, tm[i + u], 1);      // T_-1 of row - 1
-                const float dn = __shfl_down_sync(0xffffffffu, tp[i + u], 1);    // T_+1 of row + 1
-                const float v = (up + tz[i + u]) + (dn + sh[i + u]);
-                o2[u] = relu ? fmaxf(v, 0.f) : fmaxf(v, v * slope);              // leaky ReLU needs slope <= 1
-            }
-            h[i >> 1] = __floats2bfloat162_rn(o2[0], o2[1]);
-            if (SPLIT) {
-                const float2 hf2 = __bfloat1622float2(h[i >> 1]);
-                hl[i >> 1] = __floats2bfloat162_rn(o2[0] - hf2.x, o2[1] - hf2.y);
+            for (int k = 0; k < 8; ++k) asm volatile("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(hw[k]) : "f"(vv[k].y), "f"(vv[k].x));
+        } else {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const float o0 = relu ? fmaxf(vv[k].x, 0.f) : fmaxf(vv[k].x, vv[k].x * slope);     // leaky ReLU needs slope <= 1
+                const float o1 = relu ? fmaxf(vv[k].y, 0.f) : fmaxf(vv[k].y, vv[k].y * slope);
+                const __nv_bfloat162 hb = __floats2bfloat162_rn(o0, o1);
+                hw[k] = (unsigned)__bfloat16_as_ushort(hb.x) | ((unsigned)__bfloat16_as_ushort(hb.y) << 16);
+                if (SPLIT) {
+                    const float2 hf2 = __bfloat1622float2(hb);
+                    const __nv_bfloat162 lb = __floats2bfloat162_rn(o0 - hf2.x, o1 - hf2.y);
+                    lw[k] = (unsigned)__bfloat16_as_ushort(lb.x) | ((unsigned)__bfloat16_as_ushort(lb.y) << 16);
+                }
             }
         }
-        if (pad) pk[0] = pk[1] = pl[0] = pl[1] = make_uint4(0u, 0u, 0u, 0u);
+        uint4 pk[2], pl[2];
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            pk[k] = pad ? make_uint4(0u, 0u, 0u, 0u) : make_uint4(hw[4 * k], hw[4 * k + 1], hw[4 * k + 2], hw[4 * k + 3]);
+            pl[k] = pad ? make_uint4(0u, 0u, 0u, 0u) : make_uint4(lw[4 * k], lw[4 * k + 1], lw[4 * k + 2], lw[4 * k + 3]);
+        }
         if (SPLIT) {
             // hi through staging buffer 0, lo through buffer 1, both chunks: a buffer is rewritten once at most one store
             // (the other buffer's) may still be reading
