@@ -181,8 +181,15 @@ class Engine:
             # native look-ahead queue: one single-threaded run of the C sampler per draw, several draws in flight
             # (a 100k-index draw takes 0.3-0.6 ms on one core), each written into the pinned buffer its host->device
             # copy reads; draw_host() stages the next one with a single native call.  One pinned allocation, sliced.
-            ahead = int(os.environ.get('PNP_HOST_AHEAD', '0')) or max(2, min(8, ncpu // 2))
-            depth = ahead + max(2, int(os.environ.get('PNP_HOST_RING_EXTRA', '12')))     # how far the host may run ahead
+            # worker threads = draws in flight: a draw is ~0.1 ms of one core (ranks only), four workers make 40k draws/s
+            # against the ~16k/s a B200 consumes at 2048^2; eight measured SLOWER through the public call (0.86-0.88 x the
+            # device-resident rate vs 0.95-0.98 x with four: profiles/r02_e2e_workers.txt)
+            ahead = int(os.environ.get('PNP_HOST_AHEAD', '0')) or max(2, min(4, ncpu // 2))
+            # how far the host may run ahead.  A staging buffer is reused only after the copy that read it, and the copies of
+            # an epoch wait on the device for the epoch two before it: with 12 extra buffers (two epochs of T2 = 10 draws) the
+            # host staged every epoch late and the epoch graph waited 64 us for its index sets (66.4 vs 61.7 us per inner
+            # iteration at 2048^2, scripts/prof_epoch_host.py); 32 keeps four epochs in hand
+            depth = ahead + max(2, int(os.environ.get('PNP_HOST_RING_EXTRA', '32')))
             # (page-locked allocations cost milliseconds: the ring is kept on the problem object between calls; the
             # previous owner's queue has been closed by its result(), nothing writes into it any more)
             ring = D.pinned_buffer(('draw_ring', id(problem)), (depth, self.B + n_extra_ints), torch.int32)
