@@ -267,13 +267,18 @@ def configs_2_3(rank, world, dev):
     if rank != 0:
         return None
 
-    def timed(fn, iters):
+    def timed(fn, iters, reps=3):
+        # these loops are ~0.1 s of mostly host-driven launches: best of three calls (one slow call -- a cold core, another
+        # process on the box -- halved the figure in single-shot runs)
         fn(max(iters // 4, 1))
-        torch.cuda.synchronize(dev)
-        t0 = time.perf_counter()
-        out = fn(iters)
-        torch.cuda.synchronize(dev)
-        return iters / (time.perf_counter() - t0), out
+        best, out = 0.0, None
+        for _ in range(reps):
+            torch.cuda.synchronize(dev)
+            t0 = time.perf_counter()
+            out = fn(iters)
+            torch.cuda.synchronize(dev)
+            best = max(best, iters / (time.perf_counter() - t0))
+        return best, out
     res = {}
     H = 256
     img = synth_image(H, H, 0)
