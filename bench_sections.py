@@ -144,6 +144,14 @@ def sweep(rank, world, dev, iters=200, size=256, batch=120, with_cpu=True, pipel
         t = torch.tensor([dt], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dt = float(t.item())
+    timing = getattr(batch_runner, 'timing', None)
+    if timing and world > 1:
+        t = torch.tensor([timing['groups_seconds'], timing['gather_seconds']], dtype=torch.float64, device=dev)
+        lo = t.clone()
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        timing = {'groups_seconds_max': float(t[0]), 'groups_seconds_min': float(lo[0]), 'gather_seconds_max': float(t[1]),
+                  'gather_seconds_min': float(lo[1])}
     if rank != 0:
         return None
     ok = [r for r in recs if 'error' not in r]
@@ -153,6 +161,9 @@ def sweep(rank, world, dev, iters=200, size=256, batch=120, with_cpu=True, pipel
            'value': len(recs) / dt, 'unit': 'recon/s', 'jobs': len(recs), 'failed': len(recs) - len(ok), 'seconds': dt, 'n_gpus': world,
            'inner_iterations_per_s': len(recs) * iters / dt,
            'mean_psnr_gain_db': float(np.mean([r['psnr_final'] - r['psnr_init'] for r in ok])) if ok else None}
+    if timing:
+        out['rank_timing'] = dict(timing, note='per rank: wall clock of its own groups (build, run, read-back) and of the record gather '
+                                               '(one all-gather; includes waiting for the slowest rank)')
     if pipelined:
         out['construct_seconds'] = batch_runner.build_seconds
         out['construct_note'] = ('host time rank 0 spent inside batched.csmri_device_batch during the timed sweep: masks, measurements, Xinit and '

@@ -278,8 +278,11 @@ template <int L, int NC> __host__ __device__ constexpr int cols_stage_off() { re
 // one item ahead.  Columns 1..hp-1 are element-wise in the spectrum: forward FFT, selection and
 // inverse FFT happen in registers + the exchange buffer.  Column 0 (DC + i*Nyquist packed) needs
 // C[kx] and C[-kx] together and is done by the last CTA after its loop.
+#ifndef PNP_COLS_MINB
+#define PNP_COLS_MINB 4
+#endif
 template <int L, int NC>
-__global__ void __launch_bounds__(NC * (L / FftPlan<L>::EPT), (NC * (L / FftPlan<L>::EPT) >= 256 ? 2 : 4))
+__global__ void __launch_bounds__(NC * (L / FftPlan<L>::EPT), (NC * (L / FftPlan<L>::EPT) >= 256 ? 2 : PNP_COLS_MINB))
 k_cols_mask(float2* __restrict__ S, const unsigned char* __restrict__ bits,
             const float2* __restrict__ Y1, const float2* __restrict__ Y2,
             const float2* __restrict__ Y1n, const float2* __restrict__ Y2n,

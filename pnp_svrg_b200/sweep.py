@@ -264,15 +264,20 @@ def run_partitioned_batched(jobs, batch_runner, rank=0, world=1, batch=56, gathe
     mine = partition(jobs, rank, world)
     local = []
     if hasattr(batch_runner, 'submit'):
+        t0 = time.time()
         for k in range(0, len(mine), batch):
             recs = batch_runner.submit(mine[k:k + batch])
             if recs:
                 local.extend(recs)
         local.extend(batch_runner.drain())
+        t1 = time.time()
         for r in local:
             r['rank'] = rank
         if gather and world > 1:
             local = _gather_records(jobs, local, rank, world)
+        # where this rank's wall clock went: its own groups (build + run + read-back) / the record gather (incl. waiting for
+        # the slowest rank)
+        batch_runner.timing = dict(groups_seconds=t1 - t0, gather_seconds=time.time() - t1)
         return sorted(local, key=lambda r: r['id'])
     for k in range(0, len(mine), batch):
         group = mine[k:k + batch]
@@ -294,24 +299,27 @@ def _gather_records(jobs, local, rank, world):
     message fall back to the pickling collective (rare, and strings do not fit a tensor)."""
     import torch
     import torch.distributed as dist
-    flag = torch.tensor([int(any('error' in r for r in local))], dtype=torch.int32,
-                        device='cuda' if dist.get_backend() == 'nccl' else 'cpu')
-    dist.all_reduce(flag, op=dist.ReduceOp.MAX)
-    if int(flag.item()):
+    dev = 'cuda' if dist.get_backend() == 'nccl' else 'cpu'
+    cap = (len(jobs) + world - 1) // world
+    # one collective: row `cap` carries this rank's "some record holds an error message" flag, so the common case needs no
+    # separate all-reduce (and no device -> host read) before the gather
+    bad = any('error' in r for r in local)
+    rows = np.full((cap + 1, 5), -1.0)
+    if local and not bad:
+        rows[:len(local)] = [(r['id'], r['psnr_init'], r['psnr_final'], r['seconds'], r['rank']) for r in local]
+    rows[cap, 0] = 1.0 if bad else 0.0
+    t = torch.from_numpy(rows).to(dev)
+    allrows = torch.empty((world,) + tuple(t.shape), dtype=t.dtype, device=dev)
+    dist.all_gather_into_tensor(allrows.view(-1, 5), t)
+    allrows = allrows.cpu().numpy()
+    if (allrows[:, cap, 0] > 0).any():
         parts = [None] * world
         dist.all_gather_object(parts, local)
         return [r for part in parts for r in part]
-    cap = (len(jobs) + world - 1) // world
-    t = torch.full((cap, 5), -1.0, dtype=torch.float64)
-    for k, r in enumerate(local):
-        t[k] = torch.tensor([r['id'], r['psnr_init'], r['psnr_final'], r['seconds'], r['rank']], dtype=torch.float64)
-    t = t.to(flag.device)
-    parts = [torch.empty_like(t) for _ in range(world)]
-    dist.all_gather(parts, t)
     by_id = {j['id']: j for j in jobs}
     proto = local[0] if local else {}
     out = []
-    for row in torch.cat(parts).cpu().numpy():
+    for row in allrows[:, :cap].reshape(-1, 5):
         if row[0] < 0:
             continue
         j = by_id[int(row[0])]
