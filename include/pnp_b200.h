@@ -65,7 +65,11 @@ typedef struct {
     const float* z_in;
     float* z_out;
     int phases;                   /* 0 = all three passes; else bit0 lines r2c, bit1 columns+selection,
-                                     bit2 lines c2r + epilogue (used to time the passes one by one) */
+                                     bit2 lines c2r + epilogue (used to time the passes one by one).
+                                     phases = 4 in the update form (vadd, z_in, z_out; no g_out / v_out) accepts
+                                     S = NULL: a zero spectrum, z_out = z_in - step * vadd without the transform --
+                                     the first inner iteration of a PnP-SVRG epoch (algorithms/pnp_svrg.py:53 with
+                                     z == w), same bits as running the three passes on z - w = 0 */
     int clear_bits;               /* != 0: the column pass zeroes `bits` after using it (single-use minibatch
                                      selection; the next pnp_csmri_sel_* call then needs clear = 0) */
     /* Optional: build the minibatch selection INSIDE pass 1 (needs phases bit0), by every thread of the pass while

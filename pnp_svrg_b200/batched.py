@@ -255,6 +255,8 @@ class BatchedSVRG:
         self.outer = 0
         self.fused_prox = True
         self.whole_run_graph = False     # sweeps set it: capture all iterations of a run as one graph (see _capture_run)
+        # the first inner iteration of an epoch skips its transform passes (whole-run graphs; PNP_BATCH_SKIP_FIRST=0: off, for A/B)
+        self.skip_first = os.environ.get('PNP_BATCH_SKIP_FIRST', '1') != '0'
         # 128^2 / 256^2, and no more problems than clusters fit the device (15 on a B200): the whole run is ONE launch, one
         # thread-block cluster per problem (csrc/small.cuh).  Larger batches would run in waves of 15 clusters on 120 of
         # the 148 SMs; the three-pass kernels with the batch dimension (and two batches in flight, sweep.DeviceBatchPipeline)
@@ -359,7 +361,8 @@ class BatchedSVRG:
     # ---- the launches -------------------------------------------------------------------------
     def _grad(self, a, b, bits, with_y, stream, phases=0, **kw):
         args = _lib.CsmriGradArgs(
-            H=self.H, W=self.W, batch=self.nb, a=D.ptr(a), b=D.ptr(b), S=D.ptr(self.S), bits=D.ptr(bits),
+            H=self.H, W=self.W, batch=self.nb, a=D.ptr(a), b=D.ptr(b), S=D.ptr(self.S) if kw.get('spectrum', True) else None,
+            bits=D.ptr(bits),
             Y1=D.ptr(self.Y1) if with_y else None, Y2=D.ptr(self.Y2) if with_y else None,
             Y1n=D.ptr(self.Y1n) if with_y else None, Y2n=D.ptr(self.Y2n) if with_y else None,
             gscale=float(kw.get('gscale', 1.0)), gscale_ptr=D.ptr(kw.get('gscale_ptr')), step=0.0,
@@ -373,9 +376,15 @@ class BatchedSVRG:
         self._grad(self.z, None, self.bits_full, True, self.sptr, gscale_ptr=self.inv_m0, g_out=self.mu)
         self.check(self.lib.pnp_copy_f32(D.ptr(self.w), D.ptr(self.z), self.nb * self.N, self.sptr))
 
-    def _inner(self):
+    def _inner(self, first_of_epoch=False):
         slot, draws = self.counters[0:1], self.counters[2:3]
         gk = dict(gscale=1.0 / self.B, vadd=self.mu, step_ptr=self.step, z_in=self.z, z_out=self.z, clear=True)
+        if first_of_epoch and self.skip_first:
+            # z == w bit for bit (the snapshot has just copied it): g_B(z) - g_B(w) is exactly zero, v = mu -- the selection,
+            # the forward line pass and the column pass are skipped, the update pass runs without a spectrum (same bits as
+            # the three passes on z - w = 0; the draw counter advances as usual, so the later minibatches are unchanged)
+            self._grad(self.z, self.w, self.bits_mb, False, self.sptr, phases=4, spectrum=False, **gk)
+            return self._prox(slot)
         # minibatch selection (device sampler, keyed by problem index) in parallel with the line pass
         self.ev_fork.record(self.stream)
         self.side.wait_event(self.ev_fork)
@@ -386,6 +395,9 @@ class BatchedSVRG:
         self._grad(self.z, self.w, self.bits_mb, False, self.sptr, phases=1, **gk)
         self.stream.wait_event(self.ev_join)
         self._grad(self.z, self.w, self.bits_mb, False, self.sptr, phases=6, **gk)
+        self._prox(slot)
+
+    def _prox(self, slot):
         if self.fused_prox:
             rc = self.lib.pnp_prox_wavelet_fused(D.ptr(self.z), D.ptr(self.z), self.H, self.W, self.nb, D.ptr(self.sig_log),
                                                  self.sigma_modifier, 0.0, D.ptr(self.xrec), D.ptr(self.mse_log), D.ptr(slot), self.sptr)
@@ -425,8 +437,8 @@ class BatchedSVRG:
                 while done < n_inner:
                     self._snapshot()
                     k = min(self.T2, n_inner - done)
-                    for _ in range(k):
-                        self._inner()
+                    for i in range(k):
+                        self._inner(first_of_epoch=(i == 0))
                     done += k
         finally:
             rc = self.lib.pnp_graph_end(self.sptr, C.byref(exec_))

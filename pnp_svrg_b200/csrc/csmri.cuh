@@ -471,8 +471,8 @@ k_lines_c2r(const float2* __restrict__ S, int nlines, long long img_stride, floa
         for (int n = 0; n < NQ; ++n) {
             const int i = threadIdx.x + n * GP * T;
             const int gg = i % GP, k = i / GP;
-            q[n] = (item * GP + gg < npairs && k >= row_lo && k < row_hi) ? ldg_stream(S4 + (long long)k * W2 + item * GP + gg)
-                                                                          : make_float4(0.f, 0.f, 0.f, 0.f);
+            q[n] = (S && item * GP + gg < npairs && k >= row_lo && k < row_hi) ? ldg_stream(S4 + (long long)k * W2 + item * GP + gg)
+                                                                               : make_float4(0.f, 0.f, 0.f, 0.f);
         }
     };
     auto issue = [&](int item) {                    // one thread: TMA bulk copies of the epilogue operands
@@ -497,28 +497,36 @@ k_lines_c2r(const float2* __restrict__ S, int nlines, long long img_stride, floa
     tw.init(t);
     for (; item < items; item += gridDim.x) {
         if (staged && threadIdx.x == 0) issue(item);
-        // X[k] = A[k] + i B[k] of the two lines, written re/im swapped for the inverse transform
-#pragma unroll
-        for (int n = 0; n < NQ; ++n) {
-            const int i = threadIdx.x + n * GP * T;
-            const int gg = i % GP, k = i / GP;
-            const SmemBuf sg{smem + gg * GS, smem + gg * GS + PL};
-            const float4 q = qn[n];                                // A = (q.x, q.y) line 2p ; B = (q.z, q.w) line 2p+1
-            if (k == 0) {
-                sg.put(0, make_float2(q.z, q.x));                  // X[0]   = A_dc + i B_dc   (swapped)
-                sg.put(L / 2, make_float2(q.w, q.y));              // X[L/2] = A_ny + i B_ny   (swapped)
-            } else {
-                sg.put(k, make_float2(q.y + q.z, q.x - q.w));      // X[k]   = A + iB
-                sg.put(L - k, make_float2(q.z - q.y, q.x + q.w));  // X[L-k] = conj A + i conj B
-            }
-        }
-        if (item + (int)gridDim.x < items) load_spec(item + gridDim.x, qn);
-        __syncthreads();
         float2 x[EPT];
+        if (UPD && !S) {
+            // no spectrum (inner-iteration form only): the gradient term is exactly zero -- first inner iteration of an
+            // SVRG epoch, z == w bit for bit, so g_B(z) - g_B(w) = 0 and v = vadd (k_update_prox does the same); the
+            // transform of zeros is skipped, the epilogue below is unchanged
 #pragma unroll
-        for (int i = 0; i < EPT; ++i) x[i] = sb.get(IX::in(t, i));
-        fft_sync(gbar, T);
-        fft_regs<L>(t, sb, x, tw, gbar);
+            for (int i = 0; i < EPT; ++i) x[i] = make_float2(0.f, 0.f);
+        } else {
+            // X[k] = A[k] + i B[k] of the two lines, written re/im swapped for the inverse transform
+#pragma unroll
+            for (int n = 0; n < NQ; ++n) {
+                const int i = threadIdx.x + n * GP * T;
+                const int gg = i % GP, k = i / GP;
+                const SmemBuf sg{smem + gg * GS, smem + gg * GS + PL};
+                const float4 q = qn[n];                                // A = (q.x, q.y) line 2p ; B = (q.z, q.w) line 2p+1
+                if (k == 0) {
+                    sg.put(0, make_float2(q.z, q.x));                  // X[0]   = A_dc + i B_dc   (swapped)
+                    sg.put(L / 2, make_float2(q.w, q.y));              // X[L/2] = A_ny + i B_ny   (swapped)
+                } else {
+                    sg.put(k, make_float2(q.y + q.z, q.x - q.w));      // X[k]   = A + iB
+                    sg.put(L - k, make_float2(q.z - q.y, q.x + q.w));  // X[L-k] = conj A + i conj B
+                }
+            }
+            if (item + (int)gridDim.x < items) load_spec(item + gridDim.x, qn);
+            __syncthreads();
+#pragma unroll
+            for (int i = 0; i < EPT; ++i) x[i] = sb.get(IX::in(t, i));
+            fft_sync(gbar, T);
+            fft_regs<L>(t, sb, x, tw, gbar);
+        }
         if (staged) mbar_wait(&bar, parity);
         parity ^= 1;
         const int pair = item * GP + g;

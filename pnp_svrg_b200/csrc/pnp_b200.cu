@@ -503,7 +503,10 @@ int pnp_csmri_grad(const pnp_csmri_grad_args* args, void* stream) {
     const pnp_csmri_grad_args& a = *args;
     if (!pow2_ok(a.H) || !pow2_ok(a.W)) return fail(PNP_ERR_ARG, "H=%d W=%d must be powers of two in [32, 4096]", a.H, a.W);
     if (a.batch < 1 || a.batch > 65535) return fail(PNP_ERR_ARG, "batch=%d out of range", a.batch);
-    if (!a.a || !a.S || !a.bits) return fail(PNP_ERR_ARG, "a, S and bits must be non-null");
+    // S may be null for the update pass alone (phases == 4 with vadd, z_in, z_out and nothing else written): the gradient
+    // term is then exactly zero (first inner iteration of an SVRG epoch, see pnp_b200.h)
+    const bool upd_only = a.phases == 4 && a.vadd && a.z_in && a.z_out && !a.g_out && !a.v_out;
+    if (!a.a || !a.bits || (!a.S && !upd_only)) return fail(PNP_ERR_ARG, "a, S and bits must be non-null");
     if ((a.Y1 == nullptr) != (a.Y2 == nullptr) || (a.Y1 == nullptr) != (a.Y1n == nullptr) ||
         (a.Y1 == nullptr) != (a.Y2n == nullptr))
         return fail(PNP_ERR_ARG, "Y1, Y2, Y1n, Y2n must be all null or all non-null");

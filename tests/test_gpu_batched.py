@@ -190,3 +190,31 @@ def test_pipeline_builds_groups_inside_the_engines(cuda):
     with pytest.raises(ValueError):
         SW.run_partitioned_batched(jobs[:8], pipe, 0, 1, batch=4, gather=False)
     pipe.close()
+
+
+@pytest.mark.parametrize('H', [64, 256])
+def test_whole_run_graph_skipping_the_first_transforms_of_an_epoch_is_bit_identical(cuda, H):
+    """Sweeps capture a whole run as one graph in which the first inner iteration of every epoch (z == w bit for bit,
+    algorithms/pnp_svrg.py:53: the stochastic term is exactly zero) runs the update pass WITHOUT a spectrum instead of the
+    selection and the three transform passes (pnp_csmri_grad, phases = 4, S = NULL).  Same bits as the full sequence,
+    same minibatches afterwards (the draw counter advances either way)."""
+    from pnp_svrg_b200.batched import BatchedSVRG, csmri_host_spec
+    specs = [csmri_host_spec(synth_image(H, H, s), H, H, a, snr, rng=np.random.RandomState(s)) for s, a, snr in
+             [(0, 0.3, 20.), (1, 0.5, 10.), (2, 0.7, 30.), (3, 0.4, 25.), (4, 0.9, 15.)]]
+    B = 200
+    etas = [min(0.15 * s['M0'], 3.0 * B) for s in specs]
+    outs = []
+    for skip in (False, True):
+        b = BatchedSVRG(specs, T2=10, mini_batch_size=B, etas=etas, seed=3)
+        b.use_small = False                       # the three-pass kernels (what batches beyond the cluster kernel's capacity run)
+        b.whole_run_graph = True
+        b.skip_first = skip
+        b.run(23)
+        outs.append(b.results())
+        b.close()
+    assert np.all(np.isfinite(outs[0]['z']))
+    assert np.array_equal(outs[0]['z'], outs[1]['z'])
+    assert np.array_equal(outs[0]['psnr'], outs[1]['psnr'])
+    # (the logged sigma is a sum of per-line estimates by double-precision atomics: equal up to the order of the additions)
+    assert np.allclose(outs[0]['sigma_est'], outs[1]['sigma_est'], rtol=1e-12, atol=0.0)
+    assert np.all(outs[1]['psnr'][-1] > outs[1]['psnr'][0])
