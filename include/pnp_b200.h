@@ -325,7 +325,8 @@ int pnp_prox_wavelet_fused(const float* z_in, float* z_out, int H, int W, int ba
  * S = NULL means a zero spectrum: z_out = Denoise(z_in - step * vadd) without the inverse transforms.  That is the
  * first inner iteration of every PnP-SVRG epoch (algorithms/pnp_svrg.py:53 with z == w: g_B(z) - g_B(w) is exactly 0,
  * so the three transform passes of that iteration are skipped; same bits as running them on zeros).
- * barrier_ws (optional): two zero-initialised 32-bit words owned by the caller.  When given, the kernel is launched
+ * barrier_ws (optional): two zero-initialised 32-bit words (8-byte aligned: one 64-bit arrival counter) owned by the caller
+ * and used with ONE image size only.  When given, the kernel is launched
  * normally and synchronises its CTAs (all co-resident: one per SM) with a software barrier on these words instead of a
  * cooperative launch -- the caller guarantees that no other kernel using such a barrier runs on the device at the same
  * time -- and `chain` != 0 adds programmatic dependent launch (see PNP_FLAG_CHAIN). */

@@ -197,23 +197,24 @@ __device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wa
 __device__ __forceinline__ void griddep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 // Grid-wide barrier of a persistent kernel whose CTAs are all co-resident (grid <= SMs x occupancy; the caller
-// guarantees that no other kernel spinning on such a barrier shares the device).  ws[0]: arrivals, ws[1]: generation;
-// both zero before the first use, left consistent for the next one.
+// guarantees that no other kernel spinning on such a barrier shares the device).  ws: two 32-bit words used as ONE
+// 64-bit arrival counter that only ever grows (zero before the first use; 2^64 arrivals never wrap): arrival k belongs
+// to generation k / nblocks, and a CTA leaves when the counter has reached the end of its generation.  The workspace
+// therefore belongs to ONE grid size (every launch that uses it has the same nblocks, so the counter is a multiple of
+// nblocks between launches).  On the critical path of the last arriver there is one atomic on its way to L2 and one
+// poll of the waiters -- the first version (arrival count + generation word: read the generation, add, reset, fence,
+// release, poll) had four dependent L2 round trips there and was slower than the cooperative launch's barrier.
 __device__ __forceinline__ void sw_grid_sync(unsigned* ws, unsigned nblocks) {
     __syncthreads();
     if (threadIdx.x == 0) {
-        unsigned gen, g;
-        asm volatile("ld.acquire.gpu.u32 %0, [%1];" : "=r"(gen) : "l"(ws + 1) : "memory");
+        unsigned long long* c = reinterpret_cast<unsigned long long*>(ws);
         __threadfence();
-        if (atomicAdd(ws, 1u) == nblocks - 1) {
-            atomicExch(ws, 0u);
-            __threadfence();
-            asm volatile("st.release.gpu.u32 [%0], %1;" ::"l"(ws + 1), "r"(gen + 1) : "memory");
-        } else {
-            do {
-                asm volatile("ld.acquire.gpu.u32 %0, [%1];" : "=r"(g) : "l"(ws + 1) : "memory");
-            } while (g == gen);
-        }
+        const unsigned long long ticket = atomicAdd(c, 1ull);
+        const unsigned long long target = (ticket / nblocks + 1ull) * nblocks;
+        unsigned long long v;
+        do {
+            asm volatile("ld.acquire.gpu.u64 %0, [%1];" : "=l"(v) : "l"(c) : "memory");
+        } while (v < target);
     }
     __syncthreads();
 }
