@@ -327,13 +327,7 @@ class BatchedSVRG:
         if len(images) != self.nb or self.sup_stride != self.N:
             raise ValueError('build_from_images needs %d images and an engine created from a device-built batch' % self.nb)
         hits = [_device_lines(im, self.H, self.W, self.dev) for im in images]
-        if getattr(self, '_build_work', None) is None:
-            self._build_work = torch.empty(int(self.lib.pnp_csmri_build_batch_workspace(self.H, self.W, self.nb)), dtype=torch.uint8,
-                                           device=self.dev)
-            self._build_ps = torch.empty((2, self.nb), dtype=torch.float32, device=self.dev)
-            self._build_ps_host = torch.empty((2, self.nb), dtype=torch.float32).pin_memory()
-            self._build_ps_ev = None
-            self.sigma_dev = torch.empty(self.nb, dtype=torch.float32, device=self.dev)
+        self.prepare_build()
         if self._build_ps_ev is not None:
             self._build_ps_ev.synchronize()                 # the copy that last read the pinned parameters (long done)
         self._build_ps_host[0] = torch.from_numpy(np.asarray(sample_probs, dtype=np.float32))
@@ -357,6 +351,17 @@ class BatchedSVRG:
         self.data_range = np.array([1.0 if h[2] else 2.0 for h in hits])
         self.slots_used = 0
         self.outer = 0
+
+    def prepare_build(self):
+        """workspace, parameter buffers (one of them pinned host memory: milliseconds to allocate) of build_from_images;
+        sweeps call it when they create an engine, so that no group of a sweep pays for it"""
+        if getattr(self, '_build_work', None) is None:
+            self._build_work = torch.empty(int(self.lib.pnp_csmri_build_batch_workspace(self.H, self.W, self.nb)), dtype=torch.uint8,
+                                           device=self.dev)
+            self._build_ps = torch.empty((2, self.nb), dtype=torch.float32, device=self.dev)
+            self._build_ps_host = torch.empty((2, self.nb), dtype=torch.float32).pin_memory()
+            self._build_ps_ev = None
+            self.sigma_dev = torch.empty(self.nb, dtype=torch.float32, device=self.dev)
 
     # ---- the launches -------------------------------------------------------------------------
     def _grad(self, a, b, bits, with_y, stream, phases=0, **kw):
