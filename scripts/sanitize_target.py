@@ -34,3 +34,18 @@ b.run(6)
 b.results()
 b.close()
 print('sanitize target finished')
+# whole-run graph of the three-pass batched engine: first inner iteration of an epoch = update pass without a spectrum
+b = BatchedSVRG(specs, T2=3, mini_batch_size=100, etas=[200.] * 3)
+b.use_small = False
+b.whole_run_graph = True
+b.run(7)
+b.results()
+b.close()
+# software grid barrier of the tail (whole-epoch graph at a size that takes the single-launch tail)
+os.environ['PNP_SW_BARRIER'] = '1'
+np.random.seed(1)
+p5 = CSMRI(image=synth_image(512, 512, 3), H=512, W=512, sample_prob=0.3, snr=20.)
+pnp_svrg(p5, TVDenoiser(), eta=6000., tt=1e9, T2=3, mini_batch_size=5000, verbose=False, converge_check=False, max_iters=6,
+         vr_mode='paper', mb_source='device', fast=True)
+os.environ['PNP_SW_BARRIER'] = '0'
+print('sanitize target (round-2 additions) finished')
