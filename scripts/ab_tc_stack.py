@@ -1,5 +1,7 @@
 """One-launch conv stack (small images, bf16 tensor-core path): per-tile dataflow synchronisation between the layers
-(default) vs a grid barrier per layer (pnp_debug_set(1, 64)): identical outputs, forward time of DnCNN-17.
+vs a grid barrier per layer (pnp_debug_set(1, 64)): identical outputs, forward time of DnCNN-17.  The dataflow form was
+measured slower and is NOT in the tree: apply scripts/experiments/conv_stack_dataflow_sync.patch and rebuild first (without it
+both arms run the grid-barrier kernel).
     python scripts/ab_tc_stack.py"""
 import json, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))

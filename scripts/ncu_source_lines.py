@@ -3,18 +3,22 @@
 argv[2] = number of lines to list."""
 import sys, collections, re
 agg=collections.OrderedDict(); cur=None
-NC=66
+NC=66; S_OFF=60; I_OFF=59          # defaults of the first export this was written for; replaced by each table's header
 for line in open(sys.argv[1]):
     line=line.rstrip('\n')
     if line.startswith('"File Path"'):
         cur=line.split('","')[1].strip('"').split('/')[-1]; continue
     if not line.startswith('"') : continue
     parts=line.split('","')
+    if parts[0].strip('"') == 'Line No':          # header of a function's table: column positions, counted from the right
+        hdr=[h.strip('"') for h in parts]
+        NC=len(hdr); S_OFF=NC-hdr.index('# Samples'); I_OFF=NC-hdr.index('Instructions Executed')
+        continue
     if len(parts)<NC: continue
     first=parts[0].strip('"')
     if not first.isdigit(): continue
     try:
-        samples=int(parts[-60]); inst=int(parts[-59])
+        samples=int(parts[-S_OFF]); inst=int(parts[-I_OFF])
     except: continue
     src='","'.join(parts[1:len(parts)-NC+2])[:110]
     key=(cur,int(first))
