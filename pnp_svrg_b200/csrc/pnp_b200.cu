@@ -59,11 +59,14 @@ int check_init() {
 }
 
 // ---- per-size launch geometry ------------------------------------------------------------
+#ifndef PNP_GP256
+#define PNP_GP256 4                                    // line pairs per CTA at L = 256 (16 threads per transform)
+#endif
 template <int L> constexpr int lines_gp() {            // line pairs per CTA in passes 1 and 3
 #ifdef PNP_LINES_GP1
     return pnp::fft_threads<L>() >= 128 ? 1 : 4;
 #else
-    return pnp::fft_threads<L>() >= 256 ? 1 : (pnp::fft_threads<L>() >= 128 ? 2 : 4);
+    return pnp::fft_threads<L>() >= 256 ? 1 : (pnp::fft_threads<L>() >= 128 ? 2 : (pnp::fft_threads<L>() == 16 ? PNP_GP256 : 4));
 #endif
 }
 template <int L> constexpr int cols_nc() {             // packed columns per CTA in pass 2
