@@ -154,6 +154,15 @@ template <int L, int GP> __host__ __device__ constexpr int group_stride() {
 // floats of exchange planes in front of the TMA staging buffers (kept 128-byte aligned)
 template <int L, int GP> __host__ __device__ constexpr int lines_stage_off() { return (GP * group_stride<L, GP>() + 31) & ~31; }
 
+// floats between the staged line pairs of an item: with fewer than 32 threads per transform a warp holds several
+// transforms, and their pairs, 2 L floats apart, would sit in the same banks (ncu: every excess shared-memory wavefront
+// of the 256-point line passes was a read of the staged lines, 2-way).  T floats of padding put the pairs of a warp's
+// transforms side by side in the banks; one bulk copy per pair then instead of one per item.
+template <int L> __host__ __device__ constexpr int stage_pad() {
+    return fft_threads<L>() >= 32 ? 0 : (fft_threads<L>() < 4 ? 4 : fft_threads<L>());
+}
+template <int L> __host__ __device__ constexpr int stage_pair_stride() { return 2 * L + stage_pad<L>(); }
+
 // Persistent: CTA b processes items b, b + gridDim.x, ... (an item = GP line pairs).  The 2*GP input
 // lines of an item are contiguous in memory: ONE thread stages them into shared memory with TMA bulk
 // copies (cp.async.bulk + mbarrier); the copy of item i+1 is in flight while item i is transformed.
@@ -168,8 +177,9 @@ k_lines_r2c(const float* __restrict__ a, const float* __restrict__ b, float2* __
     constexpr int GS = group_stride<L, GP>();
     extern __shared__ __align__(128) float smem[];
     __shared__ __align__(8) unsigned long long bar;
+    constexpr int PSTR = stage_pair_stride<L>();
     float* stage_a = smem + lines_stage_off<L, GP>();
-    float* stage_b = stage_a + 2 * GP * L;
+    float* stage_b = stage_a + GP * PSTR;
     const int g = threadIdx.x / T, t = threadIdx.x % T;
     const int gbar = fft_group_bar<T>(g, GP);        // the barriers inside a transform involve its T threads only
     const int npairs = nlines >> 1;
@@ -183,8 +193,16 @@ k_lines_r2c(const float* __restrict__ a, const float* __restrict__ b, float2* __
         np = np < GP ? np : GP;
         const unsigned bytes = (unsigned)(np * 2 * L * sizeof(float));
         mbar_expect_tx(&bar, b ? 2 * bytes : bytes);
-        bulk_g2s_keep(stage_a, a + ibase + (long long)(2 * item * GP) * L, bytes, &bar);     // the iterate: read again by the tail
-        if (b) bulk_g2s(stage_b, b + ibase + (long long)(2 * item * GP) * L, bytes, &bar);
+        const long long off = ibase + (long long)(2 * item * GP) * L;
+        if (stage_pad<L>() == 0) {
+            bulk_g2s_keep(stage_a, a + off, bytes, &bar);     // the iterate: read again by the tail
+            if (b) bulk_g2s(stage_b, b + off, bytes, &bar);
+        } else {
+            for (int p = 0; p < np; ++p) {                    // padded pairs: one copy each
+                bulk_g2s_keep(stage_a + p * PSTR, a + off + (long long)p * 2 * L, (unsigned)(2 * L * sizeof(float)), &bar);
+                if (b) bulk_g2s(stage_b + p * PSTR, b + off + (long long)p * 2 * L, (unsigned)(2 * L * sizeof(float)), &bar);
+            }
+        }
     };
 
     trace(100, true);
@@ -209,8 +227,8 @@ k_lines_r2c(const float* __restrict__ a, const float* __restrict__ b, float2* __
         trace(101);
         parity ^= 1;
         if (item * GP + g < npairs) {
-            const float* la = stage_a + 2 * g * L;
-            const float* lb = stage_b + 2 * g * L;
+            const float* la = stage_a + g * PSTR;
+            const float* lb = stage_b + g * PSTR;
 #pragma unroll
             for (int i = 0; i < EPT; ++i) {
                 const int idx = FftIdx<L>::in(t, i);
@@ -446,8 +464,9 @@ k_lines_c2r(const float2* __restrict__ S, int nlines, long long img_stride, floa
     using IX = FftIdx<L>;
     extern __shared__ __align__(128) float smem[];
     __shared__ __align__(8) unsigned long long bar;
+    constexpr int PSTR = stage_pair_stride<L>();
     float* stage_v = smem + lines_stage_off<L, GP>();      // vadd lines of the item
-    float* stage_z = stage_v + 2 * GP * L;                  // z_in lines of the item
+    float* stage_z = stage_v + GP * PSTR;                   // z_in lines of the item
     const int g = threadIdx.x / T, t = threadIdx.x % T;
     const int gbar = fft_group_bar<T>(g, GP);        // the barriers inside a transform involve its T threads only
     const int img = blockIdx.y;
@@ -481,8 +500,15 @@ k_lines_c2r(const float2* __restrict__ S, int nlines, long long img_stride, floa
         const unsigned bytes = (unsigned)(np * 2 * L * sizeof(float));
         const long long off = ibase + (long long)(2 * item * GP) * L;
         mbar_expect_tx(&bar, ((UPD || p_vadd) ? bytes : 0u) + ((UPD || p_zout) ? bytes : 0u));
-        if (UPD || p_vadd) bulk_g2s(stage_v, p_vadd + off, bytes, &bar);
-        if (UPD || p_zout) bulk_g2s(stage_z, p_zin + off, bytes, &bar);
+        if (stage_pad<L>() == 0) {
+            if (UPD || p_vadd) bulk_g2s(stage_v, p_vadd + off, bytes, &bar);
+            if (UPD || p_zout) bulk_g2s(stage_z, p_zin + off, bytes, &bar);
+        } else {
+            for (int p = 0; p < np; ++p) {                    // padded pairs: one copy each
+                if (UPD || p_vadd) bulk_g2s(stage_v + p * PSTR, p_vadd + off + (long long)p * 2 * L, (unsigned)(2 * L * sizeof(float)), &bar);
+                if (UPD || p_zout) bulk_g2s(stage_z + p * PSTR, p_zin + off + (long long)p * 2 * L, (unsigned)(2 * L * sizeof(float)), &bar);
+            }
+        }
     };
     if (threadIdx.x == 0) { mbar_init(&bar, 1); mbar_fence_init(); }
     __syncthreads();
@@ -532,8 +558,8 @@ k_lines_c2r(const float2* __restrict__ S, int nlines, long long img_stride, floa
         const int pair = item * GP + g;
         if (pair < npairs) {
             const long long base = ibase + (long long)(2 * pair) * L;
-            const float* sv = stage_v + 2 * g * L;
-            const float* sz = stage_z + 2 * g * L;
+            const float* sv = stage_v + g * PSTR;
+            const float* sz = stage_z + g * PSTR;
 #pragma unroll
             for (int i = 0; i < EPT; ++i) {
                 const int idx = IX::out(t, i);

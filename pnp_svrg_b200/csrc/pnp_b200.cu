@@ -74,7 +74,7 @@ template <int L> constexpr int cols_nc() {             // packed columns per CTA
 }
 // exchange planes + two staging buffers of 2*GP lines each (TMA bulk copy targets)
 template <int L> constexpr size_t lines_smem() {
-    return sizeof(float) * (pnp::lines_stage_off<L, lines_gp<L>()>() + 4 * lines_gp<L>() * L);
+    return sizeof(float) * (pnp::lines_stage_off<L, lines_gp<L>()>() + 2 * lines_gp<L>() * pnp::stage_pair_stride<L>());
 }
 // exchange planes + one staging buffer of NC columns (complex)
 template <int L> constexpr size_t cols_smem() {
