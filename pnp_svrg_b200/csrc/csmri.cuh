@@ -158,6 +158,13 @@ template <int L, int GP> __host__ __device__ constexpr int lines_stage_off() { r
 // transforms, and their pairs, 2 L floats apart, would sit in the same banks (ncu: every excess shared-memory wavefront
 // of the 256-point line passes was a read of the staged lines, 2-way).  T floats of padding put the pairs of a warp's
 // transforms side by side in the banks; one bulk copy per pair then instead of one per item.
+// resident CTAs per SM the passes are compiled for: 16 warps per SM whatever the CTA size (2 x 256, 4 x 128, 8 x 64 threads).
+// CTAs of 64 threads (L = 256: 4 transforms of 16 threads) used to be compiled for 4 per SM: the inverse line pass took 198
+// registers and ran with 6.5 warps per SM in the batched sweeps (ncu, profiles/README.md).
+#ifndef PNP_SMALL_CTA_MINB
+#define PNP_SMALL_CTA_MINB 8
+#endif
+__host__ __device__ constexpr int pass_min_ctas(int threads) { return threads >= 256 ? 2 : (threads >= 128 ? 4 : PNP_SMALL_CTA_MINB); }
 template <int L> __host__ __device__ constexpr int stage_pad() {
     return fft_threads<L>() >= 32 ? 0 : (fft_threads<L>() < 4 ? 4 : fft_threads<L>());
 }
@@ -168,7 +175,7 @@ template <int L> __host__ __device__ constexpr int stage_pair_stride() { return 
 // copies (cp.async.bulk + mbarrier); the copy of item i+1 is in flight while item i is transformed.
 // smem: [GP groups x exchange planes][stage a: 2*GP*L floats][stage b: 2*GP*L floats]
 template <int L, int GP>
-__global__ void __launch_bounds__(GP * (L / FftPlan<L>::EPT), (GP * (L / FftPlan<L>::EPT) >= 256 ? 2 : 4))
+__global__ void __launch_bounds__(GP * (L / FftPlan<L>::EPT), pass_min_ctas(GP * (L / FftPlan<L>::EPT)))
 k_lines_r2c(const float* __restrict__ a, const float* __restrict__ b, float2* __restrict__ S,
             int nlines, long long img_stride, SelJob sj, int row_lo, int row_hi) {
     constexpr int T = fft_threads<L>();
@@ -300,7 +307,7 @@ template <int L, int NC> __host__ __device__ constexpr int cols_stage_off() { re
 #define PNP_COLS_MINB 4
 #endif
 template <int L, int NC>
-__global__ void __launch_bounds__(NC * (L / FftPlan<L>::EPT), (NC * (L / FftPlan<L>::EPT) >= 256 ? 2 : PNP_COLS_MINB))
+__global__ void __launch_bounds__(NC * (L / FftPlan<L>::EPT), (NC * (L / FftPlan<L>::EPT) >= 128 ? (NC * (L / FftPlan<L>::EPT) >= 256 ? 2 : PNP_COLS_MINB) : pass_min_ctas(NC * (L / FftPlan<L>::EPT))))
 k_cols_mask(float2* __restrict__ S, const unsigned char* __restrict__ bits,
             const float2* __restrict__ Y1, const float2* __restrict__ Y2,
             const float2* __restrict__ Y1n, const float2* __restrict__ Y2n,
@@ -454,7 +461,7 @@ k_cols_mask(float2* __restrict__ S, const unsigned char* __restrict__ bits,
 // UPD = true is the inner-iteration form (vadd, z_in and z_out given, nothing else written): the generic
 // epilogue with its five optional pointers unrolls to >100 KiB of code and stalls on instruction fetch.
 template <int L, int GP, bool UPD>
-__global__ void __launch_bounds__(GP * (L / FftPlan<L>::EPT), (GP * (L / FftPlan<L>::EPT) >= 256 ? 2 : 4))
+__global__ void __launch_bounds__(GP * (L / FftPlan<L>::EPT), pass_min_ctas(GP * (L / FftPlan<L>::EPT)))
 k_lines_c2r(const float2* __restrict__ S, int nlines, long long img_stride, float inv_n, GradEpilogue ep, int row_lo, int row_hi) {
     constexpr int T = fft_threads<L>();
     constexpr int EPT = FftPlan<L>::EPT;
