@@ -68,10 +68,12 @@ def small(rank, world, dev, steps=200):
     # the public call pays ~20 ms of fixed cost (engine, pinned ring, upload, download): run long enough that it is
     # amortised as in a real reconstruction (the reference runs for tt = 10 .. 100 s); 10 x the device-timed epochs
     e2e_steps = 10 * steps
-    t0 = time.time()
-    out = pnp_svrg(prob, TVDenoiser(), tt=1e9, max_iters=e2e_steps * T2, **kw)
-    torch.cuda.synchronize(dev)
-    dt = time.time() - t0
+    dt = None
+    for _ in range(3):                  # best of three complete public calls (as bench.run_e2e: one call is ~0.25 s of host-driven work)
+        t0 = time.time()
+        out = pnp_svrg(prob, TVDenoiser(), tt=1e9, max_iters=e2e_steps * T2, **kw)
+        torch.cuda.synchronize(dev)
+        dt = time.time() - t0 if dt is None else min(dt, time.time() - t0)
     N = cfg['H'] * cfg['W']
     us = 1e3 * ms / (steps * T2)
     return {'workload': cfg['workload'], 'value': steps * T2 / (ms * 1e-3), 'unit': 'inner_iterations/s', 'us_per_inner_iteration': us,
